@@ -1,0 +1,169 @@
+/*
+ * tchem_b200.h - C ABI of the B200-native internal-coordinate hot path.
+ *
+ * This is the only boundary between host code (the tchem:: C++ classes in include/tchem/,
+ * the Python binding in torch_chemistry_b200/) and the CUDA kernels. Plain pointers and
+ * sizes, no C++ or torch types. Every entry point names the reference interface it replaces
+ * (paths relative to the Torch-Chemistry tree).
+ *
+ * Conventions
+ *  - All floating-point data is IEEE float64. "Device" pointers are device memory on the
+ *    table's device; "host" entry points (suffix _host) take host pointers and perform the
+ *    host<->device copies themselves (pinned staging, chunked and overlapped with compute).
+ *  - Batched superset of the reference: the reference takes ONE geometry r[cartdim] per call
+ *    (source/IC/IntCoordSet.cpp:140-141); here every tensor has a leading batch axis of
+ *    length B and is C-contiguous: r[B][cartdim], q[B][intdim], J[B][intdim][cartdim],
+ *    K[B][intdim][cartdim][cartdim], g_q[B][intdim], H_q[B][intdim][intdim], ...
+ *  - Every function returns 0 on success or a TCHEM_E* code; tchem_last_error() returns a
+ *    thread-local message. Kernels are launched on the caller's stream and are not
+ *    synchronised. There is no CPU fallback: without a CUDA device every compute call fails
+ *    with TCHEM_ECUDA.
+ */
+#ifndef TCHEM_B200_H
+#define TCHEM_B200_H
+
+#include <stdint.h>
+
+#define TCHEM_API __attribute__((visibility("default")))
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCHEM_OK        0
+#define TCHEM_EINVAL    1   /* -> std::invalid_argument in the C++ classes */
+#define TCHEM_EDOMAIN   2   /* -> std::domain_error (unimplemented type)     */
+#define TCHEM_EFILE     3   /* -> CL::utility::file_error                    */
+#define TCHEM_ECUDA     4   /* -> std::runtime_error                         */
+#define TCHEM_ENOMEM    5
+
+/* tchem::IC::InvDisp_type, include/tchem/IC/InvDisp.hpp:9-44 (same order, same values) */
+enum tchem_invdisp_type {
+    TCHEM_DUMMY = 0, TCHEM_STRETCHING, TCHEM_BENDING, TCHEM_COSBENDING,
+    TCHEM_TORSION, TCHEM_SINTORSION, TCHEM_COSTORSION,
+    TCHEM_TORSION2, TCHEM_SINTORSION2, TCHEM_COSTORSION2, TCHEM_PXTORSION2, TCHEM_PYTORSION2,
+    TCHEM_OUTOFPLANE, TCHEM_SINOOP, TCHEM_NTYPES
+};
+
+/* One (coefficient, InvDisp) pair of one IntCoord:
+ * include/tchem/IC/InvDisp.hpp:54-63 + include/tchem/IC/IntCoord.hpp:11-12, flattened. */
+typedef struct tchem_invdisp {
+    int32_t ic;        /* index of the internal coordinate (row of q / J / K)       */
+    int32_t type;      /* enum tchem_invdisp_type                                    */
+    int32_t natoms;    /* 0, 2, 3, 4 or 5                                            */
+    int32_t atoms[5];  /* 0-based atom indices, unused entries ignored               */
+    double  coeff;     /* linear-combination coefficient, already normalised         */
+    double  min;       /* torsion / torsion2 range start, default -pi                */
+} tchem_invdisp_t;
+
+typedef struct tchem_ic_table  tchem_ic_table;   /* opaque: compiled IntCoordSet      */
+typedef struct tchem_sap_table tchem_sap_table;  /* opaque: compiled SAPSet           */
+typedef void * tchem_stream_t;                   /* cudaStream_t                      */
+
+TCHEM_API const char * tchem_last_error(void);
+/* number of CUDA devices visible (0 when there is no driver / device) */
+TCHEM_API int tchem_device_count(void);
+
+/* ---- definition files -------------------------------------------------------------- */
+/* IntCoordSet::IntCoordSet(format, file), source/IC/IntCoordSet.cpp:11-120 (both formats,
+ * including IntCoord::normalize, source/IC/IntCoord.cpp:26-31). Pure host code.
+ * Writes up to `capacity` terms to `terms`, always stores the required count in *n_terms
+ * and the number of internal coordinates in *n_ic. */
+TCHEM_API int tchem_ic_parse_file(const char * format, const char * file,
+                        tchem_invdisp_t * terms, int capacity, int * n_terms, int * n_ic);
+TCHEM_API int tchem_ic_parse_text(const char * format, const char * text,
+                        tchem_invdisp_t * terms, int capacity, int * n_terms, int * n_ic);
+
+/* SAPSet::SAPSet(sapoly_file, irreducible, dimensions), source/polynomial/SAPSet.cpp:89-109 and
+ * SAP::SAP(strs), source/polynomial/SAP.cpp:42-76. Flattened as CSR: monomial i owns
+ * coords[term_ptr[i] .. term_ptr[i+1]) as (irreducible, index) pairs, 0-based, sorted
+ * descending like SAP::coords_. term_ptr needs capacity_terms + 1 entries. */
+TCHEM_API int tchem_sap_parse_file(const char * file, int32_t * term_ptr, int capacity_terms,
+                         int32_t * coords /* [capacity_coords][2] */, int capacity_coords,
+                         int * n_terms, int * n_coords);
+TCHEM_API int tchem_sap_parse_text(const char * text, int32_t * term_ptr, int capacity_terms,
+                         int32_t * coords, int capacity_coords, int * n_terms, int * n_coords);
+
+/* ---- compiled tables ---------------------------------------------------------------- */
+/* Flattens an IntCoordSet (std::vector<IntCoord>, include/tchem/IC/IntCoordSet.hpp:11-12)
+ * into the device-resident program the kernels interpret. n_atoms fixes cartdim = 3*n_atoms;
+ * pass 0 to take 1 + the largest atom index used. */
+TCHEM_API int tchem_ic_table_create(const tchem_invdisp_t * terms, int n_terms, int n_ic, int n_atoms,
+                          int device, tchem_ic_table ** out);
+TCHEM_API void tchem_ic_table_destroy(tchem_ic_table * t);
+TCHEM_API int tchem_ic_table_intdim(const tchem_ic_table * t);
+TCHEM_API int tchem_ic_table_cartdim(const tchem_ic_table * t);
+TCHEM_API int tchem_ic_table_device(const tchem_ic_table * t);
+
+/* SAPSet (include/tchem/polynomial/SAPSet.hpp:9-31): irreducible of the set, dimensions per
+ * irreducible, monomials in CSR form as produced by tchem_sap_parse_*. */
+TCHEM_API int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int n_terms,
+                           int irreducible, const int32_t * dims, int n_irreducibles,
+                           int device, tchem_sap_table ** out);
+TCHEM_API void tchem_sap_table_destroy(tchem_sap_table * t);
+TCHEM_API int tchem_sap_table_nterms(const tchem_sap_table * t);
+TCHEM_API int tchem_sap_table_sumdim(const tchem_sap_table * t);
+
+/* ---- q / J / K ------------------------------------------------------------------------ */
+/* Replaces, over a batch:
+ *   value_path != 0 (J == K == NULL): IntCoordSet::operator(),   source/IC/IntCoordSet.cpp:139-145
+ *                                     (the clamped formulas of InvDisp::operator(), InvDisp.cpp:64-254)
+ *   K == NULL:                         IntCoordSet::compute_IC_J,  source/IC/IntCoordSet.cpp:147-159
+ *   K != NULL:                         IntCoordSet::compute_IC_J_K, source/IC/IntCoordSet.cpp:161-175
+ * q may be NULL when only J (and K) are wanted. */
+TCHEM_API int tchem_ic_eval(const tchem_ic_table * t, const double * r, int64_t B,
+                  double * q, double * J, double * K, int value_path, tchem_stream_t stream);
+/* same with host buffers; copies and kernels are pipelined in chunks on internal streams and
+ * the call returns after the results have landed in the host buffers. */
+TCHEM_API int tchem_ic_eval_host(const tchem_ic_table * t, const double * r, int64_t B,
+                       double * q, double * J, double * K, int value_path);
+
+/* ---- gradient transforms -------------------------------------------------------------- */
+/* IntCoordSet::gradient_int2cart, source/IC/IntCoordSet.cpp:207-218:  g_r = J^T g_q */
+TCHEM_API int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const double * intgrad,
+                           int64_t B, double * cartgrad, tchem_stream_t stream);
+/* IntCoordSet::gradient_cart2int, :190-205:  g_q = (J J^T)^-1 J g_r (Cholesky + explicit inverse) */
+TCHEM_API int tchem_ic_grad_cart2int(const tchem_ic_table * t, const double * r, const double * cartgrad,
+                           int64_t B, double * intgrad, tchem_stream_t stream);
+/* IntCoordSet::gradient_cart2int_matrix, :178-188:  M[B][intdim][cartdim] = (J J^T)^-1 J */
+TCHEM_API int tchem_ic_grad_cart2int_matrix(const tchem_ic_table * t, const double * r, int64_t B,
+                                  double * M, tchem_stream_t stream);
+
+/* ---- Hessian transforms --------------------------------------------------------------- */
+/* IntCoordSet::Hessian_int2cart, :248-266:  H_r = J^T H_q J + sum_k g_q[k] K[k] */
+TCHEM_API int tchem_ic_hess_int2cart(const tchem_ic_table * t, const double * r, const double * intgrad,
+                           const double * intHess, int64_t B, double * cartHess,
+                           tchem_stream_t stream);
+/* IntCoordSet::Hessian_cart2int, :221-246:
+ *   A^T = (J J^T)^-1 J,  H_q = A^T H_r A - sum_k (A^T g_r)[k] A^T K[k] A */
+TCHEM_API int tchem_ic_hess_cart2int(const tchem_ic_table * t, const double * r, const double * cartgrad,
+                           const double * cartHess, int64_t B, double * intHess,
+                           tchem_stream_t stream);
+
+/* ---- SAPSet ---------------------------------------------------------------------------- */
+/* x[B][sumdim] holds the per-irreducible vectors xs[0], xs[1], ... concatenated.
+ * y[B][nterms]          = SAPSet::operator()(xs),      source/polynomial/SAPSet.cpp:134-144
+ * J[B][nterms][sumdim]  = SAPSet::Jacobian_(xs, J),    source/polynomial/SAPSet.cpp:178-201
+ * Either output may be NULL. */
+TCHEM_API int tchem_sap_eval(const tchem_sap_table * t, const double * x, int64_t B,
+                   double * y, double * J, tchem_stream_t stream);
+/* chained path: r -> q (compute_IC_J formulas) -> xs = q split by `dims` -> SAPSet value and
+ * Jacobian, one kernel, q never leaves the chip unless q_out != NULL. Requires
+ * intdim == sumdim. Callers of the reference do this by hand (test/normal_mode/main.cpp:56-61). */
+TCHEM_API int tchem_ic_sap_eval(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r,
+                      int64_t B, double * q_out, double * y, double * J, tchem_stream_t stream);
+TCHEM_API int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r,
+                           int64_t B, double * q_out, double * y, double * J);
+
+/* ---- measurement helpers (bench.py only) ------------------------------------------------ */
+/* number of kernels this library has launched in this process so far */
+TCHEM_API int64_t tchem_launch_count(void);
+/* average device time in ms (CUDA events on `stream`) of `iters` launches of tchem_ic_eval */
+TCHEM_API int tchem_ic_eval_timed(const tchem_ic_table * t, const double * r, int64_t B, double * q,
+                        double * J, double * K, int value_path, int iters,
+                        tchem_stream_t stream, float * ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCHEM_B200_H */

@@ -1,0 +1,87 @@
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EPS = 2.220446049250313e-16
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def parity_ratio(x, ref, tol=1e-12):
+    """max over elements of |x - ref| / max(tol, tol * |ref|)   (north_star tolerance)"""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    if x.size == 0:
+        return 0.0
+    d = np.abs(x - ref)
+    bound = np.maximum(tol, tol * np.abs(ref))
+    bad = ~np.isfinite(x)
+    if bad.any():
+        return float("inf")
+    return float((d / bound).max())
+
+
+def assert_parity(x, ref, what, tol=1e-12):
+    ratio = parity_ratio(x, ref, tol)
+    assert ratio <= 1.0, "%s: worst |x-ref| / max(%g, %g|ref|) = %.3g" % (what, tol, tol, ratio)
+
+
+def assert_q_parity(q, q_ref, terms, r, what, tol=1e-12):
+    """q parity with the two allowances SURVEY.md section 8d spells out for dihedral angles:
+    compared modulo 2 pi (per term coefficient), and - because the reference takes the angle from
+    acos(cos phi), whose conditioning is 1/|sin phi| - with the bound widened to 8 eps / |sin phi|
+    for the rows that contain a torsion / torsion2 term."""
+    from oracle import tchem_oracle as O
+    q = np.asarray(q, dtype=np.float64).copy()
+    q_ref = np.asarray(q_ref, dtype=np.float64)
+    r = np.asarray(r, dtype=np.float64)
+    if r.ndim == 1:
+        r = r[None]
+        q = q.reshape(1, -1)
+        q_ref = q_ref.reshape(1, -1)
+    bound = np.maximum(tol, tol * np.abs(q_ref))
+    for (ic, coeff, typ, atoms, mn) in terms:
+        if typ not in ("torsion", "torsion2"):
+            continue
+        sin_t = "sintorsion" if typ == "torsion" else "sintorsion2"
+        s = np.abs(O.invdisp_value(O.InvDisp(sin_t, atoms), r))
+        with np.errstate(divide="ignore"):
+            bound[:, ic] = bound[:, ic] + abs(coeff) * 8.0 * EPS / np.maximum(s, 1e-300)
+        period = 2.0 * math.pi * abs(coeff)
+        d = q[:, ic] - q_ref[:, ic]
+        q[:, ic] -= np.round(d / period) * period
+    d = np.abs(q - q_ref)
+    assert np.isfinite(q).all(), what + ": non-finite q"
+    worst = float((d / bound).max())
+    assert worst <= 1.0, "%s: worst |q-ref| / bound = %.3g" % (what, worst)
+
+
+def terms_from_golden(g):
+    from oracle import tchem_oracle as O
+    out = []
+    for k in range(len(g["term_ic"])):
+        n = int(g["term_natoms"][k])
+        out.append((int(g["term_ic"][k]), float(g["term_coeff"][k]), O.TYPES[int(g["term_type"][k])],
+                    [int(a) for a in g["term_atoms"][k][:n]], float(g["term_min"][k])))
+    return out
+
+
+@pytest.fixture(scope="session")
+def have_ref():
+    from oracle import ref_lib
+    return ref_lib.available()

@@ -1,0 +1,137 @@
+"""Generates the golden vectors in this directory FROM THE REFERENCE ITSELF.
+
+Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
+It drives oracle/_ref/libtchem_ref.so - the reference's own LibTorch CPU classes compiled from
+/root/reference by oracle/Makefile - on (a) the reference's own test fixtures
+(test/intcoord/input/*, test/normal_mode/input/*, test/SApolynomial/input/*) and (b) the
+BASELINE.json workloads C1..C5 (torch_chemistry_b200/workloads.py), and stores inputs,
+definition texts and outputs as compressed .npz files. Nothing here is read at run time on
+the GPU box except the .npz files.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_lib  # noqa: E402
+import importlib.util  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("workloads", os.path.join(ROOT, "torch_chemistry_b200", "workloads.py"))
+workloads = importlib.util.module_from_spec(spec)
+sys.modules["workloads"] = workloads
+spec.loader.exec_module(workloads)
+
+REF = "/root/reference/test"
+OUT = os.path.dirname(os.path.abspath(__file__))
+BOHR = 1.8897261339212517
+
+
+def read_xyz(path):
+    lines = open(path).read().split("\n")
+    n = int(lines[0])
+    return np.array([[float(x) for x in l.split()[1:4]] for l in lines[2:2 + n]]).ravel() * BOHR
+
+
+def read_columbus_geom(path):
+    return np.array([[float(x) for x in l.split()[2:5]] for l in open(path).read().split("\n") if l.strip()]).ravel()
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-40s %8.1f KiB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def ic_case(name, fmt, def_path, geoms, rng, n_pert=2, sigma=0.02, with_K=True, transforms=False):
+    text = open(def_path).read()
+    ref = ref_lib.RefIntCoordSet(fmt, def_path)
+    r = []
+    for g in geoms:
+        r.append(g)
+        for _ in range(n_pert):
+            r.append(g + sigma * rng.standard_normal(g.shape))
+    r = np.stack(r)
+    out = dict(format=np.array(fmt), definition=np.array(text), r=r, q_value=ref.q(r))
+    t = ref.terms()
+    out.update(term_ic=t["ic"], term_coeff=t["coeff"], term_type=t["type"], term_natoms=t["natoms"],
+               term_atoms=t["atoms"], term_min=t["min"])
+    if with_K:
+        q, J, K = ref.qJK(r)
+        out.update(q=q, J=J, K=K)
+    else:
+        q, J = ref.qJ(r)
+        out.update(q=q, J=J)
+    if transforms:
+        B, n, cd = r.shape[0], ref.intdim, r.shape[1]
+        gq = rng.standard_normal((B, n))
+        A = rng.standard_normal((B, n, n))
+        Hq = 0.5 * (A + A.transpose(0, 2, 1))
+        gr = ref.gradient_int2cart(r, gq)
+        Hr = ref.Hessian_int2cart(r, gq, Hq)
+        out.update(intgrad=gq, intHess=Hq, cartgrad=gr, cartHess=Hr,
+                   cart2int_matrix=ref.gradient_cart2int_matrix(r),
+                   intgrad_back=ref.gradient_cart2int(r, gr),
+                   intHess_back=ref.Hessian_cart2int(r, gr, Hr))
+    save(name, **out)
+
+
+def main():
+    rng = np.random.default_rng(20261019)
+    I = REF + "/intcoord/input/"
+    slow, minb1, b1rot = read_xyz(I + "slow-1.5.xyz"), read_xyz(I + "min-B1.xyz"), read_xyz(I + "B1rot-2.2.xyz")
+    geom = read_columbus_geom(I + "geom")
+    intgeom = np.array([float(x) for x in open(I + "intgeom").read().split()])
+    # reference fixtures (test/intcoord/main.cpp)
+    ic_case("ref_aniline_default", "default", I + "IntCoordDef", [slow, minb1, b1rot], rng, n_pert=1, transforms=True)
+    ic_case("ref_aniline_columbus7", "Columbus7", I + "intcfl", [geom, slow], rng, n_pert=0)
+    ic_case("ref_aniline_advanced", "whatever", I + "advanced_IntCoordDef", [slow, minb1, b1rot], rng, n_pert=1)
+    save("ref_aniline_intgeom", intgeom=intgeom, geom=geom)
+    # test/normal_mode fixture: 48 ICs with un-normalised coefficients
+    N = REF + "/normal_mode/input/"
+    ic_case("ref_normal_mode", "default", N + "IntCoordDef", [read_columbus_geom(N + "geom")], rng, n_pert=1, with_K=False)
+    # SAP known answers (test/SApolynomial/main.cpp:9-25)
+    S = REF + "/SApolynomial/input/"
+    x = np.concatenate([np.array([[2.0, 3.0, 5.0, 7.0]]), rng.standard_normal((7, 4))])
+    for f, irr in (("1.in", 0), ("2.in", 1)):
+        sap = ref_lib.RefSAPSet(S + f, irr, [2, 2])
+        save("ref_sap_" + f.replace(".in", ""), definition=np.array(open(S + f).read()), irreducible=np.array(irr),
+             dims=np.array([2, 2]), x=x, y=sap.value(x), J=sap.jacobian(x), J_pow=sap.jacobian(x, True))
+    # BASELINE workloads
+    for key, nK, nT in (("C1", 64, 16), ("C2", 48, 8), ("C3", 6, 0), ("C4", 0, 3), ("C5", 32, 0)):
+        w = workloads.get(key)
+        with tempfile.NamedTemporaryFile("w", suffix=".def", delete=False) as f:
+            f.write(w.ic_text)
+            path = f.name
+        ref = ref_lib.RefIntCoordSet("default", path)
+        nJ = 256 if key != "C4" else 32
+        r = w.geometries(nJ)
+        out = dict(definition=np.array(w.ic_text), base=w.base, r=r, q_value=ref.q(r))
+        out["q"], out["J"] = ref.qJ(r)
+        if nK:
+            _, _, out["K"] = ref.qJK(r[:nK])
+        if nT:
+            B, n = nT, ref.intdim
+            gq = rng.standard_normal((B, n))
+            A = rng.standard_normal((B, n, n))
+            Hq = 0.5 * (A + A.transpose(0, 2, 1))
+            gr = ref.gradient_int2cart(r[:B], gq)
+            Hr = ref.Hessian_int2cart(r[:B], gq, Hq)
+            out.update(intgrad=gq, intHess=Hq, cartgrad=gr, cartHess=Hr,
+                       cart2int_matrix=ref.gradient_cart2int_matrix(r[:B]),
+                       intgrad_back=ref.gradient_cart2int(r[:B], gr),
+                       intHess_back=ref.Hessian_cart2int(r[:B], gr, Hr))
+        if w.sap_text:
+            with tempfile.NamedTemporaryFile("w", suffix=".in", delete=False) as f:
+                f.write(w.sap_text)
+                spath = f.name
+            sap = ref_lib.RefSAPSet(spath, 0, w.sap_dims)
+            out.update(sap_definition=np.array(w.sap_text), sap_dims=np.array(w.sap_dims),
+                       sap_y=sap.value(out["q"]), sap_J=sap.jacobian(out["q"]))
+        save("workload_" + key, **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,226 @@
+"""-m gpu: the CUDA path, called through the C ABI (torch_chemistry_b200 binds it with ctypes),
+against (a) the golden vectors the reference produced, (b) the oracle on seeded inputs at sizes
+it finishes in seconds, and (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (north_star): |x - ref| <= max(1e-12, 1e-12 |ref|), dihedral angles modulo 2 pi and
+with the acos-conditioning allowance of conftest.assert_q_parity."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, assert_q_parity, golden, terms_from_golden
+from oracle import tchem_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def T():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    import torch_chemistry_b200 as T
+    assert T.device_count() >= 1
+    return T
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+IC_CASES = ["ref_aniline_default", "ref_aniline_columbus7", "ref_aniline_advanced", "ref_normal_mode"]
+
+
+@pytest.mark.parametrize("name", IC_CASES)
+def test_reference_fixtures_q_J_K(T, name):
+    g = golden(name)
+    s = T.IntCoordSet.from_text(str(g["format"]), str(g["definition"]), n_atoms=g["r"].shape[1] // 3)
+    terms, r = terms_from_golden(g), g["r"]
+    rd = dev(r)
+    assert_q_parity(host(s(rd)), g["q_value"], terms, r, name + " q (operator())")
+    q, J = s.compute_IC_J(rd)
+    assert_q_parity(host(q), g["q"], terms, r, name + " q (compute_IC_J)")
+    assert_parity(host(J), g["J"], name + " J")
+    if "K" in g:
+        q2, J2, K = s.compute_IC_J_K(rd)
+        assert_q_parity(host(q2), g["q"], terms, r, name + " q (compute_IC_J_K)")
+        assert_parity(host(J2), g["J"], name + " J (compute_IC_J_K)")
+        assert_parity(host(K), g["K"], name + " K")
+    # one geometry, reference call shape r[cartdim]
+    q1, J1 = s.compute_IC_J(rd[0])
+    assert q1.shape == (s.intdim,) and J1.shape == (s.intdim, s.cartdim)
+    np.testing.assert_array_equal(host(q1), host(q)[0])
+    np.testing.assert_array_equal(host(J1), host(J)[0])
+
+
+@pytest.mark.parametrize("key", ["C1", "C2", "C3", "C4", "C5"])
+def test_workload_goldens(T, key):
+    g = golden("workload_" + key)
+    w = T.workloads.get(key)
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    terms = O.IntCoordSet("default", w.ic_text).terms()
+    r = g["r"]
+    rd = dev(r)
+    assert_q_parity(host(s(rd)), g["q_value"], terms, r, key + " q (operator())")
+    q, J = s.compute_IC_J(rd)
+    assert_q_parity(host(q), g["q"], terms, r, key + " q")
+    assert_parity(host(J), g["J"], key + " J")
+    if "K" in g:
+        nK = g["K"].shape[0]
+        _, _, K = s.compute_IC_J_K(rd[:nK])
+        assert_parity(host(K), g["K"], key + " K")
+    if "cartgrad" in g:
+        B = g["cartgrad"].shape[0]
+        assert_parity(host(s.gradient_int2cart(rd[:B], dev(g["intgrad"]))), g["cartgrad"], key + " gradient_int2cart")
+
+
+@pytest.mark.parametrize("key,n", [("C1", 10 ** 4), ("C2", 4099), ("C3", 257)])
+def test_against_oracle_seeded(T, key, n):
+    """ragged batch sizes (not multiples of the 32-geometry tile) against the numpy oracle"""
+    w = T.workloads.get(key)
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    orc = O.IntCoordSet("default", w.ic_text)
+    r = w.geometries(n, seed=77)
+    rd = dev(r)
+    qo, Jo = orc.qJ(r)
+    q, J = s.compute_IC_J(rd)
+    assert_q_parity(host(q), qo, orc.terms(), r, key + " q vs oracle")
+    assert_parity(host(J), Jo, key + " J vs oracle")
+    assert_q_parity(host(s(rd)), orc.q(r), orc.terms(), r, key + " value path vs oracle")
+    nk = min(n, 40)
+    _, _, K = s.compute_IC_J_K(rd[:nk])
+    assert_parity(host(K), orc.qJK(r[:nk])[2], key + " K vs oracle")
+
+
+def test_edge_batches(T):
+    w = T.workloads.get("C2")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    orc = O.IntCoordSet("default", w.ic_text)
+    empty = torch.empty((0, w.cartdim), dtype=torch.float64, device="cuda")
+    q, J = s.compute_IC_J(empty)
+    assert q.shape == (0, 12) and J.shape == (0, 12, 18)
+    for n in (1, 31, 32, 33, 65):
+        r = w.geometries(n, seed=n)
+        q, J = s.compute_IC_J(dev(r))
+        qo, Jo = orc.qJ(r)
+        assert_q_parity(host(q), qo, orc.terms(), r, "edge q n=%d" % n)
+        assert_parity(host(J), Jo, "edge J n=%d" % n)
+    with pytest.raises(ValueError):
+        s.compute_IC_J(torch.zeros(17, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        s.compute_IC_J(torch.zeros(18, dtype=torch.float32, device="cuda"))
+
+
+def test_host_buffers_match_device_path(T):
+    """the reference-facing call shape: CPU tensors in, CPU tensors out (copies inside the call)"""
+    w = T.workloads.get("C2")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    r = w.geometries(70001, seed=5)
+    rc = torch.from_numpy(r)
+    q, J = s.compute_IC_J(rc)
+    assert not q.is_cuda and not J.is_cuda
+    qd, Jd = s.compute_IC_J(rc.cuda())
+    np.testing.assert_array_equal(q.numpy(), host(qd))
+    np.testing.assert_array_equal(J.numpy(), host(Jd))
+    qv = s(rc)
+    np.testing.assert_array_equal(qv.numpy(), host(s(rc.cuda())))
+
+
+def test_full_size_properties_C2(T):
+    """10^6 geometries (BASELINE config 2): properties that need no oracle.
+    (1) a strided subsample equals the oracle; (2) translating every geometry leaves q and J
+    unchanged to rounding and the rows of J sum to zero over atoms (translational invariance);
+    (3) evaluating the batch in two halves gives bit-identical results (no cross-geometry state)."""
+    w = T.workloads.get("C2")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    orc = O.IntCoordSet("default", w.ic_text)
+    n = 10 ** 6
+    r = w.geometries(n)
+    rd = dev(r)
+    q, J = s.compute_IC_J(rd)
+    idx = np.arange(0, n, 997)
+    qo, Jo = orc.qJ(r[idx])
+    assert_q_parity(host(q[idx]), qo, orc.terms(), r[idx], "C2 full q subsample")
+    assert_parity(host(J[idx]), Jo, "C2 full J subsample")
+    # translational invariance: sum over atoms of each Cartesian component of every J row
+    sums = J.view(n, 12, 6, 3).sum(dim=2)
+    assert float(sums.abs().max()) < 1e-13
+    shift = torch.tensor([0.3, -1.1, 2.7], dtype=torch.float64, device="cuda").repeat(6)
+    q2, J2 = s.compute_IC_J(rd + shift)
+    assert float((J2 - J).abs().max()) < 1e-12
+    h = n // 2 + 13
+    qa, Ja = s.compute_IC_J(rd[:h])
+    qb, Jb = s.compute_IC_J(rd[h:])
+    assert torch.equal(torch.cat([qa, qb]), q) and torch.equal(torch.cat([Ja, Jb]), J)
+
+
+def test_K_properties_C3(T):
+    """K: symmetric in its last two axes, rows/columns sum to zero over atoms, matches central
+    differences of J (test/intcoord/main.cpp:34-53)."""
+    w = T.workloads.get("C3")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    n = 512
+    rd = dev(w.geometries(n, seed=9))
+    q, J, K = s.compute_IC_J_K(rd)
+    assert float((K - K.transpose(2, 3)).abs().max()) < 1e-13
+    assert float(K.view(n, 54, 60, 20, 3).sum(dim=3).abs().max()) < 1e-12
+    h = 1e-5
+    for i in (0, 7, 31, 59):
+        rp, rm = rd.clone(), rd.clone()
+        rp[:, i] += h
+        rm[:, i] -= h
+        Jp, Jm = s.compute_IC_J(rp)[1], s.compute_IC_J(rm)[1]
+        assert float(((Jp - Jm) / (2 * h) - K[:, :, :, i]).abs().max()) < 1e-8
+
+
+def test_sap_known_answers_and_goldens(T):
+    for name, irr, answer in (("ref_sap_1", 0, [1, 2, 3, 4, 6, 9, 25, 35, 49]), ("ref_sap_2", 1, [5, 7, 10, 14, 15, 21])):
+        g = golden(name)
+        s = T.SAPSet.from_text(str(g["definition"]), irr, [2, 2])
+        xs = [torch.tensor([2.0, 3.0], dtype=torch.float64, device="cuda"), torch.tensor([5.0, 7.0], dtype=torch.float64, device="cuda")]
+        np.testing.assert_array_equal(host(s(xs)), np.array(answer, dtype=float))    # test/SApolynomial/main.cpp:9-25
+        x = dev(g["x"])
+        xb = [x[:, :2], x[:, 2:]]
+        assert_parity(host(s(xb)), g["y"], name + " value")
+        assert_parity(host(s.Jacobian_cat(xb)), g["J"], name + " Jacobian_")
+        Js = s.Jacobian_(xb)
+        assert Js[0].shape == (8, s.nterms, 2) and Js[1].shape == (8, s.nterms, 2)
+    with pytest.raises(ValueError):
+        s([x[:, :2]])
+    with pytest.raises(ValueError):
+        T.SAPSet.from_text("\n1,1\n", 1, [2])
+
+
+def test_chained_sap_C5(T):
+    g = golden("workload_C5")
+    w = T.workloads.get("C5")
+    ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    sap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims)
+    assert sap.nterms == 22
+    y, J, q = sap.chained(ic, dev(g["r"]), return_q=True)
+    assert_parity(host(q), g["q"], "C5 chained q")
+    assert_parity(host(y), g["sap_y"], "C5 chained SAP value")
+    assert_parity(host(J), g["sap_J"], "C5 chained SAP Jacobian")
+    # larger ragged batch against the oracle
+    n = 100003
+    r = w.geometries(n, seed=11)
+    orc, osap = O.IntCoordSet("default", w.ic_text), O.SAPSet(w.sap_text, 0, w.sap_dims)
+    qo = orc.qJ(r)[0]
+    y, J = sap.chained(ic, dev(r))
+    assert_parity(host(y), osap.value(qo), "C5 chained value vs oracle")
+    assert_parity(host(J), osap.jacobian(qo), "C5 chained Jacobian vs oracle")
+
+
+def test_gradient_int2cart_reference_fixture(T):
+    g = golden("ref_aniline_default")
+    s = T.IntCoordSet.from_text("default", str(g["definition"]), n_atoms=14)
+    out = s.gradient_int2cart(dev(g["r"]), dev(g["intgrad"]))
+    assert_parity(host(out), g["cartgrad"], "aniline gradient_int2cart")
+    # linearity in g_q
+    a = s.gradient_int2cart(dev(g["r"]), dev(2.5 * g["intgrad"]))
+    assert_parity(host(a), 2.5 * g["cartgrad"], "aniline gradient_int2cart linearity")

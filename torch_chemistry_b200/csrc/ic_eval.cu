@@ -1,0 +1,102 @@
+// q / J / K kernel: one warp = one tile of 32 geometries (see ic_program.h for the scheme).
+// Replaces, batched: IntCoordSet::operator() / compute_IC_J / compute_IC_J_K
+// (reference source/IC/IntCoordSet.cpp:139-175).
+#include "ic_eval.cuh"
+#include "ic_table.h"
+
+namespace tchem_b200 {
+
+namespace {
+
+// dynamic shared memory: [PrimDesc x nprims][ChunkDesc x nchunks][per warp: R | P]
+__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t B,
+               double * __restrict__ q, double * __restrict__ J, double * __restrict__ K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PrimDesc * prims = reinterpret_cast<PrimDesc *>(smem_raw);
+    ChunkDesc * chunks = reinterpret_cast<ChunkDesc *>(smem_raw + align16(sizeof(PrimDesc) * prog.nprims));
+    double * warp_base = reinterpret_cast<double *>(
+        smem_raw + align16(sizeof(PrimDesc) * prog.nprims) + align16(sizeof(ChunkDesc) * prog.nchunks));
+
+    // stage the definition tables once per block (coalesced 4-byte copies)
+    {
+        const int32_t * src = reinterpret_cast<const int32_t *>(prog.prims);
+        int32_t * dst = reinterpret_cast<int32_t *>(prims);
+        const int n = prog.nprims * (int)(sizeof(PrimDesc) / 4);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        const int32_t * src2 = reinterpret_cast<const int32_t *>(prog.chunks);
+        int32_t * dst2 = reinterpret_cast<int32_t *>(chunks);
+        const int n2 = prog.nchunks * (int)(sizeof(ChunkDesc) / 4);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = src2[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cartdim = prog.cartdim, intdim = prog.intdim;
+    double * R = warp_base + (size_t)warp * (cartdim + prog.cap) * kPad;
+    double * P = R + (size_t)cartdim * kPad;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes;
+    const int64_t jstride = (int64_t)intdim * cartdim, kstride = jstride * cartdim;
+
+    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+        const int64_t b0 = tile * kLanes;
+        const int ntile = (int)min((int64_t)kLanes, B - b0);
+        stage_coordinates(r, b0, ntile, cartdim, R, lane);
+        for (int c = 0; c < prog.nchunks; c++) {
+            const ChunkDesc ch = chunks[c];
+            for (int p = ch.prim_begin; p < ch.prim_end; p++) eval_primitive<MODE>(prims[p], R, lane, CompactSink(P, prims[p].out, lane));
+            __syncwarp();
+            if (q != nullptr)
+                gather_store(prog.map + ch.qmap, prog.srcs, ch.nrows, P, q + b0 * intdim + ch.row0, intdim,
+                             ntile, ch.accumulate != 0, lane);
+            if (MODE != MODE_VALUE && J != nullptr)
+                gather_store(prog.map + ch.jmap, prog.srcs, (int64_t)ch.nrows * cartdim, P,
+                             J + b0 * jstride + (int64_t)ch.row0 * cartdim, jstride, ntile, ch.accumulate != 0, lane);
+            if (MODE == MODE_QJK && K != nullptr)
+                gather_store(prog.map + ch.kmap, prog.srcs, (int64_t)ch.nrows * cartdim * cartdim, P,
+                             K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile,
+                             ch.accumulate != 0, lane);
+            __syncwarp();
+        }
+    }
+}
+
+template <int MODE> const void * kernel_ptr() { return reinterpret_cast<const void *>(&ic_eval_kernel<MODE>); }
+
+} // namespace
+
+size_t ic_eval_table_bytes(const Program & p) {
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    return a16(sizeof(PrimDesc) * p.nprims) + a16(sizeof(ChunkDesc) * p.nchunks);
+}
+size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap) * kPad * sizeof(double); }
+
+// picks warps/block and grid, launches on `stream`
+int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
+                   double * q, double * J, double * K, cudaStream_t stream) {
+    const Program & p = t->prog[mode];
+    const void * fn = mode == MODE_VALUE ? kernel_ptr<MODE_VALUE>() : mode == MODE_QJ ? kernel_ptr<MODE_QJ>() : kernel_ptr<MODE_QJK>();
+    const size_t tb = ic_eval_table_bytes(p), wb = ic_eval_warp_bytes(p);
+    int warps = mode == MODE_QJK ? 2 : 4;
+    while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps >>= 1;
+    const size_t smem = tb + warps * wb;
+    if (smem > (size_t)t->max_smem_optin)
+        return set_error(TCHEM_EINVAL, "tchem_ic_eval: molecule too large for the shared-memory tile (cartdim + row capacity)");
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes;
+    int64_t grid = (ntiles + warps - 1) / warps;
+    grid = std::min<int64_t>(grid, (int64_t)t->sm_count * per_sm);
+    if (grid < 1) return TCHEM_OK;
+    void * args[] = {(void *)&p, (void *)&r, (void *)&B, (void *)&q, (void *)&J, (void *)&K};
+    TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
+} // namespace tchem_b200

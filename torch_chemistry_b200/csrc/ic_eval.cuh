@@ -1,0 +1,318 @@
+// Device side of the q / J / K path: per-warp tile staging, the primitive interpreter and the
+// gather-store. Shared by the q/J/K kernel (ic_eval.cu), the gradient / Hessian transforms
+// (ic_transform.cu) and the chained SAP kernel (sap.cu).
+#pragma once
+#include "ic_math.cuh"
+#include "ic_program.h"
+#include "../../include/tchem_b200.h"
+
+namespace tchem_b200 {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------
+// stage the tile's Cartesian coordinates: global r[b0 .. b0+ntile)[cartdim] (contiguous,
+// coalesced reads) -> R[c * kPad + lane]. Lanes >= ntile get a copy of the last valid
+// geometry so that the arithmetic below never sees garbage.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_coordinates(const double * __restrict__ r, int64_t b0, int ntile,
+                                                  int cartdim, double * R, int lane) {
+    const double * src = r + b0 * cartdim;
+    const int total = ntile * cartdim;
+    // running (geometry, coordinate) of flat element f = lane + 32 j, no division in the loop
+    int g = lane / cartdim, c = lane - g * cartdim;
+    const int dg = kLanes / cartdim, dc = kLanes - dg * cartdim;
+    for (int f = lane; f < total; f += kLanes) {
+        R[c * kPad + g] = __ldg(src + f);
+        g += dg; c += dc;
+        if (c >= cartdim) { c -= cartdim; g++; }
+    }
+    __syncwarp();
+    if (ntile < kLanes && lane >= ntile)
+        for (int k = 0; k < cartdim; k++) R[k * kPad + lane] = R[k * kPad + ntile - 1];
+    __syncwarp();
+}
+
+__device__ __forceinline__ V3<double> load_atom(const double * R, int atom, int lane) {
+    const double * p = R + 3 * atom * kPad + lane;
+    return v3<double>(p[0], p[kPad], p[2 * kPad]);
+}
+
+template <class S> __device__ __forceinline__ S seed(double v, int coord, int d1, int d2);
+template <> __device__ __forceinline__ Dual seed<Dual>(double v, int coord, int d1, int) {
+    return mk(v, coord == d1 ? 1.0 : 0.0);
+}
+template <> __device__ __forceinline__ Dual2 seed<Dual2>(double v, int coord, int d1, int d2) {
+    return mk2(v, coord == d1 ? 1.0 : 0.0, coord == d2 ? 1.0 : 0.0, 0.0);
+}
+template <class S, int N>
+__device__ __forceinline__ void seed_atoms(const V3<double> * a, V3<S> * s, int d1, int d2) {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        s[i] = v3<S>(seed<S>(a[i].x, 3 * i, d1, d2), seed<S>(a[i].y, 3 * i + 1, d1, d2),
+                     seed<S>(a[i].z, 3 * i + 2, d1, d2));
+}
+
+// ---------------------------------------------------------------------------------------
+// Sinks: where a primitive's results go. CompactSink parks them in the per-warp compact
+// buffer P[entry * kPad + lane] (layout [q][J 3n][K block-upper], see ic_program.h).
+// ---------------------------------------------------------------------------------------
+struct CompactSink {
+    double * Pq;    // value slot, lane folded in
+    double * PJ;    // first J slot, lane folded in
+    __device__ __forceinline__ CompactSink(double * P, int out, int lane)
+        : Pq(P + out * kPad + lane), PJ(P + (out + 1) * kPad + lane) {}
+    __device__ __forceinline__ void value(double v) const { Pq[0] = v; }
+    template <int N> __device__ __forceinline__ void jac(const int *, const V3<double> * J) const {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            PJ[(3 * i + 0) * kPad] = J[i].x;
+            PJ[(3 * i + 1) * kPad] = J[i].y;
+            PJ[(3 * i + 2) * kPad] = J[i].z;
+        }
+    }
+    __device__ __forceinline__ void jac_entry(const int *, int m, double j) const { PJ[m * kPad] = j; }
+    // tangent direction (atom j, component l) of the J expression: blocks (i <= j), entry (k, l)
+    template <int N> __device__ __forceinline__ void hess_dir(const int *, int dir, const V3<Dual> * J) const {
+        const int j = dir / 3, l = dir - 3 * j;
+        double * PK = PJ + 3 * N * kPad;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i <= j) {
+                double * blk = PK + (9 * kblock(i, j, N) + l) * kPad;
+                blk[0 * 3 * kPad] = J[i].x.d;
+                blk[1 * 3 * kPad] = J[i].y.d;
+                blk[2 * 3 * kPad] = J[i].z.d;
+            }
+        }
+    }
+    // second derivative (m1 <= m2) of a 5-atom primitive
+    __device__ __forceinline__ void hess_entry5(const int *, int m1, int m2, double k) const {
+        const int i = m1 / 3, j = m2 / 3, kk = m1 - 3 * i, ll = m2 - 3 * j;
+        double * blk = PJ + 15 * kPad + 9 * kblock(i, j, 5) * kPad;
+        blk[(3 * kk + ll) * kPad] = k;
+        if (i == j) blk[(3 * ll + kk) * kPad] = k;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// One invariant displacement for this lane's geometry.
+//   MODE_VALUE : clamped value formulas of InvDisp::operator()
+//   MODE_QPATH : value by the compute_IC_J formulas, no derivatives
+//   MODE_QJ    : value + analytic J
+//   MODE_QJK   : + one Dual pass per Cartesian direction through the same J expression
+//                (what the reference asks autograd for, source/IC/InvDisp.cpp:859-868)
+// ---------------------------------------------------------------------------------------
+template <int MODE, class Sink>
+__device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double * R, int lane, const Sink & sink) {
+    constexpr bool WANT_J = MODE == MODE_QJ || MODE == MODE_QJK;
+    const int type = pd.type;
+    if (type == TCHEM_DUMMY) { sink.value(1.0); return; }
+
+    V3<double> a[kMaxAtoms];
+#pragma unroll
+    for (int i = 0; i < kMaxAtoms; i++)
+        if (i < pd.natoms) a[i] = load_atom(R, pd.atoms[i], lane);
+
+    if (MODE == MODE_VALUE) {
+        sink.value(value_path(type, a, pd.min));
+        return;
+    }
+
+    switch (type) {
+    case TCHEM_STRETCHING: {
+        double q; V3<double> J[2];
+        stretching_J<double>(a, q, J);
+        sink.value(q);
+        if (WANT_J) sink.template jac<2>(pd.atoms, J);
+        if (MODE == MODE_QJK) {
+            for (int dir = 0; dir < 6; dir++) {
+                V3<Dual> s[2], Jd[2]; Dual qd;
+                seed_atoms<Dual, 2>(a, s, dir, -1);
+                stretching_J<Dual>(s, qd, Jd);
+                sink.template hess_dir<2>(pd.atoms, dir, Jd);
+            }
+        }
+        break;
+    }
+    case TCHEM_BENDING: case TCHEM_COSBENDING: {
+        double c; V3<double> J[3];
+        if (type == TCHEM_BENDING) { bending_J<double, false>(a, c, J); sink.value(acos(c)); }
+        else                       { bending_J<double, true>(a, c, J);  sink.value(c); }
+        if (WANT_J) sink.template jac<3>(pd.atoms, J);
+        if (MODE == MODE_QJK) {
+            for (int dir = 0; dir < 9; dir++) {
+                V3<Dual> s[3], Jd[3]; Dual cd;
+                seed_atoms<Dual, 3>(a, s, dir, -1);
+                if (type == TCHEM_BENDING) bending_J<Dual, false>(s, cd, Jd);
+                else                       bending_J<Dual, true>(s, cd, Jd);
+                sink.template hess_dir<3>(pd.atoms, dir, Jd);
+            }
+        }
+        break;
+    }
+    case TCHEM_TORSION: case TCHEM_SINTORSION: case TCHEM_COSTORSION: {
+        double sp = 0.0, cp = 0.0, st = 0.0; V3<double> J[4];
+        if (type == TCHEM_TORSION) {
+            torsion_J<double, 0>(a, sp, cp, st, J);
+            sink.value(signed_wrapped_angle(cp, st, pd.min));
+        } else if (type == TCHEM_SINTORSION) { torsion_J<double, 1>(a, sp, cp, st, J); sink.value(sp); }
+        else                                 { torsion_J<double, 2>(a, sp, cp, st, J); sink.value(cp); }
+        if (WANT_J) sink.template jac<4>(pd.atoms, J);
+        if (MODE == MODE_QJK) {
+            for (int dir = 0; dir < 12; dir++) {
+                V3<Dual> s[4], Jd[4]; Dual spd, cpd, std_;
+                seed_atoms<Dual, 4>(a, s, dir, -1);
+                if (type == TCHEM_TORSION)         torsion_J<Dual, 0>(s, spd, cpd, std_, Jd);
+                else if (type == TCHEM_SINTORSION) torsion_J<Dual, 1>(s, spd, cpd, std_, Jd);
+                else                               torsion_J<Dual, 2>(s, spd, cpd, std_, Jd);
+                sink.template hess_dir<4>(pd.atoms, dir, Jd);
+            }
+        }
+        break;
+    }
+    case TCHEM_OUTOFPLANE: case TCHEM_SINOOP: {
+        double s_; V3<double> J[4];
+        if (type == TCHEM_OUTOFPLANE) { oop_J<double, false>(a, s_, J); sink.value(asin(s_)); }
+        else                          { oop_J<double, true>(a, s_, J);  sink.value(s_); }
+        if (WANT_J) sink.template jac<4>(pd.atoms, J);
+        if (MODE == MODE_QJK) {
+            for (int dir = 0; dir < 12; dir++) {
+                V3<Dual> s[4], Jd[4]; Dual sd;
+                seed_atoms<Dual, 4>(a, s, dir, -1);
+                if (type == TCHEM_OUTOFPLANE) oop_J<Dual, false>(s, sd, Jd);
+                else                          oop_J<Dual, true>(s, sd, Jd);
+                sink.template hess_dir<4>(pd.atoms, dir, Jd);
+            }
+        }
+        break;
+    }
+    default: {
+        // 5-atom torsion2 family: the reference differentiates the value expression with
+        // autograd (source/IC/InvDisp.cpp:415-570 first order, :893-1065 second order).
+        // px/py = sin(theta) * cos/sin(phi): the reference applies the product rule with an
+        // analytic J(sin theta) (:530-536, :1022); differentiating the product directly is
+        // the same function.
+        double sv, cv, tv;
+        torsion2_sincos<double>(a, sv, cv, tv);
+        const bool use_cos = fabs(sv) > fabs(cv);       // :432, :904
+        double sintheta = 0.0;
+        if (type == TCHEM_PXTORSION2 || type == TCHEM_PYTORSION2) {
+            V3<double> u12 = a[1] - a[0], u23 = a[2] - a[1];
+            u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+            double ct = -dot(u12, u23);
+            sintheta = sqrt(1.0 - ct * ct);
+        }
+        switch (type) {
+        case TCHEM_TORSION2:    sink.value(signed_wrapped_angle(cv, tv, pd.min)); break;
+        case TCHEM_SINTORSION2: sink.value(sv); break;
+        case TCHEM_COSTORSION2: sink.value(cv); break;
+        case TCHEM_PXTORSION2:  sink.value(sintheta * cv); break;
+        default:                sink.value(sintheta * sv); break;
+        }
+        if (MODE == MODE_QJ) {
+            for (int dir = 0; dir < 15; dir++) {
+                V3<Dual> s[5]; Dual sd, cd, td;
+                seed_atoms<Dual, 5>(a, s, dir, -1);
+                torsion2_sincos<Dual>(s, sd, cd, td);
+                double j;
+                if (type == TCHEM_TORSION2) j = use_cos ? cd.d / (-sv) : sd.d / cv;
+                else if (type == TCHEM_SINTORSION2) j = sd.d;
+                else if (type == TCHEM_COSTORSION2) j = cd.d;
+                else {
+                    V3<Dual> u12 = s[1] - s[0], u23 = s[2] - s[1];
+                    u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+                    Dual ct = -dot(u12, u23);
+                    Dual sth = sqrt_(1.0 - ct * ct);
+                    j = (sth * (type == TCHEM_PXTORSION2 ? cd : sd)).d;
+                }
+                sink.jac_entry(pd.atoms, dir, j);
+            }
+        } else if (MODE == MODE_QJK) {
+            for (int d2 = 0; d2 < 15; d2++) {
+                for (int d1 = 0; d1 <= d2; d1++) {
+                    V3<Dual2> s[5]; Dual2 sd, cd, td;
+                    seed_atoms<Dual2, 5>(a, s, d1, d2);
+                    torsion2_sincos<Dual2>(s, sd, cd, td);
+                    double j2, k;      // d/d(d2) and d2/d(d1)d(d2)
+                    if (type == TCHEM_TORSION2) {
+                        if (use_cos) {  // J = Jcos / -sin ; K = (Kcos + Jsin (x) J) / -sin   (:917-918)
+                            j2 = cd.b / (-sv);
+                            k = (cd.c + sd.a * j2) / (-sv);
+                        } else {        // J = Jsin / cos ; K = (Ksin - Jcos (x) J) / cos     (:935-936)
+                            j2 = sd.b / cv;
+                            k = (sd.c - cd.a * j2) / cv;
+                        }
+                    } else if (type == TCHEM_SINTORSION2) { j2 = sd.b; k = sd.c; }
+                    else if (type == TCHEM_COSTORSION2) { j2 = cd.b; k = cd.c; }
+                    else {
+                        V3<Dual2> u12 = s[1] - s[0], u23 = s[2] - s[1];
+                        u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+                        Dual2 ct = -dot(u12, u23);
+                        Dual2 sth = sqrt_(1.0 - ct * ct);
+                        Dual2 f = sth * (type == TCHEM_PXTORSION2 ? cd : sd);
+                        j2 = f.b; k = f.c;
+                    }
+                    if (d1 == d2) sink.jac_entry(pd.atoms, d2, j2);
+                    sink.hess_entry5(pd.atoms, d1, d2, k);
+                }
+            }
+        }
+        break;
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// gather-store: dense output span of S elements per geometry, element k of geometry g is
+//   sum_j coef_j * P[entry_j][g]     (no sources: structural zero)
+// lanes run along k (coalesced 256 B segments), the g loop walks the tile.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_store(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
+                                             int64_t S, const double * P, double * out, int64_t gstride,
+                                             int ntile, bool accumulate, int lane) {
+    for (int64_t k0 = 0; k0 < S; k0 += kLanes) {
+        const int64_t k = k0 + lane;
+        const bool valid = k < S;
+        uint32_t w = valid ? __ldg(map + k) : 0u;
+        const int cnt = (int)(w >> kMapCountShift);
+        const uint32_t off = w & kMapOffsetMask;
+        double * o = out + k;
+        const int maxcnt = __reduce_max_sync(kFull, cnt);
+        if (maxcnt == 0 && !accumulate) {
+            if (valid) {
+#pragma unroll 8
+                for (int g = 0; g < ntile; g++) o[g * gstride] = 0.0;
+            }
+        } else if (maxcnt <= 2) {
+            double c0 = 0.0, c1 = 0.0;
+            const double * p0 = P, * p1 = P;
+            if (cnt > 0) { Src s = srcs[off];     c0 = s.coef; p0 = P + s.entry * kPad; }
+            if (cnt > 1) { Src s = srcs[off + 1]; c1 = s.coef; p1 = P + s.entry * kPad; }
+            if (valid) {
+#pragma unroll 4
+                for (int g = 0; g < ntile; g++) {
+                    double v = 0.0;
+                    if (cnt > 0) v = c0 * p0[g];
+                    if (cnt > 1) v = fma(c1, p1[g], v);
+                    if (accumulate) v += o[g * gstride];
+                    o[g * gstride] = v;
+                }
+            }
+        } else {
+            if (valid) {
+                for (int g = 0; g < ntile; g++) {
+                    double v = 0.0;
+                    for (int j = 0; j < cnt; j++) {
+                        Src s = srcs[off + j];
+                        v = fma(s.coef, P[s.entry * kPad + g], v);
+                    }
+                    if (accumulate) v += o[g * gstride];
+                    o[g * gstride] = v;
+                }
+            }
+        }
+    }
+}
+
+} // namespace tchem_b200

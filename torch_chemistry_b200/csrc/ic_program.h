@@ -1,0 +1,72 @@
+// Device-resident "program" an IntCoordSet is compiled into (host side: ic_table.cpp,
+// device side: ic_eval.cu).
+//
+// Layout idea. A warp owns a tile of 32 geometries, one geometry per lane. The IC set is cut
+// into chunks of consecutive rows (internal coordinates). For a chunk, every DISTINCT
+// invariant displacement ("primitive") used by its rows is evaluated once per geometry in
+// registers and its sparse results (value, <=15 gradient entries, and in K mode the <=135
+// block-upper second-derivative entries) are parked in a per-warp compact shared-memory
+// buffer P[entry][lane]. The dense, API-mandated outputs q / J / K are then produced by a
+// gather: every output element owns a short list of (compact entry, coefficient) sources -
+// empty for the structural zeros - so that linear combinations, repeated atoms and the
+// zero fill all happen on the way out, in fully coalesced stores.
+#pragma once
+#include <stdint.h>
+
+namespace tchem_b200 {
+
+constexpr int kLanes = 32;
+constexpr int kPad = 33;          // P[entry * kPad + lane]: conflict-free for both phases
+constexpr int kMaxAtoms = 5;
+
+// MODE_VALUE/QJ/QJK are table modes (each has its own compiled program); MODE_QPATH is an
+// evaluation flavour only: values by the compute_IC_J formulas, no derivatives.
+enum Mode { MODE_VALUE = 0, MODE_QJ = 1, MODE_QJK = 2, MODE_COUNT = 3, MODE_QPATH = 4 };
+
+struct PrimDesc {                  // one distinct InvDisp of a chunk
+    int32_t type;
+    int32_t natoms;
+    int32_t atoms[kMaxAtoms];
+    int32_t out;                   // first compact entry: [q][J 3n][K block-upper 9 n(n+1)/2]
+    double  min;
+};
+
+struct Src {                       // one source of one output element
+    int32_t entry;                 // compact entry index
+    int32_t pad_;
+    double  coef;
+};
+
+struct ChunkDesc {
+    int32_t prim_begin, prim_end;  // range in prims[]
+    int32_t row0, nrows;           // rows (internal coordinates) this chunk produces
+    int32_t accumulate;            // != 0: add to what an earlier chunk stored (split row)
+    int32_t pad_;
+    int64_t qmap, jmap, kmap;      // offsets into map[]: nrows, nrows*cartdim, nrows*cartdim^2 words
+};
+
+// map word: (count << 24) | first source index
+constexpr uint32_t kMapCountShift = 24;
+constexpr uint32_t kMapOffsetMask = 0x00ffffffu;
+
+struct Program {                   // all pointers are device pointers
+    const PrimDesc *  prims;
+    const ChunkDesc * chunks;
+    const uint32_t *  map;
+    const Src *       srcs;
+    int32_t nprims, nchunks;
+    int32_t cap;                   // compact entries per lane
+    int32_t intdim, cartdim;
+};
+
+// compact entries of one primitive
+__host__ __device__ inline int prim_entries(int natoms, int mode) {
+    if (mode == MODE_VALUE) return 1;
+    int n = 1 + 3 * natoms;
+    if (mode == MODE_QJK) n += 9 * (natoms * (natoms + 1) / 2);
+    return n;
+}
+// index of 3x3 block (i <= j) in the block-upper K storage of an n-atom primitive
+__host__ __device__ inline int kblock(int i, int j, int n) { return i * n - (i * (i - 1)) / 2 + (j - i); }
+
+} // namespace tchem_b200

@@ -1,0 +1,213 @@
+// Host-side "compiler": std::vector<IntCoord> (flattened as tchem_invdisp_t terms) -> Program.
+// Reference structures being flattened: include/tchem/IC/IntCoordSet.hpp:11-12,
+// include/tchem/IC/IntCoord.hpp:11-12, include/tchem/IC/InvDisp.hpp:54-63.
+#include "ic_table.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace tchem_b200 {
+
+namespace {
+
+const int kTypeAtoms[TCHEM_NTYPES] = {0, 2, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 4, 4};
+
+struct PrimKey {
+    int type, natoms, atoms[kMaxAtoms];
+    double min;
+    bool operator<(const PrimKey & o) const {
+        return std::tie(type, natoms, atoms[0], atoms[1], atoms[2], atoms[3], atoms[4], min)
+             < std::tie(o.type, o.natoms, o.atoms[0], o.atoms[1], o.atoms[2], o.atoms[3], o.atoms[4], o.min);
+    }
+};
+
+PrimKey key_of(const tchem_invdisp_t & t) {
+    PrimKey k;
+    k.type = t.type; k.natoms = t.natoms;
+    for (int i = 0; i < kMaxAtoms; i++) k.atoms[i] = i < t.natoms ? t.atoms[i] : -1;
+    // `min` only matters for the two angle-valued dihedrals
+    k.min = (t.type == TCHEM_TORSION || t.type == TCHEM_TORSION2) ? t.min : 0.0;
+    return k;
+}
+
+} // namespace
+
+int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
+                  HostProgram & hp) {
+    hp = HostProgram();
+    // terms grouped by row, file order kept (source/IC/IntCoord.cpp:62-76 accumulates in order)
+    std::vector<std::vector<int>> rows(n_ic);
+    for (size_t t = 0; t < terms.size(); t++) {
+        const auto & d = terms[t];
+        if (d.ic < 0 || d.ic >= n_ic) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: term with ic index out of range");
+        if (d.type < 0 || d.type >= TCHEM_NTYPES) return set_error(TCHEM_EDOMAIN, "tchem_ic_table_create: unimplemented internal coordinate type");
+        if (d.natoms != kTypeAtoms[d.type]) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: wrong number of atoms for type");
+        for (int i = 0; i < d.natoms; i++)
+            if (d.atoms[i] < 0 || 3 * d.atoms[i] + 2 >= cartdim) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: atom index out of range");
+        rows[d.ic].push_back((int)t);
+    }
+    for (int i = 0; i < n_ic; i++)
+        if (rows[i].empty()) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: internal coordinate without terms");
+
+    // capacity policy: at least the largest primitive; otherwise the largest whole row up to a
+    // target that keeps the per-warp shared-memory footprint moderate
+    int max_prim = 1, max_row = 1;
+    for (int i = 0; i < n_ic; i++) {
+        std::map<PrimKey, int> seen;
+        int row_entries = 0;
+        for (int t : rows[i]) {
+            int e = prim_entries(terms[t].natoms, mode);
+            max_prim = std::max(max_prim, e);
+            if (seen.emplace(key_of(terms[t]), 0).second) row_entries += e;
+        }
+        max_row = std::max(max_row, row_entries);
+    }
+    const int target = mode == MODE_QJK ? 160 : 64;
+    hp.cap = std::max(max_prim, std::min(max_row, target));
+
+    // greedy chunking over rows; a row that does not fit by itself is split into several
+    // single-row chunks, the later ones accumulating
+    struct Pending { int row0, nrows; bool accumulate; std::vector<int> term_ids; };
+    std::vector<Pending> pend;
+    {
+        Pending cur{0, 0, false, {}};
+        std::map<PrimKey, int> cur_prims;
+        int cur_entries = 0;
+        auto flush = [&]() {
+            if (cur.nrows > 0) pend.push_back(cur);
+            cur = Pending{0, 0, false, {}};
+            cur_prims.clear();
+            cur_entries = 0;
+        };
+        for (int i = 0; i < n_ic; i++) {
+            // entries this row would add to the current chunk
+            std::map<PrimKey, int> add;
+            int add_entries = 0, alone_entries = 0;
+            {
+                std::map<PrimKey, int> alone;
+                for (int t : rows[i]) {
+                    PrimKey k = key_of(terms[t]);
+                    int e = prim_entries(terms[t].natoms, mode);
+                    if (alone.emplace(k, 0).second) alone_entries += e;
+                    if (!cur_prims.count(k) && add.emplace(k, 0).second) add_entries += e;
+                }
+            }
+            if (cur.nrows > 0 && cur_entries + add_entries <= hp.cap) {
+                for (auto & kv : add) cur_prims.insert(kv);
+                cur_entries += add_entries;
+                cur.nrows++;
+                for (int t : rows[i]) cur.term_ids.push_back(t);
+                continue;
+            }
+            flush();
+            if (alone_entries <= hp.cap) {
+                cur.row0 = i; cur.nrows = 1;
+                for (int t : rows[i]) { cur_prims.emplace(key_of(terms[t]), 0); cur.term_ids.push_back(t); }
+                cur_entries = alone_entries;
+                continue;
+            }
+            // split row
+            bool first = true;
+            Pending part{i, 1, false, {}};
+            std::map<PrimKey, int> part_prims;
+            int part_entries = 0;
+            for (int t : rows[i]) {
+                PrimKey k = key_of(terms[t]);
+                int e = part_prims.count(k) ? 0 : prim_entries(terms[t].natoms, mode);
+                if (part_entries + e > hp.cap) {
+                    part.accumulate = !first;
+                    pend.push_back(part);
+                    first = false;
+                    part = Pending{i, 1, true, {}};
+                    part_prims.clear();
+                    part_entries = 0;
+                    e = prim_entries(terms[t].natoms, mode);
+                }
+                part_prims.emplace(k, 0);
+                part_entries += e;
+                part.term_ids.push_back(t);
+            }
+            part.accumulate = !first;
+            pend.push_back(part);
+        }
+        flush();
+    }
+
+    // emit chunks
+    const int64_t cd = cartdim;
+    for (const Pending & pc : pend) {
+        ChunkDesc ch;
+        std::memset(&ch, 0, sizeof(ch));
+        ch.row0 = pc.row0; ch.nrows = pc.nrows; ch.accumulate = pc.accumulate ? 1 : 0;
+        ch.prim_begin = (int)hp.prims.size();
+        std::map<PrimKey, int> index;   // key -> prim index (global)
+        int next_entry = 0;
+        for (int t : pc.term_ids) {
+            PrimKey k = key_of(terms[t]);
+            if (index.count(k)) continue;
+            PrimDesc pd;
+            std::memset(&pd, 0, sizeof(pd));
+            pd.type = terms[t].type; pd.natoms = terms[t].natoms;
+            for (int a = 0; a < kMaxAtoms; a++) pd.atoms[a] = a < pd.natoms ? terms[t].atoms[a] : 0;
+            pd.out = next_entry;
+            pd.min = terms[t].min;
+            next_entry += prim_entries(pd.natoms, mode);
+            index[k] = (int)hp.prims.size();
+            hp.prims.push_back(pd);
+        }
+        ch.prim_end = (int)hp.prims.size();
+
+        // per-row source lists
+        auto emit = [&](std::vector<std::vector<Src>> & lists, int64_t & map_off) {
+            map_off = (int64_t)hp.map.size();
+            for (auto & l : lists) {
+                if (l.size() > 255 || hp.srcs.size() + l.size() > kMapOffsetMask) return false;
+                uint32_t w = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)hp.srcs.size());
+                hp.map.push_back(w);
+                for (auto & s : l) hp.srcs.push_back(s);
+            }
+            return true;
+        };
+        std::vector<std::vector<Src>> ql(pc.nrows), jl, kl;
+        if (mode != MODE_VALUE) jl.resize((size_t)pc.nrows * cd);
+        if (mode == MODE_QJK) kl.resize((size_t)pc.nrows * cd * cd);
+        for (int t : pc.term_ids) {
+            const auto & d = terms[t];
+            const PrimDesc & pd = hp.prims[index[key_of(d)]];
+            const int lr = d.ic - pc.row0;
+            Src s; s.pad_ = 0; s.coef = d.coeff;
+            s.entry = pd.out;
+            ql[lr].push_back(s);
+            if (mode == MODE_VALUE) continue;
+            const int n = d.natoms;
+            for (int a = 0; a < n; a++)
+                for (int c = 0; c < 3; c++) {
+                    s.entry = pd.out + 1 + 3 * a + c;
+                    jl[(size_t)lr * cd + 3 * d.atoms[a] + c].push_back(s);
+                }
+            if (mode != MODE_QJK) continue;
+            const int kbase = pd.out + 1 + 3 * n;
+            for (int a = 0; a < n; a++)
+                for (int b = 0; b < n; b++)
+                    for (int c = 0; c < 3; c++)
+                        for (int e = 0; e < 3; e++) {
+                            // block (a<=b) stored as is, the mirror block reads it transposed
+                            // (source/IC/InvDisp.cpp:869-876)
+                            if (a <= b) s.entry = kbase + 9 * kblock(a, b, n) + 3 * c + e;
+                            else        s.entry = kbase + 9 * kblock(b, a, n) + 3 * e + c;
+                            size_t row = 3 * d.atoms[a] + c, col = 3 * d.atoms[b] + e;
+                            kl[((size_t)lr * cd + row) * cd + col].push_back(s);
+                        }
+        }
+        bool ok = emit(ql, ch.qmap);
+        if (ok && mode != MODE_VALUE) ok = emit(jl, ch.jmap);
+        if (ok && mode == MODE_QJK) ok = emit(kl, ch.kmap);
+        if (!ok) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: internal coordinate definition too large for the gather map");
+        hp.chunks.push_back(ch);
+    }
+    return TCHEM_OK;
+}
+
+} // namespace tchem_b200

@@ -1,0 +1,317 @@
+// SAPSet value + Jacobian, stand-alone and chained behind the internal coordinates.
+// Replaces, batched: SAPSet::operator() and SAPSet::Jacobian_(xs, J)
+// (reference source/polynomial/SAPSet.cpp:134-144, :178-201; per-term arithmetic
+// source/polynomial/SAP.cpp:93-99 and :147-175).
+//
+// Same tile scheme as the q/J/K kernel: one lane per geometry evaluates every monomial and
+// its <= order distinct partial derivatives in registers, parks them in the per-warp compact
+// buffer and the dense y[B][nterms] / J[B][nterms][sumdim] come out through gather_store.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "ic_eval.cuh"
+#include "ic_table.h"
+
+namespace tchem_b200 {
+
+struct SapUniq { int32_t col, power; };           // x[col]^power
+struct SapTerm { int32_t ubegin, uend; };         // distinct coordinates of one monomial
+
+struct SapProgram {                               // device pointers
+    const SapTerm *   terms;
+    const SapUniq *   uniqs;
+    const ChunkDesc * chunks;                     // prim_begin/end = term range, row0/nrows likewise
+    const uint32_t *  map;
+    const Src *       srcs;
+    int32_t nterms, nuniqs, nchunks, cap, sumdim;
+};
+
+int ensure_program(tchem_ic_table * t, int mode);
+
+} // namespace tchem_b200
+
+struct tchem_sap_table {
+    int device = 0;
+    int nterms = 0, sumdim = 0, irreducible = 0;
+    int sm_count = 0, max_smem_optin = 0;
+    std::vector<int32_t> dims;
+    tchem_b200::SapProgram prog;
+    void * dev_blob = nullptr;
+};
+
+namespace tchem_b200 {
+
+namespace {
+
+__device__ __forceinline__ double ipow(double x, int p) {
+    double r = 1.0;
+    for (int i = 0; i < p; i++) r *= x;
+    return r;
+}
+
+// evaluate monomials [t0, t1) for this lane's geometry; X[col * kPad + lane]
+__device__ __forceinline__ void eval_sap_terms(const SapProgram & sp, int t0, int t1, const double * X,
+                                               double * P, int lane, bool want_J) {
+    for (int t = t0; t < t1; t++) {
+        const SapTerm term = sp.terms[t];
+        const int first = sp.terms[t0].ubegin;
+        // value: 1 * x * x * ...   (SAP.cpp:93-99)
+        double v = 1.0;
+        for (int u = term.ubegin; u < term.uend; u++) {
+            const SapUniq q = sp.uniqs[u];
+            v *= ipow(X[q.col * kPad + lane], q.power);
+        }
+        P[(t - t0) * kPad + lane] = v;
+        if (!want_J) continue;
+        // d/dx_u = p x_u^(p-1) prod_{v != u} x_v^(p_v)   (SAP.cpp:147-175)
+        const int gbase = (t1 - t0) + (term.ubegin - first);
+        for (int u = term.ubegin; u < term.uend; u++) {
+            const SapUniq qu = sp.uniqs[u];
+            double g = (double)qu.power * ipow(X[qu.col * kPad + lane], qu.power - 1);
+            for (int w = term.ubegin; w < term.uend; w++) {
+                if (w == u) continue;
+                const SapUniq qw = sp.uniqs[w];
+                g *= ipow(X[qw.col * kPad + lane], qw.power);
+            }
+            P[(gbase + (u - term.ubegin)) * kPad + lane] = g;
+        }
+    }
+}
+
+// CHAINED: x = q(r) evaluated with the compute_IC_J formulas from the IC program (value-mode
+// chunking, one compact entry per primitive); otherwise x is read from global memory.
+template <bool CHAINED>
+__global__ void __launch_bounds__(256)
+sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict__ in, const int64_t B,
+                double * __restrict__ q_out, double * __restrict__ y, double * __restrict__ J) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int sumdim = sp.sumdim;
+    const int cartdim = CHAINED ? ic.cartdim : 0, iccap = CHAINED ? ic.cap : 0;
+    const size_t per_warp = (size_t)(cartdim + iccap + sumdim + sp.cap) * kPad;
+    double * R = reinterpret_cast<double *>(smem_raw) + warp * per_warp;
+    double * PI = R + (size_t)cartdim * kPad;
+    double * X = PI + (size_t)iccap * kPad;
+    double * P = X + (size_t)sumdim * kPad;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes;
+
+    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+        const int64_t b0 = tile * kLanes;
+        const int ntile = (int)min((int64_t)kLanes, B - b0);
+        if (CHAINED) {
+            stage_coordinates(in, b0, ntile, cartdim, R, lane);
+            for (int c = 0; c < ic.nchunks; c++) {
+                const ChunkDesc ch = ic.chunks[c];
+                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH>(pd, R, lane, CompactSink(PI, pd.out, lane)); }
+                // every lane combines its own column: x[row] = sum coef * q_prim (IntCoord.cpp:66-74)
+                for (int row = 0; row < ch.nrows; row++) {
+                    const uint32_t w = ic.map[ch.qmap + row];
+                    const int cnt = (int)(w >> kMapCountShift);
+                    const uint32_t off = w & kMapOffsetMask;
+                    double x = 0.0;
+                    for (int j = 0; j < cnt; j++) {
+                        const Src s = ic.srcs[off + j];
+                        x = fma(s.coef, PI[s.entry * kPad + lane], x);
+                    }
+                    double * xp = X + (ch.row0 + row) * kPad + lane;
+                    *xp = ch.accumulate ? *xp + x : x;
+                }
+            }
+            __syncwarp();
+            if (q_out != nullptr) {
+                for (int k = lane; k < sumdim; k += kLanes)
+                    for (int g = 0; g < ntile; g++) q_out[(b0 + g) * sumdim + k] = X[k * kPad + g];
+            }
+        } else {
+            stage_coordinates(in, b0, ntile, sumdim, X, lane);
+        }
+        for (int c = 0; c < sp.nchunks; c++) {
+            const ChunkDesc ch = sp.chunks[c];
+            eval_sap_terms(sp, ch.prim_begin, ch.prim_end, X, P, lane, J != nullptr);
+            __syncwarp();
+            if (y != nullptr)
+                gather_store(sp.map + ch.qmap, sp.srcs, ch.nrows, P, y + b0 * sp.nterms + ch.row0, sp.nterms,
+                             ntile, false, lane);
+            if (J != nullptr)
+                gather_store(sp.map + ch.jmap, sp.srcs, (int64_t)ch.nrows * sumdim, P,
+                             J + (b0 * sp.nterms + ch.row0) * sumdim, (int64_t)sp.nterms * sumdim, ntile, false, lane);
+            __syncwarp();
+        }
+    }
+}
+
+int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const double * in, int64_t B,
+               double * q_out, double * y, double * J, cudaStream_t stream) {
+    const bool chained = ict != nullptr;
+    const void * fn = chained ? reinterpret_cast<const void *>(&sap_eval_kernel<true>)
+                              : reinterpret_cast<const void *>(&sap_eval_kernel<false>);
+    Program icp;
+    std::memset(&icp, 0, sizeof(icp));
+    if (chained) icp = ict->prog[MODE_VALUE];
+    const size_t wb = (size_t)((chained ? icp.cartdim + icp.cap : 0) + st->sumdim + st->prog.cap) * kPad * sizeof(double);
+    int warps = 4;
+    while (warps > 1 && warps * wb > (size_t)st->max_smem_optin) warps >>= 1;
+    const size_t smem = warps * wb;
+    if (smem > (size_t)st->max_smem_optin) return set_error(TCHEM_EINVAL, "tchem_sap_eval: set too large for the shared-memory tile");
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes;
+    int64_t grid = std::min<int64_t>((ntiles + warps - 1) / warps, (int64_t)st->sm_count * per_sm);
+    if (grid < 1) return TCHEM_OK;
+    void * args[] = {(void *)&st->prog, (void *)&icp, (void *)&in, (void *)&B, (void *)&q_out, (void *)&y, (void *)&J};
+    TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
+} // namespace
+} // namespace tchem_b200
+
+using namespace tchem_b200;
+
+extern "C" {
+
+int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int n_terms, int irreducible,
+                           const int32_t * dims, int n_irreducibles, int device, tchem_sap_table ** out) {
+    if (!term_ptr || !dims || !out || n_terms <= 0 || n_irreducibles <= 0)
+        return set_error(TCHEM_EINVAL, "tchem_sap_table_create: empty definition");
+    if (term_ptr[n_terms] > 0 && !coords) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: coords is null");
+    std::vector<int32_t> offset(n_irreducibles + 1, 0);
+    for (int i = 0; i < n_irreducibles; i++) {
+        if (dims[i] < 0) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: negative dimension");
+        offset[i + 1] = offset[i] + dims[i];
+    }
+    const int sumdim = offset[n_irreducibles];
+    if (sumdim <= 0) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: no coordinates");
+    std::vector<SapTerm> terms(n_terms);
+    std::vector<SapUniq> uniqs;
+    for (int t = 0; t < n_terms; t++) {
+        // SAPSet::construct_orders_, source/polynomial/SAPSet.cpp:47-48
+        if (term_ptr[t + 1] == term_ptr[t] && irreducible != 0)
+            return set_error(TCHEM_EINVAL, "tchem::SAPSet::construct_orders_: Only the totally symmetric irreducible can have 0th order term");
+        std::map<int32_t, int32_t> powers;              // ascending column
+        for (int c = term_ptr[t]; c < term_ptr[t + 1]; c++) {
+            const int irr = coords[2 * c], idx = coords[2 * c + 1];
+            if (irr < 0 || irr >= n_irreducibles || idx < 0 || idx >= dims[irr])
+                return set_error(TCHEM_EINVAL, "tchem_sap_table_create: coordinate outside the declared dimensions");
+            powers[offset[irr] + idx]++;
+        }
+        terms[t].ubegin = (int32_t)uniqs.size();
+        for (auto & kv : powers) uniqs.push_back(SapUniq{kv.first, kv.second});
+        terms[t].uend = (int32_t)uniqs.size();
+    }
+    // chunk consecutive terms: entries = terms + their distinct coordinates
+    int max_term = 1;
+    for (auto & t : terms) max_term = std::max(max_term, 1 + t.uend - t.ubegin);
+    const int total_entries = n_terms + (int)uniqs.size();
+    const int cap = std::max(max_term, std::min(total_entries, 64));
+    std::vector<ChunkDesc> chunks;
+    std::vector<uint32_t> map;
+    std::vector<Src> srcs;
+    for (int t0 = 0; t0 < n_terms;) {
+        int t1 = t0, entries = 0;
+        while (t1 < n_terms && entries + 1 + terms[t1].uend - terms[t1].ubegin <= cap) {
+            entries += 1 + terms[t1].uend - terms[t1].ubegin;
+            t1++;
+        }
+        ChunkDesc ch;
+        std::memset(&ch, 0, sizeof(ch));
+        ch.prim_begin = t0; ch.prim_end = t1; ch.row0 = t0; ch.nrows = t1 - t0;
+        ch.qmap = (int64_t)map.size();
+        for (int t = t0; t < t1; t++) {
+            map.push_back((1u << kMapCountShift) | (uint32_t)srcs.size());
+            srcs.push_back(Src{t - t0, 0, 1.0});
+        }
+        ch.jmap = (int64_t)map.size();
+        const int first = terms[t0].ubegin;
+        for (int t = t0; t < t1; t++) {
+            std::vector<uint32_t> row(sumdim, 0u);
+            for (int u = terms[t].ubegin; u < terms[t].uend; u++) {
+                row[uniqs[u].col] = (1u << kMapCountShift) | (uint32_t)srcs.size();
+                srcs.push_back(Src{(t1 - t0) + (u - first), 0, 1.0});
+            }
+            map.insert(map.end(), row.begin(), row.end());
+        }
+        if (srcs.size() > kMapOffsetMask) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
+        chunks.push_back(ch);
+        t0 = t1;
+    }
+    int ndev = tchem_device_count();
+    if (device < 0 || device >= ndev)
+        return set_error(TCHEM_ECUDA, "tchem_sap_table_create: no such CUDA device (this library has no CPU path)");
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    const size_t o_terms = 0, o_uniqs = o_terms + a16(terms.size() * sizeof(SapTerm));
+    const size_t o_chunks = o_uniqs + a16(uniqs.size() * sizeof(SapUniq) + 8);
+    const size_t o_map = o_chunks + a16(chunks.size() * sizeof(ChunkDesc));
+    const size_t o_srcs = o_map + a16(map.size() * sizeof(uint32_t));
+    const size_t total = o_srcs + a16(srcs.size() * sizeof(Src)) + 16;
+    std::vector<unsigned char> blob(total, 0);
+    std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SapTerm));
+    std::memcpy(blob.data() + o_uniqs, uniqs.data(), uniqs.size() * sizeof(SapUniq));
+    std::memcpy(blob.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
+    std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(Src));
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    void * dev = nullptr;
+    TC_CUDA(cudaMalloc(&dev, total));
+    cudaError_t e = cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); return set_error(TCHEM_ECUDA, cudaGetErrorString(e)); }
+    tchem_sap_table * t = new tchem_sap_table();
+    t->device = device; t->nterms = n_terms; t->sumdim = sumdim; t->irreducible = irreducible;
+    t->dims.assign(dims, dims + n_irreducibles);
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    unsigned char * d = static_cast<unsigned char *>(dev);
+    t->prog.terms = reinterpret_cast<const SapTerm *>(d + o_terms);
+    t->prog.uniqs = reinterpret_cast<const SapUniq *>(d + o_uniqs);
+    t->prog.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
+    t->prog.map = reinterpret_cast<const uint32_t *>(d + o_map);
+    t->prog.srcs = reinterpret_cast<const Src *>(d + o_srcs);
+    t->prog.nterms = n_terms; t->prog.nuniqs = (int)uniqs.size(); t->prog.nchunks = (int)chunks.size();
+    t->prog.cap = cap; t->prog.sumdim = sumdim;
+    t->dev_blob = dev;
+    *out = t;
+    return TCHEM_OK;
+}
+
+void tchem_sap_table_destroy(tchem_sap_table * t) {
+    if (!t) return;
+    { DeviceGuard guard(t->device); cudaFree(t->dev_blob); }
+    delete t;
+}
+int tchem_sap_table_nterms(const tchem_sap_table * t) { return t ? t->nterms : 0; }
+int tchem_sap_table_sumdim(const tchem_sap_table * t) { return t ? t->sumdim : 0; }
+
+int tchem_sap_eval(const tchem_sap_table * t, const double * x, int64_t B, double * y, double * J,
+                   tchem_stream_t stream) {
+    if (!t) return set_error(TCHEM_EINVAL, "tchem_sap_eval: null table");
+    if (B < 0) return set_error(TCHEM_EINVAL, "tchem_sap_eval: negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!x || (!y && !J)) return set_error(TCHEM_EINVAL, "tchem_sap_eval: null argument");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    return launch_sap(t, nullptr, x, B, nullptr, y, J, static_cast<cudaStream_t>(stream));
+}
+
+int tchem_ic_sap_eval(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r, int64_t B,
+                      double * q_out, double * y, double * J, tchem_stream_t stream) {
+    if (!ic || !sap) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval: null table");
+    if (ic->intdim != sap->sumdim)
+        return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval: x must have a same dimension as the coordinates (intdim != sum of dimensions)");
+    if (ic->device != sap->device) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval: tables live on different devices");
+    if (B < 0) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval: negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!r || (!y && !J && !q_out)) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval: null argument");
+    int rc = ensure_program(const_cast<tchem_ic_table *>(ic), MODE_VALUE);
+    if (rc != TCHEM_OK) return rc;
+    DeviceGuard guard(ic->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    return launch_sap(sap, ic, r, B, q_out, y, J, static_cast<cudaStream_t>(stream));
+}
+
+} // extern "C"

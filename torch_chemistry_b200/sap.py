@@ -1,0 +1,124 @@
+"""Host-side mirror of tchem::polynomial::SAPSet (reference include/tchem/polynomial/SAPSet.hpp:9-86),
+value and Jacobian only (the hot path), over the C ABI.
+
+xs is the reference's std::vector<at::Tensor>: one tensor per irreducible, xs[i] of shape
+[dims[i]] or batched [B, dims[i]].
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import lib, check
+from .intcoord import IntCoordSet, _stream_ptr
+
+
+class SAPSet:
+    def __init__(self, sapoly_file, irreducible, dimensions, *, text=None, device=None):
+        nt, nc = C.c_int(0), C.c_int(0)
+        if text is not None:
+            parse = lambda tp, ct, cs, cc: lib.tchem_sap_parse_text(text.encode(), tp, ct, cs, cc, C.byref(nt), C.byref(nc))
+        else:
+            parse = lambda tp, ct, cs, cc: lib.tchem_sap_parse_file(str(sapoly_file).encode(), tp, ct, cs, cc, C.byref(nt), C.byref(nc))
+        check(parse(None, 0, None, 0))
+        self._term_ptr = (C.c_int32 * (nt.value + 1))()
+        self._coords = (C.c_int32 * max(2 * nc.value, 2))()
+        check(parse(self._term_ptr, nt.value, self._coords, nc.value))
+        self.irreducible = int(irreducible)
+        self.dimensions = [int(d) for d in dimensions]
+        dims = (C.c_int32 * len(self.dimensions))(*self.dimensions)
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = torch.device("cuda", int(device) if not isinstance(device, torch.device) else (device.index or 0))
+        self._handle = C.c_void_p()
+        check(lib.tchem_sap_table_create(self._term_ptr, self._coords, nt.value, self.irreducible, dims,
+                                         len(self.dimensions), self.device.index, C.byref(self._handle)))
+        self.nterms = lib.tchem_sap_table_nterms(self._handle)
+        self.sumdim = lib.tchem_sap_table_sumdim(self._handle)
+
+    @classmethod
+    def from_text(cls, text, irreducible, dimensions, **kw):
+        return cls(None, irreducible, dimensions, text=text, **kw)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            lib.tchem_sap_table_destroy(h)
+            self._handle = None
+
+    def SAPs(self):
+        """monomials as lists of (irreducible, index) pairs, sorted descending like SAP::coords_"""
+        out = []
+        for i in range(self.nterms):
+            out.append([(self._coords[2 * c], self._coords[2 * c + 1])
+                        for c in range(self._term_ptr[i], self._term_ptr[i + 1])])
+        return out
+
+    def _cat(self, xs, name):
+        # argument checks of source/polynomial/SAPSet.cpp:135-140
+        for x in xs:
+            if not isinstance(x, torch.Tensor) or x.dim() not in (1, 2):
+                raise ValueError("tchem::polynomial::SAPSet::%s: x must be a vector" % name)
+        if len(xs) != len(self.dimensions):
+            raise ValueError("tchem::polynomial::SAPSet::%s: x must share a same number of irreducibles as the coordinate system" % name)
+        for x, d in zip(xs, self.dimensions):
+            if x.shape[-1] != d:
+                raise ValueError("tchem::polynomial::SAPSet::%s: x must have a same dimension as the coordinates" % name)
+        batched = xs[0].dim() == 2
+        x = torch.cat([t if batched else t.unsqueeze(0) for t in xs], dim=1).to(torch.float64)
+        was_cuda = x.is_cuda
+        return x.to(self.device).contiguous(), batched, was_cuda
+
+    def _run(self, xs, want_y, want_J, name):
+        x, batched, was_cuda = self._cat(xs, name)
+        B = x.shape[0]
+        y = torch.empty((B, self.nterms), dtype=torch.float64, device=self.device) if want_y else None
+        J = torch.empty((B, self.nterms, self.sumdim), dtype=torch.float64, device=self.device) if want_J else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
+        if B > 0:
+            check(lib.tchem_sap_eval(self._handle, ptr(x), B, ptr(y), ptr(J), _stream_ptr(self.device)))
+        outs = []
+        for o in (y, J):
+            if o is not None:
+                o = o if was_cuda else o.cpu()
+                outs.append(o if batched else o[0])
+        return outs
+
+    def __call__(self, xs):
+        """SAPSet::operator(), source/polynomial/SAPSet.cpp:134-144"""
+        return self._run(xs, True, False, "operator()")[0]
+
+    def Jacobian_cat(self, xs):
+        """the concatenated tensor J that SAPSet::Jacobian_(xs, J) harvests (:178-201)"""
+        return self._run(xs, False, True, "Jacobian_")[0]
+
+    def Jacobian_(self, xs):
+        """per-irreducible (NSAP x dim_i) blocks, views of the concatenated tensor (:161-201)"""
+        J = self.Jacobian_cat(xs)
+        return list(torch.split(J, self.dimensions, dim=-1))
+
+    Jacobian = Jacobian_
+
+    def value_and_jacobian(self, xs):
+        y, J = self._run(xs, True, True, "Jacobian_")
+        return y, J
+
+    # ---- chained path ----------------------------------------------------------------------
+    def chained(self, intcoordset, r, return_q=False):
+        """r -> q (compute_IC_J formulas) -> SAP values and d SAP / d q in one kernel."""
+        if not isinstance(intcoordset, IntCoordSet):
+            raise ValueError("tchem::polynomial::SAPSet::chained: needs an IntCoordSet")
+        r2, batched = intcoordset._prep(r, "compute_IC_J")
+        was_cuda = r2.is_cuda
+        r2 = intcoordset._on_device(r2)
+        B = r2.shape[0]
+        y = torch.empty((B, self.nterms), dtype=torch.float64, device=self.device)
+        J = torch.empty((B, self.nterms, self.sumdim), dtype=torch.float64, device=self.device)
+        q = torch.empty((B, self.sumdim), dtype=torch.float64, device=self.device) if return_q else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
+        if B > 0:
+            check(lib.tchem_ic_sap_eval(intcoordset._handle, self._handle, ptr(r2), B, ptr(q), ptr(y), ptr(J),
+                                        _stream_ptr(self.device)))
+        outs = [y, J] + ([q] if return_q else [])
+        outs = [o if was_cuda else o.cpu() for o in outs]
+        return tuple(o if batched else o[0] for o in outs)
