@@ -11,8 +11,10 @@ namespace {
 // dynamic shared memory: [PrimDesc x nprims][ChunkDesc x nchunks][per warp: R | P]
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+// launch bounds: <= 128 threads per block; 3 resident blocks (12 warps / SM) cap the q+J
+// flavours at 168 registers, the K flavour keeps the full 255
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, MODE == MODE_QJK ? 1 : 3)
 ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t B,
                double * __restrict__ q, double * __restrict__ J, double * __restrict__ K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -266,53 +266,73 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
 // ---------------------------------------------------------------------------------------
 // gather-store: dense output span of S elements per geometry, element k of geometry g is
 //   sum_j coef_j * P[entry_j][g]     (no sources: structural zero)
-// lanes run along k (coalesced 256 B segments), the g loop walks the tile.
+// lanes run along k (coalesced 256 B segments), the g loop walks the tile. Up to NS sources per
+// element are held in registers; elements with more take further rounds that accumulate.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void gather_store(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
-                                             int64_t S, const double * P, double * out, int64_t gstride,
-                                             int ntile, bool accumulate, int lane) {
+template <int NS, bool FULL>
+__device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const double * P,
+                                             double * o, int64_t gstride, int ntile, bool accumulate) {
+    double c[NS];
+    const double * p[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        c[j] = 0.0;
+        p[j] = P;
+        if (j < cnt) {
+            const Src s = srcs[off + j];
+            c[j] = s.coef;
+            p[j] = P + s.entry * kPad;
+        }
+    }
+    const int n = FULL ? kLanes : ntile;
+#pragma unroll 8
+    for (int g = 0; g < n; g++) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; j++)
+            if (j < cnt) v = fma(c[j], p[j][g], v);
+        if (accumulate) v += o[g * gstride];
+        o[g * gstride] = v;
+    }
+}
+
+template <bool FULL>
+__device__ __noinline__ void gather_store_impl(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
+                                                  int64_t S, const double * P, double * out, int64_t gstride,
+                                                  int ntile, bool accumulate, int lane) {
     for (int64_t k0 = 0; k0 < S; k0 += kLanes) {
         const int64_t k = k0 + lane;
         const bool valid = k < S;
-        uint32_t w = valid ? __ldg(map + k) : 0u;
+        const uint32_t w = valid ? __ldg(map + k) : 0u;
         const int cnt = (int)(w >> kMapCountShift);
         const uint32_t off = w & kMapOffsetMask;
         double * o = out + k;
         const int maxcnt = __reduce_max_sync(kFull, cnt);
-        if (maxcnt == 0 && !accumulate) {
-            if (valid) {
+        if (maxcnt == 0) {
+            if (valid && !accumulate) {
+                const int n = FULL ? kLanes : ntile;
 #pragma unroll 8
-                for (int g = 0; g < ntile; g++) o[g * gstride] = 0.0;
+                for (int g = 0; g < n; g++) o[g * gstride] = 0.0;
             }
-        } else if (maxcnt <= 2) {
-            double c0 = 0.0, c1 = 0.0;
-            const double * p0 = P, * p1 = P;
-            if (cnt > 0) { Src s = srcs[off];     c0 = s.coef; p0 = P + s.entry * kPad; }
-            if (cnt > 1) { Src s = srcs[off + 1]; c1 = s.coef; p1 = P + s.entry * kPad; }
-            if (valid) {
-#pragma unroll 4
-                for (int g = 0; g < ntile; g++) {
-                    double v = 0.0;
-                    if (cnt > 0) v = c0 * p0[g];
-                    if (cnt > 1) v = fma(c1, p1[g], v);
-                    if (accumulate) v += o[g * gstride];
-                    o[g * gstride] = v;
-                }
-            }
-        } else {
-            if (valid) {
-                for (int g = 0; g < ntile; g++) {
-                    double v = 0.0;
-                    for (int j = 0; j < cnt; j++) {
-                        Src s = srcs[off + j];
-                        v = fma(s.coef, P[s.entry * kPad + g], v);
-                    }
-                    if (accumulate) v += o[g * gstride];
-                    o[g * gstride] = v;
-                }
-            }
+            continue;
+        }
+        for (int base = 0; base < maxcnt; base += 4) {
+            const int rem = maxcnt - base;               // warp-uniform
+            const int mine = cnt - base;                 // this lane's sources in this round
+            const bool acc = accumulate || base > 0;
+            if (!valid) continue;
+            if (rem == 1)      gather_round<1, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
+            else if (rem == 2) gather_round<2, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
+            else               gather_round<4, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
         }
     }
+}
+
+__device__ __forceinline__ void gather_store(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
+                                             int64_t S, const double * P, double * out, int64_t gstride,
+                                             int ntile, bool accumulate, int lane) {
+    if (ntile == kLanes) gather_store_impl<true>(map, srcs, S, P, out, gstride, ntile, accumulate, lane);
+    else                 gather_store_impl<false>(map, srcs, S, P, out, gstride, ntile, accumulate, lane);
 }
 
 } // namespace tchem_b200

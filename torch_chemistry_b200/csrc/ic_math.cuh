@@ -70,6 +70,10 @@ __device__ __forceinline__ Dual2 sqrt_(Dual2 x) {
 }
 
 __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
+// reciprocals: one division per scalar, the 3-vector scalings below are multiplies
+__device__ __forceinline__ double rcp_(double a) { return 1.0 / a; }
+__device__ __forceinline__ Dual rcp_(Dual a) { double i = 1.0 / a.v; return mk(i, -a.d * i * i); }
+__device__ __forceinline__ Dual2 rcp_(Dual2 a) { return recip_(a); }
 __device__ __forceinline__ double val(double a) { return a; }
 __device__ __forceinline__ double val(Dual a) { return a.v; }
 __device__ __forceinline__ double val(Dual2 a) { return a.v; }
@@ -85,7 +89,7 @@ template <class S> __device__ __forceinline__ V3<S> operator+(V3<S> a, V3<S> b) 
 template <class S> __device__ __forceinline__ V3<S> operator-(V3<S> a, V3<S> b) { return v3<S>(a.x - b.x, a.y - b.y, a.z - b.z); }
 template <class S> __device__ __forceinline__ V3<S> operator-(V3<S> a) { return v3<S>(-a.x, -a.y, -a.z); }
 template <class S> __device__ __forceinline__ V3<S> operator*(S s, V3<S> a) { return v3<S>(s * a.x, s * a.y, s * a.z); }
-template <class S> __device__ __forceinline__ V3<S> operator/(V3<S> a, S s) { return v3<S>(a.x / s, a.y / s, a.z / s); }
+template <class S> __device__ __forceinline__ V3<S> operator/(V3<S> a, S s) { S i = rcp_(s); return v3<S>(a.x * i, a.y * i, a.z * i); }
 template <class S> __device__ __forceinline__ S dot(V3<S> a, V3<S> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 template <class S> __device__ __forceinline__ V3<S> cross(V3<S> a, V3<S> b) {
     return v3<S>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
@@ -115,11 +119,14 @@ __device__ __forceinline__ double signed_wrapped_angle(double cosphi, double sig
 // double since only its value is ever needed).
 // ---------------------------------------------------------------------------------------
 
+// The reference divides vector by scalar component-wise; here every distinct denominator is
+// inverted once and multiplied through (differs from the reference by rounding only).
+
 // stretching :261-272
 template <class S> __device__ __forceinline__ void stretching_J(const V3<S> * a, S & q, V3<S> * J) {
     V3<S> r12 = a[1] - a[0];
     S n = norm(r12);
-    V3<S> u = r12 / n;
+    V3<S> u = rcp_(n) * r12;
     q = n;
     J[0] = -u;
     J[1] = u;
@@ -128,20 +135,20 @@ template <class S> __device__ __forceinline__ void stretching_J(const V3<S> * a,
 // bending :273-296 (angle = acos(q_cos)), cosbending :297-316
 template <class S, bool COS> __device__ __forceinline__ void bending_J(const V3<S> * a, S & costheta, V3<S> * J) {
     V3<S> r21 = a[0] - a[1];
-    S n21 = norm(r21);
-    V3<S> u21 = r21 / n21;
+    S i21 = rcp_(norm(r21));
+    V3<S> u21 = i21 * r21;
     V3<S> r23 = a[2] - a[1];
-    S n23 = norm(r23);
-    V3<S> u23 = r23 / n23;
+    S i23 = rcp_(norm(r23));
+    V3<S> u23 = i23 * r23;
     costheta = dot(u21, u23);
     V3<S> J0, J2;
     if (COS) {
-        J0 = (u23 - costheta * u21) / n21;
-        J2 = (u21 - costheta * u23) / n23;
+        J0 = i21 * (u23 - costheta * u21);
+        J2 = i23 * (u21 - costheta * u23);
     } else {
-        S sintheta = sqrt_(1.0 - costheta * costheta);
-        J0 = (costheta * u21 - u23) / (sintheta * n21);
-        J2 = (costheta * u23 - u21) / (sintheta * n23);
+        S isin = rcp_(sqrt_(1.0 - costheta * costheta));
+        J0 = (isin * i21) * (costheta * u21 - u23);
+        J2 = (isin * i23) * (costheta * u23 - u21);
     }
     J[0] = J0;
     J[2] = J2;
@@ -154,27 +161,28 @@ template <class S, bool COS> __device__ __forceinline__ void bending_J(const V3<
 template <class S, int VAR>
 __device__ __forceinline__ void torsion_J(const V3<S> * a, S & sinphi, S & cosphi, S & sign_test, V3<S> * J) {
     V3<S> r12 = a[1] - a[0];
-    S n12 = norm(r12);
-    V3<S> u12 = r12 / n12;
+    S n12 = norm(r12), i12 = rcp_(n12);
+    V3<S> u12 = i12 * r12;
     V3<S> r23 = a[2] - a[1];
-    S n23 = norm(r23);
-    V3<S> u23 = r23 / n23;
+    S n23 = norm(r23), i23 = rcp_(n23);
+    V3<S> u23 = i23 * r23;
     V3<S> r34 = a[3] - a[2];
-    S n34 = norm(r34);
-    V3<S> u34 = r34 / n34;
+    S n34 = norm(r34), i34 = rcp_(n34);
+    V3<S> u34 = i34 * r34;
     S cos123 = -dot(u12, u23);
-    S sin123 = sqrt_(1.0 - cos123 * cos123);
+    S is123 = rcp_(sqrt_(1.0 - cos123 * cos123));
     S cos234 = -dot(u23, u34);
-    S sin234 = sqrt_(1.0 - cos234 * cos234);
-    V3<S> n123 = cross(u12, u23) / sin123;
-    V3<S> n234 = cross(u23, u34) / sin234;
+    S is234 = rcp_(sqrt_(1.0 - cos234 * cos234));
+    V3<S> n123 = is123 * cross(u12, u23);
+    V3<S> n234 = is234 * cross(u23, u34);
     cosphi = dot(n123, n234);
     if (VAR == 0) sign_test = dot(n123, cross(n234, u23));
     if (VAR != 0) sinphi = dot(cross(n123, n234), u23);
-    V3<S> J0 = -n123 / (n12 * sin123);
-    V3<S> J1 = ((n23 - n12 * cos123) / (n12 * n23 * sin123)) * n123 - (cos234 / (n23 * sin234)) * n234;
-    V3<S> J2 = ((n34 * cos234 - n23) / (n23 * n34 * sin234)) * n234 + (cos123 / (n23 * sin123)) * n123;
-    V3<S> J3 = n234 / (n34 * sin234);
+    S a23 = i23 * is123, b23 = i23 * is234;
+    V3<S> J0 = -(i12 * is123) * n123;
+    V3<S> J1 = ((n23 - n12 * cos123) * (i12 * a23)) * n123 - (cos234 * b23) * n234;
+    V3<S> J2 = ((n34 * cos234 - n23) * (i34 * b23)) * n234 + (cos123 * a23) * n123;
+    V3<S> J3 = (i34 * is234) * n234;
     if (VAR == 1) { J0 = cosphi * J0; J1 = cosphi * J1; J2 = cosphi * J2; J3 = cosphi * J3; }
     if (VAR == 2) { S m = -sinphi; J0 = m * J0; J1 = m * J1; J2 = m * J2; J3 = m * J3; }
     J[0] = J0; J[1] = J1; J[2] = J2; J[3] = J3;
@@ -183,29 +191,32 @@ __device__ __forceinline__ void torsion_J(const V3<S> * a, S & sinphi, S & cosph
 // OutOfPlane :571-602 (angle = asin(sintheta)), sinoop :603-631
 template <class S, bool SIN> __device__ __forceinline__ void oop_J(const V3<S> * a, S & sintheta, V3<S> * J) {
     V3<S> r21 = a[0] - a[1];
-    S n21 = norm(r21);
-    V3<S> u21 = r21 / n21;
+    S i21 = rcp_(norm(r21));
+    V3<S> u21 = i21 * r21;
     V3<S> r23 = a[2] - a[1];
-    S n23 = norm(r23);
-    V3<S> u23 = r23 / n23;
+    S i23 = rcp_(norm(r23));
+    V3<S> u23 = i23 * r23;
     V3<S> r24 = a[3] - a[1];
-    S n24 = norm(r24);
-    V3<S> u24 = r24 / n24;
+    S i24 = rcp_(norm(r24));
+    V3<S> u24 = i24 * r24;
     S cos324 = dot(u23, u24);
     S sin324sq = 1.0 - cos324 * cos324;
-    S sin324 = sqrt_(sin324sq);
-    sintheta = dot(u23, cross(u24, u21)) / sin324;
+    S is324 = rcp_(sqrt_(sin324sq));
+    S is324sq = is324 * is324;
+    sintheta = dot(u23, cross(u24, u21)) * is324;
     V3<S> J0, J2, J3;
     if (SIN) {
-        J0 = (cross(u23, u24) / sin324 - sintheta * u21) / n21;
-        J2 = (cross(u24, u21) / sin324 - (sintheta / sin324sq) * (u23 - cos324 * u24)) / n23;
-        J3 = (cross(u21, u23) / sin324 - (sintheta / sin324sq) * (u24 - cos324 * u23)) / n24;
+        S t = sintheta * is324sq;
+        J0 = i21 * (is324 * cross(u23, u24) - sintheta * u21);
+        J2 = i23 * (is324 * cross(u24, u21) - t * (u23 - cos324 * u24));
+        J3 = i24 * (is324 * cross(u21, u23) - t * (u24 - cos324 * u23));
     } else {
-        S costheta = sqrt_(1.0 - sintheta * sintheta);
-        S tantheta = sintheta / costheta;
-        J0 = ((cross(u23, u24) / costheta) / sin324 - tantheta * u21) / n21;
-        J2 = ((cross(u24, u21) / costheta) / sin324 - (tantheta / sin324sq) * (u23 - cos324 * u24)) / n23;
-        J3 = ((cross(u21, u23) / costheta) / sin324 - (tantheta / sin324sq) * (u24 - cos324 * u23)) / n24;
+        S icos = rcp_(sqrt_(1.0 - sintheta * sintheta));
+        S tantheta = sintheta * icos;
+        S w = icos * is324, t = tantheta * is324sq;
+        J0 = i21 * (w * cross(u23, u24) - tantheta * u21);
+        J2 = i23 * (w * cross(u24, u21) - t * (u23 - cos324 * u24));
+        J3 = i24 * (w * cross(u21, u23) - t * (u24 - cos324 * u23));
     }
     J[0] = J0;
     J[2] = J2;
@@ -227,21 +238,6 @@ __device__ __forceinline__ void torsion2_sincos(const V3<S> * a, S & sinphi, S &
     sinphi = dot(cross(n123, n2345), r23 / norm(r23));
     cosphi = dot(n123, n2345);
     sign_test = dot(n123, cross(n2345, r23));
-}
-
-// sin(angle 1-2-3) and its analytic gradient used by px/pytorsion2, :521-535 / :994-1006
-template <class S> __device__ __forceinline__ void sintheta_J(const V3<S> * a, S & sintheta, V3<S> * J) {
-    V3<S> r12 = a[1] - a[0];
-    V3<S> r23 = a[2] - a[1];
-    S n21 = norm(r12), n23 = norm(r23);
-    V3<S> u21 = (-r12) / n21, u23 = r23 / n23;
-    S costheta = dot(u21, u23);
-    sintheta = sqrt_(1.0 - costheta * costheta);
-    V3<S> J0 = (costheta * (costheta * u21 - u23)) / (sintheta * n21);
-    V3<S> J2 = (costheta * (costheta * u23 - u21)) / (sintheta * n23);
-    J[0] = J0;
-    J[2] = J2;
-    J[1] = -J0 - J2;
 }
 
 // ---------------------------------------------------------------------------------------
