@@ -66,3 +66,35 @@ for r in csv.reader(src.splitlines()):
 print("-- instructions per source line (all profiled launches summed): total", tot)
 for (f, ln, s), (inst, samp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top_n]:
     print("%-14s%5s %12d %5.1f%% samples %6d  %s" % (f, ln, inst, 100.0 * inst / max(tot, 1), samp, s))
+
+# ---- top lines by stall samples with the reasons
+import re
+agg2 = collections.OrderedDict()
+cur = None
+h = None
+for r in csv.reader(src.splitlines()):
+    if not r:
+        continue
+    if r[0] == "File Path":
+        cur = r[1].split("/")[-1]
+        continue
+    if r[0] == "Line No":
+        h = r
+        stall_cols = [(i, n) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+        iS = h.index("# Samples")
+        continue
+    if h is None or not r[0].isdigit() or len(r) <= iS:
+        continue
+    key = (cur, r[0], r[1].strip()[:70])
+    d = agg2.setdefault(key, collections.Counter())
+    try:
+        d["#"] += int(float(r[iS] or 0))
+        for i, n in stall_cols:
+            if i < len(r) and r[i]:
+                d[n] += int(float(r[i]))
+    except ValueError:
+        pass
+print("-- top lines by stall samples")
+for (f, ln, s_), d in sorted(agg2.items(), key=lambda kv: -kv[1]["#"])[:25]:
+    reasons = ", ".join("%s %d" % (k.replace("stall_", ""), v) for k, v in d.most_common(4) if k != "#")
+    print("%-14s%5s %6d  %-70s | %s" % (f, ln, d["#"], s_, reasons))

@@ -34,12 +34,16 @@ int ensure_program(tchem_ic_table * t, int mode) {
     const size_t o_prims = 0;
     const size_t o_chunks = o_prims + a16(hp.prims.size() * sizeof(PrimDesc));
     const size_t o_map = o_chunks + a16(hp.chunks.size() * sizeof(ChunkDesc));
-    const size_t o_srcs = o_map + a16(hp.map.size() * sizeof(uint32_t));
+    const size_t o_qsrcs = o_map + a16(hp.map.size() * sizeof(uint32_t));
+    const size_t o_emap = o_qsrcs + a16(hp.qsrcs.size() * sizeof(Src));
+    const size_t o_srcs = o_emap + a16(hp.emap.size() * sizeof(ElemMap));
     const size_t total = o_srcs + a16(hp.srcs.size() * sizeof(Src)) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_prims, hp.prims.data(), hp.prims.size() * sizeof(PrimDesc));
     std::memcpy(blob.data() + o_chunks, hp.chunks.data(), hp.chunks.size() * sizeof(ChunkDesc));
     std::memcpy(blob.data() + o_map, hp.map.data(), hp.map.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + o_qsrcs, hp.qsrcs.data(), hp.qsrcs.size() * sizeof(Src));
+    std::memcpy(blob.data() + o_emap, hp.emap.data(), hp.emap.size() * sizeof(ElemMap));
     std::memcpy(blob.data() + o_srcs, hp.srcs.data(), hp.srcs.size() * sizeof(Src));
     DeviceGuard guard(t->device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
@@ -52,6 +56,10 @@ int ensure_program(tchem_ic_table * t, int mode) {
     p.prims = reinterpret_cast<const PrimDesc *>(d + o_prims);
     p.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
     p.map = reinterpret_cast<const uint32_t *>(d + o_map);
+    p.qsrcs = reinterpret_cast<const Src *>(d + o_qsrcs);
+    p.nqsrcs = (int)hp.qsrcs.size();
+    p.nmap = (int)hp.map.size();
+    p.emap = reinterpret_cast<const ElemMap *>(d + o_emap);
     p.srcs = reinterpret_cast<const Src *>(d + o_srcs);
     p.nprims = (int)hp.prims.size();
     p.nchunks = (int)hp.chunks.size();
@@ -127,6 +135,7 @@ int tchem_ic_table_create(const tchem_invdisp_t * terms, int n_terms, int n_ic, 
     t->natoms = n_atoms;
     t->cartdim = 3 * n_atoms;
     t->terms.assign(terms, terms + n_terms);
+    for (const auto & d : t->terms) if (d.natoms == 5) t->has5 = true;
     std::memset(t->prog, 0, sizeof(t->prog));
     // validate once on the host (cheap mode) so that definition errors surface here
     HostProgram hp;

@@ -2,6 +2,8 @@
 // Replaces, batched: IntCoordSet::operator() / compute_IC_J / compute_IC_J_K
 // (reference source/IC/IntCoordSet.cpp:139-175).
 #include "ic_eval.cuh"
+#include <cstdlib>
+
 #include "ic_table.h"
 
 namespace tchem_b200 {
@@ -13,15 +15,20 @@ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(
 
 // launch bounds: <= 128 threads per block; 3 resident blocks (12 warps / SM) cap the q+J
 // flavours at 168 registers, the K flavour keeps the full 255
-template <int MODE>
-__global__ void __launch_bounds__(128, MODE == MODE_QJK ? 1 : 3)
+template <int MODE, bool HAS5, int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, NB)
 ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t B,
                double * __restrict__ q, double * __restrict__ J, double * __restrict__ K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PrimDesc * prims = reinterpret_cast<PrimDesc *>(smem_raw);
-    ChunkDesc * chunks = reinterpret_cast<ChunkDesc *>(smem_raw + align16(sizeof(PrimDesc) * prog.nprims));
-    double * warp_base = reinterpret_cast<double *>(
-        smem_raw + align16(sizeof(PrimDesc) * prog.nprims) + align16(sizeof(ChunkDesc) * prog.nchunks));
+    size_t off = align16(sizeof(PrimDesc) * prog.nprims);
+    ChunkDesc * chunks = reinterpret_cast<ChunkDesc *>(smem_raw + off);
+    off += align16(sizeof(ChunkDesc) * prog.nchunks);
+    Src * qsrcs = reinterpret_cast<Src *>(smem_raw + off);
+    off += align16(sizeof(Src) * prog.nqsrcs);
+    uint32_t * qmap = reinterpret_cast<uint32_t *>(smem_raw + off);
+    off += align16(sizeof(uint32_t) * prog.nmap);
+    double * warp_base = reinterpret_cast<double *>(smem_raw + off);
 
     // stage the definition tables once per block (coalesced 4-byte copies)
     {
@@ -33,6 +40,12 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         int32_t * dst2 = reinterpret_cast<int32_t *>(chunks);
         const int n2 = prog.nchunks * (int)(sizeof(ChunkDesc) / 4);
         for (int i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = src2[i];
+        const int32_t * src3 = reinterpret_cast<const int32_t *>(prog.qsrcs);
+        int32_t * dst3 = reinterpret_cast<int32_t *>(qsrcs);
+        const int n3 = prog.nqsrcs * (int)(sizeof(Src) / 4);
+        for (int i = threadIdx.x; i < n3; i += blockDim.x) dst3[i] = src3[i];
+        const int n4 = prog.nmap;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) qmap[i] = prog.map[i];
     }
     __syncthreads();
 
@@ -49,16 +62,16 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         stage_coordinates(r, b0, ntile, cartdim, R, lane);
         for (int c = 0; c < prog.nchunks; c++) {
             const ChunkDesc ch = chunks[c];
-            for (int p = ch.prim_begin; p < ch.prim_end; p++) eval_primitive<MODE>(prims[p], R, lane, CompactSink(P, prims[p].out, lane));
+            eval_chunk<MODE, HAS5>(prims, ch.prim_begin, ch.prim_end, R, P, lane);
+            if (q != nullptr) combine_rows(qmap + ch.qmap, qsrcs, ch.nrows, P, ch.qslot, lane);
             __syncwarp();
             if (q != nullptr)
-                gather_store(prog.map + ch.qmap, prog.srcs, ch.nrows, P, q + b0 * intdim + ch.row0, intdim,
-                             ntile, ch.accumulate != 0, lane);
+                store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
             if (MODE != MODE_VALUE && J != nullptr)
-                gather_store(prog.map + ch.jmap, prog.srcs, (int64_t)ch.nrows * cartdim, P,
+                gather_store(prog.emap + ch.jmap, prog.srcs, (int64_t)ch.nrows * cartdim, P,
                              J + b0 * jstride + (int64_t)ch.row0 * cartdim, jstride, ntile, ch.accumulate != 0, lane);
             if (MODE == MODE_QJK && K != nullptr)
-                gather_store(prog.map + ch.kmap, prog.srcs, (int64_t)ch.nrows * cartdim * cartdim, P,
+                gather_store(prog.emap + ch.kmap, prog.srcs, (int64_t)ch.nrows * cartdim * cartdim, P,
                              K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile,
                              ch.accumulate != 0, lane);
             __syncwarp();
@@ -66,13 +79,14 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
     }
 }
 
-template <int MODE> const void * kernel_ptr() { return reinterpret_cast<const void *>(&ic_eval_kernel<MODE>); }
+template <int MODE, bool HAS5, int NW, int NB> const void * kernel_ptr() { return reinterpret_cast<const void *>(&ic_eval_kernel<MODE, HAS5, NW, NB>); }
 
 } // namespace
 
 size_t ic_eval_table_bytes(const Program & p) {
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-    return a16(sizeof(PrimDesc) * p.nprims) + a16(sizeof(ChunkDesc) * p.nchunks);
+    return a16(sizeof(PrimDesc) * p.nprims) + a16(sizeof(ChunkDesc) * p.nchunks) + a16(sizeof(Src) * p.nqsrcs)
+         + a16(sizeof(uint32_t) * p.nmap);
 }
 size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap) * kPad * sizeof(double); }
 
@@ -80,11 +94,21 @@ size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
                    double * q, double * J, double * K, cudaStream_t stream) {
     const Program & p = t->prog[mode];
-    const void * fn = mode == MODE_VALUE ? kernel_ptr<MODE_VALUE>() : mode == MODE_QJ ? kernel_ptr<MODE_QJ>() : kernel_ptr<MODE_QJK>();
+    // launch shapes: q / q+J run 4 warps per block, 3 blocks per SM (<= 168 registers);
+    // q+J+K 2 warps per block with the full register file
     const size_t tb = ic_eval_table_bytes(p), wb = ic_eval_warp_bytes(p);
     int warps = mode == MODE_QJK ? 2 : 4;
-    while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps >>= 1;
+    while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps--;
+    const bool has5 = t->has5;
+    const void * fn;
+    if (mode == MODE_QJK)        fn = has5 ? kernel_ptr<MODE_QJK, true, 2, 1>() : kernel_ptr<MODE_QJK, false, 2, 1>();
+    else if (mode == MODE_VALUE) fn = kernel_ptr<MODE_VALUE, false, 4, 3>();
+    else                         fn = has5 ? kernel_ptr<MODE_QJ, true, 4, 3>() : kernel_ptr<MODE_QJ, false, 4, 3>();
     const size_t smem = tb + warps * wb;
+    // the gather addresses geometry g of a tile as base + g * stride_bytes in 32 bits
+    const double widest = 8.0 * p.intdim * p.cartdim * (mode == MODE_QJK ? (double)p.cartdim : 1.0);
+    if (widest * kLanes >= 4294967296.0)
+        return set_error(TCHEM_EINVAL, "tchem_ic_eval: per-geometry output block too large");
     if (smem > (size_t)t->max_smem_optin)
         return set_error(TCHEM_EINVAL, "tchem_ic_eval: molecule too large for the shared-memory tile (cartdim + row capacity)");
     TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -23,7 +23,7 @@ __device__ __forceinline__ void stage_coordinates(const double * __restrict__ r,
     int g = lane / cartdim, c = lane - g * cartdim;
     const int dg = kLanes / cartdim, dc = kLanes - dg * cartdim;
     for (int f = lane; f < total; f += kLanes) {
-        R[c * kPad + g] = __ldg(src + f);
+        R[c * kPad + g] = __ldcs(src + f);      // streamed once: keep it out of the way of the tables
         g += dg; c += dc;
         if (c >= cartdim) { c -= cartdim; g++; }
     }
@@ -63,27 +63,21 @@ struct CompactSink {
     __device__ __forceinline__ CompactSink(double * P, int out, int lane)
         : Pq(P + out * kPad + lane), PJ(P + (out + 1) * kPad + lane) {}
     __device__ __forceinline__ void value(double v) const { Pq[0] = v; }
-    template <int N> __device__ __forceinline__ void jac(const int *, const V3<double> * J) const {
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            PJ[(3 * i + 0) * kPad] = J[i].x;
-            PJ[(3 * i + 1) * kPad] = J[i].y;
-            PJ[(3 * i + 2) * kPad] = J[i].z;
-        }
+    __device__ __forceinline__ void jac_block(const int *, int i, const V3<double> & J) const {
+        PJ[(3 * i + 0) * kPad] = J.x;
+        PJ[(3 * i + 1) * kPad] = J.y;
+        PJ[(3 * i + 2) * kPad] = J.z;
     }
     __device__ __forceinline__ void jac_entry(const int *, int m, double j) const { PJ[m * kPad] = j; }
-    // tangent direction (atom j, component l) of the J expression: blocks (i <= j), entry (k, l)
-    template <int N> __device__ __forceinline__ void hess_dir(const int *, int dir, const V3<Dual> * J) const {
+    // tangent direction (atom j, component l) of block i of the J expression: kept when i <= j,
+    // entry (k, l) of block (i, j)
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int dir, int i, const V3<Dual> & J) const {
         const int j = dir / 3, l = dir - 3 * j;
-        double * PK = PJ + 3 * N * kPad;
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            if (i <= j) {
-                double * blk = PK + (9 * kblock(i, j, N) + l) * kPad;
-                blk[0 * 3 * kPad] = J[i].x.d;
-                blk[1 * 3 * kPad] = J[i].y.d;
-                blk[2 * 3 * kPad] = J[i].z.d;
-            }
+        if (i <= j) {
+            double * blk = PJ + 3 * N * kPad + (9 * kblock(i, j, N) + l) * kPad;
+            blk[0 * 3 * kPad] = J.x.d;
+            blk[1 * 3 * kPad] = J.y.d;
+            blk[2 * 3 * kPad] = J.z.d;
         }
     }
     // second derivative (m1 <= m2) of a 5-atom primitive
@@ -95,6 +89,86 @@ struct CompactSink {
     }
 };
 
+// 5-atom torsion2 family, kept out of line: it is rare and register hungry (Dual / Dual2 passes
+// over 15 coordinates) and must not inflate the register allocation of the common types.
+template <int MODE, class Sink>
+__device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double * R, int lane, const Sink sink) {
+    const int type = pd.type;
+    V3<double> a[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) a[i] = load_atom(R, pd.atoms[i], lane);
+        // 5-atom torsion2 family: the reference differentiates the value expression with
+    // autograd (source/IC/InvDisp.cpp:415-570 first order, :893-1065 second order).
+    // px/py = sin(theta) * cos/sin(phi): the reference applies the product rule with an
+    // analytic J(sin theta) (:530-536, :1022); differentiating the product directly is
+    // the same function.
+    double sv, cv, tv;
+    torsion2_sincos<double>(a, sv, cv, tv);
+    const bool use_cos = fabs(sv) > fabs(cv);       // :432, :904
+    double sintheta = 0.0;
+    if (type == TCHEM_PXTORSION2 || type == TCHEM_PYTORSION2) {
+        V3<double> u12 = a[1] - a[0], u23 = a[2] - a[1];
+        u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+        double ct = -dot(u12, u23);
+        sintheta = sqrt(1.0 - ct * ct);
+    }
+    switch (type) {
+    case TCHEM_TORSION2:    sink.value(signed_wrapped_angle(cv, tv, pd.min)); break;
+    case TCHEM_SINTORSION2: sink.value(sv); break;
+    case TCHEM_COSTORSION2: sink.value(cv); break;
+    case TCHEM_PXTORSION2:  sink.value(sintheta * cv); break;
+    default:                sink.value(sintheta * sv); break;
+    }
+    if (MODE == MODE_QJ) {
+        for (int dir = 0; dir < 15; dir++) {
+            V3<Dual> s[5]; Dual sd, cd, td;
+            seed_atoms<Dual, 5>(a, s, dir, -1);
+            torsion2_sincos<Dual>(s, sd, cd, td);
+            double j;
+            if (type == TCHEM_TORSION2) j = use_cos ? cd.d / (-sv) : sd.d / cv;
+            else if (type == TCHEM_SINTORSION2) j = sd.d;
+            else if (type == TCHEM_COSTORSION2) j = cd.d;
+            else {
+                V3<Dual> u12 = s[1] - s[0], u23 = s[2] - s[1];
+                u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+                Dual ct = -dot(u12, u23);
+                Dual sth = sqrt_(1.0 - ct * ct);
+                j = (sth * (type == TCHEM_PXTORSION2 ? cd : sd)).d;
+            }
+            sink.jac_entry(pd.atoms, dir, j);
+        }
+    } else if (MODE == MODE_QJK) {
+        for (int d2 = 0; d2 < 15; d2++) {
+            for (int d1 = 0; d1 <= d2; d1++) {
+                V3<Dual2> s[5]; Dual2 sd, cd, td;
+                seed_atoms<Dual2, 5>(a, s, d1, d2);
+                torsion2_sincos<Dual2>(s, sd, cd, td);
+                double j2, k;      // d/d(d2) and d2/d(d1)d(d2)
+                if (type == TCHEM_TORSION2) {
+                    if (use_cos) {  // J = Jcos / -sin ; K = (Kcos + Jsin (x) J) / -sin   (:917-918)
+                        j2 = cd.b / (-sv);
+                        k = (cd.c + sd.a * j2) / (-sv);
+                    } else {        // J = Jsin / cos ; K = (Ksin - Jcos (x) J) / cos     (:935-936)
+                        j2 = sd.b / cv;
+                        k = (sd.c - cd.a * j2) / cv;
+                    }
+                } else if (type == TCHEM_SINTORSION2) { j2 = sd.b; k = sd.c; }
+                else if (type == TCHEM_COSTORSION2) { j2 = cd.b; k = cd.c; }
+                else {
+                    V3<Dual2> u12 = s[1] - s[0], u23 = s[2] - s[1];
+                    u12 = u12 / norm(u12); u23 = u23 / norm(u23);
+                    Dual2 ct = -dot(u12, u23);
+                    Dual2 sth = sqrt_(1.0 - ct * ct);
+                    Dual2 f = sth * (type == TCHEM_PXTORSION2 ? cd : sd);
+                    j2 = f.b; k = f.c;
+                }
+                if (d1 == d2) sink.jac_entry(pd.atoms, d2, j2);
+                sink.hess_entry5(pd.atoms, d1, d2, k);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // One invariant displacement for this lane's geometry.
 //   MODE_VALUE : clamped value formulas of InvDisp::operator()
@@ -103,12 +177,19 @@ struct CompactSink {
 //   MODE_QJK   : + one Dual pass per Cartesian direction through the same J expression
 //                (what the reference asks autograd for, source/IC/InvDisp.cpp:859-868)
 // ---------------------------------------------------------------------------------------
-template <int MODE, class Sink>
+// HAS5: the table contains 5-atom (torsion2 family) primitives. Those are evaluated by an
+// out-of-line function; a kernel instantiated with HAS5 = false carries no call at all, which
+// keeps its long-lived state in registers (values live across a call site go to the stack).
+template <int MODE, bool HAS5, class Sink>
 __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double * R, int lane, const Sink & sink) {
     constexpr bool WANT_J = MODE == MODE_QJ || MODE == MODE_QJK;
     const int type = pd.type;
     if (type == TCHEM_DUMMY) { sink.value(1.0); return; }
 
+    if (MODE != MODE_VALUE && pd.natoms == 5) {
+        if (HAS5) eval_primitive5<MODE, Sink>(pd, R, lane, sink);
+        return;
+    }
     V3<double> a[kMaxAtoms];
 #pragma unroll
     for (int i = 0; i < kMaxAtoms; i++)
@@ -119,159 +200,107 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
         return;
     }
 
+    // J blocks leave the registers as soon as they are formed
+    auto emitJ = [&](int i, const V3<double> & v) { if (WANT_J) sink.jac_block(pd.atoms, i, v); };
     switch (type) {
     case TCHEM_STRETCHING: {
-        double q; V3<double> J[2];
-        stretching_J<double>(a, q, J);
+        double q;
+        stretching_J<double>(a, q, emitJ);
         sink.value(q);
-        if (WANT_J) sink.template jac<2>(pd.atoms, J);
         if (MODE == MODE_QJK) {
             for (int dir = 0; dir < 6; dir++) {
-                V3<Dual> s[2], Jd[2]; Dual qd;
+                V3<Dual> s[2]; Dual qd;
                 seed_atoms<Dual, 2>(a, s, dir, -1);
-                stretching_J<Dual>(s, qd, Jd);
-                sink.template hess_dir<2>(pd.atoms, dir, Jd);
+                stretching_J<Dual>(s, qd, [&](int i, const V3<Dual> & v) { sink.template hess_block<2>(pd.atoms, dir, i, v); });
             }
         }
         break;
     }
     case TCHEM_BENDING: case TCHEM_COSBENDING: {
-        double c; V3<double> J[3];
-        if (type == TCHEM_BENDING) { bending_J<double, false>(a, c, J); sink.value(acos(c)); }
-        else                       { bending_J<double, true>(a, c, J);  sink.value(c); }
-        if (WANT_J) sink.template jac<3>(pd.atoms, J);
+        double c;
+        if (type == TCHEM_BENDING) { bending_J<double, false>(a, c, emitJ); sink.value(acos(c)); }
+        else                       { bending_J<double, true>(a, c, emitJ);  sink.value(c); }
         if (MODE == MODE_QJK) {
             for (int dir = 0; dir < 9; dir++) {
-                V3<Dual> s[3], Jd[3]; Dual cd;
+                V3<Dual> s[3]; Dual cd;
                 seed_atoms<Dual, 3>(a, s, dir, -1);
-                if (type == TCHEM_BENDING) bending_J<Dual, false>(s, cd, Jd);
-                else                       bending_J<Dual, true>(s, cd, Jd);
-                sink.template hess_dir<3>(pd.atoms, dir, Jd);
+                auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<3>(pd.atoms, dir, i, v); };
+                if (type == TCHEM_BENDING) bending_J<Dual, false>(s, cd, emitK);
+                else                       bending_J<Dual, true>(s, cd, emitK);
             }
         }
         break;
     }
     case TCHEM_TORSION: case TCHEM_SINTORSION: case TCHEM_COSTORSION: {
-        double sp = 0.0, cp = 0.0, st = 0.0; V3<double> J[4];
+        double sp = 0.0, cp = 0.0, st = 0.0;
         if (type == TCHEM_TORSION) {
-            torsion_J<double, 0>(a, sp, cp, st, J);
+            torsion_J<double, 0>(a, sp, cp, st, emitJ);
             sink.value(signed_wrapped_angle(cp, st, pd.min));
-        } else if (type == TCHEM_SINTORSION) { torsion_J<double, 1>(a, sp, cp, st, J); sink.value(sp); }
-        else                                 { torsion_J<double, 2>(a, sp, cp, st, J); sink.value(cp); }
-        if (WANT_J) sink.template jac<4>(pd.atoms, J);
+        } else if (type == TCHEM_SINTORSION) { torsion_J<double, 1>(a, sp, cp, st, emitJ); sink.value(sp); }
+        else                                 { torsion_J<double, 2>(a, sp, cp, st, emitJ); sink.value(cp); }
         if (MODE == MODE_QJK) {
             for (int dir = 0; dir < 12; dir++) {
-                V3<Dual> s[4], Jd[4]; Dual spd, cpd, std_;
+                V3<Dual> s[4]; Dual spd, cpd, std_;
                 seed_atoms<Dual, 4>(a, s, dir, -1);
-                if (type == TCHEM_TORSION)         torsion_J<Dual, 0>(s, spd, cpd, std_, Jd);
-                else if (type == TCHEM_SINTORSION) torsion_J<Dual, 1>(s, spd, cpd, std_, Jd);
-                else                               torsion_J<Dual, 2>(s, spd, cpd, std_, Jd);
-                sink.template hess_dir<4>(pd.atoms, dir, Jd);
+                auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<4>(pd.atoms, dir, i, v); };
+                if (type == TCHEM_TORSION)         torsion_J<Dual, 0>(s, spd, cpd, std_, emitK);
+                else if (type == TCHEM_SINTORSION) torsion_J<Dual, 1>(s, spd, cpd, std_, emitK);
+                else                               torsion_J<Dual, 2>(s, spd, cpd, std_, emitK);
             }
         }
         break;
     }
     case TCHEM_OUTOFPLANE: case TCHEM_SINOOP: {
-        double s_; V3<double> J[4];
-        if (type == TCHEM_OUTOFPLANE) { oop_J<double, false>(a, s_, J); sink.value(asin(s_)); }
-        else                          { oop_J<double, true>(a, s_, J);  sink.value(s_); }
-        if (WANT_J) sink.template jac<4>(pd.atoms, J);
+        double s_;
+        if (type == TCHEM_OUTOFPLANE) { oop_J<double, false>(a, s_, emitJ); sink.value(asin(s_)); }
+        else                          { oop_J<double, true>(a, s_, emitJ);  sink.value(s_); }
         if (MODE == MODE_QJK) {
             for (int dir = 0; dir < 12; dir++) {
-                V3<Dual> s[4], Jd[4]; Dual sd;
+                V3<Dual> s[4]; Dual sd;
                 seed_atoms<Dual, 4>(a, s, dir, -1);
-                if (type == TCHEM_OUTOFPLANE) oop_J<Dual, false>(s, sd, Jd);
-                else                          oop_J<Dual, true>(s, sd, Jd);
-                sink.template hess_dir<4>(pd.atoms, dir, Jd);
+                auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<4>(pd.atoms, dir, i, v); };
+                if (type == TCHEM_OUTOFPLANE) oop_J<Dual, false>(s, sd, emitK);
+                else                          oop_J<Dual, true>(s, sd, emitK);
             }
         }
         break;
     }
-    default: {
-        // 5-atom torsion2 family: the reference differentiates the value expression with
-        // autograd (source/IC/InvDisp.cpp:415-570 first order, :893-1065 second order).
-        // px/py = sin(theta) * cos/sin(phi): the reference applies the product rule with an
-        // analytic J(sin theta) (:530-536, :1022); differentiating the product directly is
-        // the same function.
-        double sv, cv, tv;
-        torsion2_sincos<double>(a, sv, cv, tv);
-        const bool use_cos = fabs(sv) > fabs(cv);       // :432, :904
-        double sintheta = 0.0;
-        if (type == TCHEM_PXTORSION2 || type == TCHEM_PYTORSION2) {
-            V3<double> u12 = a[1] - a[0], u23 = a[2] - a[1];
-            u12 = u12 / norm(u12); u23 = u23 / norm(u23);
-            double ct = -dot(u12, u23);
-            sintheta = sqrt(1.0 - ct * ct);
-        }
-        switch (type) {
-        case TCHEM_TORSION2:    sink.value(signed_wrapped_angle(cv, tv, pd.min)); break;
-        case TCHEM_SINTORSION2: sink.value(sv); break;
-        case TCHEM_COSTORSION2: sink.value(cv); break;
-        case TCHEM_PXTORSION2:  sink.value(sintheta * cv); break;
-        default:                sink.value(sintheta * sv); break;
-        }
-        if (MODE == MODE_QJ) {
-            for (int dir = 0; dir < 15; dir++) {
-                V3<Dual> s[5]; Dual sd, cd, td;
-                seed_atoms<Dual, 5>(a, s, dir, -1);
-                torsion2_sincos<Dual>(s, sd, cd, td);
-                double j;
-                if (type == TCHEM_TORSION2) j = use_cos ? cd.d / (-sv) : sd.d / cv;
-                else if (type == TCHEM_SINTORSION2) j = sd.d;
-                else if (type == TCHEM_COSTORSION2) j = cd.d;
-                else {
-                    V3<Dual> u12 = s[1] - s[0], u23 = s[2] - s[1];
-                    u12 = u12 / norm(u12); u23 = u23 / norm(u23);
-                    Dual ct = -dot(u12, u23);
-                    Dual sth = sqrt_(1.0 - ct * ct);
-                    j = (sth * (type == TCHEM_PXTORSION2 ? cd : sd)).d;
-                }
-                sink.jac_entry(pd.atoms, dir, j);
-            }
-        } else if (MODE == MODE_QJK) {
-            for (int d2 = 0; d2 < 15; d2++) {
-                for (int d1 = 0; d1 <= d2; d1++) {
-                    V3<Dual2> s[5]; Dual2 sd, cd, td;
-                    seed_atoms<Dual2, 5>(a, s, d1, d2);
-                    torsion2_sincos<Dual2>(s, sd, cd, td);
-                    double j2, k;      // d/d(d2) and d2/d(d1)d(d2)
-                    if (type == TCHEM_TORSION2) {
-                        if (use_cos) {  // J = Jcos / -sin ; K = (Kcos + Jsin (x) J) / -sin   (:917-918)
-                            j2 = cd.b / (-sv);
-                            k = (cd.c + sd.a * j2) / (-sv);
-                        } else {        // J = Jsin / cos ; K = (Ksin - Jcos (x) J) / cos     (:935-936)
-                            j2 = sd.b / cv;
-                            k = (sd.c - cd.a * j2) / cv;
-                        }
-                    } else if (type == TCHEM_SINTORSION2) { j2 = sd.b; k = sd.c; }
-                    else if (type == TCHEM_COSTORSION2) { j2 = cd.b; k = cd.c; }
-                    else {
-                        V3<Dual2> u12 = s[1] - s[0], u23 = s[2] - s[1];
-                        u12 = u12 / norm(u12); u23 = u23 / norm(u23);
-                        Dual2 ct = -dot(u12, u23);
-                        Dual2 sth = sqrt_(1.0 - ct * ct);
-                        Dual2 f = sth * (type == TCHEM_PXTORSION2 ? cd : sd);
-                        j2 = f.b; k = f.c;
-                    }
-                    if (d1 == d2) sink.jac_entry(pd.atoms, d2, j2);
-                    sink.hess_entry5(pd.atoms, d1, d2, k);
-                }
-            }
-        }
+    default:
         break;
     }
-    }
+}
+
+// All distinct primitives of one chunk for this lane's geometry -> compact buffer.
+template <int MODE, bool HAS5>
+__device__ __forceinline__ void eval_chunk(const PrimDesc * prims, int p0, int p1, const double * R, double * P, int lane) {
+    for (int p = p0; p < p1; p++) eval_primitive<MODE, HAS5>(prims[p], R, lane, CompactSink(P, prims[p].out, lane));
 }
 
 // ---------------------------------------------------------------------------------------
 // gather-store: dense output span of S elements per geometry, element k of geometry g is
 //   sum_j coef_j * P[entry_j][g]     (no sources: structural zero)
-// lanes run along k (coalesced 256 B segments), the g loop walks the tile. Up to NS sources per
-// element are held in registers; elements with more take further rounds that accumulate.
+// Lanes run along the (sector-sorted, see ElemMap) elements, the g loop walks the tile. Up to 4
+// sources per element are held in registers; elements with more take further rounds that
+// accumulate.
 // ---------------------------------------------------------------------------------------
-template <int NS, bool FULL>
+// read-only table loads through the non-coherent path (L1-resident: the tables are re-read by
+// every warp for every tile)
+__device__ __forceinline__ Src load_src(const Src * p) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+    Src s;
+    s.entry = v.x; s.pad_ = 0; s.coef = __hiloint2double(v.w, v.z);
+    return s;
+}
+__device__ __forceinline__ ElemMap load_emap(const ElemMap * p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    ElemMap m;
+    m.word = v.x; m.k = v.y;
+    return m;
+}
+
+template <int NS, bool FULL, bool ACC>
 __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const double * P,
-                                             double * o, int64_t gstride, int ntile, bool accumulate) {
+                                             char * o, uint32_t gbytes, int ntile) {
     double c[NS];
     const double * p[NS];
 #pragma unroll
@@ -279,60 +308,106 @@ __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint
         c[j] = 0.0;
         p[j] = P;
         if (j < cnt) {
-            const Src s = srcs[off + j];
+            const Src s = load_src(srcs + off + j);
             c[j] = s.coef;
             p[j] = P + s.entry * kPad;
         }
     }
     const int n = FULL ? kLanes : ntile;
-#pragma unroll 8
+#pragma unroll 4
     for (int g = 0; g < n; g++) {
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; j++)
             if (j < cnt) v = fma(c[j], p[j][g], v);
-        if (accumulate) v += o[g * gstride];
-        o[g * gstride] = v;
+        double * og = reinterpret_cast<double *>(o + (size_t)((uint32_t)g * gbytes));
+        if (ACC) v += *og;
+        *og = v;
     }
 }
 
-template <bool FULL>
-__device__ __noinline__ void gather_store_impl(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
-                                                  int64_t S, const double * P, double * out, int64_t gstride,
-                                                  int ntile, bool accumulate, int lane) {
+// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host),
+// so every store address is one 32x32+64 multiply-add away from the element's base pointer
+template <bool FULL, bool ACC>
+__device__ __forceinline__ void gather_store_impl(const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
+                                               int64_t S, const double * P, double * out, uint32_t gbytes,
+                                               int ntile, int lane) {
+    ElemMap next;
+    next.word = 0u; next.k = 0u;
+    if (lane < S) next = load_emap(emap + lane);
     for (int64_t k0 = 0; k0 < S; k0 += kLanes) {
-        const int64_t k = k0 + lane;
-        const bool valid = k < S;
-        const uint32_t w = valid ? __ldg(map + k) : 0u;
-        const int cnt = (int)(w >> kMapCountShift);
-        const uint32_t off = w & kMapOffsetMask;
-        double * o = out + k;
-        const int maxcnt = __reduce_max_sync(kFull, cnt);
+        const bool valid = k0 + lane < S;
+        const ElemMap m = next;
+        if (k0 + kLanes + lane < S) next = load_emap(emap + k0 + kLanes + lane);
+        const int cnt = (int)(m.word >> kMapCountShift);
+        const uint32_t off = m.word & kMapOffsetMask;
+        char * o = reinterpret_cast<char *>(out + m.k);
+        const int maxcnt = __reduce_max_sync(kFull, valid ? cnt : 0);
         if (maxcnt == 0) {
-            if (valid && !accumulate) {
+            if (valid && !ACC) {
                 const int n = FULL ? kLanes : ntile;
-#pragma unroll 8
-                for (int g = 0; g < n; g++) o[g * gstride] = 0.0;
+#pragma unroll 4
+                for (int g = 0; g < n; g++) *reinterpret_cast<double *>(o + (size_t)((uint32_t)g * gbytes)) = 0.0;
             }
             continue;
         }
-        for (int base = 0; base < maxcnt; base += 4) {
-            const int rem = maxcnt - base;               // warp-uniform
-            const int mine = cnt - base;                 // this lane's sources in this round
-            const bool acc = accumulate || base > 0;
-            if (!valid) continue;
-            if (rem == 1)      gather_round<1, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
-            else if (rem == 2) gather_round<2, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
-            else               gather_round<4, FULL>(srcs, off + base, mine, P, o, gstride, ntile, acc);
+        if (!valid) continue;
+        {   // first round
+            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
+            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
+            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
         }
+        for (int base = 4; base < maxcnt; base += 4)       // rare: more than 4 sources
+            gather_round<4, FULL, true>(srcs, off + base, cnt - base, P, o, gbytes, ntile);
     }
 }
 
-__device__ __forceinline__ void gather_store(const uint32_t * __restrict__ map, const Src * __restrict__ srcs,
+__device__ __forceinline__ void gather_store(const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
                                              int64_t S, const double * P, double * out, int64_t gstride,
                                              int ntile, bool accumulate, int lane) {
-    if (ntile == kLanes) gather_store_impl<true>(map, srcs, S, P, out, gstride, ntile, accumulate, lane);
-    else                 gather_store_impl<false>(map, srcs, S, P, out, gstride, ntile, accumulate, lane);
+    const uint32_t gbytes = (uint32_t)(gstride * sizeof(double));
+    if (accumulate) {
+        if (ntile == kLanes) gather_store_impl<true, true>(emap, srcs, S, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, true>(emap, srcs, S, P, out, gbytes, ntile, lane);
+    } else {
+        if (ntile == kLanes) gather_store_impl<true, false>(emap, srcs, S, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, false>(emap, srcs, S, P, out, gbytes, ntile, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// q rows of a chunk: every lane combines its own geometry, q[row] = sum coef * q_prim
+// (source/IC/IntCoord.cpp:53-60 / :66-74), parks the rows in the chunk's q slots and the warp
+// writes the [ntile][nrows] block with lanes running over (geometry, row) pairs.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void combine_rows(const uint32_t * __restrict__ qmap, const Src * __restrict__ srcs,
+                                             int nrows, double * P, int qslot, int lane) {
+    for (int row = 0; row < nrows; row++) {
+        const uint32_t w = qmap[row];
+        const int cnt = (int)(w >> kMapCountShift);
+        const uint32_t off = w & kMapOffsetMask;
+        double x = 0.0;
+        for (int j = 0; j < cnt; j++) {
+            const Src s = srcs[off + j];
+            x = fma(s.coef, P[s.entry * kPad + lane], x);
+        }
+        P[(qslot + row) * kPad + lane] = x;
+    }
+}
+
+__device__ __forceinline__ void store_rows(const double * P, int qslot, int nrows, double * out /* &q[b0][row0] */,
+                                           int64_t gstride, int ntile, bool accumulate, int lane) {
+    const int total = ntile * nrows;
+    int g = lane / nrows, row = lane - g * nrows;
+    const int dg = kLanes / nrows, dr = kLanes - dg * nrows;
+    for (int f = lane; f < total; f += kLanes) {
+        double v = P[(qslot + row) * kPad + g];
+        double * o = out + (int64_t)g * gstride + row;
+        if (accumulate) v += *o;
+        *o = v;
+        g += dg; row += dr;
+        if (row >= nrows) { row -= nrows; g++; }
+    }
 }
 
 } // namespace tchem_b200

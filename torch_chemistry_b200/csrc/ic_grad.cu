@@ -30,25 +30,23 @@ struct ScatterSink {
     double * G;      // g_r tile, lane folded in: G[col * kPad]
     double W;
     __device__ __forceinline__ void value(double) const {}
-    template <int N> __device__ __forceinline__ void jac(const int * atoms, const V3<double> * J) const {
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            double * g = G + 3 * atoms[i] * kPad;
-            g[0] = fma(W, J[i].x, g[0]);
-            g[kPad] = fma(W, J[i].y, g[kPad]);
-            g[2 * kPad] = fma(W, J[i].z, g[2 * kPad]);
-        }
+    __device__ __forceinline__ void jac_block(const int * atoms, int i, const V3<double> & J) const {
+        double * g = G + 3 * atoms[i] * kPad;
+        g[0] = fma(W, J.x, g[0]);
+        g[kPad] = fma(W, J.y, g[kPad]);
+        g[2 * kPad] = fma(W, J.z, g[2 * kPad]);
     }
     __device__ __forceinline__ void jac_entry(const int * atoms, int m, double j) const {
         const int a = m / 3;
         double * g = G + (3 * atoms[a] + (m - 3 * a)) * kPad;
         g[0] = fma(W, j, g[0]);
     }
-    template <int N> __device__ __forceinline__ void hess_dir(const int *, int, const V3<Dual> *) const {}
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int, int, const V3<Dual> &) const {}
     __device__ __forceinline__ void hess_entry5(const int *, int, int, double) const {}
 };
 
-__global__ void __launch_bounds__(256)
+template <bool HAS5>
+__global__ void __launch_bounds__(128)
 grad_int2cart_kernel(const GradProgram gp, const double * __restrict__ r, const double * __restrict__ gq,
                      const int64_t B, double * __restrict__ gr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -74,7 +72,7 @@ grad_int2cart_kernel(const GradProgram gp, const double * __restrict__ r, const 
             ScatterSink sink;
             sink.G = G + lane;
             sink.W = W;
-            eval_primitive<MODE_QJ>(pd, R, lane, sink);
+            eval_primitive<MODE_QJ, HAS5>(pd, R, lane, sink);
         }
         __syncwarp();
         double * out = gr + b0 * cartdim;
@@ -182,7 +180,8 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
     GradProgram gp;
     int rc = get_grad_program(t, gp);
     if (rc != TCHEM_OK) return rc;
-    const void * fn = reinterpret_cast<const void *>(&grad_int2cart_kernel);
+    const void * fn = t->has5 ? reinterpret_cast<const void *>(&grad_int2cart_kernel<true>)
+                              : reinterpret_cast<const void *>(&grad_int2cart_kernel<false>);
     const size_t wb = (size_t)(2 * t->cartdim + t->intdim) * kPad * sizeof(double);
     int warps = 4;
     while (warps > 1 && warps * wb > (size_t)t->max_smem_optin) warps >>= 1;

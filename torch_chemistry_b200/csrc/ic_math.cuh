@@ -74,6 +74,13 @@ __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
 __device__ __forceinline__ double rcp_(double a) { return 1.0 / a; }
 __device__ __forceinline__ Dual rcp_(Dual a) { double i = 1.0 / a.v; return mk(i, -a.d * i * i); }
 __device__ __forceinline__ Dual2 rcp_(Dual2 a) { return recip_(a); }
+// x^(-1/2): norms and 1/sin come from one reciprocal square root instead of sqrt + divide
+__device__ __forceinline__ double rsqrt_(double a) { return rsqrt(a); }
+__device__ __forceinline__ Dual rsqrt_(Dual a) { double i = rsqrt(a.v); return mk(i, -0.5 * i * i * i * a.d); }
+__device__ __forceinline__ Dual2 rsqrt_(Dual2 x) {
+    double i = rsqrt(x.v), i2 = i * i, f1 = -0.5 * i * i2, f2 = 0.75 * i * i2 * i2;
+    return mk2(i, f1 * x.a, f1 * x.b, f1 * x.c + f2 * x.a * x.b);
+}
 __device__ __forceinline__ double val(double a) { return a; }
 __device__ __forceinline__ double val(Dual a) { return a.v; }
 __device__ __forceinline__ double val(Dual2 a) { return a.v; }
@@ -95,6 +102,12 @@ template <class S> __device__ __forceinline__ V3<S> cross(V3<S> a, V3<S> b) {
     return v3<S>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 template <class S> __device__ __forceinline__ S norm(V3<S> a) { return sqrt_(dot(a, a)); }
+// |a| and 1/|a| together
+template <class S> __device__ __forceinline__ void norm_inv(V3<S> a, S & n, S & inv) {
+    S n2 = dot(a, a);
+    inv = rsqrt_(n2);
+    n = n2 * inv;
+}
 
 // ---------------------------------------------------------------------------------------
 // angle post-processing shared by torsion / torsion2 (source/IC/InvDisp.cpp:108-118, 339-347)
@@ -122,23 +135,27 @@ __device__ __forceinline__ double signed_wrapped_angle(double cosphi, double sig
 // The reference divides vector by scalar component-wise; here every distinct denominator is
 // inverted once and multiplied through (differs from the reference by rounding only).
 
+// Every J function hands its per-atom blocks to `emit(i, block)` as soon as they exist (i is
+// the atom's position in the InvDisp), so that no more than one block is live at a time.
+
 // stretching :261-272
-template <class S> __device__ __forceinline__ void stretching_J(const V3<S> * a, S & q, V3<S> * J) {
+template <class S, class Emit> __device__ __forceinline__ void stretching_J(const V3<S> * a, S & q, Emit emit) {
     V3<S> r12 = a[1] - a[0];
-    S n = norm(r12);
-    V3<S> u = rcp_(n) * r12;
+    S n, i;
+    norm_inv(r12, n, i);
+    V3<S> u = i * r12;
     q = n;
-    J[0] = -u;
-    J[1] = u;
+    emit(0, -u);
+    emit(1, u);
 }
 
 // bending :273-296 (angle = acos(q_cos)), cosbending :297-316
-template <class S, bool COS> __device__ __forceinline__ void bending_J(const V3<S> * a, S & costheta, V3<S> * J) {
+template <class S, bool COS, class Emit> __device__ __forceinline__ void bending_J(const V3<S> * a, S & costheta, Emit emit) {
     V3<S> r21 = a[0] - a[1];
-    S i21 = rcp_(norm(r21));
+    S i21 = rsqrt_(dot(r21, r21));
     V3<S> u21 = i21 * r21;
     V3<S> r23 = a[2] - a[1];
-    S i23 = rcp_(norm(r23));
+    S i23 = rsqrt_(dot(r23, r23));
     V3<S> u23 = i23 * r23;
     costheta = dot(u21, u23);
     V3<S> J0, J2;
@@ -146,82 +163,87 @@ template <class S, bool COS> __device__ __forceinline__ void bending_J(const V3<
         J0 = i21 * (u23 - costheta * u21);
         J2 = i23 * (u21 - costheta * u23);
     } else {
-        S isin = rcp_(sqrt_(1.0 - costheta * costheta));
+        S isin = rsqrt_(1.0 - costheta * costheta);
         J0 = (isin * i21) * (costheta * u21 - u23);
         J2 = (isin * i23) * (costheta * u23 - u21);
     }
-    J[0] = J0;
-    J[2] = J2;
-    J[1] = -J0 - J2;
+    emit(0, J0);
+    emit(2, J2);
+    emit(1, -J0 - J2);
 }
 
 // torsion :317-354, sintorsion :355-384, costorsion :385-414
 // VAR 0: torsion (J of the angle), 1: sintorsion, 2: costorsion.
 // sinphi / cosphi / sign_test are returned for the caller to form q.
-template <class S, int VAR>
-__device__ __forceinline__ void torsion_J(const V3<S> * a, S & sinphi, S & cosphi, S & sign_test, V3<S> * J) {
+template <class S, int VAR, class Emit>
+__device__ __forceinline__ void torsion_J(const V3<S> * a, S & sinphi, S & cosphi, S & sign_test, Emit emit) {
     V3<S> r12 = a[1] - a[0];
-    S n12 = norm(r12), i12 = rcp_(n12);
+    S n12, i12;
+    norm_inv(r12, n12, i12);
     V3<S> u12 = i12 * r12;
     V3<S> r23 = a[2] - a[1];
-    S n23 = norm(r23), i23 = rcp_(n23);
+    S n23, i23;
+    norm_inv(r23, n23, i23);
     V3<S> u23 = i23 * r23;
     V3<S> r34 = a[3] - a[2];
-    S n34 = norm(r34), i34 = rcp_(n34);
+    S n34, i34;
+    norm_inv(r34, n34, i34);
     V3<S> u34 = i34 * r34;
     S cos123 = -dot(u12, u23);
-    S is123 = rcp_(sqrt_(1.0 - cos123 * cos123));
+    S is123 = rsqrt_(1.0 - cos123 * cos123);
     S cos234 = -dot(u23, u34);
-    S is234 = rcp_(sqrt_(1.0 - cos234 * cos234));
+    S is234 = rsqrt_(1.0 - cos234 * cos234);
     V3<S> n123 = is123 * cross(u12, u23);
     V3<S> n234 = is234 * cross(u23, u34);
     cosphi = dot(n123, n234);
     if (VAR == 0) sign_test = dot(n123, cross(n234, u23));
     if (VAR != 0) sinphi = dot(cross(n123, n234), u23);
+    // common factor of the sin / cos variants: d sin = cos dphi, d cos = -sin dphi
     S a23 = i23 * is123, b23 = i23 * is234;
-    V3<S> J0 = -(i12 * is123) * n123;
-    V3<S> J1 = ((n23 - n12 * cos123) * (i12 * a23)) * n123 - (cos234 * b23) * n234;
-    V3<S> J2 = ((n34 * cos234 - n23) * (i34 * b23)) * n234 + (cos123 * a23) * n123;
-    V3<S> J3 = (i34 * is234) * n234;
-    if (VAR == 1) { J0 = cosphi * J0; J1 = cosphi * J1; J2 = cosphi * J2; J3 = cosphi * J3; }
-    if (VAR == 2) { S m = -sinphi; J0 = m * J0; J1 = m * J1; J2 = m * J2; J3 = m * J3; }
-    J[0] = J0; J[1] = J1; J[2] = J2; J[3] = J3;
+    S w0 = -(i12 * is123), w1a = (n23 - n12 * cos123) * (i12 * a23), w1b = -(cos234 * b23);
+    S w2a = (n34 * cos234 - n23) * (i34 * b23), w2b = cos123 * a23, w3 = i34 * is234;
+    if (VAR == 1) { w0 = cosphi * w0; w1a = cosphi * w1a; w1b = cosphi * w1b; w2a = cosphi * w2a; w2b = cosphi * w2b; w3 = cosphi * w3; }
+    if (VAR == 2) { S m = -sinphi; w0 = m * w0; w1a = m * w1a; w1b = m * w1b; w2a = m * w2a; w2b = m * w2b; w3 = m * w3; }
+    emit(0, w0 * n123);
+    emit(1, w1a * n123 + w1b * n234);
+    emit(2, w2a * n234 + w2b * n123);
+    emit(3, w3 * n234);
 }
 
 // OutOfPlane :571-602 (angle = asin(sintheta)), sinoop :603-631
-template <class S, bool SIN> __device__ __forceinline__ void oop_J(const V3<S> * a, S & sintheta, V3<S> * J) {
+template <class S, bool SIN, class Emit> __device__ __forceinline__ void oop_J(const V3<S> * a, S & sintheta, Emit emit) {
     V3<S> r21 = a[0] - a[1];
-    S i21 = rcp_(norm(r21));
+    S i21 = rsqrt_(dot(r21, r21));
     V3<S> u21 = i21 * r21;
     V3<S> r23 = a[2] - a[1];
-    S i23 = rcp_(norm(r23));
+    S i23 = rsqrt_(dot(r23, r23));
     V3<S> u23 = i23 * r23;
     V3<S> r24 = a[3] - a[1];
-    S i24 = rcp_(norm(r24));
+    S i24 = rsqrt_(dot(r24, r24));
     V3<S> u24 = i24 * r24;
     S cos324 = dot(u23, u24);
     S sin324sq = 1.0 - cos324 * cos324;
-    S is324 = rcp_(sqrt_(sin324sq));
+    S is324 = rsqrt_(sin324sq);
     S is324sq = is324 * is324;
-    sintheta = dot(u23, cross(u24, u21)) * is324;
-    V3<S> J0, J2, J3;
+    V3<S> c41 = cross(u24, u21);
+    sintheta = dot(u23, c41) * is324;
+    S w, t, s1;            // J0 = i21 (w u23 x u24 - s1 u21), J2 = i23 (w u24 x u21 - t (u23 - c u24)), ...
     if (SIN) {
-        S t = sintheta * is324sq;
-        J0 = i21 * (is324 * cross(u23, u24) - sintheta * u21);
-        J2 = i23 * (is324 * cross(u24, u21) - t * (u23 - cos324 * u24));
-        J3 = i24 * (is324 * cross(u21, u23) - t * (u24 - cos324 * u23));
+        w = is324; t = sintheta * is324sq; s1 = sintheta;
     } else {
-        S icos = rcp_(sqrt_(1.0 - sintheta * sintheta));
+        S icos = rsqrt_(1.0 - sintheta * sintheta);
         S tantheta = sintheta * icos;
-        S w = icos * is324, t = tantheta * is324sq;
-        J0 = i21 * (w * cross(u23, u24) - tantheta * u21);
-        J2 = i23 * (w * cross(u24, u21) - t * (u23 - cos324 * u24));
-        J3 = i24 * (w * cross(u21, u23) - t * (u24 - cos324 * u23));
+        w = icos * is324; t = tantheta * is324sq; s1 = tantheta;
     }
-    J[0] = J0;
-    J[2] = J2;
-    J[3] = J3;
-    J[1] = -J0 - J2 - J3;
+    V3<S> J0 = i21 * (w * cross(u23, u24) - s1 * u21);
+    emit(0, J0);
+    V3<S> acc = J0;
+    V3<S> J2 = i23 * (w * c41 - t * (u23 - cos324 * u24));
+    emit(2, J2);
+    acc = acc + J2;
+    V3<S> J3 = i24 * (w * cross(u21, u23) - t * (u24 - cos324 * u23));
+    emit(3, J3);
+    emit(1, -(acc + J3));
 }
 
 // sin / cos of the 5-atom dihedral, source/IC/InvDisp.cpp:419-429 (value expression that the

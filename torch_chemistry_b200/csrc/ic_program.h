@@ -41,19 +41,32 @@ struct ChunkDesc {
     int32_t prim_begin, prim_end;  // range in prims[]
     int32_t row0, nrows;           // rows (internal coordinates) this chunk produces
     int32_t accumulate;            // != 0: add to what an earlier chunk stored (split row)
-    int32_t pad_;
-    int64_t qmap, jmap, kmap;      // offsets into map[]: nrows, nrows*cartdim, nrows*cartdim^2 words
+    int32_t qslot;                 // first of nrows compact entries that hold the combined q rows
+    int64_t qmap;                  // offset into map[]:  nrows words, in row order
+    int64_t jmap, kmap;            // offsets into emap[]: nrows*cartdim and nrows*cartdim^2 entries
 };
 
 // map word: (count << 24) | first source index
 constexpr uint32_t kMapCountShift = 24;
 constexpr uint32_t kMapOffsetMask = 0x00ffffffu;
 
+// One dense output element of a span: its source word and its position in the span. The
+// entries of a span are ordered so that groups of 4 consecutive elements (one 32-byte sector)
+// with similar source counts sit next to each other: a warp step then works on 32 elements
+// that need the same number of gather rounds, and all-zero steps take the store-only path.
+struct ElemMap {
+    uint32_t word;                 // (count << 24) | first source index
+    uint32_t k;                    // element offset inside the span
+};
+
 struct Program {                   // all pointers are device pointers
     const PrimDesc *  prims;
     const ChunkDesc * chunks;
-    const uint32_t *  map;
+    const uint32_t *  map;         // q rows: (count << 24) | first index into qsrcs
+    const Src *       qsrcs;
+    const ElemMap *   emap;        // J / K elements, sources in srcs
     const Src *       srcs;
+    int32_t nqsrcs, nmap;          // sizes of qsrcs[] and map[]
     int32_t nprims, nchunks;
     int32_t cap;                   // compact entries per lane
     int32_t intdim, cartdim;

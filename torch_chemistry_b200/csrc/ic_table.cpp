@@ -34,6 +34,37 @@ PrimKey key_of(const tchem_invdisp_t & t) {
 
 } // namespace
 
+int64_t emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
+                  std::vector<ElemMap> & emap, std::vector<Src> & srcs) {
+    const int64_t S = (int64_t)lists.size();
+    const int64_t off0 = (int64_t)emap.size();
+    const int64_t shift = (gstride % 4 == 0) ? (abs_off % 4) : 0;     // sector phase of element 0
+    struct Unit { int64_t first, last; int maxcnt; };
+    std::vector<Unit> units;
+    for (int64_t k = 0; k < S;) {
+        int64_t end = std::min<int64_t>(S, ((k + shift) / 4 + 1) * 4 - shift);
+        int m = 0;
+        for (int64_t e = k; e < end; e++) m = std::max<int>(m, (int)lists[e].size());
+        units.push_back(Unit{k, end, m});
+        k = end;
+    }
+    // rounds of 4 sources: order by the number of rounds, then by 1 / 2 / 3-4 sources inside the
+    // last round, keeping the address order otherwise
+    auto klass = [](int m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m <= 4 ? 3 : 4 + (m - 1) / 4; };
+    std::stable_sort(units.begin(), units.end(), [&](const Unit & a, const Unit & b) { return klass(a.maxcnt) > klass(b.maxcnt); });
+    for (const Unit & u : units)
+        for (int64_t e = u.first; e < u.last; e++) {
+            const auto & l = lists[e];
+            if (l.size() > 255 || srcs.size() + l.size() > kMapOffsetMask) return -1;
+            ElemMap m;
+            m.word = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)srcs.size());
+            m.k = (uint32_t)e;
+            emap.push_back(m);
+            for (const Src & s : l) srcs.push_back(s);
+        }
+    return off0;
+}
+
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
                   HostProgram & hp) {
     hp = HostProgram();
@@ -56,10 +87,10 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
     int max_prim = 1, max_row = 1;
     for (int i = 0; i < n_ic; i++) {
         std::map<PrimKey, int> seen;
-        int row_entries = 0;
+        int row_entries = 1;           // the row's combined q value
         for (int t : rows[i]) {
             int e = prim_entries(terms[t].natoms, mode);
-            max_prim = std::max(max_prim, e);
+            max_prim = std::max(max_prim, e + 1);
             if (seen.emplace(key_of(terms[t]), 0).second) row_entries += e;
         }
         max_row = std::max(max_row, row_entries);
@@ -84,7 +115,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
         for (int i = 0; i < n_ic; i++) {
             // entries this row would add to the current chunk
             std::map<PrimKey, int> add;
-            int add_entries = 0, alone_entries = 0;
+            int add_entries = 1, alone_entries = 1;      // + the row's q slot
             {
                 std::map<PrimKey, int> alone;
                 for (int t : rows[i]) {
@@ -112,7 +143,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             bool first = true;
             Pending part{i, 1, false, {}};
             std::map<PrimKey, int> part_prims;
-            int part_entries = 0;
+            int part_entries = 1;
             for (int t : rows[i]) {
                 PrimKey k = key_of(terms[t]);
                 int e = part_prims.count(k) ? 0 : prim_entries(terms[t].natoms, mode);
@@ -122,7 +153,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
                     first = false;
                     part = Pending{i, 1, true, {}};
                     part_prims.clear();
-                    part_entries = 0;
+                    part_entries = 1;
                     e = prim_entries(terms[t].natoms, mode);
                 }
                 part_prims.emplace(k, 0);
@@ -158,17 +189,22 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             hp.prims.push_back(pd);
         }
         ch.prim_end = (int)hp.prims.size();
+        ch.qslot = next_entry;
 
         // per-row source lists
         auto emit = [&](std::vector<std::vector<Src>> & lists, int64_t & map_off) {
             map_off = (int64_t)hp.map.size();
             for (auto & l : lists) {
-                if (l.size() > 255 || hp.srcs.size() + l.size() > kMapOffsetMask) return false;
-                uint32_t w = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)hp.srcs.size());
+                if (l.size() > 255 || hp.qsrcs.size() + l.size() > kMapOffsetMask) return false;
+                uint32_t w = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)hp.qsrcs.size());
                 hp.map.push_back(w);
-                for (auto & s : l) hp.srcs.push_back(s);
+                for (auto & s : l) hp.qsrcs.push_back(s);
             }
             return true;
+        };
+        auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, int64_t & map_off) {
+            map_off = emit_span(lists, abs_off, gstride, hp.emap, hp.srcs);
+            return map_off >= 0;
         };
         std::vector<std::vector<Src>> ql(pc.nrows), jl, kl;
         if (mode != MODE_VALUE) jl.resize((size_t)pc.nrows * cd);
@@ -202,8 +238,8 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
                         }
         }
         bool ok = emit(ql, ch.qmap);
-        if (ok && mode != MODE_VALUE) ok = emit(jl, ch.jmap);
-        if (ok && mode == MODE_QJK) ok = emit(kl, ch.kmap);
+        if (ok && mode != MODE_VALUE) ok = emit_sorted(jl, (int64_t)pc.row0 * cd, (int64_t)n_ic * cd, ch.jmap);
+        if (ok && mode == MODE_QJK) ok = emit_sorted(kl, (int64_t)pc.row0 * cd * cd, (int64_t)n_ic * cd * cd, ch.kmap);
         if (!ok) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: internal coordinate definition too large for the gather map");
         hp.chunks.push_back(ch);
     }

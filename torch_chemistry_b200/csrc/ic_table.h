@@ -9,6 +9,7 @@ struct tchem_ic_table {
     int device = 0;
     int intdim = 0, cartdim = 0, natoms = 0;
     int sm_count = 0;
+    bool has5 = false;            // any 5-atom (torsion2 family) term
     int max_smem_optin = 0;
     std::vector<tchem_invdisp_t> terms;
     tchem_b200::Program prog[tchem_b200::MODE_COUNT];       // device pointers
@@ -23,9 +24,17 @@ struct HostProgram {
     std::vector<PrimDesc> prims;
     std::vector<ChunkDesc> chunks;
     std::vector<uint32_t> map;
-    std::vector<Src> srcs;
+    std::vector<ElemMap> emap;
+    std::vector<Src> srcs, qsrcs;
     int cap = 0;
 };
+
+// Appends the element map of one dense span (lists[k] = sources of element k) to emap/srcs and
+// returns its offset, or -1 when a list is too long for the encoding. Elements are grouped in
+// sectors of 4 (aligned to `abs_off`, the span's element offset inside the geometry block, when
+// the block stride keeps sectors aligned) and the sectors are ordered by source count.
+int64_t emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
+                  std::vector<ElemMap> & emap, std::vector<Src> & srcs);
 
 // pure host: flatten terms into a program for one mode
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,

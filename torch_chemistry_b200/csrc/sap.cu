@@ -23,7 +23,7 @@ struct SapProgram {                               // device pointers
     const SapTerm *   terms;
     const SapUniq *   uniqs;
     const ChunkDesc * chunks;                     // prim_begin/end = term range, row0/nrows likewise
-    const uint32_t *  map;
+    const ElemMap *   emap;
     const Src *       srcs;
     int32_t nterms, nuniqs, nchunks, cap, sumdim;
 };
@@ -82,7 +82,7 @@ __device__ __forceinline__ void eval_sap_terms(const SapProgram & sp, int t0, in
 
 // CHAINED: x = q(r) evaluated with the compute_IC_J formulas from the IC program (value-mode
 // chunking, one compact entry per primitive); otherwise x is read from global memory.
-template <bool CHAINED>
+template <bool CHAINED, bool HAS5>
 __global__ void __launch_bounds__(256)
 sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict__ in, const int64_t B,
                 double * __restrict__ q_out, double * __restrict__ y, double * __restrict__ J) {
@@ -104,7 +104,7 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
             stage_coordinates(in, b0, ntile, cartdim, R, lane);
             for (int c = 0; c < ic.nchunks; c++) {
                 const ChunkDesc ch = ic.chunks[c];
-                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH>(pd, R, lane, CompactSink(PI, pd.out, lane)); }
+                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH, HAS5>(pd, R, lane, CompactSink(PI, pd.out, lane)); }
                 // every lane combines its own column: x[row] = sum coef * q_prim (IntCoord.cpp:66-74)
                 for (int row = 0; row < ch.nrows; row++) {
                     const uint32_t w = ic.map[ch.qmap + row];
@@ -112,7 +112,7 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
                     const uint32_t off = w & kMapOffsetMask;
                     double x = 0.0;
                     for (int j = 0; j < cnt; j++) {
-                        const Src s = ic.srcs[off + j];
+                        const Src s = ic.qsrcs[off + j];
                         x = fma(s.coef, PI[s.entry * kPad + lane], x);
                     }
                     double * xp = X + (ch.row0 + row) * kPad + lane;
@@ -132,10 +132,10 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
             eval_sap_terms(sp, ch.prim_begin, ch.prim_end, X, P, lane, J != nullptr);
             __syncwarp();
             if (y != nullptr)
-                gather_store(sp.map + ch.qmap, sp.srcs, ch.nrows, P, y + b0 * sp.nterms + ch.row0, sp.nterms,
+                gather_store(sp.emap + ch.qmap, sp.srcs, ch.nrows, P, y + b0 * sp.nterms + ch.row0, sp.nterms,
                              ntile, false, lane);
             if (J != nullptr)
-                gather_store(sp.map + ch.jmap, sp.srcs, (int64_t)ch.nrows * sumdim, P,
+                gather_store(sp.emap + ch.jmap, sp.srcs, (int64_t)ch.nrows * sumdim, P,
                              J + (b0 * sp.nterms + ch.row0) * sumdim, (int64_t)sp.nterms * sumdim, ntile, false, lane);
             __syncwarp();
         }
@@ -145,8 +145,9 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
 int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const double * in, int64_t B,
                double * q_out, double * y, double * J, cudaStream_t stream) {
     const bool chained = ict != nullptr;
-    const void * fn = chained ? reinterpret_cast<const void *>(&sap_eval_kernel<true>)
-                              : reinterpret_cast<const void *>(&sap_eval_kernel<false>);
+    const void * fn = !chained ? reinterpret_cast<const void *>(&sap_eval_kernel<false, false>)
+                    : ict->has5 ? reinterpret_cast<const void *>(&sap_eval_kernel<true, true>)
+                                : reinterpret_cast<const void *>(&sap_eval_kernel<true, false>);
     Program icp;
     std::memset(&icp, 0, sizeof(icp));
     if (chained) icp = ict->prog[MODE_VALUE];
@@ -210,7 +211,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     const int total_entries = n_terms + (int)uniqs.size();
     const int cap = std::max(max_term, std::min(total_entries, 64));
     std::vector<ChunkDesc> chunks;
-    std::vector<uint32_t> map;
+    std::vector<ElemMap> map;
     std::vector<Src> srcs;
     for (int t0 = 0; t0 < n_terms;) {
         int t1 = t0, entries = 0;
@@ -221,22 +222,16 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
         ChunkDesc ch;
         std::memset(&ch, 0, sizeof(ch));
         ch.prim_begin = t0; ch.prim_end = t1; ch.row0 = t0; ch.nrows = t1 - t0;
-        ch.qmap = (int64_t)map.size();
-        for (int t = t0; t < t1; t++) {
-            map.push_back((1u << kMapCountShift) | (uint32_t)srcs.size());
-            srcs.push_back(Src{t - t0, 0, 1.0});
-        }
-        ch.jmap = (int64_t)map.size();
+        std::vector<std::vector<Src>> yl(t1 - t0), jl((size_t)(t1 - t0) * sumdim);
         const int first = terms[t0].ubegin;
         for (int t = t0; t < t1; t++) {
-            std::vector<uint32_t> row(sumdim, 0u);
-            for (int u = terms[t].ubegin; u < terms[t].uend; u++) {
-                row[uniqs[u].col] = (1u << kMapCountShift) | (uint32_t)srcs.size();
-                srcs.push_back(Src{(t1 - t0) + (u - first), 0, 1.0});
-            }
-            map.insert(map.end(), row.begin(), row.end());
+            yl[t - t0].push_back(Src{t - t0, 0, 1.0});
+            for (int u = terms[t].ubegin; u < terms[t].uend; u++)
+                jl[(size_t)(t - t0) * sumdim + uniqs[u].col].push_back(Src{(t1 - t0) + (u - first), 0, 1.0});
         }
-        if (srcs.size() > kMapOffsetMask) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
+        ch.qmap = emit_span(yl, t0, n_terms, map, srcs);
+        ch.jmap = emit_span(jl, (int64_t)t0 * sumdim, (int64_t)n_terms * sumdim, map, srcs);
+        if (ch.qmap < 0 || ch.jmap < 0) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
         chunks.push_back(ch);
         t0 = t1;
     }
@@ -247,13 +242,13 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     const size_t o_terms = 0, o_uniqs = o_terms + a16(terms.size() * sizeof(SapTerm));
     const size_t o_chunks = o_uniqs + a16(uniqs.size() * sizeof(SapUniq) + 8);
     const size_t o_map = o_chunks + a16(chunks.size() * sizeof(ChunkDesc));
-    const size_t o_srcs = o_map + a16(map.size() * sizeof(uint32_t));
+    const size_t o_srcs = o_map + a16(map.size() * sizeof(ElemMap));
     const size_t total = o_srcs + a16(srcs.size() * sizeof(Src)) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SapTerm));
     std::memcpy(blob.data() + o_uniqs, uniqs.data(), uniqs.size() * sizeof(SapUniq));
     std::memcpy(blob.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
-    std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(ElemMap));
     std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(Src));
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
@@ -270,7 +265,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     t->prog.terms = reinterpret_cast<const SapTerm *>(d + o_terms);
     t->prog.uniqs = reinterpret_cast<const SapUniq *>(d + o_uniqs);
     t->prog.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
-    t->prog.map = reinterpret_cast<const uint32_t *>(d + o_map);
+    t->prog.emap = reinterpret_cast<const ElemMap *>(d + o_map);
     t->prog.srcs = reinterpret_cast<const Src *>(d + o_srcs);
     t->prog.nterms = n_terms; t->prog.nuniqs = (int)uniqs.size(); t->prog.nchunks = (int)chunks.size();
     t->prog.cap = cap; t->prog.sumdim = sumdim;
