@@ -56,15 +56,24 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
     const int64_t ntiles = (B + kLanes - 1) / kLanes;
     const int64_t jstride = (int64_t)intdim * cartdim, kstride = jstride * cartdim;
 
-    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t tile_step = (int64_t)gridDim.x * nwarps;
+    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+    if (tile < ntiles) stage_issue(r, tile * kLanes, (int)min((int64_t)kLanes, B - tile * kLanes), cartdim, R, lane);
+    for (; tile < ntiles; tile += tile_step) {
         const int64_t b0 = tile * kLanes;
         const int ntile = (int)min((int64_t)kLanes, B - b0);
-        stage_coordinates(r, b0, ntile, cartdim, R, lane);
+        stage_finish(ntile, cartdim, R, lane);
         for (int c = 0; c < prog.nchunks; c++) {
             const ChunkDesc ch = chunks[c];
             eval_chunk<MODE, HAS5>(prims, ch.prim_begin, ch.prim_end, R, P, lane);
             if (q != nullptr) combine_rows(qmap + ch.qmap, qsrcs, ch.nrows, P, ch.qslot, lane);
             __syncwarp();
+            // R is dead after the last chunk's arithmetic: start fetching the next tile now, its
+            // DRAM latency hides behind this tile's remaining stores
+            if (c == prog.nchunks - 1 && tile + tile_step < ntiles) {
+                const int64_t nb0 = (tile + tile_step) * kLanes;
+                stage_issue(r, nb0, (int)min((int64_t)kLanes, B - nb0), cartdim, R, lane);
+            }
             if (q != nullptr)
                 store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
             if (MODE != MODE_VALUE && J != nullptr)

@@ -14,23 +14,36 @@ constexpr unsigned kFull = 0xffffffffu;
 // stage the tile's Cartesian coordinates: global r[b0 .. b0+ntile)[cartdim] (contiguous,
 // coalesced reads) -> R[c * kPad + lane]. Lanes >= ntile get a copy of the last valid
 // geometry so that the arithmetic below never sees garbage.
+// The copy is asynchronous (cp.async, 8 bytes per element straight into the transposed shared
+// layout): stage_issue() can be called for the NEXT tile as soon as the current tile no longer
+// reads R, so that the DRAM latency hides behind the current tile's gather phase.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_coordinates(const double * __restrict__ r, int64_t b0, int ntile,
-                                                  int cartdim, double * R, int lane) {
+__device__ __forceinline__ void stage_issue(const double * __restrict__ r, int64_t b0, int ntile,
+                                            int cartdim, double * R, int lane) {
     const double * src = r + b0 * cartdim;
     const int total = ntile * cartdim;
     // running (geometry, coordinate) of flat element f = lane + 32 j, no division in the loop
     int g = lane / cartdim, c = lane - g * cartdim;
     const int dg = kLanes / cartdim, dc = kLanes - dg * cartdim;
     for (int f = lane; f < total; f += kLanes) {
-        R[c * kPad + g] = __ldcs(src + f);      // streamed once: keep it out of the way of the tables
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(R + c * kPad + g);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + f) : "memory");
         g += dg; c += dc;
         if (c >= cartdim) { c -= cartdim; g++; }
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void stage_finish(int ntile, int cartdim, double * R, int lane) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncwarp();
     if (ntile < kLanes && lane >= ntile)
         for (int k = 0; k < cartdim; k++) R[k * kPad + lane] = R[k * kPad + ntile - 1];
     __syncwarp();
+}
+__device__ __forceinline__ void stage_coordinates(const double * __restrict__ r, int64_t b0, int ntile,
+                                                  int cartdim, double * R, int lane) {
+    stage_issue(r, b0, ntile, cartdim, R, lane);
+    stage_finish(ntile, cartdim, R, lane);
 }
 
 __device__ __forceinline__ V3<double> load_atom(const double * R, int atom, int lane) {
@@ -299,8 +312,8 @@ __device__ __forceinline__ ElemMap load_emap(const ElemMap * p) {
 }
 
 template <int NS, bool FULL, bool ACC>
-__device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const double * P,
-                                             char * o, uint32_t gbytes, int ntile) {
+__device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const Src & first,
+                                             const double * P, char * o, uint32_t gbytes, int ntile) {
     double c[NS];
     const double * p[NS];
 #pragma unroll
@@ -308,37 +321,48 @@ __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint
         c[j] = 0.0;
         p[j] = P;
         if (j < cnt) {
-            const Src s = load_src(srcs + off + j);
+            const Src s = j == 0 ? first : load_src(srcs + off + j);
             c[j] = s.coef;
             p[j] = P + s.entry * kPad;
         }
     }
     const int n = FULL ? kLanes : ntile;
-#pragma unroll 4
+#pragma unroll 8
     for (int g = 0; g < n; g++) {
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; j++)
             if (j < cnt) v = fma(c[j], p[j][g], v);
-        double * og = reinterpret_cast<double *>(o + (size_t)((uint32_t)g * gbytes));
+        double * og = reinterpret_cast<double *>(o);
         if (ACC) v += *og;
         *og = v;
+        o += gbytes;
     }
 }
 
-// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host),
-// so every store address is one 32x32+64 multiply-add away from the element's base pointer
+// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host).
+// Table reads are software-pipelined: while step s runs, the element word of step s+1 and its
+// first source are already in flight (the further sources of an element share its cache line).
 template <bool FULL, bool ACC>
 __device__ __forceinline__ void gather_store_impl(const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
-                                               int64_t S, const double * P, double * out, uint32_t gbytes,
-                                               int ntile, int lane) {
+                                                  int64_t S, const double * P, double * out, uint32_t gbytes,
+                                                  int ntile, int lane) {
     ElemMap next;
+    Src next_src;
     next.word = 0u; next.k = 0u;
-    if (lane < S) next = load_emap(emap + lane);
+    next_src.entry = 0; next_src.pad_ = 0; next_src.coef = 0.0;
+    if (lane < S) {
+        next = load_emap(emap + lane);
+        if (next.word) next_src = load_src(srcs + (next.word & kMapOffsetMask));
+    }
     for (int64_t k0 = 0; k0 < S; k0 += kLanes) {
         const bool valid = k0 + lane < S;
         const ElemMap m = next;
-        if (k0 + kLanes + lane < S) next = load_emap(emap + k0 + kLanes + lane);
+        const Src first = next_src;
+        if (k0 + kLanes + lane < S) {
+            next = load_emap(emap + k0 + kLanes + lane);
+            if (next.word) next_src = load_src(srcs + (next.word & kMapOffsetMask));
+        }
         const int cnt = (int)(m.word >> kMapCountShift);
         const uint32_t off = m.word & kMapOffsetMask;
         char * o = reinterpret_cast<char *>(out + m.k);
@@ -346,19 +370,23 @@ __device__ __forceinline__ void gather_store_impl(const ElemMap * __restrict__ e
         if (maxcnt == 0) {
             if (valid && !ACC) {
                 const int n = FULL ? kLanes : ntile;
-#pragma unroll 4
-                for (int g = 0; g < n; g++) *reinterpret_cast<double *>(o + (size_t)((uint32_t)g * gbytes)) = 0.0;
+#pragma unroll 8
+                for (int g = 0; g < n; g++) { *reinterpret_cast<double *>(o) = 0.0; o += gbytes; }
             }
             continue;
         }
         if (!valid) continue;
         {   // first round
-            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
-            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
-            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, P, o, gbytes, ntile);
+            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
+            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
+            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
         }
-        for (int base = 4; base < maxcnt; base += 4)       // rare: more than 4 sources
-            gather_round<4, FULL, true>(srcs, off + base, cnt - base, P, o, gbytes, ntile);
+        for (int base = 4; base < maxcnt; base += 4) {     // rare: more than 4 sources
+            Src f2;
+            f2.entry = 0; f2.pad_ = 0; f2.coef = 0.0;
+            if (cnt > base) f2 = load_src(srcs + off + base);
+            gather_round<4, FULL, true>(srcs, off + base, cnt - base, f2, P, o, gbytes, ntile);
+        }
     }
 }
 
