@@ -140,6 +140,11 @@ TCHEM_API int tchem_ic_hess_cart2int(const tchem_ic_table * t, const double * r,
                            const double * cartHess, int64_t B, double * intHess,
                            tchem_stream_t stream);
 
+/* The cart2int entry points factor J J^T per geometry. Returns 1 (and clears the flag) when any
+ * factorisation since the last call met a non-positive pivot - redundant or singular internal
+ * coordinates, where the reference's at::cholesky throws - else 0. Synchronises the device. */
+TCHEM_API int tchem_ic_factor_status(const tchem_ic_table * t);
+
 /* ---- SAPSet ---------------------------------------------------------------------------- */
 /* x[B][sumdim] holds the per-irreducible vectors xs[0], xs[1], ... concatenated.
  * y[B][nterms]          = SAPSet::operator()(xs),      source/polynomial/SAPSet.cpp:134-144

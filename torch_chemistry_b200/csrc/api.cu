@@ -20,6 +20,7 @@ int set_error(int code, const std::string & msg) { g_error = msg; return code; }
 void count_launch(int n) { g_launches += n; }
 
 void release_grad_program(const tchem_ic_table * t);
+void release_dense_program(const tchem_ic_table * t);
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
                    double * q, double * J, double * K, cudaStream_t stream);
 
@@ -158,6 +159,7 @@ void tchem_ic_table_destroy(tchem_ic_table * t) {
         DeviceGuard guard(t->device);
         for (int m = 0; m < MODE_COUNT; m++) cudaFree(t->dev_blob[m]);
         release_grad_program(t);
+        release_dense_program(t);
         if (t->pipe) { t->pipe->release(); delete t->pipe; }
     }
     delete t;

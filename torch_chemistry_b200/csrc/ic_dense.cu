@@ -1,20 +1,522 @@
-// placeholder: dense per-geometry transforms (cart2int gradient, Hessians) - implemented next
+// Dense per-geometry transforms: one thread block owns one geometry at a time, J (and the
+// other operands) live in shared memory, the contractions run on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64 = DMMA).
+//
+// Replaces, batched (reference source/IC/IntCoordSet.cpp):
+//   gradient_cart2int_matrix :178-188   M   = (J J^T)^-1 J
+//   gradient_cart2int        :190-205   g_q = M g_r
+//   Hessian_int2cart         :248-266   H_r = J^T H_q J + sum_k g_q[k] K[k]
+//   Hessian_cart2int         :221-246   H_q = A^T H_r A - sum_k (A^T g_r)[k] A^T K[k] A,  A^T = M
+// K (intdim x cartdim x cartdim per geometry) is never materialised: the second-derivative
+// blocks of every term are formed in registers (Dual passes through the analytic J expression,
+// what the reference asks autograd for at source/IC/InvDisp.cpp:859-868) and added, weighted by
+// g_q[k] * coeff, straight into the cartdim x cartdim accumulator. Hessian_cart2int uses
+//   sum_k g_k A^T K_k A = A^T (sum_k g_k K_k) A
+// instead of the reference's intdim separate triple products.
+// (J J^T)^-1 follows the reference's algorithm - Cholesky factor, explicit inverse of the
+// factor, L^-T L^-1 (LAPACK potrf + potri behind at::cholesky / at::cholesky_inverse) - because a
+// mathematically equivalent solve already differs from it by ~cond * eps.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "ic_eval.cuh"
 #include "ic_table.h"
+
+namespace tchem_b200 {
+
+struct DenseTerm {
+    PrimDesc pd;       // pd.out = internal coordinate (row) of the term
+    double coef;
+};
+struct DenseTask { int32_t term, dir; };
+struct DenseProgram {                 // device pointers
+    const DenseTerm * terms;
+    const int32_t *   row_ptr;        // CSR over rows
+    const DenseTask * tasks;          // (term, Cartesian direction) pairs for the K passes
+    int32_t nterms, ntasks, intdim, cartdim;
+    int32_t ldj, ldh;                 // leading dimensions: width >= cartdim / intdim, = 4 or 12 mod 16
+};
+
+namespace {
+
+constexpr int kDenseThreads = 256;
+
+// ---------------------------------------------------------------------------------------
+// DMMA: D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragments (PTX ISA, mma.m8n8k4 .f64):
+//   a : row = lane >> 2, col = lane & 3          b : row = lane & 3, col = lane >> 2
+//   c0, c1 : row = lane >> 2, col = 2 * (lane & 3) + {0, 1}
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double & d0, double & d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C[M x N] = (ACC ? C : 0) + s * opA(A)[M x K] * opB(B)[K x N], all operands in shared memory.
+//   TA: A is stored K x M (opA(A)[m][k] = A[k * lda + m]);  TB: B is stored N x K.
+// Each warp owns 16 x 16 tiles of C (2 x 2 DMMA tiles). Leading dimensions = 4 or 12 (mod 16)
+// keep both fragment access patterns free of bank conflicts.
+template <bool TA, bool TB, bool ACC>
+__device__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
+                            double * C, int ldc, double s = 1.0) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int tm = (M + 15) / 16, tn = (N + 15) / 16;
+    for (int t = warp; t < tm * tn; t += nwarps) {
+        const int m0 = (t / tn) * 16, n0 = (t % tn) * 16;
+        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        const bool full = m0 + 16 <= M && n0 + 16 <= N && (K & 3) == 0;
+        if (full) {
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                double a[2], b[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int m = m0 + 8 * i + gid, k = k0 + tig;
+                    a[i] = TA ? A[k * lda + m] : A[m * lda + k];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int n = n0 + 8 * j + gid, k = k0 + tig;
+                    b[j] = TB ? B[n * ldb + k] : B[k * ldb + n];
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        } else {
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                double a[2], b[2];
+                const int k = k0 + tig;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int m = m0 + 8 * i + gid;
+                    a[i] = (m < M && k < K) ? (TA ? A[k * lda + m] : A[m * lda + k]) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int n = n0 + 8 * j + gid;
+                    b[j] = (n < N && k < K) ? (TB ? B[n * ldb + k] : B[k * ldb + n]) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int m = m0 + 8 * i + gid, n = n0 + 8 * j + 2 * tig;
+                if (m < M) {
+                    if (n < N)     C[m * ldc + n]     = (ACC ? C[m * ldc + n] : 0.0) + s * acc[i][j][0];
+                    if (n + 1 < N) C[m * ldc + n + 1] = (ACC ? C[m * ldc + n + 1] : 0.0) + s * acc[i][j][1];
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sinks of the per-term evaluation
+// ---------------------------------------------------------------------------------------
+struct RowSink {                       // J[row][.] += coef * J_term   (row owned by one thread)
+    double * row;
+    double coef;
+    __device__ __forceinline__ void value(double) const {}
+    __device__ __forceinline__ void jac_block(const int * atoms, int i, const V3<double> & J) const {
+        double * p = row + 3 * atoms[i];
+        p[0] = fma(coef, J.x, p[0]);
+        p[1] = fma(coef, J.y, p[1]);
+        p[2] = fma(coef, J.z, p[2]);
+    }
+    __device__ __forceinline__ void jac_entry(const int * atoms, int m, double j) const {
+        const int a = m / 3;
+        double * p = row + 3 * atoms[a] + (m - 3 * a);
+        p[0] = fma(coef, j, p[0]);
+    }
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int, int, const V3<Dual> &) const {}
+    __device__ __forceinline__ void hess_entry5(const int *, int, int, double) const {}
+};
+
+struct HessSink {                      // H[.][.] += w * K_term   (shared accumulator, atomics)
+    double * H;
+    int ld;
+    double w;
+    __device__ __forceinline__ void value(double) const {}
+    __device__ __forceinline__ void jac_block(const int *, int, const V3<double> &) const {}
+    __device__ __forceinline__ void jac_entry(const int *, int, double) const {}
+    __device__ __forceinline__ void add(int r, int c, double v, bool mirror) const {
+        atomicAdd(H + r * ld + c, v);
+        if (mirror) atomicAdd(H + c * ld + r, v);
+    }
+    // tangent direction (atom j, component l) of block i: entry (k, l) of block (i, j), i <= j,
+    // mirrored into block (j, i) like source/IC/InvDisp.cpp:869-876
+    template <int N> __device__ __forceinline__ void hess_block(const int * atoms, int dir, int i, const V3<Dual> & J) const {
+        const int j = dir / 3, l = dir - 3 * j;
+        if (i > j) return;
+        const int r = 3 * atoms[i], c = 3 * atoms[j] + l;
+        add(r, c, w * J.x.d, i < j);
+        add(r + 1, c, w * J.y.d, i < j);
+        add(r + 2, c, w * J.z.d, i < j);
+    }
+    __device__ __forceinline__ void hess_entry5(const int * atoms, int m1, int m2, double k) const {
+        const int a1 = m1 / 3, a2 = m2 / 3;
+        add(3 * atoms[a1] + (m1 - 3 * a1), 3 * atoms[a2] + (m2 - 3 * a2), w * k, m1 != m2);
+    }
+};
+
+// J[intdim][ldj] of the block's geometry: zero, then one thread per internal coordinate adds its
+// terms (source/IC/IntCoord.cpp:62-76)
+template <bool HAS5>
+__device__ void block_compute_J(const DenseProgram & dp, const double * rg, double * J) {
+    for (int i = threadIdx.x; i < dp.intdim * dp.ldj; i += blockDim.x) J[i] = 0.0;
+    __syncthreads();
+    for (int row = threadIdx.x; row < dp.intdim; row += blockDim.x) {
+        RowSink sink;
+        sink.row = J + row * dp.ldj;
+        for (int t = dp.row_ptr[row]; t < dp.row_ptr[row + 1]; t++) {
+            sink.coef = dp.terms[t].coef;
+            eval_primitive<MODE_QJ, HAS5>(dp.terms[t].pd, GeomLoader{rg}, sink);
+        }
+    }
+    __syncthreads();
+}
+
+// H[cartdim][ld] += sum over terms of weight[row] * coef * K_term, one (term, direction) per thread
+template <bool HAS5>
+__device__ void block_add_gK(const DenseProgram & dp, const double * rg, const double * weight, double sign,
+                             double * H, int ld) {
+    for (int k = threadIdx.x; k < dp.ntasks; k += blockDim.x) {
+        const DenseTask task = dp.tasks[k];
+        const DenseTerm & term = dp.terms[task.term];
+        HessSink sink;
+        sink.H = H; sink.ld = ld;
+        sink.w = sign * weight[term.pd.out] * term.coef;
+        eval_primitive<MODE_KDIR, HAS5>(term.pd, GeomLoader{rg}, sink, task.dir, task.dir + 1);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void block_load(const double * __restrict__ g, double * s, int rows, int cols, int ld) {
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        s[r * ld + c] = __ldcs(g + i);
+    }
+}
+__device__ __forceinline__ void block_store(const double * s, double * __restrict__ g, int rows, int cols, int ld) {
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        __stcs(g + i, s[r * ld + c]);
+    }
+}
+
+// In-place lower Cholesky factor of the n x n matrix A (lda), then Linv = L^-1 (lower) into W and
+// A <- Linv^T Linv = (L L^T)^-1 (full symmetric), i.e. potrf + trtri + lauum.
+// Returns false (all threads) when a pivot is not positive.
+__device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int j = 0; j < n; j++) {
+        // column j: A[j][j] <- sqrt, A[i][j] <- A[i][j] / A[j][j]
+        const double d = A[j * lda + j];
+        __syncthreads();
+        if (!(d > 0.0)) { if (threadIdx.x == 0) bad = 1; break; }
+        const double sd = sqrt(d), isd = 1.0 / sd;
+        for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i * lda + j] = (i == j) ? sd : A[i * lda + j] * isd;
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][k] -= A[i][j] * A[k][j], j < k <= i
+        const int m = n - j - 1;
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = j + 1 + e / m, k = j + 1 + e % m;
+            if (k <= i) A[i * lda + k] -= A[i * lda + j] * A[k * lda + j];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (bad) return false;
+    // Linv: column c solves L x = e_c by forward substitution, one column per thread
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        for (int i = 0; i < c; i++) W[i * ldw + c] = 0.0;
+        W[c * ldw + c] = 1.0 / A[c * lda + c];
+        for (int i = c + 1; i < n; i++) {
+            double s = 0.0;
+            for (int k = c; k < i; k++) s = fma(A[i * lda + k], W[k * ldw + c], s);
+            W[i * ldw + c] = -s / A[i * lda + i];
+        }
+    }
+    __syncthreads();
+    // A <- W^T W
+    block_dgemm<true, false, false>(n, n, n, W, ldw, W, ldw, A, lda);
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory plan (in doubles). Regions:  rg | v1 | v2 | M | ARENA
+// ---------------------------------------------------------------------------------------
+struct DensePlan {
+    int rg, v1, v2, M, arena, total;
+};
+__host__ __device__ inline int even(int x) { return (x + 1) & ~1; }
+__host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, int ldh) {
+    DensePlan p;
+    p.rg = 0;
+    p.v1 = p.rg + even(cd);
+    p.v2 = p.v1 + even(cd > n ? cd : n);
+    p.M = p.v2 + even(cd > n ? cd : n);
+    const int szJ = n * ldj, szA = n * ldh, szH = cd * ldj, szT2 = cd * ldh;
+    int arena = 0;
+    switch (op) {
+    case 0: case 1: p.arena = p.M + szJ; arena = szJ + szA; break;                         // M | J, A (W = M region)
+    case 2: p.arena = p.M + szJ; arena = szJ + (szA > szH ? szA : szH); break;            // J | T, Hq/Hacc
+    default: p.arena = p.M + szJ; arena = (szJ + szA > szH + szT2) ? szJ + szA : szH + szT2; break;
+    }
+    p.total = p.arena + arena;
+    return p;
+}
+
+// OP 0: gradient_cart2int_matrix   out = M[n][cd]
+// OP 1: gradient_cart2int          in1 = g_r[cd]                       out = g_q[n]
+// OP 2: Hessian_int2cart           in1 = g_q[n],  in2 = H_q[n][n]      out = H_r[cd][cd]
+// OP 3: Hessian_cart2int           in1 = g_r[cd], in2 = H_r[cd][cd]    out = H_q[n][n]
+template <int OP, bool HAS5>
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double * __restrict__ in1,
+             const double * __restrict__ in2, const int64_t B, double * __restrict__ out, int * __restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = dp.intdim, cd = dp.cartdim, ldj = dp.ldj, ldh = dp.ldh;
+    const DensePlan pl = dense_plan(OP, n, cd, ldj, ldh);
+    double * rg = sm + pl.rg, * v1 = sm + pl.v1, * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int i = threadIdx.x; i < cd; i += blockDim.x) rg[i] = r[b * cd + i];
+        __syncthreads();
+
+        if (OP == 2) {
+            double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
+            for (int i = threadIdx.x; i < n; i += blockDim.x) v1[i] = in1[b * n + i];
+            block_load(in2 + b * (int64_t)n * n, X, n, n, ldh);
+            block_compute_J<HAS5>(dp, rg, J);                             // syncs
+            block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj);      // T = H_q J
+            __syncthreads();
+            for (int i = threadIdx.x; i < cd * ldj; i += blockDim.x) X[i] = 0.0;
+            __syncthreads();
+            block_add_gK<HAS5>(dp, rg, v1, 1.0, X, ldj);                  // X = sum_k g_q[k] K[k]
+            block_dgemm<true, false, true>(cd, cd, n, J, ldj, T, ldj, X, ldj);       // X += J^T T
+            __syncthreads();
+            block_store(X, out + b * (int64_t)cd * cd, cd, cd, ldj);
+            __syncthreads();
+            continue;
+        }
+
+        // OP 0, 1, 3 start with M = (J J^T)^-1 J
+        double * J = arena, * A = arena + n * ldj, * W = Mreg;           // W (n x n, ldh) borrows the M region
+        block_compute_J<HAS5>(dp, rg, J);
+        block_dgemm<false, true, false>(n, n, cd, J, ldj, J, ldj, A, ldh);           // A = J J^T
+        __syncthreads();
+        const bool ok = block_spd_inverse(n, A, ldh, W, ldh);                        // A = (J J^T)^-1
+        if (!ok && threadIdx.x == 0) atomicExch(status, 1);
+        if (OP == 1) {
+            // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203)
+            for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
+            __syncthreads();
+            block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj);   // M = inv J
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double s = 0.0;
+                for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
+                out[b * n + i] = s;
+            }
+            __syncthreads();
+            continue;
+        }
+        block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj);       // M = inv J
+        __syncthreads();
+        if (OP == 0) {
+            block_store(Mreg, out + b * (int64_t)n * cd, n, cd, ldj);
+            __syncthreads();
+            continue;
+        }
+        // OP 3: H_q = M (H_r - sum_k g_q[k] K[k]) M^T,  g_q = M g_r
+        double * Hc = arena, * T2 = arena + cd * ldj;                    // J and A are dead now
+        for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double s = 0.0;
+            for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
+            v2[i] = s;
+        }
+        block_load(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj);
+        __syncthreads();
+        block_add_gK<HAS5>(dp, rg, v2, -1.0, Hc, ldj);                   // Hc = H_r - sum g_q K
+        block_dgemm<false, true, false>(cd, n, cd, Hc, ldj, Mreg, ldj, T2, ldh);     // T2 = Hc M^T
+        __syncthreads();
+        block_dgemm<false, false, false>(n, n, cd, Mreg, ldj, T2, ldh, Hc, ldh);     // H_q = M T2 (into Hc, ld = ldh)
+        __syncthreads();
+        block_store(Hc, out + b * (int64_t)n * n, n, n, ldh);
+        __syncthreads();
+    }
+}
+
+struct DenseTable {
+    DenseProgram prog;
+    void * blob = nullptr;
+    int * status = nullptr;
+};
+std::map<const tchem_ic_table *, DenseTable> & dense_tables() {
+    static std::map<const tchem_ic_table *, DenseTable> m;
+    return m;
+}
+std::mutex & dense_mutex() { static std::mutex m; return m; }
+
+int pick_ld(int width) {      // smallest ld >= width with ld = 4 or 12 (mod 16)
+    int ld = width;
+    while ((ld & 15) != 4 && (ld & 15) != 12) ld++;
+    return ld;
+}
+
+int get_dense(const tchem_ic_table * t, DenseTable & out) {
+    std::lock_guard<std::mutex> lock(dense_mutex());
+    auto it = dense_tables().find(t);
+    if (it != dense_tables().end()) { out = it->second; return TCHEM_OK; }
+    std::vector<std::vector<int>> rows(t->intdim);
+    for (size_t k = 0; k < t->terms.size(); k++) rows[t->terms[k].ic].push_back((int)k);
+    std::vector<DenseTerm> terms;
+    std::vector<int32_t> row_ptr(1, 0);
+    std::vector<DenseTask> tasks;
+    for (int i = 0; i < t->intdim; i++) {
+        for (int k : rows[i]) {
+            const auto & d = t->terms[k];
+            DenseTerm dt;
+            std::memset(&dt, 0, sizeof(dt));
+            dt.pd.type = d.type; dt.pd.natoms = d.natoms;
+            for (int a = 0; a < 5; a++) dt.pd.atoms[a] = a < d.natoms ? d.atoms[a] : 0;
+            dt.pd.out = i;
+            dt.pd.min = d.min;
+            dt.coef = d.coeff;
+            for (int dir = 0; dir < 3 * d.natoms; dir++) tasks.push_back(DenseTask{(int32_t)terms.size(), dir});
+            terms.push_back(dt);
+        }
+        row_ptr.push_back((int32_t)terms.size());
+    }
+    // heavier tasks first (torsions before bends before stretches) so the tail of the task loop is short
+    std::stable_sort(tasks.begin(), tasks.end(), [&](const DenseTask & a, const DenseTask & b) {
+        return terms[a.term].pd.natoms > terms[b.term].pd.natoms;
+    });
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    const size_t o_t = 0, o_r = a16(terms.size() * sizeof(DenseTerm)), o_k = o_r + a16(row_ptr.size() * 4);
+    const size_t total = o_k + a16(tasks.size() * sizeof(DenseTask)) + 16;
+    std::vector<unsigned char> blob(total, 0);
+    std::memcpy(blob.data() + o_t, terms.data(), terms.size() * sizeof(DenseTerm));
+    std::memcpy(blob.data() + o_r, row_ptr.data(), row_ptr.size() * 4);
+    std::memcpy(blob.data() + o_k, tasks.data(), tasks.size() * sizeof(DenseTask));
+    void * dev = nullptr;
+    TC_CUDA(cudaMalloc(&dev, total));
+    cudaError_t e = cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); return set_error(TCHEM_ECUDA, cudaGetErrorString(e)); }
+    DenseTable dt;
+    dt.blob = dev;
+    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&dt.status), sizeof(int)));
+    TC_CUDA(cudaMemset(dt.status, 0, sizeof(int)));
+    unsigned char * d = static_cast<unsigned char *>(dev);
+    dt.prog.terms = reinterpret_cast<const DenseTerm *>(d + o_t);
+    dt.prog.row_ptr = reinterpret_cast<const int32_t *>(d + o_r);
+    dt.prog.tasks = reinterpret_cast<const DenseTask *>(d + o_k);
+    dt.prog.nterms = (int)terms.size();
+    dt.prog.ntasks = (int)tasks.size();
+    dt.prog.intdim = t->intdim;
+    dt.prog.cartdim = t->cartdim;
+    dt.prog.ldj = pick_ld(t->cartdim);
+    dt.prog.ldh = pick_ld(t->intdim);
+    dense_tables()[t] = dt;
+    out = dt;
+    return TCHEM_OK;
+}
+
+template <int OP> const void * dense_fn(bool has5) {
+    return has5 ? reinterpret_cast<const void *>(&dense_kernel<OP, true>) : reinterpret_cast<const void *>(&dense_kernel<OP, false>);
+}
+
+int launch_dense(int op, const char * who, const tchem_ic_table * t, const double * r, const double * in1,
+                 const double * in2, int64_t B, double * out, cudaStream_t stream) {
+    const std::string name = std::string("tchem::IC::IntCoordSet::") + who;
+    if (!t) return set_error(TCHEM_EINVAL, name + ": null table");
+    if (B < 0) return set_error(TCHEM_EINVAL, name + ": negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!r || !out || (op >= 1 && !in1) || (op >= 2 && !in2)) return set_error(TCHEM_EINVAL, name + ": null argument");
+    if (op != 2 && t->intdim > t->cartdim)
+        return set_error(TCHEM_EINVAL, name + ": more internal coordinates than Cartesian coordinates (J J^T is singular)");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    DenseTable dt;
+    int rc = get_dense(t, dt);
+    if (rc != TCHEM_OK) return rc;
+    const void * fn = op == 0 ? dense_fn<0>(t->has5) : op == 1 ? dense_fn<1>(t->has5) : op == 2 ? dense_fn<2>(t->has5) : dense_fn<3>(t->has5);
+    const DensePlan pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh);
+    const size_t smem = (size_t)pl.total * sizeof(double);
+    if (smem > (size_t)t->max_smem_optin)
+        return set_error(TCHEM_EINVAL, name + ": molecule too large for the per-geometry shared-memory plan");
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::min<int64_t>(B, (int64_t)t->sm_count * per_sm);
+    void * args[] = {(void *)&dt.prog, (void *)&r, (void *)&in1, (void *)&in2, (void *)&B, (void *)&out, (void *)&dt.status};
+    TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kDenseThreads), args, smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
+} // namespace
+
+void release_dense_program(const tchem_ic_table * t) {
+    std::lock_guard<std::mutex> lock(dense_mutex());
+    auto it = dense_tables().find(t);
+    if (it != dense_tables().end()) { cudaFree(it->second.blob); cudaFree(it->second.status); dense_tables().erase(it); }
+}
+
+// 1 when a previous cart2int launch on this table met a non-positive Cholesky pivot (redundant or
+// singular internal coordinates; the reference's at::cholesky throws there). Synchronises.
+int dense_status(const tchem_ic_table * t) {
+    std::lock_guard<std::mutex> lock(dense_mutex());
+    auto it = dense_tables().find(t);
+    if (it == dense_tables().end()) return 0;
+    int s = 0;
+    cudaMemcpy(&s, it->second.status, sizeof(int), cudaMemcpyDeviceToHost);
+    if (s) cudaMemset(it->second.status, 0, sizeof(int));
+    return s;
+}
+
+} // namespace tchem_b200
+
 using namespace tchem_b200;
+
 extern "C" {
-int tchem_ic_grad_cart2int(const tchem_ic_table *, const double *, const double *, int64_t, double *, tchem_stream_t) {
-    return set_error(TCHEM_EDOMAIN, "tchem_ic_grad_cart2int: not implemented yet");
+
+int tchem_ic_grad_cart2int_matrix(const tchem_ic_table * t, const double * r, int64_t B, double * M, tchem_stream_t stream) {
+    return launch_dense(0, "gradient_cart2int", t, r, nullptr, nullptr, B, M, static_cast<cudaStream_t>(stream));
 }
-int tchem_ic_grad_cart2int_matrix(const tchem_ic_table *, const double *, int64_t, double *, tchem_stream_t) {
-    return set_error(TCHEM_EDOMAIN, "tchem_ic_grad_cart2int_matrix: not implemented yet");
+int tchem_ic_grad_cart2int(const tchem_ic_table * t, const double * r, const double * cartgrad, int64_t B,
+                           double * intgrad, tchem_stream_t stream) {
+    return launch_dense(1, "gradient_cart2int", t, r, cartgrad, nullptr, B, intgrad, static_cast<cudaStream_t>(stream));
 }
-int tchem_ic_hess_int2cart(const tchem_ic_table *, const double *, const double *, const double *, int64_t, double *, tchem_stream_t) {
-    return set_error(TCHEM_EDOMAIN, "tchem_ic_hess_int2cart: not implemented yet");
+int tchem_ic_hess_int2cart(const tchem_ic_table * t, const double * r, const double * intgrad, const double * intHess,
+                           int64_t B, double * cartHess, tchem_stream_t stream) {
+    return launch_dense(2, "Hessian_int2cart", t, r, intgrad, intHess, B, cartHess, static_cast<cudaStream_t>(stream));
 }
-int tchem_ic_hess_cart2int(const tchem_ic_table *, const double *, const double *, const double *, int64_t, double *, tchem_stream_t) {
-    return set_error(TCHEM_EDOMAIN, "tchem_ic_hess_cart2int: not implemented yet");
+int tchem_ic_hess_cart2int(const tchem_ic_table * t, const double * r, const double * cartgrad, const double * cartHess,
+                           int64_t B, double * intHess, tchem_stream_t stream) {
+    return launch_dense(3, "Hessian_cart2int", t, r, cartgrad, cartHess, B, intHess, static_cast<cudaStream_t>(stream));
 }
+// 0 = every Cholesky factorisation since the last call succeeded
+int tchem_ic_factor_status(const tchem_ic_table * t) { return t ? dense_status(t) : 0; }
+
 int tchem_ic_sap_eval_host(const tchem_ic_table *, const tchem_sap_table *, const double *, int64_t, double *, double *, double *) {
     return set_error(TCHEM_EDOMAIN, "tchem_ic_sap_eval_host: not implemented yet");
 }
-}
+
+} // extern "C"

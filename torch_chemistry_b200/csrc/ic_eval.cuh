@@ -50,6 +50,19 @@ __device__ __forceinline__ V3<double> load_atom(const double * R, int atom, int 
     const double * p = R + 3 * atom * kPad + lane;
     return v3<double>(p[0], p[kPad], p[2 * kPad]);
 }
+// where a primitive reads its atoms from: the warp tile (one geometry per lane) ...
+struct TileLoader {
+    const double * R;
+    int lane;
+    __device__ __forceinline__ V3<double> operator()(int atom) const { return load_atom(R, atom, lane); }
+};
+// ... or one geometry r[cartdim] shared by the whole block (dense per-geometry kernels)
+struct GeomLoader {
+    const double * r;
+    __device__ __forceinline__ V3<double> operator()(int atom) const {
+        return v3<double>(r[3 * atom], r[3 * atom + 1], r[3 * atom + 2]);
+    }
+};
 
 template <class S> __device__ __forceinline__ S seed(double v, int coord, int d1, int d2);
 template <> __device__ __forceinline__ Dual seed<Dual>(double v, int coord, int d1, int) {
@@ -104,12 +117,12 @@ struct CompactSink {
 
 // 5-atom torsion2 family, kept out of line: it is rare and register hungry (Dual / Dual2 passes
 // over 15 coordinates) and must not inflate the register allocation of the common types.
-template <int MODE, class Sink>
-__device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double * R, int lane, const Sink sink) {
+template <int MODE, class Sink, class Loader>
+__device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const Loader load, const Sink sink, int dir0, int dir1) {
     const int type = pd.type;
     V3<double> a[5];
 #pragma unroll
-    for (int i = 0; i < 5; i++) a[i] = load_atom(R, pd.atoms[i], lane);
+    for (int i = 0; i < 5; i++) a[i] = load(pd.atoms[i]);
         // 5-atom torsion2 family: the reference differentiates the value expression with
     // autograd (source/IC/InvDisp.cpp:415-570 first order, :893-1065 second order).
     // px/py = sin(theta) * cos/sin(phi): the reference applies the product rule with an
@@ -125,12 +138,14 @@ __device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double *
         double ct = -dot(u12, u23);
         sintheta = sqrt(1.0 - ct * ct);
     }
-    switch (type) {
-    case TCHEM_TORSION2:    sink.value(signed_wrapped_angle(cv, tv, pd.min)); break;
-    case TCHEM_SINTORSION2: sink.value(sv); break;
-    case TCHEM_COSTORSION2: sink.value(cv); break;
-    case TCHEM_PXTORSION2:  sink.value(sintheta * cv); break;
-    default:                sink.value(sintheta * sv); break;
+    if (MODE != MODE_KDIR) {
+        switch (type) {
+        case TCHEM_TORSION2:    sink.value(signed_wrapped_angle(cv, tv, pd.min)); break;
+        case TCHEM_SINTORSION2: sink.value(sv); break;
+        case TCHEM_COSTORSION2: sink.value(cv); break;
+        case TCHEM_PXTORSION2:  sink.value(sintheta * cv); break;
+        default:                sink.value(sintheta * sv); break;
+        }
     }
     if (MODE == MODE_QJ) {
         for (int dir = 0; dir < 15; dir++) {
@@ -150,8 +165,8 @@ __device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double *
             }
             sink.jac_entry(pd.atoms, dir, j);
         }
-    } else if (MODE == MODE_QJK) {
-        for (int d2 = 0; d2 < 15; d2++) {
+    } else if (MODE == MODE_QJK || MODE == MODE_KDIR) {
+        for (int d2 = max(dir0, 0); d2 < min(dir1, 15); d2++) {
             for (int d1 = 0; d1 <= d2; d1++) {
                 V3<Dual2> s[5]; Dual2 sd, cd, td;
                 seed_atoms<Dual2, 5>(a, s, d1, d2);
@@ -175,7 +190,7 @@ __device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double *
                     Dual2 f = sth * (type == TCHEM_PXTORSION2 ? cd : sd);
                     j2 = f.b; k = f.c;
                 }
-                if (d1 == d2) sink.jac_entry(pd.atoms, d2, j2);
+                if (d1 == d2 && MODE != MODE_KDIR) sink.jac_entry(pd.atoms, d2, j2);
                 sink.hess_entry5(pd.atoms, d1, d2, k);
             }
         }
@@ -193,23 +208,30 @@ __device__ __noinline__ void eval_primitive5(const PrimDesc & pd, const double *
 // HAS5: the table contains 5-atom (torsion2 family) primitives. Those are evaluated by an
 // out-of-line function; a kernel instantiated with HAS5 = false carries no call at all, which
 // keeps its long-lived state in registers (values live across a call site go to the stack).
-template <int MODE, bool HAS5, class Sink>
-__device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double * R, int lane, const Sink & sink) {
+template <int MODE, bool HAS5, class Sink, class Loader>
+__device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const Loader & load, const Sink & sink,
+                                               int dir0 = 0, int dir1 = 15) {
     constexpr bool WANT_J = MODE == MODE_QJ || MODE == MODE_QJK;
+    constexpr bool WANT_K = MODE == MODE_QJK || MODE == MODE_KDIR;
+    constexpr bool WANT_Q = MODE != MODE_KDIR;
     const int type = pd.type;
-    if (type == TCHEM_DUMMY) { sink.value(1.0); return; }
-
+    if (type == TCHEM_DUMMY) { if (WANT_Q) sink.value(1.0); return; }
     if (MODE != MODE_VALUE && pd.natoms == 5) {
-        if (HAS5) eval_primitive5<MODE, Sink>(pd, R, lane, sink);
+        if (HAS5) eval_primitive5<MODE, Sink, Loader>(pd, load, sink, dir0, dir1);
         return;
     }
-    V3<double> a[kMaxAtoms];
+    V3<double> a[4];
 #pragma unroll
-    for (int i = 0; i < kMaxAtoms; i++)
-        if (i < pd.natoms) a[i] = load_atom(R, pd.atoms[i], lane);
-
+    for (int i = 0; i < 4; i++)
+        if (i < pd.natoms) a[i] = load(pd.atoms[i]);
+    if (MODE == MODE_VALUE && pd.natoms == 5) {
+        V3<double> a5[5] = {a[0], a[1], a[2], a[3], load(pd.atoms[4])};
+        sink.value(value_path(type, a5, pd.min));
+        return;
+    }
     if (MODE == MODE_VALUE) {
-        sink.value(value_path(type, a, pd.min));
+        V3<double> a5[5] = {a[0], a[1], a[2], a[3], a[3]};
+        sink.value(value_path(type, a5, pd.min));
         return;
     }
 
@@ -217,11 +239,13 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
     auto emitJ = [&](int i, const V3<double> & v) { if (WANT_J) sink.jac_block(pd.atoms, i, v); };
     switch (type) {
     case TCHEM_STRETCHING: {
-        double q;
-        stretching_J<double>(a, q, emitJ);
-        sink.value(q);
-        if (MODE == MODE_QJK) {
-            for (int dir = 0; dir < 6; dir++) {
+        if (WANT_Q) {
+            double q;
+            stretching_J<double>(a, q, emitJ);
+            sink.value(q);
+        }
+        if (WANT_K) {
+            for (int dir = dir0; dir < min(dir1, 6); dir++) {
                 V3<Dual> s[2]; Dual qd;
                 seed_atoms<Dual, 2>(a, s, dir, -1);
                 stretching_J<Dual>(s, qd, [&](int i, const V3<Dual> & v) { sink.template hess_block<2>(pd.atoms, dir, i, v); });
@@ -230,11 +254,13 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
         break;
     }
     case TCHEM_BENDING: case TCHEM_COSBENDING: {
-        double c;
-        if (type == TCHEM_BENDING) { bending_J<double, false>(a, c, emitJ); sink.value(acos(c)); }
-        else                       { bending_J<double, true>(a, c, emitJ);  sink.value(c); }
-        if (MODE == MODE_QJK) {
-            for (int dir = 0; dir < 9; dir++) {
+        if (WANT_Q) {
+            double c;
+            if (type == TCHEM_BENDING) { bending_J<double, false>(a, c, emitJ); sink.value(acos(c)); }
+            else                       { bending_J<double, true>(a, c, emitJ);  sink.value(c); }
+        }
+        if (WANT_K) {
+            for (int dir = dir0; dir < min(dir1, 9); dir++) {
                 V3<Dual> s[3]; Dual cd;
                 seed_atoms<Dual, 3>(a, s, dir, -1);
                 auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<3>(pd.atoms, dir, i, v); };
@@ -245,14 +271,16 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
         break;
     }
     case TCHEM_TORSION: case TCHEM_SINTORSION: case TCHEM_COSTORSION: {
-        double sp = 0.0, cp = 0.0, st = 0.0;
-        if (type == TCHEM_TORSION) {
-            torsion_J<double, 0>(a, sp, cp, st, emitJ);
-            sink.value(signed_wrapped_angle(cp, st, pd.min));
-        } else if (type == TCHEM_SINTORSION) { torsion_J<double, 1>(a, sp, cp, st, emitJ); sink.value(sp); }
-        else                                 { torsion_J<double, 2>(a, sp, cp, st, emitJ); sink.value(cp); }
-        if (MODE == MODE_QJK) {
-            for (int dir = 0; dir < 12; dir++) {
+        if (WANT_Q) {
+            double sp = 0.0, cp = 0.0, st = 0.0;
+            if (type == TCHEM_TORSION) {
+                torsion_J<double, 0>(a, sp, cp, st, emitJ);
+                sink.value(signed_wrapped_angle(cp, st, pd.min));
+            } else if (type == TCHEM_SINTORSION) { torsion_J<double, 1>(a, sp, cp, st, emitJ); sink.value(sp); }
+            else                                 { torsion_J<double, 2>(a, sp, cp, st, emitJ); sink.value(cp); }
+        }
+        if (WANT_K) {
+            for (int dir = dir0; dir < min(dir1, 12); dir++) {
                 V3<Dual> s[4]; Dual spd, cpd, std_;
                 seed_atoms<Dual, 4>(a, s, dir, -1);
                 auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<4>(pd.atoms, dir, i, v); };
@@ -264,11 +292,13 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
         break;
     }
     case TCHEM_OUTOFPLANE: case TCHEM_SINOOP: {
-        double s_;
-        if (type == TCHEM_OUTOFPLANE) { oop_J<double, false>(a, s_, emitJ); sink.value(asin(s_)); }
-        else                          { oop_J<double, true>(a, s_, emitJ);  sink.value(s_); }
-        if (MODE == MODE_QJK) {
-            for (int dir = 0; dir < 12; dir++) {
+        if (WANT_Q) {
+            double s_;
+            if (type == TCHEM_OUTOFPLANE) { oop_J<double, false>(a, s_, emitJ); sink.value(asin(s_)); }
+            else                          { oop_J<double, true>(a, s_, emitJ);  sink.value(s_); }
+        }
+        if (WANT_K) {
+            for (int dir = dir0; dir < min(dir1, 12); dir++) {
                 V3<Dual> s[4]; Dual sd;
                 seed_atoms<Dual, 4>(a, s, dir, -1);
                 auto emitK = [&](int i, const V3<Dual> & v) { sink.template hess_block<4>(pd.atoms, dir, i, v); };
@@ -286,7 +316,7 @@ __device__ __forceinline__ void eval_primitive(const PrimDesc & pd, const double
 // All distinct primitives of one chunk for this lane's geometry -> compact buffer.
 template <int MODE, bool HAS5>
 __device__ __forceinline__ void eval_chunk(const PrimDesc * prims, int p0, int p1, const double * R, double * P, int lane) {
-    for (int p = p0; p < p1; p++) eval_primitive<MODE, HAS5>(prims[p], R, lane, CompactSink(P, prims[p].out, lane));
+    for (int p = p0; p < p1; p++) eval_primitive<MODE, HAS5>(prims[p], TileLoader{R, lane}, CompactSink(P, prims[p].out, lane));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -72,7 +72,7 @@ grad_int2cart_kernel(const GradProgram gp, const double * __restrict__ r, const 
             ScatterSink sink;
             sink.G = G + lane;
             sink.W = W;
-            eval_primitive<MODE_QJ, HAS5>(pd, R, lane, sink);
+            eval_primitive<MODE_QJ, HAS5>(pd, TileLoader{R, lane}, sink);
         }
         __syncwarp();
         double * out = gr + b0 * cartdim;

@@ -21,7 +21,8 @@ constexpr int kMaxAtoms = 5;
 
 // MODE_VALUE/QJ/QJK are table modes (each has its own compiled program); MODE_QPATH is an
 // evaluation flavour only: values by the compute_IC_J formulas, no derivatives.
-enum Mode { MODE_VALUE = 0, MODE_QJ = 1, MODE_QJK = 2, MODE_COUNT = 3, MODE_QPATH = 4 };
+// MODE_KDIR: only the second-derivative passes of a range of Cartesian directions.
+enum Mode { MODE_VALUE = 0, MODE_QJ = 1, MODE_QJK = 2, MODE_COUNT = 3, MODE_QPATH = 4, MODE_KDIR = 5 };
 
 struct PrimDesc {                  // one distinct InvDisp of a chunk
     int32_t type;

@@ -104,7 +104,7 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
             stage_coordinates(in, b0, ntile, cartdim, R, lane);
             for (int c = 0; c < ic.nchunks; c++) {
                 const ChunkDesc ch = ic.chunks[c];
-                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH, HAS5>(pd, R, lane, CompactSink(PI, pd.out, lane)); }
+                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH, HAS5>(pd, TileLoader{R, lane}, CompactSink(PI, pd.out, lane)); }
                 // every lane combines its own column: x[row] = sum coef * q_prim (IntCoord.cpp:66-74)
                 for (int row = 0; row < ch.nrows; row++) {
                     const uint32_t w = ic.map[ch.qmap + row];
