@@ -31,9 +31,36 @@ WORKLOADS = {
     "C3": ("q+J", lambda cd, n, ns: 8 * (cd + n + n * cd)),
     "C3K": ("q+J+K", lambda cd, n, ns: 8 * (cd + n + n * cd + n * cd * cd)),
     "C4g": ("gradient_int2cart", lambda cd, n, ns: 8 * (cd + n + cd)),
+    "C4gc": ("gradient_cart2int", lambda cd, n, ns: 8 * (cd + cd + n)),
+    "C4H": ("Hessian_int2cart", lambda cd, n, ns: 8 * (cd + n + n * n + cd * cd)),
+    "C4Hc": ("Hessian_cart2int", lambda cd, n, ns: 8 * (cd + cd + cd * cd + n * n)),
     "C5": ("q->SAPSet value+Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * n)),
 }
-DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4g": 10 ** 5, "C5": 12500000}
+DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4g": 10 ** 5, "C4gc": 10 ** 5, "C4H": 10 ** 5,
+                 "C4Hc": 10 ** 5, "C5": 12500000}
+# dense flops per geometry of the contraction-bound transforms
+FLOPS = {
+    "C4H": lambda cd, n: 2 * n * n * cd + 2 * cd * n * cd + 2 * n * cd * cd,
+    "C4Hc": lambda cd, n: 2 * n * n * cd + (n ** 3) // 3 + 2 * (n ** 3) // 3 + 2 * n ** 3 + 2 * n * n * cd
+                          + 2 * cd * cd * n + 2 * n * cd * n + 2 * n * cd * cd,
+    "C4gc": lambda cd, n: 2 * n * n * cd + (n ** 3) // 3 + 2 * (n ** 3) // 3 + 2 * n ** 3 + 2 * n * n * cd,
+}
+
+
+def measured_fp64_peak(device):
+    """cuBLAS DGEMM 4096^3 through torch.matmul, best of 5 (TFLOP/s): the FP64 roofline denominator"""
+    import torch
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
 
 
 def measured_peak():
@@ -137,6 +164,12 @@ def _cpu_worker(r):
         s.qJK(r)
     elif what == "gradient_int2cart":
         s.gradient_int2cart(r, np.ones((r.shape[0], s.intdim)))
+    elif what == "gradient_cart2int":
+        s.gradient_cart2int(r, np.ones((r.shape[0], r.shape[1])))
+    elif what == "Hessian_int2cart":
+        s.Hessian_int2cart(r, np.ones((r.shape[0], s.intdim)), np.tile(np.eye(s.intdim), (r.shape[0], 1, 1)))
+    elif what == "Hessian_cart2int":
+        s.Hessian_cart2int(r, np.ones((r.shape[0], r.shape[1])), np.tile(np.eye(r.shape[1]), (r.shape[0], 1, 1)))
     else:
         q = s.qJ(r)[0]
         sap.value(q)
@@ -187,7 +220,7 @@ def cpu_baseline(w, what, per_core, cores=None):
 
 def per_core_sample(key):
     # sized for roughly 10-20 s of CPU work per process with the reference's measured per-geometry cost
-    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4g": 1000, "C5": 20000}[key]
+    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000}[key]
 
 
 # ------------------------------------------------------------------------------------------
@@ -234,7 +267,7 @@ def main():
     wl = importlib.util.module_from_spec(spec)
     sys.modules["_wl"] = wl
     spec.loader.exec_module(wl)
-    wkey = {"C3K": "C3", "C4g": "C4"}.get(args.workload, args.workload)
+    wkey = {"C3K": "C3", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
     w = wl.get(wkey)
     what, bytes_fn = WORKLOADS[args.workload]
     B = args.batch or DEFAULT_BATCH[args.workload]
@@ -272,7 +305,15 @@ def main():
     r_host = torch.from_numpy(w.geometries(B, seed=w.seed + 1000 * rank)).pin_memory()
     r_dev = r_host.to(device)
     f64 = dict(dtype=torch.float64, device=device)
-    gq_dev = torch.randn(B, n, **f64) if what == "gradient_int2cart" else None
+    gq_dev = torch.randn(B, n, **f64) if what in ("gradient_int2cart", "Hessian_int2cart") else None
+    gr_dev = torch.randn(B, cd, **f64) if what in ("gradient_cart2int", "Hessian_cart2int") else None
+    Hq_dev = Hr_dev = None
+    if what == "Hessian_int2cart":
+        Hq_dev = torch.randn(B, n, n, **f64)
+        Hq_dev = 0.5 * (Hq_dev + Hq_dev.transpose(1, 2)).contiguous()
+    if what == "Hessian_cart2int":
+        Hr_dev = torch.randn(B, cd, cd, **f64)
+        Hr_dev = 0.5 * (Hr_dev + Hr_dev.transpose(1, 2)).contiguous()
 
     if what == "q+J":
         outs = [torch.empty(B, n, **f64), torch.empty(B, n, cd, **f64)]
@@ -282,6 +323,12 @@ def main():
         step = lambda: ic.compute_IC_J_K(r_dev, out=outs)
     elif what == "gradient_int2cart":
         step = lambda: ic.gradient_int2cart(r_dev, gq_dev)
+    elif what == "gradient_cart2int":
+        step = lambda: ic.gradient_cart2int(r_dev, gr_dev)
+    elif what == "Hessian_int2cart":
+        step = lambda: ic.Hessian_int2cart(r_dev, gq_dev, Hq_dev)
+    elif what == "Hessian_cart2int":
+        step = lambda: ic.Hessian_cart2int(r_dev, gr_dev, Hr_dev)
     else:
         step = lambda: sap.chained(ic, r_dev)
     need_flush = B * bytes_per_geom <= 126e6
@@ -343,14 +390,23 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
+        kernel = ("sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
+                  else "dense_kernel" if args.workload in FLOPS else "ic_eval_kernel")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_geometry": bytes_per_geom, "kernel": kernel, "launch_ms": avg_launch_s * 1e3}
+        if args.workload in FLOPS:
+            fl = FLOPS[args.workload](cd, n)
+            fpeak = measured_fp64_peak(device)
+            tf = fl * B / avg_launch_s / 1e12
+            roof = {"bound": "tensor", "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak, "traffic": None,
+                    "peak_source": "FP64 DGEMM 4096^3 via cuBLAS (torch.matmul), measured in this run",
+                    "dense_flops_per_geometry": fl, "kernel": kernel, "launch_ms": avg_launch_s * 1e3,
+                    "hbm_GBps": achieved, "hbm_frac": achieved / peak}
         line = {"metric": metric, "value": value, "unit": "geometries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "impl": "ours",
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                             "algorithmic_bytes_per_geometry": bytes_per_geom, "kernel": "ic_eval_kernel" if sap is None else "sap_eval_kernel",
-                             "launch_ms": avg_launch_s * 1e3},
+                "impl": "ours", "roofline": roof,
                 "clocks": sampler.summary(), "gpu_launches": int(launches)}
         if e2e:
             line["e2e"] = e2e
