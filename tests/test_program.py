@@ -1,0 +1,152 @@
+"""CPU check of the host-side "compiler" (torch_chemistry_b200/csrc/ic_table.cpp): the program it
+emits - distinct primitives per chunk, compact entry layout, q maps, sector-sorted element maps -
+is exported through the C ABI and interpreted here in numpy with the ORACLE supplying each
+primitive's value / J / K. The dense q, J, K this reconstructs must equal the oracle's own. This
+pins the chunking, de-duplication and gather logic without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, golden
+from oracle import tchem_oracle as O
+
+capi = pytest.importorskip("torch_chemistry_b200._capi")
+lib = capi.lib
+
+
+class PrimDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("natoms", C.c_int32), ("atoms", C.c_int32 * 5), ("out", C.c_int32), ("min", C.c_double)]
+
+
+class ChunkDesc(C.Structure):
+    _fields_ = [("prim_begin", C.c_int32), ("prim_end", C.c_int32), ("row0", C.c_int32), ("nrows", C.c_int32),
+                ("accumulate", C.c_int32), ("qslot", C.c_int32), ("qmap", C.c_int64), ("jmap", C.c_int64), ("kmap", C.c_int64)]
+
+
+class Src(C.Structure):
+    _fields_ = [("entry", C.c_int32), ("pad", C.c_int32), ("coef", C.c_double)]
+
+
+class ElemMap(C.Structure):
+    _fields_ = [("word", C.c_uint32), ("k", C.c_uint32)]
+
+
+def export(text, fmt, cartdim, mode):
+    nt, nic = C.c_int(0), C.c_int(0)
+    capi.check(lib.tchem_ic_parse_text(fmt.encode(), text.encode(), None, 0, C.byref(nt), C.byref(nic)))
+    terms = (capi.InvDisp * nt.value)()
+    capi.check(lib.tchem_ic_parse_text(fmt.encode(), text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
+    counts = (C.c_int64 * 8)()
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, None, None, None, None, None, None))
+    prims, chunks = (PrimDesc * counts[0])(), (ChunkDesc * counts[1])()
+    qmap, qsrcs = (C.c_uint32 * max(counts[2], 1))(), (Src * max(counts[3], 1))()
+    emap, srcs = (ElemMap * max(counts[4], 1))(), (Src * max(counts[5], 1))()
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, prims, chunks, qmap, qsrcs, emap, srcs))
+    return dict(prims=prims, chunks=chunks, qmap=qmap, qsrcs=qsrcs, emap=emap, srcs=srcs, cap=counts[6], nic=nic.value)
+
+
+def interpret(prog, r, mode):
+    """numpy twin of the device interpreter: compact buffer per chunk, then the gathers"""
+    B, cd = r.shape
+    n = prog["nic"]
+    q = np.full((B, n), np.nan)
+    J = np.full((B, n, cd), np.nan) if mode >= 1 else None
+    K = np.full((B, n, cd, cd), np.nan) if mode == 2 else None
+    for ch in prog["chunks"]:
+        P = np.zeros((prog["cap"], B))
+        for p in range(ch.prim_begin, ch.prim_end):
+            pd = prog["prims"][p]
+            d = O.InvDisp(O.TYPES[pd.type], [pd.atoms[i] for i in range(pd.natoms)], pd.min)
+            na = pd.natoms
+            if mode == 0:
+                P[pd.out] = O.invdisp_value(d, r)
+                continue
+            qv, Jl, Kl = O.invdisp_qJK(d, r, mode == 2)
+            P[pd.out] = qv
+            for m in range(3 * na):
+                P[pd.out + 1 + m] = Jl[:, m]
+            if mode == 2:
+                kbase = pd.out + 1 + 3 * na
+                for i in range(na):
+                    for j in range(i, na):
+                        blk = i * na - (i * (i - 1)) // 2 + (j - i)
+                        for c in range(3):
+                            for e in range(3):
+                                P[kbase + 9 * blk + 3 * c + e] = Kl[:, 3 * i + c, 3 * j + e]
+        assert ch.qslot + ch.nrows <= prog["cap"]
+
+        def gather(word, table):
+            cnt, off = word >> 24, word & 0xFFFFFF
+            v = np.zeros(B)
+            for s in range(off, off + cnt):
+                v = v + table[s].coef * P[table[s].entry]
+            return v
+
+        for row in range(ch.nrows):
+            v = gather(prog["qmap"][ch.qmap + row], prog["qsrcs"])
+            q[:, ch.row0 + row] = v + (q[:, ch.row0 + row] if ch.accumulate else 0.0)
+        for name, out, span, off0 in (("J", J, ch.nrows * cd, ch.jmap), ("K", K, ch.nrows * cd * cd, ch.kmap)):
+            if out is None:
+                continue
+            flat = out.reshape(B, -1)
+            base = ch.row0 * (cd if name == "J" else cd * cd)
+            seen = np.zeros(span, dtype=bool)
+            for e in range(span):
+                m = prog["emap"][off0 + e]
+                assert not seen[m.k], "element emitted twice"
+                seen[m.k] = True
+                v = gather(m.word, prog["srcs"])
+                flat[:, base + m.k] = v + (flat[:, base + m.k] if ch.accumulate else 0.0)
+            assert seen.all(), "element map does not cover the span"
+    return q, J, K
+
+
+CASES = [("ref_aniline_default", 2), ("ref_aniline_advanced", 2), ("ref_normal_mode", 1), ("workload_C2", 2), ("workload_C3", 1)]
+
+
+@pytest.mark.parametrize("name,mode", CASES)
+def test_compiled_program_reproduces_the_oracle(name, mode):
+    g = golden(name)
+    fmt = str(g["format"]) if "format" in g else "default"
+    text = str(g["definition"])
+    r = g["r"][:2]
+    prog = export(text, fmt, r.shape[1], mode)
+    orc = O.IntCoordSet(fmt, text)
+    q, J, K = interpret(prog, r, mode)
+    if mode == 2:
+        qo, Jo, Ko = orc.qJK(r)
+        assert_parity(K, Ko, name + " K through the program")
+    else:
+        qo, Jo = orc.qJ(r)
+    assert_parity(q, qo, name + " q through the program")
+    assert_parity(J, Jo, name + " J through the program")
+    # value-path program
+    q0, _, _ = interpret(export(text, fmt, r.shape[1], 0), r, 0)
+    assert_parity(q0, orc.q(r), name + " q (value path) through the program")
+
+
+def test_primitives_are_shared_inside_a_chunk():
+    """C2: 41 terms but 15 distinct invariant displacements; the four C-H stretch combinations
+    share their four stretches."""
+    g = golden("workload_C2")
+    prog = export(str(g["definition"]), "default", 18, 1)
+    assert len(prog["prims"]) == 15
+    assert sum(ch.nrows for ch in prog["chunks"]) == 12
+
+
+def test_row_wider_than_capacity_is_split_and_accumulated():
+    # one coordinate = 8 torsions: 8 * 13 + 1 entries exceed the q+J capacity target of 64
+    lines = []
+    for k in range(8):
+        head = "%6d" % 1 if k == 0 else " " * 6
+        lines.append(head + "%12.6f%14s%6d%6d%6d%6d" % (1.0, "torsion", k + 1, k + 2, k + 3, k + 4))
+    text = "\n".join(lines) + "\n"
+    prog = export(text, "default", 33, 1)
+    assert len(prog["chunks"]) >= 2 and [ch.accumulate for ch in prog["chunks"]][1:] == [1] * (len(prog["chunks"]) - 1)
+    rng = np.random.default_rng(3)
+    r = rng.standard_normal((2, 33)) * 2.0
+    q, J, _ = interpret(prog, r, 1)
+    qo, Jo = O.IntCoordSet("default", text).qJ(r)
+    assert_parity(J, Jo, "split row J")
+    assert np.abs(q - qo).max() < 1e-9

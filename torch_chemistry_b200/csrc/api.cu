@@ -194,6 +194,27 @@ int tchem_ic_eval(const tchem_ic_table * tc, const double * r, int64_t B, double
     return launch_ic_eval(t, mode, r, B, q, J, K, static_cast<cudaStream_t>(stream));
 }
 
+int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int mode,
+                            int64_t * counts, void * prims, void * chunks, uint32_t * map, void * qsrcs,
+                            void * emap, void * srcs) {
+    if (!terms || !counts || n_terms <= 0 || n_ic <= 0 || mode < 0 || mode >= MODE_COUNT)
+        return set_error(TCHEM_EINVAL, "tchem_ic_program_export: bad arguments");
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    HostProgram hp;
+    int rc = build_program(v, n_ic, cartdim, mode, hp);
+    if (rc != TCHEM_OK) return rc;
+    counts[0] = (int64_t)hp.prims.size(); counts[1] = (int64_t)hp.chunks.size(); counts[2] = (int64_t)hp.map.size();
+    counts[3] = (int64_t)hp.qsrcs.size(); counts[4] = (int64_t)hp.emap.size(); counts[5] = (int64_t)hp.srcs.size();
+    counts[6] = hp.cap;
+    if (prims) std::memcpy(prims, hp.prims.data(), hp.prims.size() * sizeof(PrimDesc));
+    if (chunks) std::memcpy(chunks, hp.chunks.data(), hp.chunks.size() * sizeof(ChunkDesc));
+    if (map) std::memcpy(map, hp.map.data(), hp.map.size() * sizeof(uint32_t));
+    if (qsrcs) std::memcpy(qsrcs, hp.qsrcs.data(), hp.qsrcs.size() * sizeof(Src));
+    if (emap) std::memcpy(emap, hp.emap.data(), hp.emap.size() * sizeof(ElemMap));
+    if (srcs) std::memcpy(srcs, hp.srcs.data(), hp.srcs.size() * sizeof(Src));
+    return TCHEM_OK;
+}
+
 int tchem_ic_eval_timed(const tchem_ic_table * tc, const double * r, int64_t B, double * q, double * J,
                         double * K, int value_path, int iters, tchem_stream_t stream, float * ms_per_launch) {
     if (iters < 1 || !ms_per_launch) return set_error(TCHEM_EINVAL, "tchem_ic_eval_timed: bad arguments");
