@@ -366,10 +366,14 @@ def main():
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
-    if not args.no_e2e and what in ("q+J", "q+J+K"):
+    if not args.no_e2e and (what in ("q+J", "q+J+K") or sap is not None):
         pin = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
-        houts = [pin(B, n), pin(B, n, cd)] + ([pin(B, n, cd, cd)] if what == "q+J+K" else [])
-        call = (lambda: ic.compute_IC_J(r_host, out=houts)) if what == "q+J" else (lambda: ic.compute_IC_J_K(r_host, out=houts))
+        if sap is not None:
+            houts = [pin(B, ns), pin(B, ns, n)]
+            call = lambda: sap.chained(ic, r_host, out=houts)
+        else:
+            houts = [pin(B, n), pin(B, n, cd)] + ([pin(B, n, cd, cd)] if what == "q+J+K" else [])
+            call = (lambda: ic.compute_IC_J(r_host, out=houts)) if what == "q+J" else (lambda: ic.compute_IC_J_K(r_host, out=houts))
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
             call()
@@ -384,7 +388,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * e2e_steps / float(tt.item()), "unit": "geometries/s",
                "h2d_bytes_per_step": int(B * cd * 8), "d2h_bytes_per_step": int(sum(o.numel() for o in houts) * 8),
-               "steps": e2e_steps, "api": "IntCoordSet.compute_IC_J(r) with pinned host tensors -> tchem_ic_eval_host"}
+               "steps": e2e_steps, "api": ("SAPSet.chained(IntCoordSet, r) with pinned host tensors -> tchem_ic_sap_eval_host" if sap is not None
+                       else "IntCoordSet.compute_IC_J(r) with pinned host tensors -> tchem_ic_eval_host")}
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -283,3 +283,16 @@ def test_transform_round_trip_C4(T):
     orc = O.IntCoordSet("default", w.ic_text)
     k = 3
     assert_parity(host(Hr[:k]), orc.Hessian_int2cart(host(r[:k]), host(gq[:k]), host(Hq[:k])), "C4 Hessian_int2cart vs oracle")
+
+
+def test_chained_host_buffers_match_device_path(T):
+    w = T.workloads.get("C5")
+    ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    sap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims)
+    r = torch.from_numpy(w.geometries(300007, seed=8))
+    y, J, q = sap.chained(ic, r, return_q=True)
+    assert not y.is_cuda and not J.is_cuda and not q.is_cuda
+    yd, Jd, qd = sap.chained(ic, r.cuda(), return_q=True)
+    np.testing.assert_array_equal(y.numpy(), host(yd))
+    np.testing.assert_array_equal(J.numpy(), host(Jd))
+    np.testing.assert_array_equal(q.numpy(), host(qd))

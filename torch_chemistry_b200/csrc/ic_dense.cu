@@ -515,8 +515,4 @@ int tchem_ic_hess_cart2int(const tchem_ic_table * t, const double * r, const dou
 // 0 = every Cholesky factorisation since the last call succeeded
 int tchem_ic_factor_status(const tchem_ic_table * t) { return t ? dense_status(t) : 0; }
 
-int tchem_ic_sap_eval_host(const tchem_ic_table *, const tchem_sap_table *, const double *, int64_t, double *, double *, double *) {
-    return set_error(TCHEM_EDOMAIN, "tchem_ic_sap_eval_host: not implemented yet");
-}
-
 } // extern "C"

@@ -32,7 +32,16 @@ int ensure_program(tchem_ic_table * t, int mode);
 
 } // namespace tchem_b200
 
+struct SapHostPipe {                     // device staging of the chained host-buffer entry point
+    static constexpr int kSlots = 3;
+    cudaStream_t stream[kSlots] = {};
+    double * buf[kSlots] = {};
+    size_t cap = 0;
+    bool ok = false;
+};
+
 struct tchem_sap_table {
+    SapHostPipe pipe;
     int device = 0;
     int nterms = 0, sumdim = 0, irreducible = 0;
     int sm_count = 0, max_smem_optin = 0;
@@ -276,7 +285,14 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
 
 void tchem_sap_table_destroy(tchem_sap_table * t) {
     if (!t) return;
-    { DeviceGuard guard(t->device); cudaFree(t->dev_blob); }
+    {
+        DeviceGuard guard(t->device);
+        cudaFree(t->dev_blob);
+        for (int s = 0; s < SapHostPipe::kSlots; s++) {
+            cudaFree(t->pipe.buf[s]);
+            if (t->pipe.ok) cudaStreamDestroy(t->pipe.stream[s]);
+        }
+    }
     delete t;
 }
 int tchem_sap_table_nterms(const tchem_sap_table * t) { return t ? t->nterms : 0; }
@@ -307,6 +323,58 @@ int tchem_ic_sap_eval(const tchem_ic_table * ic, const tchem_sap_table * sap, co
     DeviceGuard guard(ic->device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
     return launch_sap(sap, ic, r, B, q_out, y, J, static_cast<cudaStream_t>(stream));
+}
+
+// Host buffers in, host buffers out: pieces of the batch rotate over 3 stream/buffer slots so that
+// the upload of piece i+1 and the download of piece i-1 overlap the kernel of piece i.
+int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sapc, const double * r, int64_t B,
+                           double * q_out, double * y, double * J) {
+    tchem_sap_table * sap = const_cast<tchem_sap_table *>(sapc);
+    if (!ic || !sap) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: null table");
+    if (ic->intdim != sap->sumdim)
+        return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: x must have a same dimension as the coordinates (intdim != sum of dimensions)");
+    if (B < 0) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!r || (!y && !J && !q_out)) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: null argument");
+    int rc = ensure_program(const_cast<tchem_ic_table *>(ic), MODE_VALUE);
+    if (rc != TCHEM_OK) return rc;
+    DeviceGuard guard(ic->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    const size_t cd = ic->cartdim, n = sap->sumdim, nt = sap->nterms;
+    const size_t per_geom = cd + (q_out ? n : 0) + (y ? nt : 0) + (J ? nt * n : 0);          // doubles
+    int64_t piece = (int64_t)std::max<size_t>(32, ((size_t(48) << 20) / (8 * per_geom)) / 32 * 32);
+    piece = std::min<int64_t>(piece, (B + 31) / 32 * 32);
+    SapHostPipe & hp = sap->pipe;
+    if (!hp.ok) {
+        for (int s = 0; s < SapHostPipe::kSlots; s++) TC_CUDA(cudaStreamCreateWithFlags(&hp.stream[s], cudaStreamNonBlocking));
+        hp.ok = true;
+    }
+    const size_t need = (size_t)piece * per_geom * 8;
+    if (need > hp.cap) {
+        for (int s = 0; s < SapHostPipe::kSlots; s++) {
+            cudaFree(hp.buf[s]);
+            hp.buf[s] = nullptr;
+            TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&hp.buf[s]), need));
+        }
+        hp.cap = need;
+    }
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += piece, slot = (slot + 1) % SapHostPipe::kSlots) {
+        const int64_t nb = std::min<int64_t>(piece, B - b0);
+        cudaStream_t s = hp.stream[slot];
+        double * d_r = hp.buf[slot];
+        double * d_q = d_r + piece * cd;
+        double * d_y = d_q + (q_out ? piece * n : 0);
+        double * d_J = d_y + (y ? piece * nt : 0);
+        TC_CUDA(cudaMemcpyAsync(d_r, r + b0 * cd, nb * cd * 8, cudaMemcpyHostToDevice, s));
+        rc = launch_sap(sap, ic, d_r, nb, q_out ? d_q : nullptr, y ? d_y : nullptr, J ? d_J : nullptr, s);
+        if (rc != TCHEM_OK) return rc;
+        if (q_out) TC_CUDA(cudaMemcpyAsync(q_out + b0 * n, d_q, nb * n * 8, cudaMemcpyDeviceToHost, s));
+        if (y) TC_CUDA(cudaMemcpyAsync(y + b0 * nt, d_y, nb * nt * 8, cudaMemcpyDeviceToHost, s));
+        if (J) TC_CUDA(cudaMemcpyAsync(J + b0 * nt * n, d_J, nb * nt * n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < SapHostPipe::kSlots; s++) TC_CUDA(cudaStreamSynchronize(hp.stream[s]));
+    return TCHEM_OK;
 }
 
 } // extern "C"

@@ -104,21 +104,29 @@ class SAPSet:
         return y, J
 
     # ---- chained path ----------------------------------------------------------------------
-    def chained(self, intcoordset, r, return_q=False):
-        """r -> q (compute_IC_J formulas) -> SAP values and d SAP / d q in one kernel."""
+    def chained(self, intcoordset, r, return_q=False, out=None):
+        """r -> q (compute_IC_J formulas) -> SAP values and d SAP / d q in one kernel. Host tensors
+        go through the pipelined host-buffer entry point and give host results; `out` = (y, J[, q])
+        preallocated result tensors on the same side as r."""
         if not isinstance(intcoordset, IntCoordSet):
             raise ValueError("tchem::polynomial::SAPSet::chained: needs an IntCoordSet")
         r2, batched = intcoordset._prep(r, "compute_IC_J")
-        was_cuda = r2.is_cuda
-        r2 = intcoordset._on_device(r2)
+        host = not r2.is_cuda
         B = r2.shape[0]
-        y = torch.empty((B, self.nterms), dtype=torch.float64, device=self.device)
-        J = torch.empty((B, self.nterms, self.sumdim), dtype=torch.float64, device=self.device)
-        q = torch.empty((B, self.sumdim), dtype=torch.float64, device=self.device) if return_q else None
+        if out is not None:
+            y, J = out[0].view(B, self.nterms), out[1].view(B, self.nterms, self.sumdim)
+            q = out[2].view(B, self.sumdim) if return_q else None
+        else:
+            kw = dict(dtype=torch.float64, pin_memory=True) if host else dict(dtype=torch.float64, device=self.device)
+            y = torch.empty((B, self.nterms), **kw)
+            J = torch.empty((B, self.nterms, self.sumdim), **kw)
+            q = torch.empty((B, self.sumdim), **kw) if return_q else None
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
         if B > 0:
-            check(lib.tchem_ic_sap_eval(intcoordset._handle, self._handle, ptr(r2), B, ptr(q), ptr(y), ptr(J),
-                                        _stream_ptr(self.device)))
+            if host:
+                check(lib.tchem_ic_sap_eval_host(intcoordset._handle, self._handle, ptr(r2), B, ptr(q), ptr(y), ptr(J)))
+            else:
+                check(lib.tchem_ic_sap_eval(intcoordset._handle, self._handle, ptr(r2), B, ptr(q), ptr(y), ptr(J),
+                                            _stream_ptr(self.device)))
         outs = [y, J] + ([q] if return_q else [])
-        outs = [o if was_cuda else o.cpu() for o in outs]
         return tuple(o if batched else o[0] for o in outs)
