@@ -19,9 +19,17 @@ class PrimDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("natoms", C.c_int32), ("atoms", C.c_int32 * 5), ("out", C.c_int32), ("min", C.c_double)]
 
 
+class SpanDesc(C.Structure):
+    _fields_ = [("map", C.c_int64), ("n", C.c_int32), ("run0", C.c_int32), ("nruns", C.c_int32), ("pad", C.c_int32)]
+
+
 class ChunkDesc(C.Structure):
     _fields_ = [("prim_begin", C.c_int32), ("prim_end", C.c_int32), ("row0", C.c_int32), ("nrows", C.c_int32),
-                ("accumulate", C.c_int32), ("qslot", C.c_int32), ("qmap", C.c_int64), ("jmap", C.c_int64), ("kmap", C.c_int64)]
+                ("accumulate", C.c_int32), ("qslot", C.c_int32), ("qmap", C.c_int64), ("jspan", SpanDesc), ("kspan", SpanDesc)]
+
+
+class ZeroRun(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("len", C.c_uint32)]
 
 
 class Src(C.Structure):
@@ -38,12 +46,14 @@ def export(text, fmt, cartdim, mode):
     terms = (capi.InvDisp * nt.value)()
     capi.check(lib.tchem_ic_parse_text(fmt.encode(), text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
     counts = (C.c_int64 * 8)()
-    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, None, None, None, None, None, None))
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, None, None, None, None, None, None, None))
     prims, chunks = (PrimDesc * counts[0])(), (ChunkDesc * counts[1])()
     qmap, qsrcs = (C.c_uint32 * max(counts[2], 1))(), (Src * max(counts[3], 1))()
     emap, srcs = (ElemMap * max(counts[4], 1))(), (Src * max(counts[5], 1))()
-    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, prims, chunks, qmap, qsrcs, emap, srcs))
-    return dict(prims=prims, chunks=chunks, qmap=qmap, qsrcs=qsrcs, emap=emap, srcs=srcs, cap=counts[6], nic=nic.value)
+    runs = (ZeroRun * max(counts[7], 1))()
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, prims, chunks, qmap, qsrcs, emap, srcs, runs))
+    return dict(prims=prims, chunks=chunks, qmap=qmap, qsrcs=qsrcs, emap=emap, srcs=srcs, runs=runs, cap=counts[6], nic=nic.value,
+                nruns=counts[7])
 
 
 def interpret(prog, r, mode):
@@ -86,19 +96,25 @@ def interpret(prog, r, mode):
         for row in range(ch.nrows):
             v = gather(prog["qmap"][ch.qmap + row], prog["qsrcs"])
             q[:, ch.row0 + row] = v + (q[:, ch.row0 + row] if ch.accumulate else 0.0)
-        for name, out, span, off0 in (("J", J, ch.nrows * cd, ch.jmap), ("K", K, ch.nrows * cd * cd, ch.kmap)):
+        for name, out, span, sd in (("J", J, ch.nrows * cd, ch.jspan), ("K", K, ch.nrows * cd * cd, ch.kspan)):
             if out is None:
                 continue
             flat = out.reshape(B, -1)
             base = ch.row0 * (cd if name == "J" else cd * cd)
             seen = np.zeros(span, dtype=bool)
-            for e in range(span):
-                m = prog["emap"][off0 + e]
+            for i in range(sd.nruns):                       # long stretches of structural zeros
+                run = prog["runs"][sd.run0 + i]
+                assert run.len >= 64 and not seen[run.k:run.k + run.len].any()
+                seen[run.k:run.k + run.len] = True
+                if not ch.accumulate:
+                    flat[:, base + run.k:base + run.k + run.len] = 0.0
+            for e in range(sd.n):
+                m = prog["emap"][sd.map + e]
                 assert not seen[m.k], "element emitted twice"
                 seen[m.k] = True
                 v = gather(m.word, prog["srcs"])
                 flat[:, base + m.k] = v + (flat[:, base + m.k] if ch.accumulate else 0.0)
-            assert seen.all(), "element map does not cover the span"
+            assert seen.all(), "element map and zero runs do not cover the span"
     return q, J, K
 
 

@@ -38,8 +38,10 @@ int ensure_program(tchem_ic_table * t, int mode) {
     const size_t o_qsrcs = o_map + a16(hp.map.size() * sizeof(uint32_t));
     const size_t o_emap = o_qsrcs + a16(hp.qsrcs.size() * sizeof(Src));
     const size_t o_srcs = o_emap + a16(hp.emap.size() * sizeof(ElemMap));
-    const size_t total = o_srcs + a16(hp.srcs.size() * sizeof(Src)) + 16;
+    const size_t o_runs = o_srcs + a16(hp.srcs.size() * sizeof(Src));
+    const size_t total = o_runs + a16(hp.runs.size() * sizeof(ZeroRun)) + 16;
     std::vector<unsigned char> blob(total, 0);
+    std::memcpy(blob.data() + o_runs, hp.runs.data(), hp.runs.size() * sizeof(ZeroRun));
     std::memcpy(blob.data() + o_prims, hp.prims.data(), hp.prims.size() * sizeof(PrimDesc));
     std::memcpy(blob.data() + o_chunks, hp.chunks.data(), hp.chunks.size() * sizeof(ChunkDesc));
     std::memcpy(blob.data() + o_map, hp.map.data(), hp.map.size() * sizeof(uint32_t));
@@ -60,8 +62,11 @@ int ensure_program(tchem_ic_table * t, int mode) {
     p.qsrcs = reinterpret_cast<const Src *>(d + o_qsrcs);
     p.nqsrcs = (int)hp.qsrcs.size();
     p.nmap = (int)hp.map.size();
+    p.split_rows = 0;
+    for (const ChunkDesc & ch : hp.chunks) if (ch.accumulate) p.split_rows = 1;
     p.emap = reinterpret_cast<const ElemMap *>(d + o_emap);
     p.srcs = reinterpret_cast<const Src *>(d + o_srcs);
+    p.runs = reinterpret_cast<const ZeroRun *>(d + o_runs);
     p.nprims = (int)hp.prims.size();
     p.nchunks = (int)hp.chunks.size();
     p.cap = hp.cap;
@@ -196,7 +201,7 @@ int tchem_ic_eval(const tchem_ic_table * tc, const double * r, int64_t B, double
 
 int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int mode,
                             int64_t * counts, void * prims, void * chunks, uint32_t * map, void * qsrcs,
-                            void * emap, void * srcs) {
+                            void * emap, void * srcs, void * runs) {
     if (!terms || !counts || n_terms <= 0 || n_ic <= 0 || mode < 0 || mode >= MODE_COUNT)
         return set_error(TCHEM_EINVAL, "tchem_ic_program_export: bad arguments");
     std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
@@ -206,6 +211,8 @@ int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic
     counts[0] = (int64_t)hp.prims.size(); counts[1] = (int64_t)hp.chunks.size(); counts[2] = (int64_t)hp.map.size();
     counts[3] = (int64_t)hp.qsrcs.size(); counts[4] = (int64_t)hp.emap.size(); counts[5] = (int64_t)hp.srcs.size();
     counts[6] = hp.cap;
+    counts[7] = (int64_t)hp.runs.size();
+    if (runs) std::memcpy(runs, hp.runs.data(), hp.runs.size() * sizeof(ZeroRun));
     if (prims) std::memcpy(prims, hp.prims.data(), hp.prims.size() * sizeof(PrimDesc));
     if (chunks) std::memcpy(chunks, hp.chunks.data(), hp.chunks.size() * sizeof(ChunkDesc));
     if (map) std::memcpy(map, hp.map.data(), hp.map.size() * sizeof(uint32_t));

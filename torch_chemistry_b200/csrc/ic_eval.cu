@@ -56,34 +56,44 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
     const int64_t ntiles = (B + kLanes - 1) / kLanes;
     const int64_t jstride = (int64_t)intdim * cartdim, kstride = jstride * cartdim;
 
-    const int64_t tile_step = (int64_t)gridDim.x * nwarps;
-    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
-    if (tile < ntiles) stage_issue(r, tile * kLanes, (int)min((int64_t)kLanes, B - tile * kLanes), cartdim, R, lane);
-    for (; tile < ntiles; tile += tile_step) {
+    // Work items are (tile, chunk) pairs, handed out as one contiguous range per warp: consecutive
+    // items of a warp share the tile (its coordinates stay staged), and a batch with few tiles
+    // but wide outputs (q+J+K) still spreads over the whole grid.
+    // (a set with rows split into accumulating passes keeps whole tiles together: the passes of a
+    // row must run in order on one warp)
+    const int nchunks = prog.split_rows ? 1 : prog.nchunks, cper = prog.split_rows ? prog.nchunks : 1;
+    const int64_t items = ntiles * nchunks, nw = (int64_t)gridDim.x * nwarps, gw = (int64_t)blockIdx.x * nwarps + warp;
+    const int64_t i0 = (items / nw) * gw + min(gw, items % nw), i1 = i0 + items / nw + (gw < items % nw ? 1 : 0);
+    int64_t staged = -1;                                   // tile whose coordinates are in R (or in flight)
+    for (int64_t it = i0; it < i1; it++) {
+        const int64_t tile = it / nchunks;
+        const int c = (int)(it - tile * nchunks);
         const int64_t b0 = tile * kLanes;
         const int ntile = (int)min((int64_t)kLanes, B - b0);
-        stage_finish(ntile, cartdim, R, lane);
-        for (int c = 0; c < prog.nchunks; c++) {
-            const ChunkDesc ch = chunks[c];
-            eval_chunk<MODE, HAS5>(prims, ch.prim_begin, ch.prim_end, R, P, lane);
-            if (q != nullptr) combine_rows(qmap + ch.qmap, qsrcs, ch.nrows, P, ch.qslot, lane);
-            __syncwarp();
-            // R is dead after the last chunk's arithmetic: start fetching the next tile now, its
-            // DRAM latency hides behind this tile's remaining stores
-            if (c == prog.nchunks - 1 && tile + tile_step < ntiles) {
-                const int64_t nb0 = (tile + tile_step) * kLanes;
-                stage_issue(r, nb0, (int)min((int64_t)kLanes, B - nb0), cartdim, R, lane);
-            }
-            if (q != nullptr)
-                store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
-            if (MODE != MODE_VALUE && J != nullptr)
-                gather_store(prog.emap + ch.jmap, prog.srcs, (int64_t)ch.nrows * cartdim, P,
-                             J + b0 * jstride + (int64_t)ch.row0 * cartdim, jstride, ntile, ch.accumulate != 0, lane);
-            if (MODE == MODE_QJK && K != nullptr)
-                gather_store(prog.emap + ch.kmap, prog.srcs, (int64_t)ch.nrows * cartdim * cartdim, P,
-                             K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile,
-                             ch.accumulate != 0, lane);
-            __syncwarp();
+        if (staged != tile) stage_issue(r, b0, ntile, cartdim, R, lane);
+        if (staged != tile || c == 0 || it == i0) stage_finish(ntile, cartdim, R, lane);
+        staged = tile;
+        for (int cc = c * cper; cc < (c + 1) * cper; cc++) {
+        const ChunkDesc & ch = chunks[cc];
+        eval_chunk<MODE, HAS5>(prims, ch.prim_begin, ch.prim_end, R, P, lane);
+        if (q != nullptr) combine_rows(qmap + ch.qmap, qsrcs, ch.nrows, P, ch.qslot, lane);
+        __syncwarp();
+        // R is dead after a tile's last chunk: start fetching the next tile now, its DRAM latency
+        // hides behind this chunk's stores
+        if (c == nchunks - 1 && cc == (c + 1) * cper - 1 && it + 1 < i1) {
+            const int64_t nb0 = (tile + 1) * kLanes;
+            stage_issue(r, nb0, (int)min((int64_t)kLanes, B - nb0), cartdim, R, lane);
+            staged = tile + 1;
+        }
+        if (q != nullptr)
+            store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
+        if (MODE != MODE_VALUE && J != nullptr)
+            gather_store(ch.jspan, prog.emap, prog.srcs, prog.runs, P, J + b0 * jstride + (int64_t)ch.row0 * cartdim,
+                         jstride, ntile, ch.accumulate != 0, lane);
+        if (MODE == MODE_QJK && K != nullptr)
+            gather_store(ch.kspan, prog.emap, prog.srcs, prog.runs, P,
+                         K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile, ch.accumulate != 0, lane);
+        __syncwarp();
         }
     }
 }
@@ -124,8 +134,8 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
     int per_sm = 0;
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t ntiles = (B + kLanes - 1) / kLanes;
-    int64_t grid = (ntiles + warps - 1) / warps;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes, items = ntiles * (p.split_rows ? 1 : p.nchunks);
+    int64_t grid = (items + warps - 1) / warps;
     grid = std::min<int64_t>(grid, (int64_t)t->sm_count * per_sm);
     if (grid < 1) return TCHEM_OK;
     void * args[] = {(void *)&p, (void *)&r, (void *)&B, (void *)&q, (void *)&J, (void *)&K};

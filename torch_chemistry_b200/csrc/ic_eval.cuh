@@ -370,29 +370,60 @@ __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint
     }
 }
 
-// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host).
-// Table reads are software-pipelined: while step s runs, the element word of step s+1 and its
-// first source are already in flight (the further sources of an element share its cache line).
-template <bool FULL, bool ACC>
-__device__ __forceinline__ void gather_store_impl(const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
-                                                  int64_t S, const double * P, double * out, uint32_t gbytes,
-                                                  int ntile, int lane) {
-    ElemMap next;
-    Src next_src;
-    next.word = 0u; next.k = 0u;
-    next_src.entry = 0; next_src.pad_ = 0; next_src.coef = 0.0;
-    if (lane < S) {
-        next = load_emap(emap + lane);
-        if (next.word) next_src = load_src(srcs + (next.word & kMapOffsetMask));
-    }
-    for (int64_t k0 = 0; k0 < S; k0 += kLanes) {
-        const bool valid = k0 + lane < S;
-        const ElemMap m = next;
-        const Src first = next_src;
-        if (k0 + kLanes + lane < S) {
-            next = load_emap(emap + k0 + kLanes + lane);
-            if (next.word) next_src = load_src(srcs + (next.word & kMapOffsetMask));
+// a stretch of structural zeros [0, len) of every geometry of the tile: 16-byte stores when the
+// alignment allows, no table lookups
+template <bool FULL>
+__device__ __forceinline__ void zero_run(double * base, uint32_t len, uint32_t gbytes, int ntile, int lane) {
+    const int n = FULL ? kLanes : ntile;
+    char * row = reinterpret_cast<char *>(base);
+    if (((reinterpret_cast<uintptr_t>(base) | gbytes) & 15) == 0) {
+        const uint32_t pairs = len >> 1;
+        for (int g = 0; g < n; g++, row += gbytes) {
+            double2 * p = reinterpret_cast<double2 *>(row);
+#pragma unroll 4
+            for (uint32_t e = lane; e < pairs; e += kLanes) p[e] = make_double2(0.0, 0.0);
+            if ((len & 1) && lane == 0) reinterpret_cast<double *>(row)[len - 1] = 0.0;
         }
+    } else {
+        for (int g = 0; g < n; g++, row += gbytes) {
+            double * p = reinterpret_cast<double *>(row);
+#pragma unroll 4
+            for (uint32_t e = lane; e < len; e += kLanes) p[e] = 0.0;
+        }
+    }
+}
+
+// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host).
+// Table reads are software-pipelined: while step s runs, the element words of steps s+1 and s+2
+// and the first source of step s+1 are already in flight (the further sources of an element
+// share its cache line).
+template <bool FULL, bool ACC>
+__device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const ElemMap * __restrict__ emap_all,
+                                                  const Src * __restrict__ srcs, const ZeroRun * __restrict__ runs,
+                                                  const double * P, double * out, uint32_t gbytes, int ntile, int lane) {
+    if (!ACC)
+        for (int i = 0; i < sp.nruns; i++) {
+            const ZeroRun run = runs[sp.run0 + i];
+            zero_run<FULL>(out + run.k, run.len, gbytes, ntile, lane);
+        }
+    const ElemMap * emap = emap_all + sp.map;
+    const int S = sp.n;
+    ElemMap m1, m2;
+    Src s1;
+    m1.word = 0u; m1.k = 0u; m2 = m1;
+    s1.entry = 0; s1.pad_ = 0; s1.coef = 0.0;
+    if (lane < S) m1 = load_emap(emap + lane);
+    if (lane + kLanes < S) m2 = load_emap(emap + lane + kLanes);
+    if (m1.word) s1 = load_src(srcs + (m1.word & kMapOffsetMask));
+    for (int k0 = 0; k0 < S; k0 += kLanes) {
+        const bool valid = k0 + lane < S;
+        const ElemMap m = m1;
+        const Src first = s1;
+        m1 = m2;
+        m2.word = 0u; m2.k = 0u;
+        if (k0 + 2 * kLanes + lane < S) m2 = load_emap(emap + k0 + 2 * kLanes + lane);
+        s1.coef = 0.0; s1.entry = 0;
+        if (m1.word) s1 = load_src(srcs + (m1.word & kMapOffsetMask));
         const int cnt = (int)(m.word >> kMapCountShift);
         const uint32_t off = m.word & kMapOffsetMask;
         char * o = reinterpret_cast<char *>(out + m.k);
@@ -420,16 +451,16 @@ __device__ __forceinline__ void gather_store_impl(const ElemMap * __restrict__ e
     }
 }
 
-__device__ __forceinline__ void gather_store(const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
-                                             int64_t S, const double * P, double * out, int64_t gstride,
-                                             int ntile, bool accumulate, int lane) {
+__device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
+                                             const ZeroRun * __restrict__ runs, const double * P, double * out,
+                                             int64_t gstride, int ntile, bool accumulate, int lane) {
     const uint32_t gbytes = (uint32_t)(gstride * sizeof(double));
     if (accumulate) {
-        if (ntile == kLanes) gather_store_impl<true, true>(emap, srcs, S, P, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, true>(emap, srcs, S, P, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, true>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
     } else {
-        if (ntile == kLanes) gather_store_impl<true, false>(emap, srcs, S, P, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, false>(emap, srcs, S, P, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, false>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
     }
 }
 

@@ -38,14 +38,28 @@ struct Src {                       // one source of one output element
     double  coef;
 };
 
+// One dense output span (the J rows or the K rows of a chunk): `n` element-map entries starting
+// at emap[map] cover every element that has sources (plus the zeros inside their sectors and short
+// zero stretches); long stretches of structural zeros are listed as runs instead and are stored
+// without any table lookup.
+struct SpanDesc {
+    int64_t map;                   // first ElemMap entry
+    int32_t n;                     // number of ElemMap entries
+    int32_t run0, nruns;           // zero runs in runs[]
+    int32_t pad_;
+};
+
 struct ChunkDesc {
     int32_t prim_begin, prim_end;  // range in prims[]
     int32_t row0, nrows;           // rows (internal coordinates) this chunk produces
     int32_t accumulate;            // != 0: add to what an earlier chunk stored (split row)
     int32_t qslot;                 // first of nrows compact entries that hold the combined q rows
     int64_t qmap;                  // offset into map[]:  nrows words, in row order
-    int64_t jmap, kmap;            // offsets into emap[]: nrows*cartdim and nrows*cartdim^2 entries
+    SpanDesc jspan, kspan;         // nrows*cartdim and nrows*cartdim^2 elements
 };
+
+struct ZeroRun { uint32_t k, len; };   // elements [k, k + len) of a span are structural zeros
+constexpr int kMinZeroRun = 64;
 
 // map word: (count << 24) | first source index
 constexpr uint32_t kMapCountShift = 24;
@@ -67,7 +81,9 @@ struct Program {                   // all pointers are device pointers
     const Src *       qsrcs;
     const ElemMap *   emap;        // J / K elements, sources in srcs
     const Src *       srcs;
+    const ZeroRun *   runs;
     int32_t nqsrcs, nmap;          // sizes of qsrcs[] and map[]
+    int32_t split_rows;            // some row is split into accumulating chunks
     int32_t nprims, nchunks;
     int32_t cap;                   // compact entries per lane
     int32_t intdim, cartdim;

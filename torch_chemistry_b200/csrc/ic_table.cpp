@@ -34,10 +34,12 @@ PrimKey key_of(const tchem_invdisp_t & t) {
 
 } // namespace
 
-int64_t emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
-                  std::vector<ElemMap> & emap, std::vector<Src> & srcs) {
+bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
+               std::vector<ElemMap> & emap, std::vector<Src> & srcs, std::vector<ZeroRun> & runs, SpanDesc & span) {
     const int64_t S = (int64_t)lists.size();
-    const int64_t off0 = (int64_t)emap.size();
+    span.map = (int64_t)emap.size();
+    span.run0 = (int32_t)runs.size();
+    span.pad_ = 0;
     const int64_t shift = (gstride % 4 == 0) ? (abs_off % 4) : 0;     // sector phase of element 0
     struct Unit { int64_t first, last; int maxcnt; };
     std::vector<Unit> units;
@@ -48,21 +50,38 @@ int64_t emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, 
         units.push_back(Unit{k, end, m});
         k = end;
     }
+    // long stretches of all-zero sectors become runs
+    std::vector<char> in_run(units.size(), 0);
+    for (size_t u = 0; u < units.size();) {
+        if (units[u].maxcnt != 0) { u++; continue; }
+        size_t v = u;
+        while (v < units.size() && units[v].maxcnt == 0) v++;
+        const int64_t len = units[v - 1].last - units[u].first;
+        if (len >= kMinZeroRun) {
+            runs.push_back(ZeroRun{(uint32_t)units[u].first, (uint32_t)len});
+            for (size_t w = u; w < v; w++) in_run[w] = 1;
+        }
+        u = v;
+    }
+    std::vector<Unit> rest;
+    for (size_t u = 0; u < units.size(); u++) if (!in_run[u]) rest.push_back(units[u]);
     // rounds of 4 sources: order by the number of rounds, then by 1 / 2 / 3-4 sources inside the
     // last round, keeping the address order otherwise
     auto klass = [](int m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m <= 4 ? 3 : 4 + (m - 1) / 4; };
-    std::stable_sort(units.begin(), units.end(), [&](const Unit & a, const Unit & b) { return klass(a.maxcnt) > klass(b.maxcnt); });
-    for (const Unit & u : units)
+    std::stable_sort(rest.begin(), rest.end(), [&](const Unit & a, const Unit & b) { return klass(a.maxcnt) > klass(b.maxcnt); });
+    for (const Unit & u : rest)
         for (int64_t e = u.first; e < u.last; e++) {
             const auto & l = lists[e];
-            if (l.size() > 255 || srcs.size() + l.size() > kMapOffsetMask) return -1;
+            if (l.size() > 255 || srcs.size() + l.size() > kMapOffsetMask) return false;
             ElemMap m;
             m.word = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)srcs.size());
             m.k = (uint32_t)e;
             emap.push_back(m);
             for (const Src & s : l) srcs.push_back(s);
         }
-    return off0;
+    span.n = (int32_t)(emap.size() - span.map);
+    span.nruns = (int32_t)runs.size() - span.run0;
+    return true;
 }
 
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
@@ -202,9 +221,8 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             }
             return true;
         };
-        auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, int64_t & map_off) {
-            map_off = emit_span(lists, abs_off, gstride, hp.emap, hp.srcs);
-            return map_off >= 0;
+        auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, SpanDesc & span) {
+            return emit_span(lists, abs_off, gstride, hp.emap, hp.srcs, hp.runs, span);
         };
         std::vector<std::vector<Src>> ql(pc.nrows), jl, kl;
         if (mode != MODE_VALUE) jl.resize((size_t)pc.nrows * cd);
@@ -238,8 +256,8 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
                         }
         }
         bool ok = emit(ql, ch.qmap);
-        if (ok && mode != MODE_VALUE) ok = emit_sorted(jl, (int64_t)pc.row0 * cd, (int64_t)n_ic * cd, ch.jmap);
-        if (ok && mode == MODE_QJK) ok = emit_sorted(kl, (int64_t)pc.row0 * cd * cd, (int64_t)n_ic * cd * cd, ch.kmap);
+        if (ok && mode != MODE_VALUE) ok = emit_sorted(jl, (int64_t)pc.row0 * cd, (int64_t)n_ic * cd, ch.jspan);
+        if (ok && mode == MODE_QJK) ok = emit_sorted(kl, (int64_t)pc.row0 * cd * cd, (int64_t)n_ic * cd * cd, ch.kspan);
         if (!ok) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: internal coordinate definition too large for the gather map");
         hp.chunks.push_back(ch);
     }

@@ -26,15 +26,16 @@ struct HostProgram {
     std::vector<uint32_t> map;
     std::vector<ElemMap> emap;
     std::vector<Src> srcs, qsrcs;
+    std::vector<ZeroRun> runs;
     int cap = 0;
 };
 
-// Appends the element map of one dense span (lists[k] = sources of element k) to emap/srcs and
-// returns its offset, or -1 when a list is too long for the encoding. Elements are grouped in
+// Appends the element map of one dense span (lists[k] = sources of element k) to emap/srcs/runs,
+// fills `span`; false when a list is too long for the encoding. Elements are grouped in
 // sectors of 4 (aligned to `abs_off`, the span's element offset inside the geometry block, when
 // the block stride keeps sectors aligned) and the sectors are ordered by source count.
-int64_t emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
-                  std::vector<ElemMap> & emap, std::vector<Src> & srcs);
+bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
+               std::vector<ElemMap> & emap, std::vector<Src> & srcs, std::vector<ZeroRun> & runs, SpanDesc & span);
 
 // pure host: flatten terms into a program for one mode
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,

@@ -25,6 +25,7 @@ struct SapProgram {                               // device pointers
     const ChunkDesc * chunks;                     // prim_begin/end = term range, row0/nrows likewise
     const ElemMap *   emap;
     const Src *       srcs;
+    const ZeroRun *   runs;
     int32_t nterms, nuniqs, nchunks, cap, sumdim;
 };
 
@@ -140,12 +141,11 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
             const ChunkDesc ch = sp.chunks[c];
             eval_sap_terms(sp, ch.prim_begin, ch.prim_end, X, P, lane, J != nullptr);
             __syncwarp();
-            if (y != nullptr)
-                gather_store(sp.emap + ch.qmap, sp.srcs, ch.nrows, P, y + b0 * sp.nterms + ch.row0, sp.nterms,
-                             ntile, false, lane);
+            // monomial values sit in compact entries [0, nrows): written (geometry, term)-flattened
+            if (y != nullptr) store_rows(P, 0, ch.nrows, y + b0 * sp.nterms + ch.row0, sp.nterms, ntile, false, lane);
             if (J != nullptr)
-                gather_store(sp.emap + ch.jmap, sp.srcs, (int64_t)ch.nrows * sumdim, P,
-                             J + (b0 * sp.nterms + ch.row0) * sumdim, (int64_t)sp.nterms * sumdim, ntile, false, lane);
+                gather_store(ch.jspan, sp.emap, sp.srcs, sp.runs, P, J + (b0 * sp.nterms + ch.row0) * sumdim,
+                             (int64_t)sp.nterms * sumdim, ntile, false, lane);
             __syncwarp();
         }
     }
@@ -222,6 +222,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     std::vector<ChunkDesc> chunks;
     std::vector<ElemMap> map;
     std::vector<Src> srcs;
+    std::vector<ZeroRun> runs;
     for (int t0 = 0; t0 < n_terms;) {
         int t1 = t0, entries = 0;
         while (t1 < n_terms && entries + 1 + terms[t1].uend - terms[t1].ubegin <= cap) {
@@ -231,16 +232,13 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
         ChunkDesc ch;
         std::memset(&ch, 0, sizeof(ch));
         ch.prim_begin = t0; ch.prim_end = t1; ch.row0 = t0; ch.nrows = t1 - t0;
-        std::vector<std::vector<Src>> yl(t1 - t0), jl((size_t)(t1 - t0) * sumdim);
+        std::vector<std::vector<Src>> jl((size_t)(t1 - t0) * sumdim);
         const int first = terms[t0].ubegin;
-        for (int t = t0; t < t1; t++) {
-            yl[t - t0].push_back(Src{t - t0, 0, 1.0});
+        for (int t = t0; t < t1; t++)
             for (int u = terms[t].ubegin; u < terms[t].uend; u++)
                 jl[(size_t)(t - t0) * sumdim + uniqs[u].col].push_back(Src{(t1 - t0) + (u - first), 0, 1.0});
-        }
-        ch.qmap = emit_span(yl, t0, n_terms, map, srcs);
-        ch.jmap = emit_span(jl, (int64_t)t0 * sumdim, (int64_t)n_terms * sumdim, map, srcs);
-        if (ch.qmap < 0 || ch.jmap < 0) return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
+        if (!emit_span(jl, (int64_t)t0 * sumdim, (int64_t)n_terms * sumdim, map, srcs, runs, ch.jspan))
+            return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
         chunks.push_back(ch);
         t0 = t1;
     }
@@ -252,13 +250,15 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     const size_t o_chunks = o_uniqs + a16(uniqs.size() * sizeof(SapUniq) + 8);
     const size_t o_map = o_chunks + a16(chunks.size() * sizeof(ChunkDesc));
     const size_t o_srcs = o_map + a16(map.size() * sizeof(ElemMap));
-    const size_t total = o_srcs + a16(srcs.size() * sizeof(Src)) + 16;
+    const size_t o_runs = o_srcs + a16(srcs.size() * sizeof(Src));
+    const size_t total = o_runs + a16(runs.size() * sizeof(ZeroRun)) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SapTerm));
     std::memcpy(blob.data() + o_uniqs, uniqs.data(), uniqs.size() * sizeof(SapUniq));
     std::memcpy(blob.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
     std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(ElemMap));
     std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(Src));
+    std::memcpy(blob.data() + o_runs, runs.data(), runs.size() * sizeof(ZeroRun));
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
     void * dev = nullptr;
@@ -276,6 +276,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     t->prog.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
     t->prog.emap = reinterpret_cast<const ElemMap *>(d + o_map);
     t->prog.srcs = reinterpret_cast<const Src *>(d + o_srcs);
+    t->prog.runs = reinterpret_cast<const ZeroRun *>(d + o_runs);
     t->prog.nterms = n_terms; t->prog.nuniqs = (int)uniqs.size(); t->prog.nchunks = (int)chunks.size();
     t->prog.cap = cap; t->prog.sumdim = sumdim;
     t->dev_blob = dev;
