@@ -16,7 +16,9 @@
 
 namespace tchem_b200 {
 
-struct SapUniq { int32_t col, power; };           // x[col]^power
+// distinct coordinate of a monomial: x[col]^power; e_pow / e_powm1 = entries of the per-lane power
+// table holding x[col]^power and x[col]^(power-1)
+struct SapUniq { int32_t col, power, e_pow, e_powm1; };
 struct SapTerm { int32_t ubegin, uend; };         // distinct coordinates of one monomial
 
 struct SapProgram {                               // device pointers
@@ -26,7 +28,8 @@ struct SapProgram {                               // device pointers
     const ElemMap *   emap;
     const Src *       srcs;
     const ZeroRun *   runs;
-    int32_t nterms, nuniqs, nchunks, cap, sumdim;
+    const int32_t *   pow_off;                    // power table: entries pow_off[col] + p hold x[col]^p, p = 0..maxpow
+    int32_t nterms, nuniqs, nchunks, cap, sumdim, npow;
 };
 
 int ensure_program(tchem_ic_table * t, int mode);
@@ -55,36 +58,33 @@ namespace tchem_b200 {
 
 namespace {
 
-__device__ __forceinline__ double ipow(double x, int p) {
-    double r = 1.0;
-    for (int i = 0; i < p; i++) r *= x;
-    return r;
+// x[col]^p for every power a monomial of the set needs, per lane: XP[(pow_off[col] + p) * kPad + lane]
+__device__ __forceinline__ void build_powers(const int32_t * pow_off, int sumdim, const double * X, double * XP, int lane) {
+    for (int col = 0; col < sumdim; col++) {
+        const int e0 = pow_off[col], e1 = pow_off[col + 1];
+        const double x = X[col * kPad + lane];
+        double v = 1.0;
+        for (int e = e0; e < e1; e++) { XP[e * kPad + lane] = v; v *= x; }
+    }
 }
 
-// evaluate monomials [t0, t1) for this lane's geometry; X[col * kPad + lane]
-__device__ __forceinline__ void eval_sap_terms(const SapProgram & sp, int t0, int t1, const double * X,
-                                               double * P, int lane, bool want_J) {
+// monomials [t0, t1) for this lane's geometry: value = prod x^p (SAP.cpp:93-99),
+// d/dx_u = p x_u^(p-1) prod_{v != u} x_v^(p_v) (SAP.cpp:147-175); factors come from the power table
+__device__ __forceinline__ void eval_sap_terms(const SapTerm * terms, const SapUniq * uniqs, int t0, int t1,
+                                               const double * XP, double * P, int lane, bool want_J) {
+    const int first = terms[t0].ubegin;
     for (int t = t0; t < t1; t++) {
-        const SapTerm term = sp.terms[t];
-        const int first = sp.terms[t0].ubegin;
-        // value: 1 * x * x * ...   (SAP.cpp:93-99)
+        const SapTerm term = terms[t];
         double v = 1.0;
-        for (int u = term.ubegin; u < term.uend; u++) {
-            const SapUniq q = sp.uniqs[u];
-            v *= ipow(X[q.col * kPad + lane], q.power);
-        }
+        for (int u = term.ubegin; u < term.uend; u++) v *= XP[uniqs[u].e_pow * kPad + lane];
         P[(t - t0) * kPad + lane] = v;
         if (!want_J) continue;
-        // d/dx_u = p x_u^(p-1) prod_{v != u} x_v^(p_v)   (SAP.cpp:147-175)
         const int gbase = (t1 - t0) + (term.ubegin - first);
         for (int u = term.ubegin; u < term.uend; u++) {
-            const SapUniq qu = sp.uniqs[u];
-            double g = (double)qu.power * ipow(X[qu.col * kPad + lane], qu.power - 1);
-            for (int w = term.ubegin; w < term.uend; w++) {
-                if (w == u) continue;
-                const SapUniq qw = sp.uniqs[w];
-                g *= ipow(X[qw.col * kPad + lane], qw.power);
-            }
+            const SapUniq qu = uniqs[u];
+            double g = (double)qu.power * XP[qu.e_powm1 * kPad + lane];
+            for (int w = term.ubegin; w < term.uend; w++)
+                if (w != u) g *= XP[uniqs[w].e_pow * kPad + lane];
             P[(gbase + (u - term.ubegin)) * kPad + lane] = g;
         }
     }
@@ -92,54 +92,97 @@ __device__ __forceinline__ void eval_sap_terms(const SapProgram & sp, int t0, in
 
 // CHAINED: x = q(r) evaluated with the compute_IC_J formulas from the IC program (value-mode
 // chunking, one compact entry per primitive); otherwise x is read from global memory.
+// dynamic shared memory: [SapTerm][SapUniq][SAP ChunkDesc][pow_off] and, chained, [PrimDesc][IC ChunkDesc]
+// [q map][q sources]; then per warp: R | PI | X | XP | P
+__device__ __forceinline__ size_t sap_align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <class T> __device__ __forceinline__ T * stage_table(unsigned char *& cursor, const T * src, int n) {
+    T * dst = reinterpret_cast<T *>(cursor);
+    const int words = n * (int)(sizeof(T) / 4);
+    const int32_t * s = reinterpret_cast<const int32_t *>(src);
+    int32_t * d = reinterpret_cast<int32_t *>(dst);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+    cursor += sap_align16(sizeof(T) * n);
+    return dst;
+}
+
 template <bool CHAINED, bool HAS5>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict__ in, const int64_t B,
                 double * __restrict__ q_out, double * __restrict__ y, double * __restrict__ J) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char * cursor = smem_raw;
+    const SapTerm * terms = stage_table(cursor, sp.terms, sp.nterms);
+    const SapUniq * uniqs = stage_table(cursor, sp.uniqs, sp.nuniqs);
+    const ChunkDesc * schunks = stage_table(cursor, sp.chunks, sp.nchunks);
+    const int32_t * pow_off = stage_table(cursor, sp.pow_off, sp.sumdim + 1);
+    const PrimDesc * prims = nullptr;
+    const ChunkDesc * ichunks = nullptr;
+    const uint32_t * qmap = nullptr;
+    const Src * qsrcs = nullptr;
+    if (CHAINED) {
+        prims = stage_table(cursor, ic.prims, ic.nprims);
+        ichunks = stage_table(cursor, ic.chunks, ic.nchunks);
+        qmap = stage_table(cursor, ic.map, ic.nmap);
+        qsrcs = stage_table(cursor, ic.qsrcs, ic.nqsrcs);
+    }
+    __syncthreads();
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int sumdim = sp.sumdim;
     const int cartdim = CHAINED ? ic.cartdim : 0, iccap = CHAINED ? ic.cap : 0;
-    const size_t per_warp = (size_t)(cartdim + iccap + sumdim + sp.cap) * kPad;
-    double * R = reinterpret_cast<double *>(smem_raw) + warp * per_warp;
+    const size_t per_warp = (size_t)(cartdim + iccap + sumdim + sp.npow + sp.cap) * kPad;
+    double * R = reinterpret_cast<double *>(cursor) + warp * per_warp;
     double * PI = R + (size_t)cartdim * kPad;
     double * X = PI + (size_t)iccap * kPad;
-    double * P = X + (size_t)sumdim * kPad;
+    double * XP = X + (size_t)sumdim * kPad;
+    double * P = XP + (size_t)sp.npow * kPad;
     const int64_t ntiles = (B + kLanes - 1) / kLanes;
+    const int64_t tile_step = (int64_t)gridDim.x * nwarps;
+    double * stage_dst = CHAINED ? R : X;
+    const int stage_dim = CHAINED ? cartdim : sumdim;
 
-    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+    if (tile < ntiles) stage_issue(in, tile * kLanes, (int)min((int64_t)kLanes, B - tile * kLanes), stage_dim, stage_dst, lane);
+    for (; tile < ntiles; tile += tile_step) {
         const int64_t b0 = tile * kLanes;
         const int ntile = (int)min((int64_t)kLanes, B - b0);
+        stage_finish(ntile, stage_dim, stage_dst, lane);
         if (CHAINED) {
-            stage_coordinates(in, b0, ntile, cartdim, R, lane);
             for (int c = 0; c < ic.nchunks; c++) {
-                const ChunkDesc ch = ic.chunks[c];
-                for (int p = ch.prim_begin; p < ch.prim_end; p++) { const PrimDesc pd = ic.prims[p]; eval_primitive<MODE_QPATH, HAS5>(pd, TileLoader{R, lane}, CompactSink(PI, pd.out, lane)); }
+                const ChunkDesc & ch = ichunks[c];
+                for (int p = ch.prim_begin; p < ch.prim_end; p++)
+                    eval_primitive<MODE_QPATH, HAS5>(prims[p], TileLoader{R, lane}, CompactSink(PI, prims[p].out, lane));
                 // every lane combines its own column: x[row] = sum coef * q_prim (IntCoord.cpp:66-74)
                 for (int row = 0; row < ch.nrows; row++) {
-                    const uint32_t w = ic.map[ch.qmap + row];
+                    const uint32_t w = qmap[ch.qmap + row];
                     const int cnt = (int)(w >> kMapCountShift);
                     const uint32_t off = w & kMapOffsetMask;
                     double x = 0.0;
-                    for (int j = 0; j < cnt; j++) {
-                        const Src s = ic.qsrcs[off + j];
-                        x = fma(s.coef, PI[s.entry * kPad + lane], x);
-                    }
+                    for (int j = 0; j < cnt; j++) x = fma(qsrcs[off + j].coef, PI[qsrcs[off + j].entry * kPad + lane], x);
                     double * xp = X + (ch.row0 + row) * kPad + lane;
                     *xp = ch.accumulate ? *xp + x : x;
                 }
             }
             __syncwarp();
-            if (q_out != nullptr) {
-                for (int k = lane; k < sumdim; k += kLanes)
-                    for (int g = 0; g < ntile; g++) q_out[(b0 + g) * sumdim + k] = X[k * kPad + g];
+            // R is dead: the next tile's coordinates can start moving now
+            if (tile + tile_step < ntiles) {
+                const int64_t nb0 = (tile + tile_step) * kLanes;
+                stage_issue(in, nb0, (int)min((int64_t)kLanes, B - nb0), stage_dim, stage_dst, lane);
             }
-        } else {
-            stage_coordinates(in, b0, ntile, sumdim, X, lane);
+            if (q_out != nullptr) store_rows(X, 0, sumdim, q_out + b0 * sumdim, sumdim, ntile, false, lane);
+        }
+        build_powers(pow_off, sumdim, X, XP, lane);
+        if (!CHAINED) {
+            __syncwarp();
+            if (tile + tile_step < ntiles) {
+                const int64_t nb0 = (tile + tile_step) * kLanes;
+                stage_issue(in, nb0, (int)min((int64_t)kLanes, B - nb0), stage_dim, stage_dst, lane);
+            }
         }
         for (int c = 0; c < sp.nchunks; c++) {
-            const ChunkDesc ch = sp.chunks[c];
-            eval_sap_terms(sp, ch.prim_begin, ch.prim_end, X, P, lane, J != nullptr);
+            const ChunkDesc & ch = schunks[c];
+            eval_sap_terms(terms, uniqs, ch.prim_begin, ch.prim_end, XP, P, lane, J != nullptr);
             __syncwarp();
             // monomial values sit in compact entries [0, nrows): written (geometry, term)-flattened
             if (y != nullptr) store_rows(P, 0, ch.nrows, y + b0 * sp.nterms + ch.row0, sp.nterms, ntile, false, lane);
@@ -160,10 +203,15 @@ int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const dou
     Program icp;
     std::memset(&icp, 0, sizeof(icp));
     if (chained) icp = ict->prog[MODE_VALUE];
-    const size_t wb = (size_t)((chained ? icp.cartdim + icp.cap : 0) + st->sumdim + st->prog.cap) * kPad * sizeof(double);
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    size_t tb = a16(sizeof(SapTerm) * st->prog.nterms) + a16(sizeof(SapUniq) * st->prog.nuniqs)
+              + a16(sizeof(ChunkDesc) * st->prog.nchunks) + a16(4 * (st->sumdim + 1));
+    if (chained) tb += a16(sizeof(PrimDesc) * icp.nprims) + a16(sizeof(ChunkDesc) * icp.nchunks) + a16(4 * icp.nmap)
+                     + a16(sizeof(Src) * icp.nqsrcs);
+    const size_t wb = (size_t)((chained ? icp.cartdim + icp.cap : 0) + st->sumdim + st->prog.npow + st->prog.cap) * kPad * sizeof(double);
     int warps = 4;
-    while (warps > 1 && warps * wb > (size_t)st->max_smem_optin) warps >>= 1;
-    const size_t smem = warps * wb;
+    while (warps > 1 && tb + warps * wb > (size_t)st->max_smem_optin) warps--;
+    const size_t smem = tb + warps * wb;
     if (smem > (size_t)st->max_smem_optin) return set_error(TCHEM_EINVAL, "tchem_sap_eval: set too large for the shared-memory tile");
     TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -211,14 +259,19 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
             powers[offset[irr] + idx]++;
         }
         terms[t].ubegin = (int32_t)uniqs.size();
-        for (auto & kv : powers) uniqs.push_back(SapUniq{kv.first, kv.second});
+        for (auto & kv : powers) uniqs.push_back(SapUniq{kv.first, kv.second, 0, 0});
         terms[t].uend = (int32_t)uniqs.size();
     }
+    // power table layout: column c owns entries pow_off[c] .. pow_off[c+1]-1 = x^0 .. x^maxpow(c)
+    std::vector<int32_t> maxpow(sumdim, 0), pow_off(sumdim + 1, 0);
+    for (auto & u : uniqs) maxpow[u.col] = std::max(maxpow[u.col], u.power);
+    for (int c = 0; c < sumdim; c++) pow_off[c + 1] = pow_off[c] + maxpow[c] + 1;
+    for (auto & u : uniqs) { u.e_pow = pow_off[u.col] + u.power; u.e_powm1 = u.e_pow - 1; }
     // chunk consecutive terms: entries = terms + their distinct coordinates
     int max_term = 1;
     for (auto & t : terms) max_term = std::max(max_term, 1 + t.uend - t.ubegin);
     const int total_entries = n_terms + (int)uniqs.size();
-    const int cap = std::max(max_term, std::min(total_entries, 64));
+    const int cap = std::max(max_term, std::min(total_entries, 32));
     std::vector<ChunkDesc> chunks;
     std::vector<ElemMap> map;
     std::vector<Src> srcs;
@@ -246,7 +299,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     if (device < 0 || device >= ndev)
         return set_error(TCHEM_ECUDA, "tchem_sap_table_create: no such CUDA device (this library has no CPU path)");
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-    const size_t o_terms = 0, o_uniqs = o_terms + a16(terms.size() * sizeof(SapTerm));
+    const size_t o_terms = 0, o_pow = o_terms + a16(terms.size() * sizeof(SapTerm));
+    const size_t o_uniqs = o_pow + a16(pow_off.size() * 4);
     const size_t o_chunks = o_uniqs + a16(uniqs.size() * sizeof(SapUniq) + 8);
     const size_t o_map = o_chunks + a16(chunks.size() * sizeof(ChunkDesc));
     const size_t o_srcs = o_map + a16(map.size() * sizeof(ElemMap));
@@ -255,6 +309,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SapTerm));
     std::memcpy(blob.data() + o_uniqs, uniqs.data(), uniqs.size() * sizeof(SapUniq));
+    std::memcpy(blob.data() + o_pow, pow_off.data(), pow_off.size() * 4);
     std::memcpy(blob.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
     std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(ElemMap));
     std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(Src));
@@ -273,6 +328,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     unsigned char * d = static_cast<unsigned char *>(dev);
     t->prog.terms = reinterpret_cast<const SapTerm *>(d + o_terms);
     t->prog.uniqs = reinterpret_cast<const SapUniq *>(d + o_uniqs);
+    t->prog.pow_off = reinterpret_cast<const int32_t *>(d + o_pow);
+    t->prog.npow = pow_off[sumdim];
     t->prog.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
     t->prog.emap = reinterpret_cast<const ElemMap *>(d + o_map);
     t->prog.srcs = reinterpret_cast<const Src *>(d + o_srcs);
