@@ -68,24 +68,60 @@ __device__ __forceinline__ void build_powers(const int32_t * pow_off, int sumdim
     }
 }
 
-// monomials [t0, t1) for this lane's geometry: value = prod x^p (SAP.cpp:93-99),
-// d/dx_u = p x_u^(p-1) prod_{v != u} x_v^(p_v) (SAP.cpp:147-175); factors come from the power table
+// one monomial with U distinct coordinates, fully unrolled: every factor is read once from the
+// power table, value = prod x^p (SAP.cpp:93-99), d/dx_u = p x_u^(p-1) prod_{v != u} x_v^(p_v)
+// (SAP.cpp:147-175)
+template <int U>
+__device__ __forceinline__ void eval_sap_term(const SapUniq * uq, const double * XP, double * Pv, double * Pg, bool want_J) {
+    double xp[U > 0 ? U : 1], xm[U > 0 ? U : 1];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        xp[u] = XP[uq[u].e_pow * kPad];
+        xm[u] = (double)uq[u].power * XP[uq[u].e_powm1 * kPad];
+    }
+    double v = 1.0;
+#pragma unroll
+    for (int u = 0; u < U; u++) v *= xp[u];
+    Pv[0] = v;
+    if (!want_J) return;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double g = xm[u];
+#pragma unroll
+        for (int w = 0; w < U; w++)
+            if (w != u) g *= xp[w];
+        Pg[u * kPad] = g;
+    }
+}
+
+// monomials [t0, t1) for this lane's geometry; XP and P have the lane folded in
 __device__ __forceinline__ void eval_sap_terms(const SapTerm * terms, const SapUniq * uniqs, int t0, int t1,
                                                const double * XP, double * P, int lane, bool want_J) {
     const int first = terms[t0].ubegin;
+    XP += lane;
+    P += lane;
     for (int t = t0; t < t1; t++) {
         const SapTerm term = terms[t];
-        double v = 1.0;
-        for (int u = term.ubegin; u < term.uend; u++) v *= XP[uniqs[u].e_pow * kPad + lane];
-        P[(t - t0) * kPad + lane] = v;
-        if (!want_J) continue;
-        const int gbase = (t1 - t0) + (term.ubegin - first);
-        for (int u = term.ubegin; u < term.uend; u++) {
-            const SapUniq qu = uniqs[u];
-            double g = (double)qu.power * XP[qu.e_powm1 * kPad + lane];
-            for (int w = term.ubegin; w < term.uend; w++)
-                if (w != u) g *= XP[uniqs[w].e_pow * kPad + lane];
-            P[(gbase + (u - term.ubegin)) * kPad + lane] = g;
+        const SapUniq * uq = uniqs + term.ubegin;
+        double * Pv = P + (t - t0) * kPad, * Pg = P + ((t1 - t0) + (term.ubegin - first)) * kPad;
+        switch (term.uend - term.ubegin) {
+        case 0: eval_sap_term<0>(uq, XP, Pv, Pg, want_J); break;
+        case 1: eval_sap_term<1>(uq, XP, Pv, Pg, want_J); break;
+        case 2: eval_sap_term<2>(uq, XP, Pv, Pg, want_J); break;
+        case 3: eval_sap_term<3>(uq, XP, Pv, Pg, want_J); break;
+        case 4: eval_sap_term<4>(uq, XP, Pv, Pg, want_J); break;
+        default: {
+            double v = 1.0;
+            for (int u = term.ubegin; u < term.uend; u++) v *= XP[uniqs[u].e_pow * kPad];
+            Pv[0] = v;
+            if (!want_J) break;
+            for (int u = term.ubegin; u < term.uend; u++) {
+                double g = (double)uniqs[u].power * XP[uniqs[u].e_powm1 * kPad];
+                for (int w = term.ubegin; w < term.uend; w++)
+                    if (w != u) g *= XP[uniqs[w].e_pow * kPad];
+                Pg[(u - term.ubegin) * kPad] = g;
+            }
+        }
         }
     }
 }
