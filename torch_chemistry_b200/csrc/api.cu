@@ -154,6 +154,7 @@ int tchem_ic_table_create(const tchem_invdisp_t * terms, int n_terms, int n_ic, 
     }
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&t->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     *out = t;
     return TCHEM_OK;
 }

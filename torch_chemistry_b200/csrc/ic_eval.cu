@@ -2,6 +2,7 @@
 // Replaces, batched: IntCoordSet::operator() / compute_IC_J / compute_IC_J_K
 // (reference source/IC/IntCoordSet.cpp:139-175).
 #include "ic_eval.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 #include "ic_table.h"
@@ -113,20 +114,38 @@ size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
                    double * q, double * J, double * K, cudaStream_t stream) {
     const Program & p = t->prog[mode];
-    // launch shapes: q / q+J run 4 warps per block, 3 blocks per SM (<= 168 registers);
-    // q+J+K 2 warps per block with the full register file
+    // launch shapes (warps per block x resident blocks): the register budget of the q / q+J flavours
+    // allows 12 warps per SM; whichever split of those 12 warps fits the most warps into shared
+    // memory wins (the per-block tables are paid once per block). q+J+K: 2 warps per block.
     const size_t tb = ic_eval_table_bytes(p), wb = ic_eval_warp_bytes(p);
-    int warps = mode == MODE_QJK ? 2 : 4;
-    while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps--;
     const bool has5 = t->has5;
-    const void * fn;
-    if (mode == MODE_QJK)        fn = has5 ? kernel_ptr<MODE_QJK, true, 2, 1>() : kernel_ptr<MODE_QJK, false, 2, 1>();
-    else if (mode == MODE_VALUE) fn = kernel_ptr<MODE_VALUE, false, 4, 3>();
-    else                         fn = has5 ? kernel_ptr<MODE_QJ, true, 4, 3>() : kernel_ptr<MODE_QJ, false, 4, 3>();
+    const void * fn = nullptr;
+    int warps = 0;
+    if (mode == MODE_QJK) {
+        warps = 2;
+        while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps--;
+        fn = has5 ? kernel_ptr<MODE_QJK, true, 2, 1>() : kernel_ptr<MODE_QJK, false, 2, 1>();
+    } else {
+        struct Shape { int nw, nb; const void * fn; };
+        const Shape shapes[3] = {
+            {4, 3, mode == MODE_VALUE ? kernel_ptr<MODE_VALUE, false, 4, 3>() : has5 ? kernel_ptr<MODE_QJ, true, 4, 3>() : kernel_ptr<MODE_QJ, false, 4, 3>()},
+            {6, 2, mode == MODE_VALUE ? kernel_ptr<MODE_VALUE, false, 6, 2>() : has5 ? kernel_ptr<MODE_QJ, true, 6, 2>() : kernel_ptr<MODE_QJ, false, 6, 2>()},
+            {12, 1, mode == MODE_VALUE ? kernel_ptr<MODE_VALUE, false, 12, 1>() : has5 ? kernel_ptr<MODE_QJ, true, 12, 1>() : kernel_ptr<MODE_QJ, false, 12, 1>()}};
+        int best = 0;
+        for (const Shape & sh : shapes) {
+            // largest warp count <= nw that fits, times the blocks that then fit (1 KB reserved per block)
+            int nw = sh.nw;
+            while (nw > 1 && tb + nw * wb > (size_t)t->max_smem_optin) nw--;
+            const size_t per_block = tb + nw * wb + 1024;
+            const int nb = std::min<int>(sh.nb, (int)((size_t)t->max_smem_sm / per_block));
+            if (nw * nb > best) { best = nw * nb; warps = nw; fn = sh.fn; }
+        }
+        if (!fn) { fn = shapes[0].fn; warps = 1; }
+    }
     const size_t smem = tb + warps * wb;
     // the gather addresses geometry g of a tile as base + g * stride_bytes in 32 bits
     const double widest = 8.0 * p.intdim * p.cartdim * (mode == MODE_QJK ? (double)p.cartdim : 1.0);
-    if (widest * kLanes >= 4294967296.0)
+    if (widest * kLanes >= 2147483648.0)
         return set_error(TCHEM_EINVAL, "tchem_ic_eval: per-geometry output block too large");
     if (smem > (size_t)t->max_smem_optin)
         return set_error(TCHEM_EINVAL, "tchem_ic_eval: molecule too large for the shared-memory tile (cartdim + row capacity)");
@@ -138,6 +157,9 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
     int64_t grid = (items + warps - 1) / warps;
     grid = std::min<int64_t>(grid, (int64_t)t->sm_count * per_sm);
     if (grid < 1) return TCHEM_OK;
+    static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
+    if (debug) fprintf(stderr, "[tchem] ic_eval mode %d: grid %lld x %d threads, %zu B smem (%zu tables + %d x %zu), %d blocks/SM, cap %d, %d chunks\n",
+                       mode, (long long)grid, warps * 32, smem, tb, warps, wb, per_sm, p.cap, p.nchunks);
     void * args[] = {(void *)&p, (void *)&r, (void *)&B, (void *)&q, (void *)&J, (void *)&K};
     TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
     count_launch();

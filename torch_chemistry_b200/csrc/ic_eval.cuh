@@ -343,13 +343,13 @@ __device__ __forceinline__ ElemMap load_emap(const ElemMap * p) {
 
 template <int NS, bool FULL, bool ACC>
 __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const Src & first,
-                                             const double * P, char * o, uint32_t gbytes, int ntile) {
+                                             const double * P, const double * zero, char * o, int gbytes, int ntile) {
     double c[NS];
     const double * p[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         c[j] = 0.0;
-        p[j] = P;
+        p[j] = zero;
         if (j < cnt) {
             const Src s = j == 0 ? first : load_src(srcs + off + j);
             c[j] = s.coef;
@@ -359,24 +359,25 @@ __device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint
     const int n = FULL ? kLanes : ntile;
 #pragma unroll 8
     for (int g = 0; g < n; g++) {
+        // (predicated on purpose: unconditional reads of the zero row measured slower - they add
+        // shared-memory wavefronts to steps where most lanes have fewer than NS sources)
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; j++)
             if (j < cnt) v = fma(c[j], p[j][g], v);
-        double * og = reinterpret_cast<double *>(o);
+        double * og = reinterpret_cast<double *>(o + (int64_t)g * gbytes);
         if (ACC) v += *og;
         *og = v;
-        o += gbytes;
     }
 }
 
 // a stretch of structural zeros [0, len) of every geometry of the tile: 16-byte stores when the
 // alignment allows, no table lookups
 template <bool FULL>
-__device__ __forceinline__ void zero_run(double * base, uint32_t len, uint32_t gbytes, int ntile, int lane) {
+__device__ __forceinline__ void zero_run(double * base, uint32_t len, int gbytes, int ntile, int lane) {
     const int n = FULL ? kLanes : ntile;
     char * row = reinterpret_cast<char *>(base);
-    if (((reinterpret_cast<uintptr_t>(base) | gbytes) & 15) == 0) {
+    if (((reinterpret_cast<uintptr_t>(base) | (uint32_t)gbytes) & 15) == 0) {
         const uint32_t pairs = len >> 1;
         for (int g = 0; g < n; g++, row += gbytes) {
             double2 * p = reinterpret_cast<double2 *>(row);
@@ -400,7 +401,8 @@ __device__ __forceinline__ void zero_run(double * base, uint32_t len, uint32_t g
 template <bool FULL, bool ACC>
 __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const ElemMap * __restrict__ emap_all,
                                                   const Src * __restrict__ srcs, const ZeroRun * __restrict__ runs,
-                                                  const double * P, double * out, uint32_t gbytes, int ntile, int lane) {
+                                                  const double * P, const double * zero, double * out, int gbytes,
+                                                  int ntile, int lane) {
     if (!ACC)
         for (int i = 0; i < sp.nruns; i++) {
             const ZeroRun run = runs[sp.run0 + i];
@@ -432,21 +434,21 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
             if (valid && !ACC) {
                 const int n = FULL ? kLanes : ntile;
 #pragma unroll 8
-                for (int g = 0; g < n; g++) { *reinterpret_cast<double *>(o) = 0.0; o += gbytes; }
+                for (int g = 0; g < n; g++) *reinterpret_cast<double *>(o + (int64_t)g * gbytes) = 0.0;
             }
             continue;
         }
         if (!valid) continue;
         {   // first round
-            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
-            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
-            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, first, P, o, gbytes, ntile);
+            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
+            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
+            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
         }
         for (int base = 4; base < maxcnt; base += 4) {     // rare: more than 4 sources
             Src f2;
             f2.entry = 0; f2.pad_ = 0; f2.coef = 0.0;
             if (cnt > base) f2 = load_src(srcs + off + base);
-            gather_round<4, FULL, true>(srcs, off + base, cnt - base, f2, P, o, gbytes, ntile);
+            gather_round<4, FULL, true>(srcs, off + base, cnt - base, f2, P, zero, o, gbytes, ntile);
         }
     }
 }
@@ -454,15 +456,17 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
 __device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
                                              const ZeroRun * __restrict__ runs, const double * P, double * out,
                                              int64_t gstride, int ntile, bool accumulate, int lane) {
-    const uint32_t gbytes = (uint32_t)(gstride * sizeof(double));
+    const int gbytes = (int)(gstride * sizeof(double));
+    const double * zero = P;
     if (accumulate) {
-        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, true>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, true>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
     } else {
-        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, false>(sp, emap, srcs, runs, P, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, false>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
     }
 }
+
 
 // ---------------------------------------------------------------------------------------
 // q rows of a chunk: every lane combines its own geometry, q[row] = sum coef * q_prim

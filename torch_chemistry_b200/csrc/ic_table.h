@@ -11,6 +11,7 @@ struct tchem_ic_table {
     int sm_count = 0;
     bool has5 = false;            // any 5-atom (torsion2 family) term
     int max_smem_optin = 0;
+    int max_smem_sm = 0;          // shared memory per SM
     std::vector<tchem_invdisp_t> terms;
     tchem_b200::Program prog[tchem_b200::MODE_COUNT];       // device pointers
     void * dev_blob[tchem_b200::MODE_COUNT] = {nullptr, nullptr, nullptr};
