@@ -200,16 +200,44 @@ __device__ void block_add_gK(const DenseProgram & dp, const double * rg, const d
     __syncthreads();
 }
 
-__device__ __forceinline__ void block_load(const double * __restrict__ g, double * s, int rows, int cols, int ld) {
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
-        const int r = i / cols, c = i - r * cols;
-        s[r * ld + c] = __ldcs(g + i);
+// global [rows][cols] -> shared [rows][ld], asynchronously (cp.async; 16 bytes per copy when the row
+// pitch allows, else 8): the caller overlaps the transfer with arithmetic and calls
+// block_load_wait() + __syncthreads() before touching the tile. One warp per row at a time.
+__device__ __forceinline__ void block_load_async(const double * __restrict__ g, double * s, int rows, int cols, int ld) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+    for (int r = warp; r < rows; r += nwarps) {
+        const double * src = g + (int64_t)r * cols;
+        double * dst = s + r * ld;
+        if (vec) {
+            for (int c = 2 * lane; c < cols; c += 2 * kLanes) {
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + c) : "memory");
+            }
+        } else {
+            for (int c = lane; c < cols; c += kLanes) {
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + c);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + c) : "memory");
+            }
+        }
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
+__device__ __forceinline__ void block_load_wait() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// shared [rows][ld] -> global [rows][cols], one warp per row at a time (no index division)
 __device__ __forceinline__ void block_store(const double * s, double * __restrict__ g, int rows, int cols, int ld) {
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
-        const int r = i / cols, c = i - r * cols;
-        __stcs(g + i, s[r * ld + c]);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+    for (int r = warp; r < rows; r += nwarps) {
+        const double * src = s + r * ld;
+        double * dst = g + (int64_t)r * cols;
+        if (vec) {
+            for (int c = 2 * lane; c < cols; c += 2 * kLanes)
+                __stcs(reinterpret_cast<double2 *>(dst + c), *reinterpret_cast<const double2 *>(src + c));
+        } else {
+            for (int c = lane; c < cols; c += kLanes) __stcs(dst + c, src[c]);
+        }
     }
 }
 
@@ -229,10 +257,13 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
         for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i * lda + j] = (i == j) ? sd : A[i * lda + j] * isd;
         __syncthreads();
         // trailing update of the lower triangle: A[i][k] -= A[i][j] * A[k][j], j < k <= i
-        const int m = n - j - 1;
-        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-            const int i = j + 1 + e / m, k = j + 1 + e % m;
-            if (k <= i) A[i * lda + k] -= A[i * lda + j] * A[k * lda + j];
+        // (16 x 16 thread grid striding over rows and columns: no index division)
+        {
+            const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, ny = blockDim.x >> 4;
+            for (int i = j + 1 + ty; i < n; i += ny) {
+                const double lij = A[i * lda + j];
+                for (int k = j + 1 + tx; k <= i; k += 16) A[i * lda + k] -= lij * A[k * lda + j];
+            }
         }
         __syncthreads();
     }
@@ -243,9 +274,17 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
         for (int i = 0; i < c; i++) W[i * ldw + c] = 0.0;
         W[c * ldw + c] = 1.0 / A[c * lda + c];
         for (int i = c + 1; i < n; i++) {
-            double s = 0.0;
-            for (int k = c; k < i; k++) s = fma(A[i * lda + k], W[k * ldw + c], s);
-            W[i * ldw + c] = -s / A[i * lda + i];
+            // four independent partial sums: the dot product is latency bound otherwise
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = c;
+            for (; k + 3 < i; k += 4) {
+                s0 = fma(A[i * lda + k], W[k * ldw + c], s0);
+                s1 = fma(A[i * lda + k + 1], W[(k + 1) * ldw + c], s1);
+                s2 = fma(A[i * lda + k + 2], W[(k + 2) * ldw + c], s2);
+                s3 = fma(A[i * lda + k + 3], W[(k + 3) * ldw + c], s3);
+            }
+            for (; k < i; k++) s0 = fma(A[i * lda + k], W[k * ldw + c], s0);
+            W[i * ldw + c] = -((s0 + s1) + (s2 + s3)) / A[i * lda + i];
         }
     }
     __syncthreads();
@@ -299,8 +338,10 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         if (OP == 2) {
             double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
             for (int i = threadIdx.x; i < n; i += blockDim.x) v1[i] = in1[b * n + i];
-            block_load(in2 + b * (int64_t)n * n, X, n, n, ldh);
+            block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh);    // in flight while J is formed
             block_compute_J<HAS5>(dp, rg, J);                             // syncs
+            block_load_wait();
+            __syncthreads();
             block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj);      // T = H_q J
             __syncthreads();
             for (int i = threadIdx.x; i < cd * ldj; i += blockDim.x) X[i] = 0.0;
@@ -321,14 +362,18 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         const bool ok = block_spd_inverse(n, A, ldh, W, ldh);                        // A = (J J^T)^-1
         if (!ok && threadIdx.x == 0) atomicExch(status, 1);
         if (OP == 1) {
-            // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203)
+            // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203, without forming inv J)
             for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
-            __syncthreads();
-            block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj);   // M = inv J
             __syncthreads();
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 double s = 0.0;
-                for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
+                for (int k = 0; k < cd; k++) s = fma(J[i * ldj + k], v1[k], s);
+                v2[i] = s;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double s = 0.0;
+                for (int k = 0; k < n; k++) s = fma(A[i * ldh + k], v2[k], s);
                 out[b * n + i] = s;
             }
             __syncthreads();
@@ -350,7 +395,8 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
             for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
             v2[i] = s;
         }
-        block_load(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj);
+        block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj);
+        block_load_wait();
         __syncthreads();
         block_add_gK<HAS5>(dp, rg, v2, -1.0, Hc, ldj);                   // Hc = H_r - sum g_q K
         block_dgemm<false, true, false>(cd, n, cd, Hc, ldj, Mreg, ldj, T2, ldh);     // T2 = Hc M^T
