@@ -163,13 +163,14 @@ TCHEM_API int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_
 /* ---- introspection (host only, no device needed; used by the CPU tests) ------------------------ */
 /* Compiles the definition for `mode` (0 value path, 1 q+J, 2 q+J+K) exactly as
  * tchem_ic_table_create does and reports the sizes of the resulting program:
- * counts[0..7] = primitives, chunks, q-map words, q sources, element-map entries, element
- * sources, compact capacity, zero runs. With non-NULL pointers the arrays themselves are copied out
- * (layouts: torch_chemistry_b200/csrc/ic_program.h: PrimDesc, ChunkDesc, uint32, Src, ElemMap, Src,
- * ZeroRun). */
+ * counts[0..8] (room for 16) = primitives, chunks, q-map words, q sources, element-map entries,
+ * packed element sources (uint32 words, 4 per quad), compact capacity, zero runs, distinct
+ * coefficients. With non-NULL pointers the arrays themselves are copied out (layouts:
+ * torch_chemistry_b200/csrc/ic_program.h: PrimDesc, ChunkDesc, uint32, Src, ElemMap, uint32,
+ * ZeroRun, double). */
 TCHEM_API int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int mode,
                                       int64_t * counts, void * prims, void * chunks, uint32_t * map, void * qsrcs,
-                                      void * emap, void * srcs, void * runs);
+                                      void * emap, void * srcs, void * runs, double * coefs);
 
 /* ---- measurement helpers (bench.py only) ------------------------------------------------ */
 /* number of kernels this library has launched in this process so far */

@@ -45,15 +45,15 @@ def export(text, fmt, cartdim, mode):
     capi.check(lib.tchem_ic_parse_text(fmt.encode(), text.encode(), None, 0, C.byref(nt), C.byref(nic)))
     terms = (capi.InvDisp * nt.value)()
     capi.check(lib.tchem_ic_parse_text(fmt.encode(), text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
-    counts = (C.c_int64 * 8)()
-    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, None, None, None, None, None, None, None))
+    counts = (C.c_int64 * 16)()
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, None, None, None, None, None, None, None, None))
     prims, chunks = (PrimDesc * counts[0])(), (ChunkDesc * counts[1])()
     qmap, qsrcs = (C.c_uint32 * max(counts[2], 1))(), (Src * max(counts[3], 1))()
-    emap, srcs = (ElemMap * max(counts[4], 1))(), (Src * max(counts[5], 1))()
-    runs = (ZeroRun * max(counts[7], 1))()
-    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, prims, chunks, qmap, qsrcs, emap, srcs, runs))
-    return dict(prims=prims, chunks=chunks, qmap=qmap, qsrcs=qsrcs, emap=emap, srcs=srcs, runs=runs, cap=counts[6], nic=nic.value,
-                nruns=counts[7])
+    emap, psrcs = (ElemMap * max(counts[4], 1))(), (C.c_uint32 * max(counts[5], 1))()
+    runs, coefs = (ZeroRun * max(counts[7], 1))(), (C.c_double * max(counts[8], 1))()
+    capi.check(lib.tchem_ic_program_export(terms, nt.value, nic.value, cartdim, mode, counts, prims, chunks, qmap, qsrcs, emap, psrcs, runs, coefs))
+    return dict(prims=prims, chunks=chunks, qmap=qmap, qsrcs=qsrcs, emap=emap, psrcs=psrcs, coefs=coefs, runs=runs, cap=counts[6],
+                nic=nic.value, nruns=counts[7])
 
 
 def interpret(prog, r, mode):
@@ -86,11 +86,19 @@ def interpret(prog, r, mode):
                                 P[kbase + 9 * blk + 3 * c + e] = Kl[:, 3 * i + c, 3 * j + e]
         assert ch.qslot + ch.nrows <= prog["cap"]
 
-        def gather(word, table):
+        def gather(word, table):                        # q rows: 16-byte (entry, coefficient) records
             cnt, off = word >> 24, word & 0xFFFFFF
             v = np.zeros(B)
             for s in range(off, off + cnt):
                 v = v + table[s].coef * P[table[s].entry]
+            return v
+
+        def gather_packed(word):                        # J / K elements: packed sources, quad aligned
+            cnt, quad = word >> 24, word & 0xFFFFFF
+            v = np.zeros(B)
+            for s in range(4 * quad, 4 * quad + cnt):
+                w = prog["psrcs"][s]
+                v = v + prog["coefs"][w >> 16] * P[w & 0xFFFF]
             return v
 
         for row in range(ch.nrows):
@@ -112,7 +120,7 @@ def interpret(prog, r, mode):
                 m = prog["emap"][sd.map + e]
                 assert not seen[m.k], "element emitted twice"
                 seen[m.k] = True
-                v = gather(m.word, prog["srcs"])
+                v = gather_packed(m.word)
                 flat[:, base + m.k] = v + (flat[:, base + m.k] if ch.accumulate else 0.0)
             assert seen.all(), "element map and zero runs do not cover the span"
     return q, J, K

@@ -66,7 +66,7 @@ _sig("tchem_ic_grad_cart2int_matrix", _int, _vp, _dp, _i64, _dp, _vp)
 _sig("tchem_ic_hess_int2cart", _int, _vp, _dp, _dp, _dp, _i64, _dp, _vp)
 _sig("tchem_ic_hess_cart2int", _int, _vp, _dp, _dp, _dp, _i64, _dp, _vp)
 _sig("tchem_ic_factor_status", _int, _vp)
-_sig("tchem_ic_program_export", _int, C.POINTER(InvDisp), _int, _int, _int, _int, C.POINTER(C.c_int64), _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig("tchem_ic_program_export", _int, C.POINTER(InvDisp), _int, _int, _int, _int, C.POINTER(C.c_int64), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _sig("tchem_sap_eval", _int, _vp, _dp, _i64, _dp, _dp, _vp)
 _sig("tchem_ic_sap_eval", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp, _vp)
 _sig("tchem_ic_sap_eval_host", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp)

@@ -38,7 +38,8 @@ int ensure_program(tchem_ic_table * t, int mode) {
     const size_t o_qsrcs = o_map + a16(hp.map.size() * sizeof(uint32_t));
     const size_t o_emap = o_qsrcs + a16(hp.qsrcs.size() * sizeof(Src));
     const size_t o_srcs = o_emap + a16(hp.emap.size() * sizeof(ElemMap));
-    const size_t o_runs = o_srcs + a16(hp.srcs.size() * sizeof(Src));
+    const size_t o_coefs = o_srcs + a16(hp.psrcs.size() * sizeof(uint32_t));
+    const size_t o_runs = o_coefs + a16(hp.coefs.size() * sizeof(double));
     const size_t total = o_runs + a16(hp.runs.size() * sizeof(ZeroRun)) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_runs, hp.runs.data(), hp.runs.size() * sizeof(ZeroRun));
@@ -47,7 +48,8 @@ int ensure_program(tchem_ic_table * t, int mode) {
     std::memcpy(blob.data() + o_map, hp.map.data(), hp.map.size() * sizeof(uint32_t));
     std::memcpy(blob.data() + o_qsrcs, hp.qsrcs.data(), hp.qsrcs.size() * sizeof(Src));
     std::memcpy(blob.data() + o_emap, hp.emap.data(), hp.emap.size() * sizeof(ElemMap));
-    std::memcpy(blob.data() + o_srcs, hp.srcs.data(), hp.srcs.size() * sizeof(Src));
+    std::memcpy(blob.data() + o_srcs, hp.psrcs.data(), hp.psrcs.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + o_coefs, hp.coefs.data(), hp.coefs.size() * sizeof(double));
     DeviceGuard guard(t->device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
     void * dev = nullptr;
@@ -65,7 +67,9 @@ int ensure_program(tchem_ic_table * t, int mode) {
     p.split_rows = 0;
     for (const ChunkDesc & ch : hp.chunks) if (ch.accumulate) p.split_rows = 1;
     p.emap = reinterpret_cast<const ElemMap *>(d + o_emap);
-    p.srcs = reinterpret_cast<const Src *>(d + o_srcs);
+    p.psrcs = reinterpret_cast<const uint4 *>(d + o_srcs);
+    p.coefs = reinterpret_cast<const double *>(d + o_coefs);
+    p.ncoefs = (int)hp.coefs.size();
     p.runs = reinterpret_cast<const ZeroRun *>(d + o_runs);
     p.nprims = (int)hp.prims.size();
     p.nchunks = (int)hp.chunks.size();
@@ -202,7 +206,7 @@ int tchem_ic_eval(const tchem_ic_table * tc, const double * r, int64_t B, double
 
 int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int mode,
                             int64_t * counts, void * prims, void * chunks, uint32_t * map, void * qsrcs,
-                            void * emap, void * srcs, void * runs) {
+                            void * emap, void * srcs, void * runs, double * coefs) {
     if (!terms || !counts || n_terms <= 0 || n_ic <= 0 || mode < 0 || mode >= MODE_COUNT)
         return set_error(TCHEM_EINVAL, "tchem_ic_program_export: bad arguments");
     std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
@@ -210,7 +214,8 @@ int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic
     int rc = build_program(v, n_ic, cartdim, mode, hp);
     if (rc != TCHEM_OK) return rc;
     counts[0] = (int64_t)hp.prims.size(); counts[1] = (int64_t)hp.chunks.size(); counts[2] = (int64_t)hp.map.size();
-    counts[3] = (int64_t)hp.qsrcs.size(); counts[4] = (int64_t)hp.emap.size(); counts[5] = (int64_t)hp.srcs.size();
+    counts[3] = (int64_t)hp.qsrcs.size(); counts[4] = (int64_t)hp.emap.size(); counts[5] = (int64_t)hp.psrcs.size();
+    counts[8] = (int64_t)hp.coefs.size();
     counts[6] = hp.cap;
     counts[7] = (int64_t)hp.runs.size();
     if (runs) std::memcpy(runs, hp.runs.data(), hp.runs.size() * sizeof(ZeroRun));
@@ -219,7 +224,8 @@ int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms, int n_ic
     if (map) std::memcpy(map, hp.map.data(), hp.map.size() * sizeof(uint32_t));
     if (qsrcs) std::memcpy(qsrcs, hp.qsrcs.data(), hp.qsrcs.size() * sizeof(Src));
     if (emap) std::memcpy(emap, hp.emap.data(), hp.emap.size() * sizeof(ElemMap));
-    if (srcs) std::memcpy(srcs, hp.srcs.data(), hp.srcs.size() * sizeof(Src));
+    if (srcs) std::memcpy(srcs, hp.psrcs.data(), hp.psrcs.size() * sizeof(uint32_t));
+    if (coefs) std::memcpy(coefs, hp.coefs.data(), hp.coefs.size() * sizeof(double));
     return TCHEM_OK;
 }
 

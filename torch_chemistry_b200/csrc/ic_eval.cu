@@ -29,6 +29,10 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
     off += align16(sizeof(Src) * prog.nqsrcs);
     uint32_t * qmap = reinterpret_cast<uint32_t *>(smem_raw + off);
     off += align16(sizeof(uint32_t) * prog.nmap);
+    const int ncoef_s = prog.ncoefs <= kMaxStagedCoefs ? prog.ncoefs : 0;
+    double * coef_s = reinterpret_cast<double *>(smem_raw + off);
+    off += align16(sizeof(double) * ncoef_s);
+    const double * coefs = ncoef_s ? coef_s : prog.coefs;
     double * warp_base = reinterpret_cast<double *>(smem_raw + off);
 
     // stage the definition tables once per block (coalesced 4-byte copies)
@@ -47,6 +51,7 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         for (int i = threadIdx.x; i < n3; i += blockDim.x) dst3[i] = src3[i];
         const int n4 = prog.nmap;
         for (int i = threadIdx.x; i < n4; i += blockDim.x) qmap[i] = prog.map[i];
+        for (int i = threadIdx.x; i < ncoef_s; i += blockDim.x) coef_s[i] = prog.coefs[i];
     }
     __syncthreads();
 
@@ -89,10 +94,10 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         if (q != nullptr)
             store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
         if (MODE != MODE_VALUE && J != nullptr)
-            gather_store(ch.jspan, prog.emap, prog.srcs, prog.runs, P, J + b0 * jstride + (int64_t)ch.row0 * cartdim,
+            gather_store(ch.jspan, prog.emap, prog.psrcs, coefs, prog.runs, P, J + b0 * jstride + (int64_t)ch.row0 * cartdim,
                          jstride, ntile, ch.accumulate != 0, lane);
         if (MODE == MODE_QJK && K != nullptr)
-            gather_store(ch.kspan, prog.emap, prog.srcs, prog.runs, P,
+            gather_store(ch.kspan, prog.emap, prog.psrcs, coefs, prog.runs, P,
                          K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile, ch.accumulate != 0, lane);
         __syncwarp();
         }
@@ -106,7 +111,7 @@ template <int MODE, bool HAS5, int NW, int NB> const void * kernel_ptr() { retur
 size_t ic_eval_table_bytes(const Program & p) {
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     return a16(sizeof(PrimDesc) * p.nprims) + a16(sizeof(ChunkDesc) * p.nchunks) + a16(sizeof(Src) * p.nqsrcs)
-         + a16(sizeof(uint32_t) * p.nmap);
+         + a16(sizeof(uint32_t) * p.nmap) + a16(sizeof(double) * (p.ncoefs <= kMaxStagedCoefs ? p.ncoefs : 0));
 }
 size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap) * kPad * sizeof(double); }
 

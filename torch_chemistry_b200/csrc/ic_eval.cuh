@@ -326,14 +326,9 @@ __device__ __forceinline__ void eval_chunk(const PrimDesc * prims, int p0, int p
 // sources per element are held in registers; elements with more take further rounds that
 // accumulate.
 // ---------------------------------------------------------------------------------------
-// read-only table loads through the non-coherent path (L1-resident: the tables are re-read by
-// every warp for every tile)
-__device__ __forceinline__ Src load_src(const Src * p) {
-    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
-    Src s;
-    s.entry = v.x; s.pad_ = 0; s.coef = __hiloint2double(v.w, v.z);
-    return s;
-}
+// read-only table loads through the non-coherent path
+__device__ __forceinline__ uint4 load_quad(const uint4 * p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t quad_get(const uint4 & q, int j) { return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w; }
 __device__ __forceinline__ ElemMap load_emap(const ElemMap * p) {
     const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
     ElemMap m;
@@ -341,25 +336,26 @@ __device__ __forceinline__ ElemMap load_emap(const ElemMap * p) {
     return m;
 }
 
+// one round of <= NS (<= 4) sources per element, all of them in the quad `q`
 template <int NS, bool FULL, bool ACC>
-__device__ __forceinline__ void gather_round(const Src * __restrict__ srcs, uint32_t off, int cnt, const Src & first,
-                                             const double * P, const double * zero, char * o, int gbytes, int ntile) {
+__device__ __forceinline__ void gather_round(const uint4 & q, int cnt, const double * __restrict__ coefs,
+                                             const double * P, char * o, int gbytes, int ntile) {
     double c[NS];
     const double * p[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         c[j] = 0.0;
-        p[j] = zero;
+        p[j] = P;
         if (j < cnt) {
-            const Src s = j == 0 ? first : load_src(srcs + off + j);
-            c[j] = s.coef;
-            p[j] = P + s.entry * kPad;
+            const uint32_t s = quad_get(q, j);
+            c[j] = coefs[s >> 16];
+            p[j] = P + (s & kSrcEntryMask) * kPad;
         }
     }
     const int n = FULL ? kLanes : ntile;
 #pragma unroll 8
     for (int g = 0; g < n; g++) {
-        // (predicated on purpose: unconditional reads of the zero row measured slower - they add
+        // (predicated on purpose: unconditional reads of a zero row measured slower - they add
         // shared-memory wavefronts to steps where most lanes have fewer than NS sources)
         double v = 0.0;
 #pragma unroll
@@ -394,15 +390,14 @@ __device__ __forceinline__ void zero_run(double * base, uint32_t len, int gbytes
     }
 }
 
-// the byte distance between consecutive geometries of a tile fits 32 bits (checked on the host).
+// the byte distance between consecutive geometries of a tile fits 31 bits (checked on the host).
 // Table reads are software-pipelined: while step s runs, the element words of steps s+1 and s+2
-// and the first source of step s+1 are already in flight (the further sources of an element
-// share its cache line).
+// and the source quad of step s+1 are already in flight.
 template <bool FULL, bool ACC>
 __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const ElemMap * __restrict__ emap_all,
-                                                  const Src * __restrict__ srcs, const ZeroRun * __restrict__ runs,
-                                                  const double * P, const double * zero, double * out, int gbytes,
-                                                  int ntile, int lane) {
+                                                  const uint4 * __restrict__ psrcs, const double * __restrict__ coefs,
+                                                  const ZeroRun * __restrict__ runs, const double * P, double * out,
+                                                  int gbytes, int ntile, int lane) {
     if (!ACC)
         for (int i = 0; i < sp.nruns; i++) {
             const ZeroRun run = runs[sp.run0 + i];
@@ -411,21 +406,19 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
     const ElemMap * emap = emap_all + sp.map;
     const int S = sp.n;
     ElemMap m1, m2;
-    Src s1;
+    uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
     m1.word = 0u; m1.k = 0u; m2 = m1;
-    s1.entry = 0; s1.pad_ = 0; s1.coef = 0.0;
     if (lane < S) m1 = load_emap(emap + lane);
     if (lane + kLanes < S) m2 = load_emap(emap + lane + kLanes);
-    if (m1.word) s1 = load_src(srcs + (m1.word & kMapOffsetMask));
+    if (m1.word) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
     for (int k0 = 0; k0 < S; k0 += kLanes) {
         const bool valid = k0 + lane < S;
         const ElemMap m = m1;
-        const Src first = s1;
+        const uint4 q = q1;
         m1 = m2;
         m2.word = 0u; m2.k = 0u;
         if (k0 + 2 * kLanes + lane < S) m2 = load_emap(emap + k0 + 2 * kLanes + lane);
-        s1.coef = 0.0; s1.entry = 0;
-        if (m1.word) s1 = load_src(srcs + (m1.word & kMapOffsetMask));
+        if (m1.word) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
         const int cnt = (int)(m.word >> kMapCountShift);
         const uint32_t off = m.word & kMapOffsetMask;
         char * o = reinterpret_cast<char *>(out + m.k);
@@ -440,33 +433,31 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
         }
         if (!valid) continue;
         {   // first round
-            if (maxcnt == 1)      gather_round<1, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
-            else if (maxcnt == 2) gather_round<2, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
-            else                  gather_round<4, FULL, ACC>(srcs, off, cnt, first, P, zero, o, gbytes, ntile);
+            if (maxcnt == 1)      gather_round<1, FULL, ACC>(q, cnt, coefs, P, o, gbytes, ntile);
+            else if (maxcnt == 2) gather_round<2, FULL, ACC>(q, cnt, coefs, P, o, gbytes, ntile);
+            else                  gather_round<4, FULL, ACC>(q, cnt, coefs, P, o, gbytes, ntile);
         }
         for (int base = 4; base < maxcnt; base += 4) {     // rare: more than 4 sources
-            Src f2;
-            f2.entry = 0; f2.pad_ = 0; f2.coef = 0.0;
-            if (cnt > base) f2 = load_src(srcs + off + base);
-            gather_round<4, FULL, true>(srcs, off + base, cnt - base, f2, P, zero, o, gbytes, ntile);
+            uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
+            if (cnt > base) q2 = load_quad(psrcs + off + base / 4);
+            gather_round<4, FULL, true>(q2, cnt - base, coefs, P, o, gbytes, ntile);
         }
     }
 }
 
-__device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const Src * __restrict__ srcs,
-                                             const ZeroRun * __restrict__ runs, const double * P, double * out,
-                                             int64_t gstride, int ntile, bool accumulate, int lane) {
+// `coefs` = the table of distinct coefficients (shared-memory copy when it is small)
+__device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const uint4 * __restrict__ psrcs,
+                                             const double * __restrict__ coefs, const ZeroRun * __restrict__ runs,
+                                             const double * P, double * out, int64_t gstride, int ntile, bool accumulate, int lane) {
     const int gbytes = (int)(gstride * sizeof(double));
-    const double * zero = P;
     if (accumulate) {
-        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, true>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, true>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane);
     } else {
-        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
-        else                 gather_store_impl<false, false>(sp, emap, srcs, runs, P, zero, out, gbytes, ntile, lane);
+        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane);
+        else                 gather_store_impl<false, false>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane);
     }
 }
-
 
 // ---------------------------------------------------------------------------------------
 // q rows of a chunk: every lane combines its own geometry, q[row] = sum coef * q_prim

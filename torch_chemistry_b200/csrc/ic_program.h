@@ -61,9 +61,15 @@ struct ChunkDesc {
 struct ZeroRun { uint32_t k, len; };   // elements [k, k + len) of a span are structural zeros
 constexpr int kMinZeroRun = 64;
 
-// map word: (count << 24) | first source index
+// map word: (count << 24) | first source index (q rows: index into qsrcs; J / K elements: index of
+// the element's first 16-byte quad of packed sources)
 constexpr uint32_t kMapCountShift = 24;
 constexpr uint32_t kMapOffsetMask = 0x00ffffffu;
+
+// Packed source of a J / K element: (coefficient index << 16) | compact entry. An element's
+// sources start on a quad boundary, so one 16-byte load fetches up to four of them.
+constexpr uint32_t kSrcEntryMask = 0xffffu;
+constexpr int kMaxStagedCoefs = 128;     // coefficient tables up to this size are staged in shared memory
 
 // One dense output element of a span: its source word and its position in the span. The
 // entries of a span are ordered so that groups of 4 consecutive elements (one 32-byte sector)
@@ -79,9 +85,11 @@ struct Program {                   // all pointers are device pointers
     const ChunkDesc * chunks;
     const uint32_t *  map;         // q rows: (count << 24) | first index into qsrcs
     const Src *       qsrcs;
-    const ElemMap *   emap;        // J / K elements, sources in srcs
-    const Src *       srcs;
+    const ElemMap *   emap;        // J / K elements, sources in psrcs
+    const uint4 *     psrcs;       // packed sources, 4 per 16-byte quad (see PackedSrc)
+    const double *    coefs;       // distinct coefficient values
     const ZeroRun *   runs;
+    int32_t ncoefs;
     int32_t nqsrcs, nmap;          // sizes of qsrcs[] and map[]
     int32_t split_rows;            // some row is split into accumulating chunks
     int32_t nprims, nchunks;

@@ -34,8 +34,19 @@ PrimKey key_of(const tchem_invdisp_t & t) {
 
 } // namespace
 
+namespace {
+// index of `value` in the table of distinct coefficients (bitwise equality), appended when new
+int coef_index(std::vector<double> & coefs, double value) {
+    for (size_t i = 0; i < coefs.size(); i++)
+        if (std::memcmp(&coefs[i], &value, sizeof(double)) == 0) return (int)i;
+    coefs.push_back(value);
+    return (int)coefs.size() - 1;
+}
+}
+
 bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
-               std::vector<ElemMap> & emap, std::vector<Src> & srcs, std::vector<ZeroRun> & runs, SpanDesc & span) {
+               std::vector<ElemMap> & emap, std::vector<uint32_t> & psrcs, std::vector<double> & coefs,
+               std::vector<ZeroRun> & runs, SpanDesc & span) {
     const int64_t S = (int64_t)lists.size();
     span.map = (int64_t)emap.size();
     span.run0 = (int32_t)runs.size();
@@ -72,12 +83,17 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
     for (const Unit & u : rest)
         for (int64_t e = u.first; e < u.last; e++) {
             const auto & l = lists[e];
-            if (l.size() > 255 || srcs.size() + l.size() > kMapOffsetMask) return false;
+            if (l.size() > 255 || psrcs.size() / 4 + l.size() > kMapOffsetMask) return false;
             ElemMap m;
-            m.word = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)srcs.size());
+            m.word = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)(psrcs.size() / 4));
             m.k = (uint32_t)e;
             emap.push_back(m);
-            for (const Src & s : l) srcs.push_back(s);
+            for (const Src & s : l) {
+                const int ci = coef_index(coefs, s.coef);
+                if (ci > 0xffff || s.entry > (int)kSrcEntryMask) return false;
+                psrcs.push_back(((uint32_t)ci << 16) | (uint32_t)s.entry);
+            }
+            while (psrcs.size() % 4) psrcs.push_back(0u);       // the next element starts a new quad
         }
     span.n = (int32_t)(emap.size() - span.map);
     span.nruns = (int32_t)runs.size() - span.run0;
@@ -222,7 +238,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             return true;
         };
         auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, SpanDesc & span) {
-            return emit_span(lists, abs_off, gstride, hp.emap, hp.srcs, hp.runs, span);
+            return emit_span(lists, abs_off, gstride, hp.emap, hp.psrcs, hp.coefs, hp.runs, span);
         };
         std::vector<std::vector<Src>> ql(pc.nrows), jl, kl;
         if (mode != MODE_VALUE) jl.resize((size_t)pc.nrows * cd);

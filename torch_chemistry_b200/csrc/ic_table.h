@@ -26,7 +26,9 @@ struct HostProgram {
     std::vector<ChunkDesc> chunks;
     std::vector<uint32_t> map;
     std::vector<ElemMap> emap;
-    std::vector<Src> srcs, qsrcs;
+    std::vector<Src> qsrcs;
+    std::vector<uint32_t> psrcs;          // packed J / K sources, quads
+    std::vector<double> coefs;            // distinct coefficients
     std::vector<ZeroRun> runs;
     int cap = 0;
 };
@@ -36,7 +38,8 @@ struct HostProgram {
 // sectors of 4 (aligned to `abs_off`, the span's element offset inside the geometry block, when
 // the block stride keeps sectors aligned) and the sectors are ordered by source count.
 bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
-               std::vector<ElemMap> & emap, std::vector<Src> & srcs, std::vector<ZeroRun> & runs, SpanDesc & span);
+               std::vector<ElemMap> & emap, std::vector<uint32_t> & psrcs, std::vector<double> & coefs,
+               std::vector<ZeroRun> & runs, SpanDesc & span);
 
 // pure host: flatten terms into a program for one mode
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,

@@ -26,7 +26,8 @@ struct SapProgram {                               // device pointers
     const SapUniq *   uniqs;
     const ChunkDesc * chunks;                     // prim_begin/end = term range, row0/nrows likewise
     const ElemMap *   emap;
-    const Src *       srcs;
+    const uint4 *     psrcs;
+    const double *    coefs;
     const ZeroRun *   runs;
     const int32_t *   pow_off;                    // power table: entries pow_off[col] + p hold x[col]^p, p = 0..maxpow
     int32_t nterms, nuniqs, nchunks, cap, sumdim, npow;
@@ -223,7 +224,7 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
             // monomial values sit in compact entries [0, nrows): written (geometry, term)-flattened
             if (y != nullptr) store_rows(P, 0, ch.nrows, y + b0 * sp.nterms + ch.row0, sp.nterms, ntile, false, lane);
             if (J != nullptr)
-                gather_store(ch.jspan, sp.emap, sp.srcs, sp.runs, P, J + (b0 * sp.nterms + ch.row0) * sumdim,
+                gather_store(ch.jspan, sp.emap, sp.psrcs, sp.coefs, sp.runs, P, J + (b0 * sp.nterms + ch.row0) * sumdim,
                              (int64_t)sp.nterms * sumdim, ntile, false, lane);
             __syncwarp();
         }
@@ -310,7 +311,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     const int cap = std::max(max_term, std::min(total_entries, 32));
     std::vector<ChunkDesc> chunks;
     std::vector<ElemMap> map;
-    std::vector<Src> srcs;
+    std::vector<uint32_t> srcs;
+    std::vector<double> coefs;
     std::vector<ZeroRun> runs;
     for (int t0 = 0; t0 < n_terms;) {
         int t1 = t0, entries = 0;
@@ -326,7 +328,7 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
         for (int t = t0; t < t1; t++)
             for (int u = terms[t].ubegin; u < terms[t].uend; u++)
                 jl[(size_t)(t - t0) * sumdim + uniqs[u].col].push_back(Src{(t1 - t0) + (u - first), 0, 1.0});
-        if (!emit_span(jl, (int64_t)t0 * sumdim, (int64_t)n_terms * sumdim, map, srcs, runs, ch.jspan))
+        if (!emit_span(jl, (int64_t)t0 * sumdim, (int64_t)n_terms * sumdim, map, srcs, coefs, runs, ch.jspan))
             return set_error(TCHEM_EINVAL, "tchem_sap_table_create: set too large");
         chunks.push_back(ch);
         t0 = t1;
@@ -340,7 +342,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     const size_t o_chunks = o_uniqs + a16(uniqs.size() * sizeof(SapUniq) + 8);
     const size_t o_map = o_chunks + a16(chunks.size() * sizeof(ChunkDesc));
     const size_t o_srcs = o_map + a16(map.size() * sizeof(ElemMap));
-    const size_t o_runs = o_srcs + a16(srcs.size() * sizeof(Src));
+    const size_t o_coefs = o_srcs + a16(srcs.size() * sizeof(uint32_t));
+    const size_t o_runs = o_coefs + a16(coefs.size() * sizeof(double) + 8);
     const size_t total = o_runs + a16(runs.size() * sizeof(ZeroRun)) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SapTerm));
@@ -348,7 +351,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     std::memcpy(blob.data() + o_pow, pow_off.data(), pow_off.size() * 4);
     std::memcpy(blob.data() + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc));
     std::memcpy(blob.data() + o_map, map.data(), map.size() * sizeof(ElemMap));
-    std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(Src));
+    std::memcpy(blob.data() + o_srcs, srcs.data(), srcs.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + o_coefs, coefs.data(), coefs.size() * sizeof(double));
     std::memcpy(blob.data() + o_runs, runs.data(), runs.size() * sizeof(ZeroRun));
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
@@ -368,7 +372,8 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     t->prog.npow = pow_off[sumdim];
     t->prog.chunks = reinterpret_cast<const ChunkDesc *>(d + o_chunks);
     t->prog.emap = reinterpret_cast<const ElemMap *>(d + o_map);
-    t->prog.srcs = reinterpret_cast<const Src *>(d + o_srcs);
+    t->prog.psrcs = reinterpret_cast<const uint4 *>(d + o_srcs);
+    t->prog.coefs = reinterpret_cast<const double *>(d + o_coefs);
     t->prog.runs = reinterpret_cast<const ZeroRun *>(d + o_runs);
     t->prog.nterms = n_terms; t->prog.nuniqs = (int)uniqs.size(); t->prog.nchunks = (int)chunks.size();
     t->prog.cap = cap; t->prog.sumdim = sumdim;
