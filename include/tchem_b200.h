@@ -172,6 +172,17 @@ TCHEM_API int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms
                                       int64_t * counts, void * prims, void * chunks, uint32_t * map, void * qsrcs,
                                       void * emap, void * srcs, void * runs, double * coefs);
 
+/* Large batches of q + J on tables without 5-atom terms are served by a kernel SPECIALISED to the
+ * table: the definition is emitted as straight-line CUDA C++ over the same device functions and
+ * compiled for sm_100a with NVRTC on first use (environment: TCHEM_JIT=0 disables it,
+ * TCHEM_JIT_MIN_BATCH sets the batch threshold). These two entry points expose the generator for
+ * inspection and for the CPU-side tests: the source for a definition (returns the buffer size
+ * needed, 0 when the table is not eligible) and an NVRTC compile check of a source (no device
+ * needed; 0 = compiled, the compiler / ptxas log is copied to `log`). */
+TCHEM_API int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap,
+                                      char * buf, int64_t capacity);
+TCHEM_API int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity);
+
 /* ---- measurement helpers (bench.py only) ------------------------------------------------ */
 /* number of kernels this library has launched in this process so far */
 TCHEM_API int64_t tchem_launch_count(void);

@@ -25,10 +25,23 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _embed_math_header():
+    """csrc/ic_math.cuh as a raw string literal (csrc/ic_math_embedded.inc): the specialised kernels
+    that jit.cu generates #include it through NVRTC's in-memory headers."""
+    src = os.path.join(CSRC, "ic_math.cuh")
+    dst = os.path.join(CSRC, "ic_math_embedded.inc")
+    text = open(src).read()
+    body = 'R"TCHEMHDR(' + text + ')TCHEMHDR"\n'
+    if not os.path.exists(dst) or open(dst).read() != body:
+        with open(dst, "w") as f:
+            f.write(body)
+
+
 def build(verbose=False, force=False, extra_flags=()):
     os.makedirs(OBJ, exist_ok=True)
+    _embed_math_header()
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
-    headers = (glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+    headers = (glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc"))
                + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     jobs = []
     objs = []

@@ -21,6 +21,8 @@ void count_launch(int n) { g_launches += n; }
 
 void release_grad_program(const tchem_ic_table * t);
 void release_dense_program(const tchem_ic_table * t);
+void release_jit(const tchem_ic_table * t);
+extern thread_local int64_t g_batch_hint;
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
                    double * q, double * J, double * K, cudaStream_t stream);
 
@@ -170,6 +172,7 @@ void tchem_ic_table_destroy(tchem_ic_table * t) {
         for (int m = 0; m < MODE_COUNT; m++) cudaFree(t->dev_blob[m]);
         release_grad_program(t);
         release_dense_program(t);
+        release_jit(t);
         if (t->pipe) { t->pipe->release(); delete t->pipe; }
     }
     delete t;
@@ -290,6 +293,7 @@ int tchem_ic_eval_host(const tchem_ic_table * tc, const double * r, int64_t B, d
     if (K && (rc = grow(hp.d_K, hp.cap_K, piece * n * cd * cd * 8)) != TCHEM_OK) return rc;
 
     int slot = 0;
+    struct HintScope { HintScope(int64_t b) { g_batch_hint = b; } ~HintScope() { g_batch_hint = 0; } } hint(B);
     for (int64_t b0 = 0; b0 < B; b0 += piece, slot = (slot + 1) % HostPipe::kSlots) {
         const int64_t nb = std::min<int64_t>(piece, B - b0);
         cudaStream_t s = hp.stream[slot];

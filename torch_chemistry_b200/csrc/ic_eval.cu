@@ -115,9 +115,16 @@ size_t ic_eval_table_bytes(const Program & p) {
 }
 size_t ic_eval_warp_bytes(const Program & p) { return (size_t)(p.cartdim + p.cap) * kPad * sizeof(double); }
 
+int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double * q, double * J, cudaStream_t stream);
+
 // picks warps/block and grid, launches on `stream`
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
                    double * q, double * J, double * K, cudaStream_t stream) {
+    if (mode == MODE_QJ) {
+        // large batches: the kernel specialised to this table (jit.cu); -1 = not eligible, interpret
+        const int rc = launch_jit_qJ(t, r, B, q, J, stream);
+        if (rc != -1) return rc;
+    }
     const Program & p = t->prog[mode];
     // launch shapes (warps per block x resident blocks): the register budget of the q / q+J flavours
     // allows 12 warps per SM; whichever split of those 12 warps fits the most warps into shared

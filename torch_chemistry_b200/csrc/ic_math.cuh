@@ -7,8 +7,10 @@
 // Here the same expressions are differentiated in registers: Dual carries one tangent
 // direction, Dual2 two directions plus the mixed second-order term.
 #pragma once
+#ifndef __CUDACC_RTC__          // NVRTC (specialised kernels, jit.cu) has the math built-ins without headers
 #include <cuda_runtime.h>
 #include <math.h>
+#endif
 
 namespace tchem_b200 {
 

@@ -1,0 +1,380 @@
+// Table-specialised q + J kernels.
+//
+// The generic kernel (ic_eval.cu) INTERPRETS the compiled definition table: every warp walks the
+// primitive list, switches on the type, looks atoms and gather sources up at run time. With 12
+// resident warps per SM that loop is latency bound. For large batches of a small-to-medium set the
+// table is instead turned into straight-line CUDA C++ - atom indices, coefficients and the sparsity
+// of every J row become compile-time constants, the hand-written device functions of ic_math.cuh
+// are called back to back so their independent arithmetic interleaves (ILP), common bond vectors
+// are shared by the compiler - and compiled once per table for sm_100a with NVRTC.
+//
+// Same warp-tile scheme as the interpreter: lane = geometry, cp.async staging of the coordinates
+// with prefetch of the next tile, dense row chunks staged [element][lane] in shared memory and
+// written out transposed (coalesced 256-byte segments). Replaces IntCoordSet::compute_IC_J
+// (reference source/IC/IntCoordSet.cpp:147-159) for tables without the 5-atom torsion2 family.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ic_table.h"
+
+namespace tchem_b200 {
+
+namespace {
+
+const char kMathHeader[] =
+#include "ic_math_embedded.inc"
+    ;
+
+// ---- NVRTC through dlopen: the library itself does not link against it ----------------------
+typedef struct _nvrtcProgram * nvrtcProgram;
+struct Nvrtc {
+    void * lib = nullptr;
+    int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char * const *, const char * const *) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, const char * const *) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram *) = nullptr;
+    bool ok = false;
+    Nvrtc() {
+        const char * names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (const char * n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
+        if (!lib) return;
+#define TC_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) return;
+        TC_SYM(CreateProgram, "nvrtcCreateProgram")
+        TC_SYM(CompileProgram, "nvrtcCompileProgram")
+        TC_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+        TC_SYM(GetCUBIN, "nvrtcGetCUBIN")
+        TC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        TC_SYM(GetProgramLog, "nvrtcGetProgramLog")
+        TC_SYM(DestroyProgram, "nvrtcDestroyProgram")
+#undef TC_SYM
+        ok = true;
+    }
+};
+Nvrtc & nvrtc() { static Nvrtc n; return n; }
+
+std::string hexd(double v) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%a", v);
+    return buf;
+}
+
+const char kPrelude[] = R"TCHEM(
+typedef long long int64_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#include "ic_math.cuh"
+using namespace tchem_b200;
+#define KPAD 33
+#define LANES 32
+// global r[b0 .. b0+ntile)[CD] -> R[c * KPAD + lane] with cp.async (see ic_eval.cuh::stage_issue)
+__device__ __forceinline__ void stage_issue(const double * __restrict__ r, int64_t b0, int ntile, double * R, int lane) {
+    const double * src = r + b0 * CD;
+    const int total = ntile * CD;
+    int g = lane / CD, c = lane - g * CD;
+    const int dg = LANES / CD, dc = LANES - dg * CD;
+    for (int f = lane; f < total; f += LANES) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(R + c * KPAD + g);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + f) : "memory");
+        g += dg; c += dc;
+        if (c >= CD) { c -= CD; g++; }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void stage_finish(int ntile, double * R, int lane) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    if (ntile < LANES && lane >= ntile)
+        for (int k = 0; k < CD; k++) R[k * KPAD + lane] = R[k * KPAD + ntile - 1];
+    __syncwarp();
+}
+// staged [span][lane] -> out[(b0 + g) * gstride + k]: lanes along k, coalesced segments
+template <int SPAN, int GSTRIDE>
+__device__ __forceinline__ void copy_out(const double * D, double * __restrict__ out, int ntile, int lane) {
+    for (int k = lane; k < SPAN; k += LANES) {
+        const double * src = D + k * KPAD;
+        double * o = out + k;
+        if (ntile == LANES) {
+#pragma unroll 8
+            for (int g = 0; g < LANES; g++) o[(int64_t)g * GSTRIDE] = src[g];
+        } else {
+            for (int g = 0; g < ntile; g++) o[(int64_t)g * GSTRIDE] = src[g];
+        }
+    }
+}
+// q rows of a chunk, (geometry, row)-flattened
+template <int NROWS, int GSTRIDE>
+__device__ __forceinline__ void copy_rows(const double * Q, double * __restrict__ out, int ntile, int lane) {
+    const int total = ntile * NROWS;
+    int g = lane / NROWS, row = lane - g * NROWS;
+    const int dg = LANES / NROWS, dr = LANES - dg * NROWS;
+    for (int f = lane; f < total; f += LANES) {
+        out[(int64_t)g * GSTRIDE + row] = Q[row * KPAD + g];
+        g += dg; row += dr;
+        if (row >= NROWS) { row -= NROWS; g++; }
+    }
+}
+)TCHEM";
+
+struct JitPrim { int type, natoms, atoms[5]; double min; };
+
+} // namespace
+
+// The CUDA C++ source of the specialised kernel for this table; `dcap` = dense elements staged
+// per chunk. Empty string when the table is not eligible.
+std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int dcap, int warps, int blocks) {
+    typedef std::tuple<int, int, int, int, int, int, double> Key;
+    std::map<Key, int> index;
+    std::vector<JitPrim> prims;
+    std::vector<std::vector<std::pair<double, int>>> rows(n_ic);       // (coef, prim) in file order
+    for (const auto & d : terms) {
+        if (d.natoms == 5) return std::string();
+        int a[5];
+        for (int i = 0; i < 5; i++) a[i] = i < d.natoms ? d.atoms[i] : -1;
+        const double mn = d.type == TCHEM_TORSION ? d.min : 0.0;
+        Key k(d.type, a[0], a[1], a[2], a[3], a[4], mn);
+        auto f = index.find(k);
+        int id;
+        if (f == index.end()) {
+            id = (int)prims.size();
+            index[k] = id;
+            JitPrim p;
+            p.type = d.type; p.natoms = d.natoms; p.min = d.min;
+            for (int i = 0; i < 5; i++) p.atoms[i] = a[i];
+            prims.push_back(p);
+        } else id = f->second;
+        rows[d.ic].push_back({d.coeff, id});
+    }
+    if (cartdim > dcap) return std::string();
+    // chunks of consecutive rows, <= dcap dense elements (+ their q rows)
+    std::vector<std::pair<int, int>> chunks;
+    const int rows_per = std::max(1, dcap / (cartdim + 1));
+    for (int r0 = 0; r0 < n_ic; r0 += rows_per) chunks.push_back({r0, std::min(n_ic, r0 + rows_per)});
+    const int natoms = cartdim / 3;
+
+    std::ostringstream o;
+    o << "#define CD " << cartdim << "\n#define NIC " << n_ic << "\n#define DCAP " << rows_per * (cartdim + 1) << "\n";
+    o << kPrelude;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << warps * 32 << ", " << blocks << ")\n"
+      << "tchem_jit_qJ(const double * __restrict__ r, const long long B, double * __restrict__ q, double * __restrict__ J) {\n"
+      << "    extern __shared__ __align__(16) double smem[];\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n"
+      << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
+      << "    double * D = R + CD * KPAD;\n"
+      << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
+      << "    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;\n"
+      << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue(r, b0, (int)min((int64_t)LANES, B - b0), R, lane); }\n"
+      << "    for (; tile < ntiles; tile += step) {\n"
+      << "        const int64_t b0 = tile * LANES;\n"
+      << "        const int ntile = (int)min((int64_t)LANES, B - b0);\n"
+      << "        stage_finish(ntile, R, lane);\n"
+      << "        V3<double> a[" << natoms << "];\n";
+    std::vector<char> atom_used(natoms, 0);
+    for (const auto & p : prims) for (int i = 0; i < p.natoms; i++) atom_used[p.atoms[i]] = 1;
+    for (int at = 0; at < natoms; at++)
+        if (atom_used[at])
+            o << "        a[" << at << "] = v3<double>(R[" << 3 * at << " * KPAD + lane], R[" << 3 * at + 1 << " * KPAD + lane], R["
+              << 3 * at + 2 << " * KPAD + lane]);\n";
+    o << "        __syncwarp();\n"
+      << "        // the coordinates now live in registers: the next tile's copy can start\n"
+      << "        if (tile + step < ntiles) { const int64_t nb0 = (tile + step) * LANES; stage_issue(r, nb0, (int)min((int64_t)LANES, B - nb0), R, lane); }\n";
+    for (const auto & ch : chunks) {
+        const int r0 = ch.first, r1 = ch.second, nrows = r1 - r0;
+        o << "        {   // rows " << r0 << " .. " << r1 - 1 << "\n";
+        std::vector<char> need(prims.size(), 0);
+        for (int i = r0; i < r1; i++) for (auto & t : rows[i]) need[t.second] = 1;
+        for (size_t p = 0; p < prims.size(); p++) {
+            if (!need[p]) continue;
+            const JitPrim & pr = prims[p];
+            o << "            double q" << p << " = 1.0;";
+            if (pr.natoms == 0) { o << "\n"; continue; }
+            o << " V3<double> j" << p << "[" << pr.natoms << "];\n            { const V3<double> A[" << pr.natoms << "] = {";
+            for (int i = 0; i < pr.natoms; i++) o << (i ? ", " : "") << "a[" << pr.atoms[i] << "]";
+            o << "}; auto emit = [&](int i, const V3<double> & v) { j" << p << "[i] = v; };";
+            switch (pr.type) {
+            case TCHEM_STRETCHING: o << " stretching_J<double>(A, q" << p << ", emit);"; break;
+            case TCHEM_BENDING:    o << " double c; bending_J<double, false>(A, c, emit); q" << p << " = acos(c);"; break;
+            case TCHEM_COSBENDING: o << " bending_J<double, true>(A, q" << p << ", emit);"; break;
+            case TCHEM_TORSION:    o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 0>(A, sp, cp, st, emit); q" << p
+                                     << " = signed_wrapped_angle(cp, st, " << hexd(pr.min) << ");"; break;
+            case TCHEM_SINTORSION: o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 1>(A, sp, cp, st, emit); q" << p << " = sp;"; break;
+            case TCHEM_COSTORSION: o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 2>(A, sp, cp, st, emit); q" << p << " = cp;"; break;
+            case TCHEM_OUTOFPLANE: o << " double s; oop_J<double, false>(A, s, emit); q" << p << " = asin(s);"; break;
+            case TCHEM_SINOOP:     o << " oop_J<double, true>(A, q" << p << ", emit);"; break;
+            default: return std::string();
+            }
+            o << " }\n";
+        }
+        // dense elements of the chunk: [row - r0][col] then the q rows
+        for (int i = r0; i < r1; i++) {
+            std::vector<std::string> expr(cartdim);
+            for (auto & t : rows[i]) {
+                const JitPrim & pr = prims[t.second];
+                for (int s = 0; s < pr.natoms; s++)
+                    for (int c = 0; c < 3; c++) {
+                        std::string & e = expr[3 * pr.atoms[s] + c];
+                        std::ostringstream term;
+                        term << hexd(t.first) << " * j" << t.second << "[" << s << "]." << "xyz"[c];
+                        e = e.empty() ? term.str() : "fma(" + hexd(t.first) + ", j" + std::to_string(t.second) + "[" + std::to_string(s)
+                                                      + "]." + std::string(1, "xyz"[c]) + ", " + e + ")";
+                    }
+            }
+            for (int c = 0; c < cartdim; c++)
+                o << "            D[" << (i - r0) * cartdim + c << " * KPAD + lane] = " << (expr[c].empty() ? "0.0" : expr[c]) << ";\n";
+            std::string qe;
+            for (auto & t : rows[i]) {
+                const std::string term = hexd(t.first) + " * q" + std::to_string(t.second);
+                qe = qe.empty() ? term : "fma(" + hexd(t.first) + ", q" + std::to_string(t.second) + ", " + qe + ")";
+            }
+            o << "            D[" << nrows * cartdim + (i - r0) << " * KPAD + lane] = " << qe << ";\n";
+        }
+        o << "            __syncwarp();\n"
+          << "            if (J) copy_out<" << nrows * cartdim << ", NIC * CD>(D, J + b0 * (NIC * CD) + " << r0 * cartdim << ", ntile, lane);\n"
+          << "            if (q) copy_rows<" << nrows << ", NIC>(D + " << nrows * cartdim << " * KPAD, q + b0 * NIC + " << r0 << ", ntile, lane);\n"
+          << "            __syncwarp();\n        }\n";
+    }
+    o << "    }\n}\n";
+    return o.str();
+}
+
+// compiles `src` for sm_100a; returns the cubin (empty on failure, reason in `log`)
+std::vector<char> jit_compile(const std::string & src, std::string & log, bool verbose) {
+    std::vector<char> cubin;
+    Nvrtc & n = nvrtc();
+    if (!n.ok) { log = "NVRTC (libnvrtc.so.12) not available"; return cubin; }
+    nvrtcProgram prog = nullptr;
+    const char * hdr_src[] = {kMathHeader};
+    const char * hdr_name[] = {"ic_math.cuh"};
+    if (n.CreateProgram(&prog, src.c_str(), "tchem_jit.cu", 1, hdr_src, hdr_name) != 0) { log = "nvrtcCreateProgram failed"; return cubin; }
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    if (verbose) opts.push_back("--ptxas-options=-v");
+    const int rc = n.CompileProgram(prog, (int)opts.size(), opts.data());
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    if (ls > 1) { log.resize(ls); n.GetProgramLog(prog, &log[0]); }
+    if (rc == 0) {
+        size_t cs = 0;
+        if (n.GetCUBINSize(prog, &cs) == 0 && cs > 0) { cubin.resize(cs); n.GetCUBIN(prog, cubin.data()); }
+    }
+    n.DestroyProgram(&prog);
+    return cubin;
+}
+
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t fn = nullptr;
+    int warps = 4, blocks = 3, per_sm = 1;
+    size_t smem = 0;
+    bool failed = false;
+};
+
+namespace {
+std::map<const tchem_ic_table *, JitKernel> & jit_kernels() { static std::map<const tchem_ic_table *, JitKernel> m; return m; }
+std::mutex & jit_mutex() { static std::mutex m; return m; }
+int env_int(const char * name, int dflt) { const char * v = getenv(name); return v ? atoi(v) : dflt; }
+}
+
+void release_jit(const tchem_ic_table * t) {
+    std::lock_guard<std::mutex> lock(jit_mutex());
+    auto it = jit_kernels().find(t);
+    if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
+}
+
+// q + J through the specialised kernel. Returns TCHEM_OK when launched, -1 when this table / batch
+// is served by the interpreter instead (never an error by itself).
+// the host-buffer entry point cuts one batch into pieces: the kernel choice follows the whole batch
+thread_local int64_t g_batch_hint = 0;
+
+int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double * q, double * J, cudaStream_t stream) {
+    static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
+    static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
+    if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 96 || t->terms.size() > 160) return -1;
+    JitKernel * k;
+    {
+        std::lock_guard<std::mutex> lock(jit_mutex());
+        JitKernel & jk = jit_kernels()[t];
+        k = &jk;
+        if (!jk.fn && !jk.failed) {
+            // shape: elements staged per chunk and the launch bounds the register allocation follows
+            const int dcap = env_int("TCHEM_JIT_DCAP", std::max(t->cartdim + 1, 76));
+            jk.warps = env_int("TCHEM_JIT_WARPS", 4);
+            jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);      // 2 x 4 warps: the full register file, no spills (measured best)
+            const std::string src = jit_source(t->terms, t->intdim, t->cartdim, dcap, jk.warps, jk.blocks);
+            std::string log;
+            std::vector<char> cubin;
+            if (!src.empty()) cubin = jit_compile(src, log, debug);
+            if (debug) fprintf(stderr, "[tchem] jit: %zu bytes of source, %zu bytes of cubin\n%s\n", src.size(), cubin.size(), log.c_str());
+            if (cubin.empty()) jk.failed = true;
+            else if (cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess
+                     || cudaLibraryGetKernel(&jk.fn, jk.lib, "tchem_jit_qJ") != cudaSuccess) {
+                cudaGetLastError();
+                jk.failed = true;
+            } else {
+                const int rows_per = std::max(1, dcap / (t->cartdim + 1));
+                jk.smem = (size_t)jk.warps * (t->cartdim + rows_per * (t->cartdim + 1)) * 33 * sizeof(double);
+                if (jk.smem > (size_t)t->max_smem_optin
+                    || cudaFuncSetAttribute((const void *)jk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jk.smem) != cudaSuccess
+                    || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jk.per_sm, (const void *)jk.fn, jk.warps * 32, jk.smem) != cudaSuccess
+                    || jk.per_sm < 1) {
+                    cudaGetLastError();
+                    jk.failed = true;
+                }
+            }
+            if (debug) fprintf(stderr, "[tchem] jit: %s, %d warps/block, %d blocks/SM, %zu B smem\n", jk.failed ? "FAILED (interpreter serves this table)" : "ok",
+                               jk.warps, jk.per_sm, jk.smem);
+        }
+        if (jk.failed) return -1;
+    }
+    const int64_t ntiles = (B + 31) / 32;
+    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
+    long long Bll = B;
+    void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J};
+    TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
+} // namespace tchem_b200
+
+using namespace tchem_b200;
+
+extern "C" {
+
+// the generated source of the specialised q + J kernel (testing / inspection); returns the length
+// needed (0: table not eligible), copies at most `capacity` bytes including the terminator
+int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap, char * buf, int64_t capacity) {
+    if (!terms || n_terms <= 0) return 0;
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    const std::string s = jit_source(v, n_ic, cartdim, dcap > 0 ? dcap : std::max(cartdim + 1, 76), 4, 3);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+// compiles that source for sm_100a (no device needed); 0 on success, the NVRTC / ptxas log in `log`
+int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity) {
+    std::string l;
+    const std::vector<char> cubin = jit_compile(source ? source : "", l, true);
+    if (log && capacity > 0) {
+        const size_t n = std::min<size_t>(l.size(), (size_t)capacity - 1);
+        std::memcpy(log, l.data(), n);
+        log[n] = 0;
+    }
+    return cubin.empty() ? 1 : 0;
+}
+
+} // extern "C"
