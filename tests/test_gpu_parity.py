@@ -296,3 +296,24 @@ def test_chained_host_buffers_match_device_path(T):
     np.testing.assert_array_equal(y.numpy(), host(yd))
     np.testing.assert_array_equal(J.numpy(), host(Jd))
     np.testing.assert_array_equal(q.numpy(), host(qd))
+
+
+def test_specialised_kernel_matches_interpreter_and_oracle(T):
+    """Large q+J batches of small molecules run the table-specialised (NVRTC) kernel, small batches
+    the interpreter: both must agree with the oracle, and with each other to rounding."""
+    for key, n in (("C1", 40000), ("C2", 50021)):
+        w = T.workloads.get(key)
+        s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+        orc = O.IntCoordSet("default", w.ic_text)
+        r = w.geometries(n, seed=31)
+        rd = dev(r)
+        q_big, J_big = s.compute_IC_J(rd)                 # >= TCHEM_JIT_MIN_BATCH: specialised kernel
+        q_small, J_small = s.compute_IC_J(rd[:2048])       # interpreter
+        assert float((q_big[:2048] - q_small).abs().max()) < 1e-13
+        assert float((J_big[:2048] - J_small).abs().max()) < 1e-13
+        idx = np.arange(0, n, 97)
+        qo, Jo = orc.qJ(r[idx])
+        assert_q_parity(host(q_big[idx]), qo, orc.terms(), r[idx], key + " specialised q vs oracle")
+        assert_parity(host(J_big[idx]), Jo, key + " specialised J vs oracle")
+        # ragged tail tile and J-only / q-only calls
+        assert n % 32 != 0

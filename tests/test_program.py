@@ -174,3 +174,35 @@ def test_row_wider_than_capacity_is_split_and_accumulated():
     qo, Jo = O.IntCoordSet("default", text).qJ(r)
     assert_parity(J, Jo, "split row J")
     assert np.abs(q - qo).max() < 1e-9
+
+
+def test_specialised_kernel_source_compiles_for_sm100a():
+    """jit.cu: the generated CUDA C++ for a definition is valid and NVRTC compiles it for sm_100a
+    without a device (skipped when libnvrtc is not installed)."""
+    for name, cd in (("workload_C2", 18), ("workload_C1", 9), ("ref_aniline_default", 42)):
+        g = golden(name)
+        text = str(g["definition"])
+        nt, nic = C.c_int(0), C.c_int(0)
+        capi.check(lib.tchem_ic_parse_text(b"default", text.encode(), None, 0, C.byref(nt), C.byref(nic)))
+        terms = (capi.InvDisp * nt.value)()
+        capi.check(lib.tchem_ic_parse_text(b"default", text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
+        n = lib.tchem_ic_jit_source(terms, nt.value, nic.value, cd, 0, None, 0)
+        assert n > 0
+        buf = C.create_string_buffer(n)
+        lib.tchem_ic_jit_source(terms, nt.value, nic.value, cd, 0, buf, n)
+        src = buf.value.decode()
+        assert "tchem_jit_qJ" in src and "stage_issue" in src
+        assert src.count("stretching_J<double>") >= 1
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.tchem_ic_jit_compile_check(src.encode(), log, 1 << 16)
+        if rc != 0 and "not available" in log.value.decode():
+            pytest.skip("NVRTC not available")
+        assert rc == 0, log.value.decode()[-2000:]
+        assert "Used" in log.value.decode()
+    # tables with 5-atom (torsion2 family) terms are not eligible: the interpreter serves them
+    a = golden("ref_aniline_advanced")
+    text = str(a["definition"])
+    capi.check(lib.tchem_ic_parse_text(b"whatever", text.encode(), None, 0, C.byref(nt), C.byref(nic)))
+    terms = (capi.InvDisp * nt.value)()
+    capi.check(lib.tchem_ic_parse_text(b"whatever", text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
+    assert lib.tchem_ic_jit_source(terms, nt.value, nic.value, 42, 0, None, 0) == 0

@@ -99,9 +99,23 @@ __device__ __forceinline__ void stage_finish(int ntile, double * R, int lane) {
         for (int k = 0; k < CD; k++) R[k * KPAD + lane] = R[k * KPAD + ntile - 1];
     __syncwarp();
 }
-// staged [span][lane] -> out[(b0 + g) * gstride + k]: lanes along k, coalesced segments
+// staged [span][lane] -> out[(b0 + g) * gstride + k]: lanes along k, coalesced segments; two
+// adjacent elements per lane and 16-byte stores when the span, the stride and the pointer are even
 template <int SPAN, int GSTRIDE>
 __device__ __forceinline__ void copy_out(const double * D, double * __restrict__ out, int ntile, int lane) {
+    if (SPAN % 2 == 0 && GSTRIDE % 2 == 0 && (reinterpret_cast<uint64_t>(out) & 15) == 0) {
+        for (int k = 2 * lane; k < SPAN; k += 2 * LANES) {
+            const double * s0 = D + k * KPAD, * s1 = s0 + KPAD;
+            double * o = out + k;
+            if (ntile == LANES) {
+#pragma unroll 8
+                for (int g = 0; g < LANES; g++) *reinterpret_cast<double2 *>(o + (int64_t)g * GSTRIDE) = make_double2(s0[g], s1[g]);
+            } else {
+                for (int g = 0; g < ntile; g++) *reinterpret_cast<double2 *>(o + (int64_t)g * GSTRIDE) = make_double2(s0[g], s1[g]);
+            }
+        }
+        return;
+    }
     for (int k = lane; k < SPAN; k += LANES) {
         const double * src = D + k * KPAD;
         double * o = out + k;
@@ -299,7 +313,9 @@ thread_local int64_t g_batch_hint = 0;
 int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double * q, double * J, cudaStream_t stream) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
     static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
-    if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 96 || t->terms.size() > 160) return -1;
+    // (measured: wins for small molecules - C2H4: 0.42 vs 0.64 ms - and loses beyond ~12 atoms, where dense
+    // row staging is mostly zeros and the interpreter's compact staging is the better scheme)
+    if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128) return -1;
     JitKernel * k;
     {
         std::lock_guard<std::mutex> lock(jit_mutex());
