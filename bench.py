@@ -396,7 +396,9 @@ def main():
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
         kernel = ("sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
-                  else "dense_kernel" if args.workload in FLOPS else "ic_eval_kernel")
+                  else "dense_kernel" if args.workload in FLOPS
+                  else "tchem_jit_qJ (table-specialised, NVRTC)" if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)
+                  else "ic_eval_kernel")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_geometry": bytes_per_geom, "kernel": kernel, "launch_ms": avg_launch_s * 1e3}

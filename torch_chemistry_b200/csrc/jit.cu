@@ -381,6 +381,15 @@ int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic
     return (int64_t)s.size() + (s.empty() ? 0 : 1);
 }
 
+// 1 when tchem_ic_eval(J != NULL, K == NULL) on a batch of B geometries runs the specialised kernel
+int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B) {
+    static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
+    if (!t || !enabled || B < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128) return 0;
+    std::lock_guard<std::mutex> lock(jit_mutex());
+    auto it = jit_kernels().find(t);
+    return it == jit_kernels().end() || !it->second.failed ? 1 : 0;
+}
+
 // compiles that source for sm_100a (no device needed); 0 on success, the NVRTC / ptxas log in `log`
 int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity) {
     std::string l;
