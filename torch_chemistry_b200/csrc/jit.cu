@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "ic_table.h"
+#include "sap_table.h"
 
 namespace tchem_b200 {
 
@@ -144,6 +145,162 @@ __device__ __forceinline__ void copy_rows(const double * Q, double * __restrict_
 struct JitPrim { int type, natoms, atoms[5]; double min; };
 
 } // namespace
+
+namespace {
+
+// distinct primitives + per-row (coefficient, primitive) lists of a definition; false: not eligible
+bool collect(const std::vector<tchem_invdisp_t> & terms, int n_ic, std::vector<JitPrim> & prims,
+             std::vector<std::vector<std::pair<double, int>>> & rows) {
+    typedef std::tuple<int, int, int, int, int, int, double> Key;
+    std::map<Key, int> index;
+    rows.assign(n_ic, {});
+    for (const auto & d : terms) {
+        if (d.natoms == 5) return false;
+        int a[5];
+        for (int i = 0; i < 5; i++) a[i] = i < d.natoms ? d.atoms[i] : -1;
+        const double mn = d.type == TCHEM_TORSION ? d.min : 0.0;
+        Key k(d.type, a[0], a[1], a[2], a[3], a[4], mn);
+        auto f = index.find(k);
+        int id;
+        if (f == index.end()) {
+            id = (int)prims.size();
+            index[k] = id;
+            JitPrim p;
+            p.type = d.type; p.natoms = d.natoms; p.min = d.min;
+            for (int i = 0; i < 5; i++) p.atoms[i] = a[i];
+            prims.push_back(p);
+        } else id = f->second;
+        rows[d.ic].push_back({d.coeff, id});
+    }
+    return true;
+}
+
+// `double q<p>; V3<double> j<p>[n];` + the call that fills them (want_J false: the gradient
+// blocks are dropped on the floor and the compiler removes their arithmetic)
+bool emit_prim(std::ostringstream & o, const JitPrim & pr, size_t p, bool want_J, const char * indent) {
+    o << indent << "double q" << p << " = 1.0;";
+    if (pr.natoms == 0) { o << "\n"; return true; }
+    if (want_J) o << " V3<double> j" << p << "[" << pr.natoms << "];";
+    o << "\n" << indent << "{ const V3<double> A[" << pr.natoms << "] = {";
+    for (int i = 0; i < pr.natoms; i++) o << (i ? ", " : "") << "a[" << pr.atoms[i] << "]";
+    if (want_J) o << "}; auto emit = [&](int i, const V3<double> & v) { j" << p << "[i] = v; };";
+    else        o << "}; auto emit = [&](int, const V3<double> &) {};";
+    switch (pr.type) {
+    case TCHEM_STRETCHING: o << " stretching_J<double>(A, q" << p << ", emit);"; break;
+    case TCHEM_BENDING:    o << " double c; bending_J<double, false>(A, c, emit); q" << p << " = acos(c);"; break;
+    case TCHEM_COSBENDING: o << " bending_J<double, true>(A, q" << p << ", emit);"; break;
+    case TCHEM_TORSION:    o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 0>(A, sp, cp, st, emit); q" << p
+                             << " = signed_wrapped_angle(cp, st, " << hexd(pr.min) << ");"; break;
+    case TCHEM_SINTORSION: o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 1>(A, sp, cp, st, emit); q" << p << " = sp;"; break;
+    case TCHEM_COSTORSION: o << " double sp = 0.0, cp = 0.0, st = 0.0; torsion_J<double, 2>(A, sp, cp, st, emit); q" << p << " = cp;"; break;
+    case TCHEM_OUTOFPLANE: o << " double s; oop_J<double, false>(A, s, emit); q" << p << " = asin(s);"; break;
+    case TCHEM_SINOOP:     o << " oop_J<double, true>(A, q" << p << ", emit);"; break;
+    default: return false;
+    }
+    o << " }\n";
+    return true;
+}
+
+// kernel signature up to and including the per-tile prologue (coordinates staged, atoms in
+// registers, next tile's copy in flight); `params` = the kernel's pointer parameters after r, B
+void emit_prologue(std::ostringstream & o, const char * name, const char * params, int cartdim, int dcap_entries,
+                   int warps, int blocks, const std::vector<JitPrim> & prims) {
+    const int natoms = cartdim / 3;
+    o << "#define CD " << cartdim << "\n#define DCAP " << dcap_entries << "\n";
+    o << kPrelude;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << warps * 32 << ", " << blocks << ")\n"
+      << name << "(const double * __restrict__ r, const long long B, " << params << ") {\n"
+      << "    extern __shared__ __align__(16) double smem[];\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n"
+      << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
+      << "    double * D = R + CD * KPAD;\n"
+      << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
+      << "    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;\n"
+      << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue(r, b0, (int)min((int64_t)LANES, B - b0), R, lane); }\n"
+      << "    for (; tile < ntiles; tile += step) {\n"
+      << "        const int64_t b0 = tile * LANES;\n"
+      << "        const int ntile = (int)min((int64_t)LANES, B - b0);\n"
+      << "        stage_finish(ntile, R, lane);\n"
+      << "        V3<double> a[" << natoms << "];\n";
+    std::vector<char> atom_used(natoms, 0);
+    for (const auto & p : prims) for (int i = 0; i < p.natoms; i++) atom_used[p.atoms[i]] = 1;
+    for (int at = 0; at < natoms; at++)
+        if (atom_used[at])
+            o << "        a[" << at << "] = v3<double>(R[" << 3 * at << " * KPAD + lane], R[" << 3 * at + 1 << " * KPAD + lane], R["
+              << 3 * at + 2 << " * KPAD + lane]);\n";
+    o << "        __syncwarp();\n"
+      << "        // the coordinates now live in registers: the next tile's copy can start\n"
+      << "        if (tile + step < ntiles) { const int64_t nb0 = (tile + step) * LANES; stage_issue(r, nb0, (int)min((int64_t)LANES, B - nb0), R, lane); }\n";
+}
+
+std::string row_expr(const std::vector<std::pair<double, int>> & row, const char * var) {
+    std::string e;
+    for (auto & t : row) {
+        const std::string term = hexd(t.first) + " * " + var + std::to_string(t.second);
+        e = e.empty() ? term : "fma(" + hexd(t.first) + ", " + var + std::to_string(t.second) + ", " + e + ")";
+    }
+    return e;
+}
+
+} // namespace
+
+// Chained r -> q -> SAPSet: straight-line q rows (compute_IC_J value formulas, gradients elided),
+// then every monomial and its partial derivatives as explicit products of shared powers. Staged
+// per chunk of monomials: [values][Jacobian rows], written out like the q+J kernel.
+std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim,
+                             const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks) {
+    std::vector<JitPrim> prims;
+    std::vector<std::vector<std::pair<double, int>>> rows;
+    if (!collect(terms, n_ic, prims, rows)) return std::string();
+    const int nt = (int)saps.size(), sd = n_ic;
+    const int per_term = 1 + sd;
+    if (per_term > dcap) return std::string();
+    const int nchunks = (nt * per_term + dcap - 1) / dcap, tper = (nt + nchunks - 1) / nchunks;
+    std::ostringstream o;
+    o << "#define NT " << nt << "\n#define SD " << sd << "\n";
+    emit_prologue(o, "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
+                  cartdim, std::max(tper * per_term, sd), warps, blocks, prims);
+    for (size_t p = 0; p < prims.size(); p++)
+        if (!emit_prim(o, prims[p], p, false, "        ")) return std::string();
+    std::vector<int> maxpow(sd, 0);
+    for (auto & t : saps) for (auto & u : t) maxpow[u.first] = std::max(maxpow[u.first], u.second);
+    for (int i = 0; i < n_ic; i++) {
+        o << "        const double x" << i << "p1 = " << row_expr(rows[i], "q") << ";\n";
+        for (int p = 2; p <= maxpow[i]; p++) o << "        const double x" << i << "p" << p << " = x" << i << "p" << p - 1 << " * x" << i << "p1;\n";
+    }
+    o << "        if (q) {\n";
+    for (int i = 0; i < n_ic; i++) o << "            D[" << i << " * KPAD + lane] = x" << i << "p1;\n";
+    o << "            __syncwarp();\n            copy_rows<SD, SD>(D, q + b0 * SD, ntile, lane);\n            __syncwarp();\n        }\n";
+    auto power = [](int col, int p) { return "x" + std::to_string(col) + "p" + std::to_string(p); };
+    for (int t0 = 0; t0 < nt; t0 += tper) {
+        const int t1 = std::min(nt, t0 + tper), n = t1 - t0;
+        o << "        {   // monomials " << t0 << " .. " << t1 - 1 << "\n";
+        for (int t = t0; t < t1; t++) {
+            // value: product of the powers (source/polynomial/SAP.cpp:93-99)
+            std::string v;
+            for (auto & u : saps[t]) v = v.empty() ? power(u.first, u.second) : v + " * " + power(u.first, u.second);
+            o << "            D[" << (t - t0) << " * KPAD + lane] = " << (v.empty() ? "1.0" : v) << ";\n";
+            // d/dx_u = p x_u^(p-1) prod_{w != u} x_w^(p_w)   (SAP.cpp:147-175); zero elsewhere
+            std::vector<std::string> g(sd, "0.0");
+            for (size_t ui = 0; ui < saps[t].size(); ui++) {
+                const auto & u = saps[t][ui];
+                std::string e = hexd((double)u.second);
+                if (u.second > 1) e += " * " + power(u.first, u.second - 1);
+                for (size_t wi = 0; wi < saps[t].size(); wi++)
+                    if (wi != ui) e += " * " + power(saps[t][wi].first, saps[t][wi].second);
+                g[u.first] = e;
+            }
+            for (int c = 0; c < sd; c++)
+                o << "            D[" << n + (t - t0) * sd + c << " * KPAD + lane] = " << g[c] << ";\n";
+        }
+        o << "            __syncwarp();\n"
+          << "            if (y) copy_rows<" << n << ", NT>(D, y + b0 * NT + " << t0 << ", ntile, lane);\n"
+          << "            if (J) copy_out<" << n * sd << ", NT * SD>(D + " << n << " * KPAD, J + b0 * (NT * SD) + " << t0 * sd << ", ntile, lane);\n"
+          << "            __syncwarp();\n        }\n";
+    }
+    o << "    }\n}\n";
+    return o.str();
+}
 
 // The CUDA C++ source of the specialised kernel for this table; `dcap` = dense elements staged
 // per chunk. Empty string when the table is not eligible.
@@ -285,6 +442,9 @@ std::vector<char> jit_compile(const std::string & src, std::string & log, bool v
     return cubin;
 }
 
+// the host-buffer entry point cuts one batch into pieces: the kernel choice follows the whole batch
+thread_local int64_t g_batch_hint = 0;
+
 struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t fn = nullptr;
@@ -299,17 +459,91 @@ std::mutex & jit_mutex() { static std::mutex m; return m; }
 int env_int(const char * name, int dflt) { const char * v = getenv(name); return v ? atoi(v) : dflt; }
 }
 
+namespace {
+std::map<std::pair<const tchem_sap_table *, const tchem_ic_table *>, JitKernel> & chain_kernels() {
+    static std::map<std::pair<const tchem_sap_table *, const tchem_ic_table *>, JitKernel> m;
+    return m;
+}
+}
+
 void release_jit(const tchem_ic_table * t) {
     std::lock_guard<std::mutex> lock(jit_mutex());
     auto it = jit_kernels().find(t);
     if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
+    for (auto c = chain_kernels().begin(); c != chain_kernels().end();) {
+        if (c->first.second == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
+        else ++c;
+    }
+}
+void release_jit_sap(const tchem_sap_table * t) {
+    std::lock_guard<std::mutex> lock(jit_mutex());
+    for (auto c = chain_kernels().begin(); c != chain_kernels().end();) {
+        if (c->first.first == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
+        else ++c;
+    }
+}
+
+namespace {
+// NVRTC-compiles `src`, loads `name` and sizes the launch; marks `jk.failed` on any problem
+void jit_finish(JitKernel & jk, const std::string & src, const char * name, size_t smem, int max_smem_optin, bool debug) {
+    std::string log;
+    std::vector<char> cubin;
+    if (!src.empty()) cubin = jit_compile(src, log, debug);
+    if (debug) fprintf(stderr, "[tchem] jit %s: %zu bytes of source, %zu bytes of cubin\n%s\n", name, src.size(), cubin.size(), log.c_str());
+    jk.smem = smem;
+    if (cubin.empty()) jk.failed = true;
+    else if (cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess
+             || cudaLibraryGetKernel(&jk.fn, jk.lib, name) != cudaSuccess
+             || smem > (size_t)max_smem_optin
+             || cudaFuncSetAttribute((const void *)jk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+             || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jk.per_sm, (const void *)jk.fn, jk.warps * 32, smem) != cudaSuccess
+             || jk.per_sm < 1) {
+        cudaGetLastError();
+        jk.failed = true;
+    }
+    if (debug) fprintf(stderr, "[tchem] jit %s: %s, %d warps/block, %d blocks/SM, %zu B smem\n", name,
+                       jk.failed ? "FAILED (interpreter serves this table)" : "ok", jk.warps, jk.per_sm, jk.smem);
+}
+}
+
+// chained r -> q -> SAPSet through a kernel specialised to (IntCoordSet, SAPSet); -1: not eligible
+int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
+                     double * q, double * y, double * J, cudaStream_t stream) {
+    static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
+    static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
+    if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128
+        || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return -1;
+    JitKernel * k;
+    {
+        std::lock_guard<std::mutex> lock(jit_mutex());
+        JitKernel & jk = chain_kernels()[{st, t}];
+        k = &jk;
+        if (!jk.fn && !jk.failed) {
+            // one chunk when the whole set fits ~128 staged entries: a chunk that ends inside a geometry's
+            // y / J block leaves 32-byte sectors half written, and partial-sector writes cost DRAM
+            // read-modify-write traffic (measured on C5: 2 chunks 3.55 ms, 1 chunk 1.79 ms)
+            const int per_term = 1 + st->sumdim, nt = st->nterms;
+            const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, 76));
+            jk.warps = env_int("TCHEM_JIT_WARPS", 4);
+            jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
+            const int nchunks = (nt * per_term + dcap - 1) / dcap, tper = (nt + nchunks - 1) / nchunks;
+            const std::string src = jit_chain_source(t->terms, t->intdim, t->cartdim, st->h_terms, dcap, jk.warps, jk.blocks);
+            const size_t smem = (size_t)jk.warps * (t->cartdim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
+            jit_finish(jk, src, "tchem_jit_chain", smem, t->max_smem_optin, debug);
+        }
+        if (jk.failed) return -1;
+    }
+    const int64_t ntiles = (B + 31) / 32;
+    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
+    long long Bll = B;
+    void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
+    TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    count_launch();
+    return TCHEM_OK;
 }
 
 // q + J through the specialised kernel. Returns TCHEM_OK when launched, -1 when this table / batch
 // is served by the interpreter instead (never an error by itself).
-// the host-buffer entry point cuts one batch into pieces: the kernel choice follows the whole batch
-thread_local int64_t g_batch_hint = 0;
-
 int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double * q, double * J, cudaStream_t stream) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
     static const bool debug = getenv("TCHEM_DEBUG") != nullptr;

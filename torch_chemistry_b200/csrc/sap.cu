@@ -14,48 +14,14 @@
 #include "ic_eval.cuh"
 #include "ic_table.h"
 
-namespace tchem_b200 {
-
-// distinct coordinate of a monomial: x[col]^power; e_pow / e_powm1 = entries of the per-lane power
-// table holding x[col]^power and x[col]^(power-1)
-struct SapUniq { int32_t col, power, e_pow, e_powm1; };
-struct SapTerm { int32_t ubegin, uend; };         // distinct coordinates of one monomial
-
-struct SapProgram {                               // device pointers
-    const SapTerm *   terms;
-    const SapUniq *   uniqs;
-    const ChunkDesc * chunks;                     // prim_begin/end = term range, row0/nrows likewise
-    const ElemMap *   emap;
-    const uint4 *     psrcs;
-    const double *    coefs;
-    const ZeroRun *   runs;
-    const int32_t *   pow_off;                    // power table: entries pow_off[col] + p hold x[col]^p, p = 0..maxpow
-    int32_t nterms, nuniqs, nchunks, cap, sumdim, npow;
-};
-
-int ensure_program(tchem_ic_table * t, int mode);
-
-} // namespace tchem_b200
-
-struct SapHostPipe {                     // device staging of the chained host-buffer entry point
-    static constexpr int kSlots = 3;
-    cudaStream_t stream[kSlots] = {};
-    double * buf[kSlots] = {};
-    size_t cap = 0;
-    bool ok = false;
-};
-
-struct tchem_sap_table {
-    SapHostPipe pipe;
-    int device = 0;
-    int nterms = 0, sumdim = 0, irreducible = 0;
-    int sm_count = 0, max_smem_optin = 0;
-    std::vector<int32_t> dims;
-    tchem_b200::SapProgram prog;
-    void * dev_blob = nullptr;
-};
+#include "sap_table.h"
 
 namespace tchem_b200 {
+
+int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
+                     double * q, double * y, double * J, cudaStream_t stream);
+void release_jit_sap(const tchem_sap_table * t);
+extern thread_local int64_t g_batch_hint;
 
 namespace {
 
@@ -234,6 +200,11 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
 int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const double * in, int64_t B,
                double * q_out, double * y, double * J, cudaStream_t stream) {
     const bool chained = ict != nullptr;
+    if (chained) {
+        // large batches of small molecules: the kernel specialised to this (IntCoordSet, SAPSet) pair
+        const int rc = launch_jit_chain(st, ict, in, B, q_out, y, J, stream);
+        if (rc != -1) return rc;
+    }
     const void * fn = !chained ? reinterpret_cast<const void *>(&sap_eval_kernel<false, false>)
                     : ict->has5 ? reinterpret_cast<const void *>(&sap_eval_kernel<true, true>)
                                 : reinterpret_cast<const void *>(&sap_eval_kernel<true, false>);
@@ -363,6 +334,10 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
     tchem_sap_table * t = new tchem_sap_table();
     t->device = device; t->nterms = n_terms; t->sumdim = sumdim; t->irreducible = irreducible;
     t->dims.assign(dims, dims + n_irreducibles);
+    for (const SapTerm & tm : terms) {
+        t->h_terms.emplace_back();
+        for (int u = tm.ubegin; u < tm.uend; u++) t->h_terms.back().push_back({uniqs[u].col, uniqs[u].power});
+    }
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&t->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     unsigned char * d = static_cast<unsigned char *>(dev);
@@ -386,6 +361,7 @@ void tchem_sap_table_destroy(tchem_sap_table * t) {
     if (!t) return;
     {
         DeviceGuard guard(t->device);
+        release_jit_sap(t);
         cudaFree(t->dev_blob);
         for (int s = 0; s < SapHostPipe::kSlots; s++) {
             cudaFree(t->pipe.buf[s]);
@@ -458,6 +434,7 @@ int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sa
         hp.cap = need;
     }
     int slot = 0;
+    struct HintScope { HintScope(int64_t b) { g_batch_hint = b; } ~HintScope() { g_batch_hint = 0; } } hint(B);
     for (int64_t b0 = 0; b0 < B; b0 += piece, slot = (slot + 1) % SapHostPipe::kSlots) {
         const int64_t nb = std::min<int64_t>(piece, B - b0);
         cudaStream_t s = hp.stream[slot];
