@@ -139,39 +139,35 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
     std::vector<Pending> pend;
     {
         Pending cur{0, 0, false, {}};
-        std::map<PrimKey, int> cur_prims;
-        int cur_entries = 0;
         auto flush = [&]() {
             if (cur.nrows > 0) pend.push_back(cur);
             cur = Pending{0, 0, false, {}};
-            cur_prims.clear();
-            cur_entries = 0;
         };
-        for (int i = 0; i < n_ic; i++) {
-            // entries this row would add to the current chunk
-            std::map<PrimKey, int> add;
-            int add_entries = 1, alone_entries = 1;      // + the row's q slot
-            {
-                std::map<PrimKey, int> alone;
-                for (int t : rows[i]) {
-                    PrimKey k = key_of(terms[t]);
-                    int e = prim_entries(terms[t].natoms, mode);
-                    if (alone.emplace(k, 0).second) alone_entries += e;
-                    if (!cur_prims.count(k) && add.emplace(k, 0).second) add_entries += e;
-                }
-            }
-            if (cur.nrows > 0 && cur_entries + add_entries <= hp.cap) {
-                for (auto & kv : add) cur_prims.insert(kv);
-                cur_entries += add_entries;
-                cur.nrows++;
-                for (int t : rows[i]) cur.term_ids.push_back(t);
-                continue;
-            }
-            flush();
-            if (alone_entries <= hp.cap) {
-                cur.row0 = i; cur.nrows = 1;
-                for (int t : rows[i]) { cur_prims.emplace(key_of(terms[t]), 0); cur.term_ids.push_back(t); }
-                cur_entries = alone_entries;
+        // entries of rows [s, e) staged together (shared primitives counted once)
+        auto entries_of = [&](int s, int e) {
+            std::map<PrimKey, int> seen;
+            int n = e - s;                               // the rows' q slots
+            for (int i = s; i < e; i++)
+                for (int t : rows[i])
+                    if (seen.emplace(key_of(terms[t]), 0).second) n += prim_entries(terms[t].natoms, mode);
+            return n;
+        };
+        // a chunk that ends inside a 32-byte sector of q (4 rows) or of J leaves that sector half
+        // written; the partial write costs a DRAM read-modify-write.  Prefer ends on 4-row boundaries.
+        auto aligned = [&](int e) { return e == n_ic || e % 4 == 0; };
+        for (int i = 0; i < n_ic; ) {
+            int e_max = i;
+            while (e_max < n_ic && entries_of(i, e_max + 1) <= hp.cap) e_max++;
+            if (e_max > i) {
+                int e = e_max;
+                while (e > i && !aligned(e)) e--;
+                // ... unless the rows pushed out share primitives with the ones kept (recomputing
+                // them costs more than the sector)
+                if (e == i || entries_of(i, e) + entries_of(e, e_max) != entries_of(i, e_max)) e = e_max;
+                cur.row0 = i; cur.nrows = e - i;
+                for (int r = i; r < e; r++) for (int t : rows[r]) cur.term_ids.push_back(t);
+                flush();
+                i = e;
                 continue;
             }
             // split row
@@ -197,6 +193,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             }
             part.accumulate = !first;
             pend.push_back(part);
+            i++;
         }
         flush();
     }

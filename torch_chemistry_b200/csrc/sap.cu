@@ -291,6 +291,9 @@ int tchem_sap_table_create(const int32_t * term_ptr, const int32_t * coords, int
             entries += 1 + terms[t1].uend - terms[t1].ubegin;
             t1++;
         }
+        // end on a 4-term boundary when possible: y (8 B per term) and J then fill whole 32-byte
+        // sectors instead of leaving them half written between chunks
+        if (t1 < n_terms && t1 % 4 != 0 && (t1 & ~3) > t0) t1 &= ~3;
         ChunkDesc ch;
         std::memset(&ch, 0, sizeof(ch));
         ch.prim_begin = t0; ch.prim_end = t1; ch.row0 = t0; ch.nrows = t1 - t0;
