@@ -400,7 +400,7 @@ def main():
                   else "tchem_jit_qJ (table-specialised, NVRTC)" if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)
                   else "ic_eval_kernel")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "traffic": ncu_traffic(args.workload) if B == DEFAULT_BATCH[args.workload] else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_geometry": bytes_per_geom, "kernel": kernel, "launch_ms": avg_launch_s * 1e3}
         if args.workload in FLOPS:
             fl = FLOPS[args.workload](cd, n)
