@@ -395,7 +395,8 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
-        kernel = ("sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
+        kernel = ("tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
+                  else "sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
                   else "dense_kernel" if args.workload in FLOPS
                   else "tchem_jit_qJ (table-specialised, NVRTC)" if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)
                   else "ic_eval_kernel")

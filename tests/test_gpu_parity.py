@@ -216,6 +216,38 @@ def test_chained_sap_C5(T):
     assert_parity(host(J), osap.jacobian(qo), "C5 chained Jacobian vs oracle")
 
 
+def test_chained_specialised_multichunk_C2(T):
+    """A SAPSet over all 12 C2H4 coordinates with 40 monomials (orders 0-4, repeated columns):
+    (1 + 12) * 40 staged entries do not fit one chunk, so the pair-specialised kernel runs its
+    multi-chunk path; small batches run the interpreter. Both against the oracle."""
+    w = T.workloads.get("C2")
+    rng = np.random.default_rng(5)
+    dims = [5, 4, 3]
+    cols = [(i + 1, j + 1) for i, d in enumerate(dims) for j in range(d)]
+    lines = [""]                                              # the 0th-order term is an empty line
+    for t in range(39):
+        order = 1 + t % 4
+        picks = sorted((cols[k] for k in rng.integers(0, len(cols), order)), reverse=True)
+        lines.append("    ".join("%d,%d" % p for p in picks))
+    text = "\n".join(lines) + "\n"
+    ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    sap = T.SAPSet.from_text(text, 0, dims)
+    orc, osap = O.IntCoordSet("default", w.ic_text), O.SAPSet(text, 0, dims)
+    assert sap.nterms == 40 == osap.nterms
+    for n in (20011, 517):
+        r = w.geometries(n, seed=n)
+        assert bool(T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, n)) == (n >= 16384)
+        y, J, q = sap.chained(ic, dev(r), return_q=True)
+        idx = np.arange(0, n, 7)
+        qo = orc.qJ(r[idx])[0]
+        assert_q_parity(host(q[idx]), qo, orc.terms(), r[idx], "C2 chained q")
+        # monomials of the oracle's own q would differ by the torsion allowance: evaluate the oracle
+        # polynomial on the q this library produced (q itself is checked above)
+        qd = host(q[idx])
+        assert_parity(host(y[idx]), osap.value(qd), "C2 chained value (n=%d)" % n)
+        assert_parity(host(J[idx]), osap.jacobian(qd), "C2 chained Jacobian (n=%d)" % n)
+
+
 def test_gradient_int2cart_reference_fixture(T):
     g = golden("ref_aniline_default")
     s = T.IntCoordSet.from_text("default", str(g["definition"]), n_atoms=14)

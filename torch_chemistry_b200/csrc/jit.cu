@@ -624,6 +624,16 @@ int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B) {
     return it == jit_kernels().end() || !it->second.failed ? 1 : 0;
 }
 
+// 1 when tchem_ic_sap_eval on B geometries runs the pair-specialised chained kernel
+int tchem_ic_sap_uses_specialised(const tchem_sap_table * st, const tchem_ic_table * t, int64_t B) {
+    static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
+    if (!st || !t || !enabled || B < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128
+        || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return 0;
+    std::lock_guard<std::mutex> lock(jit_mutex());
+    auto it = chain_kernels().find({st, t});
+    return it == chain_kernels().end() || !it->second.failed ? 1 : 0;
+}
+
 // compiles that source for sm_100a (no device needed); 0 on success, the NVRTC / ptxas log in `log`
 int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity) {
     std::string l;
