@@ -56,66 +56,64 @@ __device__ __forceinline__ void dmma(double & d0, double & d1, double a, double 
 
 // C[M x N] = (ACC ? C : 0) + s * opA(A)[M x K] * opB(B)[K x N], all operands in shared memory.
 //   TA: A is stored K x M (opA(A)[m][k] = A[k * lda + m]);  TB: B is stored N x K.
+//   LOWER: only the 16 x 16 tiles on or below the diagonal are formed (symmetric updates).
 // Each warp owns 16 x 16 tiles of C (2 x 2 DMMA tiles). Leading dimensions = 4 or 12 (mod 16)
-// keep both fragment access patterns free of bank conflicts.
-template <bool TA, bool TB, bool ACC>
+// keep both fragment access patterns free of bank conflicts. Edge tiles read a clamped (in-bounds)
+// row / column instead of predicating every load: D[m][n] only depends on row m of A and column n
+// of B, and the duplicated rows are simply not stored. K is walked in unpredicated steps of 4 with
+// one masked tail step.
+template <bool TA, bool TB, bool ACC, bool LOWER = false>
 __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
                             double * C, int ldc, double s = 1.0) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int tm = (M + 15) / 16, tn = (N + 15) / 16;
-    for (int t = warp; t < tm * tn; t += nwarps) {
-        const int m0 = (t / tn) * 16, n0 = (t % tn) * 16;
-        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-        const bool full = m0 + 16 <= M && n0 + 16 <= N && (K & 3) == 0;
-        if (full) {
-            for (int k0 = 0; k0 < K; k0 += 4) {
-                double a[2], b[2];
+    const int tm = (M + 15) >> 4, tn = (N + 15) >> 4;
+    const int K4 = K & ~3;
+    const int sa = TA ? lda : 1, sb = TB ? 1 : ldb;          // stride between consecutive k
+    int mt = 0, nt = warp;                                    // tile coordinates, advanced without division
+    while (nt >= tn) { nt -= tn; mt++; }
+    for (; mt < tm; ) {
+        if (!LOWER || nt <= mt) {
+            const int m0 = mt * 16, n0 = nt * 16;
+            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            const double * pa[2], * pb[2];
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int m = m0 + 8 * i + gid, k = k0 + tig;
-                    a[i] = TA ? A[k * lda + m] : A[m * lda + k];
-                }
+            for (int i = 0; i < 2; i++) {
+                const int m = min(m0 + 8 * i + gid, M - 1), n = min(n0 + 8 * i + gid, N - 1);
+                pa[i] = A + (TA ? m : m * lda) + tig * sa;
+                pb[i] = B + (TB ? n * ldb : n) + tig * sb;
+            }
+#pragma unroll 2
+            for (int k0 = 0; k0 < K4; k0 += 4) {
+                const double a0 = pa[0][k0 * sa], a1 = pa[1][k0 * sa], b0 = pb[0][k0 * sb], b1 = pb[1][k0 * sb];
+                dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+                dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+                dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+                dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+            }
+            if (K4 < K) {
+                const bool in = K4 + tig < K;
+                const int k0 = in ? K4 : K - 1 - tig;        // clamped address, value masked
+                const double a0 = in ? pa[0][k0 * sa] : 0.0, a1 = in ? pa[1][k0 * sa] : 0.0;
+                const double b0 = in ? pb[0][k0 * sb] : 0.0, b1 = in ? pb[1][k0 * sb] : 0.0;
+                dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+                dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+                dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+                dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const int n = n0 + 8 * j + gid, k = k0 + tig;
-                    b[j] = TB ? B[n * ldb + k] : B[k * ldb + n];
+                    const int m = m0 + 8 * i + gid, n = n0 + 8 * j + 2 * tig;
+                    if (m < M) {
+                        if (n < N)     C[m * ldc + n]     = (ACC ? C[m * ldc + n] : 0.0) + s * acc[i][j][0];
+                        if (n + 1 < N) C[m * ldc + n + 1] = (ACC ? C[m * ldc + n + 1] : 0.0) + s * acc[i][j][1];
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        } else {
-            for (int k0 = 0; k0 < K; k0 += 4) {
-                double a[2], b[2];
-                const int k = k0 + tig;
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int m = m0 + 8 * i + gid;
-                    a[i] = (m < M && k < K) ? (TA ? A[k * lda + m] : A[m * lda + k]) : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int n = n0 + 8 * j + gid;
-                    b[j] = (n < N && k < K) ? (TB ? B[n * ldb + k] : B[k * ldb + n]) : 0.0;
-                }
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
         }
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int m = m0 + 8 * i + gid, n = n0 + 8 * j + 2 * tig;
-                if (m < M) {
-                    if (n < N)     C[m * ldc + n]     = (ACC ? C[m * ldc + n] : 0.0) + s * acc[i][j][0];
-                    if (n + 1 < N) C[m * ldc + n + 1] = (ACC ? C[m * ldc + n + 1] : 0.0) + s * acc[i][j][1];
-                }
-            }
+        nt += nwarps;
+        while (nt >= tn) { nt -= tn; mt++; }
     }
 }
 
@@ -241,54 +239,126 @@ __device__ __forceinline__ void block_store(const double * s, double * __restric
     }
 }
 
-// In-place lower Cholesky factor of the n x n matrix A (lda), then Linv = L^-1 (lower) into W and
-// A <- Linv^T Linv = (L L^T)^-1 (full symmetric), i.e. potrf + trtri + lauum.
+// (J J^T)^-1 the way LAPACK does it behind at::cholesky / at::cholesky_inverse: blocked potrf, then
+// potri = trtri (explicit inverse of the factor) + lauum (L^-T L^-1), block size 16.
+//   A (n x n, lda): in  = the SPD matrix (lower triangle read),  out = its inverse (full, symmetric)
+//   W (n x n, ldw): scratch, ends as L^-1 (lower, zeros above)
+// Work split: the 16 x 16 diagonal blocks are handled by one warp in registers (the sequential part:
+// 16 dependent sqrt / scale steps), the panel below by one thread per row, everything else - the
+// trailing updates, the block rows of L^-1, the final product - by DMMA.
 // Returns false (all threads) when a pivot is not positive.
-__device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw) {
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = 0;
-    __syncthreads();
-    for (int j = 0; j < n; j++) {
-        // column j: A[j][j] <- sqrt, A[i][j] <- A[i][j] / A[j][j]
-        const double d = A[j * lda + j];
-        __syncthreads();
-        if (!(d > 0.0)) { if (threadIdx.x == 0) bad = 1; break; }
+constexpr int kNB = 16;
+constexpr int kMaxN = 256;
+
+// lanes 0..15 = rows of the diagonal block at D (bs <= 16 rows): in-place lower Cholesky factor;
+// dinv[j] = 1 / L[j][j]. Lanes / columns >= bs carry an identity so every lane runs the same code.
+__device__ __forceinline__ bool warp_potrf16(double * D, int ld, int bs, double * dinv, int lane) {
+    double a[kNB];
+    const bool live = lane < bs;
+#pragma unroll
+    for (int k = 0; k < kNB; k++) a[k] = (live && k <= lane) ? D[lane * ld + k] : (k == lane ? 1.0 : 0.0);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < kNB; j++) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        ok = ok && d > 0.0;
         const double sd = sqrt(d), isd = 1.0 / sd;
-        for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i * lda + j] = (i == j) ? sd : A[i * lda + j] * isd;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][k] -= A[i][j] * A[k][j], j < k <= i
-        // (16 x 16 thread grid striding over rows and columns: no index division)
-        {
-            const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, ny = blockDim.x >> 4;
-            for (int i = j + 1 + ty; i < n; i += ny) {
-                const double lij = A[i * lda + j];
-                for (int k = j + 1 + tx; k <= i; k += 16) A[i * lda + k] -= lij * A[k * lda + j];
+        if (lane == j) { a[j] = sd; if (live) dinv[j] = isd; }
+        else if (lane > j) a[j] *= isd;
+#pragma unroll
+        for (int k = 0; k < kNB; k++) {
+            if (k > j) {
+                const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                if (lane >= k) a[k] = fma(-a[j], lkj, a[k]);
             }
         }
+    }
+#pragma unroll
+    for (int k = 0; k < kNB; k++)
+        if (live && k <= lane) D[lane * ld + k] = a[k];
+    return ok;
+}
+
+// lanes 0..15 = columns of the inverse of the lower-triangular diagonal block D (bs rows), written
+// to X (same shape, zeros above the diagonal); dinv = reciprocals of D's diagonal
+__device__ __forceinline__ void warp_trtri16(const double * D, int ld, int bs, const double * dinv, double * X, int ldx, int lane) {
+    double x[kNB];
+    const int c = lane;
+#pragma unroll
+    for (int i = 0; i < kNB; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kNB; k++)
+            if (k < i) s = fma(i < bs ? D[i * ld + k] : 0.0, x[k], s);                  // x[k] = 0 for k < c
+        x[i] = i == c ? (i < bs ? dinv[i] : 0.0) : (i > c && i < bs ? -s * dinv[i] : 0.0);
+    }
+    if (c < bs) {
+#pragma unroll
+        for (int i = 0; i < kNB; i++)
+            if (i < bs) X[i * ldx + c] = x[i];
+    }
+}
+
+__device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw) {
+    __shared__ int bad;
+    __shared__ double dinv[kMaxN];
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    // ---- potrf, right-looking over 16-column panels
+    for (int jb = 0; jb < n; jb += kNB) {
+        const int bs = min(kNB, n - jb), below = n - jb - bs;
+        double * D = A + jb * lda + jb;
+        if (warp == 0) {
+            const bool ok = warp_potrf16(D, lda, bs, dinv + jb, lane);
+            if (!ok && lane == 0) bad = 1;
+        }
         __syncthreads();
+        if (bad) break;
+        if (below > 0) {
+            // panel rows: x L11^T = a, one thread per row (L11 reads are broadcasts)
+            for (int i = threadIdx.x; i < below; i += blockDim.x) {
+                double * row = A + (jb + bs + i) * lda + jb;
+                double x[kNB];
+#pragma unroll
+                for (int j = 0; j < kNB; j++) {
+                    double sacc = row[j];
+#pragma unroll
+                    for (int k = 0; k < kNB; k++)
+                        if (k < j) sacc = fma(-x[k], D[j * lda + k], sacc);
+                    x[j] = sacc * dinv[jb + j];
+                }
+#pragma unroll
+                for (int j = 0; j < kNB; j++) row[j] = x[j];
+            }
+            __syncthreads();
+            // trailing block: A22 -= P P^T (lower tiles)
+            const double * P = A + (jb + bs) * lda + jb;
+            block_dgemm<false, true, true, true>(below, below, kNB, P, lda, P, lda, A + (jb + bs) * lda + jb + bs, lda, -1.0);
+            __syncthreads();
+        }
     }
     __syncthreads();
     if (bad) return false;
-    // Linv: column c solves L x = e_c by forward substitution, one column per thread
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        for (int i = 0; i < c; i++) W[i * ldw + c] = 0.0;
-        W[c * ldw + c] = 1.0 / A[c * lda + c];
-        for (int i = c + 1; i < n; i++) {
-            // four independent partial sums: the dot product is latency bound otherwise
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = c;
-            for (; k + 3 < i; k += 4) {
-                s0 = fma(A[i * lda + k], W[k * ldw + c], s0);
-                s1 = fma(A[i * lda + k + 1], W[(k + 1) * ldw + c], s1);
-                s2 = fma(A[i * lda + k + 2], W[(k + 2) * ldw + c], s2);
-                s3 = fma(A[i * lda + k + 3], W[(k + 3) * ldw + c], s3);
-            }
-            for (; k < i; k++) s0 = fma(A[i * lda + k], W[k * ldw + c], s0);
-            W[i * ldw + c] = -((s0 + s1) + (s2 + s3)) / A[i * lda + i];
-        }
+    // ---- trtri: W = L^-1. Diagonal blocks first (one warp each), zeros above the diagonal
+    const int nblk = (n + kNB - 1) / kNB;
+    for (int i = threadIdx.x; i < n * ldw; i += blockDim.x) W[i] = 0.0;
+    __syncthreads();
+    for (int b = warp; b < nblk; b += nwarps) {
+        const int jb = b * kNB;
+        if (lane < kNB) warp_trtri16(A + jb * lda + jb, lda, min(kNB, n - jb), dinv + jb, W + jb * ldw + jb, ldw, lane);
     }
     __syncthreads();
-    // A <- W^T W
+    // block row I: W[I][0:I] = -W[I][I] * (L[I][0:I] * W[0:I][0:I])
+    for (int ib = kNB; ib < n; ib += kNB) {
+        const int bs = min(kNB, n - ib);
+        block_dgemm<false, false, false>(bs, ib, ib, A + ib * lda, lda, W, ldw, W + ib * ldw, ldw);
+        __syncthreads();
+        // in place: every warp reads the columns of its own tile completely before it stores them
+        block_dgemm<false, false, false>(bs, ib, bs, W + ib * ldw + ib, ldw, W + ib * ldw, ldw, W + ib * ldw, ldw, -1.0);
+        __syncthreads();
+    }
+    // ---- lauum: A <- W^T W
     block_dgemm<true, false, false>(n, n, n, W, ldw, W, ldw, A, lda);
     __syncthreads();
     return true;
@@ -494,6 +564,8 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     if (B < 0) return set_error(TCHEM_EINVAL, name + ": negative batch");
     if (B == 0) return TCHEM_OK;
     if (!r || !out || (op >= 1 && !in1) || (op >= 2 && !in2)) return set_error(TCHEM_EINVAL, name + ": null argument");
+    if (op != 2 && t->intdim > kMaxN)
+        return set_error(TCHEM_EINVAL, name + ": too many internal coordinates for the per-geometry shared-memory plan");
     if (op != 2 && t->intdim > t->cartdim)
         return set_error(TCHEM_EINVAL, name + ": more internal coordinates than Cartesian coordinates (J J^T is singular)");
     DeviceGuard guard(t->device);
@@ -504,7 +576,7 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     const void * fn = op == 0 ? dense_fn<0>(t->has5) : op == 1 ? dense_fn<1>(t->has5) : op == 2 ? dense_fn<2>(t->has5) : dense_fn<3>(t->has5);
     const DensePlan pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh);
     const size_t smem = (size_t)pl.total * sizeof(double);
-    if (smem > (size_t)t->max_smem_optin)
+    if (smem + 4096 > (size_t)t->max_smem_optin)        // + the kernel's static shared memory
         return set_error(TCHEM_EINVAL, name + ": molecule too large for the per-geometry shared-memory plan");
     TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
