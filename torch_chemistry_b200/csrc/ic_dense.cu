@@ -56,13 +56,16 @@ __device__ __forceinline__ void dmma(double & d0, double & d1, double a, double 
 
 // C[M x N] = (ACC ? C : 0) + s * opA(A)[M x K] * opB(B)[K x N], all operands in shared memory.
 //   TA: A is stored K x M (opA(A)[m][k] = A[k * lda + m]);  TB: B is stored N x K.
-//   LOWER: only the 16 x 16 tiles on or below the diagonal are formed (symmetric updates).
+//   TRI: 0 = all tiles; 1 = only the 16 x 16 tiles on or below the diagonal (symmetric result of
+//        which the lower triangle is wanted); 2 = those tiles, mirrored into the upper triangle.
+//   KS:  operands with structural zeros - 1: terms with k < m0 vanish (W^T W, W lower triangular),
+//        2: terms with k < n0 vanish (L W).
 // Each warp owns 16 x 16 tiles of C (2 x 2 DMMA tiles). Leading dimensions = 4 or 12 (mod 16)
 // keep both fragment access patterns free of bank conflicts. Edge tiles read a clamped (in-bounds)
 // row / column instead of predicating every load: D[m][n] only depends on row m of A and column n
 // of B, and the duplicated rows are simply not stored. K is walked in unpredicated steps of 4 with
 // one masked tail step.
-template <bool TA, bool TB, bool ACC, bool LOWER = false>
+template <bool TA, bool TB, bool ACC, int TRI = 0, int KS = 0>
 __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
                             double * C, int ldc, double s = 1.0) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -73,8 +76,9 @@ __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, cons
     int mt = 0, nt = warp;                                    // tile coordinates, advanced without division
     while (nt >= tn) { nt -= tn; mt++; }
     for (; mt < tm; ) {
-        if (!LOWER || nt <= mt) {
+        if (TRI == 0 || nt <= mt) {
             const int m0 = mt * 16, n0 = nt * 16;
+            const int kbeg = KS == 1 ? m0 : KS == 2 ? n0 : 0;
             double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
             const double * pa[2], * pb[2];
 #pragma unroll
@@ -84,7 +88,7 @@ __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, cons
                 pb[i] = B + (TB ? n * ldb : n) + tig * sb;
             }
 #pragma unroll 2
-            for (int k0 = 0; k0 < K4; k0 += 4) {
+            for (int k0 = kbeg; k0 < K4; k0 += 4) {
                 const double a0 = pa[0][k0 * sa], a1 = pa[1][k0 * sa], b0 = pb[0][k0 * sb], b1 = pb[1][k0 * sb];
                 dmma(acc[0][0][0], acc[0][0][1], a0, b0);
                 dmma(acc[0][1][0], acc[0][1][1], a0, b1);
@@ -109,6 +113,10 @@ __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, cons
                     if (m < M) {
                         if (n < N)     C[m * ldc + n]     = (ACC ? C[m * ldc + n] : 0.0) + s * acc[i][j][0];
                         if (n + 1 < N) C[m * ldc + n + 1] = (ACC ? C[m * ldc + n + 1] : 0.0) + s * acc[i][j][1];
+                        if (TRI == 2 && nt < mt) {           // square result: M == N
+                            if (n < N) C[n * ldc + m] = (ACC ? C[n * ldc + m] : 0.0) + s * acc[i][j][0];
+                            if (n + 1 < N) C[(n + 1) * ldc + m] = (ACC ? C[(n + 1) * ldc + m] : 0.0) + s * acc[i][j][1];
+                        }
                     }
                 }
         }
@@ -262,7 +270,11 @@ __device__ __forceinline__ bool warp_potrf16(double * D, int ld, int bs, double 
     for (int j = 0; j < kNB; j++) {
         const double d = __shfl_sync(0xffffffffu, a[j], j);
         ok = ok && d > 0.0;
-        const double sd = sqrt(d), isd = 1.0 / sd;
+        // 1/sqrt first (one dependent chain instead of sqrt followed by a division); the square root
+        // is d * isd with one correction step
+        const double isd = rsqrt(d);
+        double sd = d * isd;
+        sd = fma(fma(-sd, sd, d), 0.5 * isd, sd);
         if (lane == j) { a[j] = sd; if (live) dinv[j] = isd; }
         else if (lane > j) a[j] *= isd;
 #pragma unroll
@@ -334,7 +346,7 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
             __syncthreads();
             // trailing block: A22 -= P P^T (lower tiles)
             const double * P = A + (jb + bs) * lda + jb;
-            block_dgemm<false, true, true, true>(below, below, kNB, P, lda, P, lda, A + (jb + bs) * lda + jb + bs, lda, -1.0);
+            block_dgemm<false, true, true, 1>(below, below, kNB, P, lda, P, lda, A + (jb + bs) * lda + jb + bs, lda, -1.0);
             __syncthreads();
         }
     }
@@ -352,14 +364,14 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
     // block row I: W[I][0:I] = -W[I][I] * (L[I][0:I] * W[0:I][0:I])
     for (int ib = kNB; ib < n; ib += kNB) {
         const int bs = min(kNB, n - ib);
-        block_dgemm<false, false, false>(bs, ib, ib, A + ib * lda, lda, W, ldw, W + ib * ldw, ldw);
+        block_dgemm<false, false, false, 0, 2>(bs, ib, ib, A + ib * lda, lda, W, ldw, W + ib * ldw, ldw);
         __syncthreads();
         // in place: every warp reads the columns of its own tile completely before it stores them
         block_dgemm<false, false, false>(bs, ib, bs, W + ib * ldw + ib, ldw, W + ib * ldw, ldw, W + ib * ldw, ldw, -1.0);
         __syncthreads();
     }
     // ---- lauum: A <- W^T W
-    block_dgemm<true, false, false>(n, n, n, W, ldw, W, ldw, A, lda);
+    block_dgemm<true, false, false, 2, 1>(n, n, n, W, ldw, W, ldw, A, lda);
     __syncthreads();
     return true;
 }
@@ -427,7 +439,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         // OP 0, 1, 3 start with M = (J J^T)^-1 J
         double * J = arena, * A = arena + n * ldj, * W = Mreg;           // W (n x n, ldh) borrows the M region
         block_compute_J<HAS5>(dp, rg, J);
-        block_dgemm<false, true, false>(n, n, cd, J, ldj, J, ldj, A, ldh);           // A = J J^T
+        block_dgemm<false, true, false, 1>(n, n, cd, J, ldj, J, ldj, A, ldh);        // A = J J^T (lower)
         __syncthreads();
         const bool ok = block_spd_inverse(n, A, ldh, W, ldh);                        // A = (J J^T)^-1
         if (!ok && threadIdx.x == 0) atomicExch(status, 1);
