@@ -265,24 +265,35 @@ __device__ __forceinline__ bool warp_potrf16(double * D, int ld, int bs, double 
     const bool live = lane < bs;
 #pragma unroll
     for (int k = 0; k < kNB; k++) a[k] = (live && k <= lane) ? D[lane * ld + k] : (k == lane ? 1.0 : 0.0);
-    bool ok = true;
+    // Software-pipelined over the pivots: the element the NEXT pivot depends on is updated first and
+    // its 1/sqrt started, the rest of this column's rank-1 update then runs under that latency.
+    // (1/sqrt rather than sqrt followed by a division: one dependent chain; sqrt = d * isd, corrected)
+    double d = __shfl_sync(0xffffffffu, a[0], 0);
+    bool ok = d > 0.0;
+    double isd = rsqrt(d);
 #pragma unroll
     for (int j = 0; j < kNB; j++) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        ok = ok && d > 0.0;
-        // 1/sqrt first (one dependent chain instead of sqrt followed by a division); the square root
-        // is d * isd with one correction step
-        const double isd = rsqrt(d);
-        double sd = d * isd;
-        sd = fma(fma(-sd, sd, d), 0.5 * isd, sd);
-        if (lane == j) { a[j] = sd; if (live) dinv[j] = isd; }
-        else if (lane > j) a[j] *= isd;
+        const double dj = d, isdj = isd;
+        if (lane > j) a[j] *= isdj;
+        if (j + 1 < kNB) {
+            const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
+            if (lane >= j + 1) a[j + 1] = fma(-a[j], l1, a[j + 1]);
+            d = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+            ok = ok && d > 0.0;
+            isd = rsqrt(d);
+        }
+        double l[kNB];
 #pragma unroll
-        for (int k = 0; k < kNB; k++) {
-            if (k > j) {
-                const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-                if (lane >= k) a[k] = fma(-a[j], lkj, a[k]);
-            }
+        for (int k = 0; k < kNB; k++)
+            if (k > j + 1) l[k] = __shfl_sync(0xffffffffu, a[j], k);
+#pragma unroll
+        for (int k = 0; k < kNB; k++)
+            if (k > j + 1 && lane >= k) a[k] = fma(-a[j], l[k], a[k]);
+        if (lane == j) {
+            double sd = dj * isdj;
+            sd = fma(fma(-sd, sd, dj), 0.5 * isdj, sd);
+            a[j] = sd;
+            if (live) dinv[j] = isdj;
         }
     }
 #pragma unroll
