@@ -30,13 +30,14 @@ WORKLOADS = {
     "C2": ("q+J", lambda cd, n, ns: 8 * (cd + n + n * cd)),
     "C3": ("q+J", lambda cd, n, ns: 8 * (cd + n + n * cd)),
     "C3K": ("q+J+K", lambda cd, n, ns: 8 * (cd + n + n * cd + n * cd * cd)),
+    "C4J": ("q+J", lambda cd, n, ns: 8 * (cd + n + n * cd)),
     "C4g": ("gradient_int2cart", lambda cd, n, ns: 8 * (cd + n + cd)),
     "C4gc": ("gradient_cart2int", lambda cd, n, ns: 8 * (cd + cd + n)),
     "C4H": ("Hessian_int2cart", lambda cd, n, ns: 8 * (cd + n + n * n + cd * cd)),
     "C4Hc": ("Hessian_cart2int", lambda cd, n, ns: 8 * (cd + cd + cd * cd + n * n)),
     "C5": ("q->SAPSet value+Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * n)),
 }
-DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4g": 10 ** 5, "C4gc": 10 ** 5, "C4H": 10 ** 5,
+DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4J": 5 * 10 ** 4, "C4g": 10 ** 5, "C4gc": 10 ** 5, "C4H": 10 ** 5,
                  "C4Hc": 10 ** 5, "C5": 12500000}
 # dense flops per geometry of the contraction-bound transforms
 FLOPS = {
@@ -220,7 +221,7 @@ def cpu_baseline(w, what, per_core, cores=None):
 
 def per_core_sample(key):
     # sized for roughly 10-20 s of CPU work per process with the reference's measured per-geometry cost
-    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000}[key]
+    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000}[key]
 
 
 # ------------------------------------------------------------------------------------------
@@ -267,7 +268,7 @@ def main():
     wl = importlib.util.module_from_spec(spec)
     sys.modules["_wl"] = wl
     spec.loader.exec_module(wl)
-    wkey = {"C3K": "C3", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
+    wkey = {"C3K": "C3", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
     w = wl.get(wkey)
     what, bytes_fn = WORKLOADS[args.workload]
     B = args.batch or DEFAULT_BATCH[args.workload]

@@ -5,6 +5,7 @@ it finishes in seconds, and (c) size-independent properties at BASELINE.json's f
 Tolerance (north_star): |x - ref| <= max(1e-12, 1e-12 |ref|), dihedral angles modulo 2 pi and
 with the acos-conditioning allowance of conftest.assert_q_parity."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -349,3 +350,17 @@ def test_specialised_kernel_matches_interpreter_and_oracle(T):
         assert_parity(host(J_big[idx]), Jo, key + " specialised J vs oracle")
         # ragged tail tile and J-only / q-only calls
         assert n % 32 != 0
+
+
+@pytest.mark.parametrize("env", [{"TCHEM_GROUP_G": "0"}, {"TCHEM_GROUP_G": "2"}, {"TCHEM_GROUP_G": "4"},
+                                 {"TCHEM_GROUP_G": "6", "TCHEM_LINE": "0"}, {"TCHEM_STAGE_SPANS": "0", "TCHEM_GROUP_G": "0"}])
+def test_warp_group_kernel_variants(T, env):
+    """Mid-size molecules run q + J on the warp-group kernel (default: 6 warps share a tile, line-buffer
+    write-out). The other launch shapes - one warp per tile, G = 2 / 4, no line buffer, tables not
+    staged - must give the same answers; the knobs are read once per process, hence the subprocess."""
+    import subprocess, sys
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_group_check.py")],
+                         env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]

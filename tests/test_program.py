@@ -20,7 +20,7 @@ class PrimDesc(C.Structure):
 
 
 class SpanDesc(C.Structure):
-    _fields_ = [("map", C.c_int64), ("n", C.c_int32), ("run0", C.c_int32), ("nruns", C.c_int32), ("pad", C.c_int32)]
+    _fields_ = [("map", C.c_int64), ("n", C.c_int32), ("run0", C.c_int32), ("nruns", C.c_int32), ("nnz", C.c_int32)]
 
 
 class ChunkDesc(C.Structure):

@@ -1,6 +1,7 @@
 // C ABI glue: error state, table life cycle, q/J/K entry points (include/tchem_b200.h).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -31,7 +32,29 @@ int ensure_program(tchem_ic_table * t, int mode) {
     std::lock_guard<std::mutex> lock(g_build_mutex);
     if (t->dev_blob[mode]) return TCHEM_OK;
     HostProgram hp;
-    int rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp);
+    int rc = TCHEM_OK;
+    bool grouped = false;
+    if (mode == MODE_QJ && t->cartdim > 36) {
+        // mid-size molecules (beyond the specialised kernel's range): q + J runs on the warp-group
+        // kernel - G warps share a tile's staged coordinates, 12 warps per SM. The compact capacity
+        // per warp is what is left of the shared memory (TCHEM_GROUP_G=0 disables, 2 / 4 / 6 force G)
+        static const int g_env = [] { const char * e = getenv("TCHEM_GROUP_G"); return e ? atoi(e) : 6; }();
+        const int G = (g_env == 2 || g_env == 4 || g_env == 6) ? g_env : 0;
+        if (G) {
+            const int ngroups = 12 / G;
+            // per group: cartdim coordinate rows + per warp `cap` compact rows (kPad doubles each) and a
+            // line buffer of rows_per_chunk * cartdim <= cap / 8 * cartdim doubles
+            const int group_doubles = ((t->max_smem_sm - 1024 - 12 * 1024) / ngroups) / (int)sizeof(double);
+            const int cap = (int)((group_doubles - t->cartdim * kPad) / (G * (kPad + t->cartdim / 8.0)));
+            if (cap >= 8) {
+                rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp, cap);
+                bool split = false;
+                for (const ChunkDesc & ch : hp.chunks) split = split || ch.accumulate;
+                if (rc == TCHEM_OK && !split && hp.cap <= cap) { t->group_warps = G; grouped = true; }
+            }
+        }
+    }
+    if (!grouped) rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp);
     if (rc != TCHEM_OK) return rc;
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     const size_t o_prims = 0;
@@ -78,6 +101,22 @@ int ensure_program(tchem_ic_table * t, int mode) {
     p.cap = hp.cap;
     p.intdim = t->intdim;
     p.cartdim = t->cartdim;
+    p.line_elems = 0;
+    if (mode == MODE_QJ && grouped) {
+        // multi-row chunks of the warp-group kernel: J pieces up to 1024 doubles go out through the
+        // per-warp line buffer (TCHEM_LINE=0 disables). One-row chunks gain nothing from it (measured).
+        static const int on = [] { const char * e = getenv("TCHEM_LINE"); return e ? atoi(e) : 1; }();
+        int widest = 0;
+        for (const ChunkDesc & ch : hp.chunks) widest = std::max(widest, ch.nrows * t->cartdim);
+        if (on && widest <= 1024) p.line_elems = (widest + 1) & ~1;
+    }
+    // small J-mode tables are staged per block in shared memory: under a saturated store stream the
+    // L2 latency of table reads is what the write-out waits for (TCHEM_STAGE_SPANS=0 disables)
+    {
+        static const int limit = [] { const char * e = getenv("TCHEM_STAGE_SPANS"); return e ? atoi(e) : 48 * 1024; }();
+        const size_t bytes = (o_runs + a16(hp.runs.size() * sizeof(ZeroRun))) - o_emap;
+        p.span_bytes = (mode != MODE_QJK && !grouped && bytes <= (size_t)limit) ? (int32_t)bytes : 0;
+    }
     t->dev_blob[mode] = dev;
     return TCHEM_OK;
 }

@@ -46,7 +46,7 @@ struct SpanDesc {
     int64_t map;                   // first ElemMap entry
     int32_t n;                     // number of ElemMap entries
     int32_t run0, nruns;           // zero runs in runs[]
-    int32_t pad_;
+    int32_t nnz;                   // the first nnz entries cover every sector that holds a non-zero element
 };
 
 struct ChunkDesc {
@@ -95,6 +95,8 @@ struct Program {                   // all pointers are device pointers
     int32_t nprims, nchunks;
     int32_t cap;                   // compact entries per lane
     int32_t intdim, cartdim;
+    int32_t line_elems;            // > 0: J spans are written through a per-warp line buffer of this many doubles
+    int32_t span_bytes;            // > 0: emap | psrcs | coefs | runs (contiguous from emap) are staged in shared memory
 };
 
 // compact entries of one primitive

@@ -4,6 +4,7 @@
 #include "ic_table.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -44,13 +45,20 @@ int coef_index(std::vector<double> & coefs, double value) {
 }
 }
 
+// shortest stretch of structural zeros written as a run (16-byte stores, no table lookups) instead of
+// element by element; TCHEM_MIN_ZERO_RUN overrides for experiments
+static int min_zero_run() {
+    static const int v = [] { const char * e = getenv("TCHEM_MIN_ZERO_RUN"); return e ? std::max(4, atoi(e)) : kMinZeroRun; }();
+    return v;
+}
+
 bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
                std::vector<ElemMap> & emap, std::vector<uint32_t> & psrcs, std::vector<double> & coefs,
                std::vector<ZeroRun> & runs, SpanDesc & span) {
     const int64_t S = (int64_t)lists.size();
     span.map = (int64_t)emap.size();
     span.run0 = (int32_t)runs.size();
-    span.pad_ = 0;
+    span.nnz = 0;
     const int64_t shift = (gstride % 4 == 0) ? (abs_off % 4) : 0;     // sector phase of element 0
     struct Unit { int64_t first, last; int maxcnt; };
     std::vector<Unit> units;
@@ -68,7 +76,7 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
         size_t v = u;
         while (v < units.size() && units[v].maxcnt == 0) v++;
         const int64_t len = units[v - 1].last - units[u].first;
-        if (len >= kMinZeroRun) {
+        if (len >= min_zero_run()) {
             runs.push_back(ZeroRun{(uint32_t)units[u].first, (uint32_t)len});
             for (size_t w = u; w < v; w++) in_run[w] = 1;
         }
@@ -80,7 +88,8 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
     // last round, keeping the address order otherwise
     auto klass = [](int m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m <= 4 ? 3 : 4 + (m - 1) / 4; };
     std::stable_sort(rest.begin(), rest.end(), [&](const Unit & a, const Unit & b) { return klass(a.maxcnt) > klass(b.maxcnt); });
-    for (const Unit & u : rest)
+    for (const Unit & u : rest) {
+        if (u.maxcnt > 0) span.nnz += (int32_t)(u.last - u.first);
         for (int64_t e = u.first; e < u.last; e++) {
             const auto & l = lists[e];
             if (l.size() > 255 || psrcs.size() / 4 + l.size() > kMapOffsetMask) return false;
@@ -95,13 +104,16 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
             }
             while (psrcs.size() % 4) psrcs.push_back(0u);       // the next element starts a new quad
         }
+    }
     span.n = (int32_t)(emap.size() - span.map);
     span.nruns = (int32_t)runs.size() - span.run0;
+    for (const Unit & u : rest)
+        if (u.maxcnt > 4) span.nnz = -1;          // (the line-buffer write-out holds <= 4 sources per element)
     return true;
 }
 
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
-                  HostProgram & hp) {
+                  HostProgram & hp, int cap_hint) {
     hp = HostProgram();
     // terms grouped by row, file order kept (source/IC/IntCoord.cpp:62-76 accumulates in order)
     std::vector<std::vector<int>> rows(n_ic);
@@ -132,6 +144,8 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
     }
     const int target = mode == MODE_QJK ? 160 : 64;
     hp.cap = std::max(max_prim, std::min(max_row, target));
+    if (cap_hint > 0) hp.cap = std::max(max_prim, cap_hint);
+    if (const char * e = getenv("TCHEM_CAP_MIN")) hp.cap = std::max(hp.cap, atoi(e));   // experiments
 
     // greedy chunking over rows; a row that does not fit by itself is split into several
     // single-row chunks, the later ones accumulating

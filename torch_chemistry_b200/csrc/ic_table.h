@@ -15,6 +15,11 @@ struct tchem_ic_table {
     std::vector<tchem_invdisp_t> terms;
     tchem_b200::Program prog[tchem_b200::MODE_COUNT];       // device pointers
     void * dev_blob[tchem_b200::MODE_COUNT] = {nullptr, nullptr, nullptr};
+    // launch shape of ic_eval_kernel per mode, resolved on first use (function attribute and
+    // occupancy queries cost microseconds each: too much for 10^4-geometry calls)
+    struct LaunchCfg { const void * fn = nullptr; int warps = 0, per_sm = 0; size_t smem = 0; };
+    int group_warps = 0;          // > 0: the q+J program was built for the warp-group kernel (G warps share a tile)
+    mutable LaunchCfg cfg[tchem_b200::MODE_COUNT];
     // host pipeline state for the *_host entry points (lazily created)
     struct HostPipe * pipe = nullptr;
 };
@@ -42,7 +47,8 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
                std::vector<ZeroRun> & runs, SpanDesc & span);
 
 // pure host: flatten terms into a program for one mode
+// cap_hint > 0: compact capacity to aim for (at least the largest primitive), 0: default policy
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
-                  HostProgram & out);
+                  HostProgram & out, int cap_hint = 0);
 
 } // namespace tchem_b200
