@@ -32,6 +32,25 @@ __global__ void k_rows(double * out, long ntiles, int gdoubles, int piece) {
         }
     }
 }
+// linear per tile with 32-byte stores (st.global.v4.f64, sm_100) and with streaming / write-through hints
+template <int KIND>
+__global__ void k_linear_x(double * out, long ntiles, long tile_doubles) {
+    const int lane = threadIdx.x & 31;
+    const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (long)gridDim.x * (blockDim.x >> 5);
+    for (long t = w; t < ntiles; t += nw) {
+        double * p = out + t * tile_doubles;
+        if (KIND == 0) {
+            for (long e = 4 * lane; e + 3 < tile_doubles; e += 128)
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p + e), "d"(0.0), "d"(1.0), "d"(2.0), "d"(3.0) : "memory");
+        } else if (KIND == 1) {
+            for (long e = 2 * lane; e + 1 < tile_doubles; e += 64) __stcs(reinterpret_cast<double2 *>(p + e), make_double2(0.0, 1.0));
+        } else if (KIND == 2) {
+            for (long e = 2 * lane; e + 1 < tile_doubles; e += 64) __stwt(reinterpret_cast<double2 *>(p + e), make_double2(0.0, 1.0));
+        } else {
+            for (long e = 2 * lane; e + 1 < tile_doubles; e += 64) __stcg(reinterpret_cast<double2 *>(p + e), make_double2(0.0, 1.0));
+        }
+    }
+}
 // rows pattern with 16-byte stores (lane = 2 adjacent elements)
 __global__ void k_rows16(double * out, long ntiles, int gdoubles, int piece) {
     const int lane = threadIdx.x & 31;
@@ -89,7 +108,13 @@ int main(int argc, char ** argv) {
     };
     run("cudaMemset", [&] { cudaMemsetAsync(out, 0, sizeof(double) * B * gdoubles); });
     run("linear per tile", [&] { k_linear<<<148, wps * 32>>>(out, ntiles, 32L * gdoubles); });
-    for (int rows : {1, 2, 4, 8, 16, intdim}) {
+    run("linear v4.f64 (32 B)", [&] { k_linear_x<0><<<148, wps * 32>>>(out, ntiles, 32L * gdoubles); });
+    run("linear .cs", [&] { k_linear_x<1><<<148, wps * 32>>>(out, ntiles, 32L * gdoubles); });
+    run("linear .wt", [&] { k_linear_x<2><<<148, wps * 32>>>(out, ntiles, 32L * gdoubles); });
+    run("linear .cg", [&] { k_linear_x<3><<<148, wps * 32>>>(out, ntiles, 32L * gdoubles); });
+    run("linear 2x148 blocks", [&] { k_linear<<<296, wps * 16>>>(out, ntiles, 32L * gdoubles); });
+    run("linear 1184 blocks x 64 thr", [&] { k_linear<<<1184, 64>>>(out, ntiles, 32L * gdoubles); });
+    for (int rows : {4, intdim}) {
         char name[64]; snprintf(name, 64, "rows=%d (piece %d B)", rows, rows * cartdim * 8);
         run(name, [&] { k_rows<<<148, wps * 32>>>(out, ntiles, gdoubles, rows * cartdim); });
     }

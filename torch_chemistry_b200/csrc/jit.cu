@@ -104,28 +104,29 @@ __device__ __forceinline__ void stage_finish(int ntile, double * R, int lane) {
 // adjacent elements per lane and 16-byte stores when the span, the stride and the pointer are even
 template <int SPAN, int GSTRIDE>
 __device__ __forceinline__ void copy_out(const double * D, double * __restrict__ out, int ntile, int lane) {
+    // geometry after geometry, lanes running over the (geometry, element pair) pairs: consecutive
+    // stores continue where the previous one ended. (Walking the 32 geometries element step by
+    // element step instead caps the HBM write stream: tools/micro/write_pattern.cu.)
     if (SPAN % 2 == 0 && GSTRIDE % 2 == 0 && (reinterpret_cast<uint64_t>(out) & 15) == 0) {
-        for (int k = 2 * lane; k < SPAN; k += 2 * LANES) {
-            const double * s0 = D + k * KPAD, * s1 = s0 + KPAD;
-            double * o = out + k;
-            if (ntile == LANES) {
-#pragma unroll 8
-                for (int g = 0; g < LANES; g++) *reinterpret_cast<double2 *>(o + (int64_t)g * GSTRIDE) = make_double2(s0[g], s1[g]);
-            } else {
-                for (int g = 0; g < ntile; g++) *reinterpret_cast<double2 *>(o + (int64_t)g * GSTRIDE) = make_double2(s0[g], s1[g]);
-            }
+        constexpr int PAIRS = SPAN / 2, DG = LANES / PAIRS, DP = LANES - DG * PAIRS;
+        const int total = ntile * PAIRS;
+        int g = lane / PAIRS, p = lane - g * PAIRS;
+#pragma unroll 4
+        for (int f = lane; f < total; f += LANES) {
+            const double * s0 = D + (2 * p) * KPAD + g;
+            *reinterpret_cast<double2 *>(out + (int64_t)g * GSTRIDE + 2 * p) = make_double2(s0[0], s0[KPAD]);
+            g += DG; p += DP;
+            if (p >= PAIRS) { p -= PAIRS; g++; }
         }
         return;
     }
-    for (int k = lane; k < SPAN; k += LANES) {
-        const double * src = D + k * KPAD;
-        double * o = out + k;
-        if (ntile == LANES) {
-#pragma unroll 8
-            for (int g = 0; g < LANES; g++) o[(int64_t)g * GSTRIDE] = src[g];
-        } else {
-            for (int g = 0; g < ntile; g++) o[(int64_t)g * GSTRIDE] = src[g];
-        }
+    constexpr int DG = LANES / SPAN, DK = LANES - DG * SPAN;
+    const int total = ntile * SPAN;
+    int g = lane / SPAN, k = lane - g * SPAN;
+    for (int f = lane; f < total; f += LANES) {
+        out[(int64_t)g * GSTRIDE + k] = D[k * KPAD + g];
+        g += DG; k += DK;
+        if (k >= SPAN) { k -= SPAN; g++; }
     }
 }
 // q rows of a chunk, (geometry, row)-flattened
