@@ -484,55 +484,62 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
 // consecutive 16-byte stores, geometry after geometry (measured ceiling of that pattern: 5.4-5.8 TB/s).
 // ---------------------------------------------------------------------------------------
 constexpr int kLineMaxNnz = 2 * kLanes;
+__device__ __forceinline__ bool line_eligible(const SpanDesc & sp) { return sp.nnz >= 0 && (sp.nnz & 0xffff) <= kLineMaxNnz; }
+template <int NS>
 struct LineSrc {
-    double c[4];
-    uint32_t p[4];                 // compact entry * kPad
-    int cnt;
+    double c[NS];
+    uint32_t p[NS];                // compact entry * kPad
     uint32_t k;
+    bool live;
 };
+template <int NS>
 __device__ __forceinline__ void line_sources(const ElemMap & m, bool live, const uint4 * __restrict__ psrcs,
-                                             const double * __restrict__ coefs, LineSrc & s) {
-    s.cnt = live ? (int)(m.word >> kMapCountShift) : 0;
+                                             const double * __restrict__ coefs, LineSrc<NS> & s) {
+    const int cnt = live ? (int)(m.word >> kMapCountShift) : 0;
     s.k = m.k;
+    s.live = live;
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (s.cnt) q = load_quad(psrcs + (m.word & kMapOffsetMask));
+    if (cnt) q = load_quad(psrcs + (m.word & kMapOffsetMask));
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < NS; j++) {
+        // an absent source reads entry 0 with coefficient 0: no predicate inside the geometry loop
         const uint32_t w = quad_get(q, j);
-        s.c[j] = j < s.cnt ? coefs[w >> 16] : 0.0;
-        s.p[j] = j < s.cnt ? (w & kSrcEntryMask) * kPad : 0u;
+        s.c[j] = j < cnt ? coefs[w >> 16] : 0.0;
+        s.p[j] = j < cnt ? (w & kSrcEntryMask) * kPad : 0u;
     }
 }
-template <bool FULL>
-__device__ __forceinline__ void gather_store_line(const SpanDesc & sp, const uint4 * __restrict__ psrcs,
-                                                  const double * __restrict__ coefs, const double * P, double * L, int E,
-                                                  double * out, int64_t gstride, int ntile, int lane, const SpanPrefetch & pf) {
-    const int Epad = (E + 1) & ~1;
+template <int NS>
+__device__ __forceinline__ double line_value(const LineSrc<NS> & s, const double * P, int g) {
+    double v = s.c[0] * P[s.p[0] + g];
+#pragma unroll
+    for (int j = 1; j < NS; j++) v = fma(s.c[j], P[s.p[j] + g], v);
+    return v;
+}
+template <bool FULL, int NS>
+__device__ __forceinline__ void gather_store_line_ns(const SpanDesc & sp, const uint4 * __restrict__ psrcs,
+                                                     const double * __restrict__ coefs, const double * P, double * L, int E,
+                                                     double * out, int64_t gstride, int ntile, int lane, const SpanPrefetch & pf) {
+    const int Epad = (E + 1) & ~1, nnz = sp.nnz & 0xffff;
     for (int e = 2 * lane; e < Epad; e += 2 * kLanes) *reinterpret_cast<double2 *>(L + e) = make_double2(0.0, 0.0);
-    LineSrc s0, s1;
-    const bool live0 = lane < sp.nnz, live1 = lane + kLanes < sp.nnz;
-    line_sources(pf.m1, live0, psrcs, coefs, s0);
-    line_sources(pf.m2, live1, psrcs, coefs, s1);
+    LineSrc<NS> s0, s1;
+    line_sources<NS>(pf.m1, lane < nnz, psrcs, coefs, s0);
+    line_sources<NS>(pf.m2, lane + kLanes < nnz, psrcs, coefs, s1);
+    const bool two = nnz > kLanes;                      // warp-uniform
     __syncwarp();
     const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((gstride & 1) == 0);
     const int n = FULL ? kLanes : ntile;
+    const int e0 = 2 * lane;
     for (int g = 0; g < n; g++) {
-        if (live0) {
-            double v = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < s0.cnt) v = fma(s0.c[j], P[s0.p[j] + g], v);
-            L[s0.k] = v;
-        }
-        if (live1) {
-            double v = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < s1.cnt) v = fma(s1.c[j], P[s1.p[j] + g], v);
-            L[s1.k] = v;
-        }
+        if (s0.live) L[s0.k] = line_value<NS>(s0, P, g);
+        if (two && s1.live) L[s1.k] = line_value<NS>(s1, P, g);
         __syncwarp();
         double * og = out + (int64_t)g * gstride;
         if (vec) {
-            for (int e = 2 * lane; e + 1 < E; e += 2 * kLanes)
+            // pieces up to 256 doubles: four independent 16-byte copies per lane, then the rest
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + 64 * u + 1 < E) *reinterpret_cast<double2 *>(og + e0 + 64 * u) = *reinterpret_cast<const double2 *>(L + e0 + 64 * u);
+            for (int e = e0 + 256; e + 1 < E; e += 2 * kLanes)
                 *reinterpret_cast<double2 *>(og + e) = *reinterpret_cast<const double2 *>(L + e);
             if ((E & 1) && lane == 0) og[E - 1] = L[E - 1];
         } else {
@@ -540,6 +547,17 @@ __device__ __forceinline__ void gather_store_line(const SpanDesc & sp, const uin
         }
         __syncwarp();
     }
+}
+// (out of line on purpose: at the call site only a few pointers are live, and inside the write-out gets
+// a register allocation of its own instead of competing with the primitive evaluation's)
+template <bool FULL>
+__device__ __noinline__ void gather_store_line(const SpanDesc & sp, const uint4 * __restrict__ psrcs,
+                                                  const double * __restrict__ coefs, const double * P, double * L, int E,
+                                                  double * out, int64_t gstride, int ntile, int lane, const SpanPrefetch & pf) {
+    const int maxcnt = sp.nnz >> 16;
+    if (maxcnt <= 1)      gather_store_line_ns<FULL, 1>(sp, psrcs, coefs, P, L, E, out, gstride, ntile, lane, pf);
+    else if (maxcnt == 2) gather_store_line_ns<FULL, 2>(sp, psrcs, coefs, P, L, E, out, gstride, ntile, lane, pf);
+    else                  gather_store_line_ns<FULL, 4>(sp, psrcs, coefs, P, L, E, out, gstride, ntile, lane, pf);
 }
 
 // `coefs` = the table of distinct coefficients (shared-memory copy when it is small)

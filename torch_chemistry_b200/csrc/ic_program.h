@@ -46,7 +46,8 @@ struct SpanDesc {
     int64_t map;                   // first ElemMap entry
     int32_t n;                     // number of ElemMap entries
     int32_t run0, nruns;           // zero runs in runs[]
-    int32_t nnz;                   // the first nnz entries cover every sector that holds a non-zero element
+    int32_t nnz;                   // low 16 bits: the first nnz entries cover every sector that holds a non-zero
+                                   // element; bits 16+: largest source count among them; -1: see emit_span
 };
 
 struct ChunkDesc {

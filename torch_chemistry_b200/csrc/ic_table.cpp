@@ -107,8 +107,11 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
     }
     span.n = (int32_t)(emap.size() - span.map);
     span.nruns = (int32_t)runs.size() - span.run0;
-    for (const Unit & u : rest)
-        if (u.maxcnt > 4) span.nnz = -1;          // (the line-buffer write-out holds <= 4 sources per element)
+    // line-buffer write-out: <= 64 such elements with <= 4 sources each; the largest source count
+    // rides in bits 16+ (picks the unrolled gather), -1 = not eligible
+    int maxcnt = 0;
+    for (const Unit & u : rest) maxcnt = std::max(maxcnt, u.maxcnt);
+    span.nnz = (maxcnt > 4 || span.nnz > 0xffff) ? -1 : (span.nnz | (maxcnt << 16));
     return true;
 }
 
