@@ -352,6 +352,30 @@ def test_specialised_kernel_matches_interpreter_and_oracle(T):
         assert n % 32 != 0
 
 
+def test_mid_size_odd_stride_chain13(T):
+    """13-atom chain with out-of-plane rows: cartdim 39, 33 coordinates -> the J block of a geometry is
+    1287 doubles (odd), so every other geometry is only 8-byte aligned: the warp-group kernel's line
+    write-out must take its 8-byte path. Ragged batch, J-only and q-only calls, against the oracle."""
+    w = T.workloads.chain(13, "chain13_oop", seed=9, oop_variant=True)
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=13)
+    assert (s.intdim * s.cartdim) % 2 == 1
+    orc = O.IntCoordSet("default", w.ic_text)
+    n = 613
+    r = w.geometries(n, seed=123)
+    q, J = s.compute_IC_J(dev(r))
+    qo, Jo = orc.qJ(r)
+    assert_q_parity(host(q), qo, orc.terms(), r, "chain13 q")
+    assert_parity(host(J), Jo, "chain13 J")
+    # outputs at an odd element offset inside a larger allocation (8-byte aligned only)
+    big = torch.zeros(n * s.intdim * s.cartdim + 1, dtype=torch.float64, device="cuda")
+    Jv = big[1:].view(n, s.intdim, s.cartdim)
+    qv = torch.empty(n, s.intdim, dtype=torch.float64, device="cuda")
+    s.compute_IC_J(dev(r), out=(qv, Jv))
+    np.testing.assert_array_equal(host(Jv), host(J))
+    np.testing.assert_array_equal(host(qv), host(q))
+    assert float(big[0]) == 0.0
+
+
 @pytest.mark.parametrize("env", [{"TCHEM_GROUP_G": "0"}, {"TCHEM_GROUP_G": "2"}, {"TCHEM_GROUP_G": "4"},
                                  {"TCHEM_GROUP_G": "6", "TCHEM_LINE": "0"}, {"TCHEM_STAGE_SPANS": "0", "TCHEM_GROUP_G": "0"}])
 def test_warp_group_kernel_variants(T, env):
