@@ -5,6 +5,8 @@
 // lane forms the weight  W_p = sum over the terms that use p of coeff * g_q[ic]  and adds
 // W_p * J_p (<= 15 entries, in registers) into its own column of a shared-memory g_r tile,
 // which is then written out transposed (coalesced).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -22,6 +24,15 @@ struct GradProgram {
     const int32_t *  use_ptr;     // CSR over prims
     const GradUse *  uses;
     int32_t nprims, intdim, cartdim;
+    // warp-per-geometry flavour: primitives sorted by type, every type padded to a multiple of 32 with
+    // dummies (natoms = 0), pd.out = first slot of the primitive's weighted J in the per-warp buffer;
+    // comp_ptr / comp_idx: for every Cartesian component the slots that add up to it
+    const PrimDesc * wprims;
+    const int32_t *  wuse_ptr;
+    const GradUse *  wuses;
+    const int32_t *  comp_ptr;
+    const int32_t *  comp_idx;
+    int32_t nwprims, nslots, ncomp_idx, nwuses;
 };
 
 namespace {
@@ -78,6 +89,81 @@ grad_int2cart_kernel(const GradProgram gp, const double * __restrict__ r, const 
         double * out = gr + b0 * cartdim;
         for (int k = lane; k < cartdim; k += kLanes)
             for (int g = 0; g < ntile; g++) out[(int64_t)g * cartdim + k] = G[k * kPad + g];
+        __syncwarp();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Warp-per-geometry flavour: lane = primitive. The lane-per-geometry kernel above needs
+// (2 cartdim + intdim) * 264 bytes of shared memory per warp - 70 KB for a 30-atom molecule, two or
+// three warps per SM - while the arithmetic per geometry is the same either way. Here a warp owns one
+// geometry at a time: its lanes evaluate 32 primitives of the same type at once (tables sorted by
+// type and padded), park W_p * J_p in a per-warp slot buffer (a few KB), and the Cartesian components
+// are then gathered from the slots that contribute to them - no atomics, fixed summation order.
+// ---------------------------------------------------------------------------------------
+struct SlotSink {
+    double * S;      // first slot of this primitive
+    double W;
+    __device__ __forceinline__ void value(double) const {}
+    __device__ __forceinline__ void jac_block(const int *, int i, const V3<double> & J) const {
+        S[3 * i] = W * J.x; S[3 * i + 1] = W * J.y; S[3 * i + 2] = W * J.z;
+    }
+    __device__ __forceinline__ void jac_entry(const int *, int m, double j) const { S[m] = W * j; }
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int, int, const V3<Dual> &) const {}
+    __device__ __forceinline__ void hess_entry5(const int *, int, int, double) const {}
+};
+
+template <bool HAS5>
+__global__ void __launch_bounds__(128, 3)
+grad_int2cart_warp_kernel(const GradProgram gp, const double * __restrict__ r, const double * __restrict__ gq,
+                          const int64_t B, double * __restrict__ gr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    // per block: the tables
+    PrimDesc * prims = reinterpret_cast<PrimDesc *>(smem_raw);
+    size_t off = a16(sizeof(PrimDesc) * gp.nwprims);
+    int32_t * use_ptr = reinterpret_cast<int32_t *>(smem_raw + off);  off += a16(4 * (gp.nwprims + 1));
+    GradUse * uses = reinterpret_cast<GradUse *>(smem_raw + off);     off += a16(sizeof(GradUse) * gp.nwuses);
+    int32_t * comp_ptr = reinterpret_cast<int32_t *>(smem_raw + off); off += a16(4 * (gp.cartdim + 1));
+    int32_t * comp_idx = reinterpret_cast<int32_t *>(smem_raw + off); off += a16(4 * gp.ncomp_idx);
+    {
+        auto copy4 = [&](const void * src, void * dst, int n4) {
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<int32_t *>(dst)[i] = reinterpret_cast<const int32_t *>(src)[i];
+        };
+        copy4(gp.wprims, prims, gp.nwprims * (int)(sizeof(PrimDesc) / 4));
+        copy4(gp.wuse_ptr, use_ptr, gp.nwprims + 1);
+        copy4(gp.wuses, uses, gp.nwuses * (int)(sizeof(GradUse) / 4));
+        copy4(gp.comp_ptr, comp_ptr, gp.cartdim + 1);
+        copy4(gp.comp_idx, comp_idx, gp.ncomp_idx);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cartdim = gp.cartdim, intdim = gp.intdim;
+    const size_t per_warp = (size_t)((cartdim + intdim + gp.nslots + 1) & ~1);
+    double * rs = reinterpret_cast<double *>(smem_raw + off) + (size_t)warp * per_warp;
+    double * qs = rs + cartdim;
+    double * S = qs + intdim;
+    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+        for (int k = lane; k < cartdim; k += kLanes) rs[k] = r[b * cartdim + k];
+        for (int k = lane; k < intdim; k += kLanes) qs[k] = gq[b * intdim + k];
+        __syncwarp();
+        for (int p = lane; p < gp.nwprims; p += kLanes) {
+            const PrimDesc pd = prims[p];
+            if (pd.natoms == 0) continue;                  // padding / dummy
+            double W = 0.0;
+            for (int u = use_ptr[p]; u < use_ptr[p + 1]; u++) W = fma(uses[u].coef, qs[uses[u].ic], W);
+            SlotSink sink;
+            sink.S = S + pd.out;
+            sink.W = W;
+            eval_primitive<MODE_QJ, HAS5>(pd, GeomLoader{rs}, sink);
+        }
+        __syncwarp();
+        for (int c = lane; c < cartdim; c += kLanes) {
+            double s = 0.0;
+            for (int k = comp_ptr[c]; k < comp_ptr[c + 1]; k++) s += S[comp_idx[k]];
+            gr[b * cartdim + c] = s;
+        }
         __syncwarp();
     }
 }
@@ -140,13 +226,47 @@ static int get_grad_program(const tchem_ic_table * t, GradProgram & out) {
     std::vector<int32_t> ptr(1, 0);
     std::vector<GradUse> flat;
     for (auto & u : uses) { flat.insert(flat.end(), u.begin(), u.end()); ptr.push_back((int32_t)flat.size()); }
+    // warp-per-geometry tables: by type, every type padded to whole warps; slot strides odd (bank spread)
+    std::vector<int> order(prims.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prims[a].type < prims[b].type; });
+    std::vector<PrimDesc> wprims;
+    std::vector<int32_t> wptr(1, 0);
+    std::vector<GradUse> wflat;
+    std::vector<std::vector<int32_t>> comp(t->cartdim);
+    int nslots = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+        const int id = order[k];
+        if (k > 0 && prims[order[k - 1]].type != prims[id].type)
+            while (wprims.size() % 32) { PrimDesc pad; std::memset(&pad, 0, sizeof(pad)); wprims.push_back(pad); wptr.push_back((int32_t)wflat.size()); }
+        PrimDesc pd = prims[id];
+        pd.out = nslots;
+        for (int i = 0; i < pd.natoms; i++)
+            for (int c = 0; c < 3; c++) comp[3 * pd.atoms[i] + c].push_back(nslots + 3 * i + c);
+        nslots += (3 * pd.natoms) | 1;
+        wprims.push_back(pd);
+        wflat.insert(wflat.end(), uses[id].begin(), uses[id].end());
+        wptr.push_back((int32_t)wflat.size());
+    }
+    std::vector<int32_t> comp_ptr(1, 0), comp_idx;
+    for (auto & c : comp) { comp_idx.insert(comp_idx.end(), c.begin(), c.end()); comp_ptr.push_back((int32_t)comp_idx.size()); }
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     const size_t o_p = 0, o_ptr = a16(prims.size() * sizeof(PrimDesc)), o_u = o_ptr + a16(ptr.size() * 4);
-    const size_t total = o_u + a16(flat.size() * sizeof(GradUse)) + 16;
+    const size_t o_wp = o_u + a16(flat.size() * sizeof(GradUse));
+    const size_t o_wptr = o_wp + a16(wprims.size() * sizeof(PrimDesc));
+    const size_t o_wu = o_wptr + a16(wptr.size() * 4);
+    const size_t o_cp = o_wu + a16(wflat.size() * sizeof(GradUse));
+    const size_t o_ci = o_cp + a16(comp_ptr.size() * 4);
+    const size_t total = o_ci + a16(comp_idx.size() * 4) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_p, prims.data(), prims.size() * sizeof(PrimDesc));
     std::memcpy(blob.data() + o_ptr, ptr.data(), ptr.size() * 4);
     std::memcpy(blob.data() + o_u, flat.data(), flat.size() * sizeof(GradUse));
+    std::memcpy(blob.data() + o_wp, wprims.data(), wprims.size() * sizeof(PrimDesc));
+    std::memcpy(blob.data() + o_wptr, wptr.data(), wptr.size() * 4);
+    std::memcpy(blob.data() + o_wu, wflat.data(), wflat.size() * sizeof(GradUse));
+    std::memcpy(blob.data() + o_cp, comp_ptr.data(), comp_ptr.size() * 4);
+    std::memcpy(blob.data() + o_ci, comp_idx.data(), comp_idx.size() * 4);
     void * dev = nullptr;
     TC_CUDA(cudaMalloc(&dev, total));
     cudaError_t e = cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice);
@@ -160,6 +280,15 @@ static int get_grad_program(const tchem_ic_table * t, GradProgram & out) {
     gt.prog.nprims = (int)prims.size();
     gt.prog.intdim = t->intdim;
     gt.prog.cartdim = t->cartdim;
+    gt.prog.wprims = reinterpret_cast<const PrimDesc *>(d + o_wp);
+    gt.prog.wuse_ptr = reinterpret_cast<const int32_t *>(d + o_wptr);
+    gt.prog.wuses = reinterpret_cast<const GradUse *>(d + o_wu);
+    gt.prog.comp_ptr = reinterpret_cast<const int32_t *>(d + o_cp);
+    gt.prog.comp_idx = reinterpret_cast<const int32_t *>(d + o_ci);
+    gt.prog.nwprims = (int)wprims.size();
+    gt.prog.nslots = nslots;
+    gt.prog.ncomp_idx = (int)comp_idx.size();
+    gt.prog.nwuses = (int)wflat.size();
     grad_tables()[t] = gt;
     out = gt.prog;
     return TCHEM_OK;
@@ -180,11 +309,35 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
     GradProgram gp;
     int rc = get_grad_program(t, gp);
     if (rc != TCHEM_OK) return rc;
+    {
+        // warp-per-geometry kernel whenever its tables and slot buffers fit (TCHEM_GRAD_TILE=1 forces
+        // the lane-per-geometry kernel)
+        static const bool force_tile = [] { const char * e = getenv("TCHEM_GRAD_TILE"); return e && atoi(e) != 0; }();
+        auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+        const size_t tb = a16(sizeof(PrimDesc) * gp.nwprims) + a16(4 * (gp.nwprims + 1)) + a16(sizeof(GradUse) * gp.nwuses)
+                        + a16(4 * (gp.cartdim + 1)) + a16(4 * gp.ncomp_idx);
+        const size_t pw = (size_t)((gp.cartdim + gp.intdim + gp.nslots + 1) & ~1) * sizeof(double);
+        const int wwarps = 4;
+        const size_t wsmem = tb + wwarps * pw;
+        if (!force_tile && wsmem <= (size_t)t->max_smem_optin / 2) {
+            const void * wfn = t->has5 ? reinterpret_cast<const void *>(&grad_int2cart_warp_kernel<true>)
+                                       : reinterpret_cast<const void *>(&grad_int2cart_warp_kernel<false>);
+            TC_CUDA(cudaFuncSetAttribute(wfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            int per_sm = 0;
+            TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfn, wwarps * 32, wsmem));
+            if (per_sm < 1) per_sm = 1;
+            const int64_t grid = std::min<int64_t>((B + wwarps - 1) / wwarps, (int64_t)t->sm_count * per_sm);
+            void * args[] = {(void *)&gp, (void *)&r, (void *)&intgrad, (void *)&B, (void *)&cartgrad};
+            TC_CUDA(cudaLaunchKernel(wfn, dim3((unsigned)grid), dim3(wwarps * 32), args, wsmem, static_cast<cudaStream_t>(stream)));
+            count_launch();
+            return TCHEM_OK;
+        }
+    }
     const void * fn = t->has5 ? reinterpret_cast<const void *>(&grad_int2cart_kernel<true>)
                               : reinterpret_cast<const void *>(&grad_int2cart_kernel<false>);
     const size_t wb = (size_t)(2 * t->cartdim + t->intdim) * kPad * sizeof(double);
     int warps = 4;
-    while (warps > 1 && warps * wb > (size_t)t->max_smem_optin) warps >>= 1;
+    while (warps > 1 && warps * wb > (size_t)t->max_smem_optin) warps--;
     const size_t smem = warps * wb;
     if (smem > (size_t)t->max_smem_optin)
         return set_error(TCHEM_EINVAL, "tchem::IC::IntCoordSet::gradient_int2cart: molecule too large for the shared-memory tile");
