@@ -42,12 +42,17 @@ int ensure_program(tchem_ic_table * t, int mode) {
         const int G = (g_env == 2 || g_env == 4 || g_env == 6) ? g_env : 0;
         if (G) {
             const int ngroups = 12 / G;
-            // per group: cartdim coordinate rows + per warp `cap` compact rows (kPad doubles each) and a
-            // line buffer of rows_per_chunk * cartdim <= cap / 8 * cartdim doubles
+            // per group: cartdim coordinate rows; per warp `cap` compact rows (kPad doubles each) and two
+            // line buffers of max_rows * cartdim doubles (TCHEM_GROUP_ROWS overrides max_rows)
+            // (measured: 4-row pieces for the 20-atom workload, 2-row pieces for the 30-atom one, where
+            // four-row line buffers would eat the compact capacity; 3 fights the 4-row chunk alignment)
+            static const int rows_env = [] { const char * e = getenv("TCHEM_GROUP_ROWS"); return e ? atoi(e) : 0; }();
+            const int max_rows = rows_env > 0 ? rows_env : (t->cartdim <= 72 ? 4 : 2);
             const int group_doubles = ((t->max_smem_sm - 1024 - 12 * 1024) / ngroups) / (int)sizeof(double);
-            const int cap = (int)((group_doubles - t->cartdim * kPad) / (G * (kPad + t->cartdim / 8.0)));
+            const int line = 2 * ((max_rows * t->cartdim + 1) & ~1);
+            const int cap = (group_doubles - t->cartdim * kPad - G * line) / (G * kPad);
             if (cap >= 8) {
-                rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp, cap);
+                rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp, cap, max_rows);
                 bool split = false;
                 for (const ChunkDesc & ch : hp.chunks) split = split || ch.accumulate;
                 if (rc == TCHEM_OK && !split && hp.cap <= cap) { t->group_warps = G; grouped = true; }
@@ -108,7 +113,7 @@ int ensure_program(tchem_ic_table * t, int mode) {
         static const int on = [] { const char * e = getenv("TCHEM_LINE"); return e ? atoi(e) : 1; }();
         int widest = 0;
         for (const ChunkDesc & ch : hp.chunks) widest = std::max(widest, ch.nrows * t->cartdim);
-        if (on && widest <= 1024) p.line_elems = (widest + 1) & ~1;
+        if (on && widest <= 1024) p.line_elems = 2 * ((widest + 1) & ~1);      // two buffers (double-buffered write-out)
     }
     // small J-mode tables are staged per block in shared memory: under a saturated store stream the
     // L2 latency of table reads is what the write-out waits for (TCHEM_STAGE_SPANS=0 disables)

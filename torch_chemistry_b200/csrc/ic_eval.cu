@@ -110,7 +110,7 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         if (MODE != MODE_VALUE && J != nullptr) {
             double * Jc = J + b0 * jstride + (int64_t)ch.row0 * cartdim;
             const int E = ch.nrows * cartdim;
-            if (MODE == MODE_QJ && prog.line_elems >= E && !ch.accumulate && line_eligible(ch.jspan)) {
+            if (MODE == MODE_QJ && prog.line_elems >= 2 * ((E + 1) & ~1) && !ch.accumulate && line_eligible(ch.jspan)) {
                 if (ntile == kLanes) gather_store_line<true>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
                 else                 gather_store_line<false>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
             } else {
@@ -208,7 +208,7 @@ ic_eval_group_kernel(const Program prog, const double * __restrict__ r, const in
             if (J != nullptr) {
                 double * Jc = J + b0 * jstride + (int64_t)ch.row0 * cartdim;
                 const int E = ch.nrows * cartdim;
-                if (prog.line_elems >= E && line_eligible(ch.jspan)) {
+                if (prog.line_elems >= 2 * ((E + 1) & ~1) && line_eligible(ch.jspan)) {
                     if (ntile == kLanes) gather_store_line<true>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
                     else                 gather_store_line<false>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
                 } else {

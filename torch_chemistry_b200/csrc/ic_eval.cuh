@@ -520,33 +520,43 @@ __device__ __forceinline__ void gather_store_line_ns(const SpanDesc & sp, const 
                                                      const double * __restrict__ coefs, const double * P, double * L, int E,
                                                      double * out, int64_t gstride, int ntile, int lane, const SpanPrefetch & pf) {
     const int Epad = (E + 1) & ~1, nnz = sp.nnz & 0xffff;
-    for (int e = 2 * lane; e < Epad; e += 2 * kLanes) *reinterpret_cast<double2 *>(L + e) = make_double2(0.0, 0.0);
+    // two line buffers: while geometry g streams out of one, the values of g + 1 are gathered into
+    // the other (one warp barrier per geometry, the loads of the next step already in flight)
+    double * L1 = L + Epad;
+    for (int e = 2 * lane; e < 2 * Epad; e += 2 * kLanes) *reinterpret_cast<double2 *>(L + e) = make_double2(0.0, 0.0);
     LineSrc<NS> s0, s1;
     line_sources<NS>(pf.m1, lane < nnz, psrcs, coefs, s0);
     line_sources<NS>(pf.m2, lane + kLanes < nnz, psrcs, coefs, s1);
     const bool two = nnz > kLanes;                      // warp-uniform
-    __syncwarp();
     const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((gstride & 1) == 0);
     const int n = FULL ? kLanes : ntile;
     const int e0 = 2 * lane;
+    double v0 = s0.live ? line_value<NS>(s0, P, 0) : 0.0;
+    double v1 = (two && s1.live) ? line_value<NS>(s1, P, 0) : 0.0;
+    __syncwarp();
     for (int g = 0; g < n; g++) {
-        if (s0.live) L[s0.k] = line_value<NS>(s0, P, g);
-        if (two && s1.live) L[s1.k] = line_value<NS>(s1, P, g);
+        double * Lg = (g & 1) ? L1 : L;
+        if (s0.live) Lg[s0.k] = v0;
+        if (two && s1.live) Lg[s1.k] = v1;
+        if (g + 1 < n) {
+            if (s0.live) v0 = line_value<NS>(s0, P, g + 1);
+            if (two && s1.live) v1 = line_value<NS>(s1, P, g + 1);
+        }
         __syncwarp();
         double * og = out + (int64_t)g * gstride;
         if (vec) {
             // pieces up to 256 doubles: four independent 16-byte copies per lane, then the rest
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (e0 + 64 * u + 1 < E) *reinterpret_cast<double2 *>(og + e0 + 64 * u) = *reinterpret_cast<const double2 *>(L + e0 + 64 * u);
+                if (e0 + 64 * u + 1 < E) *reinterpret_cast<double2 *>(og + e0 + 64 * u) = *reinterpret_cast<const double2 *>(Lg + e0 + 64 * u);
             for (int e = e0 + 256; e + 1 < E; e += 2 * kLanes)
-                *reinterpret_cast<double2 *>(og + e) = *reinterpret_cast<const double2 *>(L + e);
-            if ((E & 1) && lane == 0) og[E - 1] = L[E - 1];
+                *reinterpret_cast<double2 *>(og + e) = *reinterpret_cast<const double2 *>(Lg + e);
+            if ((E & 1) && lane == 0) og[E - 1] = Lg[E - 1];
         } else {
-            for (int e = lane; e < E; e += kLanes) og[e] = L[e];
+            for (int e = lane; e < E; e += kLanes) og[e] = Lg[e];
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 // (out of line on purpose: at the call site only a few pointers are live, and inside the write-out gets
 // a register allocation of its own instead of competing with the primitive evaluation's)

@@ -116,7 +116,7 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
 }
 
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
-                  HostProgram & hp, int cap_hint) {
+                  HostProgram & hp, int cap_hint, int max_rows) {
     hp = HostProgram();
     // terms grouped by row, file order kept (source/IC/IntCoord.cpp:62-76 accumulates in order)
     std::vector<std::vector<int>> rows(n_ic);
@@ -174,7 +174,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
         auto aligned = [&](int e) { return e == n_ic || e % 4 == 0; };
         for (int i = 0; i < n_ic; ) {
             int e_max = i;
-            while (e_max < n_ic && entries_of(i, e_max + 1) <= hp.cap) e_max++;
+            while (e_max < n_ic && (max_rows <= 0 || e_max - i < max_rows) && entries_of(i, e_max + 1) <= hp.cap) e_max++;
             if (e_max > i) {
                 int e = e_max;
                 while (e > i && !aligned(e)) e--;

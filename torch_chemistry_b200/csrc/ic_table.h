@@ -47,8 +47,9 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
                std::vector<ZeroRun> & runs, SpanDesc & span);
 
 // pure host: flatten terms into a program for one mode
-// cap_hint > 0: compact capacity to aim for (at least the largest primitive), 0: default policy
+// cap_hint > 0: compact capacity to aim for (at least the largest primitive), 0: default policy;
+// max_rows > 0: at most that many rows per chunk
 int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int mode,
-                  HostProgram & out, int cap_hint = 0);
+                  HostProgram & out, int cap_hint = 0, int max_rows = 0);
 
 } // namespace tchem_b200
