@@ -43,20 +43,34 @@ int ensure_program(tchem_ic_table * t, int mode) {
         if (G) {
             const int ngroups = 12 / G;
             // per group: cartdim coordinate rows; per warp `cap` compact rows (kPad doubles each) and two
-            // line buffers of max_rows * cartdim doubles (TCHEM_GROUP_ROWS overrides max_rows)
-            // (measured: 4-row pieces for the 20-atom workload, 2-row pieces for the 30-atom one, where
-            // four-row line buffers would eat the compact capacity; 3 fights the 4-row chunk alignment)
+            // line buffers of max_rows * cartdim doubles. Rows per chunk: 2, 3 or 4, whichever gives the
+            // cheapest schedule - the group's warps take chunks round-robin, a round lasts as long as
+            // its most expensive chunk (arithmetic ~ compact entries, write-out ~ 0.15 per element:
+            // ratio read off the 20-atom profile). TCHEM_GROUP_ROWS forces a value.
             static const int rows_env = [] { const char * e = getenv("TCHEM_GROUP_ROWS"); return e ? atoi(e) : 0; }();
-            const int max_rows = rows_env > 0 ? rows_env : (t->cartdim <= 72 ? 4 : 2);
             const int group_doubles = ((t->max_smem_sm - 1024 - 12 * 1024) / ngroups) / (int)sizeof(double);
-            const int line = 2 * ((max_rows * t->cartdim + 1) & ~1);
-            const int cap = (group_doubles - t->cartdim * kPad - G * line) / (G * kPad);
-            if (cap >= 8) {
-                rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp, cap, max_rows);
+            double best_cost = 0.0;
+            for (int max_rows = 2; max_rows <= 4; max_rows++) {
+                if (rows_env > 0 && max_rows != std::min(std::max(rows_env, 2), 4)) continue;
+                const int line = 2 * ((max_rows * t->cartdim + 1) & ~1);
+                const int cap = (group_doubles - t->cartdim * kPad - G * line) / (G * kPad);
+                if (cap < 8) continue;
+                HostProgram cand;
+                if (build_program(t->terms, t->intdim, t->cartdim, mode, cand, cap, max_rows) != TCHEM_OK || cand.cap > cap) continue;
                 bool split = false;
-                for (const ChunkDesc & ch : hp.chunks) split = split || ch.accumulate;
-                if (rc == TCHEM_OK && !split && hp.cap <= cap) { t->group_warps = G; grouped = true; }
+                for (const ChunkDesc & ch : cand.chunks) split = split || ch.accumulate;
+                if (split) continue;
+                double cost = 0.0, round_max = 0.0;
+                for (size_t c = 0; c < cand.chunks.size(); c++) {
+                    const ChunkDesc & ch = cand.chunks[c];
+                    int entries = ch.nrows;
+                    for (int k = ch.prim_begin; k < ch.prim_end; k++) entries += prim_entries(cand.prims[k].natoms, mode);
+                    round_max = std::max(round_max, entries + 0.15 * ch.nrows * t->cartdim);
+                    if (c % G == (size_t)G - 1 || c + 1 == cand.chunks.size()) { cost += round_max; round_max = 0.0; }
+                }
+                if (!grouped || cost < best_cost) { hp = cand; best_cost = cost; grouped = true; }
             }
+            if (grouped) t->group_warps = G;
         }
     }
     if (!grouped) rc = build_program(t->terms, t->intdim, t->cartdim, mode, hp);

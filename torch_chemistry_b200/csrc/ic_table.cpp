@@ -171,7 +171,9 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
         };
         // a chunk that ends inside a 32-byte sector of q (4 rows) or of J leaves that sector half
         // written; the partial write costs a DRAM read-modify-write.  Prefer ends on 4-row boundaries.
-        auto aligned = [&](int e) { return e == n_ic || e % 4 == 0; };
+        // (programs with a fixed row count per chunk - the warp-group kernel's - keep that count: an
+        // even spread of the chunks over the group's warps matters more than the q sectors)
+        auto aligned = [&](int e) { return max_rows > 0 || e == n_ic || e % 4 == 0; };
         for (int i = 0; i < n_ic; ) {
             int e_max = i;
             while (e_max < n_ic && (max_rows <= 0 || e_max - i < max_rows) && entries_of(i, e_max + 1) <= hp.cap) e_max++;
