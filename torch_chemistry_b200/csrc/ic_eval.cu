@@ -284,9 +284,13 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
         const void * fn = nullptr;
         int warps = 0;
         if (mode == MODE_QJK) {
-            warps = 2;
+            // q+J+K: 255 registers; 3 warps per block measured marginally best on the 20-atom workload
+            // (2 x 2 warps: 0.78, 3: 0.80, 4: 0.79 of the HBM roofline; TCHEM_K_WARPS overrides)
+            static const int k_env = [] { const char * e = getenv("TCHEM_K_WARPS"); return e ? atoi(e) : 3; }();
+            warps = std::min(std::max(k_env, 1), 4);
             while (warps > 1 && tb + warps * wb > (size_t)t->max_smem_optin) warps--;
-            fn = has5 ? kernel_ptr<MODE_QJK, true, 2, 1>() : kernel_ptr<MODE_QJK, false, 2, 1>();
+            fn = warps > 2 ? (has5 ? kernel_ptr<MODE_QJK, true, 4, 1>() : kernel_ptr<MODE_QJK, false, 4, 1>())
+                           : (has5 ? kernel_ptr<MODE_QJK, true, 2, 1>() : kernel_ptr<MODE_QJK, false, 2, 1>());
         } else {
             struct Shape { int nw, nb; const void * fn; };
             const Shape shapes[3] = {
