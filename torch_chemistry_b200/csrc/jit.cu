@@ -65,6 +65,9 @@ struct Nvrtc {
 };
 Nvrtc & nvrtc() { static Nvrtc n; return n; }
 
+// staging row of element e of a span (mirrors staged_row<SPAN> in the prelude)
+int stage_row(int e, int span) { return span % 2 == 0 ? (e >> 1) + (e & 1) * (span / 2) : e; }
+
 std::string hexd(double v) {
     char buf[64];
     std::snprintf(buf, sizeof(buf), "%a", v);
@@ -102,6 +105,12 @@ __device__ __forceinline__ void stage_finish(int ntile, double * R, int lane) {
 }
 // staged [span][lane] -> out[(b0 + g) * gstride + k]: lanes along k, coalesced segments; two
 // adjacent elements per lane and 16-byte stores when the span, the stride and the pointer are even
+// Row of element e in the staging buffer: when the span is even, elements (2p, 2p+1) - one 16-byte
+// store - sit in rows p and p + SPAN/2, so that the lanes of a store read rows one apart (stride 33
+// doubles, conflict-free) instead of two apart (2-way bank conflicts). The generator stages with
+// the same permutation (stage_row in jit.cu).
+template <int SPAN>
+__device__ __forceinline__ constexpr int staged_row(int e) { return SPAN % 2 == 0 ? (e >> 1) + (e & 1) * (SPAN / 2) : e; }
 template <int SPAN, int GSTRIDE>
 __device__ __forceinline__ void copy_out(const double * D, double * __restrict__ out, int ntile, int lane) {
     // geometry after geometry, lanes running over the (geometry, element pair) pairs: consecutive
@@ -113,8 +122,8 @@ __device__ __forceinline__ void copy_out(const double * D, double * __restrict__
         int g = lane / PAIRS, p = lane - g * PAIRS;
 #pragma unroll 4
         for (int f = lane; f < total; f += LANES) {
-            const double * s0 = D + (2 * p) * KPAD + g;
-            *reinterpret_cast<double2 *>(out + (int64_t)g * GSTRIDE + 2 * p) = make_double2(s0[0], s0[KPAD]);
+            const double * s0 = D + p * KPAD + g;
+            *reinterpret_cast<double2 *>(out + (int64_t)g * GSTRIDE + 2 * p) = make_double2(s0[0], s0[PAIRS * KPAD]);
             g += DG; p += DP;
             if (p >= PAIRS) { p -= PAIRS; g++; }
         }
@@ -124,7 +133,7 @@ __device__ __forceinline__ void copy_out(const double * D, double * __restrict__
     const int total = ntile * SPAN;
     int g = lane / SPAN, k = lane - g * SPAN;
     for (int f = lane; f < total; f += LANES) {
-        out[(int64_t)g * GSTRIDE + k] = D[k * KPAD + g];
+        out[(int64_t)g * GSTRIDE + k] = D[staged_row<SPAN>(k) * KPAD + g];
         g += DG; k += DK;
         if (k >= SPAN) { k -= SPAN; g++; }
     }
@@ -292,7 +301,7 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
                 g[u.first] = e;
             }
             for (int c = 0; c < sd; c++)
-                o << "            D[" << n + (t - t0) * sd + c << " * KPAD + lane] = " << g[c] << ";\n";
+                o << "            D[" << n + stage_row((t - t0) * sd + c, n * sd) << " * KPAD + lane] = " << g[c] << ";\n";
         }
         o << "            __syncwarp();\n"
           << "            if (y) copy_rows<" << n << ", NT>(D, y + b0 * NT + " << t0 << ", ntile, lane);\n"
@@ -403,7 +412,7 @@ std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int
                     }
             }
             for (int c = 0; c < cartdim; c++)
-                o << "            D[" << (i - r0) * cartdim + c << " * KPAD + lane] = " << (expr[c].empty() ? "0.0" : expr[c]) << ";\n";
+                o << "            D[" << stage_row((i - r0) * cartdim + c, nrows * cartdim) << " * KPAD + lane] = " << (expr[c].empty() ? "0.0" : expr[c]) << ";\n";
             std::string qe;
             for (auto & t : rows[i]) {
                 const std::string term = hexd(t.first) + " * q" + std::to_string(t.second);
