@@ -144,9 +144,42 @@ grad_int2cart_warp_kernel(const GradProgram gp, const double * __restrict__ r, c
     double * rs = reinterpret_cast<double *>(smem_raw + off) + (size_t)warp * per_warp;
     double * qs = rs + cartdim;
     double * S = qs + intdim;
-    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
-        for (int k = lane; k < cartdim; k += kLanes) rs[k] = r[b * cartdim + k];
-        for (int k = lane; k < intdim; k += kLanes) qs[k] = gq[b * intdim + k];
+    // the next geometry's coordinates and weights are fetched into registers while the current one is
+    // processed (up to kPre values per lane each; longer rows fall back to a plain load)
+    constexpr int kPre = 4;
+    const int64_t bstep = (int64_t)gridDim.x * nwarps;
+    const bool pre = cartdim <= kPre * kLanes && intdim <= kPre * kLanes;
+    double pr[kPre], pq[kPre];
+    int64_t b = (int64_t)blockIdx.x * nwarps + warp;
+    if (pre && b < B) {
+#pragma unroll
+        for (int u = 0; u < kPre; u++) {
+            const int k = lane + u * kLanes;
+            pr[u] = k < cartdim ? r[b * cartdim + k] : 0.0;
+            pq[u] = k < intdim ? gq[b * intdim + k] : 0.0;
+        }
+    }
+    for (; b < B; b += bstep) {
+        if (pre) {
+#pragma unroll
+            for (int u = 0; u < kPre; u++) {
+                const int k = lane + u * kLanes;
+                if (k < cartdim) rs[k] = pr[u];
+                if (k < intdim) qs[k] = pq[u];
+            }
+            const int64_t nb = b + bstep;
+            if (nb < B) {
+#pragma unroll
+                for (int u = 0; u < kPre; u++) {
+                    const int k = lane + u * kLanes;
+                    pr[u] = k < cartdim ? r[nb * cartdim + k] : 0.0;
+                    pq[u] = k < intdim ? gq[nb * intdim + k] : 0.0;
+                }
+            }
+        } else {
+            for (int k = lane; k < cartdim; k += kLanes) rs[k] = r[b * cartdim + k];
+            for (int k = lane; k < intdim; k += kLanes) qs[k] = gq[b * intdim + k];
+        }
         __syncwarp();
         for (int p = lane; p < gp.nwprims; p += kLanes) {
             const PrimDesc pd = prims[p];
@@ -160,9 +193,13 @@ grad_int2cart_warp_kernel(const GradProgram gp, const double * __restrict__ r, c
         }
         __syncwarp();
         for (int c = lane; c < cartdim; c += kLanes) {
-            double s = 0.0;
-            for (int k = comp_ptr[c]; k < comp_ptr[c + 1]; k++) s += S[comp_idx[k]];
-            gr[b * cartdim + c] = s;
+            // two partial sums: the slot loads of consecutive contributions do not wait for each other
+            const int k0 = comp_ptr[c], k1 = comp_ptr[c + 1];
+            double s0 = 0.0, s1 = 0.0;
+            int k = k0;
+            for (; k + 1 < k1; k += 2) { s0 += S[comp_idx[k]]; s1 += S[comp_idx[k + 1]]; }
+            if (k < k1) s0 += S[comp_idx[k]];
+            gr[b * cartdim + c] = s0 + s1;
         }
         __syncwarp();
     }
