@@ -376,6 +376,29 @@ def test_mid_size_odd_stride_chain13(T):
     assert float(big[0]) == 0.0
 
 
+def test_outputs_at_8_byte_alignment(T):
+    """Result buffers that are only 8-byte aligned (a view one double into an allocation): every
+    vectorised store path (16-byte pairs, 32-byte zero sectors, zero runs) must fall back."""
+    for key, n in (("C3", 77), ("C2", 20011), ("C2", 301)):
+        w = T.workloads.get(key)
+        s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+        r = dev(w.geometries(n, seed=5))
+        q, J, K = s.compute_IC_J_K(r[:33])
+        q, J = s.compute_IC_J(r)
+        nq, nJ, nK = n * s.intdim, n * s.intdim * s.cartdim, 33 * s.intdim * s.cartdim ** 2
+        bq = torch.zeros(nq + 1, dtype=torch.float64, device="cuda")
+        bJ = torch.zeros(nJ + 1, dtype=torch.float64, device="cuda")
+        s.compute_IC_J(r, out=(bq[1:], bJ[1:]))
+        np.testing.assert_array_equal(host(bJ[1:]).reshape(host(J).shape), host(J))
+        np.testing.assert_array_equal(host(bq[1:]).reshape(host(q).shape), host(q))
+        bK = torch.zeros(nK + 1, dtype=torch.float64, device="cuda")
+        bq2 = torch.zeros(33 * s.intdim + 1, dtype=torch.float64, device="cuda")
+        bJ2 = torch.zeros(33 * s.intdim * s.cartdim + 1, dtype=torch.float64, device="cuda")
+        s.compute_IC_J_K(r[:33], out=(bq2[1:], bJ2[1:], bK[1:]))
+        np.testing.assert_array_equal(host(bK[1:]).reshape(host(K).shape), host(K))
+        assert float(bK[0]) == 0.0 and float(bJ[0]) == 0.0 and float(bq[0]) == 0.0
+
+
 @pytest.mark.parametrize("env", [{"TCHEM_GROUP_G": "0"}, {"TCHEM_GROUP_G": "2"}, {"TCHEM_GROUP_G": "4"},
                                  {"TCHEM_GROUP_G": "6", "TCHEM_LINE": "0"}, {"TCHEM_STAGE_SPANS": "0", "TCHEM_GROUP_G": "0"}])
 def test_warp_group_kernel_variants(T, env):

@@ -118,6 +118,12 @@ def interpret(prog, r, mode):
                     flat[:, base + run.k:base + run.k + run.len] = 0.0
             for e in range(sd.n):
                 m = prog["emap"][sd.map + e]
+                if m.word == 0x00FFFFFF:                    # a whole 32-byte sector of structural zeros
+                    assert (base + m.k) % 4 == 0 and not seen[m.k:m.k + 4].any()
+                    seen[m.k:m.k + 4] = True
+                    if not ch.accumulate:
+                        flat[:, base + m.k:base + m.k + 4] = 0.0
+                    continue
                 assert not seen[m.k], "element emitted twice"
                 seen[m.k] = True
                 v = gather_packed(m.word)

@@ -67,10 +67,9 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int cartdim = prog.cartdim, intdim = prog.intdim;
-    const size_t tile_doubles = (((size_t)(cartdim + prog.cap) * kPad) + 1) & ~size_t(1);   // the line buffer is read 16 bytes at a time
+    const size_t tile_doubles = (((size_t)(cartdim + prog.cap) * kPad) + 1) & ~size_t(1);
     double * R = warp_base + (size_t)warp * (tile_doubles + prog.line_elems);
     double * P = R + (size_t)cartdim * kPad;
-    double * L = R + tile_doubles;
     const int64_t ntiles = (B + kLanes - 1) / kLanes;
     const int64_t jstride = (int64_t)intdim * cartdim, kstride = jstride * cartdim;
 
@@ -107,18 +106,13 @@ ic_eval_kernel(const Program prog, const double * __restrict__ r, const int64_t 
         }
         if (q != nullptr)
             store_rows(P, ch.qslot, ch.nrows, q + b0 * intdim + ch.row0, intdim, ntile, ch.accumulate != 0, lane);
-        if (MODE != MODE_VALUE && J != nullptr) {
-            double * Jc = J + b0 * jstride + (int64_t)ch.row0 * cartdim;
-            const int E = ch.nrows * cartdim;
-            if (MODE == MODE_QJ && prog.line_elems >= 2 * ((E + 1) & ~1) && !ch.accumulate && line_eligible(ch.jspan)) {
-                if (ntile == kLanes) gather_store_line<true>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
-                else                 gather_store_line<false>(ch.jspan, psrcs, coefs, P, L, E, Jc, jstride, ntile, lane, pfJ);
-            } else {
-                gather_store(ch.jspan, emap, psrcs, coefs, runs, P, Jc, jstride, ntile, ch.accumulate != 0, lane, pfJ);
-            }
-        }
+        // (no line-buffer write-out here: it only pays for the multi-row chunks of the warp-group
+        // kernel, and even an untaken out-of-line call costs this kernel registers)
+        if (MODE != MODE_VALUE && J != nullptr)
+            gather_store(ch.jspan, emap, psrcs, coefs, runs, P, J + b0 * jstride + (int64_t)ch.row0 * cartdim,
+                         jstride, ntile, ch.accumulate != 0, lane, pfJ);
         if (MODE == MODE_QJK && K != nullptr)
-            gather_store(ch.kspan, emap, psrcs, coefs, runs, P,
+            gather_store<true>(ch.kspan, emap, psrcs, coefs, runs, P,
                          K + b0 * kstride + (int64_t)ch.row0 * cartdim * cartdim, kstride, ntile, ch.accumulate != 0, lane);
         __syncwarp();
         }

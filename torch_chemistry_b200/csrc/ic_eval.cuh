@@ -426,7 +426,7 @@ __device__ __forceinline__ SpanPrefetch span_prefetch(const SpanDesc & sp, const
     return pf;
 }
 
-template <bool FULL, bool ACC>
+template <bool FULL, bool ACC, bool ZSEC>
 __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const ElemMap * __restrict__ emap_all,
                                                   const uint4 * __restrict__ psrcs, const double * __restrict__ coefs,
                                                   const ZeroRun * __restrict__ runs, const double * P, double * out,
@@ -438,9 +438,10 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
         }
     const ElemMap * emap = emap_all + sp.map;
     const int S = sp.n;
+    const bool al32 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;     // (the geometry stride is a multiple of 32 bytes whenever sector entries exist)
     ElemMap m1 = pf.m1, m2 = pf.m2;
     uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
-    if (m1.word) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
+    if (m1.word >> kMapCountShift) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
     for (int k0 = 0; k0 < S; k0 += kLanes) {
         const bool valid = k0 + lane < S;
         const ElemMap m = m1;
@@ -448,13 +449,28 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
         m1 = m2;
         m2.word = 0u; m2.k = 0u;
         if (k0 + 2 * kLanes + lane < S) m2 = load_emap(emap + k0 + 2 * kLanes + lane);
-        if (m1.word) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
+        if (m1.word >> kMapCountShift) q1 = load_quad(psrcs + (m1.word & kMapOffsetMask));
         const int cnt = (int)(m.word >> kMapCountShift);
         const uint32_t off = m.word & kMapOffsetMask;
         char * o = reinterpret_cast<char *>(out + m.k);
         const int maxcnt = __reduce_max_sync(kFull, valid ? cnt : 0);
+        if (ZSEC && valid && !ACC && m.word == kZeroSectorWord) {
+            // a whole sector of zeros: one 32-byte store per geometry (its first element is written
+            // once more, as 0.0, if this step also holds non-zero elements: harmless)
+            const int n = FULL ? kLanes : ntile;
+            if (al32) {
+#pragma unroll 8
+                for (int g = 0; g < n; g++)
+                    asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};\n" ::"l"(o + (int64_t)g * gbytes), "d"(0.0) : "memory");
+            } else {                               // caller's buffer is not 32-byte aligned
+                for (int g = 0; g < n; g++) {
+                    double * og = reinterpret_cast<double *>(o + (int64_t)g * gbytes);
+                    og[0] = 0.0; og[1] = 0.0; og[2] = 0.0; og[3] = 0.0;
+                }
+            }
+        }
         if (maxcnt == 0) {
-            if (valid && !ACC) {
+            if (valid && !ACC && !(ZSEC && m.word == kZeroSectorWord)) {
                 const int n = FULL ? kLanes : ntile;
 #pragma unroll 8
                 for (int g = 0; g < n; g++) *reinterpret_cast<double *>(o + (int64_t)g * gbytes) = 0.0;
@@ -570,24 +586,27 @@ __device__ __noinline__ void gather_store_line(const SpanDesc & sp, const uint4 
     else                  gather_store_line_ns<FULL, 4>(sp, psrcs, coefs, P, L, E, out, gstride, ntile, lane, pf);
 }
 
-// `coefs` = the table of distinct coefficients (shared-memory copy when it is small)
+// `coefs` = the table of distinct coefficients (shared-memory copy when it is small).
+// ZSEC: the span may hold zero-sector entries (K spans; see emit_span)
+template <bool ZSEC = false>
 __device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const uint4 * __restrict__ psrcs,
                                              const double * __restrict__ coefs, const ZeroRun * __restrict__ runs,
                                              const double * P, double * out, int64_t gstride, int ntile, bool accumulate, int lane,
                                              const SpanPrefetch & pf) {
     const int gbytes = (int)(gstride * sizeof(double));
     if (accumulate) {
-        if (ntile == kLanes) gather_store_impl<true, true>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
-        else                 gather_store_impl<false, true>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
+        if (ntile == kLanes) gather_store_impl<true, true, ZSEC>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
+        else                 gather_store_impl<false, true, ZSEC>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
     } else {
-        if (ntile == kLanes) gather_store_impl<true, false>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
-        else                 gather_store_impl<false, false>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
+        if (ntile == kLanes) gather_store_impl<true, false, ZSEC>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
+        else                 gather_store_impl<false, false, ZSEC>(sp, emap, psrcs, coefs, runs, P, out, gbytes, ntile, lane, pf);
     }
 }
+template <bool ZSEC = false>
 __device__ __forceinline__ void gather_store(const SpanDesc & sp, const ElemMap * __restrict__ emap, const uint4 * __restrict__ psrcs,
                                              const double * __restrict__ coefs, const ZeroRun * __restrict__ runs,
                                              const double * P, double * out, int64_t gstride, int ntile, bool accumulate, int lane) {
-    gather_store(sp, emap, psrcs, coefs, runs, P, out, gstride, ntile, accumulate, lane, span_prefetch(sp, emap, lane));
+    gather_store<ZSEC>(sp, emap, psrcs, coefs, runs, P, out, gstride, ntile, accumulate, lane, span_prefetch(sp, emap, lane));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -66,6 +66,9 @@ constexpr int kMinZeroRun = 64;
 // the element's first 16-byte quad of packed sources)
 constexpr uint32_t kMapCountShift = 24;
 constexpr uint32_t kMapOffsetMask = 0x00ffffffu;
+// J / K elements: this word marks a whole 32-byte sector of structural zeros (4 elements from k on,
+// 32-byte aligned in the output): one table entry and one 32-byte store instead of four of each
+constexpr uint32_t kZeroSectorWord = 0x00ffffffu;
 
 // Packed source of a J / K element: (coefficient index << 16) | compact entry. An element's
 // sources start on a quad boundary, so one 16-byte load fetches up to four of them.

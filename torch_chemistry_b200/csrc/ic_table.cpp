@@ -54,7 +54,7 @@ static int min_zero_run() {
 
 bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
                std::vector<ElemMap> & emap, std::vector<uint32_t> & psrcs, std::vector<double> & coefs,
-               std::vector<ZeroRun> & runs, SpanDesc & span) {
+               std::vector<ZeroRun> & runs, SpanDesc & span, bool zero_sectors) {
     const int64_t S = (int64_t)lists.size();
     span.map = (int64_t)emap.size();
     span.run0 = (int32_t)runs.size();
@@ -88,11 +88,35 @@ bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int
     // last round, keeping the address order otherwise
     auto klass = [](int m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m <= 4 ? 3 : 4 + (m - 1) / 4; };
     std::stable_sort(rest.begin(), rest.end(), [&](const Unit & a, const Unit & b) { return klass(a.maxcnt) > klass(b.maxcnt); });
-    for (const Unit & u : rest) {
+    // Zero sectors that do not belong to a run: one entry (and one 32-byte store) per sector instead of
+    // four - but only in warp steps of their own (a step that mixes them with gathered elements pays
+    // for both loops), i.e. from the next multiple of 32 entries on and when at least one full step
+    // of them remains. The sectors before that boundary stay element-wise.
+    const bool sectors_aligned = zero_sectors && gstride % 4 == 0;
+    size_t sector_from = rest.size();
+    if (sectors_aligned) {
+        size_t entries = 0, first_zero = rest.size();
+        for (size_t i = 0; i < rest.size(); i++) {
+            if (rest[i].maxcnt == 0) { first_zero = i; break; }
+            entries += (size_t)(rest[i].last - rest[i].first);
+        }
+        size_t i = first_zero;
+        while (i < rest.size() && entries % kLanes != 0) { entries += (size_t)(rest[i].last - rest[i].first); i++; }
+        if (i < rest.size() && rest.size() - i >= (size_t)kLanes) sector_from = i;
+    }
+    for (size_t ui = 0; ui < rest.size(); ui++) {
+        const Unit & u = rest[ui];
         if (u.maxcnt > 0) span.nnz += (int32_t)(u.last - u.first);
+        if (ui >= sector_from && u.maxcnt == 0 && u.last - u.first == 4 && (abs_off + u.first) % 4 == 0) {
+            ElemMap m;
+            m.word = kZeroSectorWord;
+            m.k = (uint32_t)u.first;
+            emap.push_back(m);
+            continue;
+        }
         for (int64_t e = u.first; e < u.last; e++) {
             const auto & l = lists[e];
-            if (l.size() > 255 || psrcs.size() / 4 + l.size() > kMapOffsetMask) return false;
+            if (l.size() > 255 || psrcs.size() / 4 + l.size() >= kMapOffsetMask) return false;
             ElemMap m;
             m.word = l.empty() ? 0u : (((uint32_t)l.size() << kMapCountShift) | (uint32_t)(psrcs.size() / 4));
             m.k = (uint32_t)e;
@@ -253,8 +277,8 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
             }
             return true;
         };
-        auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, SpanDesc & span) {
-            return emit_span(lists, abs_off, gstride, hp.emap, hp.psrcs, hp.coefs, hp.runs, span);
+        auto emit_sorted = [&](std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride, SpanDesc & span, bool zsec = false) {
+            return emit_span(lists, abs_off, gstride, hp.emap, hp.psrcs, hp.coefs, hp.runs, span, zsec);
         };
         std::vector<std::vector<Src>> ql(pc.nrows), jl, kl;
         if (mode != MODE_VALUE) jl.resize((size_t)pc.nrows * cd);
@@ -289,7 +313,7 @@ int build_program(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cart
         }
         bool ok = emit(ql, ch.qmap);
         if (ok && mode != MODE_VALUE) ok = emit_sorted(jl, (int64_t)pc.row0 * cd, (int64_t)n_ic * cd, ch.jspan);
-        if (ok && mode == MODE_QJK) ok = emit_sorted(kl, (int64_t)pc.row0 * cd * cd, (int64_t)n_ic * cd * cd, ch.kspan);
+        if (ok && mode == MODE_QJK) ok = emit_sorted(kl, (int64_t)pc.row0 * cd * cd, (int64_t)n_ic * cd * cd, ch.kspan, true);
         if (!ok) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: internal coordinate definition too large for the gather map");
         hp.chunks.push_back(ch);
     }

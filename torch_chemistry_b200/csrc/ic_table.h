@@ -42,9 +42,11 @@ struct HostProgram {
 // fills `span`; false when a list is too long for the encoding. Elements are grouped in
 // sectors of 4 (aligned to `abs_off`, the span's element offset inside the geometry block, when
 // the block stride keeps sectors aligned) and the sectors are ordered by source count.
+// zero_sectors: whole sectors of structural zeros may become single entries (kZeroSectorWord; K spans,
+// whose write-out is compiled with ZSEC).
 bool emit_span(const std::vector<std::vector<Src>> & lists, int64_t abs_off, int64_t gstride,
                std::vector<ElemMap> & emap, std::vector<uint32_t> & psrcs, std::vector<double> & coefs,
-               std::vector<ZeroRun> & runs, SpanDesc & span);
+               std::vector<ZeroRun> & runs, SpanDesc & span, bool zero_sectors = false);
 
 // pure host: flatten terms into a program for one mode
 // cap_hint > 0: compact capacity to aim for (at least the largest primitive), 0: default policy;
