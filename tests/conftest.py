@@ -15,6 +15,14 @@ EPS = 2.220446049250313e-16
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a clean checkout has no built library yet (built artefacts are git-ignored): build it once,
+    # exactly as __graft_entry__.build() does (nvcc cross-compiles for sm_100a without a GPU)
+    if not os.path.exists(os.path.join(ROOT, "torch_chemistry_b200", "libtchem_b200.so")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("tchem_b200_build", os.path.join(ROOT, "torch_chemistry_b200", "build.py"))
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        b.build()
 
 
 def golden(name):
