@@ -65,6 +65,16 @@ struct Nvrtc {
 };
 Nvrtc & nvrtc() { static Nvrtc n; return n; }
 
+// monomials per chunk of the chained kernel: as many as fit `dcap` staged entries, and - when the set
+// needs several chunks - a multiple of 4, so that every chunk's y (8 bytes per term) and J pieces end
+// on 32-byte sector boundaries (a half-written sector costs a DRAM read-modify-write)
+int chain_terms_per_chunk(int nt, int per_term, int dcap) {
+    const int nchunks = (nt * per_term + dcap - 1) / dcap;
+    int tper = (nt + nchunks - 1) / nchunks;
+    if (nchunks > 1 && tper >= 4) tper &= ~3;
+    return tper;
+}
+
 // staging row of element e of a span (mirrors staged_row<SPAN> in the prelude)
 int stage_row(int e, int span) { return span % 2 == 0 ? (e >> 1) + (e & 1) * (span / 2) : e; }
 
@@ -265,7 +275,7 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     const int nt = (int)saps.size(), sd = n_ic;
     const int per_term = 1 + sd;
     if (per_term > dcap) return std::string();
-    const int nchunks = (nt * per_term + dcap - 1) / dcap, tper = (nt + nchunks - 1) / nchunks;
+    const int tper = chain_terms_per_chunk(nt, per_term, dcap);
     std::ostringstream o;
     o << "#define NT " << nt << "\n#define SD " << sd << "\n";
     emit_prologue(o, "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
@@ -536,7 +546,7 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
             const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, 76));
             jk.warps = env_int("TCHEM_JIT_WARPS", 4);
             jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
-            const int nchunks = (nt * per_term + dcap - 1) / dcap, tper = (nt + nchunks - 1) / nchunks;
+            const int tper = chain_terms_per_chunk(nt, per_term, dcap);
             const std::string src = jit_chain_source(t->terms, t->intdim, t->cartdim, st->h_terms, dcap, jk.warps, jk.blocks);
             const size_t smem = (size_t)jk.warps * (t->cartdim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
             jit_finish(jk, src, "tchem_jit_chain", smem, t->max_smem_optin, debug);
