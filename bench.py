@@ -36,9 +36,10 @@ WORKLOADS = {
     "C4H": ("Hessian_int2cart", lambda cd, n, ns: 8 * (cd + n + n * n + cd * cd)),
     "C4Hc": ("Hessian_cart2int", lambda cd, n, ns: 8 * (cd + cd + cd * cd + n * n)),
     "C5": ("q->SAPSet value+Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * n)),
+    "C5x": ("SAPSet value+Jacobian on given coordinates", lambda cd, n, ns: 8 * (n + ns + ns * n)),
 }
 DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4J": 5 * 10 ** 4, "C4g": 10 ** 5, "C4gc": 10 ** 5, "C4H": 10 ** 5,
-                 "C4Hc": 10 ** 5, "C5": 12500000}
+                 "C4Hc": 10 ** 5, "C5": 12500000, "C5x": 12500000}
 # dense flops per geometry of the contraction-bound transforms
 FLOPS = {
     "C4H": lambda cd, n: 2 * n * n * cd + 2 * cd * n * cd + 2 * n * cd * cd,
@@ -221,7 +222,7 @@ def cpu_baseline(w, what, per_core, cores=None):
 
 def per_core_sample(key):
     # sized for roughly 10-20 s of CPU work per process with the reference's measured per-geometry cost
-    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000}[key]
+    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000, "C5x": 20000}[key]
 
 
 # ------------------------------------------------------------------------------------------
@@ -268,7 +269,7 @@ def main():
     wl = importlib.util.module_from_spec(spec)
     sys.modules["_wl"] = wl
     spec.loader.exec_module(wl)
-    wkey = {"C3K": "C3", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
+    wkey = {"C3K": "C3", "C5x": "C5", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
     w = wl.get(wkey)
     what, bytes_fn = WORKLOADS[args.workload]
     B = args.batch or DEFAULT_BATCH[args.workload]
@@ -330,6 +331,10 @@ def main():
         step = lambda: ic.Hessian_int2cart(r_dev, gq_dev, Hq_dev)
     elif what == "Hessian_cart2int":
         step = lambda: ic.Hessian_cart2int(r_dev, gr_dev, Hr_dev)
+    elif args.workload == "C5x":
+        x_dev = ic(r_dev).contiguous()                      # the coordinates a caller would bring
+        souts = sap.eval_cat(x_dev)
+        step = lambda: sap.eval_cat(x_dev, out=souts)
     else:
         step = lambda: sap.chained(ic, r_dev)
     need_flush = B * bytes_per_geom <= 126e6
@@ -367,7 +372,7 @@ def main():
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
-    if not args.no_e2e and (what in ("q+J", "q+J+K") or sap is not None):
+    if not args.no_e2e and args.workload != "C5x" and (what in ("q+J", "q+J+K") or sap is not None):
         pin = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
         if sap is not None:
             houts = [pin(B, ns), pin(B, ns, n)]
@@ -396,7 +401,8 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
-        kernel = ("tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
+        kernel = ("tchem_jit_chain (SAPSet-specialised, NVRTC)" if args.workload == "C5x" and T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, B)
+                  else "tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
                   else "sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
                   else "dense_kernel" if args.workload in FLOPS
                   else "tchem_jit_qJ (table-specialised, NVRTC)" if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)

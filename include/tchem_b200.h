@@ -184,7 +184,7 @@ TCHEM_API int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms
 TCHEM_API int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity);
 /* 1 when a q + J call on B geometries is served by the specialised kernel, 0 = interpreter */
 TCHEM_API int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B);
-/* the same question for tchem_ic_sap_eval (pair-specialised chained kernel) */
+/* the same question for tchem_ic_sap_eval (pair-specialised chained kernel); ic == NULL: tchem_sap_eval */
 TCHEM_API int tchem_ic_sap_uses_specialised(const tchem_sap_table * sap, const tchem_ic_table * ic, int64_t B);
 
 /* ---- measurement helpers (bench.py only) ------------------------------------------------ */

@@ -197,6 +197,22 @@ def test_sap_known_answers_and_goldens(T):
         T.SAPSet.from_text("\n1,1\n", 1, [2])
 
 
+def test_sap_specialised_on_given_coordinates(T):
+    """SAPSet::operator() / Jacobian_ on caller-supplied coordinates: large batches run the NVRTC kernel
+    specialised to the set, small ones the interpreter; both against the oracle, ragged batch."""
+    w = T.workloads.get("C5")
+    sap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims)
+    osap = O.SAPSet(w.sap_text, 0, w.sap_dims)
+    rng = np.random.default_rng(21)
+    for n in (40013, 777):
+        x = rng.standard_normal((n, 3)) * 0.7 + 1.0
+        xd = dev(x)
+        xs = [xd[:, :2], xd[:, 2:]]
+        assert bool(T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, n)) == (n >= 16384)
+        assert_parity(host(sap(xs)), osap.value(x), "SAPSet value (n=%d)" % n)
+        assert_parity(host(sap.Jacobian_cat(xs)), osap.jacobian(x), "SAPSet Jacobian (n=%d)" % n)
+
+
 def test_chained_sap_C5(T):
     g = golden("workload_C5")
     w = T.workloads.get("C5")

@@ -223,8 +223,9 @@ bool emit_prim(std::ostringstream & o, const JitPrim & pr, size_t p, bool want_J
 
 // kernel signature up to and including the per-tile prologue (coordinates staged, atoms in
 // registers, next tile's copy in flight); `params` = the kernel's pointer parameters after r, B
+// plain_cols > 0: the input rows are used as they are (x0p1 .. x{plain_cols-1}p1), no atoms / primitives
 void emit_prologue(std::ostringstream & o, const char * name, const char * params, int cartdim, int dcap_entries,
-                   int warps, int blocks, const std::vector<JitPrim> & prims) {
+                   int warps, int blocks, const std::vector<JitPrim> & prims, int plain_cols = 0) {
     const int natoms = cartdim / 3;
     o << "#define CD " << cartdim << "\n#define DCAP " << dcap_entries << "\n";
     o << kPrelude;
@@ -240,8 +241,12 @@ void emit_prologue(std::ostringstream & o, const char * name, const char * param
       << "    for (; tile < ntiles; tile += step) {\n"
       << "        const int64_t b0 = tile * LANES;\n"
       << "        const int ntile = (int)min((int64_t)LANES, B - b0);\n"
-      << "        stage_finish(ntile, R, lane);\n"
-      << "        V3<double> a[" << natoms << "];\n";
+      << "        stage_finish(ntile, R, lane);\n";
+    if (plain_cols > 0) {
+        for (int i = 0; i < plain_cols; i++) o << "        const double x" << i << "p1 = R[" << i << " * KPAD + lane];\n";
+    } else {
+        o << "        V3<double> a[" << natoms << "];\n";
+    }
     std::vector<char> atom_used(natoms, 0);
     for (const auto & p : prims) for (int i = 0; i < p.natoms; i++) atom_used[p.atoms[i]] = 1;
     for (int at = 0; at < natoms; at++)
@@ -269,9 +274,11 @@ std::string row_expr(const std::vector<std::pair<double, int>> & row, const char
 // per chunk of monomials: [values][Jacobian rows], written out like the q+J kernel.
 std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim,
                              const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks) {
+    // terms empty: the SAPSet alone, evaluated on given coordinates x[B][n_ic] (cartdim = n_ic)
+    const bool plain = terms.empty();
     std::vector<JitPrim> prims;
     std::vector<std::vector<std::pair<double, int>>> rows;
-    if (!collect(terms, n_ic, prims, rows)) return std::string();
+    if (!plain && !collect(terms, n_ic, prims, rows)) return std::string();
     const int nt = (int)saps.size(), sd = n_ic;
     const int per_term = 1 + sd;
     if (per_term > dcap) return std::string();
@@ -279,13 +286,13 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     std::ostringstream o;
     o << "#define NT " << nt << "\n#define SD " << sd << "\n";
     emit_prologue(o, "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
-                  cartdim, std::max(tper * per_term, sd), warps, blocks, prims);
+                  cartdim, std::max(tper * per_term, sd), warps, blocks, prims, plain ? sd : 0);
     for (size_t p = 0; p < prims.size(); p++)
         if (!emit_prim(o, prims[p], p, false, "        ")) return std::string();
     std::vector<int> maxpow(sd, 0);
     for (auto & t : saps) for (auto & u : t) maxpow[u.first] = std::max(maxpow[u.first], u.second);
     for (int i = 0; i < n_ic; i++) {
-        o << "        const double x" << i << "p1 = " << row_expr(rows[i], "q") << ";\n";
+        if (!plain) o << "        const double x" << i << "p1 = " << row_expr(rows[i], "q") << ";\n";
         for (int p = 2; p <= maxpow[i]; p++) o << "        const double x" << i << "p" << p << " = x" << i << "p" << p - 1 << " * x" << i << "p1;\n";
     }
     o << "        if (q) {\n";
@@ -531,8 +538,10 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
                      double * q, double * y, double * J, cudaStream_t stream) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
     static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
-    if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128
-        || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return -1;
+    // t == nullptr: the SAPSet alone on given coordinates (r = x[B][sumdim])
+    if (!enabled || std::max(B, g_batch_hint) < min_batch || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return -1;
+    if (t ? (t->has5 || t->cartdim > 36 || t->terms.size() > 128) : st->sumdim > 36) return -1;
+    const int in_dim = t ? t->cartdim : st->sumdim;
     JitKernel * k;
     {
         std::lock_guard<std::mutex> lock(jit_mutex());
@@ -547,14 +556,15 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
             jk.warps = env_int("TCHEM_JIT_WARPS", 4);
             jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
             const int tper = chain_terms_per_chunk(nt, per_term, dcap);
-            const std::string src = jit_chain_source(t->terms, t->intdim, t->cartdim, st->h_terms, dcap, jk.warps, jk.blocks);
-            const size_t smem = (size_t)jk.warps * (t->cartdim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
-            jit_finish(jk, src, "tchem_jit_chain", smem, t->max_smem_optin, debug);
+            static const std::vector<tchem_invdisp_t> no_terms;
+            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks);
+            const size_t smem = (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
+            jit_finish(jk, src, "tchem_jit_chain", smem, st->max_smem_optin, debug);
         }
         if (jk.failed) return -1;
     }
     const int64_t ntiles = (B + 31) / 32;
-    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
+    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)st->sm_count * k->per_sm);
     long long Bll = B;
     void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
@@ -647,8 +657,8 @@ int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B) {
 // 1 when tchem_ic_sap_eval on B geometries runs the pair-specialised chained kernel
 int tchem_ic_sap_uses_specialised(const tchem_sap_table * st, const tchem_ic_table * t, int64_t B) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
-    if (!st || !t || !enabled || B < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128
-        || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return 0;
+    if (!st || !enabled || B < min_batch || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return 0;
+    if (t ? (t->has5 || t->cartdim > 36 || t->terms.size() > 128) : st->sumdim > 36) return 0;
     std::lock_guard<std::mutex> lock(jit_mutex());
     auto it = chain_kernels().find({st, t});
     return it == chain_kernels().end() || !it->second.failed ? 1 : 0;

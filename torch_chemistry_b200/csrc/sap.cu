@@ -200,9 +200,9 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
 int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const double * in, int64_t B,
                double * q_out, double * y, double * J, cudaStream_t stream) {
     const bool chained = ict != nullptr;
-    if (chained) {
-        // large batches of small molecules: the kernel specialised to this (IntCoordSet, SAPSet) pair
-        const int rc = launch_jit_chain(st, ict, in, B, q_out, y, J, stream);
+    {
+        // large batches: the kernel specialised to this SAPSet (and, chained, to the IntCoordSet)
+        const int rc = launch_jit_chain(st, ict, in, B, chained ? q_out : nullptr, y, J, stream);
         if (rc != -1) return rc;
     }
     const void * fn = !chained ? reinterpret_cast<const void *>(&sap_eval_kernel<false, false>)

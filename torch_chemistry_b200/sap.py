@@ -103,6 +103,24 @@ class SAPSet:
         y, J = self._run(xs, True, True, "Jacobian_")
         return y, J
 
+    def eval_cat(self, x, out=None):
+        """value and concatenated Jacobian for coordinates already concatenated over the irreducibles:
+        x[B, sum(dimensions)] on the table's device -> (y[B, NSAP], J[B, NSAP, sum(dimensions)]); one
+        kernel launch, no copies (`out` = caller-provided (y, J))."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.shape[1] == self.sumdim
+                and x.dtype == torch.float64 and x.is_contiguous()):
+            raise ValueError("tchem::polynomial::SAPSet::eval_cat: x must be a contiguous CUDA float64 [B, %d] tensor" % self.sumdim)
+        B = x.shape[0]
+        if out is None:
+            y = torch.empty((B, self.nterms), dtype=torch.float64, device=self.device)
+            J = torch.empty((B, self.nterms, self.sumdim), dtype=torch.float64, device=self.device)
+        else:
+            y, J = out
+        if B > 0:
+            check(lib.tchem_sap_eval(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()), C.c_void_p(J.data_ptr()),
+                                     _stream_ptr(self.device)))
+        return y, J
+
     # ---- chained path ----------------------------------------------------------------------
     def chained(self, intcoordset, r, return_q=False, out=None):
         """r -> q (compute_IC_J formulas) -> SAP values and d SAP / d q in one kernel. Host tensors
