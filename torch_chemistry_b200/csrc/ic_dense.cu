@@ -17,6 +17,7 @@
 // factor, L^-T L^-1 (LAPACK potrf + potri behind at::cholesky / at::cholesky_inverse) - because a
 // mathematically equivalent solve already differs from it by ~cond * eps.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -209,8 +210,15 @@ __device__ void block_add_gK(const DenseProgram & dp, const double * rg, const d
 // global [rows][cols] -> shared [rows][ld], asynchronously (cp.async; 16 bytes per copy when the row
 // pitch allows, else 8): the caller overlaps the transfer with arithmetic and calls
 // block_load_wait() + __syncthreads() before touching the tile. One warp per row at a time.
-__device__ __forceinline__ void block_load_async(const double * __restrict__ g, double * s, int rows, int cols, int ld) {
+// (workspace mode - operands in global memory because the molecule is too large for shared memory -
+// copies synchronously: cp.async only writes shared memory)
+__device__ __forceinline__ void block_load_async(const double * __restrict__ g, double * s, int rows, int cols, int ld, bool in_smem = true) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    if (!in_smem) {
+        for (int r = warp; r < rows; r += nwarps)
+            for (int c = lane; c < cols; c += kLanes) s[r * ld + c] = g[(int64_t)r * cols + c];
+        return;
+    }
     const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
     for (int r = warp; r < rows; r += nwarps) {
         const double * src = g + (int64_t)r * cols;
@@ -256,7 +264,6 @@ __device__ __forceinline__ void block_store(const double * s, double * __restric
 // trailing updates, the block rows of L^-1, the final product - by DMMA.
 // Returns false (all threads) when a pivot is not positive.
 constexpr int kNB = 16;
-constexpr int kMaxN = 256;
 
 // lanes 0..15 = rows of the diagonal block at D (bs <= 16 rows): in-place lower Cholesky factor;
 // dinv[j] = 1 / L[j][j]. Lanes / columns >= bs carry an identity so every lane runs the same code.
@@ -322,9 +329,8 @@ __device__ __forceinline__ void warp_trtri16(const double * D, int ld, int bs, c
     }
 }
 
-__device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw) {
+__device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw, double * dinv /* n doubles */) {
     __shared__ int bad;
-    __shared__ double dinv[kMaxN];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
@@ -391,7 +397,7 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
 // shared-memory plan (in doubles). Regions:  rg | v1 | v2 | M | ARENA
 // ---------------------------------------------------------------------------------------
 struct DensePlan {
-    int rg, v1, v2, M, arena, total;
+    int rg, v1, v2, dinv, M, arena, total;
 };
 __host__ __device__ inline int even(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, int ldh) {
@@ -399,7 +405,8 @@ __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, 
     p.rg = 0;
     p.v1 = p.rg + even(cd);
     p.v2 = p.v1 + even(cd > n ? cd : n);
-    p.M = p.v2 + even(cd > n ? cd : n);
+    p.dinv = p.v2 + even(cd > n ? cd : n);
+    p.M = p.dinv + even(n);
     const int szJ = n * ldj, szA = n * ldh, szH = cd * ldj, szT2 = cd * ldh;
     int arena = 0;
     switch (op) {
@@ -415,13 +422,20 @@ __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, 
 // OP 1: gradient_cart2int          in1 = g_r[cd]                       out = g_q[n]
 // OP 2: Hessian_int2cart           in1 = g_q[n],  in2 = H_q[n][n]      out = H_r[cd][cd]
 // OP 3: Hessian_cart2int           in1 = g_r[cd], in2 = H_r[cd][cd]    out = H_q[n][n]
-template <int OP, bool HAS5>
+template <int OP, bool HAS5, bool WS>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double * __restrict__ in1,
-             const double * __restrict__ in2, const int64_t B, double * __restrict__ out, int * __restrict__ status) {
-    extern __shared__ __align__(16) double sm[];
+             const double * __restrict__ in2, const int64_t B, double * __restrict__ out, int * __restrict__ status,
+             double * __restrict__ workspace) {
+    // operands in shared memory, or - molecules beyond the shared-memory plan - in a per-block slice of
+    // a global workspace (same code, served from L2; functional rather than fast)
+    // (WS is a template parameter so that the shared-memory flavour keeps shared-state-space loads)
+    extern __shared__ __align__(16) double sm_dyn[];
+    constexpr bool in_smem = !WS;
     const int n = dp.intdim, cd = dp.cartdim, ldj = dp.ldj, ldh = dp.ldh;
     const DensePlan pl = dense_plan(OP, n, cd, ldj, ldh);
+    double * sm = sm_dyn;
+    if (WS) sm = workspace + (size_t)blockIdx.x * pl.total;
     double * rg = sm + pl.rg, * v1 = sm + pl.v1, * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
 
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
@@ -431,7 +445,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         if (OP == 2) {
             double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
             for (int i = threadIdx.x; i < n; i += blockDim.x) v1[i] = in1[b * n + i];
-            block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh);    // in flight while J is formed
+            block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh, in_smem);    // in flight while J is formed
             block_compute_J<HAS5>(dp, rg, J);                             // syncs
             block_load_wait();
             __syncthreads();
@@ -452,7 +466,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         block_compute_J<HAS5>(dp, rg, J);
         block_dgemm<false, true, false, 1>(n, n, cd, J, ldj, J, ldj, A, ldh);        // A = J J^T (lower)
         __syncthreads();
-        const bool ok = block_spd_inverse(n, A, ldh, W, ldh);                        // A = (J J^T)^-1
+        const bool ok = block_spd_inverse(n, A, ldh, W, ldh, sm + pl.dinv);                        // A = (J J^T)^-1
         if (!ok && threadIdx.x == 0) atomicExch(status, 1);
         if (OP == 1) {
             // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203, without forming inv J)
@@ -488,7 +502,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
             for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
             v2[i] = s;
         }
-        block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj);
+        block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj, in_smem);
         block_load_wait();
         __syncthreads();
         block_add_gK<HAS5>(dp, rg, v2, -1.0, Hc, ldj);                   // Hc = H_r - sum g_q K
@@ -576,8 +590,9 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
     return TCHEM_OK;
 }
 
-template <int OP> const void * dense_fn(bool has5) {
-    return has5 ? reinterpret_cast<const void *>(&dense_kernel<OP, true>) : reinterpret_cast<const void *>(&dense_kernel<OP, false>);
+template <int OP> const void * dense_fn(bool has5, bool ws) {
+    return ws ? (has5 ? reinterpret_cast<const void *>(&dense_kernel<OP, true, true>) : reinterpret_cast<const void *>(&dense_kernel<OP, false, true>))
+              : (has5 ? reinterpret_cast<const void *>(&dense_kernel<OP, true, false>) : reinterpret_cast<const void *>(&dense_kernel<OP, false, false>));
 }
 
 int launch_dense(int op, const char * who, const tchem_ic_table * t, const double * r, const double * in1,
@@ -587,8 +602,6 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     if (B < 0) return set_error(TCHEM_EINVAL, name + ": negative batch");
     if (B == 0) return TCHEM_OK;
     if (!r || !out || (op >= 1 && !in1) || (op >= 2 && !in2)) return set_error(TCHEM_EINVAL, name + ": null argument");
-    if (op != 2 && t->intdim > kMaxN)
-        return set_error(TCHEM_EINVAL, name + ": too many internal coordinates for the per-geometry shared-memory plan");
     if (op != 2 && t->intdim > t->cartdim)
         return set_error(TCHEM_EINVAL, name + ": more internal coordinates than Cartesian coordinates (J J^T is singular)");
     DeviceGuard guard(t->device);
@@ -596,18 +609,36 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     DenseTable dt;
     int rc = get_dense(t, dt);
     if (rc != TCHEM_OK) return rc;
-    const void * fn = op == 0 ? dense_fn<0>(t->has5) : op == 1 ? dense_fn<1>(t->has5) : op == 2 ? dense_fn<2>(t->has5) : dense_fn<3>(t->has5);
     const DensePlan pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh);
-    const size_t smem = (size_t)pl.total * sizeof(double);
-    if (smem + 4096 > (size_t)t->max_smem_optin)        // + the kernel's static shared memory
-        return set_error(TCHEM_EINVAL, name + ": molecule too large for the per-geometry shared-memory plan");
-    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int64_t grid = std::min<int64_t>(B, (int64_t)t->sm_count * per_sm);
-    void * args[] = {(void *)&dt.prog, (void *)&r, (void *)&in1, (void *)&in2, (void *)&B, (void *)&out, (void *)&dt.status};
-    TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kDenseThreads), args, smem, stream));
+    size_t smem = (size_t)pl.total * sizeof(double);
+    // Molecules whose operands do not fit the shared memory of one SM (more than ~32 atoms for a full
+    // 3N-6 set) run the same kernel on a per-block slice of a stream-ordered global workspace: correct
+    // for any size, served from L2 instead of shared memory (TCHEM_DENSE_WORKSPACE=1 forces this mode)
+    static const bool force_ws = [] { const char * e = getenv("TCHEM_DENSE_WORKSPACE"); return e && atoi(e) != 0; }();
+    const bool use_ws = force_ws || smem + 4096 > (size_t)t->max_smem_optin;
+    const void * fn = op == 0 ? dense_fn<0>(t->has5, use_ws) : op == 1 ? dense_fn<1>(t->has5, use_ws)
+                    : op == 2 ? dense_fn<2>(t->has5, use_ws) : dense_fn<3>(t->has5, use_ws);
+    double * workspace = nullptr;
+    int64_t grid;
+    if (use_ws) {
+        smem = 0;
+        int per_sm = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, 0));
+        grid = std::min<int64_t>(B, (int64_t)t->sm_count * std::max(per_sm, 1));
+        const size_t bytes = (size_t)grid * pl.total * sizeof(double);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&workspace), bytes, stream);
+        if (e != cudaSuccess) { cudaGetLastError(); return set_error(TCHEM_ECUDA, name + ": cannot allocate the workspace for a molecule of this size"); }
+    } else {
+        TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = std::min<int64_t>(B, (int64_t)t->sm_count * per_sm);
+    }
+    void * args[] = {(void *)&dt.prog, (void *)&r, (void *)&in1, (void *)&in2, (void *)&B, (void *)&out, (void *)&dt.status, (void *)&workspace};
+    cudaError_t le = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kDenseThreads), args, smem, stream);
+    if (workspace) cudaFreeAsync(workspace, stream);
+    if (le != cudaSuccess) return set_error(TCHEM_ECUDA, cudaGetErrorString(le));
     count_launch();
     return TCHEM_OK;
 }
