@@ -265,6 +265,33 @@ def test_chained_specialised_multichunk_C2(T):
         assert_parity(host(J[idx]), osap.jacobian(qd), "C2 chained Jacobian (n=%d)" % n)
 
 
+def test_full_size_properties_C5(T):
+    """BASELINE config 5 at its per-GPU size (1.25e7 geometries, ~10 GB of results): properties that
+    need no oracle - the constant term, monomials that are a coordinate or its square, their
+    Jacobian rows, agreement of every 4099th geometry with the oracle."""
+    w = T.workloads.get("C5")
+    ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    sap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims)
+    n = 12500000
+    r = dev(w.geometries(n, seed=5))
+    y, J, q = sap.chained(ic, r, return_q=True)
+    assert bool((y[:, 0] == 1.0).all()) and bool((J[:, 0] == 0.0).all())          # the 0th-order term
+    assert torch.equal(y[:, 1], q[:, 0]) and torch.equal(y[:, 2], q[:, 1])        # "1,1" and "1,2"
+    assert torch.equal(y[:, 3], q[:, 0] * q[:, 0])                                # "1,1 1,1"
+    assert torch.equal(y[:, 6], q[:, 2] * q[:, 2])                                # "2,1 2,1"
+    e = torch.zeros(3, dtype=torch.float64, device="cuda")
+    e[0] = 1.0
+    assert bool((J[:, 1] == e).all())
+    assert torch.equal(J[:, 3, 0], 2.0 * q[:, 0]) and bool((J[:, 3, 1:] == 0.0).all())
+    assert torch.equal(J[:, 4, 0], q[:, 1]) and torch.equal(J[:, 4, 1], q[:, 0])  # "1,2 1,1"
+    idx = torch.arange(0, n, 4099, device="cuda")
+    orc, osap = O.IntCoordSet("default", w.ic_text), O.SAPSet(w.sap_text, 0, w.sap_dims)
+    qo = orc.qJ(host(r[idx]))[0]
+    assert_parity(host(q[idx]), qo, "C5 full size q")
+    assert_parity(host(y[idx]), osap.value(qo), "C5 full size value")
+    assert_parity(host(J[idx]), osap.jacobian(qo), "C5 full size Jacobian")
+
+
 def test_gradient_int2cart_reference_fixture(T):
     g = golden("ref_aniline_default")
     s = T.IntCoordSet.from_text("default", str(g["definition"]), n_atoms=14)
