@@ -160,6 +160,39 @@ def test_full_size_properties_C2(T):
     assert torch.equal(torch.cat([qa, qb]), q) and torch.equal(torch.cat([Ja, Jb]), J)
 
 
+def test_full_size_properties_C3_C4(T):
+    """BASELINE configs 3 and 4 at their full batch (10^5 geometries): q + J against the oracle on a
+    strided subsample, translational invariance of every J row, bit-identical halves; C4 gradient
+    int -> cart -> int round trip over the whole batch."""
+    for key, stride in (("C3", 1009), ("C4", 2003)):
+        w = T.workloads.get(key)
+        s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+        orc = O.IntCoordSet("default", w.ic_text)
+        n = 10 ** 5
+        r = w.geometries(n)
+        rd = dev(r)
+        q, J = s.compute_IC_J(rd)
+        idx = np.arange(0, n, stride)
+        qo, Jo = orc.qJ(r[idx])
+        assert_q_parity(host(q[idx]), qo, orc.terms(), r[idx], key + " full q subsample")
+        assert_parity(host(J[idx]), Jo, key + " full J subsample")
+        assert float(J.view(n, s.intdim, w.natoms, 3).sum(dim=2).abs().max()) < 1e-12
+        h = n // 2 + 7
+        qa, Ja = s.compute_IC_J(rd[:h])
+        qb, Jb = s.compute_IC_J(rd[h:])
+        assert torch.equal(torch.cat([qa, qb]), q) and torch.equal(torch.cat([Ja, Jb]), J)
+        if key == "C4":
+            gen = torch.Generator(device="cuda").manual_seed(9)
+            gq = torch.randn(n, s.intdim, dtype=torch.float64, device="cuda", generator=gen)
+            gr = s.gradient_int2cart(rd, gq)
+            assert_parity(host(gr[idx]), np.einsum("bij,bi->bj", host(J[idx]), host(gq[idx])), "C4 full gradient_int2cart", tol=1e-11)
+            gq1 = s.gradient_cart2int(rd, gr)
+            assert s.factor_status() == 0 if hasattr(s, "factor_status") else True
+            assert float((gq1 - gq).abs().max()) < 1e-8
+        del q, J, qa, Ja, qb, Jb
+        torch.cuda.empty_cache()
+
+
 def test_K_properties_C3(T):
     """K: symmetric in its last two axes, rows/columns sum to zero over atoms, matches central
     differences of J (test/intcoord/main.cpp:34-53)."""
