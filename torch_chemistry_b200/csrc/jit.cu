@@ -588,8 +588,10 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
         if (!jk.fn && !jk.failed) {
             // shape: elements staged per chunk and the launch bounds the register allocation follows
             const int dcap = env_int("TCHEM_JIT_DCAP", std::max(t->cartdim + 1, 76));
-            jk.warps = env_int("TCHEM_JIT_WARPS", 4);
-            jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);      // 2 x 4 warps: the full register file, no spills (measured best)
+            // 8 warps per SM is what the 252-register kernel allows (at 227 registers - 9 warps - it
+            // spills and loses 25 %); as 4 blocks of 2 warps they finish 2 % sooner than as 2 blocks of 4
+            jk.warps = env_int("TCHEM_JIT_WARPS", 2);
+            jk.blocks = env_int("TCHEM_JIT_BLOCKS", 4);
             const std::string src = jit_source(t->terms, t->intdim, t->cartdim, dcap, jk.warps, jk.blocks);
             std::string log;
             std::vector<char> cubin;
