@@ -405,7 +405,8 @@ def main():
                   else "tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
                   else "sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
                   else "dense_kernel" if args.workload in FLOPS
-                  else "tchem_jit_qJ (table-specialised, NVRTC)" if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)
+                  else ("tchem_jit_qJ_bulk (table-specialised, NVRTC, TMA tensor stores)" if os.environ.get("TCHEM_JIT_BULK", "1") != "0" and args.workload == "C2"
+                        else "tchem_jit_qJ (table-specialised, NVRTC)") if what == "q+J" and T._lib.tchem_ic_uses_specialised(ic._handle, B)
                   else "ic_eval_kernel")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload) if B == DEFAULT_BATCH[args.workload] else None, "peak_source": peak_src,

@@ -181,6 +181,10 @@ TCHEM_API int tchem_ic_program_export(const tchem_invdisp_t * terms, int n_terms
  * needed; 0 = compiled, the compiler / ptxas log is copied to `log`). */
 TCHEM_API int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap,
                                       char * buf, int64_t capacity);
+/* the variant whose write-out goes through the TMA unit (cp.async.bulk stores from geometry-major
+ * staging rows; TCHEM_JIT_BULK=0 disables it); 0 when the shape does not give 16-byte aligned pieces */
+TCHEM_API int64_t tchem_ic_jit_source_bulk(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap,
+                                           char * buf, int64_t capacity);
 TCHEM_API int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity);
 /* 1 when a q + J call on B geometries is served by the specialised kernel, 0 = interpreter */
 TCHEM_API int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B);

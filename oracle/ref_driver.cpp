@@ -207,5 +207,17 @@ int ref_sap_jacobian_pow(void * hh, const double * x, int64_t B, double * J) {
         }
     });
 }
+// -> K: [B, nterms, sum(dims), sum(dims)]   (SAPSet::Jacobian2nd_(xs, K), the concatenated symmetric form)
+int ref_sap_jacobian2nd(void * hh, const double * x, int64_t B, double * K) {
+    const SapHandle & h = *static_cast<SapHandle *>(hh);
+    int64_t n = h.set.SAPs().size();
+    return guarded([&]{
+        for (int64_t b = 0; b < B; b++) {
+            at::Tensor Kb;
+            h.set.Jacobian2nd_(split_xs(h, x + b * h.sumdim), Kb);
+            store(K + b * n * h.sumdim * h.sumdim, Kb);
+        }
+    });
+}
 
 } // extern "C"

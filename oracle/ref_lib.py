@@ -48,7 +48,7 @@ def lib():
         L.ref_ic_grad_cart2int_matrix.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _dp]
         L.ref_ic_hess_int2cart.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
         L.ref_ic_hess_cart2int.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
-        for name in ("ref_sap_value", "ref_sap_jacobian", "ref_sap_jacobian_pow"):
+        for name in ("ref_sap_value", "ref_sap_jacobian", "ref_sap_jacobian_pow", "ref_sap_jacobian2nd"):
             getattr(L, name).argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
         L.ref_set_num_threads(1)
         _lib = L
@@ -188,3 +188,10 @@ class RefSAPSet:
         f = lib().ref_sap_jacobian_pow if pow_variant else lib().ref_sap_jacobian
         _check(f(self._h, _p(x), B, _p(J)))
         return J
+
+    def jacobian2nd(self, x):
+        """SAPSet::Jacobian2nd_(xs, K): K[B, nterms, sumdim, sumdim]"""
+        x, B = self._x(x)
+        K = np.empty((B, self.nterms, self.sumdim, self.sumdim))
+        _check(lib().ref_sap_jacobian2nd(self._h, _p(x), B, _p(K)))
+        return K

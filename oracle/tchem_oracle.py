@@ -638,3 +638,34 @@ class SAPSet:
                         val = val * np.power(x[:, self.offsets[v[0]] + v[1]], uniq[v])
                 J[:, i, col] = val
         return J
+
+    def jacobian2nd(self, x):
+        """Concatenated Jacobian2nd_(xs, K) (SAPSet.cpp:243-276): K[b, i] = symmetric Hessian of monomial i.
+        Per monomial (SAP.cpp:226-263): diagonal p(p-1) x^(p-2) prod_{others} x_v^{p_v} (0 when p < 2),
+        off-diagonal p_u p_v x_u^(p_u-1) x_v^(p_v-1) prod_{others}; distinct coordinates in ascending
+        (irreducible, index) order = uniques_orders_, the other factors multiplied in that order;
+        upper triangle mirrored into the lower one (SAPSet.cpp:271-274)."""
+        x = self._x(x)
+        K = np.zeros((x.shape[0], self.nterms, self.sumdim, self.sumdim))
+        for i, coords in enumerate(self.saps):
+            uniq = {}
+            for c in coords:
+                uniq[c] = uniq.get(c, 0) + 1
+            keys = sorted(uniq)
+            col = {u: self.offsets[u[0]] + u[1] for u in keys}
+            for a, u in enumerate(keys):
+                p = uniq[u]
+                if p >= 2:
+                    val = (p * (p - 1)) * np.power(x[:, col[u]], p - 2)
+                    for v in keys:
+                        if v != u:
+                            val = val * np.power(x[:, col[v]], uniq[v])
+                    K[:, i, col[u], col[u]] = val
+                for v in keys[a + 1:]:
+                    val = (p * uniq[v]) * np.power(x[:, col[u]], p - 1) * np.power(x[:, col[v]], uniq[v] - 1)
+                    for w in keys:
+                        if w != u and w != v:
+                            val = val * np.power(x[:, col[w]], uniq[w])
+                    K[:, i, col[u], col[v]] = val
+                    K[:, i, col[v], col[u]] = val
+        return K

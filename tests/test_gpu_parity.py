@@ -451,6 +451,22 @@ def test_specialised_kernel_matches_interpreter_and_oracle(T):
         assert n % 32 != 0
 
 
+def test_specialised_kernel_bulk_store_variant(T):
+    """The specialised q + J kernel hands its tiles to the TMA unit (cp.async.bulk stores) by default;
+    TCHEM_JIT_BULK=0 keeps the warp copy-out. Both must write the same bytes (and agree with the
+    oracle) on even / odd cartdim and even / odd row counts; knobs are per process -> subprocesses."""
+    import subprocess, sys
+    digests = []
+    for bulk in ("1", "0"):
+        e = dict(os.environ)
+        e["TCHEM_JIT_BULK"] = bulk
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_bulk_check.py")],
+                             env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "DIGEST" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        digests.append(out.stdout.strip().split()[-1])
+    assert digests[0] == digests[1]
+
+
 def test_mid_size_odd_stride_chain13(T):
     """13-atom chain with out-of-plane rows: cartdim 39, 33 coordinates -> the J block of a geometry is
     1287 doubles (odd), so every other geometry is only 8-byte aligned: the warp-group kernel's line

@@ -86,6 +86,37 @@ __global__ void k_gmajor(double * out, long ntiles, int gdoubles, int piece) {
         }
     }
 }
+
+// bulk (TMA) stores: every lane owns one geometry of the tile and issues one
+// cp.async.bulk.global.shared::cta of the piece (rows * cartdim doubles) from the warp's shared
+// staging rows; REFILL = the warp rewrites the staging rows (16-byte shared stores) before every piece
+template <bool REFILL>
+__global__ void k_bulk(double * out, long ntiles, int gdoubles, int piece, int pitch_doubles) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double * S = sm + (size_t)warp * 32 * pitch_doubles;
+    for (int e = 0; e < piece; e++) S[lane * pitch_doubles + e] = 1.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long w = (long)blockIdx.x * (blockDim.x >> 5) + warp, nw = (long)gridDim.x * (blockDim.x >> 5);
+    const unsigned src = (unsigned)__cvta_generic_to_shared(S + lane * pitch_doubles);
+    for (long t = w; t < ntiles; t += nw) {
+        double * base = out + t * 32L * gdoubles + (long)lane * gdoubles;
+        for (int r0 = 0; r0 < gdoubles; r0 += piece) {
+            const int len = min(piece, gdoubles - r0);
+            if (REFILL) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                for (int e = 0; e < len; e += 2) *reinterpret_cast<double2 *>(S + lane * pitch_doubles + e) = make_double2(1.0, (double)r0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            }
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + r0), "r"(src), "r"(len * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 int main(int argc, char ** argv) {
     const int cartdim = atoi(argv[1]), intdim = atoi(argv[2]);
     const long B = atol(argv[3]);
@@ -127,6 +158,22 @@ int main(int argc, char ** argv) {
         run(name, [&] { k_gmajor<1><<<148, wps * 32>>>(out, ntiles, gdoubles, rows * cartdim); });
         snprintf(name, 64, "gmajor16 rows=%d", rows);
         run(name, [&] { k_gmajor<2><<<148, wps * 32>>>(out, ntiles, gdoubles, rows * cartdim); });
+    }
+
+    for (int rows : {1, 2, 4, 16}) {
+        if (rows > intdim) continue;
+        const int piece = rows * cartdim;
+        if (piece % 2) continue;
+        int pitch = piece + 2;
+        if ((pitch / 2) % 2 == 0) pitch += 2;       // pitch / 16 B odd: conflict-free 16-byte staging stores
+        const size_t smem = (size_t)wps * 32 * pitch * 8;
+        if (smem > 220 * 1024) continue;
+        cudaFuncSetAttribute(k_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        char name[64]; snprintf(name, 64, "bulk rows=%d (%d B)", rows, piece * 8);
+        run(name, [&] { k_bulk<false><<<148, wps * 32, smem>>>(out, ntiles, gdoubles, piece, pitch); });
+        snprintf(name, 64, "bulk+refill rows=%d", rows);
+        run(name, [&] { k_bulk<true><<<148, wps * 32, smem>>>(out, ntiles, gdoubles, piece, pitch); });
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;

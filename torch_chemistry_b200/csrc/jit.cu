@@ -12,6 +12,7 @@
 // with prefetch of the next tile, dense row chunks staged [element][lane] in shared memory and
 // written out transposed (coalesced 256-byte segments). Replaces IntCoordSet::compute_IC_J
 // (reference source/IC/IntCoordSet.cpp:147-159) for tables without the 5-atom torsion2 family.
+#include <cuda.h>          // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -147,6 +148,13 @@ __device__ __forceinline__ void copy_out(const double * D, double * __restrict__
         g += DG; k += DK;
         if (k >= SPAN) { k -= SPAN; g++; }
     }
+}
+// tensor map (CUtensorMap, 128 opaque bytes) of the bulk-store variant
+struct __align__(64) TMap { unsigned long long opaque[16]; };
+// 16-byte store at byte offset `off` of a box laid out with the TMA unit's 64B swizzle
+// (16-byte unit index bits 0-1 ^= address bits 7-8)
+__device__ __forceinline__ void stage_pair(char * box, int off, double a, double b) {
+    *reinterpret_cast<double2 *>(box + (off ^ (((off >> 7) & 3) << 4))) = make_double2(a, b);
 }
 // q rows of a chunk, (geometry, row)-flattened
 template <int NROWS, int GSTRIDE>
@@ -331,7 +339,31 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
 
 // The CUDA C++ source of the specialised kernel for this table; `dcap` = dense elements staged
 // per chunk. Empty string when the table is not eligible.
-std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int dcap, int warps, int blocks) {
+// `bulk`: the write-out goes through the TMA unit. The chunk is staged geometry-major in shared
+// memory as the dense box [32 geometries][piece / 8][8 doubles] a tiled tensor map describes
+// (J seen as a 3-D tensor: 64-byte groups x groups per geometry x B), each lane storing its own
+// geometry with 16-byte shared stores at the 64B-swizzled address (conflict-free: the row pitch is a
+// multiple of 64 bytes, the swizzle spreads the 8 lanes of a quarter-warp over the 8 bank groups),
+// and ONE lane issues one cp.async.bulk.tensor store per chunk (q rows: a second, 2-D map). The
+// warp copy-out it replaces was 36 % of the kernel's instructions. (Per-lane 1-D bulk copies were
+// tried first: UBLKCP takes uniform-register operands, so the compiler serialises the 32 lanes -
+// ~330 instructions per copy - and nothing is gained.) Rows of a ragged tail tile lie outside the
+// tensor and are clipped by the TMA unit. Shapes: the piece and the geometry must be whole 64-byte
+// groups, chunks of equal even row count.
+bool jit_bulk_eligible(int n_ic, int cartdim, int dcap) {
+    if (cartdim > dcap) return false;
+    const int rows_per = std::min(n_ic, std::max(1, dcap / (cartdim + 1)));
+    return rows_per % 2 == 0 && n_ic % rows_per == 0 && (rows_per * cartdim) % 8 == 0 && rows_per * cartdim / 8 <= 256;
+}
+// per-warp shared memory of the bulk variant: [J box][q box][R], every part a multiple of 512 bytes
+size_t jit_bulk_warp_bytes(int n_ic, int cartdim, int dcap) {
+    const int rows_per = std::min(n_ic, std::max(1, dcap / (cartdim + 1)));
+    auto up = [](size_t v) { return (v + 511) & ~(size_t)511; };
+    return up((size_t)32 * rows_per * cartdim * 8) + up((size_t)32 * rows_per * 8) + up((size_t)cartdim * 33 * 8);
+}
+
+std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int dcap, int warps, int blocks, bool bulk = false) {
+    if (bulk && !jit_bulk_eligible(n_ic, cartdim, dcap)) return std::string();
     typedef std::tuple<int, int, int, int, int, int, double> Key;
     std::map<Key, int> index;
     std::vector<JitPrim> prims;
@@ -363,13 +395,29 @@ std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int
 
     std::ostringstream o;
     o << "#define CD " << cartdim << "\n#define NIC " << n_ic << "\n#define DCAP " << rows_per * (cartdim + 1) << "\n";
+    if (bulk) {
+        auto up = [](size_t v) { return (v + 511) & ~(size_t)511; };
+        o << "#define PIECEB " << rows_per * cartdim * 8 << "\n#define QB " << rows_per * 8
+          << "\n#define JBOX " << up((size_t)32 * rows_per * cartdim * 8) << "\n#define QBOX " << up((size_t)32 * rows_per * 8)
+          << "\n#define WARPB " << jit_bulk_warp_bytes(n_ic, cartdim, dcap) << "\n";
+    }
     o << kPrelude;
     o << "extern \"C\" __global__ void __launch_bounds__(" << warps * 32 << ", " << blocks << ")\n"
-      << "tchem_jit_qJ(const double * __restrict__ r, const long long B, double * __restrict__ q, double * __restrict__ J) {\n"
+      << (bulk ? "tchem_jit_qJ_bulk" : "tchem_jit_qJ") << "(const double * __restrict__ r, const long long B, double * __restrict__ q, double * __restrict__ J"
+      << (bulk ? ", const __grid_constant__ TMap tmJ, const __grid_constant__ TMap tmq" : "") << ") {\n"
       << "    extern __shared__ __align__(16) double smem[];\n"
-      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n"
-      << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
-      << "    double * D = R + CD * KPAD;\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n";
+    if (bulk)
+        o << "    // swizzle patterns follow shared-memory address bits: the boxes start on 1024-byte boundaries\n"
+          << "    char * Sbox = reinterpret_cast<char *>(smem) + ((1024 - ((uint32_t)__cvta_generic_to_shared(smem) & 1023)) & 1023) + (size_t)warp * WARPB;\n"
+          << "    char * Qbox = Sbox + JBOX;\n"
+          << "    double * R = reinterpret_cast<double *>(Qbox + QBOX);\n"
+          << "    const uint32_t S_sh = (uint32_t)__cvta_generic_to_shared(Sbox), Q_sh = (uint32_t)__cvta_generic_to_shared(Qbox);\n"
+          << "    double * Qrow = reinterpret_cast<double *>(Qbox + lane * QB);\n";
+    else
+        o << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
+          << "    double * D = R + CD * KPAD;\n";
+    o
       << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
       << "    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;\n"
       << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue(r, b0, (int)min((int64_t)LANES, B - b0), R, lane); }\n"
@@ -415,6 +463,7 @@ std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int
             o << " }\n";
         }
         // dense elements of the chunk: [row - r0][col] then the q rows
+        std::vector<std::string> bulk_J, bulk_qv;      // bulk: the chunk's expressions in output order
         for (int i = r0; i < r1; i++) {
             std::vector<std::string> expr(cartdim);
             for (auto & t : rows[i]) {
@@ -428,21 +477,47 @@ std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int
                                                       + "]." + std::string(1, "xyz"[c]) + ", " + e + ")";
                     }
             }
-            for (int c = 0; c < cartdim; c++)
-                o << "            D[" << stage_row((i - r0) * cartdim + c, nrows * cartdim) << " * KPAD + lane] = " << (expr[c].empty() ? "0.0" : expr[c]) << ";\n";
             std::string qe;
             for (auto & t : rows[i]) {
                 const std::string term = hexd(t.first) + " * q" + std::to_string(t.second);
                 qe = qe.empty() ? term : "fma(" + hexd(t.first) + ", q" + std::to_string(t.second) + ", " + qe + ")";
             }
+            if (bulk) {
+                for (int c = 0; c < cartdim; c++) bulk_J.push_back(expr[c].empty() ? "0.0" : expr[c]);
+                bulk_qv.push_back(qe);
+                continue;
+            }
+            for (int c = 0; c < cartdim; c++)
+                o << "            D[" << stage_row((i - r0) * cartdim + c, nrows * cartdim) << " * KPAD + lane] = " << (expr[c].empty() ? "0.0" : expr[c]) << ";\n";
             o << "            D[" << nrows * cartdim + (i - r0) << " * KPAD + lane] = " << qe << ";\n";
+        }
+        if (bulk) {
+            // the previous chunk's stores have read the boxes
+            o << "            if (lane == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
+              << "            __syncwarp();\n";
+            for (size_t e = 0; e + 1 < bulk_J.size(); e += 2)
+                o << "            stage_pair(Sbox, lane * PIECEB + " << e * 8 << ", " << bulk_J[e] << ", " << bulk_J[e + 1] << ");\n";
+            for (size_t e = 0; e + 1 < bulk_qv.size(); e += 2)
+                o << "            *reinterpret_cast<double2 *>(Qrow + " << e << ") = make_double2(" << bulk_qv[e] << ", " << bulk_qv[e + 1] << ");\n";
+            o << "            asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+              << "            __syncwarp();\n"
+              << "            if (lane == 0) {\n"
+              << "                if (J) asm volatile(\"cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\" ::\"l\"(&tmJ), \"r\"(0), \"r\"("
+              << r0 * cartdim / 8 << "), \"r\"((int)b0), \"r\"(S_sh) : \"memory\");\n"
+              << "                if (q) asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\" ::\"l\"(&tmq), \"r\"("
+              << r0 << "), \"r\"((int)b0), \"r\"(Q_sh) : \"memory\");\n"
+              << "                asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n"
+              << "            }\n        }\n";
+            continue;
         }
         o << "            __syncwarp();\n"
           << "            if (J) copy_out<" << nrows * cartdim << ", NIC * CD>(D, J + b0 * (NIC * CD) + " << r0 * cartdim << ", ntile, lane);\n"
           << "            if (q) copy_rows<" << nrows << ", NIC>(D + " << nrows * cartdim << " * KPAD, q + b0 * NIC + " << r0 << ", ntile, lane);\n"
           << "            __syncwarp();\n        }\n";
     }
-    o << "    }\n}\n";
+    o << "    }\n";
+    if (bulk) o << "    if (lane == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n";
+    o << "}\n";
     return o.str();
 }
 
@@ -481,9 +556,30 @@ struct JitKernel {
 };
 
 namespace {
-std::map<const tchem_ic_table *, JitKernel> & jit_kernels() { static std::map<const tchem_ic_table *, JitKernel> m; return m; }
+// (table, variant): 0 = warp copy-out, 1 = bulk (TMA) stores
+typedef std::pair<const tchem_ic_table *, int> JitKey;
+std::map<JitKey, JitKernel> & jit_kernels() { static std::map<JitKey, JitKernel> m; return m; }
 std::mutex & jit_mutex() { static std::mutex m; return m; }
 int env_int(const char * name, int dflt) { const char * v = getenv(name); return v ? atoi(v) : dflt; }
+}
+
+namespace {
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda); nullptr when the driver has none
+typedef CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeTiled tensor_map_encoder() {
+    static const TensorMapEncodeTiled fn = [] {
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &res) != cudaSuccess || res != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<TensorMapEncodeTiled>(p);
+    }();
+    return fn;
+}
 }
 
 namespace {
@@ -495,8 +591,10 @@ std::map<std::pair<const tchem_sap_table *, const tchem_ic_table *>, JitKernel> 
 
 void release_jit(const tchem_ic_table * t) {
     std::lock_guard<std::mutex> lock(jit_mutex());
-    auto it = jit_kernels().find(t);
-    if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
+    for (int variant = 0; variant < 2; variant++) {
+        auto it = jit_kernels().find({t, variant});
+        if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
+    }
     for (auto c = chain_kernels().begin(); c != chain_kernels().end();) {
         if (c->first.second == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
         else ++c;
@@ -580,49 +678,60 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
     // (measured: wins for small molecules - C2H4: 0.42 vs 0.64 ms - and loses beyond ~12 atoms, where dense
     // row staging is mostly zeros and the interpreter's compact staging is the better scheme)
     if (!enabled || std::max(B, g_batch_hint) < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128) return -1;
-    JitKernel * k;
-    {
+    static const int want_bulk = env_int("TCHEM_JIT_BULK", 1);
+    const int dcap = env_int("TCHEM_JIT_DCAP", std::max(t->cartdim + 1, 76));
+    // the TMA write-out needs 16-byte aligned results, whole 64-byte groups and 32-bit tile coordinates
+    int variant = want_bulk && jit_bulk_eligible(t->intdim, t->cartdim, dcap) && B < ((int64_t)1 << 31) && tensor_map_encoder()
+                  && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 1 : 0;
+    JitKernel * k = nullptr;
+    for (; variant >= 0 && !k; variant--) {
         std::lock_guard<std::mutex> lock(jit_mutex());
-        JitKernel & jk = jit_kernels()[t];
-        k = &jk;
+        JitKernel & jk = jit_kernels()[{t, variant}];
         if (!jk.fn && !jk.failed) {
-            // shape: elements staged per chunk and the launch bounds the register allocation follows
-            const int dcap = env_int("TCHEM_JIT_DCAP", std::max(t->cartdim + 1, 76));
-            // 8 warps per SM is what the 252-register kernel allows (at 227 registers - 9 warps - it
+            // 8 warps per SM is what the ~250-register kernel allows (at 227 registers - 9 warps - it
             // spills and loses 25 %); as 4 blocks of 2 warps they finish 2 % sooner than as 2 blocks of 4
             jk.warps = env_int("TCHEM_JIT_WARPS", 2);
             jk.blocks = env_int("TCHEM_JIT_BLOCKS", 4);
-            const std::string src = jit_source(t->terms, t->intdim, t->cartdim, dcap, jk.warps, jk.blocks);
-            std::string log;
-            std::vector<char> cubin;
-            if (!src.empty()) cubin = jit_compile(src, log, debug);
-            if (debug) fprintf(stderr, "[tchem] jit: %zu bytes of source, %zu bytes of cubin\n%s\n", src.size(), cubin.size(), log.c_str());
-            if (cubin.empty()) jk.failed = true;
-            else if (cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess
-                     || cudaLibraryGetKernel(&jk.fn, jk.lib, "tchem_jit_qJ") != cudaSuccess) {
-                cudaGetLastError();
-                jk.failed = true;
-            } else {
-                const int rows_per = std::max(1, dcap / (t->cartdim + 1));
-                jk.smem = (size_t)jk.warps * (t->cartdim + rows_per * (t->cartdim + 1)) * 33 * sizeof(double);
-                if (jk.smem > (size_t)t->max_smem_optin
-                    || cudaFuncSetAttribute((const void *)jk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jk.smem) != cudaSuccess
-                    || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jk.per_sm, (const void *)jk.fn, jk.warps * 32, jk.smem) != cudaSuccess
-                    || jk.per_sm < 1) {
-                    cudaGetLastError();
-                    jk.failed = true;
-                }
-            }
-            if (debug) fprintf(stderr, "[tchem] jit: %s, %d warps/block, %d blocks/SM, %zu B smem\n", jk.failed ? "FAILED (interpreter serves this table)" : "ok",
-                               jk.warps, jk.per_sm, jk.smem);
+            const std::string src = jit_source(t->terms, t->intdim, t->cartdim, dcap, jk.warps, jk.blocks, variant == 1);
+            const int rows_per = std::max(1, dcap / (t->cartdim + 1));
+            size_t smem = (size_t)jk.warps * (t->cartdim + rows_per * (t->cartdim + 1)) * 33 * sizeof(double);
+            if (variant == 1) smem = 1024 + (size_t)jk.warps * jit_bulk_warp_bytes(t->intdim, t->cartdim, dcap);
+            jit_finish(jk, src, variant == 1 ? "tchem_jit_qJ_bulk" : "tchem_jit_qJ", smem, t->max_smem_optin, debug);
         }
-        if (jk.failed) return -1;
+        if (!jk.failed) { k = &jk; break; }
     }
+    if (!k) return -1;
     const int64_t ntiles = (B + 31) / 32;
     const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
     long long Bll = B;
-    void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J};
-    TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    if (variant == 1) {
+        // J as [B][intdim * cartdim / 8][8 doubles] with the 64B swizzle, q as [B][intdim]; boxes = one chunk of one tile
+        const int rows_per = std::min(t->intdim, std::max(1, dcap / (t->cartdim + 1)));
+        const uint64_t G = (uint64_t)t->intdim * t->cartdim;
+        CUtensorMap tmJ, tmq;
+        std::memset(&tmJ, 0, sizeof(tmJ));
+        std::memset(&tmq, 0, sizeof(tmq));
+        const cuuint32_t ones[3] = {1, 1, 1};
+        if (J) {
+            const cuuint64_t dims[3] = {8, G / 8, (cuuint64_t)B}, strides[2] = {64, G * 8};
+            const cuuint32_t box[3] = {8, (cuuint32_t)(rows_per * t->cartdim / 8), 32};
+            if (tensor_map_encoder()(&tmJ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, J, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return set_error(TCHEM_ECUDA, "tchem_ic_eval: cuTensorMapEncodeTiled(J) failed");
+        }
+        if (q) {
+            const cuuint64_t dims[2] = {(cuuint64_t)t->intdim, (cuuint64_t)B}, strides[1] = {(cuuint64_t)t->intdim * 8};
+            const cuuint32_t box[2] = {(cuuint32_t)rows_per, 32};
+            if (tensor_map_encoder()(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, q, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return set_error(TCHEM_ECUDA, "tchem_ic_eval: cuTensorMapEncodeTiled(q) failed");
+        }
+        void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J, (void *)&tmJ, (void *)&tmq};
+        TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    } else {
+        void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J};
+        TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    }
     count_launch();
     return TCHEM_OK;
 }
@@ -647,12 +756,25 @@ int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic
     return (int64_t)s.size() + (s.empty() ? 0 : 1);
 }
 
+// same for the bulk-store (TMA write-out) variant of the kernel; 0 when the shape is not eligible
+int64_t tchem_ic_jit_source_bulk(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap, char * buf, int64_t capacity) {
+    if (!terms || n_terms <= 0) return 0;
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    const std::string s = jit_source(v, n_ic, cartdim, dcap > 0 ? dcap : std::max(cartdim + 1, 76), 2, 4, true);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
 // 1 when tchem_ic_eval(J != NULL, K == NULL) on a batch of B geometries runs the specialised kernel
 int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
     if (!t || !enabled || B < min_batch || t->has5 || t->cartdim > 36 || t->terms.size() > 128) return 0;
     std::lock_guard<std::mutex> lock(jit_mutex());
-    auto it = jit_kernels().find(t);
+    auto it = jit_kernels().find({t, 0});
     return it == jit_kernels().end() || !it->second.failed ? 1 : 0;
 }
 
