@@ -37,9 +37,10 @@ WORKLOADS = {
     "C4Hc": ("Hessian_cart2int", lambda cd, n, ns: 8 * (cd + cd + cd * cd + n * n)),
     "C5": ("q->SAPSet value+Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * n)),
     "C5x": ("SAPSet value+Jacobian on given coordinates", lambda cd, n, ns: 8 * (n + ns + ns * n)),
+    "C5K": ("SAPSet Jacobian2nd on given coordinates", lambda cd, n, ns: 8 * (n + ns * n * n)),
 }
 DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 8192, "C4J": 5 * 10 ** 4, "C4g": 10 ** 5, "C4gc": 10 ** 5, "C4H": 10 ** 5,
-                 "C4Hc": 10 ** 5, "C5": 12500000, "C5x": 12500000}
+                 "C4Hc": 10 ** 5, "C5": 12500000, "C5x": 12500000, "C5K": 12500000}
 # dense flops per geometry of the contraction-bound transforms
 FLOPS = {
     "C4H": lambda cd, n: 2 * n * n * cd + 2 * cd * n * cd + 2 * n * cd * cd,
@@ -145,14 +146,14 @@ def _cpu_init(kind, ic_text, what, sap_text, sap_dims):
             f.write(ic_text)
         s = ref_lib.RefIntCoordSet("default", f.name)
         sap = None
-        if what.startswith("q->SAP"):
+        if "SAP" in what:
             with tempfile.NamedTemporaryFile("w", suffix=".in", delete=False) as f2:
                 f2.write(sap_text)
             sap = ref_lib.RefSAPSet(f2.name, 0, sap_dims)
     else:
         from oracle import tchem_oracle as O
         s = O.IntCoordSet("default", ic_text)
-        sap = O.SAPSet(sap_text, 0, sap_dims) if what.startswith("q->SAP") else None
+        sap = O.SAPSet(sap_text, 0, sap_dims) if "SAP" in what else None
     _WORKER.update(s=s, sap=sap, what=what)
 
 
@@ -172,6 +173,14 @@ def _cpu_worker(r):
         s.Hessian_int2cart(r, np.ones((r.shape[0], s.intdim)), np.tile(np.eye(s.intdim), (r.shape[0], 1, 1)))
     elif what == "Hessian_cart2int":
         s.Hessian_cart2int(r, np.ones((r.shape[0], r.shape[1])), np.tile(np.eye(r.shape[1]), (r.shape[0], 1, 1)))
+    elif what.startswith("SAPSet"):
+        q = s.qJ(r)[0]
+        t0 = _t.perf_counter()                 # the coordinates are the caller's: only the SAPSet call is timed
+        if "Jacobian2nd" in what:
+            sap.jacobian2nd(q)
+        else:
+            sap.value(q)
+            sap.jacobian(q)
     else:
         q = s.qJ(r)[0]
         sap.value(q)
@@ -203,7 +212,9 @@ class CpuBaseline:
         t0 = time.perf_counter()
         times = self.pool.map(_cpu_worker, jobs, chunksize=1)
         wall = time.perf_counter() - t0
-        return {"value": per_core * self.cores / wall, "unit": "geometries/s", "cores": self.cores, "kind": self.kind,
+        # SAPSet on given coordinates: the workers time the SAPSet call alone (the coordinates are the caller's)
+        span = max(times) if self.what.startswith("SAPSet") else wall
+        return {"value": per_core * self.cores / span, "unit": "geometries/s", "cores": self.cores, "kind": self.kind,
                 "sample": "%d geometries (%d per process, %d single-threaded processes), %s; wall %.2f s, slowest process %.2f s"
                           % (per_core * self.cores, per_core, self.cores, self.what, wall, max(times))}
 
@@ -222,7 +233,7 @@ def cpu_baseline(w, what, per_core, cores=None):
 
 def per_core_sample(key):
     # sized for roughly 10-20 s of CPU work per process with the reference's measured per-geometry cost
-    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000, "C5x": 20000}[key]
+    return {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16, "C5": 20000, "C5x": 20000, "C5K": 20000}[key]
 
 
 # ------------------------------------------------------------------------------------------
@@ -269,7 +280,7 @@ def main():
     wl = importlib.util.module_from_spec(spec)
     sys.modules["_wl"] = wl
     spec.loader.exec_module(wl)
-    wkey = {"C3K": "C3", "C5x": "C5", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
+    wkey = {"C3K": "C3", "C5x": "C5", "C5K": "C5", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}.get(args.workload, args.workload)
     w = wl.get(wkey)
     what, bytes_fn = WORKLOADS[args.workload]
     B = args.batch or DEFAULT_BATCH[args.workload]
@@ -331,6 +342,12 @@ def main():
         step = lambda: ic.Hessian_int2cart(r_dev, gq_dev, Hq_dev)
     elif what == "Hessian_cart2int":
         step = lambda: ic.Hessian_cart2int(r_dev, gr_dev, Hr_dev)
+    elif args.workload == "C5K":
+        import ctypes as C
+        x_dev = ic(r_dev).contiguous()
+        K2 = torch.empty(B, ns, n, n, **f64)
+        step = lambda: T._capi.check(T._lib.tchem_sap_jacobian2nd(sap._handle, C.c_void_p(x_dev.data_ptr()), B, C.c_void_p(K2.data_ptr()),
+                                                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
     elif args.workload == "C5x":
         x_dev = ic(r_dev).contiguous()                      # the coordinates a caller would bring
         souts = sap.eval_cat(x_dev)
@@ -372,7 +389,7 @@ def main():
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
     e2e = None
-    if not args.no_e2e and args.workload != "C5x" and (what in ("q+J", "q+J+K") or sap is not None):
+    if not args.no_e2e and args.workload not in ("C5x", "C5K") and (what in ("q+J", "q+J+K") or sap is not None):
         pin = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
         if sap is not None:
             houts = [pin(B, ns), pin(B, ns, n)]
@@ -401,7 +418,7 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
-        kernel = ("tchem_jit_chain (SAPSet-specialised, NVRTC)" if args.workload == "C5x" and T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, B)
+        kernel = ("sap_hess_kernel" if args.workload == "C5K" else "tchem_jit_chain (SAPSet-specialised, NVRTC)" if args.workload == "C5x" and T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, B)
                   else "tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
                   else "sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
                   else "dense_kernel" if args.workload in FLOPS

@@ -572,6 +572,53 @@ std::vector<at::Tensor> SAPSet::Jacobian_(const std::vector<at::Tensor> & xs) co
 }
 std::vector<at::Tensor> SAPSet::Jacobian(const std::vector<at::Tensor> & xs) const { return Jacobian_(xs); }
 
+// second-order Jacobian (source/polynomial/SAPSet.cpp:203-276): one launch fills the concatenated
+// symmetric K; the blocks are views of it
+CL::utility::matrix<at::Tensor> SAPSet::Jacobian2nd_(const std::vector<at::Tensor> & xs, at::Tensor & K) const {
+    const std::string who = "tchem::polynomial::SAPSet::Jacobian2nd_";
+    for (const at::Tensor & x : xs) if (x.dim() != 1 && x.dim() != 2) throw std::invalid_argument(who + ": x must be a vector");
+    if (xs.size() != dimensions_.size()) throw std::invalid_argument(
+        who + ": x must share a same number of irreducibles as the coordinate system");
+    for (size_t i = 0; i < xs.size(); i++) if (xs[i].size(-1) != (int64_t)dimensions_[i]) throw std::invalid_argument(
+        who + ": x must have a same dimension as the coordinates");
+    const bool batched = xs[0].dim() == 2, host = !xs[0].is_cuda();
+    const int device = host ? default_device() : xs[0].get_device();
+    std::vector<at::Tensor> parts;
+    for (const at::Tensor & x : xs) parts.push_back(batched ? x : x.unsqueeze(0));
+    at::Tensor x = on_device_cat(parts, device);
+    const int64_t B = x.size(0), nsap = SAPs_.size(), sumdim = x.size(1);
+    c10::cuda::CUDAGuard guard(device);
+    at::Tensor Kd = at::empty({B, nsap, sumdim, sumdim}, x.options());
+    if (B > 0) check(tchem_sap_jacobian2nd(compiled(device).get(device), (const double *)ptr(x), B, (double *)ptr(Kd),
+                                           c10::cuda::getCurrentCUDAStream(device).stream()));
+    if (host) Kd = Kd.cpu();
+    K = unbatch(Kd, batched);
+    CL::utility::matrix<at::Tensor> Ks(xs.size());
+    int64_t start_row = 0;
+    for (size_t i = 0; i < xs.size(); i++) {
+        const int64_t stop_row = start_row + (int64_t)dimensions_[i];
+        int64_t start_col = start_row;
+        for (size_t j = i; j < xs.size(); j++) {
+            const int64_t stop_col = start_col + (int64_t)dimensions_[j];
+            Ks[i][j] = K.slice(-2, start_row, stop_row).slice(-1, start_col, stop_col);
+            start_col = stop_col;
+        }
+        start_row = stop_row;
+    }
+    return Ks;
+}
+// without `K` the reference fills the upper triangle only (SAP.cpp:213-263 never writes the strict
+// lower triangle of a diagonal block)
+CL::utility::matrix<at::Tensor> SAPSet::Jacobian2nd_(const std::vector<at::Tensor> & xs) const {
+    at::Tensor K;
+    CL::utility::matrix<at::Tensor> Ks = Jacobian2nd_(xs, K);
+    for (size_t i = 0; i < xs.size(); i++)
+    for (size_t j = i; j < xs.size(); j++)
+    Ks[i][j] = i == j ? at::triu(Ks[i][j]) : Ks[i][j].contiguous();
+    return Ks;
+}
+CL::utility::matrix<at::Tensor> SAPSet::Jacobian2nd(const std::vector<at::Tensor> & xs) const { return Jacobian2nd_(xs); }
+
 std::tuple<at::Tensor, at::Tensor, at::Tensor> SAPSet::chained(const tchem::IC::IntCoordSet & set, const at::Tensor & r) const {
     const std::string who = "tchem::polynomial::SAPSet::chained";
     Batch rb = as_batch(r, who, "r");

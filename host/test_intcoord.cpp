@@ -141,6 +141,23 @@ int main(int argc, char ** argv) {
         jerr += std::abs((set1[k](xs) - answer1[k]).item<double>());
     }
     report("the three Jacobian variants and SAP::gradient agree", jerr, 1e-13);
+    // second-order Jacobian: the three variants agree, K is symmetric and matches central differences of Jacobian_
+    at::Tensor cat_K;
+    auto Ka = set1.Jacobian2nd(xs), Kb = set1.Jacobian2nd_(xs), Kcat = set1.Jacobian2nd_(xs, cat_K);
+    double kerr = maxabs(cat_K - cat_K.transpose(-1, -2));
+    kerr += maxabs(Ka[0][1] - Kcat[0][1]) + maxabs(Kb[0][0] - at::triu(Kcat[0][0])) + maxabs(Kb[1][1] - at::triu(Kcat[1][1]));
+    report("the three Jacobian2nd variants agree, K symmetric", kerr, 1e-13);
+    at::Tensor xcat = at::cat(xs);
+    double fderr = 0.0;
+    for (int64_t c = 0; c < 4; c++) {
+        at::Tensor xp = xcat.clone(), xm = xcat.clone();
+        xp[c] += 1e-5; xm[c] -= 1e-5;
+        at::Tensor Jp, Jm;
+        set1.Jacobian_({xp.slice(0, 0, 2), xp.slice(0, 2, 4)}, Jp);
+        set1.Jacobian_({xm.slice(0, 0, 2), xm.slice(0, 2, 4)}, Jm);
+        fderr = std::max(fderr, maxabs((Jp - Jm) / 2e-5 - cat_K.select(-1, c)));
+    }
+    report("Jacobian2nd_ = d Jacobian_ / dx (central differences)", fderr, 1e-6);
     report("constant term only in the totally symmetric irreducible",
            throws<std::invalid_argument>([&] { tchem::polynomial::SAPSet bad(dir + "sap1.in", 1, {2, 2}); }) ? 0 : 1, 0);
 

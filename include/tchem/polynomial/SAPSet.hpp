@@ -1,7 +1,7 @@
 // tchem::polynomial::SAPSet - drop-in for include/tchem/polynomial/SAPSet.hpp of Torch-Chemistry:
-// construction from a term file, value and the three Jacobian variants, evaluated by the CUDA
-// library (batched: xs[i] may be [B][dim_i]). Jacobian2nd / rotation / translation are set-up
-// time utilities outside the B200 hot path and are not provided.
+// construction from a term file, value, the three Jacobian variants and the three second-order
+// Jacobian variants, evaluated by the CUDA library (batched: xs[i] may be [B][dim_i]).
+// rotation / translation are set-up time utilities outside the B200 hot path and are not provided.
 #ifndef tchem_polynomial_SAPSet_hpp
 #define tchem_polynomial_SAPSet_hpp
 
@@ -43,6 +43,12 @@ class SAPSet {
         std::vector<at::Tensor> Jacobian(const std::vector<at::Tensor> & xs) const;
         std::vector<at::Tensor> Jacobian_(const std::vector<at::Tensor> & xs) const;
         std::vector<at::Tensor> Jacobian_(const std::vector<at::Tensor> & xs, at::Tensor & J) const;
+        // dd{P(x)} / dx^2: blocks Ks[i][j] (j >= i) of shape [NSAP][dim_i][dim_j]; the overload with `K`
+        // harvests the concatenated symmetric tensor [NSAP][sumdim][sumdim] the blocks are views of
+        // (reference source/polynomial/SAPSet.cpp:203-276)
+        CL::utility::matrix<at::Tensor> Jacobian2nd(const std::vector<at::Tensor> & xs) const;
+        CL::utility::matrix<at::Tensor> Jacobian2nd_(const std::vector<at::Tensor> & xs) const;
+        CL::utility::matrix<at::Tensor> Jacobian2nd_(const std::vector<at::Tensor> & xs, at::Tensor & K) const;
 
         // chained path (not in the reference, where callers slice q by hand): r -> q by the
         // compute_IC_J formulas -> xs = q split by dimensions_ -> value and concatenated Jacobian

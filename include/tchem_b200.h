@@ -152,6 +152,11 @@ TCHEM_API int tchem_ic_factor_status(const tchem_ic_table * t);
  * Either output may be NULL. */
 TCHEM_API int tchem_sap_eval(const tchem_sap_table * t, const double * x, int64_t B,
                    double * y, double * J, tchem_stream_t stream);
+/* Second-order Jacobian of the set, concatenated and symmetric: K[B][nterms][sumdim][sumdim]. Replaces,
+ * batched, SAPSet::Jacobian2nd_(xs, K) (source/polynomial/SAPSet.cpp:243-276; per monomial
+ * SAP::Hessian_, source/polynomial/SAP.cpp:226-263). x[B][sumdim] and K are device pointers. */
+TCHEM_API int tchem_sap_jacobian2nd(const tchem_sap_table * t, const double * x, int64_t B, double * K,
+                                    tchem_stream_t stream);
 /* chained path: r -> q (compute_IC_J formulas) -> xs = q split by `dims` -> SAPSet value and
  * Jacobian, one kernel, q never leaves the chip unless q_out != NULL. Requires
  * intdim == sumdim. Callers of the reference do this by hand (test/normal_mode/main.cpp:56-61). */

@@ -98,7 +98,8 @@ def main():
     for f, irr in (("1.in", 0), ("2.in", 1)):
         sap = ref_lib.RefSAPSet(S + f, irr, [2, 2])
         save("ref_sap_" + f.replace(".in", ""), definition=np.array(open(S + f).read()), irreducible=np.array(irr),
-             dims=np.array([2, 2]), x=x, y=sap.value(x), J=sap.jacobian(x), J_pow=sap.jacobian(x, True))
+             dims=np.array([2, 2]), x=x, y=sap.value(x), J=sap.jacobian(x), J_pow=sap.jacobian(x, True),
+             K2=sap.jacobian2nd(x))
     # BASELINE workloads
     for key, nK, nT in (("C1", 64, 16), ("C2", 48, 8), ("C3", 6, 0), ("C4", 0, 3), ("C5", 32, 0)):
         w = workloads.get(key)
@@ -129,9 +130,27 @@ def main():
                 spath = f.name
             sap = ref_lib.RefSAPSet(spath, 0, w.sap_dims)
             out.update(sap_definition=np.array(w.sap_text), sap_dims=np.array(w.sap_dims),
-                       sap_y=sap.value(out["q"]), sap_J=sap.jacobian(out["q"]))
+                       sap_y=sap.value(out["q"]), sap_J=sap.jacobian(out["q"]), sap_K2=sap.jacobian2nd(out["q"][:64]))
         save("workload_" + key, **out)
 
 
+def add_sap_second_order():
+    """`python make_golden.py sapK2`: adds SAPSet::Jacobian2nd_(xs, K) of the reference to the SAP
+    goldens that already exist (every other array is kept byte for byte)."""
+    for name, xkey, dkey, dimkey, irrkey, kkey, n in (("ref_sap_1", "x", "definition", "dims", "irreducible", "K2", None),
+                                                      ("ref_sap_2", "x", "definition", "dims", "irreducible", "K2", None),
+                                                      ("workload_C5", "q", "sap_definition", "sap_dims", None, "sap_K2", 64)):
+        g = dict(np.load(os.path.join(OUT, name + ".npz"), allow_pickle=True))
+        with tempfile.NamedTemporaryFile("w", suffix=".in", delete=False) as f:
+            f.write(str(g[dkey]))
+            spath = f.name
+        sap = ref_lib.RefSAPSet(spath, int(g[irrkey]) if irrkey else 0, [int(d) for d in g[dimkey]])
+        g[kkey] = sap.jacobian2nd(g[xkey][:n] if n else g[xkey])
+        save(name, **g)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sapK2":
+        add_sap_second_order()
+    else:
+        main()

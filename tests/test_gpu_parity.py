@@ -230,6 +230,50 @@ def test_sap_known_answers_and_goldens(T):
         T.SAPSet.from_text("\n1,1\n", 1, [2])
 
 
+def test_sap_second_order_jacobian(T):
+    """SAPSet::Jacobian2nd_ (source/polynomial/SAPSet.cpp:203-276): reference goldens, the oracle on a
+    ragged seeded batch, block views, 8-byte aligned result, a set whose rows span several chunks."""
+    for name, irr, xk, dk, dimk, kk in (("ref_sap_1", 0, "x", "definition", "dims", "K2"), ("ref_sap_2", 1, "x", "definition", "dims", "K2"),
+                                        ("workload_C5", 0, "q", "sap_definition", "sap_dims", "sap_K2")):
+        g = golden(name)
+        dims = [int(d) for d in g[dimk]]
+        s = T.SAPSet.from_text(str(g[dk]), irr, dims)
+        x = dev(g[xk][:len(g[kk])])
+        xs = list(torch.split(x, dims, dim=1))
+        K = s.Jacobian2nd_cat(xs)
+        assert_parity(host(K), g[kk], name + " Jacobian2nd_")
+        Ks, K2 = s.Jacobian2nd_(xs, with_K=True)
+        assert Ks[0][1].shape == (len(x), s.nterms, dims[0], dims[1]) and Ks[1][0] is None
+        np.testing.assert_array_equal(host(Ks[0][1]), host(K)[..., :dims[0], dims[0]:])
+        Ku = s.Jacobian2nd_(xs)
+        np.testing.assert_array_equal(host(Ku[0][0]), np.triu(host(K)[..., :dims[0], :dims[0]]))
+        # unbatched call keeps the reference's shapes
+        K1 = s.Jacobian2nd_cat([t[0] for t in xs])
+        np.testing.assert_array_equal(host(K1), host(K)[0])
+    w = T.workloads.get("C5")
+    sap, osap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims), O.SAPSet(w.sap_text, 0, w.sap_dims)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((10007, 3)) * 0.7 + 1.0
+    xd = dev(x)
+    K = sap.Jacobian2nd_cat([xd[:, :2], xd[:, 2:]])
+    assert_parity(host(K), osap.jacobian2nd(x), "C5 Jacobian2nd_ vs oracle")
+    buf = torch.zeros(K.numel() + 1, dtype=torch.float64, device="cuda")
+    from torch_chemistry_b200 import _capi
+    import ctypes as C
+    _capi.check(T._lib.tchem_sap_jacobian2nd(sap._handle, C.c_void_p(xd.data_ptr()), len(x), C.c_void_p(buf[1:].data_ptr()), None))
+    np.testing.assert_array_equal(host(buf[1:]).reshape(host(K).shape), host(K))
+    assert float(buf[0]) == 0.0
+    # 12 coordinates, 40 monomials of orders 0-4: 144 elements per monomial, rows cut into 8-row chunks
+    rng = np.random.default_rng(9)
+    lines = [""]
+    for _ in range(39):
+        lines.append("    ".join("1,%d" % (1 + rng.integers(12)) for _ in range(1 + rng.integers(4))))
+    text = "\n".join(lines) + "\n"
+    big, obig = T.SAPSet.from_text(text, 0, [12]), O.SAPSet(text, 0, [12])
+    x = rng.standard_normal((333, 12)) * 0.5 + 1.0
+    assert_parity(host(big.Jacobian2nd_cat([dev(x)])), obig.jacobian2nd(x), "12-coordinate Jacobian2nd_ vs oracle")
+
+
 def test_sap_specialised_on_given_coordinates(T):
     """SAPSet::operator() / Jacobian_ on caller-supplied coordinates: large batches run the NVRTC kernel
     specialised to the set, small ones the interpreter; both against the oracle, ragged batch."""

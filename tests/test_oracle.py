@@ -137,6 +137,25 @@ def test_sap_known_answers():
         assert_parity(s.jacobian(g["x"]), g["J_pow"], name + " Jacobian")
 
 
+def test_sap_second_order_jacobian_goldens():
+    """SAPSet::Jacobian2nd_(xs, K) of the reference (goldens from oracle/_ref) vs the numpy restatement,
+    plus the defining property: K is the derivative of the Jacobian (central differences)."""
+    for name, xk, dk, dimk, kk in (("ref_sap_1", "x", "definition", "dims", "K2"), ("ref_sap_2", "x", "definition", "dims", "K2"),
+                                   ("workload_C5", "q", "sap_definition", "sap_dims", "sap_K2")):
+        g = golden(name)
+        s = O.SAPSet(str(g[dk]), int(g["irreducible"]) if "irreducible" in g.files else 0, list(g[dimk]))
+        x = g[xk][:len(g[kk])]
+        K = s.jacobian2nd(x)
+        assert_parity(K, g[kk], name + " Jacobian2nd_")
+        np.testing.assert_array_equal(K, np.swapaxes(K, -1, -2))
+        h = 1e-5
+        for c in range(s.sumdim):
+            e = np.zeros(s.sumdim)
+            e[c] = h
+            fd = (s.jacobian(x + e) - s.jacobian(x - e)) / (2 * h)
+            assert np.abs(fd - K[..., c]).max() < 1e-6 * max(1.0, np.abs(K).max())
+
+
 def test_sap_constant_term_only_in_totally_symmetric():
     with pytest.raises(ValueError):
         O.SAPSet("\n1,1\n", 1, [2])

@@ -2,7 +2,7 @@
 # every workload once, kernel numbers only (no CPU baseline / e2e): one JSON line per workload
 mkdir -p gpurun_out
 : > gpurun_out/bench_all.jsonl
-for w in C1 C2 C3 C3K C4J C4g C4gc C4H C4Hc C5 C5x; do
+for w in C1 C2 C3 C3K C4J C4g C4gc C4H C4Hc C5 C5x C5K; do
   extra=""
   case $w in C3K) extra="--batch 8192";; C4H|C4Hc|C4gc) extra="--batch 20000";; esac
   timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e $extra 2>gpurun_out/bench_$w.err | tail -1 >> gpurun_out/bench_all.jsonl

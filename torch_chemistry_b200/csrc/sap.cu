@@ -197,6 +197,135 @@ sap_eval_kernel(const SapProgram sp, const Program ic, const double * __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Second-order Jacobian of the set, concatenated and symmetric: K[B][nterms][sumdim][sumdim]
+// = SAPSet::Jacobian2nd_(xs, K) (source/polynomial/SAPSet.cpp:243-276), per monomial
+// SAP::Hessian_ (source/polynomial/SAP.cpp:226-263): diagonal p (p-1) x^(p-2) prod_{others} x_v^p_v
+// (0 when p < 2), off-diagonal p_u p_v x_u^(p_u-1) x_v^(p_v-1) prod_{others}, the other factors
+// multiplied in ascending (irreducible, index) order like the reference; upper triangle mirrored.
+//
+// Same warp tile: lane = geometry. The output is cut into chunks of consecutive rows of the
+// [nterms * sumdim][sumdim] matrix; a chunk is staged dense [element][lane] (structural zeros
+// included - the result is API-mandated dense) and written out geometry after geometry.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sap_hess_kernel(const SapProgram sp, const double * __restrict__ in, const int64_t B, double * __restrict__ K, const int rows_per) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char * cursor = smem_raw;
+    const SapTerm * terms = stage_table(cursor, sp.terms, sp.nterms);
+    const SapUniq * uniqs = stage_table(cursor, sp.uniqs, sp.nuniqs);
+    const int32_t * pow_off = stage_table(cursor, sp.pow_off, sp.sumdim + 1);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int sd = sp.sumdim, nrows = sp.nterms * sd;
+    const size_t per_warp = (size_t)(sd + sp.npow + rows_per * sd) * kPad;
+    double * X = reinterpret_cast<double *>(cursor) + warp * per_warp;
+    double * XP = X + (size_t)sd * kPad;
+    double * D = XP + (size_t)sp.npow * kPad;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes, tile_step = (int64_t)gridDim.x * nwarps;
+    const int64_t gstride = (int64_t)nrows * sd;
+    const bool aligned = gstride % 2 == 0 && (reinterpret_cast<uint64_t>(K) & 15) == 0;
+
+    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+    if (tile < ntiles) stage_issue(in, tile * kLanes, (int)min((int64_t)kLanes, B - tile * kLanes), sd, X, lane);
+    for (; tile < ntiles; tile += tile_step) {
+        const int64_t b0 = tile * kLanes;
+        const int ntile = (int)min((int64_t)kLanes, B - b0);
+        stage_finish(ntile, sd, X, lane);
+        build_powers(pow_off, sd, X, XP, lane);
+        __syncwarp();
+        if (tile + tile_step < ntiles) {
+            const int64_t nb0 = (tile + tile_step) * kLanes;
+            stage_issue(in, nb0, (int)min((int64_t)kLanes, B - nb0), sd, X, lane);
+        }
+        const double * xp = XP + lane;
+        for (int r0 = 0; r0 < nrows; r0 += rows_per) {
+            const int r1 = min(nrows, r0 + rows_per), span = (r1 - r0) * sd;
+            double * d = D + lane;
+            for (int e = 0; e < span; e++) d[e * kPad] = 0.0;
+            const int t0 = r0 / sd, t1 = (r1 - 1) / sd;
+            for (int t = t0; t <= t1; t++) {
+                const SapTerm term = terms[t];
+                const int rbase = t * sd - r0;                      // row of coordinate c in the chunk: rbase + c
+                for (int a = term.ubegin; a < term.uend; a++) {
+                    const SapUniq ua = uniqs[a];
+                    const int ra = rbase + ua.col;
+                    const bool a_in = ra >= 0 && ra < r1 - r0;
+                    if (ua.power >= 2 && a_in) {
+                        double v = (double)(ua.power * (ua.power - 1)) * xp[(ua.e_pow - 2) * kPad];
+                        for (int w = term.ubegin; w < term.uend; w++)
+                            if (w != a) v *= xp[uniqs[w].e_pow * kPad];
+                        d[(ra * sd + ua.col) * kPad] = v;
+                    }
+                    for (int b = a + 1; b < term.uend; b++) {
+                        const SapUniq ub = uniqs[b];
+                        const int rb = rbase + ub.col;
+                        const bool b_in = rb >= 0 && rb < r1 - r0;
+                        if (!a_in && !b_in) continue;
+                        double v = (double)(ua.power * ub.power) * xp[ua.e_powm1 * kPad] * xp[ub.e_powm1 * kPad];
+                        for (int w = term.ubegin; w < term.uend; w++)
+                            if (w != a && w != b) v *= xp[uniqs[w].e_pow * kPad];
+                        if (a_in) d[(ra * sd + ub.col) * kPad] = v;
+                        if (b_in) d[(rb * sd + ua.col) * kPad] = v;         // SAPSet.cpp:271-274
+                    }
+                }
+            }
+            __syncwarp();
+            // geometry after geometry, lanes along the chunk's elements (pairs when everything is 16-byte aligned)
+            double * out = K + b0 * gstride + (int64_t)r0 * sd;
+            if (aligned && span % 2 == 0 && (r0 * sd) % 2 == 0) {
+                const int pairs = span >> 1, total = ntile * pairs;
+                int g = lane / pairs, p = lane - g * pairs;
+                const int dg = kLanes / pairs, dp = kLanes - dg * pairs;
+                for (int f = lane; f < total; f += kLanes) {
+                    const double * s0 = D + (2 * p) * kPad + g;
+                    *reinterpret_cast<double2 *>(out + (int64_t)g * gstride + 2 * p) = make_double2(s0[0], s0[kPad]);
+                    g += dg; p += dp;
+                    if (p >= pairs) { p -= pairs; g++; }
+                }
+            } else {
+                const int total = ntile * span;
+                int g = lane / span, k = lane - g * span;
+                const int dg = kLanes / span, dk = kLanes - dg * span;
+                for (int f = lane; f < total; f += kLanes) {
+                    out[(int64_t)g * gstride + k] = D[k * kPad + g];
+                    g += dg; k += dk;
+                    if (k >= span) { k -= span; g++; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int launch_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, double * K, cudaStream_t stream) {
+    const int sd = st->sumdim, nrows = st->nterms * sd;
+    // rows per chunk: ~96 staged elements, whole sectors (4-row multiples when sumdim is odd) when possible
+    int rows_per = std::max(1, 96 / sd);
+    if (rows_per >= 4) rows_per &= ~3;
+    rows_per = std::min(rows_per, nrows);
+    auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    const size_t tb = a16(sizeof(SapTerm) * st->prog.nterms) + a16(sizeof(SapUniq) * st->prog.nuniqs) + a16(4 * (sd + 1));
+    const size_t wb = (size_t)(sd + st->prog.npow + rows_per * sd) * kPad * sizeof(double);
+    int warps = 4;
+    while (warps > 1 && tb + warps * wb > (size_t)st->max_smem_optin) warps--;
+    const size_t smem = tb + warps * wb;
+    if (smem > (size_t)st->max_smem_optin) return set_error(TCHEM_EINVAL, "tchem_sap_jacobian2nd: set too large for the shared-memory tile");
+    const void * fn = reinterpret_cast<const void *>(&sap_hess_kernel);
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (B + kLanes - 1) / kLanes;
+    const int64_t grid = std::min<int64_t>((ntiles + warps - 1) / warps, (int64_t)st->sm_count * per_sm);
+    if (grid < 1) return TCHEM_OK;
+    void * args[] = {(void *)&st->prog, (void *)&x, (void *)&B, (void *)&K, (void *)&rows_per};
+    TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
 int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const double * in, int64_t B,
                double * q_out, double * y, double * J, cudaStream_t stream) {
     const bool chained = ict != nullptr;
@@ -385,6 +514,16 @@ int tchem_sap_eval(const tchem_sap_table * t, const double * x, int64_t B, doubl
     DeviceGuard guard(t->device);
     if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
     return launch_sap(t, nullptr, x, B, nullptr, y, J, static_cast<cudaStream_t>(stream));
+}
+
+int tchem_sap_jacobian2nd(const tchem_sap_table * t, const double * x, int64_t B, double * K, tchem_stream_t stream) {
+    if (!t) return set_error(TCHEM_EINVAL, "tchem_sap_jacobian2nd: null table");
+    if (B < 0) return set_error(TCHEM_EINVAL, "tchem_sap_jacobian2nd: negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!x || !K) return set_error(TCHEM_EINVAL, "tchem_sap_jacobian2nd: null argument");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    return launch_sap_hess(t, x, B, K, static_cast<cudaStream_t>(stream));
 }
 
 int tchem_ic_sap_eval(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r, int64_t B,

@@ -1,5 +1,5 @@
-"""Host-side mirror of tchem::polynomial::SAPSet (reference include/tchem/polynomial/SAPSet.hpp:9-86),
-value and Jacobian only (the hot path), over the C ABI.
+"""Host-side mirror of tchem::polynomial::SAPSet (reference include/tchem/polynomial/SAPSet.hpp:9-86):
+value, Jacobian and second-order Jacobian, over the C ABI.
 
 xs is the reference's std::vector<at::Tensor>: one tensor per irreducible, xs[i] of shape
 [dims[i]] or batched [B, dims[i]].
@@ -98,6 +98,37 @@ class SAPSet:
         return list(torch.split(J, self.dimensions, dim=-1))
 
     Jacobian = Jacobian_
+
+    def Jacobian2nd_cat(self, xs):
+        """the concatenated symmetric tensor K[NSAP, sumdim, sumdim] that SAPSet::Jacobian2nd_(xs, K)
+        harvests (source/polynomial/SAPSet.cpp:243-276); batched xs give [B, NSAP, sumdim, sumdim]"""
+        x, batched, was_cuda = self._cat(xs, "Jacobian2nd_")
+        B = x.shape[0]
+        K = torch.empty((B, self.nterms, self.sumdim, self.sumdim), dtype=torch.float64, device=self.device)
+        if B > 0:
+            check(lib.tchem_sap_jacobian2nd(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(K.data_ptr()),
+                                            _stream_ptr(self.device)))
+        K = K if was_cuda else K.cpu()
+        return K if batched else K[0]
+
+    def Jacobian2nd_(self, xs, with_K=False):
+        """CL::utility::matrix of blocks Ks[i][j] (j >= i, None below the diagonal), Ks[i][j] of shape
+        [NSAP, dim_i, dim_j]. with_K=False mirrors Jacobian2nd_(xs) (:221-240): diagonal blocks hold
+        the upper triangle only; with_K=True mirrors Jacobian2nd_(xs, K) (:243-276) and returns (Ks, K)
+        with the blocks as views of the symmetric K."""
+        K = self.Jacobian2nd_cat(xs)
+        n = len(self.dimensions)
+        off = [0]
+        for d in self.dimensions:
+            off.append(off[-1] + d)
+        Ks = [[None] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(i, n):
+                blk = K[..., off[i]:off[i + 1], off[j]:off[j + 1]]
+                Ks[i][j] = blk if with_K or i != j else torch.triu(blk)
+        return (Ks, K) if with_K else Ks
+
+    Jacobian2nd = Jacobian2nd_
 
     def value_and_jacobian(self, xs):
         y, J = self._run(xs, True, True, "Jacobian_")
