@@ -418,8 +418,12 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = bytes_per_geom * B / avg_launch_s / 1e9
-        kernel = ("sap_hess_kernel" if args.workload == "C5K" else "tchem_jit_chain (SAPSet-specialised, NVRTC)" if args.workload == "C5x" and T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, B)
-                  else "tchem_jit_chain (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
+        bulk = os.environ.get("TCHEM_JIT_BULK", "1") != "0"
+        chain_name = "tchem_jit_chain_bulk" if bulk else "tchem_jit_chain"
+        kernel = ("tchem_jit_sap_hess (SAPSet-specialised, NVRTC, one TMA bulk store per tile)" if args.workload == "C5K" and B >= 16384
+                  else "sap_hess_kernel" if args.workload == "C5K"
+                  else chain_name + " (SAPSet-specialised, NVRTC)" if args.workload == "C5x" and T._lib.tchem_ic_sap_uses_specialised(sap._handle, None, B)
+                  else chain_name + " (pair-specialised, NVRTC)" if sap is not None and T._lib.tchem_ic_sap_uses_specialised(sap._handle, ic._handle, B)
                   else "sap_eval_kernel" if sap is not None else "grad_int2cart_kernel" if what == "gradient_int2cart"
                   else "dense_kernel" if args.workload in FLOPS
                   else ("tchem_jit_qJ_bulk (table-specialised, NVRTC, TMA tensor stores)" if os.environ.get("TCHEM_JIT_BULK", "1") != "0" and args.workload == "C2"

@@ -212,3 +212,35 @@ def test_specialised_kernel_source_compiles_for_sm100a():
     terms = (capi.InvDisp * nt.value)()
     capi.check(lib.tchem_ic_parse_text(b"whatever", text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
     assert lib.tchem_ic_jit_source(terms, nt.value, nic.value, 42, 0, None, 0) == 0
+
+
+def test_specialised_sap_second_order_source_compiles_for_sm100a():
+    """jit.cu: the generated kernel for SAPSet::Jacobian2nd_ of the C5 set (literal products, whole-geometry
+    staging, one cp.async.bulk store per tile) compiles with NVRTC for sm_100a without a device."""
+    g = golden("workload_C5")
+    text, dims = str(g["sap_definition"]), [int(d) for d in g["sap_dims"]]
+    nt, nc = C.c_int(0), C.c_int(0)
+    capi.check(lib.tchem_sap_parse_text(text.encode(), None, 0, None, 0, C.byref(nt), C.byref(nc)))
+    tp, cs = (C.c_int32 * (nt.value + 1))(), (C.c_int32 * max(2 * nc.value, 2))()
+    capi.check(lib.tchem_sap_parse_text(text.encode(), tp, nt.value, cs, nc.value, C.byref(nt), C.byref(nc)))
+    d = (C.c_int32 * len(dims))(*dims)
+    sources = []
+    n = lib.tchem_sap_jit_hess_source(tp, cs, nt.value, d, len(dims), None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n)
+    lib.tchem_sap_jit_hess_source(tp, cs, nt.value, d, len(dims), buf, n)
+    sources.append(("tchem_jit_sap_hess", buf.value.decode()))
+    # value + Jacobian on given coordinates: the warp copy-out and the TMA bulk-store variants
+    for bulk, name in ((0, "tchem_jit_chain"), (1, "tchem_jit_chain_bulk")):
+        n = lib.tchem_sap_jit_source(tp, cs, nt.value, d, len(dims), bulk, None, 0)
+        assert n > 0
+        buf = C.create_string_buffer(n)
+        lib.tchem_sap_jit_source(tp, cs, nt.value, d, len(dims), bulk, buf, n)
+        sources.append((name, buf.value.decode()))
+    for name, src in sources:
+        assert name in src and ("cp.async.bulk.global.shared::cta" in src) == (name != "tchem_jit_chain")
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.tchem_ic_jit_compile_check(src.encode(), log, 1 << 16)
+        if rc != 0 and "not available" in log.value.decode():
+            pytest.skip("NVRTC not available")
+        assert rc == 0, name + ": " + log.value.decode()[-2000:]

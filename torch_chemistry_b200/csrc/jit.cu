@@ -232,18 +232,34 @@ bool emit_prim(std::ostringstream & o, const JitPrim & pr, size_t p, bool want_J
 // kernel signature up to and including the per-tile prologue (coordinates staged, atoms in
 // registers, next tile's copy in flight); `params` = the kernel's pointer parameters after r, B
 // plain_cols > 0: the input rows are used as they are (x0p1 .. x{plain_cols-1}p1), no atoms / primitives
+// box_doubles > 0: the per-warp region starts with a 16-byte aligned box of that many doubles (TMA bulk-store
+// staging), then R, then D, each padded to an even number of doubles (chain_warp_doubles)
+size_t chain_warp_doubles(int cartdim, int dcap_entries, int box_doubles) {
+    return (size_t)box_doubles + ((cartdim * 33 + 1) & ~1) + ((dcap_entries * 33 + 1) & ~1);
+}
 void emit_prologue(std::ostringstream & o, const char * name, const char * params, int cartdim, int dcap_entries,
-                   int warps, int blocks, const std::vector<JitPrim> & prims, int plain_cols = 0) {
+                   int warps, int blocks, const std::vector<JitPrim> & prims, int plain_cols = 0, int box_doubles = 0) {
     const int natoms = cartdim / 3;
     o << "#define CD " << cartdim << "\n#define DCAP " << dcap_entries << "\n";
+    if (box_doubles > 0)
+        o << "#define BOXD " << box_doubles << "\n#define RSIZE " << ((cartdim * 33 + 1) & ~1) << "\n#define WARPD "
+          << chain_warp_doubles(cartdim, dcap_entries, box_doubles) << "\n";
     o << kPrelude;
     o << "extern \"C\" __global__ void __launch_bounds__(" << warps * 32 << ", " << blocks << ")\n"
       << name << "(const double * __restrict__ r, const long long B, " << params << ") {\n"
       << "    extern __shared__ __align__(16) double smem[];\n"
-      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n"
-      << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
-      << "    double * D = R + CD * KPAD;\n"
-      << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n";
+    if (box_doubles > 0)
+        o << "    double * Box = smem + (size_t)warp * WARPD;\n"
+          << "    double * R = Box + BOXD;\n"
+          << "    double * D = R + RSIZE;\n"
+          << "    // structural zeros never change: staged once, the box keeps them from tile to tile\n"
+          << "    for (int e = 2 * lane; e < BOXD; e += 2 * LANES) *reinterpret_cast<double2 *>(Box + e) = make_double2(0.0, 0.0);\n"
+          << "    __syncwarp();\n";
+    else
+        o << "    double * R = smem + (size_t)warp * (CD + DCAP) * KPAD;\n"
+          << "    double * D = R + CD * KPAD;\n";
+    o << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
       << "    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;\n"
       << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue(r, b0, (int)min((int64_t)LANES, B - b0), R, lane); }\n"
       << "    for (; tile < ntiles; tile += step) {\n"
@@ -280,8 +296,15 @@ std::string row_expr(const std::vector<std::pair<double, int>> & row, const char
 // Chained r -> q -> SAPSet: straight-line q rows (compute_IC_J value formulas, gradients elided),
 // then every monomial and its partial derivatives as explicit products of shared powers. Staged
 // per chunk of monomials: [values][Jacobian rows], written out like the q+J kernel.
+// `bulk` (single-chunk sets with even NT and NT * SD): y and the Jacobian are staged per lane in the
+// layout they have in global memory, so the tile's 32 geometries are one contiguous block of each
+// array and one lane hands them to the TMA unit as two 1-D bulk copies (cp.async.bulk.global.shared::cta)
+// - no copy-out instructions, a write front that is linear per warp.
+bool chain_bulk_eligible(int nt, int sd, int dcap) {
+    return nt % 2 == 0 && (nt * sd) % 2 == 0 && nt * (1 + sd) <= dcap;
+}
 std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim,
-                             const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks) {
+                             const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks, bool bulk = false) {
     // terms empty: the SAPSet alone, evaluated on given coordinates x[B][n_ic] (cartdim = n_ic)
     const bool plain = terms.empty();
     std::vector<JitPrim> prims;
@@ -291,8 +314,13 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     const int per_term = 1 + sd;
     if (per_term > dcap) return std::string();
     const int tper = chain_terms_per_chunk(nt, per_term, dcap);
+    if (bulk && !chain_bulk_eligible(nt, sd, dcap)) return std::string();
     std::ostringstream o;
     o << "#define NT " << nt << "\n#define SD " << sd << "\n";
+    if (bulk)
+        emit_prologue(o, "tchem_jit_chain_bulk", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
+                      cartdim, sd, warps, blocks, prims, plain ? sd : 0, 32 * nt * per_term);
+    else
     emit_prologue(o, "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
                   cartdim, std::max(tper * per_term, sd), warps, blocks, prims, plain ? sd : 0);
     for (size_t p = 0; p < prims.size(); p++)
@@ -307,6 +335,43 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     for (int i = 0; i < n_ic; i++) o << "            D[" << i << " * KPAD + lane] = x" << i << "p1;\n";
     o << "            __syncwarp();\n            copy_rows<SD, SD>(D, q + b0 * SD, ntile, lane);\n            __syncwarp();\n        }\n";
     auto power = [](int col, int p) { return "x" + std::to_string(col) + "p" + std::to_string(p); };
+    if (bulk) {
+        // boxes: [32][NT] values, then [32][NT * SD] Jacobian rows; a lane owns row `lane` of both
+        std::vector<std::string> yv(nt), jv((size_t)nt * sd, "0.0");
+        for (int t = 0; t < nt; t++) {
+            std::string v;
+            for (auto & u : saps[t]) v = v.empty() ? power(u.first, u.second) : v + " * " + power(u.first, u.second);
+            yv[t] = v.empty() ? "1.0" : v;
+            for (size_t ui = 0; ui < saps[t].size(); ui++) {
+                const auto & u = saps[t][ui];
+                std::string e = hexd((double)u.second);
+                if (u.second > 1) e += " * " + power(u.first, u.second - 1);
+                for (size_t wi = 0; wi < saps[t].size(); wi++)
+                    if (wi != ui) e += " * " + power(saps[t][wi].first, saps[t][wi].second);
+                jv[(size_t)t * sd + u.first] = e;
+            }
+        }
+        o << "        {\n"
+          << "            double * Yb = Box + lane * NT, * Jb = Box + LANES * NT + lane * (NT * SD);\n"
+          << "            // the previous tile's stores have read the boxes\n"
+          << "            if (lane == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
+          << "            __syncwarp();\n";
+        for (int t = 0; t < nt; t += 2)
+            o << "            *reinterpret_cast<double2 *>(Yb + " << t << ") = make_double2(" << yv[t] << ", " << yv[t + 1] << ");\n";
+        for (int e = 0; e < nt * sd; e += 2)
+            if (jv[e] != "0.0" || jv[e + 1] != "0.0")
+                o << "            *reinterpret_cast<double2 *>(Jb + " << e << ") = make_double2(" << jv[e] << ", " << jv[e + 1] << ");\n";
+        o << "            asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+          << "            __syncwarp();\n"
+          << "            if (lane == 0) {\n"
+          << "                const uint32_t box_sh = (uint32_t)__cvta_generic_to_shared(Box);\n"
+          << "                if (y) asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(y + b0 * NT), \"r\"(box_sh), \"r\"(ntile * (NT * 8)) : \"memory\");\n"
+          << "                if (J) asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(J + b0 * (NT * SD)), \"r\"(box_sh + LANES * NT * 8), \"r\"(ntile * (NT * SD * 8)) : \"memory\");\n"
+          << "                asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n"
+          << "            }\n        }\n    }\n"
+          << "    if (lane == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n}\n";
+        return o.str();
+    }
     for (int t0 = 0; t0 < nt; t0 += tper) {
         const int t1 = std::min(nt, t0 + tper), n = t1 - t0;
         o << "        {   // monomials " << t0 << " .. " << t1 - 1 << "\n";
@@ -334,6 +399,87 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
           << "            __syncwarp();\n        }\n";
     }
     o << "    }\n}\n";
+    return o.str();
+}
+
+// Second-order Jacobian of a SAPSet (SAPSet::Jacobian2nd_(xs, K), source/polynomial/SAPSet.cpp:243-276)
+// specialised to the set: every element of the symmetric [NT][SD][SD] block is a literal product of
+// shared powers (SAP::Hessian_, source/polynomial/SAP.cpp:226-263; structural zeros are literal
+// zeros). Each lane stages its WHOLE geometry (G = NT * SD * SD doubles) in the layout the result
+// has in global memory, so a tile's 32 geometries are one contiguous block and ONE lane hands it
+// to the TMA unit as a single 1-D bulk copy (cp.async.bulk.global.shared::cta): no copy-out
+// instructions, and a write front that is linear per warp (the best pattern of
+// tools/micro/write_pattern.cu). With G = 2 mod 4 the row pitch is an odd number of 16-byte
+// units and the staging stores are bank-conflict free.
+std::string jit_hess_source(const std::vector<std::vector<std::pair<int, int>>> & saps, int sd, int warps, int blocks) {
+    const int nt = (int)saps.size(), G = nt * sd * sd;
+    if (G % 2) return std::string();
+    const int rsize = (sd * 33 + 1) & ~1;
+    std::ostringstream o;
+    o << "#define CD " << sd << "\n#define DCAP 0\n#define G " << G << "\n#define RSIZE " << rsize << "\n";
+    o << kPrelude;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << warps * 32 << ", " << blocks << ")\n"
+      << "tchem_jit_sap_hess(const double * __restrict__ r, const long long B, double * __restrict__ K) {\n"
+      << "    extern __shared__ __align__(16) double smem[];\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;\n"
+      << "    double * Sbox = smem + (size_t)warp * (LANES * G + RSIZE);\n"
+      << "    double * R = Sbox + LANES * G;\n"
+      << "    double * S = Sbox + lane * G;               // this lane's geometry, laid out like the result\n"
+      << "    const uint32_t S_sh = (uint32_t)__cvta_generic_to_shared(Sbox);\n"
+      << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = (int64_t)gridDim.x * nwarps;\n"
+      << "    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;\n"
+      << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue(r, b0, (int)min((int64_t)LANES, B - b0), R, lane); }\n"
+      << "    // structural zeros never change: staged once, the box keeps them from tile to tile\n"
+      << "    for (int e = 0; e < G; e += 2) *reinterpret_cast<double2 *>(S + e) = make_double2(0.0, 0.0);\n"
+      << "    for (; tile < ntiles; tile += step) {\n"
+      << "        const int64_t b0 = tile * LANES;\n"
+      << "        const int ntile = (int)min((int64_t)LANES, B - b0);\n"
+      << "        stage_finish(ntile, R, lane);\n";
+    for (int i = 0; i < sd; i++) o << "        const double x" << i << "p1 = R[" << i << " * KPAD + lane];\n";
+    o << "        __syncwarp();\n"
+      << "        if (tile + step < ntiles) { const int64_t nb0 = (tile + step) * LANES; stage_issue(r, nb0, (int)min((int64_t)LANES, B - nb0), R, lane); }\n";
+    std::vector<int> maxpow(sd, 0);
+    for (auto & t : saps) for (auto & u : t) maxpow[u.first] = std::max(maxpow[u.first], u.second);
+    for (int i = 0; i < sd; i++)
+        for (int p = 2; p <= maxpow[i]; p++) o << "        const double x" << i << "p" << p << " = x" << i << "p" << p - 1 << " * x" << i << "p1;\n";
+    auto power = [](int col, int p) { return "x" + std::to_string(col) + "p" + std::to_string(p); };
+    std::vector<std::string> expr((size_t)G, "0.0");
+    for (int t = 0; t < nt; t++) {
+        const auto & us = saps[t];                       // (column, power), ascending column = uniques_orders_
+        for (size_t a = 0; a < us.size(); a++) {
+            const int ca = us[a].first, pa = us[a].second;
+            if (pa >= 2) {
+                std::string e = hexd((double)(pa * (pa - 1)));
+                if (pa > 2) e += " * " + power(ca, pa - 2);
+                for (size_t w = 0; w < us.size(); w++) if (w != a) e += " * " + power(us[w].first, us[w].second);
+                expr[(size_t)(t * sd + ca) * sd + ca] = e;
+            }
+            for (size_t b = a + 1; b < us.size(); b++) {
+                const int cb = us[b].first, pb = us[b].second;
+                std::string e = hexd((double)(pa * pb));
+                if (pa > 1) e += " * " + power(ca, pa - 1);
+                if (pb > 1) e += " * " + power(cb, pb - 1);
+                for (size_t w = 0; w < us.size(); w++) if (w != a && w != b) e += " * " + power(us[w].first, us[w].second);
+                expr[(size_t)(t * sd + ca) * sd + cb] = e;
+                expr[(size_t)(t * sd + cb) * sd + ca] = e;                // SAPSet.cpp:271-274
+            }
+        }
+    }
+    o << "        // the previous tile's store has read the box\n"
+      << "        if (lane == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
+      << "        __syncwarp();\n";
+    for (int e = 0; e < G; e += 2)
+        if (expr[e] != "0.0" || expr[e + 1] != "0.0")
+            o << "        *reinterpret_cast<double2 *>(S + " << e << ") = make_double2(" << expr[e] << ", " << expr[e + 1] << ");\n";
+    o << "        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+      << "        __syncwarp();\n"
+      << "        if (lane == 0) {\n"
+      << "            asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(K + b0 * G), \"r\"(S_sh), \"r\"(ntile * (G * 8)) : \"memory\");\n"
+      << "            asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n"
+      << "        }\n"
+      << "    }\n"
+      << "    if (lane == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n"
+      << "}\n";
     return o.str();
 }
 
@@ -583,8 +729,10 @@ TensorMapEncodeTiled tensor_map_encoder() {
 }
 
 namespace {
-std::map<std::pair<const tchem_sap_table *, const tchem_ic_table *>, JitKernel> & chain_kernels() {
-    static std::map<std::pair<const tchem_sap_table *, const tchem_ic_table *>, JitKernel> m;
+// (SAPSet, IntCoordSet or nullptr, variant): 0 = warp copy-out, 1 = TMA bulk stores
+typedef std::tuple<const tchem_sap_table *, const tchem_ic_table *, int> ChainKey;
+std::map<ChainKey, JitKernel> & chain_kernels() {
+    static std::map<ChainKey, JitKernel> m;
     return m;
 }
 }
@@ -596,14 +744,21 @@ void release_jit(const tchem_ic_table * t) {
         if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
     }
     for (auto c = chain_kernels().begin(); c != chain_kernels().end();) {
-        if (c->first.second == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
+        if (std::get<1>(c->first) == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
         else ++c;
     }
 }
+namespace {
+std::map<const tchem_sap_table *, JitKernel> & hess_kernels() { static std::map<const tchem_sap_table *, JitKernel> m; return m; }
+}
 void release_jit_sap(const tchem_sap_table * t) {
     std::lock_guard<std::mutex> lock(jit_mutex());
+    {
+        auto h = hess_kernels().find(t);
+        if (h != hess_kernels().end()) { if (h->second.lib) cudaLibraryUnload(h->second.lib); hess_kernels().erase(h); }
+    }
     for (auto c = chain_kernels().begin(); c != chain_kernels().end();) {
-        if (c->first.first == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
+        if (std::get<0>(c->first) == t) { if (c->second.lib) cudaLibraryUnload(c->second.lib); c = chain_kernels().erase(c); }
         else ++c;
     }
 }
@@ -640,31 +795,68 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
     if (!enabled || std::max(B, g_batch_hint) < min_batch || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return -1;
     if (t ? (t->has5 || t->cartdim > 36 || t->terms.size() > 128) : st->sumdim > 36) return -1;
     const int in_dim = t ? t->cartdim : st->sumdim;
+    // one chunk when the whole set fits ~128 staged entries: a chunk that ends inside a geometry's
+    // y / J block leaves 32-byte sectors half written, and partial-sector writes cost DRAM
+    // read-modify-write traffic (measured on C5: 2 chunks 3.55 ms, 1 chunk 1.79 ms)
+    const int per_term = 1 + st->sumdim, nt = st->nterms;
+    const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, 76));
+    static const int want_bulk = env_int("TCHEM_JIT_BULK", 1);
+    // single-chunk sets: whole-tile TMA bulk stores (16-byte aligned results, even row lengths)
+    int variant = want_bulk && chain_bulk_eligible(nt, st->sumdim, dcap)
+                  && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 1 : 0;
+    JitKernel * k = nullptr;
+    for (; variant >= 0; variant--) {
+        std::lock_guard<std::mutex> lock(jit_mutex());
+        JitKernel & jk = chain_kernels()[ChainKey(st, t, variant)];
+        if (!jk.fn && !jk.failed) {
+            jk.warps = env_int("TCHEM_JIT_WARPS", variant == 1 ? 2 : 4);
+            jk.blocks = env_int("TCHEM_JIT_BLOCKS", variant == 1 ? 4 : 2);
+            const int tper = chain_terms_per_chunk(nt, per_term, dcap);
+            static const std::vector<tchem_invdisp_t> no_terms;
+            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks, variant == 1);
+            const size_t smem = variant == 1 ? (size_t)jk.warps * chain_warp_doubles(in_dim, st->sumdim, 32 * nt * per_term) * sizeof(double)
+                                             : (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
+            jit_finish(jk, src, variant == 1 ? "tchem_jit_chain_bulk" : "tchem_jit_chain", smem, st->max_smem_optin, debug);
+        }
+        if (!jk.failed) { k = &jk; break; }
+    }
+    if (!k) return -1;
+    const int64_t ntiles = (B + 31) / 32;
+    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)st->sm_count * k->per_sm);
+    long long Bll = B;
+    void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
+    TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
+    count_launch();
+    return TCHEM_OK;
+}
+
+// SAPSet::Jacobian2nd_ through the kernel specialised to the set; -1: not eligible (interpreter)
+int launch_jit_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, double * K, cudaStream_t stream) {
+    static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
+    static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
+    const int64_t G = (int64_t)st->nterms * st->sumdim * st->sumdim;
+    // one geometry = one staged row: even (16-byte stores), at least 3 warps' boxes per SM, 16-byte aligned result
+    const size_t per_warp = (size_t)(32 * G + ((st->sumdim * 33 + 1) & ~1)) * sizeof(double);
+    if (!enabled || std::max(B, g_batch_hint) < min_batch || G % 2 || st->sumdim > 36 || G > 4096
+        || 3 * per_warp > (size_t)st->max_smem_optin || (reinterpret_cast<uintptr_t>(K) & 15)) return -1;
     JitKernel * k;
     {
         std::lock_guard<std::mutex> lock(jit_mutex());
-        JitKernel & jk = chain_kernels()[{st, t}];
+        JitKernel & jk = hess_kernels()[st];
         k = &jk;
         if (!jk.fn && !jk.failed) {
-            // one chunk when the whole set fits ~128 staged entries: a chunk that ends inside a geometry's
-            // y / J block leaves 32-byte sectors half written, and partial-sector writes cost DRAM
-            // read-modify-write traffic (measured on C5: 2 chunks 3.55 ms, 1 chunk 1.79 ms)
-            const int per_term = 1 + st->sumdim, nt = st->nterms;
-            const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, 76));
-            jk.warps = env_int("TCHEM_JIT_WARPS", 4);
-            jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
-            const int tper = chain_terms_per_chunk(nt, per_term, dcap);
-            static const std::vector<tchem_invdisp_t> no_terms;
-            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks);
-            const size_t smem = (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
-            jit_finish(jk, src, "tchem_jit_chain", smem, st->max_smem_optin, debug);
+            jk.warps = env_int("TCHEM_JIT_HESS_WARPS", 1);
+            const int fit = (int)((size_t)st->max_smem_optin / (per_warp * jk.warps + 1024));
+            jk.blocks = std::max(1, std::min(env_int("TCHEM_JIT_HESS_BLOCKS", 16), fit));
+            const std::string src = jit_hess_source(st->h_terms, st->sumdim, jk.warps, jk.blocks);
+            jit_finish(jk, src, "tchem_jit_sap_hess", per_warp * jk.warps, st->max_smem_optin, debug);
         }
         if (jk.failed) return -1;
     }
     const int64_t ntiles = (B + 31) / 32;
     const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)st->sm_count * k->per_sm);
     long long Bll = B;
-    void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
+    void * args[] = {(void *)&x, (void *)&Bll, (void *)&K};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
     count_launch();
     return TCHEM_OK;
@@ -769,6 +961,53 @@ int64_t tchem_ic_jit_source_bulk(const tchem_invdisp_t * terms, int n_terms, int
     return (int64_t)s.size() + (s.empty() ? 0 : 1);
 }
 
+// the generated source of the set-specialised SAPSet::Jacobian2nd_ kernel (testing / inspection); same
+// definition arrays as tchem_sap_table_create; returns the length needed, 0 when the set is not eligible
+int64_t tchem_sap_jit_hess_source(const int32_t * term_ptr, const int32_t * coords, int n_terms, const int32_t * dims, int n_irreducibles,
+                                  char * buf, int64_t capacity) {
+    if (!term_ptr || !dims || n_terms <= 0 || n_irreducibles <= 0) return 0;
+    std::vector<int> offset(n_irreducibles + 1, 0);
+    for (int i = 0; i < n_irreducibles; i++) offset[i + 1] = offset[i] + dims[i];
+    std::vector<std::vector<std::pair<int, int>>> saps(n_terms);
+    for (int t = 0; t < n_terms; t++) {
+        std::map<int, int> powers;
+        for (int c = term_ptr[t]; c < term_ptr[t + 1]; c++) powers[offset[coords[2 * c]] + coords[2 * c + 1]]++;
+        for (auto & kv : powers) saps[t].push_back({kv.first, kv.second});
+    }
+    const std::string s = jit_hess_source(saps, offset[n_irreducibles], 1, 4);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+// the generated source of the set-specialised SAPSet value + Jacobian kernel on given coordinates
+// (tchem_sap_eval, large batches); bulk != 0: the TMA bulk-store variant. 0 when not eligible.
+int64_t tchem_sap_jit_source(const int32_t * term_ptr, const int32_t * coords, int n_terms, const int32_t * dims, int n_irreducibles,
+                             int bulk, char * buf, int64_t capacity) {
+    if (!term_ptr || !dims || n_terms <= 0 || n_irreducibles <= 0) return 0;
+    std::vector<int> offset(n_irreducibles + 1, 0);
+    for (int i = 0; i < n_irreducibles; i++) offset[i + 1] = offset[i] + dims[i];
+    std::vector<std::vector<std::pair<int, int>>> saps(n_terms);
+    for (int t = 0; t < n_terms; t++) {
+        std::map<int, int> powers;
+        for (int c = term_ptr[t]; c < term_ptr[t + 1]; c++) powers[offset[coords[2 * c]] + coords[2 * c + 1]]++;
+        for (auto & kv : powers) saps[t].push_back({kv.first, kv.second});
+    }
+    const int sd = offset[n_irreducibles], per_term = 1 + sd;
+    const int dcap = n_terms * per_term <= 128 ? n_terms * per_term : std::max(per_term, 76);
+    static const std::vector<tchem_invdisp_t> no_terms;
+    const std::string s = jit_chain_source(no_terms, sd, sd, saps, dcap, bulk ? 2 : 4, bulk ? 4 : 2, bulk != 0);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
 // 1 when tchem_ic_eval(J != NULL, K == NULL) on a batch of B geometries runs the specialised kernel
 int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
@@ -784,7 +1023,7 @@ int tchem_ic_sap_uses_specialised(const tchem_sap_table * st, const tchem_ic_tab
     if (!st || !enabled || B < min_batch || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return 0;
     if (t ? (t->has5 || t->cartdim > 36 || t->terms.size() > 128) : st->sumdim > 36) return 0;
     std::lock_guard<std::mutex> lock(jit_mutex());
-    auto it = chain_kernels().find({st, t});
+    auto it = chain_kernels().find(ChainKey(st, t, 0));
     return it == chain_kernels().end() || !it->second.failed ? 1 : 0;
 }
 

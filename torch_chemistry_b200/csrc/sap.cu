@@ -21,6 +21,7 @@ namespace tchem_b200 {
 int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
                      double * q, double * y, double * J, cudaStream_t stream);
 void release_jit_sap(const tchem_sap_table * t);
+int launch_jit_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, double * K, cudaStream_t stream);
 extern thread_local int64_t g_batch_hint;
 
 namespace {
@@ -300,6 +301,11 @@ sap_hess_kernel(const SapProgram sp, const double * __restrict__ in, const int64
 }
 
 int launch_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, double * K, cudaStream_t stream) {
+    {
+        // large batches: the kernel specialised to this SAPSet (jit.cu); -1 = not eligible, interpret
+        const int rc = launch_jit_sap_hess(st, x, B, K, stream);
+        if (rc != -1) return rc;
+    }
     const int sd = st->sumdim, nrows = st->nterms * sd;
     // rows per chunk: ~96 staged elements, whole sectors (4-row multiples when sumdim is odd) when possible
     int rows_per = std::max(1, 96 / sd);
