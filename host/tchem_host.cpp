@@ -500,6 +500,8 @@ SAPSet::SAPSet(const std::string & sapoly_file, const size_t & _irreducible, con
     }
     construct_orders_();
 }
+SAPSet::SAPSet(const std::vector<SAP> & _SAPs, const size_t & _irreducible, const std::vector<size_t> & _dimensions)
+: SAPs_(_SAPs), irreducible_(_irreducible), dimensions_(_dimensions) { construct_orders_(); }
 SAPSet::~SAPSet() {}
 void SAPSet::construct_orders_() {
     max_order_ = 0;
@@ -639,5 +641,106 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> SAPSet::chained(const tchem::IC::
     if (host) { y = y.cpu(); J = J.cpu(); q = q.cpu(); }
     return std::make_tuple(unbatch(y, rb.batched), unbatch(J, rb.batched), unbatch(q, rb.batched));
 }
+
+// ---- Polynomial / PolynomialSet (source/polynomial/Polynomial.cpp, PolynomialSet.cpp:56-179) --------------------
+Polynomial::Polynomial() {}
+Polynomial::Polynomial(const std::vector<size_t> & _coords) : coords_(_coords) {
+    std::sort(coords_.begin(), coords_.end(), std::greater<size_t>());
+    std::map<size_t, size_t> powers;
+    for (size_t c : coords_) powers[c]++;
+    for (const auto & kv : powers) uniques_orders_.push_back(kv);
+}
+Polynomial::Polynomial(const std::vector<std::pair<size_t, size_t>> _uniques_orders) : uniques_orders_(_uniques_orders) {
+    for (const auto & uo : uniques_orders_) for (size_t i = 0; i < uo.second; i++) coords_.push_back(uo.first);
+    std::sort(coords_.begin(), coords_.end(), std::greater<size_t>());
+}
+Polynomial::~Polynomial() {}
+const std::vector<size_t> & Polynomial::coords() const { return coords_; }
+const std::vector<std::pair<size_t, size_t>> & Polynomial::uniques_orders() const { return uniques_orders_; }
+size_t Polynomial::order() const { return coords_.size(); }
+namespace {
+PolynomialSet single_term(const Polynomial & p, const at::Tensor & x, const char * who) {
+    if (x.dim() != 1 && x.dim() != 2) throw std::invalid_argument(std::string("tchem::polynomial::Polynomial::") + who + ": x must be a vector");
+    return PolynomialSet(std::vector<Polynomial>{p}, (size_t)x.size(-1));
+}
+}
+at::Tensor Polynomial::operator()(const at::Tensor & x) const { return single_term(*this, x, "operator()")(x).select(-1, 0); }
+at::Tensor Polynomial::gradient_(const at::Tensor & x) const { return single_term(*this, x, "gradient_").Jacobian_(x).select(-2, 0); }
+at::Tensor Polynomial::gradient(const at::Tensor & x) const { return gradient_(x); }
+at::Tensor Polynomial::Hessian_(const at::Tensor & x) const { return single_term(*this, x, "Hessian_").Jacobian2nd_(x).select(-3, 0); }
+at::Tensor Polynomial::Hessian(const at::Tensor & x) const { return Hessian_(x); }
+
+void PolynomialSet::construct_orders_() {
+    max_order_ = 0;
+    for (const Polynomial & p : polynomials_) max_order_ = std::max(max_order_, p.order());
+    orders_.assign(max_order_ + 1, {});
+    for (const Polynomial & p : polynomials_) orders_[p.order()].push_back(&p);
+    engine_.reset();
+}
+PolynomialSet::PolynomialSet() {}
+PolynomialSet::PolynomialSet(const std::vector<Polynomial> & _polynomials, const size_t & _dimension)
+: polynomials_(_polynomials), dimension_(_dimension) { construct_orders_(); }
+// all terms up to `_order`: orders ascending; inside an order the terms are the non-increasing index tuples,
+// enumerated with the first index running fastest (PolynomialSet.cpp:60-111)
+PolynomialSet::PolynomialSet(const size_t & _dimension, const size_t & _order) : dimension_(_dimension) {
+    polynomials_.push_back(Polynomial(std::vector<size_t>()));
+    for (size_t k = 1; k <= _order && dimension_ > 0; k++) {
+        std::vector<size_t> c(k, 0);
+        while (true) {
+            polynomials_.push_back(Polynomial(c));
+            // next non-increasing tuple: bump the first position that can still grow, reset the ones before it
+            size_t i = 0;
+            while (i < k && c[i] + 1 >= dimension_) i++;
+            if (i == k) break;
+            c[i]++;
+            for (size_t j = 0; j < i; j++) c[j] = c[i];
+        }
+    }
+    construct_orders_();
+}
+PolynomialSet::~PolynomialSet() {}
+const std::vector<Polynomial> & PolynomialSet::polynomials() const { return polynomials_; }
+const size_t & PolynomialSet::dimension() const { return dimension_; }
+const size_t & PolynomialSet::max_order() const { return max_order_; }
+const std::vector<std::vector<const Polynomial *>> & PolynomialSet::orders() const { return orders_; }
+const Polynomial & PolynomialSet::operator[](const size_t & index) const { return polynomials_[index]; }
+std::vector<at::Tensor> PolynomialSet::views(const at::Tensor & x) const {
+    std::vector<at::Tensor> out(max_order_ + 1);
+    int64_t start = 0;
+    for (size_t i = 0; i <= max_order_; i++) { out[i] = x.slice(-1, start, start + (int64_t)orders_[i].size()); start += (int64_t)orders_[i].size(); }
+    return out;
+}
+const SAPSet & PolynomialSet::engine() const {
+    if (!engine_) {
+        std::vector<SAP> saps;
+        for (const Polynomial & p : polynomials_) {
+            std::vector<std::pair<size_t, size_t>> coords;
+            for (size_t c : p.coords()) coords.emplace_back(0, c);
+            saps.push_back(SAP(coords));
+        }
+        engine_ = std::make_shared<SAPSet>(saps, 0, std::vector<size_t>{dimension_});
+    }
+    return *engine_;
+}
+void PolynomialSet::check_(const at::Tensor & x, const char * who_) const {
+    const std::string who = std::string("tchem::polynomial::PolynomialSet::") + who_;
+    if (x.dim() != 1 && x.dim() != 2) throw std::invalid_argument(who + ": x must be a vector");
+    if (x.size(-1) != (int64_t)dimension_) throw std::invalid_argument(who + ": x must have a same dimension as the coordinates");
+}
+at::Tensor PolynomialSet::operator()(const at::Tensor & x) const { check_(x, "operator()"); return engine()({x}); }
+at::Tensor PolynomialSet::Jacobian_(const at::Tensor & x) const {
+    check_(x, "Jacobian_");
+    at::Tensor J;
+    engine().Jacobian_({x}, J);
+    return J;
+}
+at::Tensor PolynomialSet::Jacobian(const at::Tensor & x) const { return Jacobian_(x); }
+at::Tensor PolynomialSet::Jacobian2nd_(const at::Tensor & x) const {
+    check_(x, "Jacobian2nd_");
+    at::Tensor K;
+    engine().Jacobian2nd_({x}, K);
+    return K;
+}
+at::Tensor PolynomialSet::Jacobian2nd(const at::Tensor & x) const { return Jacobian2nd_(x); }
 
 } } // namespace tchem::polynomial

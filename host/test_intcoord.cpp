@@ -161,6 +161,29 @@ int main(int argc, char ** argv) {
     report("constant term only in the totally symmetric irreducible",
            throws<std::invalid_argument>([&] { tchem::polynomial::SAPSet bad(dir + "sap1.in", 1, {2, 2}); }) ? 0 : 1, 0);
 
+    std::cout << "module 'polynomial' (test/polynomial/main.cpp:7-16)\n";
+    at::Tensor panswer = at::tensor({1.0, 2.0, 7.0, 4.0, 14.0, 49.0, 8.0, 28.0, 98.0, 343.0, 16.0, 56.0, 196.0, 686.0, 2401.0}, r_cpu.options());
+    tchem::polynomial::PolynomialSet pset(2, 4);
+    at::Tensor px = at::tensor({2.0, 7.0}, r_cpu.options());
+    report("value of polynomial set", (pset(px) - panswer).norm().item<double>(), 0.0);
+    tchem::polynomial::PolynomialSet pset3(3, 2);
+    const std::vector<std::vector<size_t>> expect = {{}, {0}, {1}, {2}, {0, 0}, {1, 0}, {2, 0}, {1, 1}, {2, 1}, {2, 2}};
+    double order_err = pset3.polynomials().size() == expect.size() ? 0.0 : 1.0;
+    for (size_t i = 0; i < expect.size() && order_err == 0.0; i++) if (pset3[i].coords() != expect[i]) order_err = 1.0;
+    report("generated terms (3 coordinates, order 2) in the reference's order", order_err, 0.0);
+    at::Tensor PJ = pset.Jacobian_(px), PK = pset.Jacobian2nd_(px);
+    double pfd = 0.0;
+    for (int64_t c = 0; c < 2; c++) {
+        at::Tensor xp = px.clone(), xm = px.clone();
+        xp[c] += 1e-4; xm[c] -= 1e-4;
+        pfd = std::max(pfd, maxabs((pset(xp) - pset(xm)) / 2e-4 - PJ.select(-1, c)) / 2401.0);
+        pfd = std::max(pfd, maxabs((pset.Jacobian_(xp) - pset.Jacobian_(xm)) / 2e-4 - PK.select(-1, c)) / 2401.0);
+    }
+    report("polynomial Jacobian / Jacobian2nd vs central differences", pfd, 1e-6);
+    report("Polynomial::operator(), gradient_, Hessian_ = rows of the set",
+           std::abs((pset[8](px) - panswer[8]).item<double>()) + maxabs(pset[8].gradient_(px) - PJ[8]) + maxabs(pset[8].Hessian_(px) - PK[8]), 1e-12);
+    report("dimension check", throws<std::invalid_argument>([&] { pset(at::ones({3}, r_cpu.options())); }) ? 0 : 1, 0);
+
     std::cout << (failures ? "FAILED " : "passed ") << "(" << failures << " failures)\n";
     return failures ? 1 : 0;
 }

@@ -32,6 +32,8 @@ class SAPSet {
     public:
         SAPSet();
         SAPSet(const std::string & sapoly_file, const size_t & _irreducible, const std::vector<size_t> & _dimensions);
+        // from explicit monomials (not in the reference; used by PolynomialSet)
+        SAPSet(const std::vector<SAP> & _SAPs, const size_t & _irreducible, const std::vector<size_t> & _dimensions);
         ~SAPSet();
 
         void insert_const();

@@ -16,6 +16,7 @@
 
 #include <tchem/IC/IntCoordSet.hpp>
 #include <tchem/polynomial/SAPSet.hpp>
+#include <tchem/polynomial/PolynomialSet.hpp>
 
 namespace {
 thread_local std::string g_error;
@@ -216,6 +217,39 @@ int ref_sap_jacobian2nd(void * hh, const double * x, int64_t B, double * K) {
             at::Tensor Kb;
             h.set.Jacobian2nd_(split_xs(h, x + b * h.sumdim), Kb);
             store(K + b * n * h.sumdim * h.sumdim, Kb);
+        }
+    });
+}
+
+// ---- PolynomialSet (source/polynomial/PolynomialSet.cpp): all terms up to `order` in `dimension` coordinates ----
+void * ref_poly_create(int dimension, int order) {
+    tchem::polynomial::PolynomialSet * h = nullptr;
+    int rc = guarded([&]{ h = new tchem::polynomial::PolynomialSet((size_t)dimension, (size_t)order); });
+    return rc == 0 ? h : nullptr;
+}
+void ref_poly_destroy(void * h) {delete static_cast<tchem::polynomial::PolynomialSet *>(h);}
+int ref_poly_nterms(void * h) {return (int)static_cast<tchem::polynomial::PolynomialSet *>(h)->polynomials().size();}
+// coords of every term, flattened; term_ptr[nterms + 1]. Returns the number of coords (call with NULLs to size).
+int ref_poly_terms(void * hh, int32_t * term_ptr, int32_t * coords) {
+    const auto & ps = static_cast<tchem::polynomial::PolynomialSet *>(hh)->polynomials();
+    int n = 0;
+    for (size_t i = 0; i < ps.size(); i++) {
+        if (term_ptr) term_ptr[i] = n;
+        for (size_t c : ps[i].coords()) { if (coords) coords[n] = (int32_t)c; n++; }
+    }
+    if (term_ptr) term_ptr[ps.size()] = n;
+    return n;
+}
+// x: [B, dimension] -> y [B, nterms], J [B, nterms, dimension] (Jacobian_), K [B, nterms, dimension, dimension] (Jacobian2nd_)
+int ref_poly_eval(void * hh, const double * x, int64_t B, double * y, double * J, double * K) {
+    const auto & set = *static_cast<tchem::polynomial::PolynomialSet *>(hh);
+    const int64_t n = set.polynomials().size(), d = set.dimension();
+    return guarded([&]{
+        for (int64_t b = 0; b < B; b++) {
+            at::Tensor xb = view(x + b * d, {d}).clone();
+            if (y) store(y + b * n, set(xb));
+            if (J) store(J + b * n * d, set.Jacobian_(xb));
+            if (K) store(K + b * n * d * d, set.Jacobian2nd_(xb));
         }
     });
 }

@@ -48,6 +48,12 @@ def lib():
         L.ref_ic_grad_cart2int_matrix.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _dp]
         L.ref_ic_hess_int2cart.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
         L.ref_ic_hess_cart2int.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
+        L.ref_poly_create.restype = C.c_void_p
+        L.ref_poly_create.argtypes = [C.c_int, C.c_int]
+        L.ref_poly_destroy.argtypes = [C.c_void_p]
+        L.ref_poly_nterms.argtypes = [C.c_void_p]
+        L.ref_poly_terms.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.ref_poly_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         for name in ("ref_sap_value", "ref_sap_jacobian", "ref_sap_jacobian_pow", "ref_sap_jacobian2nd"):
             getattr(L, name).argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
         L.ref_set_num_threads(1)
@@ -195,3 +201,33 @@ class RefSAPSet:
         K = np.empty((B, self.nterms, self.sumdim, self.sumdim))
         _check(lib().ref_sap_jacobian2nd(self._h, _p(x), B, _p(K)))
         return K
+
+
+class RefPolynomialSet:
+    """The reference's tchem::polynomial::PolynomialSet(dimension, order)."""
+
+    def __init__(self, dimension, order):
+        self._h = lib().ref_poly_create(int(dimension), int(order))
+        if not self._h:
+            raise RuntimeError("reference raised: " + lib().ref_last_error().decode())
+        self.dimension, self.order = int(dimension), int(order)
+        self.nterms = lib().ref_poly_nterms(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_poly_destroy(self._h)
+            self._h = None
+
+    def terms(self):
+        n = lib().ref_poly_terms(self._h, None, None)
+        tp, cs = (C.c_int32 * (self.nterms + 1))(), (C.c_int32 * max(n, 1))()
+        lib().ref_poly_terms(self._h, tp, cs)
+        return [[cs[c] for c in range(tp[i], tp[i + 1])] for i in range(self.nterms)]
+
+    def eval(self, x):
+        x = _in(x)
+        x = x[None] if x.ndim == 1 else x
+        B, d, n = x.shape[0], self.dimension, self.nterms
+        y, J, K = np.empty((B, n)), np.empty((B, n, d)), np.empty((B, n, d, d))
+        _check(lib().ref_poly_eval(self._h, _p(x), B, _p(y), _p(J), _p(K)))
+        return y, J, K

@@ -669,3 +669,39 @@ class SAPSet:
                     K[:, i, col[u], col[v]] = val
                     K[:, i, col[v], col[u]] = val
         return K
+
+
+# ----------------------------------------------------------------------------------------
+# PolynomialSet (source/polynomial/PolynomialSet.cpp:56-179, source/polynomial/Polynomial.cpp:35-160): the
+# non-symmetry-adapted sibling = a SAPSet with one irreducible
+# ----------------------------------------------------------------------------------------
+def polynomial_terms(dimension, order):
+    """All terms up to `order` (PolynomialSet.cpp:60-111): orders ascending; inside an order the
+    dimension-nary counter with former digit >= latter digit, i.e. coords sorted descending and
+    the terms compared from the last coordinate to the first."""
+    import itertools
+    if dimension == 0:
+        return [[]]
+    terms = []
+    for k in range(order + 1):
+        for combo in itertools.combinations_with_replacement(range(dimension), k):
+            terms.append(list(reversed(combo)))
+    return terms
+
+
+class PolynomialSet:
+    def __init__(self, dimension, order=None, terms=None):
+        self.dimension = int(dimension)
+        self.terms = [sorted(t, reverse=True) for t in terms] if terms is not None else polynomial_terms(self.dimension, int(order))
+        text = "".join("    ".join("1,%d" % (c + 1) for c in t) + "\n" for t in self.terms)
+        self._sap = SAPSet(text, 0, [self.dimension])
+        self.nterms = len(self.terms)
+
+    def value(self, x):
+        return self._sap.value(x)
+
+    def jacobian(self, x):
+        return self._sap.jacobian(x)
+
+    def jacobian2nd(self, x):
+        return self._sap.jacobian2nd(x)

@@ -149,8 +149,29 @@ def add_sap_second_order():
         save(name, **g)
 
 
+def polynomial_goldens():
+    """`python make_golden.py poly`: PolynomialSet(dimension, order) of the reference - generated terms,
+    value, Jacobian_, Jacobian2nd_ (known answer of test/polynomial/main.cpp:7-16 included as x[0] of (2, 4))."""
+    rng = np.random.default_rng(77)
+    out = {}
+    for d, o in ((2, 4), (3, 3), (5, 2)):
+        p = ref_lib.RefPolynomialSet(d, o)
+        terms = p.terms()
+        x = rng.standard_normal((8, d)) * 0.6 + 1.0
+        if (d, o) == (2, 4):
+            x[0] = [2.0, 7.0]
+        y, J, K = p.eval(x)
+        key = "d%d_o%d_" % (d, o)
+        out[key + "term_ptr"] = np.cumsum([0] + [len(t) for t in terms]).astype(np.int32)
+        out[key + "coords"] = np.array([c for t in terms for c in t], dtype=np.int32)
+        out.update({key + "x": x, key + "y": y, key + "J": J, key + "K": K})
+    save("ref_polynomial", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "sapK2":
+    if len(sys.argv) > 1 and sys.argv[1] == "poly":
+        polynomial_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sapK2":
         add_sap_second_order()
     else:
         main()

@@ -280,6 +280,37 @@ def test_sap_second_order_jacobian(T):
     assert_parity(host(big.Jacobian2nd_cat([dev(x)])), obig.jacobian2nd(x), "12-coordinate Jacobian2nd_ vs oracle")
 
 
+def test_polynomial_set(T):
+    """tchem::polynomial::PolynomialSet on the SAPSet kernels: reference goldens (term order, value, Jacobian_,
+    Jacobian2nd_), known answer of test/polynomial/main.cpp:7-16, explicit-term constructor, argument checks,
+    a large ragged batch (specialised kernels) against the oracle."""
+    g = golden("ref_polynomial")
+    for d, o in ((2, 4), (3, 3), (5, 2)):
+        k = "d%d_o%d_" % (d, o)
+        tp, cs = g[k + "term_ptr"], g[k + "coords"]
+        P = T.PolynomialSet(d, o)
+        assert [p.coords() for p in P.polynomials()] == [list(cs[tp[i]:tp[i + 1]]) for i in range(len(tp) - 1)]
+        assert P.max_order() == o and P.dimension() == d and len(P.orders()[1]) == d
+        x = dev(g[k + "x"])
+        assert_parity(host(P(x)), g[k + "y"], k + "value")
+        assert_parity(host(P.Jacobian_(x)), g[k + "J"], k + "Jacobian_")
+        assert_parity(host(P.Jacobian2nd_(x)), g[k + "K"], k + "Jacobian2nd_")
+        assert P(x[0]).shape == (len(tp) - 1,) and P.Jacobian2nd(x[0]).shape == (len(tp) - 1, d, d)
+    P = T.PolynomialSet(2, 4)
+    np.testing.assert_array_equal(host(P(torch.tensor([2.0, 7.0], dtype=torch.float64, device="cuda"))),
+                                  [1, 2, 7, 4, 14, 49, 8, 28, 98, 343, 16, 56, 196, 686, 2401])
+    Q = T.PolynomialSet([[1, 0], T.Polynomial([0, 0, 1])], 2)           # x0 x1, x0^2 x1
+    np.testing.assert_array_equal(host(Q(torch.tensor([2.0, 7.0], dtype=torch.float64, device="cuda"))), [14.0, 28.0])
+    with pytest.raises(ValueError):
+        P(torch.ones(3, dtype=torch.float64, device="cuda"))
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((20011, 3)) * 0.6 + 1.0
+    P3, O3 = T.PolynomialSet(3, 3), O.PolynomialSet(3, 3)
+    assert_parity(host(P3(dev(x))), O3.value(x), "PolynomialSet(3,3) value vs oracle")
+    assert_parity(host(P3.Jacobian_(dev(x))), O3.jacobian(x), "PolynomialSet(3,3) Jacobian_ vs oracle")
+    assert_parity(host(P3.Jacobian2nd_(dev(x))), O3.jacobian2nd(x), "PolynomialSet(3,3) Jacobian2nd_ vs oracle")
+
+
 def test_sap_specialised_on_given_coordinates(T):
     """SAPSet::operator() / Jacobian_ on caller-supplied coordinates: large batches run the NVRTC kernel
     specialised to the set, small ones the interpreter; both against the oracle, ragged batch."""

@@ -156,6 +156,22 @@ def test_sap_second_order_jacobian_goldens():
             assert np.abs(fd - K[..., c]).max() < 1e-6 * max(1.0, np.abs(K).max())
 
 
+def test_polynomial_set_goldens():
+    """PolynomialSet(dimension, order) of the reference (oracle/_ref goldens): generated term order, value
+    (known answer of test/polynomial/main.cpp:7-16 is x[0] of the (2, 4) set), Jacobian_, Jacobian2nd_."""
+    g = golden("ref_polynomial")
+    for d, o in ((2, 4), (3, 3), (5, 2)):
+        k = "d%d_o%d_" % (d, o)
+        tp, cs = g[k + "term_ptr"], g[k + "coords"]
+        P = O.PolynomialSet(d, o)
+        assert P.terms == [list(cs[tp[i]:tp[i + 1]]) for i in range(len(tp) - 1)]
+        x = g[k + "x"]
+        assert_parity(P.value(x), g[k + "y"], k + "value")
+        assert_parity(P.jacobian(x), g[k + "J"], k + "Jacobian_")
+        assert_parity(P.jacobian2nd(x), g[k + "K"], k + "Jacobian2nd_")
+    np.testing.assert_array_equal(g["d2_o4_y"][0], [1, 2, 7, 4, 14, 49, 8, 28, 98, 343, 16, 56, 196, 686, 2401])
+
+
 def test_sap_constant_term_only_in_totally_symmetric():
     with pytest.raises(ValueError):
         O.SAPSet("\n1,1\n", 1, [2])

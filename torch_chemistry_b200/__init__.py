@@ -7,6 +7,7 @@ the tests and bench.py. The C++ drop-in classes live in include/tchem/ + host/.
 from ._capi import lib as _lib, LIB_PATH, FileError  # noqa: F401  (import fails if the .so is missing)
 from .intcoord import IntCoordSet  # noqa: F401
 from .sap import SAPSet  # noqa: F401
+from .polynomial import Polynomial, PolynomialSet  # noqa: F401
 from . import workloads, sharding  # noqa: F401
 
 
