@@ -14,6 +14,7 @@
 #include <c10/cuda/CUDAStream.h>
 
 #include <tchem/tchem.hpp>
+#include <tchem/utility.hpp>
 
 #include "../include/tchem_b200.h"
 
@@ -744,3 +745,42 @@ at::Tensor PolynomialSet::Jacobian2nd_(const at::Tensor & x) const {
 at::Tensor PolynomialSet::Jacobian2nd(const at::Tensor & x) const { return Jacobian2nd_(x); }
 
 } } // namespace tchem::polynomial
+
+// ---- tchem::utility (source/utility.cpp) -----------------------------------------------------------------------
+namespace tchem { namespace utility {
+std::vector<double> tensor2vector(const at::Tensor & tensor) {
+    at::Tensor t = tensor.detach().to(at::kCPU, at::kDouble).contiguous().view({-1});
+    return std::vector<double>(t.data_ptr<double>(), t.data_ptr<double>() + t.numel());
+}
+CL::utility::matrix<double> tensor2matrix(const at::Tensor & tensor) {
+    if (tensor.dim() != 2) throw std::invalid_argument("tchem::utility::tensor2matrix: tensor must be a matrix");
+    at::Tensor t = tensor.detach().to(at::kCPU, at::kDouble).contiguous();
+    CL::utility::matrix<double> m(t.size(0), t.size(1));
+    for (int64_t i = 0; i < t.size(0); i++)
+    for (int64_t j = 0; j < t.size(1); j++) m[i][j] = t.data_ptr<double>()[i * t.size(1) + j];
+    return m;
+}
+at::Tensor read_vector(std::ifstream & ifs) {
+    std::vector<double> v;
+    std::string tok;
+    while (ifs >> tok) {
+        try { v.push_back(std::stod(tok)); } catch (...) { break; }
+    }
+    return at::tensor(v, at::TensorOptions().dtype(at::kDouble));
+}
+at::Tensor read_vector(const std::string & file) {
+    std::ifstream ifs(file);
+    if (!ifs.good()) throw CL::utility::file_error(file);
+    return read_vector(ifs);
+}
+size_t NParameters(const std::vector<at::Tensor> & parameters) {
+    size_t n = 0;
+    for (const at::Tensor & p : parameters) n += (size_t)p.numel();
+    return n;
+}
+double NetGradNorm(const std::vector<at::Tensor> & parameters) {
+    double norm = 0.0;
+    for (const at::Tensor & p : parameters) if (p.grad().defined()) norm += p.grad().abs().sum().item<double>();
+    return norm;
+}
+} }

@@ -39,3 +39,63 @@ def test_cpp_drop_in_classes(tmp_path):
     print(p.stderr[-2000:])
     assert p.returncode == 0, p.stdout[-3000:]
     assert "FAIL" not in p.stdout
+
+
+REF_EXE = os.path.join(ROOT, "host", "ref_test_intcoord.exe")
+ANG = 1.8897261339212517
+
+
+def _write_xyz(path, r_bohr):
+    xyz = np.asarray(r_bohr).reshape(-1, 3) / ANG
+    with open(path, "w") as f:
+        f.write("%d\n\n" % len(xyz))
+        for a in xyz:
+            f.write("X %.17e %.17e %.17e\n" % tuple(a))
+
+
+@pytest.mark.gpu
+def test_reference_own_test_program_runs_unchanged_on_the_drop_in(tmp_path):
+    """host/ref_test_intcoord.exe is the reference's OWN test/intcoord/main.cpp, compiled where it lies
+    (host/Makefile, build container only) against include/tchem + include/CppLibrary and linked with
+    host/libtchem.so - not one line of it changed. Its inputs are rebuilt here from the goldens (the
+    reference's fixture texts and geometries). It prints residuals ("Correct routines should print close
+    to 0", no exit status); the bounds below are what the reference itself prints:
+    <= 2e-13 everywhere except the 8-decimal Columbus comparison (5e-4), the finite-difference checks and
+    the operator() vs compute_IC_J torsion at the exactly planar geometry (4e-8, acos conditioning)."""
+    if not os.path.exists(REF_EXE):
+        pytest.skip("host/ref_test_intcoord.exe not built (needs /root/reference at build time)")
+    d, c, a, ig = golden("ref_aniline_default"), golden("ref_aniline_columbus7"), golden("ref_aniline_advanced"), golden("ref_aniline_intgeom")
+    (tmp_path / "IntCoordDef").write_text(str(d["definition"]))
+    (tmp_path / "intcfl").write_text(str(c["definition"]))
+    (tmp_path / "advanced_IntCoordDef").write_text(str(a["definition"]))
+    _write_xyz(tmp_path / "slow-1.5.xyz", d["r"][0])
+    _write_xyz(tmp_path / "min-B1.xyz", d["r"][2])
+    _write_xyz(tmp_path / "B1rot-2.2.xyz", d["r"][4])
+    with open(tmp_path / "geom", "w") as f:                      # Columbus: symbol Z x y z mass (bohr)
+        for at in ig["geom"].reshape(-1, 3):
+            f.write(" X 1. %.17e %.17e %.17e 1.0\n" % tuple(at))
+    np.savetxt(tmp_path / "intgeom", ig["intgeom"], fmt="%.8f")
+    p = subprocess.run([REF_EXE], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    print(p.stdout)
+    print(p.stderr[-3000:])
+    assert p.returncode == 0, p.stderr[-3000:]
+    vals = {}
+    for line in p.stdout.splitlines():
+        if ":" in line and not line.startswith("This"):
+            k, v = line.rsplit(":", 1)
+            try:
+                vals[k.strip()] = [abs(float(t)) for t in v.split()]
+            except ValueError:
+                pass
+    bounds = {"Columbus7 format internal coordinate": 1e-3,
+              "Internal coordinates calculated with Jacobians": 1e-12,
+              "Jacobian calculated with 2nd order Jacobian": 1e-12,
+              "Finite difference vs analytical Jacobian": 1e-4,
+              "Default internal coordinate and Jacobian": 5e-5,       # the two fixtures hold the geometry to 6-8 digits (observed 8e-6)
+              "Advanced internal coordinates": 1e-12,
+              "Analytical Jacobian vs finite difference": 1e-3,
+              "Advanced internal coordinates calculated with Jacobians": 1e-7,
+              "Gradient and Hessian transformations": 1e-9}
+    for k, b in bounds.items():
+        assert k in vals, "missing line: " + k + "\n" + p.stdout
+        assert max(vals[k]) <= b, "%s: %s > %g" % (k, vals[k], b)
