@@ -17,3 +17,15 @@ for key, n in (("C1", 10000), ("C2", 10000), ("C1", 100000)):
     torch.cuda.synchronize()
     py = (time.perf_counter() - t0) / 500 * 1e3
     print("%s B=%d: C-loop %.4f ms/launch, python-loop %.4f ms/call" % (key, n, ms.value, py))
+    # the same call captured once in a CUDA graph and replayed (what a caller looping over small batches would do)
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        s.compute_IC_J(r, out=(q, J)); side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(20): s.compute_IC_J(r, out=(q, J))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(25): g.replay()
+    torch.cuda.synchronize()
+    print("%s B=%d: CUDA graph of 20 launches: %.4f ms/launch" % (key, n, (time.perf_counter() - t0) / 500 * 1e3))
