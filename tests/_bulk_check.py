@@ -3,6 +3,7 @@ once per process, so each setting runs in a subprocess. Evaluates q + J through 
 kernel on three table shapes - even cartdim (C2H4), odd cartdim with even row count (5 atoms, 8
 rows: J and q as bulk copies), even cartdim with odd row count (4 atoms, 5 rows: q rows through the
 warp copy) - checks a subsample against the oracle and prints a digest of all the bytes."""
+import ctypes as C
 import hashlib
 import os
 import sys
@@ -55,6 +56,15 @@ def main():
         qo, Jo = O.IntCoordSet("default", text).qJ(r[idx])
         assert_parity(J[idx], Jo, name + " J vs oracle")
         assert np.abs(q[idx] - qo).max() < 1e-9, name
+        # J-only and q-only calls through the C ABI write the same bytes
+        rd = torch.from_numpy(np.ascontiguousarray(r)).cuda()
+        q1 = torch.zeros(len(r), s.intdim, dtype=torch.float64, device="cuda")
+        J1 = torch.zeros(len(r), s.intdim, s.cartdim, dtype=torch.float64, device="cuda")
+        capi.check(capi.lib.tchem_ic_eval(s._handle, C.c_void_p(rd.data_ptr()), len(r), C.c_void_p(q1.data_ptr()), None, None, 0, None))
+        capi.check(capi.lib.tchem_ic_eval(s._handle, C.c_void_p(rd.data_ptr()), len(r), None, C.c_void_p(J1.data_ptr()), None, 0, None))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(q1.cpu().numpy(), q)
+        np.testing.assert_array_equal(J1.cpu().numpy(), J)
         h.update(q.tobytes())
         h.update(J.tobytes())
     print("DIGEST", h.hexdigest())
