@@ -205,6 +205,120 @@ grad_int2cart_warp_kernel(const GradProgram gp, const double * __restrict__ r, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Two geometries per warp pass. The warp-per-geometry kernel above is bound by the latency of its
+// dependent FP64 chains (rsqrt -> products -> blocks; ~25 % of the FP64 pipe at 12-16 warps per SM).
+// Pair<double> is a scalar type that carries the same quantity of TWO geometries: the J formulas of
+// ic_math.cuh are templates over the scalar type, so instantiating them on Pair evaluates geometry
+// b and b + 1 in one pass with two independent instruction streams (ILP 2) and one table walk.
+// ---------------------------------------------------------------------------------------
+struct Pair { double a, b; };
+__device__ __forceinline__ Pair mkp(double a, double b) { Pair r; r.a = a; r.b = b; return r; }
+__device__ __forceinline__ Pair operator+(Pair x, Pair y) { return mkp(x.a + y.a, x.b + y.b); }
+__device__ __forceinline__ Pair operator-(Pair x, Pair y) { return mkp(x.a - y.a, x.b - y.b); }
+__device__ __forceinline__ Pair operator-(Pair x) { return mkp(-x.a, -x.b); }
+__device__ __forceinline__ Pair operator*(Pair x, Pair y) { return mkp(x.a * y.a, x.b * y.b); }
+__device__ __forceinline__ Pair operator+(double c, Pair x) { return mkp(c + x.a, c + x.b); }
+__device__ __forceinline__ Pair operator-(double c, Pair x) { return mkp(c - x.a, c - x.b); }
+__device__ __forceinline__ Pair operator*(double c, Pair x) { return mkp(c * x.a, c * x.b); }
+__device__ __forceinline__ Pair operator*(Pair x, double c) { return mkp(c * x.a, c * x.b); }
+__device__ __forceinline__ Pair sqrt_(Pair x) { return mkp(sqrt(x.a), sqrt(x.b)); }
+__device__ __forceinline__ Pair rcp_(Pair x) { return mkp(1.0 / x.a, 1.0 / x.b); }
+__device__ __forceinline__ Pair rsqrt_(Pair x) { return mkp(rsqrt(x.a), rsqrt(x.b)); }
+
+template <int DUMMY>
+__global__ void __launch_bounds__(128, 3)
+grad_int2cart_pair_kernel(const GradProgram gp, const double * __restrict__ r, const double * __restrict__ gq,
+                          const int64_t B, double * __restrict__ gr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    PrimDesc * prims = reinterpret_cast<PrimDesc *>(smem_raw);
+    size_t off = a16(sizeof(PrimDesc) * gp.nwprims);
+    int32_t * use_ptr = reinterpret_cast<int32_t *>(smem_raw + off);  off += a16(4 * (gp.nwprims + 1));
+    GradUse * uses = reinterpret_cast<GradUse *>(smem_raw + off);     off += a16(sizeof(GradUse) * gp.nwuses);
+    int32_t * comp_ptr = reinterpret_cast<int32_t *>(smem_raw + off); off += a16(4 * (gp.cartdim + 1));
+    int32_t * comp_idx = reinterpret_cast<int32_t *>(smem_raw + off); off += a16(4 * gp.ncomp_idx);
+    {
+        auto copy4 = [&](const void * src, void * dst, int n4) {
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<int32_t *>(dst)[i] = reinterpret_cast<const int32_t *>(src)[i];
+        };
+        copy4(gp.wprims, prims, gp.nwprims * (int)(sizeof(PrimDesc) / 4));
+        copy4(gp.wuse_ptr, use_ptr, gp.nwprims + 1);
+        copy4(gp.wuses, uses, gp.nwuses * (int)(sizeof(GradUse) / 4));
+        copy4(gp.comp_ptr, comp_ptr, gp.cartdim + 1);
+        copy4(gp.comp_idx, comp_idx, gp.ncomp_idx);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cartdim = gp.cartdim, intdim = gp.intdim, nslots = gp.nslots;
+    // per warp: coordinates and weights of both geometries (rows b, b + 1 are adjacent in global memory),
+    // then the two slot buffers
+    const size_t per_warp = (size_t)((2 * (cartdim + intdim + nslots) + 1) & ~1);
+    double * rs = reinterpret_cast<double *>(smem_raw + off) + (size_t)warp * per_warp;   // [2][cartdim]
+    double * qs = rs + 2 * cartdim;                                                       // [2][intdim]
+    double * SA = qs + 2 * intdim, * SB = SA + nslots;
+    const int64_t npairs = (B + 1) / 2, pstep = (int64_t)gridDim.x * nwarps;
+    for (int64_t pi = (int64_t)blockIdx.x * nwarps + warp; pi < npairs; pi += pstep) {
+        const int64_t b = 2 * pi;
+        const bool two = b + 1 < B;                           // warp-uniform
+        // a lone last geometry is evaluated twice (the second copy is never stored)
+        const int nr = two ? 2 * cartdim : cartdim, nq = two ? 2 * intdim : intdim;
+        for (int k = lane; k < 2 * cartdim; k += kLanes) rs[k] = r[b * cartdim + (k < nr ? k : k - cartdim)];
+        for (int k = lane; k < 2 * intdim; k += kLanes) qs[k] = gq[b * intdim + (k < nq ? k : k - intdim)];
+        __syncwarp();
+        for (int p = lane; p < gp.nwprims; p += kLanes) {
+            const PrimDesc pd = prims[p];
+            if (pd.natoms == 0) continue;                  // padding / dummy
+            double WA = 0.0, WB = 0.0;
+            for (int u = use_ptr[p]; u < use_ptr[p + 1]; u++) {
+                const GradUse gu = uses[u];
+                WA = fma(gu.coef, qs[gu.ic], WA);
+                WB = fma(gu.coef, qs[intdim + gu.ic], WB);
+            }
+            V3<Pair> a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < pd.natoms) {
+                    const double * ra = rs + 3 * pd.atoms[i], * rb = ra + cartdim;
+                    a[i] = v3<Pair>(mkp(ra[0], rb[0]), mkp(ra[1], rb[1]), mkp(ra[2], rb[2]));
+                }
+            double * sa = SA + pd.out, * sb = SB + pd.out;
+            auto emit = [&](int i, const V3<Pair> & J) {
+                sa[3 * i] = WA * J.x.a; sa[3 * i + 1] = WA * J.y.a; sa[3 * i + 2] = WA * J.z.a;
+                sb[3 * i] = WB * J.x.b; sb[3 * i + 1] = WB * J.y.b; sb[3 * i + 2] = WB * J.z.b;
+            };
+            Pair q, sp = mkp(0.0, 0.0), cp = sp, st = sp;
+            switch (pd.type) {
+            case TCHEM_STRETCHING: stretching_J<Pair>(a, q, emit); break;
+            case TCHEM_BENDING:    bending_J<Pair, false>(a, q, emit); break;
+            case TCHEM_COSBENDING: bending_J<Pair, true>(a, q, emit); break;
+            case TCHEM_TORSION:    torsion_J<Pair, 0>(a, sp, cp, st, emit); break;
+            case TCHEM_SINTORSION: torsion_J<Pair, 1>(a, sp, cp, st, emit); break;
+            case TCHEM_COSTORSION: torsion_J<Pair, 2>(a, sp, cp, st, emit); break;
+            case TCHEM_OUTOFPLANE: oop_J<Pair, false>(a, q, emit); break;
+            case TCHEM_SINOOP:     oop_J<Pair, true>(a, q, emit); break;
+            default: break;
+            }
+        }
+        __syncwarp();
+        for (int c = lane; c < cartdim; c += kLanes) {
+            const int k0 = comp_ptr[c], k1 = comp_ptr[c + 1];
+            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+            int k = k0;
+            for (; k + 1 < k1; k += 2) {
+                const int i0 = comp_idx[k], i1 = comp_idx[k + 1];
+                s0 += SA[i0]; s1 += SA[i1];
+                t0 += SB[i0]; t1 += SB[i1];
+            }
+            if (k < k1) { s0 += SA[comp_idx[k]]; t0 += SB[comp_idx[k]]; }
+            gr[b * cartdim + c] = s0 + s1;
+            if (two) gr[(b + 1) * cartdim + c] = t0 + t1;
+        }
+        __syncwarp();
+    }
+}
+
 } // namespace
 
 struct GradTable {
@@ -355,6 +469,23 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
                         + a16(4 * (gp.cartdim + 1)) + a16(4 * gp.ncomp_idx);
         const size_t pw = (size_t)((gp.cartdim + gp.intdim + gp.nslots + 1) & ~1) * sizeof(double);
         const int wwarps = 4;
+        // two geometries per warp pass (ILP 2) for tables without 5-atom terms; TCHEM_GRAD_PAIR=0 keeps one
+        static const bool use_pair = [] { const char * e = getenv("TCHEM_GRAD_PAIR"); return e && atoi(e) != 0; }();   // opt-in until measured
+        const size_t pw2 = (size_t)((2 * (gp.cartdim + gp.intdim + gp.nslots) + 1) & ~1) * sizeof(double);
+        if (!force_tile && use_pair && !t->has5 && tb + wwarps * pw2 <= (size_t)t->max_smem_optin / 2) {
+            const void * pfn = reinterpret_cast<const void *>(&grad_int2cart_pair_kernel<0>);
+            const size_t psmem = tb + wwarps * pw2;
+            TC_CUDA(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            int per_sm = 0;
+            TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfn, wwarps * 32, psmem));
+            if (per_sm < 1) per_sm = 1;
+            const int64_t npairs = (B + 1) / 2;
+            const int64_t grid = std::min<int64_t>((npairs + wwarps - 1) / wwarps, (int64_t)t->sm_count * per_sm);
+            void * args[] = {(void *)&gp, (void *)&r, (void *)&intgrad, (void *)&B, (void *)&cartgrad};
+            TC_CUDA(cudaLaunchKernel(pfn, dim3((unsigned)grid), dim3(wwarps * 32), args, psmem, static_cast<cudaStream_t>(stream)));
+            count_launch();
+            return TCHEM_OK;
+        }
         const size_t wsmem = tb + wwarps * pw;
         if (!force_tile && wsmem <= (size_t)t->max_smem_optin / 2) {
             const void * wfn = t->has5 ? reinterpret_cast<const void *>(&grad_int2cart_warp_kernel<true>)
