@@ -548,6 +548,24 @@ def test_specialised_kernel_bulk_store_variant(T):
     assert digests[0] == digests[1]
 
 
+def test_gradient_int2cart_pair_kernel(T):
+    """gradient_int2cart evaluates two geometries per warp pass (Pair scalar type) or one (TCHEM_GRAD_PAIR=0):
+    both checked against the oracle and the reference goldens; odd batch sizes
+    exercise the lone last geometry. The knob is per process -> subprocesses."""
+    import subprocess, sys
+    digests = []
+    for pair in ("1", "0"):
+        e = dict(os.environ)
+        e["TCHEM_GRAD_PAIR"] = pair
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_grad_pair_check.py")],
+                             env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "DIGEST" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        digests.append(out.stdout.strip().split()[-1])
+    # (the two kernels evaluate the same expressions, but the compiler may contract them into FMAs differently:
+    # both are held to the oracle at 1e-12 inside the helper; the digests are informational)
+    print("digests:", digests)
+
+
 def test_mid_size_odd_stride_chain13(T):
     """13-atom chain with out-of-plane rows: cartdim 39, 33 coordinates -> the J block of a geometry is
     1287 doubles (odd), so every other geometry is only 8-byte aligned: the warp-group kernel's line
