@@ -486,6 +486,48 @@ std::vector<at::Tensor> SAP::gradient_(const std::vector<at::Tensor> & xs, at::T
     return views;
 }
 
+// source/polynomial/SAP.cpp:177-322: diagonal p (p-1) x^(p-2) prod_{others}, strict upper triangle
+// p_u p_v x_u^(p_u-1) x_v^(p_v-1) prod_{others}; the lower triangle is left zero as in the reference
+CL::utility::matrix<at::Tensor> SAP::Hessian_(const std::vector<at::Tensor> & xs, at::Tensor & hess) const {
+    for (const at::Tensor & x : xs) if (x.dim() != 1) throw std::invalid_argument("tchem::polynomial::SAP::Hessian_: x must be a vector");
+    int64_t dimension = 0;
+    for (const at::Tensor & x : xs) dimension += x.size(0);
+    hess = xs[0].new_zeros({dimension, dimension});
+    CL::utility::matrix<at::Tensor> hesses(xs.size());
+    std::vector<int64_t> start(xs.size() + 1, 0);
+    for (size_t i = 0; i < xs.size(); i++) start[i + 1] = start[i] + xs[i].size(0);
+    for (size_t i = 0; i < xs.size(); i++)
+    for (size_t j = i; j < xs.size(); j++)
+    hesses[i][j] = hess.slice(0, start[i], start[i + 1]).slice(1, start[j], start[j + 1]);
+    auto power = [&](size_t k, int64_t p) { return at::pow(xs[uniques_orders_[k].first.first][uniques_orders_[k].first.second], (double)p); };
+    const size_t n = uniques_orders_.size();
+    for (size_t i = 0; i < n; i++) {
+        const auto & ui = uniques_orders_[i];
+        const int64_t pi = (int64_t)ui.second;
+        if (pi >= 2) {
+            at::Tensor el = (double)(pi * (pi - 1)) * power(i, pi - 2);
+            for (size_t k = 0; k < n; k++) if (k != i) el = el * power(k, (int64_t)uniques_orders_[k].second);
+            hesses[ui.first.first][ui.first.first][ui.first.second][ui.first.second] = el;
+        }
+        for (size_t j = i + 1; j < n; j++) {
+            const auto & uj = uniques_orders_[j];
+            const int64_t pj = (int64_t)uj.second;
+            at::Tensor el = (double)(pi * pj) * power(i, pi - 1) * power(j, pj - 1);
+            for (size_t k = 0; k < n; k++) if (k != i && k != j) el = el * power(k, (int64_t)uniques_orders_[k].second);
+            hesses[ui.first.first][uj.first.first][ui.first.second][uj.first.second] = el;
+        }
+    }
+    return hesses;
+}
+CL::utility::matrix<at::Tensor> SAP::Hessian_(const std::vector<at::Tensor> & xs) const {
+    at::Tensor hess;
+    CL::utility::matrix<at::Tensor> views = Hessian_(xs, hess);
+    for (size_t i = 0; i < xs.size(); i++)
+    for (size_t j = i; j < xs.size(); j++) views[i][j] = views[i][j].clone();
+    return views;
+}
+CL::utility::matrix<at::Tensor> SAP::Hessian(const std::vector<at::Tensor> & xs) const { return Hessian_(xs); }
+
 // ---- SAPSet ------------------------------------------------------------------------------------
 SAPSet::SAPSet() {}
 SAPSet::SAPSet(const std::string & sapoly_file, const size_t & _irreducible, const std::vector<size_t> & _dimensions)

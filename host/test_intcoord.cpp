@@ -158,6 +158,16 @@ int main(int argc, char ** argv) {
         fderr = std::max(fderr, maxabs((Jp - Jm) / 2e-5 - cat_K.select(-1, c)));
     }
     report("Jacobian2nd_ = d Jacobian_ / dx (central differences)", fderr, 1e-6);
+    // per-term Hessians (at:: arithmetic) = upper triangle of the set's rows
+    double herr = 0.0;
+    for (size_t k = 0; k < set1.SAPs().size(); k++) {
+        at::Tensor hk;
+        set1[k].Hessian_(xs, hk);
+        herr = std::max(herr, maxabs(hk - at::triu(cat_K[k])));
+        auto hb = set1[k].Hessian(xs);
+        herr = std::max(herr, maxabs(hb[0][1] - cat_K[k].slice(0, 0, 2).slice(1, 2, 4)));
+    }
+    report("SAP::Hessian variants = upper triangle of Jacobian2nd_ rows", herr, 1e-13);
     report("constant term only in the totally symmetric irreducible",
            throws<std::invalid_argument>([&] { tchem::polynomial::SAPSet bad(dir + "sap1.in", 1, {2, 2}); }) ? 0 : 1, 0);
 

@@ -1,5 +1,6 @@
 // tchem::polynomial::SAP - drop-in for include/tchem/polynomial/SAP.hpp of Torch-Chemistry,
-// value and gradient (the Hessian members are outside the B200 hot path and not provided).
+// value, gradient and Hessian of one monomial (per-term helpers in at:: tensor arithmetic, like the
+// reference's autograd-friendly variants; the batched work goes through SAPSet).
 #ifndef tchem_polynomial_SAP_hpp
 #define tchem_polynomial_SAP_hpp
 
@@ -33,6 +34,11 @@ class SAP {
         std::vector<at::Tensor> gradient(const std::vector<at::Tensor> & xs) const;
         std::vector<at::Tensor> gradient_(const std::vector<at::Tensor> & xs) const;
         std::vector<at::Tensor> gradient_(const std::vector<at::Tensor> & xs, at::Tensor & grad) const;
+        // ddP / dx^2: blocks hesses[i][j] (j >= i), upper triangle only (source/polynomial/SAP.cpp:177-322);
+        // `hess` harvests the concatenated [sumdim][sumdim] matrix the blocks are views of
+        CL::utility::matrix<at::Tensor> Hessian(const std::vector<at::Tensor> & xs) const;
+        CL::utility::matrix<at::Tensor> Hessian_(const std::vector<at::Tensor> & xs) const;
+        CL::utility::matrix<at::Tensor> Hessian_(const std::vector<at::Tensor> & xs, at::Tensor & hess) const;
 };
 
 } }
