@@ -45,6 +45,25 @@ namespace {
 
 constexpr int kDenseThreads = 256;
 
+// -DTCHEM_DENSE_PHASES: block 0 accumulates the clock cycles of each phase of its geometries in
+// g_dense_phase (read back through tchem_debug_dense_phases; tools/dense_phases.py). Off in the product.
+#ifdef TCHEM_DENSE_PHASES
+__device__ unsigned long long g_dense_phase[32];
+// (a clock read right after __syncthreads captures the barrier's issue, not its release: the read is made
+// to depend on a shared-memory load, which is where the deferred block fires)
+__device__ __forceinline__ long long phase_clock(const int * probe) {
+    const int x = *reinterpret_cast<const volatile int *>(probe);
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(x) : "memory");
+    return t;
+}
+#define PHASE_BEGIN() __shared__ int ph_probe; long long ph_t0 = phase_clock(&ph_probe)
+#define PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long ph_t = phase_clock(&ph_probe); g_dense_phase[i] += (unsigned long long)(ph_t - ph_t0); ph_t0 = ph_t; } } while (0)
+#else
+#define PHASE_BEGIN() do {} while (0)
+#define PHASE(i) do {} while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------
 // DMMA: D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragments (PTX ISA, mma.m8n8k4 .f64):
 //   a : row = lane >> 2, col = lane & 3          b : row = lane & 3, col = lane >> 2
@@ -66,50 +85,66 @@ __device__ __forceinline__ void dmma(double & d0, double & d1, double a, double 
 // row / column instead of predicating every load: D[m][n] only depends on row m of A and column n
 // of B, and the duplicated rows are simply not stored. K is walked in unpredicated steps of 4 with
 // one masked tail step.
-template <bool TA, bool TB, bool ACC, int TRI = 0, int KS = 0>
-__device__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
-                            double * C, int ldc, double s = 1.0) {
+template <bool TA, bool TB, bool ACC, int TRI, int KS, int WN>
+__device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
+                                                  double * C, int ldc, double s) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int tm = (M + 15) >> 4, tn = (N + 15) >> 4;
+    constexpr int TW = 8 * WN;                                // tile width (columns of C)
+    const int tm = (M + 15) >> 4, tn = (N + TW - 1) / TW;
     const int K4 = K & ~3;
     const int sa = TA ? lda : 1, sb = TB ? 1 : ldb;          // stride between consecutive k
     int mt = 0, nt = warp;                                    // tile coordinates, advanced without division
     while (nt >= tn) { nt -= tn; mt++; }
     for (; mt < tm; ) {
         if (TRI == 0 || nt <= mt) {
-            const int m0 = mt * 16, n0 = nt * 16;
+            const int m0 = mt * 16, n0 = nt * TW;
             const int kbeg = KS == 1 ? m0 : KS == 2 ? n0 : 0;
-            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-            const double * pa[2], * pb[2];
+            double acc[2][WN][2];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < WN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double * pa[2], * pb[WN];
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const int m = min(m0 + 8 * i + gid, M - 1), n = min(n0 + 8 * i + gid, N - 1);
+                const int m = min(m0 + 8 * i + gid, M - 1);
                 pa[i] = A + (TA ? m : m * lda) + tig * sa;
-                pb[i] = B + (TB ? n * ldb : n) + tig * sb;
+            }
+#pragma unroll
+            for (int j = 0; j < WN; j++) {
+                const int n = min(n0 + 8 * j + gid, N - 1);
+                pb[j] = B + (TB ? n * ldb : n) + tig * sb;
             }
 #pragma unroll 2
             for (int k0 = kbeg; k0 < K4; k0 += 4) {
-                const double a0 = pa[0][k0 * sa], a1 = pa[1][k0 * sa], b0 = pb[0][k0 * sb], b1 = pb[1][k0 * sb];
-                dmma(acc[0][0][0], acc[0][0][1], a0, b0);
-                dmma(acc[0][1][0], acc[0][1][1], a0, b1);
-                dmma(acc[1][0][0], acc[1][0][1], a1, b0);
-                dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+                double a[2], b[WN];
+#pragma unroll
+                for (int i = 0; i < 2; i++) a[i] = pa[i][k0 * sa];
+#pragma unroll
+                for (int j = 0; j < WN; j++) b[j] = pb[j][k0 * sb];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
             if (K4 < K) {
                 const bool in = K4 + tig < K;
                 const int k0 = in ? K4 : K - 1 - tig;        // clamped address, value masked
-                const double a0 = in ? pa[0][k0 * sa] : 0.0, a1 = in ? pa[1][k0 * sa] : 0.0;
-                const double b0 = in ? pb[0][k0 * sb] : 0.0, b1 = in ? pb[1][k0 * sb] : 0.0;
-                dmma(acc[0][0][0], acc[0][0][1], a0, b0);
-                dmma(acc[0][1][0], acc[0][1][1], a0, b1);
-                dmma(acc[1][0][0], acc[1][0][1], a1, b0);
-                dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+                double a[2], b[WN];
+#pragma unroll
+                for (int i = 0; i < 2; i++) a[i] = in ? pa[i][k0 * sa] : 0.0;
+#pragma unroll
+                for (int j = 0; j < WN; j++) b[j] = in ? pb[j][k0 * sb] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
+                for (int j = 0; j < WN; j++) {
                     const int m = m0 + 8 * i + gid, n = n0 + 8 * j + 2 * tig;
                     if (m < M) {
                         if (n < N)     C[m * ldc + n]     = (ACC ? C[m * ldc + n] : 0.0) + s * acc[i][j][0];
@@ -124,6 +159,22 @@ __device__ void block_dgemm(int M, int N, int K, const double * A, int lda, cons
         nt += nwarps;
         while (nt >= tn) { nt -= tn; mt++; }
     }
+}
+
+// Warp tiles are 16 x 16 (2 x 2 DMMA tiles) or, for the full (non-triangular) products, 16 x 24 when
+// that shape hands the block's warps fewer DMMA steps: C4's 84 x 90 and 90 x 90 results are 36 tiles
+// of 16 x 16 (4.5 rounds of 8 warps -> 5) but 24 tiles of 16 x 24 (3 rounds exactly, 10 % fewer DMMAs
+// on the critical path and 5 instead of 6 fragment loads per 6 DMMAs).
+template <bool TA, bool TB, bool ACC, int TRI = 0, int KS = 0>
+__device__ __forceinline__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
+                                            double * C, int ldc, double s = 1.0) {
+    if (TRI == 0 && KS == 0) {
+        const int nwarps = blockDim.x >> 5, tm = (M + 15) >> 4;
+        const int steps2 = 2 * ((tm * ((N + 15) / 16) + nwarps - 1) / nwarps);
+        const int steps3 = 3 * ((tm * ((N + 23) / 24) + nwarps - 1) / nwarps);
+        if (steps3 < steps2) { block_dgemm_tiles<TA, TB, ACC, 0, 0, 3>(M, N, K, A, lda, B, ldb, C, ldc, s); return; }
+    }
+    block_dgemm_tiles<TA, TB, ACC, TRI, KS, 2>(M, N, K, A, lda, B, ldb, C, ldc, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -156,8 +207,13 @@ struct HessSink {                      // H[.][.] += w * K_term   (shared accumu
     __device__ __forceinline__ void jac_block(const int *, int, const V3<double> &) const {}
     __device__ __forceinline__ void jac_entry(const int *, int, double) const {}
     __device__ __forceinline__ void add(int r, int c, double v, bool mirror) const {
+#ifdef TCHEM_GK_PLAIN        // timing experiment only (racy): what the phase costs without the CAS loops
+        H[r * ld + c] += v;
+        if (mirror) H[c * ld + r] += v;
+#else
         atomicAdd(H + r * ld + c, v);
         if (mirror) atomicAdd(H + c * ld + r, v);
+#endif
     }
     // tangent direction (atom j, component l) of block i: entry (k, l) of block (i, j), i <= j,
     // mirrored into block (j, i) like source/IC/InvDisp.cpp:869-876
@@ -265,62 +321,90 @@ __device__ __forceinline__ void block_store(const double * s, double * __restric
 // Returns false (all threads) when a pivot is not positive.
 constexpr int kNB = 16;
 
-// lanes 0..15 = rows of the diagonal block at D (bs <= 16 rows): in-place lower Cholesky factor;
-// dinv[j] = 1 / L[j][j]. Lanes / columns >= bs carry an identity so every lane runs the same code.
-__device__ __forceinline__ bool warp_potrf16(double * D, int ld, int bs, double * dinv, int lane) {
-    double a[kNB];
-    const bool live = lane < bs;
+// In-place lower Cholesky factor of the diagonal block at D (bs <= 16 rows); dinv[j] = 1 / L[j][j].
+// One warp runs this while the block waits, and what it costs is that warp's instruction count and the
+// chain of 16 dependent pivots, so both are kept short:
+//  * lane = (row i, column half h): 8 columns of one row in registers, all 32 lanes busy; the pivot column
+//    reaches the other lanes through 2 x 16 doubles of scratch (one store, four 16-byte broadcast loads)
+//    instead of one shuffle per column;
+//  * the columns stay UNSCALED during the elimination (u = L sqrt(d), the L D L^T recurrence), which leaves
+//    on the chain, per pivot, one reciprocal, one multiply and one fma - local to the lane that owns the
+//    next pivot - and one broadcast:   d[j+1] = a[j+1][j+1] - u[j+1][j] * (u[j+1][j] / d[j]);
+//    the 16 values 1 / sqrt(d[j]) that turn u into L are taken once, in parallel, at the end.
+// Rows / columns >= bs carry an identity so every lane runs the same code. scr: 80 doubles of SHARED memory,
+// 16-byte aligned.
+__device__ __forceinline__ bool warp_potrf16(double * D, int ld, int bs, double * dinv, double * scr, int lane) {
+    const int i = lane & 15, h = lane >> 4;
+    const bool live = i < bs;
+    double a[8];
 #pragma unroll
-    for (int k = 0; k < kNB; k++) a[k] = (live && k <= lane) ? D[lane * ld + k] : (k == lane ? 1.0 : 0.0);
-    // Software-pipelined over the pivots: the element the NEXT pivot depends on is updated first and
-    // its 1/sqrt started, the rest of this column's rank-1 update then runs under that latency.
-    // (1/sqrt rather than sqrt followed by a division: one dependent chain; sqrt = d * isd, corrected)
-    double d = __shfl_sync(0xffffffffu, a[0], 0);
-    bool ok = d > 0.0;
-    double isd = rsqrt(d);
+    for (int c = 0; c < 8; c++) {
+        const int k = 8 * h + c;
+        a[c] = (live && k <= i) ? D[i * ld + k] : (k == i ? 1.0 : 0.0);
+    }
+    double d = __shfl_sync(0xffffffffu, a[0], 0), mydiag = 1.0;
+    bool ok = true;
 #pragma unroll
     for (int j = 0; j < kNB; j++) {
-        const double dj = d, isdj = isd;
-        if (lane > j) a[j] *= isdj;
-        if (j + 1 < kNB) {
-            const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
-            if (lane >= j + 1) a[j + 1] = fma(-a[j], l1, a[j + 1]);
-            d = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
-            ok = ok && d > 0.0;
-            isd = rsqrt(d);
+        const int hj = j >> 3, jj = j & 7;                          // static after unrolling
+        double * colu = scr + 32 * (j & 1), * colt = colu + 16;     // double buffered: one __syncwarp per pivot
+        ok = ok && d > 0.0;
+        if (i == j) mydiag = d;
+        const double r = __drcp_rn(d);
+        const double t = a[jj] * r;                                 // u[i][j] / d[j] where h == hj
+        if (jj < 7) {                                               // the next pivot lives in the same lane half
+            const double dn = fma(-a[jj], t, a[jj + 1]);
+            d = __shfl_sync(0xffffffffu, dn, j + 1 + 16 * hj);
         }
-        double l[kNB];
+        if (h == hj) { colu[i] = a[jj]; colt[i] = t; }
+        __syncwarp();
+        const double u = colu[i];
+        double tk[8];
 #pragma unroll
-        for (int k = 0; k < kNB; k++)
-            if (k > j + 1) l[k] = __shfl_sync(0xffffffffu, a[j], k);
-#pragma unroll
-        for (int k = 0; k < kNB; k++)
-            if (k > j + 1 && lane >= k) a[k] = fma(-a[j], l[k], a[k]);
-        if (lane == j) {
-            double sd = dj * isdj;
-            sd = fma(fma(-sd, sd, dj), 0.5 * isdj, sd);
-            a[j] = sd;
-            if (live) dinv[j] = isdj;
+        for (int c = 0; c < 8; c += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(colt + 8 * h + c);
+            tk[c] = v.x; tk[c + 1] = v.y;
         }
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int k = 8 * h + c;
+            if (k > j && i >= k) a[c] = fma(-u, tk[c], a[c]);
+        }
+        if (jj == 7 && j + 1 < kNB) d = __shfl_sync(0xffffffffu, a[0], j + 1 + 16);
     }
+    // L = u diag(1 / sqrt(d)),  L[i][i] = sqrt(d[i]) (= d / sqrt(d), one Newton correction)
+    const double isd = rsqrt(mydiag);
+    double sd = mydiag * isd;
+    sd = fma(fma(-sd, sd, mydiag), 0.5 * isd, sd);
+    double * cis = scr + 64;
+    if (h == 0) cis[i] = isd;
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < kNB; k++)
-        if (live && k <= lane) D[lane * ld + k] = a[k];
+    for (int c = 0; c < 8; c++) {
+        const int k = 8 * h + c;
+        if (live && k <= i) D[i * ld + k] = k == i ? sd : a[c] * cis[k];
+    }
+    if (live && h == 0) dinv[i] = isd;
+    __syncwarp();
     return ok;
 }
 
 // lanes 0..15 = columns of the inverse of the lower-triangular diagonal block D (bs rows), written
 // to X (same shape, zeros above the diagonal); dinv = reciprocals of D's diagonal
 __device__ __forceinline__ void warp_trtri16(const double * D, int ld, int bs, const double * dinv, double * X, int ldx, int lane) {
-    double x[kNB];
+    // column c of the inverse by forward substitution, written right-looking: as soon as x[k] is known it
+    // is added into the sums of all later rows, so the dependent chain is two operations per row instead
+    // of one per term (every sum still receives its terms in the order k = 0, 1, ...)
+    double x[kNB], sum[kNB];
     const int c = lane;
 #pragma unroll
-    for (int i = 0; i < kNB; i++) {
-        double s = 0.0;
+    for (int i = 0; i < kNB; i++) sum[i] = 0.0;
 #pragma unroll
-        for (int k = 0; k < kNB; k++)
-            if (k < i) s = fma(i < bs ? D[i * ld + k] : 0.0, x[k], s);                  // x[k] = 0 for k < c
-        x[i] = i == c ? (i < bs ? dinv[i] : 0.0) : (i > c && i < bs ? -s * dinv[i] : 0.0);
+    for (int k = 0; k < kNB; k++) {
+        x[k] = k == c ? (k < bs ? dinv[k] : 0.0) : (k > c && k < bs ? -sum[k] * dinv[k] : 0.0);
+#pragma unroll
+        for (int i = 0; i < kNB; i++)
+            if (i > k) sum[i] = fma(i < bs ? D[i * ld + k] : 0.0, x[k], sum[i]);
     }
     if (c < bs) {
 #pragma unroll
@@ -331,18 +415,21 @@ __device__ __forceinline__ void warp_trtri16(const double * D, int ld, int bs, c
 
 __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ldw, double * dinv /* n doubles */) {
     __shared__ int bad;
+    __shared__ __align__(16) double potrf_scr[80];   // always shared memory, also in the global-workspace mode
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
+    PHASE_BEGIN();
     // ---- potrf, right-looking over 16-column panels
     for (int jb = 0; jb < n; jb += kNB) {
         const int bs = min(kNB, n - jb), below = n - jb - bs;
         double * D = A + jb * lda + jb;
         if (warp == 0) {
-            const bool ok = warp_potrf16(D, lda, bs, dinv + jb, lane);
+            const bool ok = warp_potrf16(D, lda, bs, dinv + jb, potrf_scr, lane);
             if (!ok && lane == 0) bad = 1;
         }
         __syncthreads();
+        PHASE(16);
         if (bad) break;
         if (below > 0) {
             // panel rows: x L11^T = a, one thread per row (L11 reads are broadcasts)
@@ -350,21 +437,24 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
                 double * row = A + (jb + bs + i) * lda + jb;
                 double x[kNB];
 #pragma unroll
-                for (int j = 0; j < kNB; j++) {
-                    double sacc = row[j];
+                for (int j = 0; j < kNB; j++) x[j] = row[j];
 #pragma unroll
-                    for (int k = 0; k < kNB; k++)
-                        if (k < j) sacc = fma(-x[k], D[j * lda + k], sacc);
-                    x[j] = sacc * dinv[jb + j];
+                for (int k = 0; k < kNB; k++) {          // right-looking: two dependent operations per column
+                    x[k] *= dinv[jb + k];
+#pragma unroll
+                    for (int j = 0; j < kNB; j++)
+                        if (j > k) x[j] = fma(-x[k], D[j * lda + k], x[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < kNB; j++) row[j] = x[j];
             }
             __syncthreads();
+            PHASE(17);
             // trailing block: A22 -= P P^T (lower tiles)
             const double * P = A + (jb + bs) * lda + jb;
             block_dgemm<false, true, true, 1>(below, below, kNB, P, lda, P, lda, A + (jb + bs) * lda + jb + bs, lda, -1.0);
             __syncthreads();
+            PHASE(18);
         }
     }
     __syncthreads();
@@ -378,18 +468,22 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
         if (lane < kNB) warp_trtri16(A + jb * lda + jb, lda, min(kNB, n - jb), dinv + jb, W + jb * ldw + jb, ldw, lane);
     }
     __syncthreads();
+    PHASE(19);
     // block row I: W[I][0:I] = -W[I][I] * (L[I][0:I] * W[0:I][0:I])
     for (int ib = kNB; ib < n; ib += kNB) {
         const int bs = min(kNB, n - ib);
         block_dgemm<false, false, false, 0, 2>(bs, ib, ib, A + ib * lda, lda, W, ldw, W + ib * ldw, ldw);
         __syncthreads();
+        PHASE(20);
         // in place: every warp reads the columns of its own tile completely before it stores them
         block_dgemm<false, false, false>(bs, ib, bs, W + ib * ldw + ib, ldw, W + ib * ldw, ldw, W + ib * ldw, ldw, -1.0);
         __syncthreads();
+        PHASE(21);
     }
     // ---- lauum: A <- W^T W
     block_dgemm<true, false, false, 2, 1>(n, n, n, W, ldw, W, ldw, A, lda);
     __syncthreads();
+    PHASE(22);
     return true;
 }
 
@@ -444,29 +538,41 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
 
         if (OP == 2) {
             double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
+            PHASE_BEGIN();
             for (int i = threadIdx.x; i < n; i += blockDim.x) v1[i] = in1[b * n + i];
             block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh, in_smem);    // in flight while J is formed
             block_compute_J<HAS5>(dp, rg, J);                             // syncs
+            PHASE(0);
             block_load_wait();
             __syncthreads();
+            PHASE(1);
             block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj);      // T = H_q J
             __syncthreads();
+            PHASE(2);
             for (int i = threadIdx.x; i < cd * ldj; i += blockDim.x) X[i] = 0.0;
             __syncthreads();
+            PHASE(3);
             block_add_gK<HAS5>(dp, rg, v1, 1.0, X, ldj);                  // X = sum_k g_q[k] K[k]
+            PHASE(4);
             block_dgemm<true, false, true>(cd, cd, n, J, ldj, T, ldj, X, ldj);       // X += J^T T
             __syncthreads();
+            PHASE(5);
             block_store(X, out + b * (int64_t)cd * cd, cd, cd, ldj);
             __syncthreads();
+            PHASE(6);
             continue;
         }
 
         // OP 0, 1, 3 start with M = (J J^T)^-1 J
         double * J = arena, * A = arena + n * ldj, * W = Mreg;           // W (n x n, ldh) borrows the M region
+        PHASE_BEGIN();
         block_compute_J<HAS5>(dp, rg, J);
+        PHASE(8);
         block_dgemm<false, true, false, 1>(n, n, cd, J, ldj, J, ldj, A, ldh);        // A = J J^T (lower)
         __syncthreads();
+        PHASE(9);
         const bool ok = block_spd_inverse(n, A, ldh, W, ldh, sm + pl.dinv);                        // A = (J J^T)^-1
+        PHASE(10);
         if (!ok && threadIdx.x == 0) atomicExch(status, 1);
         if (OP == 1) {
             // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203, without forming inv J)
@@ -488,6 +594,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         }
         block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj);       // M = inv J
         __syncthreads();
+        PHASE(11);
         if (OP == 0) {
             block_store(Mreg, out + b * (int64_t)n * cd, n, cd, ldj);
             __syncthreads();
@@ -495,6 +602,7 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         }
         // OP 3: H_q = M (H_r - sum_k g_q[k] K[k]) M^T,  g_q = M g_r
         double * Hc = arena, * T2 = arena + cd * ldj;                    // J and A are dead now
+        block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj, in_smem);       // in flight while g_q = M g_r is formed
         for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -502,16 +610,19 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
             for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
             v2[i] = s;
         }
-        block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj, in_smem);
         block_load_wait();
         __syncthreads();
+        PHASE(12);
         block_add_gK<HAS5>(dp, rg, v2, -1.0, Hc, ldj);                   // Hc = H_r - sum g_q K
+        PHASE(13);
         block_dgemm<false, true, false>(cd, n, cd, Hc, ldj, Mreg, ldj, T2, ldh);     // T2 = Hc M^T
         __syncthreads();
         block_dgemm<false, false, false>(n, n, cd, Mreg, ldj, T2, ldh, Hc, ldh);     // H_q = M T2 (into Hc, ld = ldh)
         __syncthreads();
+        PHASE(14);
         block_store(Hc, out + b * (int64_t)n * n, n, n, ldh);
         __syncthreads();
+        PHASE(15);
     }
 }
 
@@ -684,6 +795,14 @@ int tchem_ic_hess_cart2int(const tchem_ic_table * t, const double * r, const dou
                            int64_t B, double * intHess, tchem_stream_t stream) {
     return launch_dense(3, "Hessian_cart2int", t, r, cartgrad, cartHess, B, intHess, static_cast<cudaStream_t>(stream));
 }
+#ifdef TCHEM_DENSE_PHASES
+__attribute__((visibility("default"))) int tchem_debug_dense_phases(unsigned long long * out32, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out32, g_dense_phase, sizeof(g_dense_phase)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_dense_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
 // 0 = every Cholesky factorisation since the last call succeeded
 int tchem_ic_factor_status(const tchem_ic_table * t) { return t ? dense_status(t) : 0; }
 
