@@ -21,7 +21,7 @@ gq = torch.randn(B, n, dtype=torch.float64, device="cuda", generator=g)
 gr = torch.randn(B, cd, dtype=torch.float64, device="cuda", generator=g)
 Hq = torch.randn(B, n, n, dtype=torch.float64, device="cuda", generator=g); Hq = Hq + Hq.transpose(1, 2)
 Hr = torch.randn(B, cd, cd, dtype=torch.float64, device="cuda", generator=g); Hr = Hr + Hr.transpose(1, 2)
-names = {0: "v1 + J (Hq load in flight)", 1: "wait Hq", 2: "T = Hq J", 3: "zero X", 4: "X += g.K", 5: "X += J^T T", 6: "store",
+names = {0: "J (Hq load in flight)", 1: "wait Hq", 2: "T = Hq J", 3: "X = J^T T", 4: "X += g.K", 6: "store",
          8: "J", 9: "J J^T", 10: "spd inverse", 11: "M = inv J", 12: "g_q, load H_r", 13: "Hc -= g.K", 14: "two GEMMs", 15: "store",
          16: "  potrf: diagonal blocks (1 warp)", 17: "  potrf: panel rows", 18: "  potrf: trailing update", 19: "  trtri: zero W + diagonal blocks",
          20: "  trtri: L W", 21: "  trtri: -Wd (.)", 22: "  lauum: W^T W"}

@@ -299,13 +299,33 @@ __device__ __forceinline__ void block_load_wait() { asm volatile("cp.async.wait_
 __device__ __forceinline__ void block_store(const double * s, double * __restrict__ g, int rows, int cols, int ld) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
-    for (int r = warp; r < rows; r += nwarps) {
-        const double * src = s + r * ld;
-        double * dst = g + (int64_t)r * cols;
-        if (vec) {
-            for (int c = 2 * lane; c < cols; c += 2 * kLanes)
-                __stcs(reinterpret_cast<double2 *>(dst + c), *reinterpret_cast<const double2 *>(src + c));
-        } else {
+    if (vec) {
+        // two rows per pass: four independent 16-byte loads before the first store
+        for (int r = warp; r < rows; r += 2 * nwarps) {
+            const int r2 = r + nwarps;
+            const double * src = s + r * ld, * src2 = s + r2 * ld;
+            double * dst = g + (int64_t)r * cols, * dst2 = g + (int64_t)r2 * cols;
+            for (int c = 2 * lane; c < cols; c += 4 * kLanes) {
+                const int c2 = c + 2 * kLanes;
+                const double2 a = *reinterpret_cast<const double2 *>(src + c);
+                double2 b2 = a, a2 = a, b3 = a;
+                if (c2 < cols) b2 = *reinterpret_cast<const double2 *>(src + c2);
+                if (r2 < rows) {
+                    a2 = *reinterpret_cast<const double2 *>(src2 + c);
+                    if (c2 < cols) b3 = *reinterpret_cast<const double2 *>(src2 + c2);
+                }
+                __stcs(reinterpret_cast<double2 *>(dst + c), a);
+                if (c2 < cols) __stcs(reinterpret_cast<double2 *>(dst + c2), b2);
+                if (r2 < rows) {
+                    __stcs(reinterpret_cast<double2 *>(dst2 + c), a2);
+                    if (c2 < cols) __stcs(reinterpret_cast<double2 *>(dst2 + c2), b3);
+                }
+            }
+        }
+    } else {
+        for (int r = warp; r < rows; r += nwarps) {
+            const double * src = s + r * ld;
+            double * dst = g + (int64_t)r * cols;
             for (int c = lane; c < cols; c += kLanes) __stcs(dst + c, src[c]);
         }
     }
@@ -488,7 +508,7 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
 }
 
 // ---------------------------------------------------------------------------------------
-// shared-memory plan (in doubles). Regions:  rg | v1 | v2 | M | ARENA
+// shared-memory plan (in doubles). Regions:  rg[2] | v1[2] | v2 | dinv | M | ARENA
 // ---------------------------------------------------------------------------------------
 struct DensePlan {
     int rg, v1, v2, dinv, M, arena, total;
@@ -496,9 +516,9 @@ struct DensePlan {
 __host__ __device__ inline int even(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, int ldh) {
     DensePlan p;
-    p.rg = 0;
-    p.v1 = p.rg + even(cd);
-    p.v2 = p.v1 + even(cd > n ? cd : n);
+    p.rg = 0;                                     // rg and v1: two buffers each (next geometry prefetched)
+    p.v1 = p.rg + 2 * even(cd);
+    p.v2 = p.v1 + 2 * even(cd > n ? cd : n);
     p.dinv = p.v2 + even(cd > n ? cd : n);
     p.M = p.dinv + even(n);
     const int szJ = n * ldj, szA = n * ldh, szH = cd * ldj, szT2 = cd * ldh;
@@ -530,16 +550,42 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
     const DensePlan pl = dense_plan(OP, n, cd, ldj, ldh);
     double * sm = sm_dyn;
     if (WS) sm = workspace + (size_t)blockIdx.x * pl.total;
-    double * rg = sm + pl.rg, * v1 = sm + pl.v1, * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
+    double * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
+    // the small per-geometry inputs (coordinates; the gradient in1) are double buffered: the next
+    // geometry's copies are issued (cp.async) as soon as this one's have been picked up, so their HBM
+    // latency never shows. The global-workspace mode loads them synchronously into one buffer.
+    const int rg_len = cd, v1_len = OP == 0 ? 0 : OP == 2 ? n : cd;
+    const int rg_buf = even(cd), v1_buf = even(cd > n ? cd : n);
+    auto fetch_small = [&](int64_t bb, int buf) {
+        double * rgd = sm + pl.rg + buf * rg_buf, * v1d = sm + pl.v1 + buf * v1_buf;
+        const double * rs = r + bb * rg_len, * vs = in1 + bb * v1_len;
+        if (in_smem) {
+            for (int i = threadIdx.x; i < rg_len; i += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(rgd + i)), "l"(rs + i) : "memory");
+            for (int i = threadIdx.x; i < v1_len; i += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(v1d + i)), "l"(vs + i) : "memory");
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        } else {
+            for (int i = threadIdx.x; i < rg_len; i += blockDim.x) rgd[i] = rs[i];
+            for (int i = threadIdx.x; i < v1_len; i += blockDim.x) v1d[i] = vs[i];
+        }
+    };
+    int cur = 0;
+    if (in_smem && (int64_t)blockIdx.x < B) fetch_small(blockIdx.x, 0);
 
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        for (int i = threadIdx.x; i < cd; i += blockDim.x) rg[i] = r[b * cd + i];
+        if (!in_smem) fetch_small(b, 0);             // (every iteration ends with a barrier)
+        double * rg = sm + pl.rg + cur * rg_buf, * v1 = sm + pl.v1 + cur * v1_buf;
+        block_load_wait();
         __syncthreads();
+        if (in_smem) {                               // the other buffers were last read before this barrier
+            if (b + gridDim.x < B) fetch_small(b + gridDim.x, cur ^ 1);
+            cur ^= 1;
+        }
 
         if (OP == 2) {
             double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
             PHASE_BEGIN();
-            for (int i = threadIdx.x; i < n; i += blockDim.x) v1[i] = in1[b * n + i];
             block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh, in_smem);    // in flight while J is formed
             block_compute_J<HAS5>(dp, rg, J);                             // syncs
             PHASE(0);
@@ -549,14 +595,11 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
             block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj);      // T = H_q J
             __syncthreads();
             PHASE(2);
-            for (int i = threadIdx.x; i < cd * ldj; i += blockDim.x) X[i] = 0.0;
+            block_dgemm<true, false, false>(cd, cd, n, J, ldj, T, ldj, X, ldj);      // X = J^T T (H_q is dead)
             __syncthreads();
             PHASE(3);
-            block_add_gK<HAS5>(dp, rg, v1, 1.0, X, ldj);                  // X = sum_k g_q[k] K[k]
+            block_add_gK<HAS5>(dp, rg, v1, 1.0, X, ldj);                  // X += sum_k g_q[k] K[k]
             PHASE(4);
-            block_dgemm<true, false, true>(cd, cd, n, J, ldj, T, ldj, X, ldj);       // X += J^T T
-            __syncthreads();
-            PHASE(5);
             block_store(X, out + b * (int64_t)cd * cd, cd, cd, ldj);
             __syncthreads();
             PHASE(6);
@@ -576,8 +619,6 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         if (!ok && threadIdx.x == 0) atomicExch(status, 1);
         if (OP == 1) {
             // g_q = inv (J g_r)   (= (inv J) g_r, source/IC/IntCoordSet.cpp:202-203, without forming inv J)
-            for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
-            __syncthreads();
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 double s = 0.0;
                 for (int k = 0; k < cd; k++) s = fma(J[i * ldj + k], v1[k], s);
@@ -603,8 +644,6 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         // OP 3: H_q = M (H_r - sum_k g_q[k] K[k]) M^T,  g_q = M g_r
         double * Hc = arena, * T2 = arena + cd * ldj;                    // J and A are dead now
         block_load_async(in2 + b * (int64_t)cd * cd, Hc, cd, cd, ldj, in_smem);       // in flight while g_q = M g_r is formed
-        for (int i = threadIdx.x; i < cd; i += blockDim.x) v1[i] = in1[b * cd + i];
-        __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             double s = 0.0;
             for (int k = 0; k < cd; k++) s = fma(Mreg[i * ldj + k], v1[k], s);
