@@ -39,6 +39,8 @@ struct DenseProgram {                 // device pointers
     const DenseTask * tasks;          // (term, Cartesian direction) pairs for the K passes
     int32_t nterms, ntasks, intdim, cartdim;
     int32_t ldj, ldh;                 // leading dimensions: width >= cartdim / intdim, = 4 or 12 mod 16
+    int32_t blob_doubles;             // size of the table blob (terms | row_ptr | tasks, starts at `terms`)
+    int32_t tab_doubles;              // per launch: blob_doubles when the kernel keeps a copy in shared memory, else 0
 };
 
 namespace {
@@ -233,10 +235,14 @@ struct HessSink {                      // H[.][.] += w * K_term   (shared accumu
 
 // J[intdim][ldj] of the block's geometry: zero, then one thread per internal coordinate adds its
 // terms (source/IC/IntCoord.cpp:62-76)
-template <bool HAS5>
-__device__ void block_compute_J(const DenseProgram & dp, const double * rg, double * J) {
+template <bool HAS5, class Idle>
+__device__ void block_compute_J(const DenseProgram & dp, const double * rg, double * J, Idle idle_warps) {
     for (int i = threadIdx.x; i < dp.intdim * dp.ldj; i += blockDim.x) J[i] = 0.0;
     __syncthreads();
+    // rows occupy the first ceil(intdim / 32) warps; the others run idle_warps(first idle warp) meanwhile
+    // (the H_q copy: issued from here it does not queue ahead of the row threads' table reads)
+    const int row_warps = (dp.intdim + kLanes - 1) / kLanes;
+    if ((int)(threadIdx.x >> 5) >= row_warps) idle_warps(row_warps);
     for (int row = threadIdx.x; row < dp.intdim; row += blockDim.x) {
         RowSink sink;
         sink.row = J + row * dp.ldj;
@@ -246,6 +252,10 @@ __device__ void block_compute_J(const DenseProgram & dp, const double * rg, doub
         }
     }
     __syncthreads();
+}
+template <bool HAS5>
+__device__ void block_compute_J(const DenseProgram & dp, const double * rg, double * J) {
+    block_compute_J<HAS5>(dp, rg, J, [](int) {});
 }
 
 // H[cartdim][ld] += sum over terms of weight[row] * coef * K_term, one (term, direction) per thread
@@ -268,8 +278,11 @@ __device__ void block_add_gK(const DenseProgram & dp, const double * rg, const d
 // block_load_wait() + __syncthreads() before touching the tile. One warp per row at a time.
 // (workspace mode - operands in global memory because the molecule is too large for shared memory -
 // copies synchronously: cp.async only writes shared memory)
-__device__ __forceinline__ void block_load_async(const double * __restrict__ g, double * s, int rows, int cols, int ld, bool in_smem = true) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+// Warps [warp0, nwarps_total) take part (default: all of them).
+__device__ __forceinline__ void block_load_async(const double * __restrict__ g, double * s, int rows, int cols, int ld, bool in_smem = true,
+                                                 int warp0 = 0) {
+    const int warp = (threadIdx.x >> 5) - warp0, nwarps = (blockDim.x >> 5) - warp0, lane = threadIdx.x & 31;
+    if (warp < 0) return;
     if (!in_smem) {
         for (int r = warp; r < rows; r += nwarps)
             for (int c = lane; c < cols; c += kLanes) s[r * ld + c] = g[(int64_t)r * cols + c];
@@ -511,10 +524,10 @@ __device__ bool block_spd_inverse(int n, double * A, int lda, double * W, int ld
 // shared-memory plan (in doubles). Regions:  rg[2] | v1[2] | v2 | dinv | M | ARENA
 // ---------------------------------------------------------------------------------------
 struct DensePlan {
-    int rg, v1, v2, dinv, M, arena, total;
+    int rg, v1, v2, dinv, M, arena, tab, total;
 };
 __host__ __device__ inline int even(int x) { return (x + 1) & ~1; }
-__host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, int ldh) {
+__host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, int ldh, int tab_doubles) {
     DensePlan p;
     p.rg = 0;                                     // rg and v1: two buffers each (next geometry prefetched)
     p.v1 = p.rg + 2 * even(cd);
@@ -528,7 +541,8 @@ __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, 
     case 2: p.arena = p.M + szJ; arena = szJ + (szA > szH ? szA : szH); break;            // J | T, Hq/Hacc
     default: p.arena = p.M + szJ; arena = (szJ + szA > szH + szT2) ? szJ + szA : szH + szT2; break;
     }
-    p.total = p.arena + arena;
+    p.tab = p.arena + arena;                      // copy of the definition tables (when it fits)
+    p.total = p.tab + even(tab_doubles);
     return p;
 }
 
@@ -538,7 +552,7 @@ __host__ __device__ inline DensePlan dense_plan(int op, int n, int cd, int ldj, 
 // OP 3: Hessian_cart2int           in1 = g_r[cd], in2 = H_r[cd][cd]    out = H_q[n][n]
 template <int OP, bool HAS5, bool WS>
 __global__ void __launch_bounds__(kDenseThreads, 1)
-dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double * __restrict__ in1,
+dense_kernel(const DenseProgram dp_global, const double * __restrict__ r, const double * __restrict__ in1,
              const double * __restrict__ in2, const int64_t B, double * __restrict__ out, int * __restrict__ status,
              double * __restrict__ workspace) {
     // operands in shared memory, or - molecules beyond the shared-memory plan - in a per-block slice of
@@ -546,10 +560,22 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
     // (WS is a template parameter so that the shared-memory flavour keeps shared-state-space loads)
     extern __shared__ __align__(16) double sm_dyn[];
     constexpr bool in_smem = !WS;
-    const int n = dp.intdim, cd = dp.cartdim, ldj = dp.ldj, ldh = dp.ldh;
-    const DensePlan pl = dense_plan(OP, n, cd, ldj, ldh);
+    const int n = dp_global.intdim, cd = dp_global.cartdim, ldj = dp_global.ldj, ldh = dp_global.ldh;
+    const DensePlan pl = dense_plan(OP, n, cd, ldj, ldh, dp_global.tab_doubles);
     double * sm = sm_dyn;
     if (WS) sm = workspace + (size_t)blockIdx.x * pl.total;
+    // the definition tables (terms, row pointers, K tasks; a few KB) are read by every geometry: kept in
+    // shared memory when they fit, so those reads never queue behind the operand copies in the L1 pipeline
+    DenseProgram dp = dp_global;
+    if (in_smem && dp_global.tab_doubles > 0) {
+        double * tab = sm + pl.tab;
+        const double * src = reinterpret_cast<const double *>(dp_global.terms);
+        for (int i = threadIdx.x; i < dp_global.tab_doubles; i += blockDim.x) tab[i] = src[i];
+        const char * base = reinterpret_cast<const char *>(dp_global.terms), * tb = reinterpret_cast<const char *>(tab);
+        dp.terms = reinterpret_cast<const DenseTerm *>(tb);
+        dp.row_ptr = reinterpret_cast<const int32_t *>(tb + (reinterpret_cast<const char *>(dp_global.row_ptr) - base));
+        dp.tasks = reinterpret_cast<const DenseTask *>(tb + (reinterpret_cast<const char *>(dp_global.tasks) - base));
+    }                                                // (visible after the first barrier of the loop)
     double * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
     // the small per-geometry inputs (coordinates; the gradient in1) are double buffered: the next
     // geometry's copies are issued (cp.async) as soon as this one's have been picked up, so their HBM
@@ -586,8 +612,12 @@ dense_kernel(const DenseProgram dp, const double * __restrict__ r, const double 
         if (OP == 2) {
             double * J = Mreg, * T = arena, * X = arena + n * ldj;       // X: H_q, later the H_r accumulator
             PHASE_BEGIN();
-            block_load_async(in2 + b * (int64_t)n * n, X, n, n, ldh, in_smem);    // in flight while J is formed
-            block_compute_J<HAS5>(dp, rg, J);                             // syncs
+            // H_q travels while J is formed, issued by the warps that own no row of J (all warps, up front,
+            // when every warp owns rows)
+            const double * Hq_g = in2 + b * (int64_t)n * n;
+            const bool idle_issue = (n + kLanes - 1) / kLanes < (int)(blockDim.x >> 5);
+            if (!idle_issue) block_load_async(Hq_g, X, n, n, ldh, in_smem);
+            block_compute_J<HAS5>(dp, rg, J, [&](int warp0) { if (idle_issue) block_load_async(Hq_g, X, n, n, ldh, in_smem, warp0); });   // syncs
             PHASE(0);
             block_load_wait();
             __syncthreads();
@@ -706,9 +736,16 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
         }
         row_ptr.push_back((int32_t)terms.size());
     }
-    // heavier tasks first (torsions before bends before stretches) so the tail of the task loop is short
+    // heavier tasks first (torsions before bends before stretches) so the tail of the task loop is short;
+    // within one type direction-major: the 32 lanes of a warp then hold the SAME direction of 32 different
+    // terms - uniform control flow in the scatter (which blocks a direction touches depends on it), and
+    // lanes that add into the shared accumulator in the same instruction hit different elements (same
+    // local block of different terms), so the CAS loops of the double-precision adds rarely retry
     std::stable_sort(tasks.begin(), tasks.end(), [&](const DenseTask & a, const DenseTask & b) {
-        return terms[a.term].pd.natoms > terms[b.term].pd.natoms;
+        const auto & ta = terms[a.term].pd; const auto & tb = terms[b.term].pd;
+        if (ta.natoms != tb.natoms) return ta.natoms > tb.natoms;
+        if (ta.type != tb.type) return ta.type < tb.type;
+        return a.dir < b.dir;
     });
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     const size_t o_t = 0, o_r = a16(terms.size() * sizeof(DenseTerm)), o_k = o_r + a16(row_ptr.size() * 4);
@@ -735,6 +772,8 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
     dt.prog.cartdim = t->cartdim;
     dt.prog.ldj = pick_ld(t->cartdim);
     dt.prog.ldh = pick_ld(t->intdim);
+    dt.prog.blob_doubles = (int32_t)(total / 8);
+    dt.prog.tab_doubles = 0;
     dense_tables()[t] = dt;
     out = dt;
     return TCHEM_OK;
@@ -759,7 +798,13 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     DenseTable dt;
     int rc = get_dense(t, dt);
     if (rc != TCHEM_OK) return rc;
-    const DensePlan pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh);
+    // with a shared-memory copy of the definition tables when that still fits, without it otherwise
+    DensePlan pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh, dt.prog.blob_doubles);
+    dt.prog.tab_doubles = dt.prog.blob_doubles;
+    if ((size_t)pl.total * sizeof(double) + 4096 > (size_t)t->max_smem_optin) {
+        pl = dense_plan(op, t->intdim, t->cartdim, dt.prog.ldj, dt.prog.ldh, 0);
+        dt.prog.tab_doubles = 0;
+    }
     size_t smem = (size_t)pl.total * sizeof(double);
     // Molecules whose operands do not fit the shared memory of one SM (more than ~32 atoms for a full
     // 3N-6 set) run the same kernel on a per-block slice of a stream-ordered global workspace: correct
