@@ -39,7 +39,12 @@ struct DenseProgram {                 // device pointers
     const DenseTask * tasks;          // (term, Cartesian direction) pairs for the K passes
     int32_t nterms, ntasks, intdim, cartdim;
     int32_t ldj, ldh;                 // leading dimensions: width >= cartdim / intdim, = 4 or 12 mod 16
-    int32_t blob_doubles;             // size of the table blob (terms | row_ptr | tasks, starts at `terms`)
+    // structural sparsity of J at DMMA k-step granularity (null when intdim or cartdim > 128):
+    //   colmask[cb], cb = 8-column block of J: bit s set when rows 4s..4s+3 of J have a structural nonzero there
+    //   rowmask[rb], rb = 8-row block of J:    bit s set when columns 4s..4s+3 have one
+    const uint32_t *  colmask;
+    const uint32_t *  rowmask;
+    int32_t blob_doubles;             // size of the table blob (terms | row_ptr | tasks | masks, starts at `terms`)
     int32_t tab_doubles;              // per launch: blob_doubles when the kernel keeps a copy in shared memory, else 0
 };
 
@@ -87,9 +92,15 @@ __device__ __forceinline__ void dmma(double & d0, double & d1, double a, double 
 // row / column instead of predicating every load: D[m][n] only depends on row m of A and column n
 // of B, and the duplicated rows are simply not stored. K is walked in unpredicated steps of 4 with
 // one masked tail step.
+// kmask (optional): J's structural zeros skip whole k-steps. side 1: masks[] indexed by the 8-column block of
+// C's columns (B = J, k runs over J's rows); side 2: by the 8-row block of C's rows (A = J^T); side 3: masks[]
+// indexed by 8-row blocks of J for both C's rows and columns, intersected (J J^T, k runs over J's columns).
+// Products with structural zeros are exact zeros, so the result is the same sum.
+struct KMask { const uint32_t * masks; int side; };
+
 template <bool TA, bool TB, bool ACC, int TRI, int KS, int WN>
 __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
-                                                  double * C, int ldc, double s) {
+                                                  double * C, int ldc, double s, KMask km) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
     constexpr int TW = 8 * WN;                                // tile width (columns of C)
@@ -118,19 +129,52 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
                 const int n = min(n0 + 8 * j + gid, N - 1);
                 pb[j] = B + (TB ? n * ldb : n) + tig * sb;
             }
-#pragma unroll 2
-            for (int k0 = kbeg; k0 < K4; k0 += 4) {
-                double a[2], b[WN];
+            uint32_t live = 0xffffffffu;                     // k-steps that can contribute to this tile
+            if (km.masks) {
+                uint32_t mrow = km.side == 1 ? 0xffffffffu : 0u, mcol = km.side == 2 ? 0xffffffffu : 0u;
+                if (km.side != 1) {
 #pragma unroll
-                for (int i = 0; i < 2; i++) a[i] = pa[i][k0 * sa];
+                    for (int i = 0; i < 2; i++)
+                        if (m0 + 8 * i < M) mrow |= km.masks[(m0 >> 3) + i];
+                }
+                if (km.side != 2) {
 #pragma unroll
-                for (int j = 0; j < WN; j++) b[j] = pb[j][k0 * sb];
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < WN; j++)
+                        if (n0 + 8 * j < N) mcol |= km.masks[(n0 >> 3) + j];
+                }
+                live = mrow & mcol;
             }
-            if (K4 < K) {
+            if (km.masks) {
+                uint32_t steps = live & (uint32_t)((1ull << (K4 >> 2)) - 1ull);
+                if (KS != 0) steps &= ~(uint32_t)((1ull << (kbeg >> 2)) - 1ull);
+                while (steps) {
+                    const int k0 = 4 * (__ffs(steps) - 1);
+                    steps &= steps - 1;
+                    double a[2], b[WN];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) a[i] = pa[i][k0 * sa];
+#pragma unroll
+                    for (int j = 0; j < WN; j++) b[j] = pb[j][k0 * sb];
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            } else {
+#pragma unroll 2
+                for (int k0 = kbeg; k0 < K4; k0 += 4) {
+                    double a[2], b[WN];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) a[i] = pa[i][k0 * sa];
+#pragma unroll
+                    for (int j = 0; j < WN; j++) b[j] = pb[j][k0 * sb];
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            }
+            if (K4 < K && ((live >> (K4 >> 2)) & 1u)) {
                 const bool in = K4 + tig < K;
                 const int k0 = in ? K4 : K - 1 - tig;        // clamped address, value masked
                 double a[2], b[WN];
@@ -169,14 +213,14 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
 // on the critical path and 5 instead of 6 fragment loads per 6 DMMAs).
 template <bool TA, bool TB, bool ACC, int TRI = 0, int KS = 0>
 __device__ __forceinline__ void block_dgemm(int M, int N, int K, const double * A, int lda, const double * B, int ldb,
-                                            double * C, int ldc, double s = 1.0) {
+                                            double * C, int ldc, double s = 1.0, KMask km = KMask{nullptr, 0}) {
     if (TRI == 0 && KS == 0) {
         const int nwarps = blockDim.x >> 5, tm = (M + 15) >> 4;
         const int steps2 = 2 * ((tm * ((N + 15) / 16) + nwarps - 1) / nwarps);
         const int steps3 = 3 * ((tm * ((N + 23) / 24) + nwarps - 1) / nwarps);
-        if (steps3 < steps2) { block_dgemm_tiles<TA, TB, ACC, 0, 0, 3>(M, N, K, A, lda, B, ldb, C, ldc, s); return; }
+        if (steps3 < steps2) { block_dgemm_tiles<TA, TB, ACC, 0, 0, 3>(M, N, K, A, lda, B, ldb, C, ldc, s, km); return; }
     }
-    block_dgemm_tiles<TA, TB, ACC, TRI, KS, 2>(M, N, K, A, lda, B, ldb, C, ldc, s);
+    block_dgemm_tiles<TA, TB, ACC, TRI, KS, 2>(M, N, K, A, lda, B, ldb, C, ldc, s, km);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -575,6 +619,10 @@ dense_kernel(const DenseProgram dp_global, const double * __restrict__ r, const 
         dp.terms = reinterpret_cast<const DenseTerm *>(tb);
         dp.row_ptr = reinterpret_cast<const int32_t *>(tb + (reinterpret_cast<const char *>(dp_global.row_ptr) - base));
         dp.tasks = reinterpret_cast<const DenseTask *>(tb + (reinterpret_cast<const char *>(dp_global.tasks) - base));
+        if (dp_global.colmask) {
+            dp.colmask = reinterpret_cast<const uint32_t *>(tb + (reinterpret_cast<const char *>(dp_global.colmask) - base));
+            dp.rowmask = reinterpret_cast<const uint32_t *>(tb + (reinterpret_cast<const char *>(dp_global.rowmask) - base));
+        }
     }                                                // (visible after the first barrier of the loop)
     double * v2 = sm + pl.v2, * Mreg = sm + pl.M, * arena = sm + pl.arena;
     // the small per-geometry inputs (coordinates; the gradient in1) are double buffered: the next
@@ -622,10 +670,10 @@ dense_kernel(const DenseProgram dp_global, const double * __restrict__ r, const 
             block_load_wait();
             __syncthreads();
             PHASE(1);
-            block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj);      // T = H_q J
+            block_dgemm<false, false, false>(n, cd, n, X, ldh, J, ldj, T, ldj, 1.0, KMask{dp.colmask, 1});      // T = H_q J
             __syncthreads();
             PHASE(2);
-            block_dgemm<true, false, false>(cd, cd, n, J, ldj, T, ldj, X, ldj);      // X = J^T T (H_q is dead)
+            block_dgemm<true, false, false>(cd, cd, n, J, ldj, T, ldj, X, ldj, 1.0, KMask{dp.colmask, 2});      // X = J^T T (H_q is dead)
             __syncthreads();
             PHASE(3);
             block_add_gK<HAS5>(dp, rg, v1, 1.0, X, ldj);                  // X += sum_k g_q[k] K[k]
@@ -641,7 +689,7 @@ dense_kernel(const DenseProgram dp_global, const double * __restrict__ r, const 
         PHASE_BEGIN();
         block_compute_J<HAS5>(dp, rg, J);
         PHASE(8);
-        block_dgemm<false, true, false, 1>(n, n, cd, J, ldj, J, ldj, A, ldh);        // A = J J^T (lower)
+        block_dgemm<false, true, false, 1>(n, n, cd, J, ldj, J, ldj, A, ldh, 1.0, KMask{dp.rowmask, 3});        // A = J J^T (lower)
         __syncthreads();
         PHASE(9);
         const bool ok = block_spd_inverse(n, A, ldh, W, ldh, sm + pl.dinv);                        // A = (J J^T)^-1
@@ -663,7 +711,7 @@ dense_kernel(const DenseProgram dp_global, const double * __restrict__ r, const 
             __syncthreads();
             continue;
         }
-        block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj);       // M = inv J
+        block_dgemm<false, false, false>(n, cd, n, A, ldh, J, ldj, Mreg, ldj, 1.0, KMask{dp.colmask, 1});       // M = inv J
         __syncthreads();
         PHASE(11);
         if (OP == 0) {
@@ -748,12 +796,25 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
         return a.dir < b.dir;
     });
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    // structural nonzeros of J at k-step granularity (see DenseProgram)
+    const bool masked = t->intdim <= 128 && t->cartdim <= 128;
+    std::vector<uint32_t> colmask((t->cartdim + 7) / 8 + 4, 0), rowmask((t->intdim + 7) / 8 + 4, 0);
+    for (const DenseTerm & dt : terms)
+        for (int a = 0; a < dt.pd.natoms; a++)
+            for (int c = 0; c < 3; c++) {
+                const int row = dt.pd.out, col = 3 * dt.pd.atoms[a] + c;
+                colmask[col / 8] |= 1u << (row / 4);
+                rowmask[row / 8] |= 1u << (col / 4);
+            }
     const size_t o_t = 0, o_r = a16(terms.size() * sizeof(DenseTerm)), o_k = o_r + a16(row_ptr.size() * 4);
-    const size_t total = o_k + a16(tasks.size() * sizeof(DenseTask)) + 16;
+    const size_t o_cm = o_k + a16(tasks.size() * sizeof(DenseTask)), o_rm = o_cm + a16(colmask.size() * 4);
+    const size_t total = o_rm + a16(rowmask.size() * 4) + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_t, terms.data(), terms.size() * sizeof(DenseTerm));
     std::memcpy(blob.data() + o_r, row_ptr.data(), row_ptr.size() * 4);
     std::memcpy(blob.data() + o_k, tasks.data(), tasks.size() * sizeof(DenseTask));
+    std::memcpy(blob.data() + o_cm, colmask.data(), colmask.size() * 4);
+    std::memcpy(blob.data() + o_rm, rowmask.data(), rowmask.size() * 4);
     void * dev = nullptr;
     TC_CUDA(cudaMalloc(&dev, total));
     cudaError_t e = cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice);
@@ -766,6 +827,8 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
     dt.prog.terms = reinterpret_cast<const DenseTerm *>(d + o_t);
     dt.prog.row_ptr = reinterpret_cast<const int32_t *>(d + o_r);
     dt.prog.tasks = reinterpret_cast<const DenseTask *>(d + o_k);
+    dt.prog.colmask = masked ? reinterpret_cast<const uint32_t *>(d + o_cm) : nullptr;
+    dt.prog.rowmask = masked ? reinterpret_cast<const uint32_t *>(d + o_rm) : nullptr;
     dt.prog.nterms = (int)terms.size();
     dt.prog.ntasks = (int)tasks.size();
     dt.prog.intdim = t->intdim;
