@@ -439,6 +439,7 @@ def main():
             roof = {"bound": "tensor", "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak, "traffic": None,
                     "peak_source": "FP64 DGEMM 4096^3 via cuBLAS (torch.matmul), measured in this run",
                     "dense_flops_per_geometry": fl, "kernel": kernel, "launch_ms": avg_launch_s * 1e3,
+                    "note": "achieved = dense-equivalent (algorithmic, SURVEY 8d) flops / time; the kernel skips DMMA k-steps in which J is structurally zero, so it issues fewer flops than that",
                     "hbm_GBps": achieved, "hbm_frac": achieved / peak}
         line = {"metric": metric, "value": value, "unit": "geometries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
