@@ -147,14 +147,32 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
             if (km.masks) {
                 uint32_t steps = live & (uint32_t)((1ull << (K4 >> 2)) - 1ull);
                 if (KS != 0) steps &= ~(uint32_t)((1ull << (kbeg >> 2)) - 1ull);
-                while (steps) {
-                    const int k0 = 4 * (__ffs(steps) - 1);
-                    steps &= steps - 1;
+                // software pipelined: the fragments of the next live k-step are loaded before this step's DMMAs
+                if (steps) {
                     double a[2], b[WN];
+                    int k0 = 4 * (__ffs(steps) - 1);
+                    steps &= steps - 1;
 #pragma unroll
                     for (int i = 0; i < 2; i++) a[i] = pa[i][k0 * sa];
 #pragma unroll
                     for (int j = 0; j < WN; j++) b[j] = pb[j][k0 * sb];
+                    while (steps) {
+                        k0 = 4 * (__ffs(steps) - 1);
+                        steps &= steps - 1;
+                        double a2[2], b2[WN];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) a2[i] = pa[i][k0 * sa];
+#pragma unroll
+                        for (int j = 0; j < WN; j++) b2[j] = pb[j][k0 * sb];
+#pragma unroll
+                        for (int i = 0; i < 2; i++)
+#pragma unroll
+                            for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#pragma unroll
+                        for (int i = 0; i < 2; i++) a[i] = a2[i];
+#pragma unroll
+                        for (int j = 0; j < WN; j++) b[j] = b2[j];
+                    }
 #pragma unroll
                     for (int i = 0; i < 2; i++)
 #pragma unroll
