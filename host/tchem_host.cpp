@@ -303,9 +303,13 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> IntCoordSet::compute_IC_J_K(const
 
 namespace {
 // shared plumbing of the four transforms: device copies of the operands, launch, result back where r lives
+// factors: the call factors J J^T per geometry - the reference's at::cholesky throws c10::Error when it is not
+// positive definite (source/IC/IntCoordSet.cpp:182), so the device flag is read back (one synchronisation) and
+// turned into the same exception type. TCHEM_ASYNC_TRANSFORMS=1 skips the check and keeps the call asynchronous;
+// the affected geometries' results are NaN either way.
 template <typename Launch>
 at::Tensor transform(Call & c, std::vector<std::pair<at::Tensor, std::vector<int64_t>>> operands,
-                     std::vector<int64_t> out_shape, Launch && launch) {
+                     std::vector<int64_t> out_shape, Launch && launch, const char * factors = nullptr) {
     const int64_t B = c.r.B;
     c10::cuda::CUDAGuard guard(c.device);
     at::Tensor r_dev = on_device(c.r.t, c.device);
@@ -319,6 +323,12 @@ at::Tensor transform(Call & c, std::vector<std::pair<at::Tensor, std::vector<int
     shape.insert(shape.end(), out_shape.begin(), out_shape.end());
     at::Tensor out = at::empty(shape, r_dev.options());
     if (B > 0) check(launch(r_dev, ops, out, c10::cuda::getCurrentCUDAStream(c.device).stream()));
+    if (B > 0 && factors) {
+        static const bool async = [] { const char * e = getenv("TCHEM_ASYNC_TRANSFORMS"); return e && atoi(e) != 0; }();
+        if (!async && tchem_ic_factor_status(c.table) != 0)
+            TORCH_CHECK(false, factors, ": cholesky: J J^T is not positive definite for at least one geometry of the batch "
+                                        "(redundant or singular internal coordinates)");
+    }
     if (c.host) out = out.cpu();
     return unbatch(out, c.r.batched);
 }
@@ -330,7 +340,7 @@ at::Tensor IntCoordSet::gradient_cart2int_matrix(const at::Tensor & r) const {
     const int64_t n = size(), cd = c.r.width;
     return transform(c, {}, {n, cd}, [&](const at::Tensor & rd, std::vector<at::Tensor> &, at::Tensor & out, cudaStream_t s) {
         return tchem_ic_grad_cart2int_matrix(c.table, (const double *)ptr(rd), c.r.B, (double *)ptr(out), s);
-    });
+    }, "tchem::IC::IntCoordSet::gradient_cart2int_matrix");
 }
 at::Tensor IntCoordSet::gradient_cart2int(const at::Tensor & r, const at::Tensor & cartgrad) const {
     const std::string who = "tchem::IC::IntCoordSet::gradient_cart2int";
@@ -340,7 +350,7 @@ at::Tensor IntCoordSet::gradient_cart2int(const at::Tensor & r, const at::Tensor
     const int64_t n = size(), cd = c.r.width;
     return transform(c, {{cartgrad, {cd}}}, {n}, [&](const at::Tensor & rd, std::vector<at::Tensor> & o, at::Tensor & out, cudaStream_t s) {
         return tchem_ic_grad_cart2int(c.table, (const double *)ptr(rd), (const double *)ptr(o[0]), c.r.B, (double *)ptr(out), s);
-    });
+    }, "tchem::IC::IntCoordSet::gradient_cart2int");
 }
 at::Tensor IntCoordSet::gradient_int2cart(const at::Tensor & r, const at::Tensor & intgrad) const {
     const std::string who = "tchem::IC::IntCoordSet::gradient_int2cart";
@@ -365,7 +375,7 @@ at::Tensor IntCoordSet::Hessian_cart2int(const at::Tensor & r, const at::Tensor 
                      [&](const at::Tensor & rd, std::vector<at::Tensor> & o, at::Tensor & out, cudaStream_t s) {
         return tchem_ic_hess_cart2int(c.table, (const double *)ptr(rd), (const double *)ptr(o[0]), (const double *)ptr(o[1]),
                                       c.r.B, (double *)ptr(out), s);
-    });
+    }, "tchem::IC::IntCoordSet::Hessian_cart2int");
 }
 at::Tensor IntCoordSet::Hessian_int2cart(const at::Tensor & r, const at::Tensor & intgrad, const at::Tensor & intHess) const {
     const std::string who = "tchem::IC::IntCoordSet::Hessian_int2cart";

@@ -203,9 +203,20 @@ TCHEM_API int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B);
 /* the same question for tchem_ic_sap_eval (pair-specialised chained kernel); ic == NULL: tchem_sap_eval */
 TCHEM_API int tchem_ic_sap_uses_specialised(const tchem_sap_table * sap, const tchem_ic_table * ic, int64_t B);
 
+/* NVRTC bookkeeping of this process: out4 = {kernels compiled, kernels taken from the on-disk cubin cache,
+ * kernels that failed to build, microseconds spent inside NVRTC}. The cache lives in $TCHEM_JIT_CACHE
+ * (empty or "0": disabled), else $XDG_CACHE_HOME/tchem_b200 or $HOME/.cache/tchem_b200, keyed by a hash of the
+ * generated source, the embedded math header and the CUDA runtime version. A specialised kernel that cannot
+ * be built is reported once on stderr and the interpreter kernel serves the table; TCHEM_JIT_STRICT=1 makes
+ * the call fail with TCHEM_ECUDA instead. */
+TCHEM_API int tchem_jit_stats(int64_t * out4);
+
 /* ---- measurement helpers (bench.py only) ------------------------------------------------ */
 /* number of kernels this library has launched in this process so far */
 TCHEM_API int64_t tchem_launch_count(void);
+/* "kernel name=launch count;" for every kernel this library has launched in this process (what was actually
+ * launched, not what the environment asked for). Returns the buffer size needed, copies at most `capacity`. */
+TCHEM_API int64_t tchem_kernel_log(char * buf, int64_t capacity);
 /* average device time in ms (CUDA events on `stream`) of `iters` launches of tchem_ic_eval */
 TCHEM_API int tchem_ic_eval_timed(const tchem_ic_table * t, const double * r, int64_t B, double * q,
                         double * J, double * K, int value_path, int iters,

@@ -17,3 +17,25 @@ def device_count():
 
 def launch_count():
     return _lib.tchem_launch_count()
+
+
+def kernel_log():
+    """{kernel name: launches so far in this process} - what the library actually launched"""
+    import ctypes as C
+    n = _lib.tchem_kernel_log(None, 0)
+    buf = C.create_string_buffer(int(n))
+    _lib.tchem_kernel_log(buf, n)
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            k, v = item.rsplit("=", 1)
+            out[k] = int(v)
+    return out
+
+
+def jit_stats():
+    """NVRTC bookkeeping: kernels compiled / taken from the disk cache / failed, seconds spent compiling"""
+    import ctypes as C
+    a = (C.c_int64 * 4)()
+    _lib.tchem_jit_stats(a)
+    return {"compiled": a[0], "cache_hits": a[1], "failed": a[2], "compile_s": a[3] * 1e-6}

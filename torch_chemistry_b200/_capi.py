@@ -44,6 +44,8 @@ def _sig(name, restype, *argtypes):
 _sig("tchem_last_error", C.c_char_p)
 _sig("tchem_device_count", _int)
 _sig("tchem_launch_count", _i64)
+_sig("tchem_kernel_log", _i64, C.c_char_p, _i64)
+_sig("tchem_jit_stats", _int, C.POINTER(C.c_int64))
 _sig("tchem_ic_parse_file", _int, C.c_char_p, C.c_char_p, C.POINTER(InvDisp), _int, _ip, _ip)
 _sig("tchem_ic_parse_text", _int, C.c_char_p, C.c_char_p, C.POINTER(InvDisp), _int, _ip, _ip)
 _sig("tchem_sap_parse_file", _int, C.c_char_p, _i32p, _int, _i32p, _int, _ip, _ip)
@@ -80,7 +82,7 @@ _sig("tchem_ic_sap_eval", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp, _vp)
 _sig("tchem_ic_sap_eval_host", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp)
 
 # every symbol include/tchem_b200.h declares (checked by tests/test_capi.py)
-DECLARED = ["tchem_last_error", "tchem_device_count", "tchem_launch_count", "tchem_ic_parse_file",
+DECLARED = ["tchem_last_error", "tchem_device_count", "tchem_launch_count", "tchem_kernel_log", "tchem_jit_stats", "tchem_ic_parse_file",
             "tchem_ic_parse_text", "tchem_sap_parse_file", "tchem_sap_parse_text", "tchem_ic_table_create",
             "tchem_ic_table_destroy", "tchem_ic_table_intdim", "tchem_ic_table_cartdim", "tchem_ic_table_device",
             "tchem_sap_table_create", "tchem_sap_table_destroy", "tchem_sap_table_nterms", "tchem_sap_table_sumdim",

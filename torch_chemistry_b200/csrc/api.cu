@@ -3,7 +3,10 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -18,7 +21,30 @@ std::mutex g_build_mutex;
 }
 
 int set_error(int code, const std::string & msg) { g_error = msg; return code; }
-void count_launch(int n) { g_launches += n; }
+
+int ensure_max_dynamic_smem(const void * fn, int device, int max_smem_optin) {
+    static std::mutex m;
+    static std::set<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lock(m);
+    if (done.count({fn, device})) return TCHEM_OK;
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+    done.insert({fn, device});
+    return TCHEM_OK;
+}
+namespace {
+std::mutex g_log_mutex;
+std::map<std::string, int64_t> & kernel_log() { static std::map<std::string, int64_t> m; return m; }
+}
+void count_launch(const char * kernel, int n) {
+    g_launches += n;
+    if (kernel) { std::lock_guard<std::mutex> lock(g_log_mutex); kernel_log()[kernel] += n; }
+}
+std::string kernel_log_text() {
+    std::lock_guard<std::mutex> lock(g_log_mutex);
+    std::string out;
+    for (const auto & kv : kernel_log()) out += kv.first + "=" + std::to_string(kv.second) + ";";
+    return out;
+}
 
 void release_grad_program(const tchem_ic_table * t);
 void release_dense_program(const tchem_ic_table * t);
@@ -190,6 +216,16 @@ int tchem_device_count(void) {
 
 int64_t tchem_launch_count(void) { return g_launches.load(); }
 
+int64_t tchem_kernel_log(char * buf, int64_t capacity) {
+    const std::string text = kernel_log_text();
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(text.size(), (size_t)capacity - 1);
+        std::memcpy(buf, text.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)text.size() + 1;
+}
+
 int tchem_ic_table_create(const tchem_invdisp_t * terms, int n_terms, int n_ic, int n_atoms,
                           int device, tchem_ic_table ** out) {
     if (!terms || !out || n_terms <= 0 || n_ic <= 0) return set_error(TCHEM_EINVAL, "tchem_ic_table_create: empty definition");
@@ -338,7 +374,7 @@ int tchem_ic_eval_host(const tchem_ic_table * tc, const double * r, int64_t B, d
     // ~48 MiB of results per piece, a multiple of the 32-geometry tile
     int64_t piece = (int64_t)std::max<size_t>(32, ((size_t(48) << 20) / std::max<size_t>(out_bytes, 1)) / 32 * 32);
     piece = std::min<int64_t>(piece, (B + 31) / 32 * 32);
-    std::lock_guard<std::mutex> lock(g_build_mutex);
+    std::lock_guard<std::mutex> lock(t->pipe_mutex);      // per table: calls on different tables (devices) overlap
     if (!t->pipe) t->pipe = new HostPipe();
     HostPipe & hp = *t->pipe;
     if (!hp.streams_ok) {
@@ -358,7 +394,10 @@ int tchem_ic_eval_host(const tchem_ic_table * tc, const double * r, int64_t B, d
         TC_CUDA(cudaMemcpyAsync(hp.d_r[slot], r + b0 * cd, nb * cd * 8, cudaMemcpyHostToDevice, s));
         rc = launch_ic_eval(t, mode, hp.d_r[slot], nb, q ? hp.d_q[slot] : nullptr, J ? hp.d_J[slot] : nullptr,
                             K ? hp.d_K[slot] : nullptr, s);
-        if (rc != TCHEM_OK) return rc;
+        if (rc != TCHEM_OK) {                      // no copy into the caller's buffers may stay pending
+            for (int k = 0; k < HostPipe::kSlots; k++) cudaStreamSynchronize(hp.stream[k]);
+            return rc;
+        }
         if (q) TC_CUDA(cudaMemcpyAsync(q + b0 * n, hp.d_q[slot], nb * n * 8, cudaMemcpyDeviceToHost, s));
         if (J) TC_CUDA(cudaMemcpyAsync(J + b0 * n * cd, hp.d_J[slot], nb * n * cd * 8, cudaMemcpyDeviceToHost, s));
         if (K) TC_CUDA(cudaMemcpyAsync(K + b0 * n * cd * cd, hp.d_K[slot], nb * n * cd * cd * 8, cudaMemcpyDeviceToHost, s));

@@ -10,7 +10,11 @@
 namespace tchem_b200 {
 
 int set_error(int code, const std::string & msg);          // stores msg thread-locally, returns code
-void count_launch(int n = 1);
+void count_launch(const char * kernel = nullptr, int n = 1);   // counts a launch; `kernel` (a string literal) feeds tchem_kernel_log
+// Raises the dynamic shared-memory limit of kernel `fn` to the device's opt-in maximum, once per
+// (function, device). The attribute belongs to the FUNCTION, which every table shares: setting it to
+// one table's need would lower it under another table's cached launch shape.
+int ensure_max_dynamic_smem(const void * fn, int device, int max_smem_optin);
 
 #define TC_CUDA(expr)                                                                        \
     do {                                                                                     \

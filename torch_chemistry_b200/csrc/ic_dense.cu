@@ -192,7 +192,8 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
                         for (int j = 0; j < WN; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
-            if (K4 < K && ((live >> (K4 >> 2)) & 1u)) {
+            // (unmasked operands can be wider than 128: the tail bit then lies beyond the 32-bit mask, so it is not consulted)
+            if (K4 < K && (!km.masks || ((live >> (K4 >> 2)) & 1u))) {
                 const bool in = K4 + tig < K;
                 const int k0 = in ? K4 : K - 1 - tig;        // clamped address, value masked
                 double a[2], b[WN];
@@ -817,7 +818,7 @@ int get_dense(const tchem_ic_table * t, DenseTable & out) {
     // structural nonzeros of J at k-step granularity (see DenseProgram)
     const bool masked = t->intdim <= 128 && t->cartdim <= 128;
     std::vector<uint32_t> colmask((t->cartdim + 7) / 8 + 4, 0), rowmask((t->intdim + 7) / 8 + 4, 0);
-    for (const DenseTerm & dt : terms)
+    if (masked) for (const DenseTerm & dt : terms)
         for (int a = 0; a < dt.pd.natoms; a++)
             for (int c = 0; c < 3; c++) {
                 const int row = dt.pd.out, col = 3 * dt.pd.atoms[a] + c;
@@ -905,7 +906,7 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&workspace), bytes, stream);
         if (e != cudaSuccess) { cudaGetLastError(); return set_error(TCHEM_ECUDA, name + ": cannot allocate the workspace for a molecule of this size"); }
     } else {
-        TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
         int per_sm = 0;
         TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, smem));
         if (per_sm < 1) per_sm = 1;
@@ -915,7 +916,7 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
     cudaError_t le = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kDenseThreads), args, smem, stream);
     if (workspace) cudaFreeAsync(workspace, stream);
     if (le != cudaSuccess) return set_error(TCHEM_ECUDA, cudaGetErrorString(le));
-    count_launch();
+    count_launch(op == 0 ? "dense_kernel<0:gradient_cart2int_matrix>" : op == 1 ? "dense_kernel<1:gradient_cart2int>" : op == 2 ? "dense_kernel<2:Hessian_int2cart>" : "dense_kernel<3:Hessian_cart2int>");
     return TCHEM_OK;
 }
 

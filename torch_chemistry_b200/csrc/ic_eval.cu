@@ -256,7 +256,7 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
                 return set_error(TCHEM_EINVAL, "tchem_ic_eval: molecule too large for the shared-memory tile (cartdim + row capacity)");
             if (8.0 * p.intdim * p.cartdim * kLanes >= 2147483648.0)
                 return set_error(TCHEM_EINVAL, "tchem_ic_eval: per-geometry output block too large");
-            TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { const int rc = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc != TCHEM_OK) return rc; }
             cfg.warps = ngroups * G; cfg.per_sm = 1; cfg.smem = smem;
             cfg.fn = fn;
         }
@@ -269,7 +269,7 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
                            G, (long long)grid, cfg.warps * 32, cfg.smem, p.cap, p.nchunks);
         void * args[] = {(void *)&p, (void *)&r, (void *)&B, (void *)&q, (void *)&J};
         TC_CUDA(cudaLaunchKernel(cfg.fn, dim3((unsigned)grid), dim3(cfg.warps * 32), args, cfg.smem, stream));
-        count_launch();
+        count_launch("ic_eval_group_kernel");
         return TCHEM_OK;
     }
     if (!cfg.fn) {
@@ -309,7 +309,7 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
             return set_error(TCHEM_EINVAL, "tchem_ic_eval: per-geometry output block too large");
         if (smem > (size_t)t->max_smem_optin)
             return set_error(TCHEM_EINVAL, "tchem_ic_eval: molecule too large for the shared-memory tile (cartdim + row capacity)");
-        TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc != TCHEM_OK) return rc; }
         int per_sm = 0;
         TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
         if (per_sm < 1) per_sm = 1;
@@ -328,7 +328,7 @@ int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t
                        mode, (long long)grid, warps * 32, smem, per_sm, p.cap, p.nchunks);
     void * args[] = {(void *)&p, (void *)&r, (void *)&B, (void *)&q, (void *)&J, (void *)&K};
     TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
-    count_launch();
+    count_launch(mode == MODE_VALUE ? "ic_eval_kernel<VALUE>" : mode == MODE_QJ ? "ic_eval_kernel<QJ>" : "ic_eval_kernel<QJK>");
     return TCHEM_OK;
 }
 

@@ -458,7 +458,9 @@ __device__ __forceinline__ void gather_store_impl(const SpanDesc & sp, const Ele
             // a whole sector of zeros: one 32-byte store per geometry (its first element is written
             // once more, as 0.0, if this step also holds non-zero elements: harmless)
             const int n = FULL ? kLanes : ntile;
-            if (al32) {
+            // the 32-byte store needs the STORE address aligned, not just the chunk base: sectors are aligned to the
+            // geometry block, whose offset from `out` need not be a multiple of 4 elements
+            if (al32 && (reinterpret_cast<uintptr_t>(o) & 31) == 0 && (gbytes & 31) == 0) {
 #pragma unroll 8
                 for (int g = 0; g < n; g++)
                     asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};\n" ::"l"(o + (int64_t)g * gbytes), "d"(0.0) : "memory");

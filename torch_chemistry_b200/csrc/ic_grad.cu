@@ -475,7 +475,7 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
         if (!force_tile && use_pair && !t->has5 && tb + wwarps * pw2 <= (size_t)t->max_smem_optin / 2) {
             const void * pfn = reinterpret_cast<const void *>(&grad_int2cart_pair_kernel<0>);
             const size_t psmem = tb + wwarps * pw2;
-            TC_CUDA(cudaFuncSetAttribute(pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            { const int rc_ = ensure_max_dynamic_smem(pfn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
             int per_sm = 0;
             TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfn, wwarps * 32, psmem));
             if (per_sm < 1) per_sm = 1;
@@ -483,21 +483,21 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
             const int64_t grid = std::min<int64_t>((npairs + wwarps - 1) / wwarps, (int64_t)t->sm_count * per_sm);
             void * args[] = {(void *)&gp, (void *)&r, (void *)&intgrad, (void *)&B, (void *)&cartgrad};
             TC_CUDA(cudaLaunchKernel(pfn, dim3((unsigned)grid), dim3(wwarps * 32), args, psmem, static_cast<cudaStream_t>(stream)));
-            count_launch();
+            count_launch("grad_int2cart_pair_kernel");
             return TCHEM_OK;
         }
         const size_t wsmem = tb + wwarps * pw;
         if (!force_tile && wsmem <= (size_t)t->max_smem_optin / 2) {
             const void * wfn = t->has5 ? reinterpret_cast<const void *>(&grad_int2cart_warp_kernel<true>)
                                        : reinterpret_cast<const void *>(&grad_int2cart_warp_kernel<false>);
-            TC_CUDA(cudaFuncSetAttribute(wfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            { const int rc_ = ensure_max_dynamic_smem(wfn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
             int per_sm = 0;
             TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfn, wwarps * 32, wsmem));
             if (per_sm < 1) per_sm = 1;
             const int64_t grid = std::min<int64_t>((B + wwarps - 1) / wwarps, (int64_t)t->sm_count * per_sm);
             void * args[] = {(void *)&gp, (void *)&r, (void *)&intgrad, (void *)&B, (void *)&cartgrad};
             TC_CUDA(cudaLaunchKernel(wfn, dim3((unsigned)grid), dim3(wwarps * 32), args, wsmem, static_cast<cudaStream_t>(stream)));
-            count_launch();
+            count_launch("grad_int2cart_warp_kernel");
             return TCHEM_OK;
         }
     }
@@ -509,7 +509,7 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
     const size_t smem = warps * wb;
     if (smem > (size_t)t->max_smem_optin)
         return set_error(TCHEM_EINVAL, "tchem::IC::IntCoordSet::gradient_int2cart: molecule too large for the shared-memory tile");
-    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
     int per_sm = 0;
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -517,7 +517,7 @@ int tchem_ic_grad_int2cart(const tchem_ic_table * t, const double * r, const dou
     int64_t grid = std::min<int64_t>((ntiles + warps - 1) / warps, (int64_t)t->sm_count * per_sm);
     void * args[] = {(void *)&gp, (void *)&r, (void *)&intgrad, (void *)&B, (void *)&cartgrad};
     TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, static_cast<cudaStream_t>(stream)));
-    count_launch();
+    count_launch("grad_int2cart_kernel");
     return TCHEM_OK;
 }
 

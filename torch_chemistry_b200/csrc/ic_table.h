@@ -1,5 +1,6 @@
 // host-side compiled IntCoordSet
 #pragma once
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -22,6 +23,7 @@ struct tchem_ic_table {
     mutable LaunchCfg cfg[tchem_b200::MODE_COUNT];
     // host pipeline state for the *_host entry points (lazily created)
     struct HostPipe * pipe = nullptr;
+    std::mutex pipe_mutex;        // serialises host-buffer calls on THIS table only (they share the pipe's slots)
 };
 
 namespace tchem_b200 {

@@ -15,7 +15,11 @@
 #include <cuda.h>          // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <dlfcn.h>
 
+#include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -780,23 +784,102 @@ void release_jit_sap(const tchem_sap_table * t) {
 }
 
 namespace {
-// NVRTC-compiles `src`, loads `name` and sizes the launch; marks `jk.failed` on any problem
+// ---- on-disk cubin cache ------------------------------------------------------------------------
+// key = FNV-1a of (source, embedded math header, compile options, CUDA runtime version); directory
+// TCHEM_JIT_CACHE (empty or "0" disables), else $XDG_CACHE_HOME/tchem_b200, $HOME/.cache/tchem_b200,
+// /tmp/tchem_b200_cache. Files are written to a temporary name and renamed, so concurrent ranks never
+// read a partial cubin.
+std::string jit_cache_dir() {
+    const char * e = getenv("TCHEM_JIT_CACHE");
+    if (e) return (e[0] == 0 || std::strcmp(e, "0") == 0) ? std::string() : std::string(e);
+    if (const char * x = getenv("XDG_CACHE_HOME")) if (x[0]) return std::string(x) + "/tchem_b200";
+    if (const char * h = getenv("HOME")) if (h[0]) return std::string(h) + "/.cache/tchem_b200";
+    return "/tmp/tchem_b200_cache";
+}
+void mkdir_p(const std::string & dir) {
+    for (size_t i = 1; i <= dir.size(); i++)
+        if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
+}
+std::string jit_cache_path(const std::string & src) {
+    const std::string dir = jit_cache_dir();
+    if (dir.empty()) return std::string();
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const char * p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } };
+    mix(src.data(), src.size());
+    mix(kMathHeader, std::strlen(kMathHeader));
+    int rt = 0;
+    cudaRuntimeGetVersion(&rt);
+    const std::string tag = "sm_100a c++17 lineinfo rt" + std::to_string(rt);
+    mix(tag.data(), tag.size());
+    char name[40];
+    snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)h);
+    return dir + name;
+}
+std::vector<char> jit_cache_load(const std::string & path) {
+    std::vector<char> v;
+    if (path.empty()) return v;
+    FILE * f = fopen(path.c_str(), "rb");
+    if (!f) return v;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n > 0) { v.resize((size_t)n); if (fread(v.data(), 1, (size_t)n, f) != (size_t)n) v.clear(); }
+    fclose(f);
+    return v;
+}
+void jit_cache_store(const std::string & path, const std::vector<char> & cubin) {
+    if (path.empty() || cubin.empty()) return;
+    mkdir_p(path.substr(0, path.rfind('/')));
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    FILE * f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (ok) ::rename(tmp.c_str(), path.c_str()); else ::remove(tmp.c_str());
+}
+
+bool jit_strict() { static const bool v = env_int("TCHEM_JIT_STRICT", 0) != 0; return v; }
+struct JitStats { std::atomic<int64_t> compiled{0}, cache_hits{0}, failed{0}, compile_us{0}; };
+JitStats & jit_stats() { static JitStats s; return s; }
+
+// NVRTC-compiles `src` (or takes the cubin from the on-disk cache), loads `name` and sizes the launch; marks
+// `jk.failed` on any problem. A failure is never silent: one line on stderr per kernel (the interpreter then
+// serves the table at roughly half the throughput), and with TCHEM_JIT_STRICT=1 the launch fails instead.
 void jit_finish(JitKernel & jk, const std::string & src, const char * name, size_t smem, int max_smem_optin, bool debug) {
-    std::string log;
+    std::string log, why;
     std::vector<char> cubin;
-    if (!src.empty()) cubin = jit_compile(src, log, debug);
-    if (debug) fprintf(stderr, "[tchem] jit %s: %zu bytes of source, %zu bytes of cubin\n%s\n", name, src.size(), cubin.size(), log.c_str());
+    bool from_cache = false;
+    const std::string cpath = src.empty() ? std::string() : jit_cache_path(src);
+    if (!src.empty()) {
+        cubin = jit_cache_load(cpath);
+        from_cache = !cubin.empty();
+        if (!from_cache) {
+            const auto t0 = std::chrono::steady_clock::now();
+            cubin = jit_compile(src, log, debug);
+            jit_stats().compile_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        }
+    }
+    if (debug) fprintf(stderr, "[tchem] jit %s: %zu bytes of source, %zu bytes of cubin%s\n%s\n", name, src.size(), cubin.size(),
+                       from_cache ? " (disk cache)" : "", log.c_str());
     jk.smem = smem;
-    if (cubin.empty()) jk.failed = true;
+    if (cubin.empty()) { jk.failed = true; why = src.empty() ? "table not expressible" : log.empty() ? "NVRTC produced no cubin" : log.substr(0, 300); }
+    else if (smem > (size_t)max_smem_optin) { jk.failed = true; why = "shared-memory plan exceeds the device limit"; }
     else if (cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess
              || cudaLibraryGetKernel(&jk.fn, jk.lib, name) != cudaSuccess
-             || smem > (size_t)max_smem_optin
              || cudaFuncSetAttribute((const void *)jk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
              || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jk.per_sm, (const void *)jk.fn, jk.warps * 32, smem) != cudaSuccess
              || jk.per_sm < 1) {
-        cudaGetLastError();
+        why = std::string("loading the cubin failed: ") + cudaGetErrorString(cudaGetLastError());
         jk.failed = true;
+        if (from_cache) ::remove(cpath.c_str());          // a stale / corrupt cache entry must not fail forever
     }
+    if (jk.failed) {
+        jit_stats().failed++;
+        if (!src.empty())
+            fprintf(stderr, "[tchem] WARNING: the specialised kernel %s could not be built (%s); the interpreter kernel serves this table "
+                            "(about half the throughput). TCHEM_JIT_STRICT=1 turns this into an error.\n", name, why.c_str());
+    } else if (from_cache) jit_stats().cache_hits++;
+    else { jit_stats().compiled++; jit_cache_store(cpath, cubin); }
     if (debug) fprintf(stderr, "[tchem] jit %s: %s, %d warps/block, %d blocks/SM, %zu B smem\n", name,
                        jk.failed ? "FAILED (interpreter serves this table)" : "ok", jk.warps, jk.per_sm, jk.smem);
 }
@@ -838,13 +921,13 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
         }
         if (!jk.failed) { k = &jk; break; }
     }
-    if (!k) return -1;
+    if (!k) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem: the specialised chained kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     const int64_t ntiles = (B + 31) / 32;
     const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)st->sm_count * k->per_sm);
     long long Bll = B;
     void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
-    count_launch();
+    count_launch(variant == 1 ? "tchem_jit_chain_bulk" : "tchem_jit_chain");
     return TCHEM_OK;
 }
 
@@ -869,14 +952,14 @@ int launch_jit_sap_hess(const tchem_sap_table * st, const double * x, int64_t B,
             const std::string src = jit_hess_source(st->h_terms, st->sumdim, jk.warps, jk.blocks);
             jit_finish(jk, src, "tchem_jit_sap_hess", per_warp * jk.warps, st->max_smem_optin, debug);
         }
-        if (jk.failed) return -1;
+        if (jk.failed) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem: the specialised Jacobian2nd kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     }
     const int64_t ntiles = (B + 31) / 32;
     const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)st->sm_count * k->per_sm);
     long long Bll = B;
     void * args[] = {(void *)&x, (void *)&Bll, (void *)&K};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
-    count_launch();
+    count_launch("tchem_jit_sap_hess");
     return TCHEM_OK;
 }
 
@@ -910,7 +993,7 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
         }
         if (!jk.failed) { k = &jk; break; }
     }
-    if (!k) return -1;
+    if (!k) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem_ic_eval: the specialised q+J kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     const int64_t ntiles = (B + 31) / 32;
     const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
     long long Bll = B;
@@ -942,7 +1025,7 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
         void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J};
         TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
     }
-    count_launch();
+    count_launch(variant == 1 ? "tchem_jit_qJ_bulk" : "tchem_jit_qJ");
     return TCHEM_OK;
 }
 
@@ -1024,6 +1107,13 @@ int64_t tchem_sap_jit_source(const int32_t * term_ptr, const int32_t * coords, i
         buf[n] = 0;
     }
     return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+int tchem_jit_stats(int64_t * out4) {
+    if (!out4) return set_error(TCHEM_EINVAL, "tchem_jit_stats: null argument");
+    out4[0] = jit_stats().compiled.load(); out4[1] = jit_stats().cache_hits.load();
+    out4[2] = jit_stats().failed.load();   out4[3] = jit_stats().compile_us.load();
+    return TCHEM_OK;
 }
 
 // 1 when tchem_ic_eval(J != NULL, K == NULL) on a batch of B geometries runs the specialised kernel

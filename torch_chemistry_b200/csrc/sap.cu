@@ -319,7 +319,7 @@ int launch_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, dou
     const size_t smem = tb + warps * wb;
     if (smem > (size_t)st->max_smem_optin) return set_error(TCHEM_EINVAL, "tchem_sap_jacobian2nd: set too large for the shared-memory tile");
     const void * fn = reinterpret_cast<const void *>(&sap_hess_kernel);
-    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = ensure_max_dynamic_smem(fn, st->device, st->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
     int per_sm = 0;
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -328,7 +328,7 @@ int launch_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, dou
     if (grid < 1) return TCHEM_OK;
     void * args[] = {(void *)&st->prog, (void *)&x, (void *)&B, (void *)&K, (void *)&rows_per};
     TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
-    count_launch();
+    count_launch("sap_hess_kernel");
     return TCHEM_OK;
 }
 
@@ -356,7 +356,7 @@ int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const dou
     while (warps > 1 && tb + warps * wb > (size_t)st->max_smem_optin) warps--;
     const size_t smem = tb + warps * wb;
     if (smem > (size_t)st->max_smem_optin) return set_error(TCHEM_EINVAL, "tchem_sap_eval: set too large for the shared-memory tile");
-    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = ensure_max_dynamic_smem(fn, st->device, st->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
     int per_sm = 0;
     TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -365,7 +365,7 @@ int launch_sap(const tchem_sap_table * st, const tchem_ic_table * ict, const dou
     if (grid < 1) return TCHEM_OK;
     void * args[] = {(void *)&st->prog, (void *)&icp, (void *)&in, (void *)&B, (void *)&q_out, (void *)&y, (void *)&J};
     TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
-    count_launch();
+    count_launch(chained ? "sap_eval_kernel<chained>" : "sap_eval_kernel");
     return TCHEM_OK;
 }
 
@@ -556,6 +556,7 @@ int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sa
     if (!ic || !sap) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: null table");
     if (ic->intdim != sap->sumdim)
         return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: x must have a same dimension as the coordinates (intdim != sum of dimensions)");
+    if (ic->device != sap->device) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: tables live on different devices");
     if (B < 0) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: negative batch");
     if (B == 0) return TCHEM_OK;
     if (!r || (!y && !J && !q_out)) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_host: null argument");
@@ -568,6 +569,7 @@ int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sa
     int64_t piece = (int64_t)std::max<size_t>(32, ((size_t(48) << 20) / (8 * per_geom)) / 32 * 32);
     piece = std::min<int64_t>(piece, (B + 31) / 32 * 32);
     SapHostPipe & hp = sap->pipe;
+    std::lock_guard<std::mutex> lock(hp.mutex);
     if (!hp.ok) {
         for (int s = 0; s < SapHostPipe::kSlots; s++) TC_CUDA(cudaStreamCreateWithFlags(&hp.stream[s], cudaStreamNonBlocking));
         hp.ok = true;
@@ -592,7 +594,10 @@ int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sa
         double * d_J = d_y + (y ? piece * nt : 0);
         TC_CUDA(cudaMemcpyAsync(d_r, r + b0 * cd, nb * cd * 8, cudaMemcpyHostToDevice, s));
         rc = launch_sap(sap, ic, d_r, nb, q_out ? d_q : nullptr, y ? d_y : nullptr, J ? d_J : nullptr, s);
-        if (rc != TCHEM_OK) return rc;
+        if (rc != TCHEM_OK) {                      // no copy into the caller's buffers may stay pending
+            for (int k = 0; k < SapHostPipe::kSlots; k++) cudaStreamSynchronize(hp.stream[k]);
+            return rc;
+        }
         if (q_out) TC_CUDA(cudaMemcpyAsync(q_out + b0 * n, d_q, nb * n * 8, cudaMemcpyDeviceToHost, s));
         if (y) TC_CUDA(cudaMemcpyAsync(y + b0 * nt, d_y, nb * nt * 8, cudaMemcpyDeviceToHost, s));
         if (J) TC_CUDA(cudaMemcpyAsync(J + b0 * nt * n, d_J, nb * nt * n * 8, cudaMemcpyDeviceToHost, s));

@@ -1,5 +1,6 @@
 // host-side compiled SAPSet (shared by sap.cu and jit.cu)
 #pragma once
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -35,6 +36,7 @@ struct SapHostPipe {                     // device staging of the chained host-b
     double * buf[kSlots] = {};
     size_t cap = 0;
     bool ok = false;
+    std::mutex mutex;                    // host-buffer calls on one SAPSet share the slots: one at a time
 };
 
 struct tchem_sap_table {

@@ -153,7 +153,17 @@ class IntCoordSet:
         return tuple(self._eval(r, True, True, False, "compute_IC_J_K", out))
 
     # ---- gradient / Hessian transforms (source/IC/IntCoordSet.cpp:178-266) -----------------
-    def _transform(self, fn, name, r, extras, out_shape):
+    #: cart2int transforms factor J J^T per geometry; the reference's at::cholesky raises when it is not positive
+    #: definite (source/IC/IntCoordSet.cpp:182). True: read the device flag back after the launch (one
+    #: synchronisation) and raise RuntimeError like the reference; False keeps the call asynchronous (the affected
+    #: geometries' results are NaN either way, and `factor_status()` can be polled later).
+    check_factorisation = True
+
+    def factor_status(self):
+        """1 when a cart2int call since the last poll met a non-positive-definite J J^T (synchronises)"""
+        return int(lib.tchem_ic_factor_status(self._handle))
+
+    def _transform(self, fn, name, r, extras, out_shape, factors=False):
         r2, batched = self._prep(r, name)
         B = r2.shape[0]
         dev_r = self._on_device(r2)
@@ -164,17 +174,20 @@ class IntCoordSet:
         ptr = lambda t: C.c_void_p(t.data_ptr())
         if B > 0:
             check(fn(self._handle, ptr(dev_r), *[ptr(a) for a in args], B, ptr(out), _stream_ptr(self.device)))
+            if factors and self.check_factorisation and self.factor_status():
+                raise RuntimeError("tchem::IC::IntCoordSet::%s: cholesky: J J^T is not positive definite for at least one "
+                                   "geometry of the batch (redundant or singular internal coordinates)" % name)
         if not r2.is_cuda:
             out = out.cpu()
         return out if batched else out[0]
 
     def gradient_cart2int_matrix(self, r):
         return self._transform(lib.tchem_ic_grad_cart2int_matrix, "gradient_cart2int", r, [],
-                               (self.intdim, self.cartdim))
+                               (self.intdim, self.cartdim), factors=True)
 
     def gradient_cart2int(self, r, cartgrad):
         return self._transform(lib.tchem_ic_grad_cart2int, "gradient_cart2int", r,
-                               [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient")], (self.intdim,))
+                               [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient")], (self.intdim,), factors=True)
 
     def gradient_int2cart(self, r, intgrad):
         return self._transform(lib.tchem_ic_grad_int2cart, "gradient_int2cart", r,
@@ -184,7 +197,7 @@ class IntCoordSet:
         return self._transform(lib.tchem_ic_hess_cart2int, "Hessian_cart2int", r,
                                [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient"),
                                 (cartHess, (self.cartdim, self.cartdim), "Cartesian coordinate Hessian")],
-                               (self.intdim, self.intdim))
+                               (self.intdim, self.intdim), factors=True)
 
     def Hessian_int2cart(self, r, intgrad, intHess):
         return self._transform(lib.tchem_ic_hess_int2cart, "Hessian_int2cart", r,
