@@ -44,8 +44,37 @@ def parity_ratio(x, ref, tol=1e-12):
     return float((d / bound).max())
 
 
+# worst observed error / bound of every parity assertion of the session, written at the end of the run to
+# $TCHEM_PARITY_RATIOS (default gpurun_out/parity_ratios.json; committed copy: profiles/r02_parity_ratios.json)
+RATIOS = {}
+
+
+def record_ratio(what, ratio, tol):
+    prev = RATIOS.get(what)
+    if prev is None or ratio > prev["worst_error_over_bound"]:
+        RATIOS[what] = {"worst_error_over_bound": ratio, "tol": tol}
+
+
+def pytest_sessionfinish(session, exitstatus):
+    import json
+    if not RATIOS:
+        return
+    path = os.environ.get("TCHEM_PARITY_RATIOS", os.path.join(ROOT, "gpurun_out", "parity_ratios.json"))
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        old = {}
+        if os.path.exists(path):
+            old = json.load(open(path))
+        old.update(RATIOS)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+    except Exception:
+        pass
+
+
 def assert_parity(x, ref, what, tol=1e-12):
     ratio = parity_ratio(x, ref, tol)
+    record_ratio(what, ratio, tol)
     assert ratio <= 1.0, "%s: worst |x-ref| / max(%g, %g|ref|) = %.3g" % (what, tol, tol, ratio)
 
 
@@ -76,6 +105,7 @@ def assert_q_parity(q, q_ref, terms, r, what, tol=1e-12):
     d = np.abs(q - q_ref)
     assert np.isfinite(q).all(), what + ": non-finite q"
     worst = float((d / bound).max())
+    record_ratio(what, worst, tol)
     assert worst <= 1.0, "%s: worst |q-ref| / bound = %.3g" % (what, worst)
 
 

@@ -519,6 +519,79 @@ def test_dense_transforms_beyond_shared_memory(T):
         assert_parity(host(torch.einsum("bij,bj->bi", M, gr)), host(gq1), "chain%d cart2int matrix" % natoms, tol=1e-10)
 
 
+def test_dense_transforms_43_atoms_odd_cartdim(T):
+    """cartdim 129 (> 128, not a multiple of 4): no sparsity masks, the K % 4 remainder step of every product must
+    still run (the mask word has only 32 bits). Against the oracle."""
+    rng = np.random.default_rng(3)
+    natoms = 43
+    w = T.workloads.chain(natoms, "chain43", seed=13)
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=natoms)
+    orc = O.IntCoordSet("default", w.ic_text)
+    r = w.geometries(2, seed=5)
+    gq = rng.standard_normal((2, s.intdim))
+    Hq = rng.standard_normal((2, s.intdim, s.intdim))
+    gr = rng.standard_normal((2, s.cartdim))
+    assert_parity(host(s.Hessian_int2cart(dev(r), dev(gq), dev(Hq))), orc.Hessian_int2cart(r, gq, Hq), "chain43 Hessian_int2cart vs oracle")
+    assert_parity(host(s.gradient_cart2int(dev(r), dev(gr))), orc.gradient_cart2int(r, gr), "chain43 gradient_cart2int vs oracle", tol=1e-11)
+    assert_parity(host(s.gradient_cart2int_matrix(dev(r))), orc.gradient_cart2int_matrix(r), "chain43 cart2int matrix vs oracle", tol=1e-11)
+
+
+def test_alternating_tables_of_different_size(T):
+    """The dynamic shared-memory limit is an attribute of the kernel FUNCTION, which all tables share: a small
+    table's first use must not lower it under a larger table's cached launch shape (every kernel family)."""
+    big_w, small_w = T.workloads.get("C4"), T.workloads.chain(14, "chain14", seed=9)
+    big = T.IntCoordSet.from_text("default", big_w.ic_text, n_atoms=big_w.natoms)
+    small = T.IntCoordSet.from_text("default", small_w.ic_text, n_atoms=14)
+    rb, rs = big_w.geometries(96, seed=1), small_w.geometries(96, seed=2)
+    ob, osm = O.IntCoordSet("default", big_w.ic_text), O.IntCoordSet("default", small_w.ic_text)
+    rng = np.random.default_rng(1)
+    for rnd in range(2):
+        for s, o, r, tag in ((big, ob, rb, "big"), (small, osm, rs, "small")):
+            q, J = s.compute_IC_J(dev(r))
+            qo, Jo = o.qJ(r[:4])
+            assert_parity(host(J[:4]), Jo, "alternating %s J" % tag)
+            q, J, K = s.compute_IC_J_K(dev(r[:8]))
+            assert_parity(host(K[:2]), o.qJK(r[:2])[2], "alternating %s K" % tag)
+            assert_parity(host(s(dev(r))[:4]), o.q(r[:4]), "alternating %s value path" % tag)
+            gq = rng.standard_normal((4, s.intdim))
+            assert_parity(host(s.gradient_int2cart(dev(r[:4]), dev(gq))), o.gradient_int2cart(r[:4], gq), "alternating %s gradient_int2cart" % tag)
+            Hq = rng.standard_normal((2, s.intdim, s.intdim))
+            assert_parity(host(s.Hessian_int2cart(dev(r[:2]), dev(gq[:2]), dev(Hq))), o.Hessian_int2cart(r[:2], gq[:2], Hq),
+                          "alternating %s Hessian_int2cart" % tag)
+
+
+def test_cart2int_raises_when_factorisation_fails(T):
+    """at::cholesky throws when J J^T is not positive definite (source/IC/IntCoordSet.cpp:182) - here a geometry with
+    two coincident atoms (J is 0/0). The batched calls raise RuntimeError (flag read back after the launch); with the
+    check off the affected geometry's results are NaN, never garbage, and the other geometries are untouched."""
+    w = T.workloads.get("C1")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=3)
+    rh = w.geometries(5, seed=3)
+    rh[2, 3:6] = rh[2, 0:3]
+    r = dev(rh)
+    gr = torch.randn(5, 9, dtype=torch.float64, device="cuda")
+    Hr = torch.randn(5, 9, 9, dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError):
+        s.gradient_cart2int(r, gr)
+    with pytest.raises(RuntimeError):
+        s.gradient_cart2int_matrix(r)
+    with pytest.raises(RuntimeError):
+        s.Hessian_cart2int(r, gr, Hr)
+    s.check_factorisation = False
+    good = [0, 1, 3, 4]
+    orc = O.IntCoordSet("default", w.ic_text)
+    out = s.gradient_cart2int(r, gr)
+    torch.cuda.synchronize()
+    assert s.factor_status() == 1 and s.factor_status() == 0          # reported once, then cleared
+    assert bool(torch.isnan(out[2]).all())
+    assert_parity(host(out[good]), orc.gradient_cart2int(rh[good], host(gr)[good]), "C1 gradient_cart2int beside a failed geometry")
+    M = s.gradient_cart2int_matrix(r)
+    Hq = s.Hessian_cart2int(r, gr, Hr)
+    assert bool(torch.isnan(M[2]).all()) and bool(torch.isnan(Hq[2]).all())
+    assert bool(torch.isfinite(M[good]).all()) and bool(torch.isfinite(Hq[good]).all())
+    assert s.factor_status() == 1
+
+
 def test_chained_host_buffers_match_device_path(T):
     w = T.workloads.get("C5")
     ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)

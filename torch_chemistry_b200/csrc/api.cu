@@ -48,6 +48,7 @@ std::string kernel_log_text() {
 
 void release_grad_program(const tchem_ic_table * t);
 void release_dense_program(const tchem_ic_table * t);
+void release_sparse_program(const tchem_ic_table * t);
 void release_jit(const tchem_ic_table * t);
 extern thread_local int64_t g_batch_hint;
 int launch_ic_eval(const tchem_ic_table * t, int mode, const double * r, int64_t B,
@@ -266,6 +267,7 @@ void tchem_ic_table_destroy(tchem_ic_table * t) {
         for (int m = 0; m < MODE_COUNT; m++) cudaFree(t->dev_blob[m]);
         release_grad_program(t);
         release_dense_program(t);
+        release_sparse_program(t);
         release_jit(t);
         if (t->pipe) { t->pipe->release(); delete t->pipe; }
     }

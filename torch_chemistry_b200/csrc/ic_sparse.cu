@@ -1,0 +1,1113 @@
+// The gradient / Hessian transforms with J kept SPARSE (round 2; ic_dense.cu keeps the all-DMMA flavour for
+// definition tables whose J is not sparse).
+//
+// Replaces, batched (reference source/IC/IntCoordSet.cpp):
+//   gradient_cart2int_matrix :178-188   M   = (J J^T)^-1 J
+//   gradient_cart2int        :190-205   g_q = (J J^T)^-1 (J g_r)
+//   Hessian_int2cart         :248-266   H_r = J^T H_q J + sum_k g_q[k] K[k]
+//   Hessian_cart2int         :221-246   H_q = A^T H_r A - sum_k (A^T g_r)[k] A^T K[k] A,  A^T = (J J^T)^-1 J
+//
+// A row of J has at most 15 structural nonzeros per term (3 per atom of the invariant displacement), known from
+// the definition table alone. Every product with J therefore runs over a compressed row / column list with plain
+// FP64 FMAs (C4: 750 nonzeros instead of 7 560 elements: ~10x fewer flops than the dense-masked DMMA products),
+// and only the two genuinely dense intdim^3 products of Hessian_cart2int stay on the tensor cores.
+//
+// Two kernels:
+//  * factor_kernel - ONE WARP PER GEOMETRY, six resident per SM, no block barrier anywhere. J J^T is assembled
+//    from the compressed rows into ROW-MAJOR PACKED lower storage (28 KB for 84 coordinates), factored in place
+//    (right-looking Cholesky, panels of 8 columns held in registers, pivots exchanged by shuffles), with the
+//    right-hand side J g_r riding along as a bordered row (= the forward substitution), then back substitution.
+//    For the matrix / Hessian entry points the same warp continues with the reference's potri (explicit inverse of
+//    the factor, row-oriented; then W^T W), still in place, and parks the packed inverse and g_q in a workspace.
+//    The serial pivot chain of one geometry overlaps with the other warps' geometries instead of idling a block.
+//  * hess_kernel - one block per geometry: compressed-column products U = J^T H_q, X = U J (int -> cart) or
+//    V = J H_c, S = V J^T and the DMMA products (J J^T)^-1 S (J J^T)^-1 (cart -> int); the second-derivative term
+//    sum_k g_k K[k] is evaluated as (term, direction) Dual passes that park their 3 x 3 blocks in slots, and a fixed-
+//    order gather adds the slots into the accumulator: no atomics, bit-reproducible. The next geometry's operand
+//    matrix is in flight (cp.async) while the current one is being worked on, and its J rows are evaluated by the
+//    threads left over by the (term, direction) tasks.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <vector>
+
+#include "dmma_gemm.cuh"
+#include "ic_eval.cuh"
+#include "ic_table.h"
+
+namespace tchem_b200 {
+
+struct SpTerm {                       // 64 bytes
+    PrimDesc pd;                      // pd.out = internal coordinate (row) of the term
+    double coef;
+    int16_t pos[5];                   // Jv position of the 3 entries of atom slot a (row-compressed J)
+    int16_t pad_;
+    int32_t kslot;                    // first slot of the term's block-upper second-derivative storage
+};
+
+struct SparseProgram {                // device pointers into one blob (starts at `terms`)
+    const SpTerm *   terms;           // row order
+    const int32_t *  row_ptr;         // [intdim + 1] terms of a row
+    const int32_t *  jrow_order;      // [njrow] rows in evaluation order: grouped by type, groups padded to 32 with -1
+    const uint32_t * ktasks;          // [nktasks] (term << 8) | direction, heaviest first
+    const uint16_t * nz_ptr;          // [intdim + 1] CSR over Jv
+    const uint16_t * nz_col;          // [nnz] column of every Jv position
+    const uint16_t * col_ptr;         // [cartdim + 1] CSC
+    const uint32_t * col_ent;         // [nnz] (row << 16) | Jv position
+    const uint32_t * pair_dest;       // [npairs_pad] packed index (i (i + 1) / 2 + j) of a structurally nonzero A[i][j], j <= i
+    const uint32_t * pair_ent;        // [maxc][npairs_pad] (Jv position in row i << 16) | Jv position in row j of a common atom
+    const uint32_t * gk_blk;          // [ngblk] (atom A << 16) | atom B: 3 x 3 block of the g.K accumulator that receives slots
+    const uint32_t * gk_ptr;          // [ngblk + 1]
+    const uint32_t * gk_src;          // [ngsrc] (slot index << 1) | transposed
+    int32_t nterms, njrow, nktasks, nnz, nnz_pad, npairs_pad, maxc, ngblk, ngsrc, nslots;
+    int32_t intdim, cartdim, ldh;     // ldh: leading dimension of the intdim x intdim DMMA operands (4 or 12 mod 16)
+    int32_t blob_bytes;
+    int32_t tab_in_smem;              // per launch: the block kernel works on a shared-memory copy of the blob
+};
+
+namespace {
+
+constexpr int kNB = 8;                // panel width of the warp-level factorisation
+constexpr int kMaxSlots = 4;          // lanes x 4 = 128: upper limit of intdim + 1 and cartdim on this path
+constexpr int kHessThreads = 288;     // 9 warps: (J rows + (term, direction) tasks) of C4 = 834 tasks = 3 rounds
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ double nan64() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// ---- sinks -------------------------------------------------------------------------------------------
+struct JvSink {                        // Jv[pos[atom slot] + component] += coef * J_term   (row owned by one thread)
+    double * Jv;
+    const int16_t * pos;
+    double coef;
+    __device__ __forceinline__ void value(double) const {}
+    __device__ __forceinline__ void jac_block(const int *, int i, const V3<double> & J) const {
+        double * p = Jv + pos[i];
+        p[0] = fma(coef, J.x, p[0]);
+        p[1] = fma(coef, J.y, p[1]);
+        p[2] = fma(coef, J.z, p[2]);
+    }
+    __device__ __forceinline__ void jac_entry(const int *, int m, double j) const {
+        const int a = m / 3;
+        double * p = Jv + pos[a] + (m - 3 * a);
+        p[0] = fma(coef, j, p[0]);
+    }
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int, int, const V3<Dual> &) const {}
+    __device__ __forceinline__ void hess_entry5(const int *, int, int, double) const {}
+};
+
+struct SlotSink {                      // S[9 kblock(i, j) + 3 k + l] = w * d2 q / d r_(i,k) d r_(j,l),  i <= j
+    double * S;
+    double w;
+    __device__ __forceinline__ void value(double) const {}
+    __device__ __forceinline__ void jac_block(const int *, int, const V3<double> &) const {}
+    __device__ __forceinline__ void jac_entry(const int *, int, double) const {}
+    template <int N> __device__ __forceinline__ void hess_block(const int *, int dir, int i, const V3<Dual> & J) const {
+        const int j = dir / 3, l = dir - 3 * j;
+        if (i > j) return;
+        double * p = S + 9 * kblock(i, j, N) + l;
+        p[0] = w * J.x.d;
+        p[3] = w * J.y.d;
+        p[6] = w * J.z.d;
+    }
+    __device__ __forceinline__ void hess_entry5(const int *, int m1, int m2, double k) const {
+        const int i = m1 / 3, j = m2 / 3, kk = m1 - 3 * i, ll = m2 - 3 * j;
+        double * p = S + 9 * kblock(i, j, 5);
+        p[3 * kk + ll] = w * k;
+        if (i == j) p[3 * ll + kk] = w * k;
+    }
+};
+
+// J rows of one geometry into the compressed value array Jv (zeroed here); `tid` of `nthreads` take the rows in
+// the table's evaluation order (same-type rows share a warp)
+template <bool HAS5>
+__device__ __forceinline__ void eval_J_rows(const SparseProgram & sp, const double * rg, double * Jv, int tid, int nthreads) {
+    for (int k = tid; k < sp.njrow; k += nthreads) {
+        const int row = sp.jrow_order[k];
+        if (row < 0) continue;
+        for (int p = sp.nz_ptr[row]; p < sp.nz_ptr[row + 1]; p++) Jv[p] = 0.0;
+        for (int t = sp.row_ptr[row]; t < sp.row_ptr[row + 1]; t++) {
+            const SpTerm & term = sp.terms[t];
+            JvSink sink;
+            sink.Jv = Jv; sink.pos = term.pos; sink.coef = term.coef;
+            eval_primitive<MODE_QJ, HAS5>(term.pd, GeomLoader{rg}, sink);
+        }
+    }
+}
+
+// ======================================================================================================
+// factor_kernel: one warp = one geometry
+// ======================================================================================================
+// In-place lower Cholesky factor of the packed matrix A (rows 0 .. n-1; with `border` row n holds a right-hand
+// side b and ends as L^-1 b). Right-looking over panels of 8 columns:
+//  * panel: lane = row (rows j0 + lane + 32 m), the row's 8 panel entries in registers; pivot c belongs to lane c
+//    (slot 0); its reciprocal square root is taken by every lane, the scaled pivot column's diagonal-block entries
+//    travel by shuffle;
+//  * trailing update A[i][j] -= sum_c L[i][c] L[j][c]: lane = column j, its L[j][.] kept in registers, rows walked
+//    two at a time with the 8 panel entries of the row read as broadcasts.
+// rdiag[j] = 1 / L[j][j]. Returns false when a pivot is not positive (NaN included).
+__device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border, double * rdiag, int lane) {
+    const int last = border ? n : n - 1;
+    bool ok = true;
+    for (int j0 = 0; j0 < n; j0 += kNB) {
+        const int bs = min(kNB, n - j0);
+        const int nrows = last - j0 + 1;
+        double a[kMaxSlots][kNB];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = j0 + lane + 32 * m;
+            const double * Ai = A + tri(min(i, last)) + j0;
+#pragma unroll
+            for (int c = 0; c < kNB; c++) {
+                const bool valid = i <= last && c < bs && (j0 + c <= i || i == n);
+                a[m][c] = valid ? Ai[c] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kNB; c++) {
+            if (c < bs) {
+                const double d = __shfl_sync(kFull, a[0][c], c);
+                ok = ok && d > 0.0;
+                double rs = rsqrt(d);
+                rs = fma(0.5 * rs, fma(-d * rs, rs, 1.0), rs);          // one Newton step: correctly rounded in all but rare cases
+                if (lane == 0) rdiag[j0 + c] = rs;
+#pragma unroll
+                for (int m = 0; m < kMaxSlots; m++)
+                    if (32 * m < nrows) a[m][c] *= rs;                  // the pivot's own lane: d / sqrt(d) = sqrt(d)
+#pragma unroll
+                for (int c2 = c + 1; c2 < kNB; c2++) {
+                    if (c2 < bs) {
+                        const double t = __shfl_sync(kFull, a[0][c], c2);   // L[j0 + c2][j0 + c]
+#pragma unroll
+                        for (int m = 0; m < kMaxSlots; m++)
+                            if (32 * m < nrows) a[m][c2] = fma(-a[m][c], t, a[m][c2]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = j0 + lane + 32 * m;
+            double * Ai = A + tri(min(i, last)) + j0;
+#pragma unroll
+            for (int c = 0; c < kNB; c++) {
+                const bool valid = i <= last && c < bs && (j0 + c <= i || i == n);
+                if (valid) Ai[c] = a[m][c];
+            }
+        }
+        __syncwarp();
+        const int t0 = j0 + bs;
+        if (t0 < n) {
+            double Lj[kMaxSlots][kNB];
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int j = t0 + lane + 32 * m;
+                const double * Aj = A + tri(min(j, n - 1)) + j0;
+#pragma unroll
+                for (int c = 0; c < kNB; c++) Lj[m][c] = (j < n && c < bs) ? Aj[c] : 0.0;
+            }
+            // rows two at a time, two partial sums per element: four to twelve independent FMA chains
+            for (int i = t0; i <= last; i += 2) {
+                const bool two = i + 1 <= last;
+                double * A0 = A + tri(i), * A1 = A + tri(two ? i + 1 : i);
+                double L0[kNB], L1[kNB];
+#pragma unroll
+                for (int c = 0; c < kNB; c++) {
+                    L0[c] = c < bs ? A0[j0 + c] : 0.0;
+                    L1[c] = c < bs ? A1[j0 + c] : 0.0;
+                }
+                const int jmax0 = min(i, n - 1), jmax1 = two ? min(i + 1, n - 1) : -1;
+#pragma unroll
+                for (int m = 0; m < kMaxSlots; m++) {
+                    if (t0 + 32 * m <= max(jmax0, jmax1)) {
+                        const int j = t0 + lane + 32 * m;
+                        const bool v0 = j <= jmax0, v1 = j <= jmax1;
+                        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < kNB; c += 2) {
+                            p0 = fma(L0[c], Lj[m][c], p0);
+                            p1 = fma(L0[c + 1], Lj[m][c + 1], p1);
+                            q0 = fma(L1[c], Lj[m][c], q0);
+                            q1 = fma(L1[c + 1], Lj[m][c + 1], q1);
+                        }
+                        if (v0) A0[j] -= p0 + p1;
+                        if (v1) A1[j] -= q0 + q1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    return ok;
+}
+
+// L^T x = y, y = the bordered row: right-looking, row k of L is contiguous. x[m] = element lane + 32 m.
+__device__ __forceinline__ void warp_backsolve_packed(const double * A, int n, const double * rdiag, double * x, int lane) {
+#pragma unroll
+    for (int m = 0; m < kMaxSlots; m++) {
+        const int i = lane + 32 * m;
+        x[m] = i < n ? A[tri(n) + i] : 0.0;
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        const int km = k >> 5, kl = k & 31;
+        double xs = x[0];
+#pragma unroll
+        for (int m = 1; m < kMaxSlots; m++) xs = km == m ? x[m] : xs;
+        const double xk = __shfl_sync(kFull, xs, kl) * rdiag[k];
+        const double * Lk = A + tri(k);
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = lane + 32 * m;
+            if (m == km && lane == kl) x[m] = xk;
+            else if (i < k) x[m] = fma(-Lk[i], xk, x[m]);
+        }
+    }
+}
+
+// in place: L -> W = L^-1 (lower), row panels of 8 from the top:
+//   W[I][I] = L[I][I]^-1,   W[I][0:i0] = -W[I][I] (L[I][0:i0] W[0:i0][0:i0])
+// lanes run along the columns j of the result; Ds: 64 doubles of scratch
+__device__ __forceinline__ void warp_trtri_packed(double * A, int n, const double * rdiag, double * Ds, int lane) {
+    for (int i0 = 0; i0 < n; i0 += kNB) {
+        const int bs = min(kNB, n - i0);
+        // inverse of the 8 x 8 diagonal block: lane & 7 = column, forward substitution in registers
+        const int c = lane & 7;
+        double Dc[kNB];
+#pragma unroll
+        for (int r = 0; r < kNB; r++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < r; k++) {
+                const double l = r < bs ? A[tri(i0 + r) + i0 + k] : 0.0;
+                if (k >= c) s = fma(l, Dc[k], s);
+            }
+            const double rd = r < bs ? rdiag[i0 + r] : 0.0;
+            Dc[r] = (r < c || c >= bs) ? 0.0 : r == c ? rd : -s * rd;
+        }
+        double acc[kMaxSlots][kNB];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++)
+#pragma unroll
+            for (int r = 0; r < kNB; r++) acc[m][r] = 0.0;
+        for (int k = 0; k < i0; k++) {
+            double Lr[kNB];
+#pragma unroll
+            for (int r = 0; r < kNB; r++) Lr[r] = r < bs ? A[tri(i0 + r) + k] : 0.0;
+            const double * Wk = A + tri(k);
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                if (32 * m <= k) {
+                    const int j = lane + 32 * m;
+                    const double w = j <= k ? Wk[j] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < kNB; r++) acc[m][r] = fma(Lr[r], w, acc[m][r]);
+                }
+            }
+        }
+        __syncwarp();                                  // every lane is done reading rows I (overwritten below)
+        if (lane < kNB) {
+#pragma unroll
+            for (int r = 0; r < kNB; r++) Ds[r * kNB + lane] = Dc[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int j = lane + 32 * m;
+            if (32 * m < i0 && j < i0) {
+#pragma unroll
+                for (int r = 0; r < kNB; r++) {
+                    if (r < bs) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int r2 = 0; r2 <= r; r2++) s = fma(Ds[r * kNB + r2], acc[m][r2], s);
+                        A[tri(i0 + r) + j] = -s;
+                    }
+                }
+            }
+        }
+        if (lane < bs) {
+#pragma unroll
+            for (int r = 0; r < kNB; r++)
+                if (r < bs && r >= lane) A[tri(i0 + r) + i0 + lane] = Dc[r];
+        }
+        __syncwarp();
+    }
+}
+
+// in place: W (lower) -> lower triangle of W^T W, row panels of 8 ascending (rows below a panel are still W)
+__device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
+    for (int i0 = 0; i0 < n; i0 += kNB) {
+        const int bs = min(kNB, n - i0);
+        const int ncols = i0 + bs;
+        double acc[kMaxSlots][kNB];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++)
+#pragma unroll
+            for (int r = 0; r < kNB; r++) acc[m][r] = 0.0;
+        for (int k = i0; k < n; k++) {
+            const double * Wk = A + tri(k);
+            double Wr[kNB];
+#pragma unroll
+            for (int r = 0; r < kNB; r++) Wr[r] = (r < bs && i0 + r <= k) ? Wk[i0 + r] : 0.0;
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                if (32 * m < ncols) {
+                    const int j = lane + 32 * m;
+                    const double w = (j <= k && j < ncols) ? Wk[j] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < kNB; r++) acc[m][r] = fma(Wr[r], w, acc[m][r]);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int j = lane + 32 * m;
+#pragma unroll
+            for (int r = 0; r < kNB; r++)
+                if (r < bs && j <= i0 + r) A[tri(i0 + r) + j] = acc[m][r];
+        }
+        __syncwarp();
+    }
+}
+
+// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[64]
+__host__ __device__ inline int factor_smem_doubles(int n, int nnz_pad) {
+    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 64;
+}
+
+// OPF 0: g_q = (J J^T)^-1 (J g_r)                     -> gq_out[B][n]
+// OPF 1: the same (g_r may be null) plus the packed inverse -> ainv_out[B][n (n + 1) / 2]
+template <int OPF, bool HAS5>
+__global__ void __launch_bounds__(32)
+factor_kernel(const SparseProgram sp, const double * __restrict__ r, const double * __restrict__ gr, const int64_t B,
+              double * __restrict__ gq_out, double * __restrict__ ainv_out, int * __restrict__ status) {
+    extern __shared__ __align__(16) double sm_dyn[];
+    const int lane = threadIdx.x;
+    const int n = sp.intdim, cd = sp.cartdim;
+    const int ntri = (n * (n + 1)) >> 1;
+    double * Jv = sm_dyn;
+    double * A = Jv + sp.nnz_pad;
+    double * rdiag = A + ntri + n + 2;
+    double * Ds = rdiag + ((n + 1) & ~1);
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const double * rg = r + b * cd;
+        for (int p = sp.nnz + lane; p < sp.nnz_pad; p += kLanes) Jv[p] = 0.0;      // the zero entries the padded pair lists point to
+        eval_J_rows<HAS5>(sp, rg, Jv, lane, kLanes);
+        for (int p = lane; p < ntri + n + 2; p += kLanes) A[p] = 0.0;
+        __syncwarp();
+        // A = J J^T over the structurally nonzero pairs of rows: 3 products per common atom
+        for (int p = lane; p < sp.npairs_pad; p += kLanes) {
+            double s = 0.0;
+            for (int e = 0; e < sp.maxc; e++) {
+                const uint32_t ent = __ldg(sp.pair_ent + e * sp.npairs_pad + p);
+                const double * ji = Jv + (ent >> 16), * jj = Jv + (ent & 0xffffu);
+                s = fma(ji[0], jj[0], s);
+                s = fma(ji[1], jj[1], s);
+                s = fma(ji[2], jj[2], s);
+            }
+            A[__ldg(sp.pair_dest + p)] = s;                                         // padding pairs write the spare element
+        }
+        // bordered row: b = J g_r
+        if (gr != nullptr) {
+            const double * g = gr + b * cd;
+            for (int i = lane; i < n; i += kLanes) {
+                double s = 0.0;
+                for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) s = fma(Jv[p], __ldg(g + sp.nz_col[p]), s);
+                A[ntri + i] = s;
+            }
+        }
+        __syncwarp();
+        const bool ok = warp_potrf_packed(A, n, true, rdiag, lane);
+        if (!ok) {
+            // the reference's at::cholesky throws (IntCoordSet.cpp:182): flag the table, NaN for this geometry
+            if (lane == 0) atomicExch(status, 1);
+            if (gq_out) for (int i = lane; i < n; i += kLanes) gq_out[b * n + i] = nan64();
+            if (OPF == 1) for (int p = lane; p < ntri; p += kLanes) ainv_out[b * ntri + p] = nan64();
+            __syncwarp();
+            continue;
+        }
+        if (gq_out) {
+            double x[kMaxSlots];
+            warp_backsolve_packed(A, n, rdiag, x, lane);
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int i = lane + 32 * m;
+                if (i < n) gq_out[b * n + i] = x[m];
+            }
+        }
+        if (OPF == 1) {
+            warp_trtri_packed(A, n, rdiag, Ds, lane);
+            warp_lauum_packed(A, n, lane);
+            double * dst = ainv_out + b * ntri;
+            for (int p = lane; p < ntri; p += kLanes) dst[p] = A[p];
+        }
+        __syncwarp();
+    }
+}
+
+// ======================================================================================================
+// hess_kernel: one block = one geometry at a time
+// ======================================================================================================
+// shared-memory plan (doubles)
+struct HessPlan { int small, jv, big, mid, third, tab, total; };
+__host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
+__host__ __device__ inline HessPlan hess_plan(int op, int n, int cd, int ldh, int nnz_pad, int nslots, int tab_doubles) {
+    HessPlan p;
+    const int ldo = n | 1, ldc = cd | 1;              // odd leading dimensions: lanes that run down a column hit different banks
+    p.small = 0;                                      // 2 x (coordinates | vector)
+    p.jv = p.small + 2 * (even_up(cd) + even_up(cd > n ? cd : n));
+    p.big = p.jv + 2 * nnz_pad;
+    int big = 0, mid = 0, third = 0;
+    switch (op) {
+    case 2:  big = n * n; mid = max(cd * ldo, nslots); third = cd * cd; break;            // H_q | U, slots | X
+    case 3:  big = max(cd * cd, n * ldh); mid = max(max(n * ldc, nslots), n * ldh); third = n * ldh; break;   // H_c, S, H_q | slots, V, P | inverse
+    default: big = n * ldh; mid = n * cd; third = 0; break;                                // inverse | M
+    }
+    p.mid = p.big + even_up(big);
+    p.third = p.mid + even_up(mid);
+    p.tab = p.third + even_up(third);
+    p.total = p.tab + even_up(tab_doubles);
+    return p;
+}
+
+// global [count] -> shared, 16 bytes per cp.async when both sides allow, else 8; all threads, one commit group
+__device__ __forceinline__ void block_copy_async(const double * __restrict__ g, double * s, int count) {
+    const bool vec = (count & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+    if (vec) {
+        for (int i = 2 * threadIdx.x; i < count; i += 2 * blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s + i)), "l"(g + i) : "memory");
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s + i)), "l"(g + i) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// shared [rows][ld] -> global [rows][cols] (streaming stores, 16 bytes when everything is aligned)
+__device__ __forceinline__ void block_store_rows(const double * s, double * __restrict__ g, int rows, int cols, int ld) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    if (ld == cols && ((rows * cols) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
+        const int total = rows * cols;
+        for (int i = 2 * threadIdx.x; i < total; i += 2 * blockDim.x)
+            __stcs(reinterpret_cast<double2 *>(g + i), *reinterpret_cast<const double2 *>(s + i));
+        return;
+    }
+    for (int r = warp; r < rows; r += nwarps) {
+        const double * src = s + r * ld;
+        double * dst = g + (int64_t)r * cols;
+        for (int c = lane; c < cols; c += kLanes) __stcs(dst + c, src[c]);
+    }
+}
+
+// OUT[a][l] = sum over the nonzeros (k, v) of column a of J of  v * IN[k][l]      (OUT: cartdim x width)
+// one warp per column a, lanes along l (contiguous in IN): OUT = J^T IN
+__device__ __forceinline__ void spmm_JT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
+                                        double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int a = warp; a < sp.cartdim; a += nwarps) {
+        double acc[kMaxSlots];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
+        for (int e = sp.col_ptr[a]; e < sp.col_ptr[a + 1]; e++) {
+            const uint32_t ent = sp.col_ent[e];
+            const double v = Jv[ent & 0xffffu];
+            const double * in = IN + (ent >> 16) * ldin;
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int l = lane + 32 * m;
+                if (32 * m < width && l < width) acc[m] = fma(v, in[l], acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int l = lane + 32 * m;
+            if (l < width) OUT[a * ldout + l] = acc[m];
+        }
+    }
+}
+// OUT[a][c] = sum over the nonzeros (l, v) of column c of J of  IN[a][l] * v      (OUT: height x cartdim)
+// one warp per column c, lanes along a (IN's leading dimension is odd): OUT = IN J
+__device__ __forceinline__ void spmm_J(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
+                                       double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < sp.cartdim; c += nwarps) {
+        double acc[kMaxSlots];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
+        for (int e = sp.col_ptr[c]; e < sp.col_ptr[c + 1]; e++) {
+            const uint32_t ent = sp.col_ent[e];
+            const double v = Jv[ent & 0xffffu];
+            const double * in = IN + (ent >> 16);
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int a = lane + 32 * m;
+                if (32 * m < height && a < height) acc[m] = fma(v, in[a * ldin], acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int a = lane + 32 * m;
+            if (a < height) OUT[a * ldout + c] = acc[m];
+        }
+    }
+}
+// OUT[i][c] = sum over the nonzeros (a, v) of row i of J of  v * IN[a][c]          (OUT: intdim x width): OUT = J IN
+__device__ __forceinline__ void spmm_Jrow(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
+                                          double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < sp.intdim; i += nwarps) {
+        double acc[kMaxSlots];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
+        for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) {
+            const double v = Jv[p];
+            const double * in = IN + sp.nz_col[p] * ldin;
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int c = lane + 32 * m;
+                if (32 * m < width && c < width) acc[m] = fma(v, in[c], acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int c = lane + 32 * m;
+            if (c < width) OUT[i * ldout + c] = acc[m];
+        }
+    }
+}
+// OUT[i][j] = sum over the nonzeros (c, v) of row j of J of  IN[i][c] * v          (OUT: height x intdim): OUT = IN J^T
+__device__ __forceinline__ void spmm_JrowT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
+                                           double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < sp.intdim; j += nwarps) {
+        double acc[kMaxSlots];
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
+        for (int p = sp.nz_ptr[j]; p < sp.nz_ptr[j + 1]; p++) {
+            const double v = Jv[p];
+            const double * in = IN + sp.nz_col[p];
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) {
+                const int i = lane + 32 * m;
+                if (32 * m < height && i < height) acc[m] = fma(v, in[i * ldin], acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = lane + 32 * m;
+            if (i < height) OUT[i * ldout + j] = acc[m];
+        }
+    }
+}
+
+// (term, direction) second-derivative tasks of geometry `rg` into the slots, weights w[row] * sign * coef; the
+// threads beyond the task list evaluate the J rows of the NEXT geometry meanwhile (rg_next == nullptr: none)
+template <bool HAS5>
+__device__ __forceinline__ void run_tasks(const SparseProgram & sp, const double * rg, const double * weight, double sign, double * slots,
+                                          const double * rg_next, double * Jv_next) {
+    const int njrow = rg_next ? sp.njrow : 0;
+    for (int k = threadIdx.x; k < sp.nktasks + njrow; k += blockDim.x) {
+        if (k < sp.nktasks) {
+            const uint32_t task = sp.ktasks[k];
+            const SpTerm & term = sp.terms[task >> 8];
+            const int dir = (int)(task & 0xffu);
+            SlotSink sink;
+            sink.S = slots + term.kslot;
+            sink.w = sign * weight[term.pd.out] * term.coef;
+            eval_primitive<MODE_KDIR, HAS5>(term.pd, GeomLoader{rg}, sink, dir, dir + 1);
+        } else {
+            const int row = sp.jrow_order[k - sp.nktasks];
+            if (row >= 0) {
+                for (int p = sp.nz_ptr[row]; p < sp.nz_ptr[row + 1]; p++) Jv_next[p] = 0.0;
+                for (int t = sp.row_ptr[row]; t < sp.row_ptr[row + 1]; t++) {
+                    const SpTerm & term = sp.terms[t];
+                    JvSink sink;
+                    sink.Jv = Jv_next; sink.pos = term.pos; sink.coef = term.coef;
+                    eval_primitive<MODE_QJ, HAS5>(term.pd, GeomLoader{rg_next}, sink);
+                }
+            }
+        }
+    }
+}
+
+// H[3 A + k][3 B + l] += sum of the block's slots, in table order (no atomics: bit-reproducible)
+__device__ __forceinline__ void gather_slots(const SparseProgram & sp, const double * slots, double * H, int ld) {
+    for (int e = threadIdx.x; e < 9 * sp.ngblk; e += blockDim.x) {
+        const int blk = e / 9, el = e - 9 * blk, k = el / 3, l = el - 3 * k;
+        const uint32_t ab = sp.gk_blk[blk];
+        double s = 0.0;
+        for (uint32_t p = sp.gk_ptr[blk]; p < sp.gk_ptr[blk + 1]; p++) {
+            const uint32_t src = sp.gk_src[p];
+            s += slots[(src >> 1) + ((src & 1u) ? 3 * l + k : 3 * k + l)];
+        }
+        H[(3 * (ab >> 16) + k) * ld + 3 * (ab & 0xffffu) + l] += s;
+    }
+}
+
+// OP 0: gradient_cart2int_matrix   ainv (workspace)                                  out = M[n][cd]
+// OP 2: Hessian_int2cart           in1 = g_q[n],                in2 = H_q[n][n]      out = H_r[cd][cd]
+// OP 3: Hessian_cart2int           in1 = g_q[n] (workspace), ainv, in2 = H_r[cd][cd] out = H_q[n][n]
+template <int OP, bool HAS5>
+__global__ void __launch_bounds__(kHessThreads, 1)
+hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const double * __restrict__ in1,
+            const double * __restrict__ in2, const double * __restrict__ ainv, const int64_t B, double * __restrict__ out) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = sp_global.intdim, cd = sp_global.cartdim, ldh = sp_global.ldh;
+    const int ntri = (n * (n + 1)) >> 1;
+    const int tab_doubles = sp_global.tab_in_smem ? (sp_global.blob_bytes + 7) / 8 : 0;
+    const HessPlan pl = hess_plan(OP, n, cd, ldh, sp_global.nnz_pad, sp_global.nslots, tab_doubles);
+    SparseProgram sp = sp_global;
+    if (sp_global.tab_in_smem) {
+        double * tab = sm + pl.tab;
+        const double * src = reinterpret_cast<const double *>(sp_global.terms);
+        for (int i = threadIdx.x; i < tab_doubles; i += blockDim.x) tab[i] = src[i];
+        const char * base = reinterpret_cast<const char *>(sp_global.terms), * tb = reinterpret_cast<const char *>(tab);
+#define TC_REBASE(field, type) sp.field = reinterpret_cast<const type *>(tb + (reinterpret_cast<const char *>(sp_global.field) - base))
+        TC_REBASE(terms, SpTerm); TC_REBASE(row_ptr, int32_t); TC_REBASE(jrow_order, int32_t); TC_REBASE(ktasks, uint32_t);
+        TC_REBASE(nz_ptr, uint16_t); TC_REBASE(nz_col, uint16_t); TC_REBASE(col_ptr, uint16_t); TC_REBASE(col_ent, uint32_t);
+        TC_REBASE(gk_blk, uint32_t); TC_REBASE(gk_ptr, uint32_t); TC_REBASE(gk_src, uint32_t);
+#undef TC_REBASE
+    }
+    const int ldo = n | 1, ldc = cd | 1;
+    const int rg_buf = even_up(cd), v_buf = even_up(cd > n ? cd : n);
+    const int v_len = OP == 0 ? 0 : n;                // g_q in both Hessian transforms
+    double * BIG = sm + pl.big, * MID = sm + pl.mid, * THIRD = sm + pl.third;
+    auto rg_of = [&](int buf) { return sm + pl.small + buf * (rg_buf + v_buf); };
+    auto v_of = [&](int buf) { return sm + pl.small + buf * (rg_buf + v_buf) + rg_buf; };
+    auto jv_of = [&](int buf) { return sm + pl.jv + buf * sp.nnz_pad; };
+    auto fetch_small = [&](int64_t bb, int buf) {
+        double * rgd = rg_of(buf), * vd = v_of(buf);
+        const double * rs = r + bb * cd, * vs = in1 + bb * v_len;
+        for (int i = threadIdx.x; i < cd; i += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(rgd + i)), "l"(rs + i) : "memory");
+        for (int i = threadIdx.x; i < v_len; i += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(vd + i)), "l"(vs + i) : "memory");
+    };
+    const int big_count = OP == 2 ? n * n : cd * cd;                       // H_q / H_r of one geometry
+    auto fetch_big = [&](int64_t bb) { if (OP != 0) block_copy_async(in2 + bb * (int64_t)big_count, BIG, big_count); };
+
+    // prologue: the first geometry's small inputs, its J rows, its operand matrix
+    int cur = 0;
+    const int64_t b0 = blockIdx.x;
+    if (b0 >= B) return;
+    fetch_small(b0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();                                                       // (also publishes the table copy)
+    for (int p = sp.nnz + threadIdx.x; p < sp.nnz_pad; p += blockDim.x) { jv_of(0)[p] = 0.0; jv_of(1)[p] = 0.0; }
+    eval_J_rows<HAS5>(sp, rg_of(0), jv_of(0), threadIdx.x, blockDim.x);
+    fetch_big(b0);
+    cp_async_commit();
+
+    for (int64_t b = b0; b < B; b += gridDim.x) {
+        const int64_t bn = b + gridDim.x;
+        const bool has_next = bn < B;
+        const double * rg = rg_of(cur), * gvec = v_of(cur), * Jv = jv_of(cur);
+        // group order per thread from here on: [operand matrix of b] is pending; now [small inputs of bn]
+        if (has_next) fetch_small(bn, cur ^ 1);
+        cp_async_commit();
+
+        if (OP == 2) {
+            double * Hq = BIG, * U = MID, * X = THIRD;
+            cp_async_wait<1>();                                            // H_q of b has landed (the small inputs may still fly)
+            __syncthreads();                                               // + J rows of b (prologue or previous task phase)
+            spmm_JT(sp, Jv, Hq, n, n, U, ldo);                             // U = J^T H_q        (cd x n)
+            __syncthreads();
+            if (has_next) fetch_big(bn);                                   // H_q is dead: the next one travels during the rest
+            cp_async_commit();
+            spmm_J(sp, Jv, U, ldo, cd, X, cd);                             // X = U J            (cd x cd)
+            cp_async_wait<1>();                                            // small inputs of bn
+            __syncthreads();
+            run_tasks<HAS5>(sp, rg, gvec, 1.0, U /* slots */, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
+            __syncthreads();
+            gather_slots(sp, U, X, cd);                                    // X += sum_k g_q[k] K[k]
+            __syncthreads();
+            block_store_rows(X, out + b * (int64_t)cd * cd, cd, cd, cd);
+            cur ^= 1;
+            continue;                                                      // (the next iteration's first barrier orders the reuse of X)
+        }
+        if (OP == 0) {
+            double * Ai = BIG, * M = MID;
+            // expand the packed inverse: Ai[i][j] = Ai[j][i] = packed[tri(i) + j]
+            const double * pk = ainv + b * (int64_t)ntri;
+            for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
+                for (int j = threadIdx.x & 31; j <= i; j += kLanes) {
+                    const double v = pk[tri(i) + j];
+                    Ai[i * ldh + j] = v;
+                    Ai[j * ldh + i] = v;
+                }
+            __syncthreads();
+            spmm_JT(sp, Jv, Ai, ldh, n, M, n);          // (J^T inv)[c][i] = M[i][c]: stored transposed below
+            __syncthreads();
+            // M^T lives as [cd][n]; write out[i][c] with lanes along c
+            double * dst = out + b * (int64_t)n * cd;
+            for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
+                for (int c = threadIdx.x & 31; c < cd; c += kLanes) __stcs(dst + (int64_t)i * cd + c, M[c * n + i]);
+            cp_async_wait<0>();
+            __syncthreads();
+            if (has_next) eval_J_rows<HAS5>(sp, rg_of(cur ^ 1), jv_of(cur ^ 1), threadIdx.x, blockDim.x);
+            cur ^= 1;
+            __syncthreads();
+            continue;
+        }
+        // OP 3: H_q = inv (J (H_r - sum_k g_q[k] K[k]) J^T) inv
+        {
+            double * Hc = BIG, * SL = MID, * Ai = THIRD;
+            const double * pk = ainv + b * (int64_t)ntri;
+            for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
+                for (int j = threadIdx.x & 31; j <= i; j += kLanes) {
+                    const double v = pk[tri(i) + j];
+                    Ai[i * ldh + j] = v;
+                    Ai[j * ldh + i] = v;
+                }
+            cp_async_wait<0>();                                            // H_r of b and the small inputs of bn
+            __syncthreads();
+            run_tasks<HAS5>(sp, rg, gvec, -1.0, SL, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
+            __syncthreads();
+            gather_slots(sp, SL, Hc, cd);                                  // H_c = H_r - sum_k g_q[k] K[k]
+            __syncthreads();
+            double * V = MID;
+            spmm_Jrow(sp, Jv, Hc, cd, cd, V, ldc);                         // V = J H_c           (n x cd)
+            __syncthreads();
+            double * S = BIG;
+            spmm_JrowT(sp, Jv, V, ldc, n, S, ldh);                         // S = V J^T           (n x n)
+            __syncthreads();
+            double * P = MID;
+            block_dgemm<false, false, false>(n, n, n, Ai, ldh, S, ldh, P, ldh);      // P = inv S
+            __syncthreads();
+            block_dgemm<false, false, false>(n, n, n, P, ldh, Ai, ldh, S, ldh);      // H_q = P inv   (into S)
+            __syncthreads();
+            block_store_rows(S, out + b * (int64_t)n * n, n, n, ldh);
+            __syncthreads();                                               // the stores have read S: the next H_r may land there
+            if (has_next) fetch_big(bn);
+            cp_async_commit();
+            cur ^= 1;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ======================================================================================================
+// host side: the compressed tables
+// ======================================================================================================
+struct SparseTable {
+    SparseProgram prog;
+    void * blob = nullptr;
+    int * status = nullptr;
+    double density = 1.0;             // structural nonzeros of J / (intdim * cartdim)
+};
+std::map<const tchem_ic_table *, SparseTable> & sparse_tables() {
+    static std::map<const tchem_ic_table *, SparseTable> m;
+    return m;
+}
+std::mutex & sparse_mutex() { static std::mutex m; return m; }
+
+int pick_ld_dmma(int width) {      // smallest ld >= width with ld = 4 or 12 (mod 16)
+    int ld = width;
+    while ((ld & 15) != 4 && (ld & 15) != 12) ld++;
+    return ld;
+}
+
+int type_cost(int type, int natoms) {          // relative cost of one evaluation, for the task order
+    if (natoms == 5) return 40;
+    if (natoms == 4) return type == TCHEM_OUTOFPLANE || type == TCHEM_SINOOP ? 11 : 12;
+    if (natoms == 3) return 6;
+    return natoms == 2 ? 2 : 0;
+}
+
+int get_sparse(const tchem_ic_table * t, SparseTable & out) {
+    std::lock_guard<std::mutex> lock(sparse_mutex());
+    auto it = sparse_tables().find(t);
+    if (it != sparse_tables().end()) { out = it->second; return TCHEM_OK; }
+    const int n = t->intdim, cd = t->cartdim;
+    std::vector<std::vector<int>> rows(n);
+    for (size_t k = 0; k < t->terms.size(); k++) rows[t->terms[k].ic].push_back((int)k);
+    // compressed rows: the atoms a row touches, ascending; 3 consecutive Jv positions per atom
+    std::vector<uint16_t> nz_ptr(1, 0), nz_col;
+    std::vector<std::vector<int>> row_atoms(n);
+    std::vector<std::map<int, int>> atom_pos(n);              // atom -> first Jv position in that row
+    for (int i = 0; i < n; i++) {
+        std::set<int> atoms;
+        for (int k : rows[i]) for (int a = 0; a < t->terms[k].natoms; a++) atoms.insert(t->terms[k].atoms[a]);
+        for (int a : atoms) {
+            atom_pos[i][a] = (int)nz_col.size();
+            row_atoms[i].push_back(a);
+            for (int c = 0; c < 3; c++) nz_col.push_back((uint16_t)(3 * a + c));
+        }
+        nz_ptr.push_back((uint16_t)nz_col.size());
+    }
+    const int nnz = (int)nz_col.size();
+    const int zero_pos = nnz;                                  // 3 zeros after the values: target of the padded pair lists
+    const int nnz_pad = (nnz + 3 + 1) & ~1;
+    std::vector<SpTerm> terms;
+    std::vector<int32_t> row_ptr(1, 0);
+    std::vector<uint32_t> ktasks;
+    int nslots = 0;
+    for (int i = 0; i < n; i++) {
+        for (int k : rows[i]) {
+            const auto & d = t->terms[k];
+            SpTerm st;
+            std::memset(&st, 0, sizeof(st));
+            st.pd.type = d.type; st.pd.natoms = d.natoms;
+            for (int a = 0; a < 5; a++) st.pd.atoms[a] = a < d.natoms ? d.atoms[a] : 0;
+            st.pd.out = i;
+            st.pd.min = d.min;
+            st.coef = d.coeff;
+            for (int a = 0; a < 5; a++) st.pos[a] = (int16_t)(a < d.natoms ? atom_pos[i][d.atoms[a]] : zero_pos);
+            st.kslot = nslots;
+            nslots += 9 * (d.natoms * (d.natoms + 1) / 2);
+            for (int dir = 0; dir < 3 * d.natoms; dir++) ktasks.push_back(((uint32_t)terms.size() << 8) | (uint32_t)dir);
+            terms.push_back(st);
+        }
+        row_ptr.push_back((int32_t)terms.size());
+    }
+    // heaviest tasks first; within a type direction-major, so a warp runs one formula in lock step
+    std::stable_sort(ktasks.begin(), ktasks.end(), [&](uint32_t a, uint32_t b) {
+        const PrimDesc & ta = terms[a >> 8].pd, & tb = terms[b >> 8].pd;
+        const int ca = type_cost(ta.type, ta.natoms), cb = type_cost(tb.type, tb.natoms);
+        if (ca != cb) return ca > cb;
+        if (ta.type != tb.type) return ta.type < tb.type;
+        return (a & 0xffu) < (b & 0xffu);
+    });
+    // J rows in evaluation order: grouped by the type of the first term (heaviest first), groups padded to whole warps
+    std::vector<int32_t> jrow_order;
+    {
+        std::vector<int> order(n);
+        for (int i = 0; i < n; i++) order[i] = i;
+        auto key = [&](int i) {
+            if (rows[i].empty()) return std::make_pair(0, 0);
+            const auto & d = t->terms[rows[i][0]];
+            return std::make_pair(type_cost(d.type, d.natoms) * (int)rows[i].size(), (int)d.type);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) > key(b); });
+        for (size_t k = 0; k < order.size(); k++) {
+            if (k > 0 && key(order[k]) != key(order[k - 1]))
+                while (jrow_order.size() % 32) jrow_order.push_back(-1);
+            jrow_order.push_back(order[k]);
+        }
+        // (padding only pays when the groups are large; many small groups would only lengthen the list)
+        if ((int)jrow_order.size() > 2 * n + 64) { jrow_order.assign(order.begin(), order.end()); }
+    }
+    // CSC
+    std::vector<uint16_t> col_ptr(cd + 1, 0);
+    std::vector<uint32_t> col_ent(nnz);
+    {
+        std::vector<std::vector<uint32_t>> cols(cd);
+        for (int i = 0; i < n; i++)
+            for (int p = nz_ptr[i]; p < nz_ptr[i + 1]; p++) cols[nz_col[p]].push_back(((uint32_t)i << 16) | (uint32_t)p);
+        int k = 0;
+        for (int c = 0; c < cd; c++) {
+            col_ptr[c] = (uint16_t)k;
+            for (uint32_t e : cols[c]) col_ent[k++] = e;
+        }
+        col_ptr[cd] = (uint16_t)k;
+    }
+    // J J^T: pairs of rows that share atoms
+    std::vector<uint32_t> pair_dest;
+    std::vector<std::vector<uint32_t>> pair_lists;
+    int maxc = 1;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            std::vector<uint32_t> common;
+            for (int a : row_atoms[i]) {
+                auto f = atom_pos[j].find(a);
+                if (f != atom_pos[j].end()) common.push_back(((uint32_t)atom_pos[i][a] << 16) | (uint32_t)f->second);
+            }
+            if (common.empty()) continue;
+            pair_dest.push_back((uint32_t)(i * (i + 1) / 2 + j));
+            maxc = std::max(maxc, (int)common.size());
+            pair_lists.push_back(common);
+        }
+    const int npairs = (int)pair_dest.size();
+    const int npairs_pad = (npairs + 31) & ~31;
+    const uint32_t spare = (uint32_t)(n * (n + 1) / 2 + n);             // the spare element behind the bordered row
+    pair_dest.resize(npairs_pad, spare);
+    std::vector<uint32_t> pair_ent((size_t)maxc * npairs_pad, ((uint32_t)zero_pos << 16) | (uint32_t)zero_pos);
+    for (int p = 0; p < npairs; p++)
+        for (size_t e = 0; e < pair_lists[p].size(); e++) pair_ent[e * npairs_pad + p] = pair_lists[p][e];
+    // g.K gather: ordered atom pairs (A, B) <- slots of every term that contains both
+    std::map<std::pair<int, int>, std::vector<uint32_t>> gk;
+    for (const SpTerm & st : terms) {
+        const int N = st.pd.natoms;
+        for (int i = 0; i < N; i++)
+            for (int j = i; j < N; j++) {
+                const uint32_t base = (uint32_t)(st.kslot + 9 * (i * N - (i * (i - 1)) / 2 + (j - i)));
+                const int A = st.pd.atoms[i], Bt = st.pd.atoms[j];
+                gk[{A, Bt}].push_back(base << 1);
+                if (i != j) gk[{Bt, A}].push_back((base << 1) | 1u);
+            }
+    }
+    std::vector<uint32_t> gk_blk, gk_ptr(1, 0), gk_src;
+    for (const auto & kv : gk) {
+        gk_blk.push_back(((uint32_t)kv.first.first << 16) | (uint32_t)kv.first.second);
+        for (uint32_t s : kv.second) gk_src.push_back(s);
+        gk_ptr.push_back((uint32_t)gk_src.size());
+    }
+    // blob
+    auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    size_t off = 0;
+    auto place = [&](size_t bytes) { const size_t o = off; off += a16(bytes); return o; };
+    const size_t o_terms = place(terms.size() * sizeof(SpTerm)), o_rowptr = place(row_ptr.size() * 4), o_jrow = place(jrow_order.size() * 4),
+                 o_ktasks = place(ktasks.size() * 4), o_nzptr = place(nz_ptr.size() * 2), o_nzcol = place(nz_col.size() * 2 + 2),
+                 o_colptr = place(col_ptr.size() * 2), o_colent = place(col_ent.size() * 4 + 4), o_gkblk = place(gk_blk.size() * 4 + 4),
+                 o_gkptr = place(gk_ptr.size() * 4), o_gksrc = place(gk_src.size() * 4 + 4);
+    const size_t smem_part = off;                              // everything the block kernel reads
+    const size_t o_pdest = place(pair_dest.size() * 4), o_pent = place(pair_ent.size() * 4);
+    const size_t total = off + 16;
+    std::vector<unsigned char> blob(total, 0);
+    std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SpTerm));
+    std::memcpy(blob.data() + o_rowptr, row_ptr.data(), row_ptr.size() * 4);
+    std::memcpy(blob.data() + o_jrow, jrow_order.data(), jrow_order.size() * 4);
+    std::memcpy(blob.data() + o_ktasks, ktasks.data(), ktasks.size() * 4);
+    std::memcpy(blob.data() + o_nzptr, nz_ptr.data(), nz_ptr.size() * 2);
+    std::memcpy(blob.data() + o_nzcol, nz_col.data(), nz_col.size() * 2);
+    std::memcpy(blob.data() + o_colptr, col_ptr.data(), col_ptr.size() * 2);
+    std::memcpy(blob.data() + o_colent, col_ent.data(), col_ent.size() * 4);
+    std::memcpy(blob.data() + o_gkblk, gk_blk.data(), gk_blk.size() * 4);
+    std::memcpy(blob.data() + o_gkptr, gk_ptr.data(), gk_ptr.size() * 4);
+    std::memcpy(blob.data() + o_gksrc, gk_src.data(), gk_src.size() * 4);
+    std::memcpy(blob.data() + o_pdest, pair_dest.data(), pair_dest.size() * 4);
+    std::memcpy(blob.data() + o_pent, pair_ent.data(), pair_ent.size() * 4);
+    void * dev = nullptr;
+    TC_CUDA(cudaMalloc(&dev, total));
+    cudaError_t e = cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); return set_error(TCHEM_ECUDA, cudaGetErrorString(e)); }
+    SparseTable st;
+    st.blob = dev;
+    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.status), sizeof(int)));
+    TC_CUDA(cudaMemset(st.status, 0, sizeof(int)));
+    unsigned char * d = static_cast<unsigned char *>(dev);
+    SparseProgram & p = st.prog;
+    p.terms = reinterpret_cast<const SpTerm *>(d + o_terms);
+    p.row_ptr = reinterpret_cast<const int32_t *>(d + o_rowptr);
+    p.jrow_order = reinterpret_cast<const int32_t *>(d + o_jrow);
+    p.ktasks = reinterpret_cast<const uint32_t *>(d + o_ktasks);
+    p.nz_ptr = reinterpret_cast<const uint16_t *>(d + o_nzptr);
+    p.nz_col = reinterpret_cast<const uint16_t *>(d + o_nzcol);
+    p.col_ptr = reinterpret_cast<const uint16_t *>(d + o_colptr);
+    p.col_ent = reinterpret_cast<const uint32_t *>(d + o_colent);
+    p.pair_dest = reinterpret_cast<const uint32_t *>(d + o_pdest);
+    p.pair_ent = reinterpret_cast<const uint32_t *>(d + o_pent);
+    p.gk_blk = reinterpret_cast<const uint32_t *>(d + o_gkblk);
+    p.gk_ptr = reinterpret_cast<const uint32_t *>(d + o_gkptr);
+    p.gk_src = reinterpret_cast<const uint32_t *>(d + o_gksrc);
+    p.nterms = (int)terms.size(); p.njrow = (int)jrow_order.size(); p.nktasks = (int)ktasks.size();
+    p.nnz = nnz; p.nnz_pad = nnz_pad; p.npairs_pad = npairs_pad; p.maxc = maxc;
+    p.ngblk = (int)gk_blk.size(); p.ngsrc = (int)gk_src.size(); p.nslots = nslots;
+    p.intdim = n; p.cartdim = cd; p.ldh = pick_ld_dmma(n);
+    p.blob_bytes = (int32_t)smem_part;
+    p.tab_in_smem = 0;
+    st.density = (double)nnz / ((double)n * cd);
+    sparse_tables()[t] = st;
+    out = st;
+    return TCHEM_OK;
+}
+
+template <int OP> const void * hess_fn(bool has5) {
+    return has5 ? reinterpret_cast<const void *>(&hess_kernel<OP, true>) : reinterpret_cast<const void *>(&hess_kernel<OP, false>);
+}
+template <int OPF> const void * factor_fn(bool has5) {
+    return has5 ? reinterpret_cast<const void *>(&factor_kernel<OPF, true>) : reinterpret_cast<const void *>(&factor_kernel<OPF, false>);
+}
+
+} // namespace
+
+void release_sparse_program(const tchem_ic_table * t) {
+    std::lock_guard<std::mutex> lock(sparse_mutex());
+    auto it = sparse_tables().find(t);
+    if (it != sparse_tables().end()) { cudaFree(it->second.blob); cudaFree(it->second.status); sparse_tables().erase(it); }
+}
+
+int sparse_status(const tchem_ic_table * t) {
+    std::lock_guard<std::mutex> lock(sparse_mutex());
+    auto it = sparse_tables().find(t);
+    if (it == sparse_tables().end()) return 0;
+    int s = 0;
+    cudaMemcpy(&s, it->second.status, sizeof(int), cudaMemcpyDeviceToHost);
+    if (s) cudaMemset(it->second.status, 0, sizeof(int));
+    return s;
+}
+
+// op: 0 gradient_cart2int_matrix, 1 gradient_cart2int, 2 Hessian_int2cart, 3 Hessian_cart2int (as ic_dense.cu).
+// Returns -1 when this table / operation stays on the all-DMMA kernels of ic_dense.cu: J not sparse enough, more than
+// 127 internal or 128 Cartesian coordinates, or an operand plan beyond the shared memory of one SM.
+int launch_sparse(int op, const tchem_ic_table * t, const double * r, const double * in1, const double * in2, int64_t B,
+                  double * out, cudaStream_t stream) {
+    static const int mode = [] { const char * e = getenv("TCHEM_DENSE_DMMA"); return e ? atoi(e) : 0; }();   // 1: always the DMMA kernels
+    if (mode == 1) return -1;
+    const int n = t->intdim, cd = t->cartdim;
+    if (n + 1 > 32 * kMaxSlots || cd > 32 * kMaxSlots || n > cd && op != 2) return -1;
+    SparseTable st;
+    int rc = get_sparse(t, st);
+    if (rc != TCHEM_OK) return rc;
+    static const double max_density = [] { const char * e = getenv("TCHEM_SPARSE_MAX_DENSITY"); return e ? atof(e) : 0.5; }();
+    if (st.density > max_density || st.prog.nnz_pad > 65000 || st.prog.nslots > (1 << 30)) return -1;
+    const int ntri = n * (n + 1) / 2;
+    // ---- kernel 1 (cart -> int): factor / solve / inverse, one warp per geometry ---------------------------------
+    const size_t fsmem = (size_t)factor_smem_doubles(n, st.prog.nnz_pad) * sizeof(double);
+    if (op != 2 && fsmem + 1024 > (size_t)t->max_smem_optin) return -1;
+    // ---- kernel 2: one block per geometry ---------------------------------------------------------------------------
+    size_t hsmem = 0;
+    if (op != 1) {
+        HessPlan pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, (st.prog.blob_bytes + 7) / 8);
+        st.prog.tab_in_smem = 1;
+        if ((size_t)pl.total * sizeof(double) + 1024 > (size_t)t->max_smem_optin) {
+            pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, 0);
+            st.prog.tab_in_smem = 0;
+        }
+        hsmem = (size_t)pl.total * sizeof(double);
+        if (hsmem + 1024 > (size_t)t->max_smem_optin) return -1;
+    }
+    auto launch_factor = [&](int opf, const double * rr, const double * gr, int64_t nb, double * gq, double * ainv) -> int {
+        const void * fn = opf == 0 ? factor_fn<0>(t->has5) : factor_fn<1>(t->has5);
+        { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
+        int per_sm = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32, fsmem));
+        if (per_sm < 1) per_sm = 1;
+        const int64_t grid = std::min<int64_t>(nb, (int64_t)t->sm_count * per_sm);
+        void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&gr, (void *)&nb, (void *)&gq, (void *)&ainv, (void *)&st.status};
+        TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32), args, fsmem, stream));
+        count_launch(opf == 0 ? "factor_kernel<solve>" : "factor_kernel<inverse>");
+        return TCHEM_OK;
+    };
+    auto launch_hess = [&](int hop, const double * rr, const double * v1, const double * m2, const double * ainv, int64_t nb, double * o) -> int {
+        const void * fn = hop == 0 ? hess_fn<0>(t->has5) : hop == 2 ? hess_fn<2>(t->has5) : hess_fn<3>(t->has5);
+        { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
+        const int64_t grid = std::min<int64_t>(nb, (int64_t)t->sm_count);
+        void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&v1, (void *)&m2, (void *)&ainv, (void *)&nb, (void *)&o};
+        TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kHessThreads), args, hsmem, stream));
+        count_launch(hop == 0 ? "hess_kernel<0:gradient_cart2int_matrix>" : hop == 2 ? "hess_kernel<2:Hessian_int2cart>" : "hess_kernel<3:Hessian_cart2int>");
+        return TCHEM_OK;
+    };
+    if (op == 1) return launch_factor(0, r, in1, B, out, nullptr);
+    if (op == 2) return launch_hess(2, r, in1, in2, nullptr, B, out);
+    // matrix / Hessian cart -> int: the packed inverses (and g_q) of a slice of the batch go through a stream-ordered workspace
+    const int64_t slice = std::min<int64_t>(B, 16384);
+    double * ws = nullptr;
+    const size_t ws_doubles = (size_t)slice * (ntri + n);
+    if (cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_doubles * sizeof(double), stream) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(TCHEM_ENOMEM, "tchem::IC::IntCoordSet: cannot allocate the workspace of the cart2int transforms");
+    }
+    double * ws_ainv = ws, * ws_gq = ws + (size_t)slice * ntri;
+    rc = TCHEM_OK;
+    for (int64_t b0 = 0; b0 < B && rc == TCHEM_OK; b0 += slice) {
+        const int64_t nb = std::min<int64_t>(slice, B - b0);
+        const double * rr = r + b0 * cd;
+        if (op == 0) {
+            rc = launch_factor(1, rr, nullptr, nb, nullptr, ws_ainv);
+            if (rc == TCHEM_OK) rc = launch_hess(0, rr, nullptr, nullptr, ws_ainv, nb, out + b0 * (int64_t)n * cd);
+        } else {
+            rc = launch_factor(1, rr, in1 + b0 * cd, nb, ws_gq, ws_ainv);
+            if (rc == TCHEM_OK) rc = launch_hess(3, rr, ws_gq, in2 + b0 * (int64_t)cd * cd, ws_ainv, nb, out + b0 * (int64_t)n * n);
+        }
+    }
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+} // namespace tchem_b200

@@ -163,44 +163,57 @@ class IntCoordSet:
         """1 when a cart2int call since the last poll met a non-positive-definite J J^T (synchronises)"""
         return int(lib.tchem_ic_factor_status(self._handle))
 
-    def _transform(self, fn, name, r, extras, out_shape, factors=False):
+    def _transform(self, fn, name, r, extras, out_shape, factors=False, out=None):
+        """out: caller-provided result tensor - on the device for device inputs; for host inputs a host tensor
+        (pinned: the download is a direct DMA) that the result is copied into before the call returns"""
         r2, batched = self._prep(r, name)
         B = r2.shape[0]
+        host = not r2.is_cuda
         dev_r = self._on_device(r2)
         args = []
         for t, shape, what in extras:
             args.append(self._same(t, dev_r, (B,) + shape, name, what))
-        out = torch.empty((B,) + out_shape, dtype=torch.float64, device=self.device)
+        if out is not None and (out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != B * math.prod(out_shape)
+                                or out.is_cuda == host):
+            raise ValueError("tchem::IC::IntCoordSet::%s: bad out tensor" % name)
+        res = out.view((B,) + out_shape) if out is not None and not host else \
+            torch.empty((B,) + out_shape, dtype=torch.float64, device=self.device)
         ptr = lambda t: C.c_void_p(t.data_ptr())
         if B > 0:
-            check(fn(self._handle, ptr(dev_r), *[ptr(a) for a in args], B, ptr(out), _stream_ptr(self.device)))
+            check(fn(self._handle, ptr(dev_r), *[ptr(a) for a in args], B, ptr(res), _stream_ptr(self.device)))
             if factors and self.check_factorisation and self.factor_status():
                 raise RuntimeError("tchem::IC::IntCoordSet::%s: cholesky: J J^T is not positive definite for at least one "
                                    "geometry of the batch (redundant or singular internal coordinates)" % name)
-        if not r2.is_cuda:
-            out = out.cpu()
-        return out if batched else out[0]
+        if host:
+            if out is not None:
+                hres = out.view((B,) + out_shape)
+                hres.copy_(res, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                res = hres
+            else:
+                res = res.cpu()
+        return res if batched else res[0]
 
-    def gradient_cart2int_matrix(self, r):
+    def gradient_cart2int_matrix(self, r, out=None):
         return self._transform(lib.tchem_ic_grad_cart2int_matrix, "gradient_cart2int", r, [],
-                               (self.intdim, self.cartdim), factors=True)
+                               (self.intdim, self.cartdim), factors=True, out=out)
 
-    def gradient_cart2int(self, r, cartgrad):
+    def gradient_cart2int(self, r, cartgrad, out=None):
         return self._transform(lib.tchem_ic_grad_cart2int, "gradient_cart2int", r,
-                               [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient")], (self.intdim,), factors=True)
+                               [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient")], (self.intdim,), factors=True, out=out)
 
-    def gradient_int2cart(self, r, intgrad):
+    def gradient_int2cart(self, r, intgrad, out=None):
         return self._transform(lib.tchem_ic_grad_int2cart, "gradient_int2cart", r,
-                               [(intgrad, (self.intdim,), "Internal coordinate gradient")], (self.cartdim,))
+                               [(intgrad, (self.intdim,), "Internal coordinate gradient")], (self.cartdim,), out=out)
 
-    def Hessian_cart2int(self, r, cartgrad, cartHess):
+    def Hessian_cart2int(self, r, cartgrad, cartHess, out=None):
         return self._transform(lib.tchem_ic_hess_cart2int, "Hessian_cart2int", r,
                                [(cartgrad, (self.cartdim,), "Cartesian coordinate gradient"),
                                 (cartHess, (self.cartdim, self.cartdim), "Cartesian coordinate Hessian")],
-                               (self.intdim, self.intdim), factors=True)
+                               (self.intdim, self.intdim), factors=True, out=out)
 
-    def Hessian_int2cart(self, r, intgrad, intHess):
+    def Hessian_int2cart(self, r, intgrad, intHess, out=None):
         return self._transform(lib.tchem_ic_hess_int2cart, "Hessian_int2cart", r,
                                [(intgrad, (self.intdim,), "Internal coordinate gradient"),
                                 (intHess, (self.intdim, self.intdim), "Internal coordinate Hessian")],
-                               (self.cartdim, self.cartdim))
+                               (self.cartdim, self.cartdim), out=out)
