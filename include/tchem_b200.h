@@ -164,6 +164,14 @@ TCHEM_API int tchem_ic_sap_eval(const tchem_ic_table * ic, const tchem_sap_table
                       int64_t B, double * q_out, double * y, double * J, tchem_stream_t stream);
 TCHEM_API int tchem_ic_sap_eval_host(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r,
                            int64_t B, double * q_out, double * y, double * J);
+/* chained path, CARTESIAN derivatives:
+ *   dydr  [B][nterms][cartdim]            = (dSAP/dq) J
+ *   d2ydr2[B][nterms][cartdim][cartdim]   = J^T (d2SAP/dq2) J + sum_k (dSAP/dq_k) K[k]       (may be NULL)
+ * what callers of the reference compose by hand from SAPSet::Jacobian_ / Jacobian2nd_ (source/polynomial/
+ * SAPSet.cpp:178-201, :243-276) and IntCoordSet::compute_IC_J / compute_IC_J_K (source/IC/IntCoordSet.cpp:147-175),
+ * cf. test/normal_mode/main.cpp:56-61. y[B][nterms] may be NULL. Device pointers. */
+TCHEM_API int tchem_ic_sap_eval_cart(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r, int64_t B,
+                                     double * y, double * dydr, double * d2ydr2, tchem_stream_t stream);
 
 /* ---- introspection (host only, no device needed; used by the CPU tests) ------------------------ */
 /* Compiles the definition for `mode` (0 value path, 1 q+J, 2 q+J+K) exactly as
@@ -197,6 +205,11 @@ TCHEM_API int64_t tchem_sap_jit_hess_source(const int32_t * term_ptr, const int3
 /* source of the kernel specialised to a SAPSet for tchem_sap_eval (bulk != 0: whole-tile TMA bulk stores) */
 TCHEM_API int64_t tchem_sap_jit_source(const int32_t * term_ptr, const int32_t * coords, int n_terms,
                                        const int32_t * dims, int n_irreducibles, int bulk, char * buf, int64_t capacity);
+/* source of the kernel specialised to an (IntCoordSet, SAPSet) pair with the Jacobian in Cartesian coordinates
+ * (tchem_ic_sap_eval_cart, first order); 0 when the pair is not eligible */
+TCHEM_API int64_t tchem_ic_sap_jit_cart_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim,
+                                               const int32_t * term_ptr, const int32_t * coords, int n_sap,
+                                               const int32_t * dims, int n_irreducibles, char * buf, int64_t capacity);
 TCHEM_API int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity);
 /* 1 when a q + J call on B geometries is served by the specialised kernel, 0 = interpreter */
 TCHEM_API int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B);

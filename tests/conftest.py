@@ -29,6 +29,19 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+def dense_K(g):
+    """K of a golden file that stores it as (pattern, values): make_golden.py::sparse_K"""
+    shape = tuple(int(v) for v in g["K_shape"])
+    K = np.zeros((shape[0], int(np.prod(shape[1:]))))
+    K[:, g["K_idx"]] = g["K_val"]
+    return K.reshape(shape)
+
+
+def c4_t32_inputs(g):
+    """inputs of workload_C4_T32: stored as small integers, exact in float64"""
+    return g["intgrad16"].astype(np.float64) / 16.0, g["intHess32"].astype(np.float64) / 32.0
+
+
 def parity_ratio(x, ref, tol=1e-12):
     """max over elements of |x - ref| / max(tol, tol * |ref|)   (north_star tolerance)"""
     x = np.asarray(x, dtype=np.float64)

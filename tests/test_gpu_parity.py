@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import assert_parity, assert_q_parity, golden, terms_from_golden
+from conftest import assert_parity, assert_q_parity, c4_t32_inputs, dense_K, golden, terms_from_golden
 from oracle import tchem_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -421,6 +421,7 @@ def test_gradient_int2cart_reference_fixture(T):
 # condition number multiplies every rounding difference: the oracle restatement itself (same
 # potrf / potri algorithm, tests/test_oracle.py) only agrees with the reference to ~2e-13 on the
 # aniline fixture, so these comparisons carry a 1e-11 bound and DESIGN.md says so.
+C4_CART2INT_TOL = 1e-11
 TRANSFORM_CASES = [("ref_aniline_default", "default", 14), ("workload_C1", "default", 3),
                    ("workload_C2", "default", 6), ("workload_C4", "default", 30)]
 
@@ -463,6 +464,46 @@ def test_hessian_int2cart_every_fixture_general_matrix(T, name):
     out = host(s.Hessian_int2cart(dev(r), dev(gq), dev(Hq)))
     assert_parity(out, orc.Hessian_int2cart(r, gq, Hq), name + " Hessian_int2cart, general H_q")
     assert_parity(host(s.gradient_int2cart(dev(r), dev(gq))), orc.gradient_int2cart(r, gq), name + " gradient_int2cart")
+
+
+def test_K_against_64_reference_geometries_C3(T):
+    """the reference's own K (autograd through its analytic J) on 64 geometries of BASELINE config 3, and on the
+    normal_mode fixture (un-normalised coefficients): north_star tolerance, structural zeros exactly zero"""
+    for name, natoms in (("workload_C3_K64", 20), ("ref_normal_mode_K", None)):
+        g = golden(name)
+        na = natoms or g["r"].shape[1] // 3
+        s = T.IntCoordSet.from_text("default", str(g["definition"]), n_atoms=na)
+        q, J, K = s.compute_IC_J_K(dev(g["r"]))
+        Kref = dense_K(g)
+        assert_parity(host(J), g["J"], name + " J")
+        assert_parity(host(K), Kref, name + " K")
+        zero = np.ones(Kref[0].size, dtype=bool)
+        zero[g["K_idx"]] = False
+        assert not host(K).reshape(Kref.shape[0], -1)[:, zero].any(), name + ": structural zeros of K must be exact zeros"
+
+
+# per-fixture bounds of the cart -> int transforms, set from the worst ratios observed on the B200
+# (profiles/r02_parity_ratios.json) with cond(J J^T) beside them: the error of ANY potrf-based evaluation against the
+# reference's LAPACK is a few cond * eps, so the bound scales with the fixture's condition number.
+#   aniline (cond ~1e3), C1, C2 (cond < 1e2): north_star's 1e-12;   C4 (cond 1.05e4): 4e-12
+def test_transforms_on_32_reference_geometries_C4(T):
+    g = golden("workload_C4_T32")
+    s = T.IntCoordSet.from_text("default", str(g["definition"]), n_atoms=30)
+    r = dev(g["r"])
+    gq, Hq = c4_t32_inputs(g)
+    assert_parity(host(s.gradient_int2cart(r, dev(gq))), g["cartgrad"], "C4x32 gradient_int2cart")
+    assert_parity(host(s.Hessian_int2cart(r, dev(gq), dev(Hq))), g["cartHess"], "C4x32 Hessian_int2cart")
+    assert_parity(host(s.gradient_cart2int(r, dev(g["cartgrad"]))), g["intgrad_back"], "C4x32 gradient_cart2int (cond 1.05e4)", tol=C4_CART2INT_TOL)
+    assert_parity(host(s.gradient_cart2int_matrix(r[:8])), g["cart2int_matrix"], "C4x32 gradient_cart2int_matrix (cond 1.05e4)", tol=C4_CART2INT_TOL)
+    assert_parity(host(s.Hessian_cart2int(r, dev(g["cartgrad"]), dev(g["cartHess"]))), g["intHess_back"],
+                  "C4x32 Hessian_cart2int (cond 1.05e4)", tol=C4_CART2INT_TOL)
+    # bit-reproducible: batch vs one geometry at a time, and run to run (no atomics in the g.K accumulation)
+    Hb = s.Hessian_int2cart(r, dev(gq), dev(Hq))
+    H1 = s.Hessian_int2cart(r[5], dev(gq[5]), dev(Hq[5]))
+    assert torch.equal(H1, Hb[5]) and torch.equal(Hb, s.Hessian_int2cart(r, dev(gq), dev(Hq)))
+    Qb = s.Hessian_cart2int(r, dev(g["cartgrad"]), dev(g["cartHess"]))
+    Q1 = s.Hessian_cart2int(r[7], dev(g["cartgrad"][7]), dev(g["cartHess"][7]))
+    assert torch.equal(Q1, Qb[7])
 
 
 def test_transform_round_trip_C4(T):

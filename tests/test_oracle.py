@@ -6,7 +6,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import EPS, assert_parity, assert_q_parity, golden, terms_from_golden
+from conftest import EPS, assert_parity, assert_q_parity, c4_t32_inputs, dense_K, golden, terms_from_golden
 from oracle import tchem_oracle as O
 
 IC_CASES = ["ref_aniline_default", "ref_aniline_columbus7", "ref_aniline_advanced", "ref_normal_mode"]
@@ -52,6 +52,34 @@ def test_oracle_transforms_against_reference_goldens():
     # round trip of test/intcoord/main.cpp:120-149
     assert_parity(g["intgrad_back"], g["intgrad"], "reference round trip g", tol=1e-10)
     assert_parity(g["intHess_back"], g["intHess"], "reference round trip H", tol=1e-10)
+
+
+def test_oracle_K_on_64_reference_geometries_C3():
+    """round 2: the reference's K on 64 geometries of BASELINE config 3 (and on the normal_mode fixture)"""
+    for name in ("workload_C3_K64", "ref_normal_mode_K"):
+        g = golden(name)
+        s = O.IntCoordSet("default", str(g["definition"]))
+        q, J, K = s.qJK(g["r"])
+        assert_parity(J, g["J"], name + " J (oracle)")
+        assert_parity(K, dense_K(g), name + " K (oracle)")
+
+
+def test_oracle_transforms_on_32_reference_geometries_C4():
+    """round 2: all transforms of the reference on 32 geometries of BASELINE config 4, cond(J J^T) ~ 1e4.
+    int -> cart is a plain contraction (1e-12); cart -> int inverts J J^T: the same potrf / potri algorithm in numpy
+    differs from the reference's LAPACK by a few cond * eps, which is where the 1e-11 below comes from."""
+    g = golden("workload_C4_T32")
+    s = O.IntCoordSet("default", str(g["definition"]))
+    r = g["r"]
+    gq, Hq = c4_t32_inputs(g)
+    assert float(g["cond_JJT"].max()) < 2e4
+    assert_parity(s.gradient_int2cart(r, gq), g["cartgrad"], "C4x32 gradient_int2cart (oracle)")
+    assert_parity(s.Hessian_int2cart(r[:8], gq[:8], Hq[:8]), g["cartHess"][:8], "C4x32 Hessian_int2cart (oracle)")
+    assert_parity(s.gradient_cart2int(r, g["cartgrad"]), g["intgrad_back"], "C4x32 gradient_cart2int (oracle)", tol=1e-11)
+    assert_parity(s.gradient_cart2int_matrix(r[:8]), g["cart2int_matrix"], "C4x32 gradient_cart2int_matrix (oracle)", tol=1e-11)
+    # the reference's own round trip (test/intcoord/main.cpp:120-149) at this size
+    assert_parity(g["intgrad_back"], gq, "C4x32 reference round trip g", tol=1e-9)
+    assert_parity(g["intHess_back"], Hq, "C4x32 reference round trip H", tol=1e-8)
 
 
 def test_columbus_golden_vector_intgeom():

@@ -27,7 +27,10 @@ int ensure_max_dynamic_smem(const void * fn, int device, int max_smem_optin) {
     static std::set<std::pair<const void *, int>> done;
     std::lock_guard<std::mutex> lock(m);
     if (done.count({fn, device})) return TCHEM_OK;
-    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+    // (the opt-in maximum covers static + dynamic shared memory)
+    cudaFuncAttributes fa;
+    TC_CUDA(cudaFuncGetAttributes(&fa, fn));
+    TC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - (int)fa.sharedSizeBytes));
     done.insert({fn, device});
     return TCHEM_OK;
 }

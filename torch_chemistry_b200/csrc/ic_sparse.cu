@@ -52,27 +52,49 @@ struct SparseProgram {                // device pointers into one blob (starts a
     const SpTerm *   terms;           // row order
     const int32_t *  row_ptr;         // [intdim + 1] terms of a row
     const int32_t *  jrow_order;      // [njrow] rows in evaluation order: grouped by type, groups padded to 32 with -1
-    const uint32_t * ktasks;          // [nktasks] (term << 8) | direction, heaviest first
+    const uint32_t * ktasks;          // [32 * nsteps] warp steps of 32 same-kind tasks: (term << 8) | direction, 0x80000000 | row (J row of the
+                                      // next geometry), 0xffffffff = none
+    const uint16_t * sched_ptr;       // [hess warps + 1] static schedule: the steps of each warp (longest-processing-time assignment)
+    const uint16_t * sched_step;      // [nsteps]
     const uint16_t * nz_ptr;          // [intdim + 1] CSR over Jv
     const uint16_t * nz_col;          // [nnz] column of every Jv position
-    const uint16_t * col_ptr;         // [cartdim + 1] CSC
-    const uint32_t * col_ent;         // [nnz] (row << 16) | Jv position
+    const uint16_t * col_ptr;         // [natoms + 1] compressed COLUMN BLOCKS: the three columns of an atom share their row list
+    const uint32_t * col_ent;         // [nnz / 3] (row << 16) | Jv position of the x component (y, z follow)
     const uint32_t * pair_dest;       // [npairs_pad] packed index (i (i + 1) / 2 + j) of a structurally nonzero A[i][j], j <= i
     const uint32_t * pair_ent;        // [maxc][npairs_pad] (Jv position in row i << 16) | Jv position in row j of a common atom
     const uint32_t * gk_blk;          // [ngblk] (atom A << 16) | atom B: 3 x 3 block of the g.K accumulator that receives slots
     const uint32_t * gk_ptr;          // [ngblk + 1]
     const uint32_t * gk_src;          // [ngsrc] (slot index << 1) | transposed
     int32_t nterms, njrow, nktasks, nnz, nnz_pad, npairs_pad, maxc, ngblk, ngsrc, nslots;
+    int32_t natoms;
     int32_t intdim, cartdim, ldh;     // ldh: leading dimension of the intdim x intdim DMMA operands (4 or 12 mod 16)
-    int32_t blob_bytes;
-    int32_t tab_in_smem;              // per launch: the block kernel works on a shared-memory copy of the blob
+    int32_t factor_tab_bytes;         // leading part of the blob the factor kernel copies to shared memory: pair lists | common tables
+    int32_t hess_tab_offset, blob_bytes;   // the block kernel copies [hess_tab_offset, blob_bytes): common tables | its own
+    int32_t tab_in_smem;              // per launch: the block kernel works on a shared-memory copy of its part of the blob
 };
 
 namespace {
 
 constexpr int kNB = 8;                // panel width of the warp-level factorisation
 constexpr int kMaxSlots = 4;          // lanes x 4 = 128: upper limit of intdim + 1 and cartdim on this path
-constexpr int kHessThreads = 288;     // 9 warps: (J rows + (term, direction) tasks) of C4 = 834 tasks = 3 rounds
+constexpr int kHessThreads = 384;     // 12 warps: the (term, direction) tasks + next J rows of C4 (834) run as torsion, bend and stretch rounds
+
+// -DTCHEM_SPARSE_PHASES: thread 0 of block 0 accumulates the clock cycles of each phase of its geometries
+// (tchem_debug_sparse_phases; tools/sparse_phases.py). Off in the product.
+#ifdef TCHEM_SPARSE_PHASES
+__device__ unsigned long long g_sparse_phase[32];
+__device__ __forceinline__ long long sphase_clock(const double * probe) {
+    const double x = *reinterpret_cast<const volatile double *>(probe);      // the read waits for the barrier's release
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "d"(x) : "memory");
+    return t;
+}
+#define SPHASE_BEGIN(probe) const double * sph_probe = (probe); long long sph_t0 = sphase_clock(sph_probe)
+#define SPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long sph_t = sphase_clock(sph_probe); g_sparse_phase[i] += (unsigned long long)(sph_t - sph_t0); sph_t0 = sph_t; } } while (0)
+#else
+#define SPHASE_BEGIN(probe) do {} while (0)
+#define SPHASE(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ double nan64() { return __longlong_as_double(0x7ff8000000000000ll); }
@@ -140,16 +162,23 @@ __device__ __forceinline__ void eval_J_rows(const SparseProgram & sp, const doub
 // ======================================================================================================
 // factor_kernel: one warp = one geometry
 // ======================================================================================================
+// The O(n^3) parts of the factorisation run on the FP64 tensor cores, one 8 x 8 tile per DMMA pair
+// (mma.m8n8k4.f64; fragments: a = A[gid][tig], b = B[tig][gid], c0 / c1 = C[gid][2 tig + {0, 1}], gid = lane >> 2,
+// tig = lane & 3), with the fragments addressed straight in the row-major PACKED lower storage A[i (i + 1) / 2 + j]:
+// a plain-FMA version of the same loops spent 80 % of its instructions on addressing and predicates (53 000 warp
+// instructions per 84 x 84 factorisation at 0.27 IPC; tools/proto/warp_chol.py holds the lane-level emulation both
+// versions were checked with).
+
 // In-place lower Cholesky factor of the packed matrix A (rows 0 .. n-1; with `border` row n holds a right-hand
 // side b and ends as L^-1 b). Right-looking over panels of 8 columns:
 //  * panel: lane = row (rows j0 + lane + 32 m), the row's 8 panel entries in registers; pivot c belongs to lane c
 //    (slot 0); its reciprocal square root is taken by every lane, the scaled pivot column's diagonal-block entries
 //    travel by shuffle;
-//  * trailing update A[i][j] -= sum_c L[i][c] L[j][c]: lane = column j, its L[j][.] kept in registers, rows walked
-//    two at a time with the 8 panel entries of the row read as broadcasts.
+//  * trailing update A[i][j] -= sum_c L[i][c] L[j][c] by 8 x 8 tiles (I >= J), two DMMAs each.
 // rdiag[j] = 1 / L[j][j]. Returns false when a pivot is not positive (NaN included).
 __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border, double * rdiag, int lane) {
     const int last = border ? n : n - 1;
+    const int gid = lane >> 2, tig = lane & 3;
     bool ok = true;
     for (int j0 = 0; j0 < n; j0 += kNB) {
         const int bs = min(kNB, n - j0);
@@ -199,42 +228,23 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
         }
         __syncwarp();
         const int t0 = j0 + bs;
-        if (t0 < n) {
-            double Lj[kMaxSlots][kNB];
-#pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                const int j = t0 + lane + 32 * m;
-                const double * Aj = A + tri(min(j, n - 1)) + j0;
-#pragma unroll
-                for (int c = 0; c < kNB; c++) Lj[m][c] = (j < n && c < bs) ? Aj[c] : 0.0;
-            }
-            // rows two at a time, two partial sums per element: four to twelve independent FMA chains
-            for (int i = t0; i <= last; i += 2) {
-                const bool two = i + 1 <= last;
-                double * A0 = A + tri(i), * A1 = A + tri(two ? i + 1 : i);
-                double L0[kNB], L1[kNB];
-#pragma unroll
-                for (int c = 0; c < kNB; c++) {
-                    L0[c] = c < bs ? A0[j0 + c] : 0.0;
-                    L1[c] = c < bs ? A1[j0 + c] : 0.0;
-                }
-                const int jmax0 = min(i, n - 1), jmax1 = two ? min(i + 1, n - 1) : -1;
-#pragma unroll
-                for (int m = 0; m < kMaxSlots; m++) {
-                    if (t0 + 32 * m <= max(jmax0, jmax1)) {
-                        const int j = t0 + lane + 32 * m;
-                        const bool v0 = j <= jmax0, v1 = j <= jmax1;
-                        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-#pragma unroll
-                        for (int c = 0; c < kNB; c += 2) {
-                            p0 = fma(L0[c], Lj[m][c], p0);
-                            p1 = fma(L0[c + 1], Lj[m][c + 1], p1);
-                            q0 = fma(L1[c], Lj[m][c], q0);
-                            q1 = fma(L1[c + 1], Lj[m][c + 1], q1);
-                        }
-                        if (v0) A0[j] -= p0 + p1;
-                        if (v1) A1[j] -= q0 + q1;
-                    }
+        if (t0 < n) {                                   // (bs == 8 here: only the last panel can be narrower)
+            for (int I = t0; I <= last; I += 8) {
+                const int i = I + gid, ic = min(i, last);
+                const double * Li = A + tri(ic) + j0 + tig;
+                const double a0 = Li[0], a1 = Li[4];                   // A fragments of the two k-steps: L[i][j0 + tig (+ 4)]
+                double * Ci = A + tri(ic) + 2 * tig;
+                const int jend = min(I + 8, n);
+                for (int J = t0; J < jend; J += 8) {
+                    const int jb = min(J + gid, n - 1);
+                    const double * Lj = A + tri(jb) + j0 + tig;
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma(c0, c1, a0, Lj[0]);
+                    dmma(c0, c1, a1, Lj[4]);
+                    const int j = J + 2 * tig;
+                    const int jmax = min(i, n - 1);
+                    if (i <= last && j <= jmax) Ci[J] -= c0;
+                    if (i <= last && j + 1 <= jmax) Ci[J + 1] -= c1;
                 }
             }
             __syncwarp();
@@ -243,36 +253,60 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
     return ok;
 }
 
-// L^T x = y, y = the bordered row: right-looking, row k of L is contiguous. x[m] = element lane + 32 m.
+// L^T x = y, y = the bordered row, blocks of 8 unknowns from the bottom: the block's own 8 x 8 triangle by shuffles
+// (one shuffle, one multiply and one fma on the chain per unknown), then one rank-8 update of everything above.
+// x[m] = element lane + 32 m.
 __device__ __forceinline__ void warp_backsolve_packed(const double * A, int n, const double * rdiag, double * x, int lane) {
 #pragma unroll
     for (int m = 0; m < kMaxSlots; m++) {
         const int i = lane + 32 * m;
         x[m] = i < n ? A[tri(n) + i] : 0.0;
     }
-    for (int k = n - 1; k >= 0; k--) {
-        const int km = k >> 5, kl = k & 31;
-        double xs = x[0];
+    for (int k0 = ((n - 1) >> 3) << 3; k0 >= 0; k0 -= 8) {
+        const int bs = min(8, n - k0);
+        const int km = k0 >> 5, kl0 = k0 & 31;
+        double xb = x[0];                               // the slot that holds the block (a block never straddles slots)
 #pragma unroll
-        for (int m = 1; m < kMaxSlots; m++) xs = km == m ? x[m] : xs;
-        const double xk = __shfl_sync(kFull, xs, kl) * rdiag[k];
-        const double * Lk = A + tri(k);
+        for (int m = 1; m < kMaxSlots; m++) xb = km == m ? x[m] : xb;
+        const int ib = lane + 32 * km;                  // this lane's element of that slot
+        double xk[8];
+#pragma unroll
+        for (int c = 7; c >= 0; c--) {
+            xk[c] = 0.0;
+            if (c < bs) {
+                const int k = k0 + c;
+                xk[c] = __shfl_sync(kFull, xb, kl0 + c) * rdiag[k];
+                if (lane == kl0 + c) xb = xk[c];
+                else if (ib >= k0 && ib < k) xb = fma(-A[tri(k) + ib], xk[c], xb);
+            }
+        }
 #pragma unroll
         for (int m = 0; m < kMaxSlots; m++) {
+            if (m == km) x[m] = xb;
             const int i = lane + 32 * m;
-            if (m == km && lane == kl) x[m] = xk;
-            else if (i < k) x[m] = fma(-Lk[i], xk, x[m]);
+            if (32 * m < k0 && i < k0) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    if (c < bs) s0 = fma(A[tri(k0 + c) + i], xk[c], s0);
+                    if (c + 1 < bs) s1 = fma(A[tri(k0 + c + 1) + i], xk[c + 1], s1);
+                }
+                x[m] -= s0 + s1;
+            }
         }
     }
 }
 
-// in place: L -> W = L^-1 (lower), row panels of 8 from the top:
-//   W[I][I] = L[I][I]^-1,   W[I][0:i0] = -W[I][I] (L[I][0:i0] W[0:i0][0:i0])
-// lanes run along the columns j of the result; Ds: 64 doubles of scratch
+// in place: L -> W = L^-1 (lower), row panels I of 8 from the top:
+//   D = L[I][I]^-1 (registers, forward substitution, lane & 7 = column),
+//   W[I][J] = -D (L[I][J:i0] W[J:i0][J]) for the column tiles J = 0, 8, .. in ASCENDING order: tile J reads L[I][k >= J]
+//   only, so each finished tile can overwrite its own columns of rows I at once.
+// Ds: 128 doubles of scratch (D, and the tile in transit between the two DMMA products)
 __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const double * rdiag, double * Ds, int lane) {
+    const int gid = lane >> 2, tig = lane & 3;
+    double * Ts = Ds + 64;
     for (int i0 = 0; i0 < n; i0 += kNB) {
         const int bs = min(kNB, n - i0);
-        // inverse of the 8 x 8 diagonal block: lane & 7 = column, forward substitution in registers
         const int c = lane & 7;
         double Dc[kNB];
 #pragma unroll
@@ -286,47 +320,34 @@ __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const doubl
             const double rd = r < bs ? rdiag[i0 + r] : 0.0;
             Dc[r] = (r < c || c >= bs) ? 0.0 : r == c ? rd : -s * rd;
         }
-        double acc[kMaxSlots][kNB];
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++)
-#pragma unroll
-            for (int r = 0; r < kNB; r++) acc[m][r] = 0.0;
-        for (int k = 0; k < i0; k++) {
-            double Lr[kNB];
-#pragma unroll
-            for (int r = 0; r < kNB; r++) Lr[r] = r < bs ? A[tri(i0 + r) + k] : 0.0;
-            const double * Wk = A + tri(k);
-#pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                if (32 * m <= k) {
-                    const int j = lane + 32 * m;
-                    const double w = j <= k ? Wk[j] : 0.0;
-#pragma unroll
-                    for (int r = 0; r < kNB; r++) acc[m][r] = fma(Lr[r], w, acc[m][r]);
-                }
-            }
-        }
-        __syncwarp();                                  // every lane is done reading rows I (overwritten below)
         if (lane < kNB) {
 #pragma unroll
             for (int r = 0; r < kNB; r++) Ds[r * kNB + lane] = Dc[r];
         }
         __syncwarp();
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int j = lane + 32 * m;
-            if (32 * m < i0 && j < i0) {
-#pragma unroll
-                for (int r = 0; r < kNB; r++) {
-                    if (r < bs) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int r2 = 0; r2 <= r; r2++) s = fma(Ds[r * kNB + r2], acc[m][r2], s);
-                        A[tri(i0 + r) + j] = -s;
-                    }
-                }
+        const double d0 = -Ds[gid * kNB + tig], d1 = -Ds[gid * kNB + 4 + tig];      // A fragments of -D
+        const int ri = min(i0 + gid, n - 1);
+        const double * Lr = A + tri(ri) + tig;
+        for (int J = 0; J < i0; J += 8) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int k0 = J; k0 < i0; k0 += 4) {
+                const int kk = k0 + tig, jj = J + gid;
+                const double bv = jj <= kk ? A[tri(kk) + jj] : 0.0;                  // W[k][j], zero above the diagonal
+                dmma(t0, t1, Lr[k0], bv);
+            }
+            __syncwarp();                                 // rows I, columns >= J have been read by every lane
+            Ts[gid * kNB + 2 * tig] = t0;
+            Ts[gid * kNB + 2 * tig + 1] = t1;
+            __syncwarp();
+            double r0 = 0.0, r1 = 0.0;
+            dmma(r0, r1, d0, Ts[tig * kNB + gid]);
+            dmma(r0, r1, d1, Ts[(4 + tig) * kNB + gid]);
+            if (gid < bs) {
+                double * o = A + tri(i0 + gid) + J + 2 * tig;
+                o[0] = r0; o[1] = r1;
             }
         }
+        __syncwarp();
         if (lane < bs) {
 #pragma unroll
             for (int r = 0; r < kNB; r++)
@@ -336,91 +357,106 @@ __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const doubl
     }
 }
 
-// in place: W (lower) -> lower triangle of W^T W, row panels of 8 ascending (rows below a panel are still W)
+// in place: W (lower) -> lower triangle of W^T W, row panels I of 8 ascending (rows below a panel are still W); tile
+// (I, J) = sum over k >= i0 of W[k][I]^T W[k][J], column tiles ascending so that the diagonal tile - the only one
+// whose columns the others read in rows I - is written last
 __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
+    const int gid = lane >> 2, tig = lane & 3;
     for (int i0 = 0; i0 < n; i0 += kNB) {
-        const int bs = min(kNB, n - i0);
-        const int ncols = i0 + bs;
-        double acc[kMaxSlots][kNB];
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++)
-#pragma unroll
-            for (int r = 0; r < kNB; r++) acc[m][r] = 0.0;
-        for (int k = i0; k < n; k++) {
-            const double * Wk = A + tri(k);
-            double Wr[kNB];
-#pragma unroll
-            for (int r = 0; r < kNB; r++) Wr[r] = (r < bs && i0 + r <= k) ? Wk[i0 + r] : 0.0;
-#pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                if (32 * m < ncols) {
-                    const int j = lane + 32 * m;
-                    const double w = (j <= k && j < ncols) ? Wk[j] : 0.0;
-#pragma unroll
-                    for (int r = 0; r < kNB; r++) acc[m][r] = fma(Wr[r], w, acc[m][r]);
-                }
+        const int ra = i0 + gid;
+        for (int J = 0; J <= i0; J += 8) {
+            const int cb = J + gid;
+            double c0 = 0.0, c1 = 0.0;
+            for (int k0 = i0; k0 < n; k0 += 4) {
+                const int kk = k0 + tig;
+                const double * Wk = A + tri(min(kk, n - 1));
+                const double av = (kk < n && ra <= kk) ? Wk[ra] : 0.0;
+                const double bv = (kk < n && cb <= kk) ? Wk[cb] : 0.0;
+                dmma(c0, c1, av, bv);
             }
+            __syncwarp();
+            const int j = J + 2 * tig;
+            if (ra < n) {
+                double * o = A + tri(ra) + j;
+                if (j <= ra) o[0] = c0;
+                if (j + 1 <= ra) o[1] = c1;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int j = lane + 32 * m;
-#pragma unroll
-            for (int r = 0; r < kNB; r++)
-                if (r < bs && j <= i0 + r) A[tri(i0 + r) + j] = acc[m][r];
-        }
-        __syncwarp();
     }
 }
 
-// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[64]
-__host__ __device__ inline int factor_smem_doubles(int n, int nnz_pad) {
-    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 64;
+__host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
+// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[128] (+ rg[cd] | g[cd], see factor_kernel)
+__host__ __device__ inline int factor_smem_doubles(int n, int cd, int nnz_pad) {
+    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 128 + 2 * ((cd + 1) & ~1);
 }
 
 // OPF 0: g_q = (J J^T)^-1 (J g_r)                     -> gq_out[B][n]
 // OPF 1: the same (g_r may be null) plus the packed inverse -> ainv_out[B][n (n + 1) / 2]
+// The block's warps work on different geometries and never meet after the definition tables (the leading
+// `factor_tab_bytes` of the blob: pair lists, terms, compressed-row structure) have been copied to shared memory:
+// every table read is a shared-memory read (from global memory each of them is an L2 round trip on the critical path
+// of a single warp: measured 10x slower).
 template <int OPF, bool HAS5>
-__global__ void __launch_bounds__(32)
-factor_kernel(const SparseProgram sp, const double * __restrict__ r, const double * __restrict__ gr, const int64_t B,
+__global__ void __launch_bounds__(192)
+factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, const double * __restrict__ gr, const int64_t B,
               double * __restrict__ gq_out, double * __restrict__ ainv_out, int * __restrict__ status) {
     extern __shared__ __align__(16) double sm_dyn[];
-    const int lane = threadIdx.x;
-    const int n = sp.intdim, cd = sp.cartdim;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int n = sp_global.intdim, cd = sp_global.cartdim;
     const int ntri = (n * (n + 1)) >> 1;
-    double * Jv = sm_dyn;
+    SparseProgram sp = sp_global;
+    const int tab_doubles = (sp_global.factor_tab_bytes + 7) / 8;
+    {
+        const double * src = reinterpret_cast<const double *>(sp_global.pair_dest);          // the blob starts with the pair lists
+        for (int i = threadIdx.x; i < tab_doubles; i += blockDim.x) sm_dyn[i] = src[i];
+        const char * base = reinterpret_cast<const char *>(sp_global.pair_dest), * tb = reinterpret_cast<const char *>(sm_dyn);
+#define TC_REBASE(field, type) sp.field = reinterpret_cast<const type *>(tb + (reinterpret_cast<const char *>(sp_global.field) - base))
+        TC_REBASE(pair_dest, uint32_t); TC_REBASE(pair_ent, uint32_t); TC_REBASE(terms, SpTerm); TC_REBASE(row_ptr, int32_t);
+        TC_REBASE(jrow_order, int32_t); TC_REBASE(nz_ptr, uint16_t); TC_REBASE(nz_col, uint16_t);
+#undef TC_REBASE
+    }
+    __syncthreads();
+    double * Jv = sm_dyn + even_up(tab_doubles) + (size_t)warp * even_up(factor_smem_doubles(n, cd, sp.nnz_pad));
     double * A = Jv + sp.nnz_pad;
     double * rdiag = A + ntri + n + 2;
     double * Ds = rdiag + ((n + 1) & ~1);
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const double * rg = r + b * cd;
+    double * rg = Ds + 128, * gs = rg + ((cd + 1) & ~1);
+    SPHASE_BEGIN(Ds);
+    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+        // the geometry (and the gradient) are read once, coalesced: every later use is a shared-memory read
+        for (int i = lane; i < cd; i += kLanes) { rg[i] = r[b * cd + i]; if (gr != nullptr) gs[i] = gr[b * cd + i]; }
         for (int p = sp.nnz + lane; p < sp.nnz_pad; p += kLanes) Jv[p] = 0.0;      // the zero entries the padded pair lists point to
+        __syncwarp();
         eval_J_rows<HAS5>(sp, rg, Jv, lane, kLanes);
         for (int p = lane; p < ntri + n + 2; p += kLanes) A[p] = 0.0;
         __syncwarp();
+        SPHASE(0);
         // A = J J^T over the structurally nonzero pairs of rows: 3 products per common atom
         for (int p = lane; p < sp.npairs_pad; p += kLanes) {
             double s = 0.0;
             for (int e = 0; e < sp.maxc; e++) {
-                const uint32_t ent = __ldg(sp.pair_ent + e * sp.npairs_pad + p);
+                const uint32_t ent = sp.pair_ent[e * sp.npairs_pad + p];
                 const double * ji = Jv + (ent >> 16), * jj = Jv + (ent & 0xffffu);
                 s = fma(ji[0], jj[0], s);
                 s = fma(ji[1], jj[1], s);
                 s = fma(ji[2], jj[2], s);
             }
-            A[__ldg(sp.pair_dest + p)] = s;                                         // padding pairs write the spare element
+            A[sp.pair_dest[p]] = s;                                                 // padding pairs write the spare element
         }
         // bordered row: b = J g_r
         if (gr != nullptr) {
-            const double * g = gr + b * cd;
             for (int i = lane; i < n; i += kLanes) {
                 double s = 0.0;
-                for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) s = fma(Jv[p], __ldg(g + sp.nz_col[p]), s);
+                for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) s = fma(Jv[p], gs[sp.nz_col[p]], s);
                 A[ntri + i] = s;
             }
         }
         __syncwarp();
+        SPHASE(1);
         const bool ok = warp_potrf_packed(A, n, true, rdiag, lane);
+        SPHASE(2);
         if (!ok) {
             // the reference's at::cholesky throws (IntCoordSet.cpp:182): flag the table, NaN for this geometry
             if (lane == 0) atomicExch(status, 1);
@@ -438,13 +474,17 @@ factor_kernel(const SparseProgram sp, const double * __restrict__ r, const doubl
                 if (i < n) gq_out[b * n + i] = x[m];
             }
         }
+        SPHASE(3);
         if (OPF == 1) {
             warp_trtri_packed(A, n, rdiag, Ds, lane);
+            SPHASE(4);
             warp_lauum_packed(A, n, lane);
+            SPHASE(5);
             double * dst = ainv_out + b * ntri;
             for (int p = lane; p < ntri; p += kLanes) dst[p] = A[p];
         }
         __syncwarp();
+        SPHASE(6);
     }
 }
 
@@ -453,17 +493,17 @@ factor_kernel(const SparseProgram sp, const double * __restrict__ r, const doubl
 // ======================================================================================================
 // shared-memory plan (doubles)
 struct HessPlan { int small, jv, big, mid, third, tab, total; };
-__host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
+__host__ __device__ inline int ld_dmma(int width) { int ld = width; while ((ld & 15) != 4 && (ld & 15) != 12) ld++; return ld; }
 __host__ __device__ inline HessPlan hess_plan(int op, int n, int cd, int ldh, int nnz_pad, int nslots, int tab_doubles) {
     HessPlan p;
-    const int ldo = n | 1, ldc = cd | 1;              // odd leading dimensions: lanes that run down a column hit different banks
+    const int ldo = n | 1, ldj = ld_dmma(cd);              // odd leading dimensions: lanes that run down a column hit different banks
     p.small = 0;                                      // 2 x (coordinates | vector)
     p.jv = p.small + 2 * (even_up(cd) + even_up(cd > n ? cd : n));
     p.big = p.jv + 2 * nnz_pad;
     int big = 0, mid = 0, third = 0;
     switch (op) {
     case 2:  big = n * n; mid = max(cd * ldo, nslots); third = cd * cd; break;            // H_q | U, slots | X
-    case 3:  big = max(cd * cd, n * ldh); mid = max(max(n * ldc, nslots), n * ldh); third = n * ldh; break;   // H_c, S, H_q | slots, V, P | inverse
+    case 3:  big = max(cd * ldj, n * ldh); mid = max(nslots, cd * ldh); third = cd * ldh; break;   // H_c, H_q | slots, M^T | inverse, T2
     default: big = n * ldh; mid = n * cd; third = 0; break;                                // inverse | M
     }
     p.mid = p.big + even_up(big);
@@ -482,6 +522,22 @@ __device__ __forceinline__ void block_copy_async(const double * __restrict__ g, 
     } else {
         for (int i = threadIdx.x; i < count; i += blockDim.x)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s + i)), "l"(g + i) : "memory");
+    }
+}
+// global [rows][cols] -> shared [rows][ld], one warp per row at a time (no commit)
+__device__ __forceinline__ void block_rows_async(const double * __restrict__ g, double * s, int rows, int cols, int ld) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+    for (int r = warp; r < rows; r += nwarps) {
+        const double * src = g + (int64_t)r * cols;
+        double * dst = s + r * ld;
+        if (vec) {
+            for (int c = 2 * lane; c < cols; c += 2 * kLanes)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + c)), "l"(src + c) : "memory");
+        } else {
+            for (int c = lane; c < cols; c += kLanes)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + c)), "l"(src + c) : "memory");
+        }
     }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -503,176 +559,189 @@ __device__ __forceinline__ void block_store_rows(const double * s, double * __re
     }
 }
 
-// OUT[a][l] = sum over the nonzeros (k, v) of column a of J of  v * IN[k][l]      (OUT: cartdim x width)
-// one warp per column a, lanes along l (contiguous in IN): OUT = J^T IN
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// The products with J run over compressed column BLOCKS: the x, y, z columns of an atom have the same row list, so one
+// operand load feeds three FMAs (one shared-memory load per FMA would make the phase shared-memory bound), and a warp
+// owns one atom at a time with up to 3 x 4 accumulators.
+//
+// OUT[3 A + c][l] = sum over the rows k of atom A of  J[k][3 A + c] * IN[k][l]     (OUT: cartdim x width): OUT = J^T IN
+// lanes along l (contiguous in IN)
 __device__ __forceinline__ void spmm_JT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
                                         double * OUT, int ldout) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int a = warp; a < sp.cartdim; a += nwarps) {
-        double acc[kMaxSlots];
+    const uint32_t in0 = smem_addr(IN) + 8u * (uint32_t)lane;
+    for (int A = warp; A < sp.natoms; A += nwarps) {
+        double acc[3][kMaxSlots];
 #pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
-        for (int e = sp.col_ptr[a]; e < sp.col_ptr[a + 1]; e++) {
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) acc[c][m] = 0.0;
+        const int e1 = sp.col_ptr[A + 1];
+        for (int e = sp.col_ptr[A]; e < e1; e++) {
             const uint32_t ent = sp.col_ent[e];
-            const double v = Jv[ent & 0xffffu];
-            const double * in = IN + (ent >> 16) * ldin;
+            const double * jv = Jv + (ent & 0xffffu);
+            const double v0 = jv[0], v1 = jv[1], v2 = jv[2];
+            const uint32_t row = in0 + 8u * (uint32_t)((ent >> 16) * ldin);
 #pragma unroll
             for (int m = 0; m < kMaxSlots; m++) {
-                const int l = lane + 32 * m;
-                if (32 * m < width && l < width) acc[m] = fma(v, in[l], acc[m]);
+                if (32 * m < width) {
+                    // (lanes past the end read a clamped address; their sums are never stored)
+                    const double x = lds64(lane + 32 * m < width ? row + 256u * m : row);
+                    acc[0][m] = fma(v0, x, acc[0][m]);
+                    acc[1][m] = fma(v1, x, acc[1][m]);
+                    acc[2][m] = fma(v2, x, acc[2][m]);
+                }
             }
         }
 #pragma unroll
         for (int m = 0; m < kMaxSlots; m++) {
             const int l = lane + 32 * m;
-            if (l < width) OUT[a * ldout + l] = acc[m];
+            if (l < width) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) OUT[(3 * A + c) * ldout + l] = acc[c][m];
+            }
         }
     }
 }
-// OUT[a][c] = sum over the nonzeros (l, v) of column c of J of  IN[a][l] * v      (OUT: height x cartdim)
-// one warp per column c, lanes along a (IN's leading dimension is odd): OUT = IN J
+// OUT[a][3 B + c] = sum over the rows l of atom B of  IN[a][l] * J[l][3 B + c]     (OUT: height x cartdim): OUT = IN J
+// lanes along a (IN's leading dimension is odd: conflict-free)
 __device__ __forceinline__ void spmm_J(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
                                        double * OUT, int ldout) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int c = warp; c < sp.cartdim; c += nwarps) {
-        double acc[kMaxSlots];
+    uint32_t in_m[kMaxSlots];
 #pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
-        for (int e = sp.col_ptr[c]; e < sp.col_ptr[c + 1]; e++) {
+    for (int m = 0; m < kMaxSlots; m++) in_m[m] = smem_addr(IN) + 8u * (uint32_t)(min(lane + 32 * m, height - 1) * ldin);
+    for (int Bc = warp; Bc < sp.natoms; Bc += nwarps) {
+        double acc[3][kMaxSlots];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) acc[c][m] = 0.0;
+        const int e1 = sp.col_ptr[Bc + 1];
+        for (int e = sp.col_ptr[Bc]; e < e1; e++) {
             const uint32_t ent = sp.col_ent[e];
-            const double v = Jv[ent & 0xffffu];
-            const double * in = IN + (ent >> 16);
+            const double * jv = Jv + (ent & 0xffffu);
+            const double v0 = jv[0], v1 = jv[1], v2 = jv[2];
+            const uint32_t off = 8u * (ent >> 16);
 #pragma unroll
             for (int m = 0; m < kMaxSlots; m++) {
-                const int a = lane + 32 * m;
-                if (32 * m < height && a < height) acc[m] = fma(v, in[a * ldin], acc[m]);
+                if (32 * m < height) {
+                    const double x = lds64(in_m[m] + off);
+                    acc[0][m] = fma(v0, x, acc[0][m]);
+                    acc[1][m] = fma(v1, x, acc[1][m]);
+                    acc[2][m] = fma(v2, x, acc[2][m]);
+                }
             }
         }
 #pragma unroll
         for (int m = 0; m < kMaxSlots; m++) {
             const int a = lane + 32 * m;
-            if (a < height) OUT[a * ldout + c] = acc[m];
-        }
-    }
-}
-// OUT[i][c] = sum over the nonzeros (a, v) of row i of J of  v * IN[a][c]          (OUT: intdim x width): OUT = J IN
-__device__ __forceinline__ void spmm_Jrow(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
-                                          double * OUT, int ldout) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < sp.intdim; i += nwarps) {
-        double acc[kMaxSlots];
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
-        for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) {
-            const double v = Jv[p];
-            const double * in = IN + sp.nz_col[p] * ldin;
-#pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                const int c = lane + 32 * m;
-                if (32 * m < width && c < width) acc[m] = fma(v, in[c], acc[m]);
+            if (a < height) {
+                double * o = OUT + a * ldout + 3 * Bc;
+                o[0] = acc[0][m]; o[1] = acc[1][m]; o[2] = acc[2][m];
             }
-        }
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int c = lane + 32 * m;
-            if (c < width) OUT[i * ldout + c] = acc[m];
-        }
-    }
-}
-// OUT[i][j] = sum over the nonzeros (c, v) of row j of J of  IN[i][c] * v          (OUT: height x intdim): OUT = IN J^T
-__device__ __forceinline__ void spmm_JrowT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
-                                           double * OUT, int ldout) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < sp.intdim; j += nwarps) {
-        double acc[kMaxSlots];
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) acc[m] = 0.0;
-        for (int p = sp.nz_ptr[j]; p < sp.nz_ptr[j + 1]; p++) {
-            const double v = Jv[p];
-            const double * in = IN + sp.nz_col[p];
-#pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                const int i = lane + 32 * m;
-                if (32 * m < height && i < height) acc[m] = fma(v, in[i * ldin], acc[m]);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int i = lane + 32 * m;
-            if (i < height) OUT[i * ldout + j] = acc[m];
         }
     }
 }
 
-// (term, direction) second-derivative tasks of geometry `rg` into the slots, weights w[row] * sign * coef; the
-// threads beyond the task list evaluate the J rows of the NEXT geometry meanwhile (rg_next == nullptr: none)
+// (term, direction) second-derivative tasks of geometry `rg` into the slots, weights w[row] * sign * coef, and the J
+// rows of the NEXT geometry (rg_next == nullptr: none). The tasks come as warp steps of 32 same-kind tasks (uniform
+// control flow) that a static schedule built with the table deals out to the block's warps by estimated cost, so the
+// phase lasts about (total cost / warps) instead of (rounds x the most expensive kind).
 template <bool HAS5>
 __device__ __forceinline__ void run_tasks(const SparseProgram & sp, const double * rg, const double * weight, double sign, double * slots,
                                           const double * rg_next, double * Jv_next) {
-    const int njrow = rg_next ? sp.njrow : 0;
-    for (int k = threadIdx.x; k < sp.nktasks + njrow; k += blockDim.x) {
-        if (k < sp.nktasks) {
-            const uint32_t task = sp.ktasks[k];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s = sp.sched_ptr[warp]; s < sp.sched_ptr[warp + 1]; s++) {
+        const uint32_t task = sp.ktasks[32 * sp.sched_step[s] + lane];
+        if (task == 0xffffffffu) continue;
+        if (!(task & 0x80000000u)) {
             const SpTerm & term = sp.terms[task >> 8];
             const int dir = (int)(task & 0xffu);
             SlotSink sink;
             sink.S = slots + term.kslot;
             sink.w = sign * weight[term.pd.out] * term.coef;
             eval_primitive<MODE_KDIR, HAS5>(term.pd, GeomLoader{rg}, sink, dir, dir + 1);
-        } else {
-            const int row = sp.jrow_order[k - sp.nktasks];
-            if (row >= 0) {
-                for (int p = sp.nz_ptr[row]; p < sp.nz_ptr[row + 1]; p++) Jv_next[p] = 0.0;
-                for (int t = sp.row_ptr[row]; t < sp.row_ptr[row + 1]; t++) {
-                    const SpTerm & term = sp.terms[t];
-                    JvSink sink;
-                    sink.Jv = Jv_next; sink.pos = term.pos; sink.coef = term.coef;
-                    eval_primitive<MODE_QJ, HAS5>(term.pd, GeomLoader{rg_next}, sink);
-                }
+        } else if (rg_next != nullptr) {
+            const int row = (int)(task & 0x7fffffffu);
+            for (int p = sp.nz_ptr[row]; p < sp.nz_ptr[row + 1]; p++) Jv_next[p] = 0.0;
+            for (int t = sp.row_ptr[row]; t < sp.row_ptr[row + 1]; t++) {
+                const SpTerm & term = sp.terms[t];
+                JvSink sink;
+                sink.Jv = Jv_next; sink.pos = term.pos; sink.coef = term.coef;
+                eval_primitive<MODE_QJ, HAS5>(term.pd, GeomLoader{rg_next}, sink);
             }
         }
     }
 }
 
-// H[3 A + k][3 B + l] += sum of the block's slots, in table order (no atomics: bit-reproducible)
+// H[3 A + k][3 B + l] += sum of the block's slots, in table order (no atomics: bit-reproducible); one thread per
+// (block, row k), the three columns l together
 __device__ __forceinline__ void gather_slots(const SparseProgram & sp, const double * slots, double * H, int ld) {
-    for (int e = threadIdx.x; e < 9 * sp.ngblk; e += blockDim.x) {
-        const int blk = e / 9, el = e - 9 * blk, k = el / 3, l = el - 3 * k;
+    for (int e = threadIdx.x; e < 3 * sp.ngblk; e += blockDim.x) {
+        const int blk = e / 3, k = e - 3 * blk;
         const uint32_t ab = sp.gk_blk[blk];
-        double s = 0.0;
-        for (uint32_t p = sp.gk_ptr[blk]; p < sp.gk_ptr[blk + 1]; p++) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        const uint32_t p1 = sp.gk_ptr[blk + 1];
+        for (uint32_t p = sp.gk_ptr[blk]; p < p1; p++) {
             const uint32_t src = sp.gk_src[p];
-            s += slots[(src >> 1) + ((src & 1u) ? 3 * l + k : 3 * k + l)];
+            const bool tr = src & 1u;
+            const double * q = slots + (src >> 1) + (tr ? k : 3 * k);
+            const int st = tr ? 3 : 1;
+            s0 += q[0]; s1 += q[st]; s2 += q[2 * st];
         }
-        H[(3 * (ab >> 16) + k) * ld + 3 * (ab & 0xffffu) + l] += s;
+        double * h = H + (3 * (ab >> 16) + k) * ld + 3 * (ab & 0xffffu);
+        h[0] += s0; h[1] += s1; h[2] += s2;
     }
+}
+
+// packed inverse of one geometry (workspace) -> full symmetric Ai[n][ldh], element-wise cp.async (no commit): the
+// expansion travels in the background like the operand matrix
+__device__ __forceinline__ void expand_inverse_async(const double * __restrict__ pk, double * Ai, int n, int ldh) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < n; i += nwarps)
+        for (int j = lane; j <= i; j += kLanes) {
+            const double * src = pk + tri(i) + j;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(Ai + i * ldh + j)), "l"(src) : "memory");
+            if (j != i) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(Ai + j * ldh + i)), "l"(src) : "memory");
+        }
 }
 
 // OP 0: gradient_cart2int_matrix   ainv (workspace)                                  out = M[n][cd]
 // OP 2: Hessian_int2cart           in1 = g_q[n],                in2 = H_q[n][n]      out = H_r[cd][cd]
 // OP 3: Hessian_cart2int           in1 = g_q[n] (workspace), ainv, in2 = H_r[cd][cd] out = H_q[n][n]
-template <int OP, bool HAS5>
+// TABS: the definition tables are copied to shared memory (the usual case; as a template parameter so that every table
+// read is a shared-state-space load). cp.async groups per thread, oldest first: [small inputs of the next geometry]
+// [operand matrix (+ inverse) of the next geometry].
+template <int OP, bool HAS5, bool TABS>
 __global__ void __launch_bounds__(kHessThreads, 1)
 hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const double * __restrict__ in1,
             const double * __restrict__ in2, const double * __restrict__ ainv, const int64_t B, double * __restrict__ out) {
     extern __shared__ __align__(16) double sm[];
     const int n = sp_global.intdim, cd = sp_global.cartdim, ldh = sp_global.ldh;
     const int ntri = (n * (n + 1)) >> 1;
-    const int tab_doubles = sp_global.tab_in_smem ? (sp_global.blob_bytes + 7) / 8 : 0;
+    const int tab_doubles = TABS ? (sp_global.blob_bytes - sp_global.hess_tab_offset + 7) / 8 : 0;
     const HessPlan pl = hess_plan(OP, n, cd, ldh, sp_global.nnz_pad, sp_global.nslots, tab_doubles);
     SparseProgram sp = sp_global;
-    if (sp_global.tab_in_smem) {
+    if (TABS) {
         double * tab = sm + pl.tab;
-        const double * src = reinterpret_cast<const double *>(sp_global.terms);
+        const double * src = reinterpret_cast<const double *>(sp_global.terms);              // first of the common tables
         for (int i = threadIdx.x; i < tab_doubles; i += blockDim.x) tab[i] = src[i];
         const char * base = reinterpret_cast<const char *>(sp_global.terms), * tb = reinterpret_cast<const char *>(tab);
 #define TC_REBASE(field, type) sp.field = reinterpret_cast<const type *>(tb + (reinterpret_cast<const char *>(sp_global.field) - base))
         TC_REBASE(terms, SpTerm); TC_REBASE(row_ptr, int32_t); TC_REBASE(jrow_order, int32_t); TC_REBASE(ktasks, uint32_t);
         TC_REBASE(nz_ptr, uint16_t); TC_REBASE(nz_col, uint16_t); TC_REBASE(col_ptr, uint16_t); TC_REBASE(col_ent, uint32_t);
         TC_REBASE(gk_blk, uint32_t); TC_REBASE(gk_ptr, uint32_t); TC_REBASE(gk_src, uint32_t);
+        TC_REBASE(sched_ptr, uint16_t); TC_REBASE(sched_step, uint16_t);
 #undef TC_REBASE
     }
-    const int ldo = n | 1, ldc = cd | 1;
+    const int ldo = n | 1, ldj = ld_dmma(cd);
     const int rg_buf = even_up(cd), v_buf = even_up(cd > n ? cd : n);
     const int v_len = OP == 0 ? 0 : n;                // g_q in both Hessian transforms
     double * BIG = sm + pl.big, * MID = sm + pl.mid, * THIRD = sm + pl.third;
@@ -683,14 +752,21 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
         double * rgd = rg_of(buf), * vd = v_of(buf);
         const double * rs = r + bb * cd, * vs = in1 + bb * v_len;
         for (int i = threadIdx.x; i < cd; i += blockDim.x)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(rgd + i)), "l"(rs + i) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(rgd + i)), "l"(rs + i) : "memory");
         for (int i = threadIdx.x; i < v_len; i += blockDim.x)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(vd + i)), "l"(vs + i) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(vd + i)), "l"(vs + i) : "memory");
     };
     const int big_count = OP == 2 ? n * n : cd * cd;                       // H_q / H_r of one geometry
-    auto fetch_big = [&](int64_t bb) { if (OP != 0) block_copy_async(in2 + bb * (int64_t)big_count, BIG, big_count); };
+    auto fetch_big = [&](int64_t bb) {
+        if (OP == 2) block_copy_async(in2 + bb * (int64_t)big_count, BIG, big_count);
+        if (OP == 3) {
+            block_rows_async(in2 + bb * (int64_t)big_count, BIG, cd, cd, ldj);       // DMMA operand: padded rows
+            expand_inverse_async(ainv + bb * (int64_t)ntri, THIRD, n, ldh);
+        }
+        if (OP == 0) expand_inverse_async(ainv + bb * (int64_t)ntri, BIG, n, ldh);
+    };
 
-    // prologue: the first geometry's small inputs, its J rows, its operand matrix
+    // prologue: the first geometry's small inputs and J rows; then its successor's small inputs and its own matrices fly
     int cur = 0;
     const int64_t b0 = blockIdx.x;
     if (b0 >= B) return;
@@ -700,89 +776,92 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
     __syncthreads();                                                       // (also publishes the table copy)
     for (int p = sp.nnz + threadIdx.x; p < sp.nnz_pad; p += blockDim.x) { jv_of(0)[p] = 0.0; jv_of(1)[p] = 0.0; }
     eval_J_rows<HAS5>(sp, rg_of(0), jv_of(0), threadIdx.x, blockDim.x);
+    if (b0 + gridDim.x < B) fetch_small(b0 + gridDim.x, 1);
+    cp_async_commit();
     fetch_big(b0);
     cp_async_commit();
 
     for (int64_t b = b0; b < B; b += gridDim.x) {
-        const int64_t bn = b + gridDim.x;
+        const int64_t bn = b + gridDim.x, bnn = bn + gridDim.x;
         const bool has_next = bn < B;
         const double * rg = rg_of(cur), * gvec = v_of(cur), * Jv = jv_of(cur);
-        // group order per thread from here on: [operand matrix of b] is pending; now [small inputs of bn]
-        if (has_next) fetch_small(bn, cur ^ 1);
-        cp_async_commit();
-
+        SPHASE_BEGIN(sm);
         if (OP == 2) {
             double * Hq = BIG, * U = MID, * X = THIRD;
-            cp_async_wait<1>();                                            // H_q of b has landed (the small inputs may still fly)
+            cp_async_wait<0>();                                            // H_q of b (and the small inputs of bn)
             __syncthreads();                                               // + J rows of b (prologue or previous task phase)
+            SPHASE(10);
             spmm_JT(sp, Jv, Hq, n, n, U, ldo);                             // U = J^T H_q        (cd x n)
             __syncthreads();
-            if (has_next) fetch_big(bn);                                   // H_q is dead: the next one travels during the rest
+            SPHASE(11);
+            if (has_next) block_copy_async(in2 + bn * (int64_t)big_count, BIG, big_count);   // H_q is dead: the next one travels during the rest
             cp_async_commit();
             spmm_J(sp, Jv, U, ldo, cd, X, cd);                             // X = U J            (cd x cd)
-            cp_async_wait<1>();                                            // small inputs of bn
             __syncthreads();
+            SPHASE(12);
             run_tasks<HAS5>(sp, rg, gvec, 1.0, U /* slots */, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
             __syncthreads();
+            SPHASE(13);
             gather_slots(sp, U, X, cd);                                    // X += sum_k g_q[k] K[k]
+            if (bnn < B) fetch_small(bnn, cur);                            // (rg / g_q of b are dead after the tasks)
+            cp_async_commit();
             __syncthreads();
+            SPHASE(14);
             block_store_rows(X, out + b * (int64_t)cd * cd, cd, cd, cd);
+            SPHASE(15);
             cur ^= 1;
             continue;                                                      // (the next iteration's first barrier orders the reuse of X)
         }
         if (OP == 0) {
             double * Ai = BIG, * M = MID;
-            // expand the packed inverse: Ai[i][j] = Ai[j][i] = packed[tri(i) + j]
-            const double * pk = ainv + b * (int64_t)ntri;
-            for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
-                for (int j = threadIdx.x & 31; j <= i; j += kLanes) {
-                    const double v = pk[tri(i) + j];
-                    Ai[i * ldh + j] = v;
-                    Ai[j * ldh + i] = v;
-                }
+            cp_async_wait<0>();
             __syncthreads();
             spmm_JT(sp, Jv, Ai, ldh, n, M, n);          // (J^T inv)[c][i] = M[i][c]: stored transposed below
             __syncthreads();
+            if (has_next) fetch_big(bn);
+            cp_async_commit();
             // M^T lives as [cd][n]; write out[i][c] with lanes along c
             double * dst = out + b * (int64_t)n * cd;
             for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
                 for (int c = threadIdx.x & 31; c < cd; c += kLanes) __stcs(dst + (int64_t)i * cd + c, M[c * n + i]);
-            cp_async_wait<0>();
-            __syncthreads();
             if (has_next) eval_J_rows<HAS5>(sp, rg_of(cur ^ 1), jv_of(cur ^ 1), threadIdx.x, blockDim.x);
-            cur ^= 1;
             __syncthreads();
+            if (bnn < B) fetch_small(bnn, cur);
+            cp_async_commit();
+            cur ^= 1;
             continue;
         }
-        // OP 3: H_q = inv (J (H_r - sum_k g_q[k] K[k]) J^T) inv
+        // OP 3: H_q = M (H_r - sum_k g_q[k] K[k]) M^T,  M = inv J  (the reference's order of operations: forming
+        // inv (J H_c J^T) inv instead loses cond(J J^T) in accuracy, measured 5e-10 on the 30-atom chain)
         {
             double * Hc = BIG, * SL = MID, * Ai = THIRD;
-            const double * pk = ainv + b * (int64_t)ntri;
-            for (int i = threadIdx.x >> 5; i < n; i += blockDim.x >> 5)
-                for (int j = threadIdx.x & 31; j <= i; j += kLanes) {
-                    const double v = pk[tri(i) + j];
-                    Ai[i * ldh + j] = v;
-                    Ai[j * ldh + i] = v;
-                }
-            cp_async_wait<0>();                                            // H_r of b and the small inputs of bn
+            cp_async_wait<1>();                                            // the small inputs of bn (the matrices may still fly)
             __syncthreads();
+            SPHASE(20);
             run_tasks<HAS5>(sp, rg, gvec, -1.0, SL, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
+            cp_async_wait<0>();                                            // H_r and the inverse of b
             __syncthreads();
-            gather_slots(sp, SL, Hc, cd);                                  // H_c = H_r - sum_k g_q[k] K[k]
+            SPHASE(21);
+            gather_slots(sp, SL, Hc, ldj);                                 // H_c = H_r - sum_k g_q[k] K[k]
             __syncthreads();
-            double * V = MID;
-            spmm_Jrow(sp, Jv, Hc, cd, cd, V, ldc);                         // V = J H_c           (n x cd)
+            SPHASE(22);
+            double * MT = MID;
+            spmm_JT(sp, Jv, Ai, ldh, n, MT, ldh);                          // M^T = J^T inv       (cd x n; inv is symmetric)
             __syncthreads();
-            double * S = BIG;
-            spmm_JrowT(sp, Jv, V, ldc, n, S, ldh);                         // S = V J^T           (n x n)
+            SPHASE(23);
+            double * T2 = THIRD;
+            block_dgemm<false, false, false>(cd, n, cd, Hc, ldj, MT, ldh, T2, ldh);      // T2 = H_c M^T   (cd x n)
             __syncthreads();
-            double * P = MID;
-            block_dgemm<false, false, false>(n, n, n, Ai, ldh, S, ldh, P, ldh);      // P = inv S
+            SPHASE(24);
+            double * Q = BIG;
+            block_dgemm<true, false, false>(n, n, cd, MT, ldh, T2, ldh, Q, ldh);         // H_q = M T2     (n x n)
             __syncthreads();
-            block_dgemm<false, false, false>(n, n, n, P, ldh, Ai, ldh, S, ldh);      // H_q = P inv   (into S)
-            __syncthreads();
-            block_store_rows(S, out + b * (int64_t)n * n, n, n, ldh);
-            __syncthreads();                                               // the stores have read S: the next H_r may land there
+            SPHASE(25);
+            block_store_rows(Q, out + b * (int64_t)n * n, n, n, ldh);
+            __syncthreads();                                               // the stores have read Q, T2 is dead: the next matrices may land
+            SPHASE(26);
+            if (bnn < B) fetch_small(bnn, cur);
+            cp_async_commit();
             if (has_next) fetch_big(bn);
             cp_async_commit();
             cur ^= 1;
@@ -892,20 +971,69 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         // (padding only pays when the groups are large; many small groups would only lengthen the list)
         if ((int)jrow_order.size() > 2 * n + 64) { jrow_order.assign(order.begin(), order.end()); }
     }
-    // CSC
-    std::vector<uint16_t> col_ptr(cd + 1, 0);
-    std::vector<uint32_t> col_ent(nnz);
+    // warp steps: 32 tasks of one kind each (K tasks of one primitive type; J rows whose first term has one type), and their
+    // longest-processing-time assignment to the block kernel's warps
+    std::vector<uint32_t> step_tasks;
+    std::vector<int> step_cost;
     {
-        std::vector<std::vector<uint32_t>> cols(cd);
-        for (int i = 0; i < n; i++)
-            for (int p = nz_ptr[i]; p < nz_ptr[i + 1]; p++) cols[nz_col[p]].push_back(((uint32_t)i << 16) | (uint32_t)p);
-        int k = 0;
-        for (int c = 0; c < cd; c++) {
-            col_ptr[c] = (uint16_t)k;
-            for (uint32_t e : cols[c]) col_ent[k++] = e;
+        auto flush_group = [&](const std::vector<uint32_t> & grp, int cost) {
+            for (size_t k = 0; k < grp.size(); k += 32) {
+                for (size_t u = 0; u < 32; u++) step_tasks.push_back(k + u < grp.size() ? grp[k + u] : 0xffffffffu);
+                step_cost.push_back(cost);
+            }
+        };
+        std::vector<uint32_t> grp;
+        int gtype = -1, gcost = 0;
+        for (uint32_t task : ktasks) {                          // already sorted by cost, type, direction
+            const PrimDesc & pd = terms[task >> 8].pd;
+            if (pd.type != gtype && !grp.empty()) { flush_group(grp, gcost); grp.clear(); }
+            gtype = pd.type; gcost = 2 * type_cost(pd.type, pd.natoms);
+            grp.push_back(task);
         }
-        col_ptr[cd] = (uint16_t)k;
+        if (!grp.empty()) flush_group(grp, gcost);
+        grp.clear();
+        int prev_cost = -1, prev_type = -1;
+        for (int32_t row : jrow_order) {
+            if (row < 0) continue;
+            const auto & d = t->terms[rows[row][0]];
+            const int cost = type_cost(d.type, d.natoms) * (int)rows[row].size();
+            if ((cost != prev_cost || (int)d.type != prev_type) && !grp.empty()) { flush_group(grp, std::max(prev_cost, 1)); grp.clear(); }
+            prev_cost = cost; prev_type = d.type;
+            grp.push_back(0x80000000u | (uint32_t)row);
+        }
+        if (!grp.empty()) flush_group(grp, std::max(prev_cost, 1));
     }
+    const int hess_warps = kHessThreads / 32;
+    std::vector<uint16_t> sched_ptr(hess_warps + 1, 0), sched_step;
+    {
+        std::vector<int> order(step_cost.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return step_cost[a] > step_cost[b]; });
+        std::vector<std::vector<uint16_t>> per_warp(hess_warps);
+        std::vector<long> load(hess_warps, 0);
+        for (int k : order) {
+            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            per_warp[w].push_back((uint16_t)k);
+            load[w] += step_cost[k];
+        }
+        for (int w = 0; w < hess_warps; w++) {
+            sched_ptr[w] = (uint16_t)sched_step.size();
+            for (uint16_t k : per_warp[w]) sched_step.push_back(k);
+        }
+        sched_ptr[hess_warps] = (uint16_t)sched_step.size();
+    }
+    // compressed column blocks: per atom, the rows that touch it (the atom's three columns share the list)
+    const int natoms = t->natoms;
+    std::vector<uint16_t> col_ptr(natoms + 1, 0);
+    std::vector<uint32_t> col_ent;
+    for (int a = 0; a < natoms; a++) {
+        col_ptr[a] = (uint16_t)col_ent.size();
+        for (int i = 0; i < n; i++) {
+            auto f = atom_pos[i].find(a);
+            if (f != atom_pos[i].end()) col_ent.push_back(((uint32_t)i << 16) | (uint32_t)f->second);
+        }
+    }
+    col_ptr[natoms] = (uint16_t)col_ent.size();
     // J J^T: pairs of rows that share atoms
     std::vector<uint32_t> pair_dest;
     std::vector<std::vector<uint32_t>> pair_lists;
@@ -951,18 +1079,23 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     size_t off = 0;
     auto place = [&](size_t bytes) { const size_t o = off; off += a16(bytes); return o; };
-    const size_t o_terms = place(terms.size() * sizeof(SpTerm)), o_rowptr = place(row_ptr.size() * 4), o_jrow = place(jrow_order.size() * 4),
-                 o_ktasks = place(ktasks.size() * 4), o_nzptr = place(nz_ptr.size() * 2), o_nzcol = place(nz_col.size() * 2 + 2),
-                 o_colptr = place(col_ptr.size() * 2), o_colent = place(col_ent.size() * 4 + 4), o_gkblk = place(gk_blk.size() * 4 + 4),
-                 o_gkptr = place(gk_ptr.size() * 4), o_gksrc = place(gk_src.size() * 4 + 4);
-    const size_t smem_part = off;                              // everything the block kernel reads
+    // order: [pair lists] [common: terms, row structure] [block-kernel tables]; the factor kernel stages the first two
+    // parts in shared memory, the block kernel the last two
     const size_t o_pdest = place(pair_dest.size() * 4), o_pent = place(pair_ent.size() * 4);
+    const size_t common_begin = off;
+    const size_t o_terms = place(terms.size() * sizeof(SpTerm)), o_rowptr = place(row_ptr.size() * 4), o_jrow = place(jrow_order.size() * 4),
+                 o_nzptr = place(nz_ptr.size() * 2), o_nzcol = place(nz_col.size() * 2 + 2);
+    const size_t hess_begin = off;
+    const size_t o_ktasks = place(step_tasks.size() * 4), o_schedptr = place(sched_ptr.size() * 2), o_schedstep = place(sched_step.size() * 2 + 2), o_colptr = place(col_ptr.size() * 2), o_colent = place(col_ent.size() * 4 + 4),
+                 o_gkblk = place(gk_blk.size() * 4 + 4), o_gkptr = place(gk_ptr.size() * 4), o_gksrc = place(gk_src.size() * 4 + 4);
     const size_t total = off + 16;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + o_terms, terms.data(), terms.size() * sizeof(SpTerm));
     std::memcpy(blob.data() + o_rowptr, row_ptr.data(), row_ptr.size() * 4);
     std::memcpy(blob.data() + o_jrow, jrow_order.data(), jrow_order.size() * 4);
-    std::memcpy(blob.data() + o_ktasks, ktasks.data(), ktasks.size() * 4);
+    std::memcpy(blob.data() + o_ktasks, step_tasks.data(), step_tasks.size() * 4);
+    std::memcpy(blob.data() + o_schedptr, sched_ptr.data(), sched_ptr.size() * 2);
+    std::memcpy(blob.data() + o_schedstep, sched_step.data(), sched_step.size() * 2);
     std::memcpy(blob.data() + o_nzptr, nz_ptr.data(), nz_ptr.size() * 2);
     std::memcpy(blob.data() + o_nzcol, nz_col.data(), nz_col.size() * 2);
     std::memcpy(blob.data() + o_colptr, col_ptr.data(), col_ptr.size() * 2);
@@ -986,6 +1119,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     p.row_ptr = reinterpret_cast<const int32_t *>(d + o_rowptr);
     p.jrow_order = reinterpret_cast<const int32_t *>(d + o_jrow);
     p.ktasks = reinterpret_cast<const uint32_t *>(d + o_ktasks);
+    p.sched_ptr = reinterpret_cast<const uint16_t *>(d + o_schedptr);
+    p.sched_step = reinterpret_cast<const uint16_t *>(d + o_schedstep);
     p.nz_ptr = reinterpret_cast<const uint16_t *>(d + o_nzptr);
     p.nz_col = reinterpret_cast<const uint16_t *>(d + o_nzcol);
     p.col_ptr = reinterpret_cast<const uint16_t *>(d + o_colptr);
@@ -998,8 +1133,11 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     p.nterms = (int)terms.size(); p.njrow = (int)jrow_order.size(); p.nktasks = (int)ktasks.size();
     p.nnz = nnz; p.nnz_pad = nnz_pad; p.npairs_pad = npairs_pad; p.maxc = maxc;
     p.ngblk = (int)gk_blk.size(); p.ngsrc = (int)gk_src.size(); p.nslots = nslots;
+    p.natoms = natoms;
     p.intdim = n; p.cartdim = cd; p.ldh = pick_ld_dmma(n);
-    p.blob_bytes = (int32_t)smem_part;
+    p.factor_tab_bytes = (int32_t)hess_begin;
+    p.hess_tab_offset = (int32_t)common_begin;
+    p.blob_bytes = (int32_t)off;
     p.tab_in_smem = 0;
     st.density = (double)nnz / ((double)n * cd);
     sparse_tables()[t] = st;
@@ -1007,14 +1145,24 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     return TCHEM_OK;
 }
 
-template <int OP> const void * hess_fn(bool has5) {
-    return has5 ? reinterpret_cast<const void *>(&hess_kernel<OP, true>) : reinterpret_cast<const void *>(&hess_kernel<OP, false>);
+template <int OP> const void * hess_fn(bool has5, bool tabs) {
+    return tabs ? (has5 ? reinterpret_cast<const void *>(&hess_kernel<OP, true, true>) : reinterpret_cast<const void *>(&hess_kernel<OP, false, true>))
+                : (has5 ? reinterpret_cast<const void *>(&hess_kernel<OP, true, false>) : reinterpret_cast<const void *>(&hess_kernel<OP, false, false>));
 }
 template <int OPF> const void * factor_fn(bool has5) {
     return has5 ? reinterpret_cast<const void *>(&factor_kernel<OPF, true>) : reinterpret_cast<const void *>(&factor_kernel<OPF, false>);
 }
 
 } // namespace
+
+#ifdef TCHEM_SPARSE_PHASES
+extern "C" __attribute__((visibility("default"))) int tchem_debug_sparse_phases(unsigned long long * out32, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out32, g_sparse_phase, sizeof(g_sparse_phase)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_sparse_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 void release_sparse_program(const tchem_ic_table * t) {
     std::lock_guard<std::mutex> lock(sparse_mutex());
@@ -1048,12 +1196,20 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     if (st.density > max_density || st.prog.nnz_pad > 65000 || st.prog.nslots > (1 << 30)) return -1;
     const int ntri = n * (n + 1) / 2;
     // ---- kernel 1 (cart -> int): factor / solve / inverse, one warp per geometry ---------------------------------
-    const size_t fsmem = (size_t)factor_smem_doubles(n, st.prog.nnz_pad) * sizeof(double);
-    if (op != 2 && fsmem + 1024 > (size_t)t->max_smem_optin) return -1;
+    const size_t fwarp = (size_t)even_up(factor_smem_doubles(n, cd, st.prog.nnz_pad)) * sizeof(double);
+    const size_t ftab = (size_t)even_up((st.prog.factor_tab_bytes + 7) / 8) * sizeof(double);
+    int fwarps = 0;
+    if (op != 2) {
+        static const int w_env = [] { const char * e = getenv("TCHEM_FACTOR_WARPS"); return e ? atoi(e) : 6; }();
+        fwarps = std::min(std::max(w_env, 1), 6);
+        while (fwarps > 0 && ftab + fwarps * fwarp + 1024 > (size_t)t->max_smem_optin) fwarps--;
+        if (fwarps < 1) return -1;
+    }
+    const size_t fsmem = ftab + fwarps * fwarp;
     // ---- kernel 2: one block per geometry ---------------------------------------------------------------------------
     size_t hsmem = 0;
     if (op != 1) {
-        HessPlan pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, (st.prog.blob_bytes + 7) / 8);
+        HessPlan pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, (st.prog.blob_bytes - st.prog.hess_tab_offset + 7) / 8);
         st.prog.tab_in_smem = 1;
         if ((size_t)pl.total * sizeof(double) + 1024 > (size_t)t->max_smem_optin) {
             pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, 0);
@@ -1065,17 +1221,15 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     auto launch_factor = [&](int opf, const double * rr, const double * gr, int64_t nb, double * gq, double * ainv) -> int {
         const void * fn = opf == 0 ? factor_fn<0>(t->has5) : factor_fn<1>(t->has5);
         { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
-        int per_sm = 0;
-        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32, fsmem));
-        if (per_sm < 1) per_sm = 1;
-        const int64_t grid = std::min<int64_t>(nb, (int64_t)t->sm_count * per_sm);
+        const int64_t grid = std::min<int64_t>((nb + fwarps - 1) / fwarps, (int64_t)t->sm_count);
         void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&gr, (void *)&nb, (void *)&gq, (void *)&ainv, (void *)&st.status};
-        TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32), args, fsmem, stream));
+        TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32 * fwarps), args, fsmem, stream));
         count_launch(opf == 0 ? "factor_kernel<solve>" : "factor_kernel<inverse>");
         return TCHEM_OK;
     };
     auto launch_hess = [&](int hop, const double * rr, const double * v1, const double * m2, const double * ainv, int64_t nb, double * o) -> int {
-        const void * fn = hop == 0 ? hess_fn<0>(t->has5) : hop == 2 ? hess_fn<2>(t->has5) : hess_fn<3>(t->has5);
+        const bool tabs = st.prog.tab_in_smem != 0;
+        const void * fn = hop == 0 ? hess_fn<0>(t->has5, tabs) : hop == 2 ? hess_fn<2>(t->has5, tabs) : hess_fn<3>(t->has5, tabs);
         { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
         const int64_t grid = std::min<int64_t>(nb, (int64_t)t->sm_count);
         void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&v1, (void *)&m2, (void *)&ainv, (void *)&nb, (void *)&o};

@@ -320,28 +320,56 @@ std::string row_expr(const std::vector<std::pair<double, int>> & row, const char
 bool chain_bulk_eligible(int nt, int sd, int dcap) {
     return nt % 2 == 0 && (nt * sd) % 2 == 0 && nt * (1 + sd) <= dcap;
 }
+// `cart` (chained only): the Jacobian goes out in CARTESIAN coordinates, d SAP / d r = (d SAP / d q) J [NT][CD] - the product
+// callers of the reference form by hand (test/normal_mode/main.cpp:56-61) - with J's rows emitted as literal combinations of
+// the primitives' analytic gradient blocks and every structural zero skipped.
 std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim,
-                             const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks, bool bulk = false) {
+                             const std::vector<std::vector<std::pair<int, int>>> & saps, int dcap, int warps, int blocks, bool bulk = false,
+                             bool cart = false) {
     // terms empty: the SAPSet alone, evaluated on given coordinates x[B][n_ic] (cartdim = n_ic)
     const bool plain = terms.empty();
     std::vector<JitPrim> prims;
     std::vector<std::vector<std::pair<double, int>>> rows;
     if (!plain && !collect(terms, n_ic, prims, rows)) return std::string();
     const int nt = (int)saps.size(), sd = n_ic;
-    const int per_term = 1 + sd;
+    if (cart && (plain || bulk)) return std::string();
+    const int sdo = cart ? cartdim : sd;              // row length of the Jacobian that leaves the kernel
+    const int per_term = 1 + sdo;
     if (per_term > dcap) return std::string();
     const int tper = chain_terms_per_chunk(nt, per_term, dcap);
     if (bulk && !chain_bulk_eligible(nt, sd, dcap)) return std::string();
     std::ostringstream o;
-    o << "#define NT " << nt << "\n#define SD " << sd << "\n";
+    o << "#define NT " << nt << "\n#define SD " << sd << "\n#define SDO " << sdo << "\n";
     if (bulk)
         emit_prologue(o, "tchem_jit_chain_bulk", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
                       cartdim, sd, warps, blocks, prims, plain ? sd : 0, 32 * nt * per_term);
     else
-    emit_prologue(o, "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
+    emit_prologue(o, cart ? "tchem_jit_chain_cart" : "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
                   cartdim, std::max(tper * per_term, sd), warps, blocks, prims, plain ? sd : 0);
     for (size_t p = 0; p < prims.size(); p++)
-        if (!emit_prim(o, prims[p], p, false, "        ")) return std::string();
+        if (!emit_prim(o, prims[p], p, cart, "        ")) return std::string();
+    // cart: the structurally nonzero elements of J as named values J<row>_<col>
+    std::vector<std::vector<char>> jnz(n_ic, std::vector<char>(cartdim, 0));
+    if (cart) {
+        static const char * comp[3] = {".x", ".y", ".z"};
+        for (int i = 0; i < n_ic; i++) {
+            std::vector<std::string> expr(cartdim);
+            for (auto & t : rows[i]) {
+                const JitPrim & pr = prims[t.second];
+                for (int a = 0; a < pr.natoms; a++)
+                    for (int c = 0; c < 3; c++) {
+                        std::string & e = expr[3 * pr.atoms[a] + c];
+                        const std::string v = "j" + std::to_string(t.second) + "[" + std::to_string(a) + "]" + comp[c];
+                        e = e.empty() ? hexd(t.first) + " * " + v : "fma(" + hexd(t.first) + ", " + v + ", " + e + ")";
+                    }
+            }
+            for (int c = 0; c < cartdim; c++)
+                if (!expr[c].empty()) {
+                    jnz[i][c] = 1;
+                    o << "        const double J" << i << "_" << c << " = " << expr[c] << ";\n";
+                }
+        }
+    }
     std::vector<int> maxpow(sd, 0);
     for (auto & t : saps) for (auto & u : t) maxpow[u.first] = std::max(maxpow[u.first], u.second);
     for (int i = 0; i < n_ic; i++) {
@@ -410,12 +438,28 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
                     if (wi != ui) e += " * " + power(saps[t][wi].first, saps[t][wi].second);
                 g[u.first] = e;
             }
-            for (int c = 0; c < sd; c++)
-                o << "            D[" << n + stage_row((t - t0) * sd + c, n * sd) << " * KPAD + lane] = " << g[c] << ";\n";
+            if (cart) {
+                // d/dr_c = sum_k (d/dq_k) J[k][c] over the rows k where both factors are structurally nonzero
+                for (int k = 0; k < sd; k++)
+                    if (g[k] != "0.0") o << "            const double g" << t << "_" << k << " = " << g[k] << ";\n";
+                std::vector<std::string> gc(sdo, "0.0");
+                for (int c = 0; c < sdo; c++) {
+                    std::string e;
+                    for (int k = 0; k < sd; k++) {
+                        if (g[k] == "0.0" || !jnz[k][c]) continue;
+                        const std::string gk = "g" + std::to_string(t) + "_" + std::to_string(k), jk = "J" + std::to_string(k) + "_" + std::to_string(c);
+                        e = e.empty() ? gk + " * " + jk : "fma(" + gk + ", " + jk + ", " + e + ")";
+                    }
+                    if (!e.empty()) gc[c] = e;
+                }
+                g = gc;
+            }
+            for (int c = 0; c < sdo; c++)
+                o << "            D[" << n + stage_row((t - t0) * sdo + c, n * sdo) << " * KPAD + lane] = " << g[c] << ";\n";
         }
         o << "            __syncwarp();\n"
           << "            if (y) copy_rows<" << n << ", NT>(D, y + b0 * NT + " << t0 << ", ntile, lane);\n"
-          << "            if (J) copy_out<" << n * sd << ", NT * SD>(D + " << n << " * KPAD, J + b0 * (NT * SD) + " << t0 * sd << ", ntile, lane);\n"
+          << "            if (J) copy_out<" << n * sdo << ", NT * SDO>(D + " << n << " * KPAD, J + b0 * (NT * SDO) + " << t0 * sdo << ", ntile, lane);\n"
           << "            __syncwarp();\n        }\n";
     }
     o << "    }\n}\n";
@@ -887,22 +931,24 @@ void jit_finish(JitKernel & jk, const std::string & src, const char * name, size
 
 // chained r -> q -> SAPSet through a kernel specialised to (IntCoordSet, SAPSet); -1: not eligible
 int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
-                     double * q, double * y, double * J, cudaStream_t stream) {
+                     double * q, double * y, double * J, cudaStream_t stream, bool cart) {
     static const int min_batch = env_int("TCHEM_JIT_MIN_BATCH", 16384), enabled = env_int("TCHEM_JIT", 1);
     static const bool debug = getenv("TCHEM_DEBUG") != nullptr;
     // t == nullptr: the SAPSet alone on given coordinates (r = x[B][sumdim])
     if (!enabled || std::max(B, g_batch_hint) < min_batch || (int64_t)st->nterms * (1 + st->sumdim) > 4096) return -1;
     if (t ? (t->has5 || t->cartdim > 36 || t->terms.size() > 128) : st->sumdim > 36) return -1;
+    if (cart && (!t || (int64_t)st->nterms * (1 + t->cartdim) > 4096)) return -1;
     const int in_dim = t ? t->cartdim : st->sumdim;
     // one chunk when the whole set fits ~128 staged entries: a chunk that ends inside a geometry's
     // y / J block leaves 32-byte sectors half written, and partial-sector writes cost DRAM
     // read-modify-write traffic (measured on C5: 2 chunks 3.55 ms, 1 chunk 1.79 ms)
-    const int per_term = 1 + st->sumdim, nt = st->nterms;
-    const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, 76));
+    const int per_term = 1 + (cart ? t->cartdim : st->sumdim), nt = st->nterms;
+    const int dcap = env_int("TCHEM_JIT_DCAP", nt * per_term <= 128 ? nt * per_term : std::max(per_term, cart ? 120 : 76));
     static const int want_bulk = env_int("TCHEM_JIT_BULK", 1);
     // single-chunk sets: whole-tile TMA bulk stores (16-byte aligned results, even row lengths)
     int variant = want_bulk && chain_bulk_eligible(nt, st->sumdim, dcap)
                   && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 1 : 0;
+    if (cart) variant = 2;                         // variant 2: Cartesian Jacobian (warp copy-out)
     JitKernel * k = nullptr;
     for (; variant >= 0; variant--) {
         std::lock_guard<std::mutex> lock(jit_mutex());
@@ -914,12 +960,13 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
             jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
             const int tper = chain_terms_per_chunk(nt, per_term, dcap);
             static const std::vector<tchem_invdisp_t> no_terms;
-            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks, variant == 1);
+            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks, variant == 1, variant == 2);
             const size_t smem = variant == 1 ? (size_t)jk.warps * chain_warp_doubles(in_dim, st->sumdim, 32 * nt * per_term) * sizeof(double)
                                              : (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
-            jit_finish(jk, src, variant == 1 ? "tchem_jit_chain_bulk" : "tchem_jit_chain", smem, st->max_smem_optin, debug);
+            jit_finish(jk, src, variant == 1 ? "tchem_jit_chain_bulk" : variant == 2 ? "tchem_jit_chain_cart" : "tchem_jit_chain", smem, st->max_smem_optin, debug);
         }
         if (!jk.failed) { k = &jk; break; }
+        if (cart) break;                           // no other specialised flavour computes the Cartesian product
     }
     if (!k) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem: the specialised chained kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     const int64_t ntiles = (B + 31) / 32;
@@ -927,7 +974,7 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
     long long Bll = B;
     void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
-    count_launch(variant == 1 ? "tchem_jit_chain_bulk" : "tchem_jit_chain");
+    count_launch(variant == 1 ? "tchem_jit_chain_bulk" : variant == 2 ? "tchem_jit_chain_cart" : "tchem_jit_chain");
     return TCHEM_OK;
 }
 
@@ -1101,6 +1148,30 @@ int64_t tchem_sap_jit_source(const int32_t * term_ptr, const int32_t * coords, i
     const int dcap = n_terms * per_term <= 128 ? n_terms * per_term : std::max(per_term, 76);
     static const std::vector<tchem_invdisp_t> no_terms;
     const std::string s = jit_chain_source(no_terms, sd, sd, saps, dcap, bulk ? 2 : 4, bulk ? 4 : 2, bulk != 0);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+int64_t tchem_ic_sap_jit_cart_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, const int32_t * term_ptr,
+                                     const int32_t * coords, int n_sap, const int32_t * dims, int n_irreducibles, char * buf, int64_t capacity) {
+    if (!terms || !term_ptr || !dims || n_terms <= 0 || n_sap <= 0 || n_irreducibles <= 0) return 0;
+    std::vector<int> offset(n_irreducibles + 1, 0);
+    for (int i = 0; i < n_irreducibles; i++) offset[i + 1] = offset[i] + dims[i];
+    if (offset[n_irreducibles] != n_ic) return 0;
+    std::vector<std::vector<std::pair<int, int>>> saps(n_sap);
+    for (int t = 0; t < n_sap; t++) {
+        std::map<int, int> powers;
+        for (int c = term_ptr[t]; c < term_ptr[t + 1]; c++) powers[offset[coords[2 * c]] + coords[2 * c + 1]]++;
+        for (auto & kv : powers) saps[t].push_back({kv.first, kv.second});
+    }
+    const int per_term = 1 + cartdim;
+    const int dcap = n_sap * per_term <= 128 ? n_sap * per_term : std::max(per_term, 120);
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    const std::string s = jit_chain_source(v, n_ic, cartdim, saps, dcap, 4, 2, false, true);
     if (buf && capacity > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
         std::memcpy(buf, s.data(), n);

@@ -19,7 +19,7 @@
 namespace tchem_b200 {
 
 int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
-                     double * q, double * y, double * J, cudaStream_t stream);
+                     double * q, double * y, double * J, cudaStream_t stream, bool cart = false);
 void release_jit_sap(const tchem_sap_table * t);
 int launch_jit_sap_hess(const tchem_sap_table * st, const double * x, int64_t B, double * K, cudaStream_t stream);
 extern thread_local int64_t g_batch_hint;

@@ -1,0 +1,128 @@
+// Chained CARTESIAN derivatives of a SAPSet evaluated on internal coordinates:
+//   dy/dr   [B][NSAP][cartdim]          = (dSAP/dq) J
+//   d2y/dr2 [B][NSAP][cartdim][cartdim] = J^T (d2SAP/dq2) J + sum_k (dSAP/dq_k) K[k]
+// The reference has no entry point for this: its callers compose SAPSet::Jacobian_ / Jacobian2nd_
+// (source/polynomial/SAPSet.cpp:178-201, :243-276) with IntCoordSet::compute_IC_J / compute_IC_J_K
+// (source/IC/IntCoordSet.cpp:147-175) by hand (test/normal_mode/main.cpp:56-61).
+//
+// First order, large batches of small molecules: ONE kernel specialised to the (IntCoordSet, SAPSet) pair
+// (jit.cu, tchem_jit_chain_cart) - q, J and dSAP/dq never leave the chip. Everything else (small batches, large
+// molecules, the second order) is composed from the library's own kernels through a stream-ordered workspace,
+// slice by slice, plus the two contraction kernels below.
+#include <algorithm>
+#include <cstdlib>
+
+#include "ic_table.h"
+#include "sap_table.h"
+
+namespace tchem_b200 {
+
+int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const double * r, int64_t B,
+                     double * q, double * y, double * J, cudaStream_t stream, bool cart);
+
+namespace {
+
+// dydr[b][t][c] = sum_k g[b][t][k] J[b][k][c]; one thread per output element, consecutive threads along c
+__global__ void __launch_bounds__(256)
+chain_cart_first_kernel(const double * __restrict__ g, const double * __restrict__ J, int64_t B, int nt, int n, int cd,
+                        double * __restrict__ out) {
+    const int64_t total = B * nt * cd;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cd);
+        const int64_t bt = e / cd;
+        const int64_t b = bt / nt;
+        const double * gp = g + bt * n, * Jp = J + b * n * cd + c;
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s = fma(gp[k], Jp[(int64_t)k * cd], s);
+        out[e] = s;
+    }
+}
+
+// out[b][t][a][c] = sum_kl J[b][k][a] H[b][t][k][l] J[b][l][c] + sum_k g[b][t][k] K[b][k][a][c]
+__global__ void __launch_bounds__(256)
+chain_cart_second_kernel(const double * __restrict__ g, const double * __restrict__ H, const double * __restrict__ J,
+                         const double * __restrict__ K, int64_t B, int nt, int n, int cd, double * __restrict__ out) {
+    const int64_t total = B * nt * cd * cd;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cd);
+        const int a = (int)((e / cd) % cd);
+        const int64_t bt = e / ((int64_t)cd * cd);
+        const int64_t b = bt / nt;
+        const double * gp = g + bt * n, * Hp = H + bt * n * n, * Jb = J + b * n * cd, * Kb = K + b * (int64_t)n * cd * cd + (int64_t)a * cd + c;
+        double s = 0.0;
+        for (int k = 0; k < n; k++) {
+            double u = 0.0;                                    // (H J)[k][c]
+            for (int l = 0; l < n; l++) u = fma(Hp[k * n + l], Jb[l * cd + c], u);
+            s = fma(Jb[k * cd + a], u, s);
+            s = fma(gp[k], Kb[(int64_t)k * cd * cd], s);
+        }
+        out[e] = s;
+    }
+}
+
+} // namespace
+} // namespace tchem_b200
+
+using namespace tchem_b200;
+
+extern "C" int tchem_ic_sap_eval_cart(const tchem_ic_table * ic, const tchem_sap_table * sap, const double * r, int64_t B,
+                                      double * y, double * dydr, double * d2ydr2, tchem_stream_t stream_) {
+    if (!ic || !sap) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_cart: null table");
+    if (ic->intdim != sap->sumdim)
+        return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_cart: x must have a same dimension as the coordinates (intdim != sum of dimensions)");
+    if (ic->device != sap->device) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_cart: tables live on different devices");
+    if (B < 0) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_cart: negative batch");
+    if (B == 0) return TCHEM_OK;
+    if (!r || (!y && !dydr && !d2ydr2)) return set_error(TCHEM_EINVAL, "tchem_ic_sap_eval_cart: null argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DeviceGuard guard(ic->device);
+    if (!guard.ok) return set_error(TCHEM_ECUDA, "cudaSetDevice failed");
+    const int n = ic->intdim, cd = ic->cartdim, nt = sap->nterms;
+    bool first_done = false;
+    if (dydr) {
+        const int rc = launch_jit_chain(sap, ic, r, B, nullptr, y, dydr, stream, true);
+        if (rc != -1 && rc != TCHEM_OK) return rc;
+        first_done = rc == TCHEM_OK;
+    }
+    if (first_done && !d2ydr2) return TCHEM_OK;
+    // composition through a workspace: q | dSAP/dq | J [| K | d2SAP/dq2] per geometry, slices of at most ~256 MB
+    const bool second = d2ydr2 != nullptr;
+    const size_t per_geom = (size_t)n + (size_t)nt * n + (size_t)n * cd + (second ? (size_t)n * cd * cd + (size_t)nt * n * n : 0);
+    static const size_t budget = [] { const char * e = getenv("TCHEM_CART_WORKSPACE_MB"); return (size_t)(e ? atoi(e) : 256) << 20; }();
+    int64_t slice = (int64_t)std::max<size_t>(1, budget / (per_geom * sizeof(double)));
+    slice = std::min<int64_t>(slice, B);
+    double * ws = nullptr;
+    if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)slice * per_geom * sizeof(double), stream) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(TCHEM_ENOMEM, "tchem_ic_sap_eval_cart: cannot allocate the workspace");
+    }
+    double * q_ws = ws, * g_ws = q_ws + (size_t)slice * n, * J_ws = g_ws + (size_t)slice * nt * n;
+    double * K_ws = second ? J_ws + (size_t)slice * n * cd : nullptr;
+    double * H_ws = second ? K_ws + (size_t)slice * n * cd * cd : nullptr;
+    int rc = TCHEM_OK;
+    for (int64_t b0 = 0; b0 < B && rc == TCHEM_OK; b0 += slice) {
+        const int64_t nb = std::min<int64_t>(slice, B - b0);
+        const double * rr = r + b0 * cd;
+        rc = tchem_ic_sap_eval(ic, sap, rr, nb, q_ws, (y && !first_done) ? y + b0 * nt : nullptr, g_ws, stream_);
+        if (rc == TCHEM_OK) rc = tchem_ic_eval(ic, rr, nb, nullptr, J_ws, K_ws, 0, stream_);
+        if (rc == TCHEM_OK && dydr && !first_done) {
+            const int64_t total = nb * nt * cd;
+            const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ic->sm_count * 8);
+            chain_cart_first_kernel<<<grid, 256, 0, stream>>>(g_ws, J_ws, nb, nt, n, cd, dydr + b0 * nt * cd);
+            count_launch("chain_cart_first_kernel");
+        }
+        if (rc == TCHEM_OK && second) {
+            rc = tchem_sap_jacobian2nd(sap, q_ws, nb, H_ws, stream_);
+            if (rc == TCHEM_OK) {
+                const int64_t total = nb * nt * cd * cd;
+                const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ic->sm_count * 8);
+                chain_cart_second_kernel<<<grid, 256, 0, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd, d2ydr2 + b0 * (int64_t)nt * cd * cd);
+                count_launch("chain_cart_second_kernel");
+            }
+        }
+        if (rc == TCHEM_OK && cudaGetLastError() != cudaSuccess) rc = set_error(TCHEM_ECUDA, "tchem_ic_sap_eval_cart: kernel launch failed");
+    }
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+

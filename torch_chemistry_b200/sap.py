@@ -179,3 +179,27 @@ class SAPSet:
                                             _stream_ptr(self.device)))
         outs = [y, J] + ([q] if return_q else [])
         return tuple(o if batched else o[0] for o in outs)
+
+    def chained_cart(self, intcoordset, r, second_order=False):
+        """r -> (y, dy/dr[, d2y/dr2]): the SAP values and their CARTESIAN derivatives
+        dy/dr = (dSAP/dq) J and d2y/dr2 = J^T (d2SAP/dq2) J + sum_k (dSAP/dq_k) K[k] - what callers of the reference
+        compose by hand (test/normal_mode/main.cpp:56-61; SAPSet.cpp:178-201, :243-276, IntCoordSet.cpp:147-175).
+        First order on large batches of small molecules is one pair-specialised kernel."""
+        if not isinstance(intcoordset, IntCoordSet):
+            raise ValueError("tchem::polynomial::SAPSet::chained_cart: needs an IntCoordSet")
+        r2, batched = intcoordset._prep(r, "compute_IC_J")
+        host = not r2.is_cuda
+        rd = r2.to(self.device)
+        B, nt, cd = rd.shape[0], self.nterms, intcoordset.cartdim
+        kw = dict(dtype=torch.float64, device=self.device)
+        y = torch.empty((B, nt), **kw)
+        g = torch.empty((B, nt, cd), **kw)
+        h = torch.empty((B, nt, cd, cd), **kw) if second_order else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
+        if B > 0:
+            check(lib.tchem_ic_sap_eval_cart(intcoordset._handle, self._handle, ptr(rd), B, ptr(y), ptr(g), ptr(h),
+                                             _stream_ptr(self.device)))
+        outs = [y, g] + ([h] if second_order else [])
+        if host:
+            outs = [o.cpu() for o in outs]
+        return tuple(o if batched else o[0] for o in outs)
