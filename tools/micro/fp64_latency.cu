@@ -20,6 +20,24 @@ __global__ void dfma_chain(double * out, int iters, long long * cycles) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
+template <int ILP>
+__global__ void dmma_chain(double * out, int iters, long long * cycles) {
+    double c0[ILP], c1[ILP];
+    for (int i = 0; i < ILP; i++) { c0[i] = threadIdx.x * 1e-3 + i; c1[i] = 1.0; }
+    const double a = 1.0000001, b = 0.999999;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    const long long t1 = clock64();
+    double s = 0.0;
+    for (int i = 0; i < ILP; i++) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
 __global__ void rsqrt_chain(double * out, int iters, long long * cycles) {
     double a = 2.0 + threadIdx.x;
     const long long t0 = clock64();
@@ -64,6 +82,13 @@ int main() {
     RUN("DFMA 8 chains, 16 warps", dfma_chain<8>, 1, 512, 8)
     RUN("DFMA 8 chains, 32 warps", dfma_chain<8>, 1, 1024, 8)
     RUN("DFMA 8 chains, 32 warps x 148 blocks", dfma_chain<8>, 148, 1024, 8)
+    RUN("DMMA m8n8k4 dependent chain, 1 warp", dmma_chain<1>, 1, 32, 1)
+    RUN("DMMA 2 independent accumulators, 1 warp", dmma_chain<2>, 1, 32, 2)
+    RUN("DMMA 4 independent accumulators, 1 warp", dmma_chain<4>, 1, 32, 4)
+    RUN("DMMA 8 independent accumulators, 1 warp", dmma_chain<8>, 1, 32, 8)
+    RUN("DMMA 4 accumulators, 4 warps (1 per SMSP)", dmma_chain<4>, 1, 128, 4)
+    RUN("DMMA 4 accumulators, 8 warps", dmma_chain<4>, 1, 256, 4)
+    RUN("DMMA 4 accumulators, 16 warps", dmma_chain<4>, 1, 512, 4)
     RUN("rsqrt(double) + add dependent chain", rsqrt_chain, 1, 32, 1)
     RUN("shfl (double) dependent chain", shfl_chain, 1, 32, 1)
     RUN("LDS dependent chain (pointer chase)", lds_chain, 1, 32, 1)

@@ -176,6 +176,49 @@ __device__ __forceinline__ void eval_J_rows(const SparseProgram & sp, const doub
 //    travel by shuffle;
 //  * trailing update A[i][j] -= sum_c L[i][c] L[j][c] by 8 x 8 tiles (I >= J), two DMMAs each.
 // rdiag[j] = 1 / L[j][j]. Returns false when a pivot is not positive (NaN included).
+// panel of 8 columns starting at j0, NS = row slots in use (rows j0 + lane + 32 m): registers only
+template <int NS>
+__device__ __forceinline__ bool warp_potrf_panel(double * A, int n, int last, int j0, int bs, double * rdiag, int lane) {
+    double a[NS][kNB];
+    bool ok = true;
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+        const int i = j0 + lane + 32 * m;
+        const double * Ai = A + tri(min(i, last)) + j0;
+        const int cmax = i > last ? -1 : i == n ? bs - 1 : min(i - j0, bs - 1);       // last stored panel column of the row
+#pragma unroll
+        for (int c = 0; c < kNB; c++) a[m][c] = c <= cmax ? Ai[c] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < kNB; c++) {
+        if (c < bs) {
+            const double d = __shfl_sync(kFull, a[0][c], c);
+            ok = ok && d > 0.0;
+            double rs = rsqrt(d);
+            rs = fma(0.5 * rs, fma(-d * rs, rs, 1.0), rs);              // one Newton step: correctly rounded in all but rare cases
+            if (lane == 0) rdiag[j0 + c] = rs;
+#pragma unroll
+            for (int m = 0; m < NS; m++) a[m][c] *= rs;                 // the pivot's own lane: d / sqrt(d) = sqrt(d)
+#pragma unroll
+            for (int c2 = c + 1; c2 < kNB; c2++) {
+                const double t = __shfl_sync(kFull, a[0][c], c2);       // L[j0 + c2][j0 + c]  (columns >= bs: zeros, harmless)
+#pragma unroll
+                for (int m = 0; m < NS; m++) a[m][c2] = fma(-a[m][c], t, a[m][c2]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+        const int i = j0 + lane + 32 * m;
+        double * Ai = A + tri(min(i, last)) + j0;
+        const int cmax = i > last ? -1 : i == n ? bs - 1 : min(i - j0, bs - 1);
+#pragma unroll
+        for (int c = 0; c < kNB; c++)
+            if (c <= cmax) Ai[c] = a[m][c];
+    }
+    return ok;
+}
+
 __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border, double * rdiag, int lane) {
     const int last = border ? n : n - 1;
     const int gid = lane >> 2, tig = lane & 3;
@@ -183,49 +226,12 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
     for (int j0 = 0; j0 < n; j0 += kNB) {
         const int bs = min(kNB, n - j0);
         const int nrows = last - j0 + 1;
-        double a[kMaxSlots][kNB];
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int i = j0 + lane + 32 * m;
-            const double * Ai = A + tri(min(i, last)) + j0;
-#pragma unroll
-            for (int c = 0; c < kNB; c++) {
-                const bool valid = i <= last && c < bs && (j0 + c <= i || i == n);
-                a[m][c] = valid ? Ai[c] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < kNB; c++) {
-            if (c < bs) {
-                const double d = __shfl_sync(kFull, a[0][c], c);
-                ok = ok && d > 0.0;
-                double rs = rsqrt(d);
-                rs = fma(0.5 * rs, fma(-d * rs, rs, 1.0), rs);          // one Newton step: correctly rounded in all but rare cases
-                if (lane == 0) rdiag[j0 + c] = rs;
-#pragma unroll
-                for (int m = 0; m < kMaxSlots; m++)
-                    if (32 * m < nrows) a[m][c] *= rs;                  // the pivot's own lane: d / sqrt(d) = sqrt(d)
-#pragma unroll
-                for (int c2 = c + 1; c2 < kNB; c2++) {
-                    if (c2 < bs) {
-                        const double t = __shfl_sync(kFull, a[0][c], c2);   // L[j0 + c2][j0 + c]
-#pragma unroll
-                        for (int m = 0; m < kMaxSlots; m++)
-                            if (32 * m < nrows) a[m][c2] = fma(-a[m][c], t, a[m][c2]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
-            const int i = j0 + lane + 32 * m;
-            double * Ai = A + tri(min(i, last)) + j0;
-#pragma unroll
-            for (int c = 0; c < kNB; c++) {
-                const bool valid = i <= last && c < bs && (j0 + c <= i || i == n);
-                if (valid) Ai[c] = a[m][c];
-            }
-        }
+        bool pok;
+        if (nrows <= 32)      pok = warp_potrf_panel<1>(A, n, last, j0, bs, rdiag, lane);
+        else if (nrows <= 64) pok = warp_potrf_panel<2>(A, n, last, j0, bs, rdiag, lane);
+        else if (nrows <= 96) pok = warp_potrf_panel<3>(A, n, last, j0, bs, rdiag, lane);
+        else                  pok = warp_potrf_panel<4>(A, n, last, j0, bs, rdiag, lane);
+        ok = ok && pok;
         __syncwarp();
         const int t0 = j0 + bs;
         if (t0 < n) {                                   // (bs == 8 here: only the last panel can be narrower)
@@ -234,17 +240,20 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
                 const double * Li = A + tri(ic) + j0 + tig;
                 const double a0 = Li[0], a1 = Li[4];                   // A fragments of the two k-steps: L[i][j0 + tig (+ 4)]
                 double * Ci = A + tri(ic) + 2 * tig;
+                const int jmax = i <= last ? min(i, n - 1) : -1;
                 const int jend = min(I + 8, n);
+                // B fragments: L[J + gid][j0 + tig (+ 4)]; the row pointer advances by tri(j + 8) - tri(j) = 8 j + 36
+                int jb = t0 + gid;
+                const double * Lj = A + tri(min(jb, n - 1)) + j0 + tig;
                 for (int J = t0; J < jend; J += 8) {
-                    const int jb = min(J + gid, n - 1);
-                    const double * Lj = A + tri(jb) + j0 + tig;
                     double c0 = 0.0, c1 = 0.0;
                     dmma(c0, c1, a0, Lj[0]);
                     dmma(c0, c1, a1, Lj[4]);
                     const int j = J + 2 * tig;
-                    const int jmax = min(i, n - 1);
-                    if (i <= last && j <= jmax) Ci[J] -= c0;
-                    if (i <= last && j + 1 <= jmax) Ci[J + 1] -= c1;
+                    if (j <= jmax) Ci[J] -= c0;
+                    if (j + 1 <= jmax) Ci[J + 1] -= c1;
+                    Lj += jb + 8 < n ? 8 * jb + 36 : 0;                // (rows past the end: stay on a valid row, results unused)
+                    jb += 8;
                 }
             }
             __syncwarp();
@@ -330,10 +339,22 @@ __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const doubl
         const double * Lr = A + tri(ri) + tig;
         for (int J = 0; J < i0; J += 8) {
             double t0 = 0.0, t1 = 0.0;
-            for (int k0 = J; k0 < i0; k0 += 4) {
-                const int kk = k0 + tig, jj = J + gid;
-                const double bv = jj <= kk ? A[tri(kk) + jj] : 0.0;                  // W[k][j], zero above the diagonal
-                dmma(t0, t1, Lr[k0], bv);
+            // k-steps J and J + 4 meet the diagonal of W (zero above it); from J + 8 on every element is stored.
+            // The row pointer of W advances by tri(k + 4) - tri(k) = 4 k + 10.
+            int kk = J + tig;
+            const double * Wk = A + tri(kk) + J + gid;
+            const int jj = J + gid;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const double bv = jj <= kk ? Wk[0] : 0.0;
+                dmma(t0, t1, Lr[kk - tig], bv);
+                Wk += 4 * kk + 10;
+                kk += 4;
+            }
+            for (int k0 = J + 8; k0 < i0; k0 += 4) {
+                dmma(t0, t1, Lr[k0], Wk[0]);
+                Wk += 4 * kk + 10;
+                kk += 4;
             }
             __syncwarp();                                 // rows I, columns >= J have been read by every lane
             Ts[gid * kNB + 2 * tig] = t0;
@@ -367,12 +388,28 @@ __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
         for (int J = 0; J <= i0; J += 8) {
             const int cb = J + gid;
             double c0 = 0.0, c1 = 0.0;
-            for (int k0 = i0; k0 < n; k0 += 4) {
-                const int kk = k0 + tig;
-                const double * Wk = A + tri(min(kk, n - 1));
+            // k-steps i0 and i0 + 4 meet the diagonal block; from i0 + 8 on every element of both fragments is stored
+            // (only rows past the end are masked). Row pointer: tri(k + 4) - tri(k) = 4 k + 10.
+            int kk = i0 + tig;
+            const double * Wk = A + tri(min(kk, n - 1));
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
                 const double av = (kk < n && ra <= kk) ? Wk[ra] : 0.0;
                 const double bv = (kk < n && cb <= kk) ? Wk[cb] : 0.0;
                 dmma(c0, c1, av, bv);
+                if (kk + 4 < n) Wk += 4 * kk + 10;
+                kk += 4;
+            }
+            const int ra_c = min(ra, n - 1);               // rows of the result past the end are never stored: any valid column will do
+            for (int k0 = i0 + 8; k0 + 3 < n; k0 += 4) {
+                dmma(c0, c1, Wk[ra_c], Wk[cb]);
+                Wk += 4 * kk + 10;
+                kk += 4;
+            }
+            if (kk - tig < n && kk - tig >= i0 + 8) {      // tail k-step (n not a multiple of 4)
+                const int kc = min(kk, n - 1);
+                const double * Wt = A + tri(kc);
+                dmma(c0, c1, kk < n ? Wt[ra_c] : 0.0, kk < n ? Wt[cb] : 0.0);
             }
             __syncwarp();
             const int j = J + 2 * tig;
