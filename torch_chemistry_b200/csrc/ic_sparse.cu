@@ -245,15 +245,23 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
                 // B fragments: L[J + gid][j0 + tig (+ 4)]; the row pointer advances by tri(j + 8) - tri(j) = 8 j + 36
                 int jb = t0 + gid;
                 const double * Lj = A + tri(min(jb, n - 1)) + j0 + tig;
-                for (int J = t0; J < jend; J += 8) {
-                    double c0 = 0.0, c1 = 0.0;
-                    dmma(c0, c1, a0, Lj[0]);
-                    dmma(c0, c1, a1, Lj[4]);
+                // two column tiles per pass: four independent DMMAs in flight
+                for (int J = t0; J < jend; J += 16) {
+                    const double b00 = Lj[0], b01 = Lj[4];
+                    const double * Lj2 = Lj + (jb + 8 < n ? 8 * jb + 36 : 0);
+                    const double b10 = Lj2[0], b11 = Lj2[4];
+                    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                    dmma(c0, c1, a0, b00);
+                    dmma(e0, e1, a0, b10);
+                    dmma(c0, c1, a1, b01);
+                    dmma(e0, e1, a1, b11);
                     const int j = J + 2 * tig;
                     if (j <= jmax) Ci[J] -= c0;
                     if (j + 1 <= jmax) Ci[J + 1] -= c1;
-                    Lj += jb + 8 < n ? 8 * jb + 36 : 0;                // (rows past the end: stay on a valid row, results unused)
-                    jb += 8;
+                    if (j + 8 <= jmax) Ci[J + 8] -= e0;            // (the second tile may lie right of the diagonal: nothing stored)
+                    if (j + 9 <= jmax) Ci[J + 9] -= e1;
+                    Lj = Lj2 + (jb + 16 < n ? 8 * (jb + 8) + 36 : 0);
+                    jb += 16;
                 }
             }
             __syncwarp();
@@ -278,29 +286,35 @@ __device__ __forceinline__ void warp_backsolve_packed(const double * A, int n, c
 #pragma unroll
         for (int m = 1; m < kMaxSlots; m++) xb = km == m ? x[m] : xb;
         const int ib = lane + 32 * km;                  // this lane's element of that slot
+        // everything the chain needs is fetched up front (clamped addresses, no divergent branches on the chain):
+        // the block's reciprocal diagonal and, for the lanes inside the block, their column of the 8 x 8 triangle
+        double rd[8], lcol[8];
+        const bool inblk = ib >= k0 && ib < k0 + bs;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int k = min(k0 + c, n - 1);
+            rd[c] = rdiag[k];
+            lcol[c] = (inblk && ib < k0 + c && c < bs) ? A[tri(k) + ib] : 0.0;
+        }
         double xk[8];
 #pragma unroll
         for (int c = 7; c >= 0; c--) {
-            xk[c] = 0.0;
-            if (c < bs) {
-                const int k = k0 + c;
-                xk[c] = __shfl_sync(kFull, xb, kl0 + c) * rdiag[k];
-                if (lane == kl0 + c) xb = xk[c];
-                else if (ib >= k0 && ib < k) xb = fma(-A[tri(k) + ib], xk[c], xb);
-            }
+            const double v = __shfl_sync(kFull, xb, (kl0 + c) & 31) * rd[c];
+            xk[c] = c < bs ? v : 0.0;
+            xb = (lane == kl0 + c && c < bs) ? v : fma(-lcol[c], xk[c], xb);
         }
 #pragma unroll
         for (int m = 0; m < kMaxSlots; m++) {
             if (m == km) x[m] = xb;
-            const int i = lane + 32 * m;
-            if (32 * m < k0 && i < k0) {
+            if (32 * m < k0) {
+                const int i = lane + 32 * m, ic = min(i, k0 - 1);
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
-                    if (c < bs) s0 = fma(A[tri(k0 + c) + i], xk[c], s0);
-                    if (c + 1 < bs) s1 = fma(A[tri(k0 + c + 1) + i], xk[c + 1], s1);
+                    s0 = fma(A[tri(min(k0 + c, n - 1)) + ic], xk[c], s0);            // (xk = 0 beyond the block)
+                    s1 = fma(A[tri(min(k0 + c + 1, n - 1)) + ic], xk[c + 1], s1);
                 }
-                x[m] -= s0 + s1;
+                if (i < k0) x[m] -= s0 + s1;
             }
         }
     }
@@ -310,7 +324,7 @@ __device__ __forceinline__ void warp_backsolve_packed(const double * A, int n, c
 //   D = L[I][I]^-1 (registers, forward substitution, lane & 7 = column),
 //   W[I][J] = -D (L[I][J:i0] W[J:i0][J]) for the column tiles J = 0, 8, .. in ASCENDING order: tile J reads L[I][k >= J]
 //   only, so each finished tile can overwrite its own columns of rows I at once.
-// Ds: 128 doubles of scratch (D, and the tile in transit between the two DMMA products)
+// Ds: 192 doubles of scratch (D, and the two tiles in transit between the DMMA products)
 __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const double * rdiag, double * Ds, int lane) {
     const int gid = lane >> 2, tig = lane & 3;
     double * Ts = Ds + 64;
@@ -337,35 +351,54 @@ __device__ __forceinline__ void warp_trtri_packed(double * A, int n, const doubl
         const double d0 = -Ds[gid * kNB + tig], d1 = -Ds[gid * kNB + 4 + tig];      // A fragments of -D
         const int ri = min(i0 + gid, n - 1);
         const double * Lr = A + tri(ri) + tig;
-        for (int J = 0; J < i0; J += 8) {
-            double t0 = 0.0, t1 = 0.0;
-            // k-steps J and J + 4 meet the diagonal of W (zero above it); from J + 8 on every element is stored.
-            // The row pointer of W advances by tri(k + 4) - tri(k) = 4 k + 10.
+        // two column tiles (J, J + 8) per pass share the A fragments: two independent DMMA chains. Both are computed
+        // before either is written (tile J reads the columns tile J + 8 overwrites).
+        for (int J = 0; J < i0; J += 16) {
+            const bool two = J + 8 < i0;
+            double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
+            // k-steps J and J + 4 meet the diagonal of W (zero above it); from J + 8 on every element of tile J is stored,
+            // from J + 16 on every element of tile J + 8. Row pointer of W: tri(k + 4) - tri(k) = 4 k + 10.
             int kk = J + tig;
             const double * Wk = A + tri(kk) + J + gid;
             const int jj = J + gid;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const double bv = jj <= kk ? Wk[0] : 0.0;
-                dmma(t0, t1, Lr[kk - tig], bv);
+                dmma(t0, t1, Lr[kk - tig], jj <= kk ? Wk[0] : 0.0);
                 Wk += 4 * kk + 10;
                 kk += 4;
             }
-            for (int k0 = J + 8; k0 < i0; k0 += 4) {
-                dmma(t0, t1, Lr[k0], Wk[0]);
-                Wk += 4 * kk + 10;
-                kk += 4;
+            if (two) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const double a = Lr[kk - tig];
+                    dmma(t0, t1, a, Wk[0]);
+                    dmma(u0, u1, a, jj + 8 <= kk ? Wk[8] : 0.0);
+                    Wk += 4 * kk + 10;
+                    kk += 4;
+                }
+                for (int k0 = J + 16; k0 < i0; k0 += 4) {
+                    const double a = Lr[k0];
+                    dmma(t0, t1, a, Wk[0]);
+                    dmma(u0, u1, a, Wk[8]);
+                    Wk += 4 * kk + 10;
+                    kk += 4;
+                }
             }
             __syncwarp();                                 // rows I, columns >= J have been read by every lane
             Ts[gid * kNB + 2 * tig] = t0;
             Ts[gid * kNB + 2 * tig + 1] = t1;
+            Ts[64 + gid * kNB + 2 * tig] = u0;
+            Ts[64 + gid * kNB + 2 * tig + 1] = u1;
             __syncwarp();
-            double r0 = 0.0, r1 = 0.0;
+            double r0 = 0.0, r1 = 0.0, q0 = 0.0, q1 = 0.0;
             dmma(r0, r1, d0, Ts[tig * kNB + gid]);
+            dmma(q0, q1, d0, Ts[64 + tig * kNB + gid]);
             dmma(r0, r1, d1, Ts[(4 + tig) * kNB + gid]);
+            dmma(q0, q1, d1, Ts[64 + (4 + tig) * kNB + gid]);
             if (gid < bs) {
                 double * o = A + tri(i0 + gid) + J + 2 * tig;
                 o[0] = r0; o[1] = r1;
+                if (two) { o[8] = q0; o[9] = q1; }
             }
         }
         __syncwarp();
@@ -385,31 +418,38 @@ __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
     const int gid = lane >> 2, tig = lane & 3;
     for (int i0 = 0; i0 < n; i0 += kNB) {
         const int ra = i0 + gid;
-        for (int J = 0; J <= i0; J += 8) {
+        // two column tiles (J, J + 8) per pass share the A fragments W[k][I]; the pair that holds the diagonal tile comes last
+        for (int J = 0; J <= i0; J += 16) {
+            const bool two = J + 8 <= i0;
             const int cb = J + gid;
-            double c0 = 0.0, c1 = 0.0;
-            // k-steps i0 and i0 + 4 meet the diagonal block; from i0 + 8 on every element of both fragments is stored
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            // k-steps i0 and i0 + 4 meet the diagonal block; from i0 + 8 on every element of the fragments is stored
             // (only rows past the end are masked). Row pointer: tri(k + 4) - tri(k) = 4 k + 10.
             int kk = i0 + tig;
             const double * Wk = A + tri(min(kk, n - 1));
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const double av = (kk < n && ra <= kk) ? Wk[ra] : 0.0;
-                const double bv = (kk < n && cb <= kk) ? Wk[cb] : 0.0;
-                dmma(c0, c1, av, bv);
+                dmma(c0, c1, av, (kk < n && cb <= kk) ? Wk[cb] : 0.0);
+                dmma(e0, e1, av, (two && kk < n && cb + 8 <= kk) ? Wk[cb + 8] : 0.0);
                 if (kk + 4 < n) Wk += 4 * kk + 10;
                 kk += 4;
             }
             const int ra_c = min(ra, n - 1);               // rows of the result past the end are never stored: any valid column will do
+            const int cb2 = two ? cb + 8 : cb;
             for (int k0 = i0 + 8; k0 + 3 < n; k0 += 4) {
-                dmma(c0, c1, Wk[ra_c], Wk[cb]);
+                const double av = Wk[ra_c];
+                dmma(c0, c1, av, Wk[cb]);
+                dmma(e0, e1, av, Wk[cb2]);
                 Wk += 4 * kk + 10;
                 kk += 4;
             }
             if (kk - tig < n && kk - tig >= i0 + 8) {      // tail k-step (n not a multiple of 4)
                 const int kc = min(kk, n - 1);
                 const double * Wt = A + tri(kc);
-                dmma(c0, c1, kk < n ? Wt[ra_c] : 0.0, kk < n ? Wt[cb] : 0.0);
+                const double av = kk < n ? Wt[ra_c] : 0.0;
+                dmma(c0, c1, av, kk < n ? Wt[cb] : 0.0);
+                dmma(e0, e1, av, kk < n ? Wt[cb2] : 0.0);
             }
             __syncwarp();
             const int j = J + 2 * tig;
@@ -417,6 +457,8 @@ __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
                 double * o = A + tri(ra) + j;
                 if (j <= ra) o[0] = c0;
                 if (j + 1 <= ra) o[1] = c1;
+                if (two && j + 8 <= ra) o[8] = e0;
+                if (two && j + 9 <= ra) o[9] = e1;
             }
             __syncwarp();
         }
@@ -424,9 +466,9 @@ __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
 }
 
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
-// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[128] (+ rg[cd] | g[cd], see factor_kernel)
+// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[192] | rg[cd] | g[cd]
 __host__ __device__ inline int factor_smem_doubles(int n, int cd, int nnz_pad) {
-    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 128 + 2 * ((cd + 1) & ~1);
+    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 192 + 2 * ((cd + 1) & ~1);
 }
 
 // OPF 0: g_q = (J J^T)^-1 (J g_r)                     -> gq_out[B][n]
@@ -459,7 +501,7 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
     double * A = Jv + sp.nnz_pad;
     double * rdiag = A + ntri + n + 2;
     double * Ds = rdiag + ((n + 1) & ~1);
-    double * rg = Ds + 128, * gs = rg + ((cd + 1) & ~1);
+    double * rg = Ds + 192, * gs = rg + ((cd + 1) & ~1);
     SPHASE_BEGIN(Ds);
     for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
         // the geometry (and the gradient) are read once, coalesced: every later use is a shared-memory read
@@ -473,12 +515,17 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
         // A = J J^T over the structurally nonzero pairs of rows: 3 products per common atom
         for (int p = lane; p < sp.npairs_pad; p += kLanes) {
             double s = 0.0;
-            for (int e = 0; e < sp.maxc; e++) {
-                const uint32_t ent = sp.pair_ent[e * sp.npairs_pad + p];
-                const double * ji = Jv + (ent >> 16), * jj = Jv + (ent & 0xffffu);
-                s = fma(ji[0], jj[0], s);
-                s = fma(ji[1], jj[1], s);
-                s = fma(ji[2], jj[2], s);
+            for (int e = 0; e < sp.maxc; e += 4) {                                  // (lists padded to a multiple of 4 with zero entries)
+                uint32_t ent[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) ent[u] = sp.pair_ent[(e + u) * sp.npairs_pad + p];
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double * ji = Jv + (ent[u] >> 16), * jj = Jv + (ent[u] & 0xffffu);
+                    t[u] = fma(ji[2], jj[2], fma(ji[1], jj[1], ji[0] * jj[0]));
+                }
+                s += (t[0] + t[1]) + (t[2] + t[3]);
             }
             A[sp.pair_dest[p]] = s;                                                 // padding pairs write the spare element
         }
@@ -1087,6 +1134,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             maxc = std::max(maxc, (int)common.size());
             pair_lists.push_back(common);
         }
+    maxc = (maxc + 3) & ~3;                                  // the factor kernel reads the lists four entries at a time
     const int npairs = (int)pair_dest.size();
     const int npairs_pad = (npairs + 31) & ~31;
     const uint32_t spare = (uint32_t)(n * (n + 1) / 2 + n);             // the spare element behind the bordered row
