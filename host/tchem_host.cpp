@@ -8,6 +8,7 @@
 // std::runtime_error.
 #include <map>
 #include <mutex>
+#include <thread>
 #include <sstream>
 
 #include <c10/cuda/CUDAGuard.h>
@@ -29,6 +30,20 @@ void check(int rc) {
         case TCHEM_EFILE: throw CL::utility::file_error(msg);
         default: throw std::runtime_error(msg);
     }
+}
+
+// Host tensors may be spread over several GPUs by ONE call (geometries are independent): the batch
+// is cut into contiguous slices, one host thread and one table per device, each slice through the pipelined
+// host-buffer entry point, results landing in place in the caller-visible tensors. No collective, no extra copy.
+// TCHEM_DEVICES = "all" or a count (default 1); tchem::b200::set_host_devices() overrides the environment.
+int g_host_devices = -1;
+int host_devices() {
+    int want = g_host_devices;
+    if (want < 0) {
+        const char * e = getenv("TCHEM_DEVICES");
+        want = !e ? 1 : (std::string(e) == "all" ? 1 << 20 : atoi(e));
+    }
+    return std::max(1, std::min(want, tchem_device_count()));
 }
 
 int default_device() {
@@ -57,6 +72,11 @@ at::Tensor unbatch(const at::Tensor & t, bool batched) { return batched ? t : t[
 void * ptr(const at::Tensor & t) { return t.defined() && t.numel() > 0 ? t.data_ptr() : nullptr; }
 
 } // namespace
+
+namespace tchem { namespace b200 {
+void set_host_devices(int n) { g_host_devices = n; }
+int host_devices() { return ::host_devices(); }
+} }
 
 namespace tchem { namespace IC {
 
@@ -101,6 +121,7 @@ public:
 namespace {
 
 struct Call {                 // one evaluation request resolved against a table
+    std::shared_ptr<detail::Compiled> compiled;
     tchem_ic_table * table;
     Batch r;
     bool host;
@@ -117,6 +138,7 @@ Call resolve(const std::vector<IntCoord> & ics, std::shared_ptr<detail::Compiled
     if (!compiled) compiled = std::make_shared<detail::Compiled>(ics);
     c.host = !r.is_cuda();
     c.device = c.host ? default_device() : r.get_device();
+    c.compiled = compiled;
     c.table = compiled->get(c.device, (int)(c.r.width / 3));
     c.opts = c.r.t.options();
     return c;
@@ -128,7 +150,29 @@ std::vector<at::Tensor> evaluate(Call & c, bool want_J, bool want_K, bool value_
     if (want_J) J = at::empty({B, n, cd}, c.opts);
     if (want_K) K = at::empty({B, n, cd, cd}, c.opts);
     if (B > 0) {
-        if (c.host) {
+        const int ndev = c.host ? host_devices() : 1;
+        if (c.host && ndev > 1 && B >= 2048 * (int64_t)ndev) {
+            // one slice, one table and one host thread per device; slices are multiples of the 32-geometry tile
+            std::vector<std::thread> workers;
+            std::vector<int> rcs(ndev, TCHEM_OK);
+            std::vector<std::string> errs(ndev);
+            const int64_t per = ((B + ndev - 1) / ndev + 31) / 32 * 32;
+            const double * rp = (const double *)ptr(c.r.t);
+            double * qp = (double *)ptr(q), * Jp = (double *)ptr(J), * Kp = (double *)ptr(K);
+            for (int d = 0; d < ndev; d++) {
+                const int64_t b0 = std::min<int64_t>(B, d * per), nb = std::min<int64_t>(per, B - b0);
+                if (nb <= 0) continue;
+                tchem_ic_table * table = c.compiled->get(d, (int)(cd / 3));
+                workers.emplace_back([=, &rcs, &errs] {
+                    rcs[d] = tchem_ic_eval_host(table, rp + b0 * cd, nb, qp ? qp + b0 * n : nullptr, Jp ? Jp + b0 * n * cd : nullptr,
+                                                Kp ? Kp + b0 * n * cd * cd : nullptr, value_path ? 1 : 0);
+                    if (rcs[d] != TCHEM_OK) errs[d] = tchem_last_error();
+                });
+            }
+            for (auto & w : workers) w.join();
+            for (int d = 0; d < ndev; d++)
+                if (rcs[d] != TCHEM_OK) throw std::runtime_error(errs[d]);
+        } else if (c.host) {
             check(tchem_ic_eval_host(c.table, (const double *)ptr(c.r.t), B, (double *)ptr(q), (double *)ptr(J),
                                      (double *)ptr(K), value_path ? 1 : 0));
         } else {

@@ -194,6 +194,18 @@ int main(int argc, char ** argv) {
            std::abs((pset[8](px) - panswer[8]).item<double>()) + maxabs(pset[8].gradient_(px) - PJ[8]) + maxabs(pset[8].Hessian_(px) - PK[8]), 1e-12);
     report("dimension check", throws<std::invalid_argument>([&] { pset(at::ones({3}, r_cpu.options())); }) ? 0 : 1, 0);
 
+    {   // one call with host tensors spread over every visible GPU: bit-identical to the one-device result
+        const int64_t nb = 8192 * 2;
+        at::Tensor rb = r_cpu.unsqueeze(0).repeat({nb, 1}) + 0.01 * at::randn({nb, r_cpu.size(0)}, r_cpu.options());
+        at::Tensor qa, Ja, qb, Jb;
+        tchem::b200::set_host_devices(1);
+        std::tie(qa, Ja) = set.compute_IC_J(rb);
+        tchem::b200::set_host_devices(1 << 20);
+        std::tie(qb, Jb) = set.compute_IC_J(rb);
+        std::cout << "host tensors over " << tchem::b200::host_devices() << " device(s)\n";
+        report("compute_IC_J over all devices vs one device", maxabs(Ja - Jb) + maxabs(qa - qb), 0.0);
+        tchem::b200::set_host_devices(-1);
+    }
     std::cout << (failures ? "FAILED " : "passed ") << "(" << failures << " failures)\n";
     return failures ? 1 : 0;
 }

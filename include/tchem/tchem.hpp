@@ -3,4 +3,6 @@
 #define tchem_hpp
 #include <tchem/intcoord.hpp>
 #include <tchem/polynomial.hpp>
+#include <tchem/b200.hpp>
+
 #endif

@@ -802,3 +802,18 @@ def test_cuda_graph_capture_and_replay(T):
         for a, b in zip(got, eager):
             np.testing.assert_array_equal(a, host(b))
         assert np.abs(got[1]).max() > 0
+
+
+def test_nccl_gather_of_sharded_results(T):
+    """shards evaluated on 2 GPUs, gathered on rank 0 over NCCL, bit-identical to the one-GPU result
+    (tools/nccl_gather_check.py also reports kernel vs gather time). Needs two visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(root, "tools", "nccl_gather_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert p.stdout.count('"bit_identical_to_one_gpu": true') == 2, p.stdout[-2000:]

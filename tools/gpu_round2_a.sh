@@ -15,4 +15,4 @@ echo "rc $?" >> gpurun_out/a_smoke.log
 timeout 1200 python bench.py > gpurun_out/a_bench_default.json 2> gpurun_out/a_bench_default.err
 echo "rc $?" >> gpurun_out/a_bench_default.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/a_bench_reference.json 2> gpurun_out/a_bench_reference.err
-tail -3 gpurun_out/a_t1.log gpurun_out/a_full.log gpurun_out/a_smoke.log
+for f in a_t1 a_full a_smoke; do tail -n 3 gpurun_out/$f.log; done

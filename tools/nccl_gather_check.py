@@ -1,9 +1,15 @@
 #!/usr/bin/env python
-"""Sharded q+J over the GPUs of one node + NCCL gather on rank 0, checked against a single-GPU run.
-torchrun --nproc-per-node N tools/nccl_gather_check.py   (N = 2, 4, 8)"""
+"""Sharded evaluation over the GPUs of one node + NCCL gather of the result shards on rank 0 (SURVEY.md section 5 / 8e:
+"kernel vs gather"), checked bit for bit against a single-GPU run.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 tools/nccl_gather_check.py
+
+Workloads: C2 q+J (10^6 geometries in total, 1.82 GB of J), C3 q+J+K (8 192 geometries in total, 12.7 GB of K - the
+case where the gather, not the kernel, bounds the job). One JSON line per workload on rank 0: device time of the sharded
+kernels (max over ranks), device time of the gather, GB/s into the root against the ~900 GB/s NVLink-5 ingress of one GPU."""
+import json
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist
@@ -13,30 +19,58 @@ import torch_chemistry_b200 as T  # noqa: E402
 from torch_chemistry_b200 import sharding  # noqa: E402
 
 
+def timed(fn, reps=3):
+    """best device time (ms) of fn over `reps` runs, all ranks in step; returns (ms, last result)"""
+    best, out = None, None
+    for _ in range(reps):
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t.item()) if best is None else min(best, float(t.item()))
+    return best, out
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group("nccl")
-    w = T.workloads.get("C2")
-    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms, device=torch.device("cuda", torch.cuda.current_device()))
-    B = 200003                                         # ragged over the ranks
-    r = torch.from_numpy(w.geometries(B, seed=17))     # same bits on every rank
-    b, e = sharding.shard_bounds(B, world, rank)
-    q, J = s.compute_IC_J(r[b:e].cuda())
-    sharding.gather_shards(q, B, dst=0)                 # warm-up: communicator set-up
-    torch.cuda.synchronize(); dist.barrier()
-    t0 = time.perf_counter()
-    Jall = sharding.gather_shards(J, B, dst=0)
-    qall = sharding.gather_shards(q, B, dst=0)
-    torch.cuda.synchronize(); dist.barrier()
-    dt = time.perf_counter() - t0
-    if rank == 0:
-        qref, Jref = s.compute_IC_J(r.cuda())
-        ok = torch.equal(Jall, Jref) and torch.equal(qall, qref)
-        gb = (Jall.numel() + qall.numel()) * 8 * (world - 1) / world / 1e9
-        print("nccl gather over %d GPUs: %s, %.2f GB received in %.1f ms (%.0f GB/s)" % (world, "bit-identical to the 1-GPU result" if ok else "MISMATCH", gb, dt * 1e3, gb / dt))
-        if not ok:
-            sys.exit(1)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for key, B, want_K in (("C2", 1000003, False), ("C3", 8192, True)):
+        w = T.workloads.get(key)
+        s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms, device=dev)
+        r = torch.from_numpy(w.geometries(B, seed=17))     # same bits on every rank
+        b, e = sharding.shard_bounds(B, world, rank)
+        rd = r[b:e].to(dev)
+        run = (lambda: s.compute_IC_J_K(rd)) if want_K else (lambda: s.compute_IC_J(rd))
+        run()
+        kernel_ms, outs = timed(run)
+        big = outs[-1]                                      # J or K: the array that matters
+        sharding.gather_shards(outs[0], B, dst=0)           # warm-up: communicator set-up
+        gather_ms, full = timed(lambda: sharding.gather_shards(big, B, dst=0))
+        if rank == 0:
+            bytes_in = full.numel() * 8 * (B - (e - b)) / B
+            ok = None
+            if not want_K or world <= 8:
+                # reference: the same batch on one GPU, in slices that fit beside the gathered tensor
+                ok = True
+                step = 1024 if want_K else 200000
+                for c0 in range(0, B, step):
+                    ref = (s.compute_IC_J_K if want_K else s.compute_IC_J)(r[c0:c0 + step].to(dev))[-1]
+                    ok = ok and torch.equal(full[c0:c0 + step], ref)
+            print(json.dumps({"workload": "%s %s" % (key, "q+J+K" if want_K else "q+J"), "n_gpus": world, "geometries": B,
+                              "kernel_ms_sharded": kernel_ms, "gather_ms": gather_ms, "gathered_GB": full.numel() * 8 / 1e9,
+                              "root_ingress_GBps": bytes_in / 1e9 / (gather_ms * 1e-3), "root_ingress_bound_GBps": 900.0,
+                              "gather_over_kernel": gather_ms / kernel_ms,
+                              "bit_identical_to_one_gpu": ok}), flush=True)
+            if ok is False:
+                sys.exit(1)
+        del outs, big, full
+        torch.cuda.empty_cache()
     dist.destroy_process_group()
 
 
