@@ -785,6 +785,20 @@ __device__ __forceinline__ void gather_slots(const SparseProgram & sp, const dou
     }
 }
 
+// shared [count] (contiguous) -> global through the TMA unit (1-D bulk copy): issued by one thread AFTER every thread
+// has fenced its generic-proxy writes and the block has met; the region may be rewritten once bulk_store_read_done()
+// has returned. False: shape / alignment does not allow it (the caller stores with ordinary instructions).
+__device__ __forceinline__ bool bulk_store_ok(const double * s, const double * g, int count) {
+    return (count & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+}
+__device__ __forceinline__ void bulk_store_issue(const double * s, double * g, int count) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(g), "r"(smem_addr(s)), "r"(count * 8) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_read_done() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_all_done() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // packed inverse of one geometry (workspace) -> full symmetric Ai[n][ldh], element-wise cp.async (no commit): the
 // expansion travels in the background like the operand matrix
 __device__ __forceinline__ void expand_inverse_async(const double * __restrict__ pk, double * Ai, int n, int ldh) {
@@ -860,10 +874,11 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
     __syncthreads();                                                       // (also publishes the table copy)
     for (int p = sp.nnz + threadIdx.x; p < sp.nnz_pad; p += blockDim.x) { jv_of(0)[p] = 0.0; jv_of(1)[p] = 0.0; }
     eval_J_rows<HAS5>(sp, rg_of(0), jv_of(0), threadIdx.x, blockDim.x);
+    // group order (oldest first): Hessian_int2cart waits for its matrix first, the other two for the small inputs first
+    if (OP == 2) { fetch_big(b0); cp_async_commit(); }
     if (b0 + gridDim.x < B) fetch_small(b0 + gridDim.x, 1);
     cp_async_commit();
-    fetch_big(b0);
-    cp_async_commit();
+    if (OP != 2) { fetch_big(b0); cp_async_commit(); }
 
     for (int64_t b = b0; b < B; b += gridDim.x) {
         const int64_t bn = b + gridDim.x, bnn = bn + gridDim.x;
@@ -872,15 +887,17 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
         SPHASE_BEGIN(sm);
         if (OP == 2) {
             double * Hq = BIG, * U = MID, * X = THIRD;
-            cp_async_wait<0>();                                            // H_q of b (and the small inputs of bn)
+            cp_async_wait<1>();                                            // H_q of b (the small inputs of bn, fetched last, may still fly)
             __syncthreads();                                               // + J rows of b (prologue or previous task phase)
             SPHASE(10);
             spmm_JT(sp, Jv, Hq, n, n, U, ldo);                             // U = J^T H_q        (cd x n)
+            if (threadIdx.x == 0) bulk_store_read_done();                  // the previous geometry's X has left shared memory
             __syncthreads();
             SPHASE(11);
             if (has_next) block_copy_async(in2 + bn * (int64_t)big_count, BIG, big_count);   // H_q is dead: the next one travels during the rest
             cp_async_commit();
             spmm_J(sp, Jv, U, ldo, cd, X, cd);                             // X = U J            (cd x cd)
+            cp_async_wait<1>();                                            // the small inputs of bn (the next H_q may still fly)
             __syncthreads();
             SPHASE(12);
             run_tasks<HAS5>(sp, rg, gvec, 1.0, U /* slots */, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
@@ -889,9 +906,14 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             gather_slots(sp, U, X, cd);                                    // X += sum_k g_q[k] K[k]
             if (bnn < B) fetch_small(bnn, cur);                            // (rg / g_q of b are dead after the tasks)
             cp_async_commit();
+            double * Xg = out + b * (int64_t)cd * cd;
+            const bool bulk = bulk_store_ok(X, Xg, cd * cd);
+            if (bulk) fence_async_proxy();
             __syncthreads();
             SPHASE(14);
-            block_store_rows(X, out + b * (int64_t)cd * cd, cd, cd, cd);
+            // the result leaves through the TMA unit while the next geometry's U phase runs (X is rewritten after it)
+            if (bulk) { if (threadIdx.x == 0) bulk_store_issue(X, Xg, cd * cd); }
+            else block_store_rows(X, Xg, cd, cd, cd);
             SPHASE(15);
             cur ^= 1;
             continue;                                                      // (the next iteration's first barrier orders the reuse of X)
@@ -941,8 +963,13 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             block_dgemm<true, false, false>(n, n, cd, MT, ldh, T2, ldh, Q, ldh);         // H_q = M T2     (n x n)
             __syncthreads();
             SPHASE(25);
-            block_store_rows(Q, out + b * (int64_t)n * n, n, n, ldh);
-            __syncthreads();                                               // the stores have read Q, T2 is dead: the next matrices may land
+            double * Qg = out + b * (int64_t)n * n;
+            if (ldh == n && bulk_store_ok(Q, Qg, n * n)) {
+                fence_async_proxy();
+                __syncthreads();
+                if (threadIdx.x == 0) { bulk_store_issue(Q, Qg, n * n); bulk_store_read_done(); }
+            } else block_store_rows(Q, Qg, n, n, ldh);
+            __syncthreads();                                               // Q has been read, T2 is dead: the next matrices may land
             SPHASE(26);
             if (bnn < B) fetch_small(bnn, cur);
             cp_async_commit();
@@ -952,6 +979,7 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
         }
     }
     cp_async_wait<0>();
+    if (threadIdx.x == 0) bulk_store_all_done();
 }
 
 // ======================================================================================================
