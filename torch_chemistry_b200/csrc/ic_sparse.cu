@@ -1305,7 +1305,9 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     SparseTable st;
     int rc = get_sparse(t, st);
     if (rc != TCHEM_OK) return rc;
-    static const double max_density = [] { const char * e = getenv("TCHEM_SPARSE_MAX_DENSITY"); return e ? atof(e) : 0.5; }();
+    // (any density: on the small molecules whose J is dense the compressed lists simply hold every element, and the results
+    // stay bit-reproducible; TCHEM_SPARSE_MAX_DENSITY sends denser tables to the DMMA kernels)
+    static const double max_density = [] { const char * e = getenv("TCHEM_SPARSE_MAX_DENSITY"); return e ? atof(e) : 1.01; }();
     if (st.density > max_density || st.prog.nnz_pad > 65000 || st.prog.nslots > (1 << 30)) return -1;
     const int ntri = n * (n + 1) / 2;
     // ---- kernel 1 (cart -> int): factor / solve / inverse, one warp per geometry ---------------------------------
