@@ -738,6 +738,28 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> SAPSet::chained(const tchem::IC::
     if (host) { y = y.cpu(); J = J.cpu(); q = q.cpu(); }
     return std::make_tuple(unbatch(y, rb.batched), unbatch(J, rb.batched), unbatch(q, rb.batched));
 }
+std::tuple<at::Tensor, at::Tensor, at::Tensor> SAPSet::chained_cart(const tchem::IC::IntCoordSet & set, const at::Tensor & r,
+                                                                    const bool & second_order) const {
+    const std::string who = "tchem::polynomial::SAPSet::chained_cart";
+    Batch rb = as_batch(r, who, "r");
+    const bool host = !r.is_cuda();
+    const int device = host ? default_device() : r.get_device();
+    int64_t sumdim = 0;
+    for (size_t d : dimensions_) sumdim += (int64_t)d;
+    if ((int64_t)set.size() != sumdim) throw std::invalid_argument(who + ": x must have a same dimension as the coordinates");
+    c10::cuda::CUDAGuard guard(device);
+    at::Tensor rd = rb.t.is_cuda() ? rb.t : rb.t.to(at::Device(at::kCUDA, device));
+    const int64_t B = rb.B, nsap = SAPs_.size(), cd = rb.width;
+    at::Tensor y = at::empty({B, nsap}, rd.options()), g = at::empty({B, nsap, cd}, rd.options()), h;
+    if (second_order) h = at::empty({B, nsap, cd, cd}, rd.options());
+    if (!ic_compiled_) ic_compiled_ = std::make_shared<std::map<const void *, std::shared_ptr<tchem::IC::detail::Compiled>>>();
+    std::shared_ptr<tchem::IC::detail::Compiled> & slot = (*ic_compiled_)[&set];
+    tchem_ic_table * ict = tchem::IC::table_of(set, slot, device, (int)(rb.width / 3));
+    if (B > 0) check(tchem_ic_sap_eval_cart(ict, compiled(device).get(device), (const double *)ptr(rd), B, (double *)ptr(y), (double *)ptr(g),
+                                            (double *)ptr(h), c10::cuda::getCurrentCUDAStream(device).stream()));
+    if (host) { y = y.cpu(); g = g.cpu(); if (second_order) h = h.cpu(); }
+    return std::make_tuple(unbatch(y, rb.batched), unbatch(g, rb.batched), second_order ? unbatch(h, rb.batched) : h);
+}
 
 // ---- Polynomial / PolynomialSet (source/polynomial/Polynomial.cpp, PolynomialSet.cpp:56-179) --------------------
 Polynomial::Polynomial() {}

@@ -56,6 +56,11 @@ class SAPSet {
         // compute_IC_J formulas -> xs = q split by dimensions_ -> value and concatenated Jacobian
         // d SAP / d q in one kernel. Returns (y, J, q).
         std::tuple<at::Tensor, at::Tensor, at::Tensor> chained(const tchem::IC::IntCoordSet & set, const at::Tensor & r) const;
+        // chained path with CARTESIAN derivatives (what callers compose by hand from Jacobian_ / Jacobian2nd_ and
+        // compute_IC_J / compute_IC_J_K): values, (d SAP / d q) J and - second_order - J^T (d2 SAP / d q2) J + sum_k (d SAP / d q_k) K_k
+        // (an undefined tensor otherwise)
+        std::tuple<at::Tensor, at::Tensor, at::Tensor> chained_cart(const tchem::IC::IntCoordSet & set, const at::Tensor & r,
+                                                                    const bool & second_order = false) const;
 };
 
 } }

@@ -347,6 +347,56 @@ def test_chained_sap_C5(T):
     assert_parity(host(J), osap.jacobian(qo), "C5 chained Jacobian vs oracle")
 
 
+def test_chained_cartesian_derivatives(T):
+    """dy/dr = (dSAP/dq) J and d2y/dr2 = J^T (d2SAP/dq2) J + sum_k (dSAP/dq_k) K[k], against the composition
+    of the oracle's own outputs (what callers of the reference do by hand, test/normal_mode/main.cpp:56-61). Large
+    batch: the pair-specialised kernel (first order); small batch and the second order: the composed path."""
+    w = T.workloads.get("C5")
+    ic = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    sap = T.SAPSet.from_text(w.sap_text, 0, w.sap_dims)
+    oic, osap = O.IntCoordSet("default", w.ic_text), O.SAPSet(w.sap_text, 0, w.sap_dims)
+
+    def reference(r, second):
+        q, J, K = oic.qJK(r)
+        y, g = osap.value(q), osap.jacobian(q)
+        out = [y, np.einsum("btk,bkc->btc", g, J)]
+        if second:
+            H = osap.jacobian2nd(q)
+            out.append(np.einsum("bka,btkl,blc->btac", J, H, J) + np.einsum("btk,bkac->btac", g, K))
+        return out
+
+    r = w.geometries(20011, seed=31)                       # ragged tile, above the specialised kernel's threshold
+    before = T.kernel_log().get("tchem_jit_chain_cart", 0)
+    y, g = sap.chained_cart(ic, dev(r))
+    assert T.kernel_log().get("tchem_jit_chain_cart", 0) == before + 1
+    idx = np.arange(0, 20011, 997)
+    yo, go = reference(r[idx], False)
+    assert_parity(host(y)[idx], yo, "C5 chained Cartesian: values (specialised)")
+    assert_parity(host(g)[idx], go, "C5 chained Cartesian: dy/dr (specialised)")
+    rs = r[:37]
+    y2, g2, h2 = sap.chained_cart(ic, dev(rs), second_order=True)
+    yo, go, ho = reference(rs, True)
+    assert_parity(host(y2), yo, "C5 chained Cartesian: values (composed)")
+    assert_parity(host(g2), go, "C5 chained Cartesian: dy/dr (composed)")
+    assert_parity(host(h2), ho, "C5 chained Cartesian: d2y/dr2 (composed)")
+    assert float((h2 - h2.transpose(2, 3)).abs().max()) < 1e-12
+    # one geometry, host tensor: reference call shapes
+    y1, g1 = sap.chained_cart(ic, torch.from_numpy(rs[0]))
+    assert y1.shape == (sap.nterms,) and g1.shape == (sap.nterms, ic.cartdim) and not g1.is_cuda
+    assert_parity(g1.numpy(), go[0], "C5 chained Cartesian: one geometry")
+    # a larger molecule chained into a small set: C2H4 (12 coordinates, one irreducible)
+    w2 = T.workloads.get("C2")
+    ic2 = T.IntCoordSet.from_text("default", w2.ic_text, n_atoms=w2.natoms)
+    text = "1,1\n1,2    1,1\n1,12    1,12\n1,3    1,2    1,1\n"
+    sap2, osap2 = T.SAPSet.from_text(text, 0, [12]), O.SAPSet(text, 0, [12])
+    oic2 = O.IntCoordSet("default", w2.ic_text)
+    r2 = w2.geometries(17000, seed=5)
+    y3, g3 = sap2.chained_cart(ic2, dev(r2))
+    q, J = oic2.qJ(r2[::1000])
+    assert_parity(host(g3)[::1000], np.einsum("btk,bkc->btc", osap2.jacobian(q), J), "C2 chained Cartesian: dy/dr")
+    assert_parity(host(y3)[::1000], osap2.value(q), "C2 chained Cartesian: values")
+
+
 def test_chained_specialised_multichunk_C2(T):
     """A SAPSet over all 12 C2H4 coordinates with 40 monomials (orders 0-4, repeated columns):
     (1 + 12) * 40 staged entries do not fit one chunk, so the pair-specialised kernel runs its

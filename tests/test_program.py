@@ -244,3 +244,34 @@ def test_specialised_sap_second_order_source_compiles_for_sm100a():
         if rc != 0 and "not available" in log.value.decode():
             pytest.skip("NVRTC not available")
         assert rc == 0, name + ": " + log.value.decode()[-2000:]
+
+
+def test_chained_cartesian_jacobian_source_compiles_for_sm100a():
+    """jit.cu: the (IntCoordSet, SAPSet) pair kernel with the Jacobian in Cartesian coordinates - J's structurally
+    nonzero elements as named values, every output element a literal fma chain - for the C5 pair and for C2H4 chained
+    into a small set; compiled with NVRTC for sm_100a without a device."""
+    g = golden("workload_C5")
+    cases = [(str(g["definition"]), 9, str(g["sap_definition"]), [int(d) for d in g["sap_dims"]])]
+    c2 = golden("workload_C2")
+    cases.append((str(c2["definition"]), 18, "1,1\n1,2    1,1\n1,12    1,12\n1,3    1,2    1,1\n", [12]))
+    for ic_text, cd, sap_text, dims in cases:
+        nt, nic = C.c_int(0), C.c_int(0)
+        capi.check(lib.tchem_ic_parse_text(b"default", ic_text.encode(), None, 0, C.byref(nt), C.byref(nic)))
+        terms = (capi.InvDisp * nt.value)()
+        capi.check(lib.tchem_ic_parse_text(b"default", ic_text.encode(), terms, nt.value, C.byref(nt), C.byref(nic)))
+        ns, nc = C.c_int(0), C.c_int(0)
+        capi.check(lib.tchem_sap_parse_text(sap_text.encode(), None, 0, None, 0, C.byref(ns), C.byref(nc)))
+        tp, cs = (C.c_int32 * (ns.value + 1))(), (C.c_int32 * max(2 * nc.value, 2))()
+        capi.check(lib.tchem_sap_parse_text(sap_text.encode(), tp, ns.value, cs, nc.value, C.byref(ns), C.byref(nc)))
+        d = (C.c_int32 * len(dims))(*dims)
+        n = lib.tchem_ic_sap_jit_cart_source(terms, nt.value, nic.value, cd, tp, cs, ns.value, d, len(dims), None, 0)
+        assert n > 0
+        buf = C.create_string_buffer(n)
+        lib.tchem_ic_sap_jit_cart_source(terms, nt.value, nic.value, cd, tp, cs, ns.value, d, len(dims), buf, n)
+        src = buf.value.decode()
+        assert "tchem_jit_chain_cart" in src and "J0_0" in src and "#define SDO %d" % cd in src
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.tchem_ic_jit_compile_check(src.encode(), log, 1 << 16)
+        if rc != 0 and "not available" in log.value.decode():
+            pytest.skip("NVRTC not available")
+        assert rc == 0, log.value.decode()[-2000:]

@@ -11,6 +11,9 @@ for spec in "C2:tchem_jit_qJ_bulk" "C3:ic_eval_group_kernel" "C3K:ic_eval_kernel
   n=1; skip=1; if [ "$w" = "C4Hc" ]; then n=2; skip=2; fi
   timeout 900 ncu --set full --import-source on --clock-control none -k regex:"$k" --launch-skip $skip -c $n -f -o gpurun_out/e_$w python tools/profile_all.py $w > gpurun_out/e_ncu_$w.log 2>&1
   echo "$w rc $?"
+  # summaries are made here (the reports together exceed what travels back); the large reports are dropped
+  python tools/ncu_summary.py gpurun_out/e_$w.ncu-rep 30 > gpurun_out/e_summary_$w.txt 2>&1
+  case $w in C3|C3K|C4gc|C4Hc) rm -f gpurun_out/e_$w.ncu-rep;; esac
 done
 mkdir -p gpurun_out/e_cubins; cp ~/.cache/tchem_b200/*.cubin gpurun_out/e_cubins/ 2>/dev/null; ls gpurun_out/e_cubins | wc -l
 ls -la gpurun_out/e_*.ncu-rep
