@@ -198,6 +198,9 @@ TCHEM_API int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms
  * staging rows; TCHEM_JIT_BULK=0 disables it); 0 when the shape does not give 16-byte aligned pieces */
 TCHEM_API int64_t tchem_ic_jit_source_bulk(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int dcap,
                                            char * buf, int64_t capacity);
+/* the group variant: G warps of a block share one tile and ONE whole-geometry TMA box (contiguous tile stores) */
+TCHEM_API int64_t tchem_ic_jit_source_group(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int G,
+                                            char * buf, int64_t capacity);
 /* source of the kernel specialised to a SAPSet for tchem_sap_jacobian2nd (large batches; whole-geometry
  * staging, one 1-D TMA bulk store per tile); definition arrays as for tchem_sap_table_create */
 TCHEM_API int64_t tchem_sap_jit_hess_source(const int32_t * term_ptr, const int32_t * coords, int n_terms,

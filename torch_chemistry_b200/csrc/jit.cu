@@ -15,6 +15,7 @@
 #include <cuda.h>          // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -22,8 +23,10 @@
 #include <unistd.h>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <string>
 #include <tuple>
@@ -104,6 +107,20 @@ __device__ __forceinline__ void stage_issue(const double * __restrict__ r, int64
     int g = lane / CD, c = lane - g * CD;
     const int dg = LANES / CD, dc = LANES - dg * CD;
     for (int f = lane; f < total; f += LANES) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(R + c * KPAD + g);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + f) : "memory");
+        g += dg; c += dc;
+        if (c >= CD) { c -= CD; g++; }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+// the same copy issued by all `nthreads` threads of a block (thread t), one commit per thread
+__device__ __forceinline__ void stage_issue_block(const double * __restrict__ r, int64_t b0, int ntile, double * R, int t, int nthreads) {
+    const double * src = r + b0 * CD;
+    const int total = ntile * CD;
+    int g = t / CD, c = t - g * CD;
+    const int dg = nthreads / CD, dc = nthreads - dg * CD;
+    for (int f = t; f < total; f += nthreads) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(R + c * KPAD + g);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + f) : "memory");
         g += dg; c += dc;
@@ -731,6 +748,152 @@ std::string jit_source(const std::vector<tchem_invdisp_t> & terms, int n_ic, int
     return o.str();
 }
 
+// ---- "group" variant of the bulk q + J kernel (opt-in experiment, TCHEM_JIT_GROUP = G) ---------------------------
+// The bulk variant above writes a tile in row chunks: 32 pieces of (rows per chunk) x cartdim doubles, one geometry
+// stride apart (C2H4: 576-byte pieces 1 728 bytes apart) - a write front that tops out at 80-85 % of the HBM peak
+// even with no arithmetic (tools/micro/write_pattern.cu), while whole-geometry stores of a tile are one contiguous
+// block (C2H4: 55 KB). One warp cannot stage whole geometries (55 KB per warp leaves 3 warps per SM), so here the G
+// warps of a BLOCK share one tile: the rows are dealt out to the warps by estimated cost - rows that share primitives
+// stay together, so no primitive is evaluated twice; lanes still run identical code - every warp stages its rows into
+// the ONE whole-geometry box of the block, and after a block barrier one thread hands the box to the TMA unit as a
+// single tensor store (plus one for q). Structural zeros are staged once per kernel.
+// MEASURED (B200, C2H4, 10^6 geometries): bit-identical results, but 0.46-0.49 ms for G = 2 .. 4 against 0.40 ms of the
+// per-warp chunked kernel: three 55 KB boxes per SM mean three tiles in flight instead of eight, each with three block
+// barriers, and the per-warp code sections thrash the instruction cache (ncu: barrier and no_instructions are the top
+// stalls). The better write front does not pay for the lost overlap, so the variant stays off by default.
+// Shapes: cartdim even (16-byte pairs never straddle rows), whole 64-byte groups per geometry, intdim even.
+bool jit_group_eligible(int n_ic, int cartdim) {
+    const int G8 = n_ic * cartdim;
+    return cartdim % 2 == 0 && n_ic % 2 == 0 && G8 % 8 == 0 && G8 / 8 <= 256 && n_ic <= 256;
+}
+size_t jit_group_block_bytes(int n_ic, int cartdim) {
+    auto up = [](size_t v) { return (v + 511) & ~(size_t)511; };
+    return 1024 + up((size_t)32 * n_ic * cartdim * 8) + up((size_t)32 * n_ic * 8) + up((size_t)cartdim * 33 * 8);
+}
+std::string jit_source_group(const std::vector<tchem_invdisp_t> & terms, int n_ic, int cartdim, int G, int blocks) {
+    if (!jit_group_eligible(n_ic, cartdim) || G < 1 || G > 8) return std::string();
+    std::vector<JitPrim> prims;
+    std::vector<std::vector<std::pair<double, int>>> rows;
+    if (!collect(terms, n_ic, prims, rows)) return std::string();
+    const int natoms = cartdim / 3;
+    auto prim_cost = [&](int p) {
+        const JitPrim & pr = prims[p];
+        return pr.natoms == 4 ? (pr.type == TCHEM_OUTOFPLANE || pr.type == TCHEM_SINOOP ? 11 : 12) : pr.natoms == 3 ? 6 : pr.natoms == 2 ? 2 : 0;
+    };
+    // rows -> warps: rows that share primitives stay together (connected components: a split would make two warps
+    // evaluate the same primitives), the components are dealt out longest processing time first
+    std::vector<int> parent(n_ic);
+    for (int i = 0; i < n_ic; i++) parent[i] = i;
+    std::function<int(int)> find = [&](int x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
+    {
+        std::map<int, int> owner;                          // primitive -> first row that uses it
+        for (int i = 0; i < n_ic; i++)
+            for (auto & t : rows[i]) {
+                auto f = owner.find(t.second);
+                if (f == owner.end()) owner[t.second] = i;
+                else parent[find(i)] = find(f->second);
+            }
+    }
+    std::map<int, std::vector<int>> members;
+    for (int i = 0; i < n_ic; i++) members[find(i)].push_back(i);
+    std::vector<std::pair<int, std::vector<int>>> comps;   // (cost, rows)
+    for (auto & kv : members) {
+        std::set<int> ps;
+        for (int i : kv.second) for (auto & t : rows[i]) ps.insert(t.second);
+        int c = (int)kv.second.size();
+        for (int p : ps) c += prim_cost(p);
+        comps.push_back({c, kv.second});
+    }
+    std::stable_sort(comps.begin(), comps.end(), [](const std::pair<int, std::vector<int>> & a, const std::pair<int, std::vector<int>> & b) { return a.first > b.first; });
+    std::vector<std::vector<int>> bins(G);
+    std::vector<std::set<int>> bin_prims(G);
+    std::vector<int> load(G, 0);
+    for (auto & c : comps) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[w] += c.first;
+        for (int i : c.second) { bins[w].push_back(i); for (auto & t : rows[i]) bin_prims[w].insert(t.second); }
+    }
+    auto up = [](size_t v) { return (v + 511) & ~(size_t)511; };
+    const size_t GB = (size_t)n_ic * cartdim * 8;          // bytes of J per geometry
+    std::ostringstream o;
+    o << "#define CD " << cartdim << "\n#define NIC " << n_ic << "\n#define DCAP 1\n#define GEOMB " << GB
+      << "\n#define JBOX " << up(32 * GB) << "\n#define QBOX " << up((size_t)32 * n_ic * 8) << "\n";
+    o << kPrelude;
+    o << "// rows per warp (estimated cost):";
+    for (int w = 0; w < G; w++) { o << "  w" << w << " {"; for (int i : bins[w]) o << " " << i; o << " } = " << load[w]; }
+    o << "\nextern \"C\" __global__ void __launch_bounds__(" << G * 32 << ", " << blocks << ")\n"
+      << "tchem_jit_qJ_group(const double * __restrict__ r, const long long B, double * __restrict__ q, double * __restrict__ J"
+      << ", const __grid_constant__ TMap tmJ, const __grid_constant__ TMap tmq) {\n"
+      << "    extern __shared__ __align__(16) double smem[];\n"
+      << "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n"
+      << "    // swizzle patterns follow shared-memory address bits: the boxes start on a 1024-byte boundary\n"
+      << "    char * Sbox = reinterpret_cast<char *>(smem) + ((1024 - ((uint32_t)__cvta_generic_to_shared(smem) & 1023)) & 1023);\n"
+      << "    char * Qbox = Sbox + JBOX;\n"
+      << "    double * R = reinterpret_cast<double *>(Qbox + QBOX);\n"
+      << "    const uint32_t S_sh = (uint32_t)__cvta_generic_to_shared(Sbox), Q_sh = (uint32_t)__cvta_generic_to_shared(Qbox);\n"
+      << "    double * Qrow = reinterpret_cast<double *>(Qbox) + lane * NIC;\n"
+      << "    // structural zeros never change: staged once, the box keeps them from tile to tile\n"
+      << "    for (int e = threadIdx.x; e < JBOX / 16; e += blockDim.x) reinterpret_cast<double2 *>(Sbox)[e] = make_double2(0.0, 0.0);\n"
+      << "    const int64_t ntiles = (B + LANES - 1) / LANES, step = gridDim.x;\n"
+      << "    int64_t tile = blockIdx.x;\n"
+      << "    if (tile < ntiles) { const int64_t b0 = tile * LANES; stage_issue_block(r, b0, (int)min((int64_t)LANES, B - b0), R, threadIdx.x, blockDim.x); }\n"
+      << "    for (; tile < ntiles; tile += step) {\n"
+      << "        const int64_t b0 = tile * LANES;\n"
+      << "        const int ntile = (int)min((int64_t)LANES, B - b0);\n"
+      << "        asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");\n"
+      << "        __syncthreads();                                   // the tile's coordinates have landed (and, first tile, the zeros)\n"
+      << "        const int gl = min(lane, ntile - 1);               // ragged tile: idle lanes compute on a copy of the last geometry\n"
+      << "        V3<double> a[" << natoms << "];\n";
+    std::vector<char> atom_used(natoms, 0);
+    for (const auto & p : prims) for (int i = 0; i < p.natoms; i++) atom_used[p.atoms[i]] = 1;
+    for (int at = 0; at < natoms; at++)
+        if (atom_used[at])
+            o << "        a[" << at << "] = v3<double>(R[" << 3 * at << " * KPAD + gl], R[" << 3 * at + 1 << " * KPAD + gl], R["
+              << 3 * at + 2 << " * KPAD + gl]);\n";
+    o << "        // the previous tile's stores have read the boxes; every warp holds its coordinates in registers\n"
+      << "        if (threadIdx.x == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
+      << "        __syncthreads();\n"
+      << "        if (tile + step < ntiles) { const int64_t nb0 = (tile + step) * LANES; stage_issue_block(r, nb0, (int)min((int64_t)LANES, B - nb0), R, threadIdx.x, blockDim.x); }\n"
+      << "        switch (warp) {\n";
+    static const char * xyz[3] = {".x", ".y", ".z"};
+    for (int w = 0; w < G; w++) {
+        o << "        case " << w << ": {\n";
+        for (int p : bin_prims[w])
+            if (!emit_prim(o, prims[p], (size_t)p, true, "            ")) return std::string();
+        std::vector<int> mine = bins[w];
+        std::sort(mine.begin(), mine.end());
+        for (int i : mine) {
+            std::vector<std::string> expr(cartdim);
+            for (auto & t : rows[i]) {
+                const JitPrim & pr = prims[t.second];
+                for (int a = 0; a < pr.natoms; a++)
+                    for (int c = 0; c < 3; c++) {
+                        std::string & e = expr[3 * pr.atoms[a] + c];
+                        const std::string v = "j" + std::to_string(t.second) + "[" + std::to_string(a) + "]" + xyz[c];
+                        e = e.empty() ? hexd(t.first) + " * " + v : "fma(" + hexd(t.first) + ", " + v + ", " + e + ")";
+                    }
+            }
+            // (the swizzle follows the FULL box offset, lane part included)
+            for (int c = 0; c < cartdim; c += 2)
+                if (!expr[c].empty() || !expr[c + 1].empty())
+                    o << "            stage_pair(Sbox, lane * GEOMB + " << (size_t)(i * cartdim + c) * 8 << ", " << (expr[c].empty() ? "0.0" : expr[c]) << ", "
+                      << (expr[c + 1].empty() ? "0.0" : expr[c + 1]) << ");\n";
+            o << "            Qrow[" << i << "] = " << row_expr(rows[i], "q") << ";\n";
+        }
+        o << "        } break;\n";
+    }
+    o << "        default: break;\n        }\n"
+      << "        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+      << "        __syncthreads();                                   // the whole tile is staged\n"
+      << "        if (threadIdx.x == 0) {\n"
+      << "            if (J) asm volatile(\"cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\" ::\"l\"(&tmJ), \"r\"(0), \"r\"(0), \"r\"((int)b0), \"r\"(S_sh) : \"memory\");\n"
+      << "            if (q) asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\" ::\"l\"(&tmq), \"r\"(0), \"r\"((int)b0), \"r\"(Q_sh) : \"memory\");\n"
+      << "            asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n"
+      << "        }\n    }\n"
+      << "    if (threadIdx.x == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n}\n";
+    return o.str();
+}
+
 // compiles `src` for sm_100a; returns the cubin (empty on failure, reason in `log`)
 std::vector<char> jit_compile(const std::string & src, std::string & log, bool verbose) {
     std::vector<char> cubin;
@@ -803,7 +966,7 @@ std::map<ChainKey, JitKernel> & chain_kernels() {
 
 void release_jit(const tchem_ic_table * t) {
     std::lock_guard<std::mutex> lock(jit_mutex());
-    for (int variant = 0; variant < 2; variant++) {
+    for (int variant = 0; variant < 3; variant++) {
         auto it = jit_kernels().find({t, variant});
         if (it != jit_kernels().end()) { if (it->second.lib) cudaLibraryUnload(it->second.lib); jit_kernels().erase(it); }
     }
@@ -1021,12 +1184,24 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
     static const int want_bulk = env_int("TCHEM_JIT_BULK", 1);
     const int dcap = env_int("TCHEM_JIT_DCAP", std::max(t->cartdim + 1, 76));
     // the TMA write-out needs 16-byte aligned results, whole 64-byte groups and 32-bit tile coordinates
-    int variant = want_bulk && jit_bulk_eligible(t->intdim, t->cartdim, dcap) && B < ((int64_t)1 << 31) && tensor_map_encoder()
-                  && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 1 : 0;
+    const bool tma_ok = want_bulk && B < ((int64_t)1 << 31) && tensor_map_encoder()
+                        && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(J)) & 15) == 0;
+    // variant 2 (opt-in): G warps of a block share one tile and one whole-geometry TMA box (TCHEM_JIT_GROUP = G)
+    static const int group_g = env_int("TCHEM_JIT_GROUP", 0);
+    int variant = tma_ok && group_g > 0 && jit_group_eligible(t->intdim, t->cartdim)
+                  && jit_group_block_bytes(t->intdim, t->cartdim) <= (size_t)t->max_smem_optin ? 2
+                  : tma_ok && jit_bulk_eligible(t->intdim, t->cartdim, dcap) ? 1 : 0;
     JitKernel * k = nullptr;
     for (; variant >= 0 && !k; variant--) {
+        if (variant == 1 && !(tma_ok && jit_bulk_eligible(t->intdim, t->cartdim, dcap))) continue;
         std::lock_guard<std::mutex> lock(jit_mutex());
         JitKernel & jk = jit_kernels()[{t, variant}];
+        if (!jk.fn && !jk.failed && variant == 2) {
+            jk.warps = std::min(group_g, 8);
+            jk.blocks = env_int("TCHEM_JIT_GROUP_BLOCKS", 3);
+            const std::string src = jit_source_group(t->terms, t->intdim, t->cartdim, jk.warps, jk.blocks);
+            jit_finish(jk, src, "tchem_jit_qJ_group", jit_group_block_bytes(t->intdim, t->cartdim), t->max_smem_optin, debug);
+        }
         if (!jk.fn && !jk.failed) {
             // 8 warps per SM is what the ~250-register kernel allows (at 227 registers - 9 warps - it
             // spills and loses 25 %); as 4 blocks of 2 warps they finish 2 % sooner than as 2 blocks of 4
@@ -1042,11 +1217,13 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
     }
     if (!k) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem_ic_eval: the specialised q+J kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     const int64_t ntiles = (B + 31) / 32;
-    const int64_t grid = std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
+    const int64_t grid = variant == 2 ? std::min<int64_t>(ntiles, (int64_t)t->sm_count * k->per_sm)
+                                      : std::min<int64_t>((ntiles + k->warps - 1) / k->warps, (int64_t)t->sm_count * k->per_sm);
     long long Bll = B;
-    if (variant == 1) {
+    if (variant >= 1) {
         // J as [B][intdim * cartdim / 8][8 doubles] with the 64B swizzle, q as [B][intdim]; boxes = one chunk of one tile
-        const int rows_per = std::min(t->intdim, std::max(1, dcap / (t->cartdim + 1)));
+        // (group variant: the whole geometry)
+        const int rows_per = variant == 2 ? t->intdim : std::min(t->intdim, std::max(1, dcap / (t->cartdim + 1)));
         const uint64_t G = (uint64_t)t->intdim * t->cartdim;
         CUtensorMap tmJ, tmq;
         std::memset(&tmJ, 0, sizeof(tmJ));
@@ -1072,7 +1249,7 @@ int launch_jit_qJ(const tchem_ic_table * t, const double * r, int64_t B, double 
         void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&J};
         TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
     }
-    count_launch(variant == 1 ? "tchem_jit_qJ_bulk" : "tchem_jit_qJ");
+    count_launch(variant == 2 ? "tchem_jit_qJ_group" : variant == 1 ? "tchem_jit_qJ_bulk" : "tchem_jit_qJ");
     return TCHEM_OK;
 }
 
@@ -1088,6 +1265,19 @@ int64_t tchem_ic_jit_source(const tchem_invdisp_t * terms, int n_terms, int n_ic
     if (!terms || n_terms <= 0) return 0;
     std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
     const std::string s = jit_source(v, n_ic, cartdim, dcap > 0 ? dcap : std::max(cartdim + 1, 76), 4, 3);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+// the group variant (G warps of a block share one tile and one whole-geometry TMA box); 0 when not eligible
+int64_t tchem_ic_jit_source_group(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, int G, char * buf, int64_t capacity) {
+    if (!terms || n_terms <= 0) return 0;
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    const std::string s = jit_source_group(v, n_ic, cartdim, G, 3);
     if (buf && capacity > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
         std::memcpy(buf, s.data(), n);
