@@ -725,13 +725,15 @@ def test_specialised_kernel_bulk_store_variant(T):
     oracle) on even / odd cartdim and even / odd row counts; knobs are per process -> subprocesses."""
     import subprocess, sys
     digests = []
-    for bulk in ("1", "0"):
+    # (third run: the opt-in group variant - G warps share a tile and one whole-geometry TMA box - on the shapes it takes)
+    for env in ({"TCHEM_JIT_BULK": "1"}, {"TCHEM_JIT_BULK": "0"}, {"TCHEM_JIT_GROUP": "3"}):
         e = dict(os.environ)
-        e["TCHEM_JIT_BULK"] = bulk
+        e.update(env)
         out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_bulk_check.py")],
                              env=e, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "DIGEST" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
         digests.append(out.stdout.strip().split()[-1])
+    assert digests[0] == digests[2]
     assert digests[0] == digests[1]
 
 

@@ -35,7 +35,7 @@ def run(label, fn, per):
         if buf[i]:
             print("   %-44s %8.0f cycles  %5.1f %%" % (names.get(i, str(i)), buf[i] / per, 100.0 * buf[i] / tot))
 per_block = (B + 147) // 148
-fw = int(os.environ.get("TCHEM_FACTOR_WARPS", "5"))
+fw = int(os.environ.get("TCHEM_FACTOR_WARPS", "6"))
 per_warp = (B + 148 * fw - 1) // (148 * fw)
 run("Hessian_int2cart", lambda: s.Hessian_int2cart(r, gq, Hq), per_block)
 run("gradient_cart2int (one warp of %d)" % fw, lambda: s.gradient_cart2int(r, gr), per_warp)

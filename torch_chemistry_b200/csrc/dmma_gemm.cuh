@@ -43,10 +43,14 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
     const int tm = (M + 15) >> 4, tn = (N + TW - 1) / TW;
     const int K4 = K & ~3;
     const int sa = TA ? lda : 1, sb = TB ? 1 : ldb;          // stride between consecutive k
-    int mt = 0, nt = warp;                                    // tile coordinates, advanced without division
-    while (nt >= tn) { nt -= tn; mt++; }
+    // tile coordinates, advanced without division. Triangular products (TRI != 0; square, tm == tn) enumerate only the
+    // tiles on or below the diagonal, row by row, so that the warps share THOSE evenly (walking the full grid and
+    // skipping the upper tiles left some warps with three tiles and others with none)
+    int mt = 0, nt = warp;
+    if (TRI == 0) { while (nt >= tn) { nt -= tn; mt++; } }
+    else          { while (nt > mt) { nt -= mt + 1; mt++; } }
     for (; mt < tm; ) {
-        if (TRI == 0 || nt <= mt) {
+        {
             const int m0 = mt * 16, n0 = nt * TW;
             const int kbeg = KS == 1 ? m0 : KS == 2 ? n0 : 0;
             double acc[2][WN][2];
@@ -158,7 +162,8 @@ __device__ __forceinline__ void block_dgemm_tiles(int M, int N, int K, const dou
                 }
         }
         nt += nwarps;
-        while (nt >= tn) { nt -= tn; mt++; }
+        if (TRI == 0) { while (nt >= tn) { nt -= tn; mt++; } }
+        else          { while (nt > mt) { nt -= mt + 1; mt++; } }
     }
 }
 

@@ -68,6 +68,8 @@ struct SparseProgram {                // device pointers into one blob (starts a
     int32_t nterms, njrow, nktasks, nnz, nnz_pad, npairs_pad, maxc, ngblk, ngsrc, nslots;
     int32_t natoms;
     int32_t intdim, cartdim, ldh;     // ldh: leading dimension of the intdim x intdim DMMA operands (4 or 12 mod 16)
+    int32_t jv_alias, npairs_lo;      // jv_alias: the factor kernel keeps Jv in the tail of the packed matrix's storage (see factor_kernel);
+                                      // npairs_lo: pairs whose destination lies below that tail
     int32_t factor_tab_bytes;         // leading part of the blob the factor kernel copies to shared memory: pair lists | common tables
     int32_t hess_tab_offset, blob_bytes;   // the block kernel copies [hess_tab_offset, blob_bytes): common tables | its own
     int32_t tab_in_smem;              // per launch: the block kernel works on a shared-memory copy of its part of the blob
@@ -466,10 +468,13 @@ __device__ __forceinline__ void warp_lauum_packed(double * A, int n, int lane) {
 }
 
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
-// shared memory of one warp (doubles): Jv[nnz_pad] | A[tri(n) + n + 2] | rdiag[n] | Ds[192] | rg[cd] | g[cd]
-__host__ __device__ inline int factor_smem_doubles(int n, int cd, int nnz_pad) {
-    return nnz_pad + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 192 + 2 * ((cd + 1) & ~1);
+// shared memory of one warp (doubles): A[tri(n) + n + 2] | rdiag[n] | Ds[192] | rg[cd] | g[cd] | Jv[nnz_pad]; with jv_alias Jv
+// lives in the TAIL of A instead (it is dead once J J^T and the bordered row exist): 32 KB instead of 38 KB per geometry of 84
+// coordinates, i.e. six geometries in flight per SM instead of five
+__host__ __device__ inline int factor_smem_doubles(int n, int cd, int nnz_pad, int jv_alias) {
+    return (jv_alias ? 0 : nnz_pad) + ((n * (n + 1)) / 2 + n + 2) + ((n + 1) & ~1) + 192 + 2 * ((cd + 1) & ~1);
 }
+constexpr int kMaxHiPairs = 8;        // pairs per lane that can wait in registers while Jv still occupies their destination
 
 // OPF 0: g_q = (J J^T)^-1 (J g_r)                     -> gq_out[B][n]
 // OPF 1: the same (g_r may be null) plus the packed inverse -> ainv_out[B][n (n + 1) / 2]
@@ -497,11 +502,15 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
 #undef TC_REBASE
     }
     __syncthreads();
-    double * Jv = sm_dyn + even_up(tab_doubles) + (size_t)warp * even_up(factor_smem_doubles(n, cd, sp.nnz_pad));
-    double * A = Jv + sp.nnz_pad;
-    double * rdiag = A + ntri + n + 2;
+    const int atot = ntri + n + 2;
+    double * A = sm_dyn + even_up(tab_doubles) + (size_t)warp * even_up(factor_smem_doubles(n, cd, sp.nnz_pad, sp.jv_alias));
+    double * rdiag = A + atot;
     double * Ds = rdiag + ((n + 1) & ~1);
     double * rg = Ds + 192, * gs = rg + ((cd + 1) & ~1);
+    // Jv: behind everything else, or (jv_alias) in the tail of A: the pairs / bordered-row entries whose destination it
+    // covers are formed in registers and written once Jv is dead
+    double * Jv = sp.jv_alias ? A + (atot - sp.nnz_pad) : gs + ((cd + 1) & ~1);
+    const int lo_end = sp.jv_alias ? atot - sp.nnz_pad : atot;             // A[0 .. lo_end) does not overlap Jv
     SPHASE_BEGIN(Ds);
     for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
         // the geometry (and the gradient) are read once, coalesced: every later use is a shared-memory read
@@ -509,11 +518,11 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
         for (int p = sp.nnz + lane; p < sp.nnz_pad; p += kLanes) Jv[p] = 0.0;      // the zero entries the padded pair lists point to
         __syncwarp();
         eval_J_rows<HAS5>(sp, rg, Jv, lane, kLanes);
-        for (int p = lane; p < ntri + n + 2; p += kLanes) A[p] = 0.0;
+        for (int p = lane; p < lo_end; p += kLanes) A[p] = 0.0;
         __syncwarp();
         SPHASE(0);
         // A = J J^T over the structurally nonzero pairs of rows: 3 products per common atom
-        for (int p = lane; p < sp.npairs_pad; p += kLanes) {
+        auto pair_value = [&](int p) {
             double s = 0.0;
             for (int e = 0; e < sp.maxc; e += 4) {                                  // (lists padded to a multiple of 4 with zero entries)
                 uint32_t ent[4];
@@ -527,15 +536,37 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
                 }
                 s += (t[0] + t[1]) + (t[2] + t[3]);
             }
-            A[sp.pair_dest[p]] = s;                                                 // padding pairs write the spare element
+            return s;
+        };
+        for (int p = lane; p < sp.npairs_lo; p += kLanes) A[sp.pair_dest[p]] = pair_value(p);
+        // the pairs whose destination Jv still occupies (none without jv_alias; the padding pairs write the spare element)
+        // and the bordered row b = J g_r wait in registers
+        double hv[kMaxHiPairs], bv[kMaxSlots];
+#pragma unroll
+        for (int k = 0; k < kMaxHiPairs; k++) {
+            const int p = sp.npairs_lo + lane + 32 * k;
+            hv[k] = p < sp.npairs_pad ? pair_value(p) : 0.0;
         }
-        // bordered row: b = J g_r
-        if (gr != nullptr) {
-            for (int i = lane; i < n; i += kLanes) {
-                double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = lane + 32 * m;
+            double s = 0.0;
+            if (gr != nullptr && i < n)
                 for (int p = sp.nz_ptr[i]; p < sp.nz_ptr[i + 1]; p++) s = fma(Jv[p], gs[sp.nz_col[p]], s);
-                A[ntri + i] = s;
-            }
+            bv[m] = s;
+        }
+        __syncwarp();                                                               // Jv is dead
+        for (int p = lo_end + lane; p < atot; p += kLanes) A[p] = 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kMaxHiPairs; k++) {
+            const int p = sp.npairs_lo + lane + 32 * k;
+            if (p < sp.npairs_pad) A[sp.pair_dest[p]] = hv[k];
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxSlots; m++) {
+            const int i = lane + 32 * m;
+            if (i < n) A[ntri + i] = bv[m];
         }
         __syncwarp();
         SPHASE(1);
@@ -960,6 +991,9 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             __syncthreads();
             SPHASE(24);
             double * Q = BIG;
+            // (a symmetric second product - lower tiles mirrored - would need an exactly symmetric H_c: the diagonal 3 x 3
+            // blocks of sum_k g_k K[k] come from different Dual passes and are symmetric only to rounding, and checking
+            // costs more than half of what the triangular product saves: measured, not kept)
             block_dgemm<true, false, false>(n, n, cd, MT, ldh, T2, ldh, Q, ldh);         // H_q = M T2     (n x n)
             __syncthreads();
             SPHASE(25);
@@ -1251,6 +1285,14 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     p.factor_tab_bytes = (int32_t)hess_begin;
     p.hess_tab_offset = (int32_t)common_begin;
     p.blob_bytes = (int32_t)off;
+    {
+        // Jv in the tail of the packed matrix (factor_kernel): possible when the pairs that land in that tail fit the registers
+        const int atot = n * (n + 1) / 2 + n + 2, lo_end = atot - nnz_pad;
+        int lo = 0;
+        while (lo < npairs && (int)pair_dest[lo] < lo_end) lo++;
+        p.jv_alias = (lo_end >= 0 && npairs_pad - lo <= 32 * kMaxHiPairs) ? 1 : 0;
+        p.npairs_lo = p.jv_alias ? lo : npairs_pad;
+    }
     p.tab_in_smem = 0;
     st.density = (double)nnz / ((double)n * cd);
     sparse_tables()[t] = st;
@@ -1311,7 +1353,9 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     if (st.density > max_density || st.prog.nnz_pad > 65000 || st.prog.nslots > (1 << 30)) return -1;
     const int ntri = n * (n + 1) / 2;
     // ---- kernel 1 (cart -> int): factor / solve / inverse, one warp per geometry ---------------------------------
-    const size_t fwarp = (size_t)even_up(factor_smem_doubles(n, cd, st.prog.nnz_pad)) * sizeof(double);
+    static const int alias_env = [] { const char * e = getenv("TCHEM_FACTOR_ALIAS"); return e ? atoi(e) : 1; }();
+    if (!alias_env) { st.prog.jv_alias = 0; st.prog.npairs_lo = st.prog.npairs_pad; }
+    const size_t fwarp = (size_t)even_up(factor_smem_doubles(n, cd, st.prog.nnz_pad, st.prog.jv_alias)) * sizeof(double);
     const size_t ftab = (size_t)even_up((st.prog.factor_tab_bytes + 7) / 8) * sizeof(double);
     int fwarps = 0;
     if (op != 2) {
