@@ -15,6 +15,7 @@
 #include <c10/cuda/CUDAStream.h>
 
 #include <tchem/tchem.hpp>
+#include <tchem/chem/normal_mode.hpp>
 #include <tchem/utility.hpp>
 
 #include "../include/tchem_b200.h"
@@ -901,4 +902,127 @@ double NetGradNorm(const std::vector<at::Tensor> & parameters) {
     for (const at::Tensor & p : parameters) if (p.grad().defined()) norm += p.grad().abs().sum().item<double>();
     return norm;
 }
+} }
+
+
+// ---- normal modes (reference source/chem/normal_mode.cpp) ------------------------------
+// Batched device operations: cuBLAS batched products for the reductions, cuSOLVER (through ATen) for the Cholesky
+// factorisations and the symmetric eigen-solves. IntNormalMode::kernel performs the reduction LAPACK dsygv (itype 3)
+// performs behind the reference's Fortran shim: G = L L^T, C = L^T H L, C y = lambda y, x = L y.
+namespace tchem { namespace chem {
+
+namespace {
+at::Tensor to_device_batched(const at::Tensor & t, bool batched) {
+    if (tchem_device_count() <= 0) throw std::runtime_error("tchem::chem: no CUDA device (this library has no CPU path)");
+    at::Tensor b = (batched ? t : t.unsqueeze(0)).to(at::kDouble);
+    return (b.is_cuda() ? b : b.to(at::Device(at::kCUDA, c10::cuda::current_device()))).clone();
+}
+at::Tensor signed_sqrt(const at::Tensor & x) { return at::where(x > 0, x.abs().sqrt(), -x.abs().sqrt()); }
+at::Tensor mass_vector(const std::vector<double> & masses, const at::Tensor & like) {
+    return at::tensor(masses, at::TensorOptions().dtype(at::kDouble)).to(like.device()).repeat_interleave(3);
+}
+}
+
+CartNormalMode::CartNormalMode() {}
+CartNormalMode::CartNormalMode(const std::vector<double> & _masses, const at::Tensor & _Hessian) {
+    if (_Hessian.dim() != 2 && _Hessian.dim() != 3) throw std::invalid_argument("tchem::chem::CartNormalMode: Hessian must be a matrix");
+    if (_Hessian.size(-1) != _Hessian.size(-2)) throw std::invalid_argument("tchem::chem::CartNormalMode: Hessian must be a square matrix");
+    if ((int64_t)(3 * _masses.size()) != _Hessian.size(-1)) throw std::invalid_argument("tchem::chem::CartNormalMode: inconsistent dimension between masses and Hessian");
+    masses_ = _masses;
+    host_ = !_Hessian.is_cuda();
+    batched_ = _Hessian.dim() == 3;
+    Hessian_ = to_device_batched(_Hessian, batched_);
+}
+CartNormalMode::~CartNormalMode() {}
+at::Tensor CartNormalMode::out(const at::Tensor & t) const {
+    at::Tensor r = batched_ ? t : t[0];
+    return host_ ? r.cpu() : r;
+}
+void CartNormalMode::kernel() {
+    at::Tensor s = mass_vector(masses_, Hessian_).sqrt();
+    at::Tensor H = Hessian_ / s.unsqueeze(0).unsqueeze(2) / s.unsqueeze(0).unsqueeze(1);
+    at::Tensor w, v;
+    std::tie(w, v) = at::linalg_eigh(H, "L");
+    at::Tensor modes = v.transpose(1, 2);
+    // rule out the 6 modes of smallest |eigenvalue| (translations and rotations), then ascending frequency
+    at::Tensor keep = at::argsort(w.abs(), /*stable=*/true, 1, false).slice(1, 6);
+    at::Tensor freq = signed_sqrt(w.gather(1, keep));
+    modes = modes.gather(1, keep.unsqueeze(2).expand({-1, -1, modes.size(2)})) / s.unsqueeze(0).unsqueeze(1);
+    at::Tensor order = at::argsort(freq, /*stable=*/true, 1, false);
+    frequency_ = freq.gather(1, order);
+    cartmode_ = modes.gather(1, order.unsqueeze(2).expand({-1, -1, modes.size(2)}));
+    ready_ = true;
+}
+at::Tensor CartNormalMode::frequency() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::CartNormalMode::frequency");
+    return out(frequency_);
+}
+at::Tensor CartNormalMode::cartmode() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::CartNormalMode::cartmode");
+    return out(cartmode_);
+}
+
+IntNormalMode::IntNormalMode() {}
+IntNormalMode::IntNormalMode(const std::vector<double> & _masses, const at::Tensor & _Jacobian, const at::Tensor & _Hessian) {
+    if (_Jacobian.dim() != 2 && _Jacobian.dim() != 3) throw std::invalid_argument("tchem::chem::IntNormalMode: Jacobian must be a matrix");
+    if ((int64_t)(3 * _masses.size()) != _Jacobian.size(-1)) throw std::invalid_argument("tchem::chem::IntNormalMode: inconsistent dimension between masses and Jacobian");
+    if (_Hessian.dim() != _Jacobian.dim()) throw std::invalid_argument("tchem::chem::IntNormalMode: Hessian must be a matrix");
+    if (_Hessian.size(-1) != _Hessian.size(-2)) throw std::invalid_argument("tchem::chem::IntNormalMode: Hessian must be a square matrix");
+    if (_Jacobian.size(-2) != _Hessian.size(-1)) throw std::invalid_argument("tchem::chem::IntNormalMode: inconsistent dimension between Jacobian and Hessian");
+    masses_ = _masses;
+    host_ = !_Jacobian.is_cuda();
+    batched_ = _Jacobian.dim() == 3;
+    Jacobian_ = to_device_batched(_Jacobian, batched_);
+    Hessian_ = to_device_batched(_Hessian, batched_).to(Jacobian_.device());
+}
+IntNormalMode::~IntNormalMode() {}
+void IntNormalMode::kernel() {
+    at::Tensor minv = 1.0 / mass_vector(masses_, Jacobian_);
+    at::Tensor G = at::matmul(Jacobian_ * minv.unsqueeze(0).unsqueeze(1), Jacobian_.transpose(1, 2));
+    at::Tensor L = at::linalg_cholesky(G);
+    at::Tensor C = at::matmul(L.transpose(1, 2), at::matmul(Hessian_, L));
+    C = 0.5 * (C + C.transpose(1, 2));
+    at::Tensor w, Y;
+    std::tie(w, Y) = at::linalg_eigh(C, "L");
+    frequency_ = signed_sqrt(w);
+    intmode_ = at::matmul(L, Y).transpose(1, 2).contiguous();
+    Linv_ = at::cholesky_solve(intmode_.transpose(1, 2), L).transpose(1, 2).contiguous();
+    at::Tensor Lj = at::linalg_cholesky(at::matmul(Jacobian_, Jacobian_.transpose(1, 2)));
+    cartmode_ = at::matmul(at::cholesky_solve(intmode_.transpose(1, 2), Lj).transpose(1, 2), Jacobian_);
+    ready_ = true;
+}
+at::Tensor IntNormalMode::intmode() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::IntNormalMode::intmode");
+    return out(intmode_);
+}
+at::Tensor IntNormalMode::Linv() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::IntNormalMode::Linv");
+    return out(Linv_);
+}
+
+SANormalMode::SANormalMode() {}
+SANormalMode::SANormalMode(const std::vector<double> & _masses, const std::vector<at::Tensor> & _Jacobians, const std::vector<at::Tensor> & _Hessians) {
+    if (_Jacobians.size() != _Hessians.size()) throw std::invalid_argument("tchem::chem::SANormalMode: inconsistent number of irreducibles between Jacobian and Hessian");
+    for (size_t i = 0; i < _Jacobians.size(); i++) parts_.emplace_back(_masses, _Jacobians[i], _Hessians[i]);
+}
+SANormalMode::~SANormalMode() {}
+void SANormalMode::kernel() { for (auto & p : parts_) p.kernel(); ready_ = true; }
+std::vector<at::Tensor> SANormalMode::frequencies() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::SANormalMode::frequencies");
+    std::vector<at::Tensor> v; for (const auto & p : parts_) v.push_back(p.frequency()); return v;
+}
+std::vector<at::Tensor> SANormalMode::intmodes() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::SANormalMode::intmodes");
+    std::vector<at::Tensor> v; for (const auto & p : parts_) v.push_back(p.intmode()); return v;
+}
+std::vector<at::Tensor> SANormalMode::Linvs() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::SANormalMode::Linvs");
+    std::vector<at::Tensor> v; for (const auto & p : parts_) v.push_back(p.Linv()); return v;
+}
+std::vector<at::Tensor> SANormalMode::cartmodes() const {
+    if (!ready_) throw CL::utility::not_ready("tchem::chem::SANormalMode::cartmodes");
+    std::vector<at::Tensor> v; for (const auto & p : parts_) v.push_back(p.cartmode()); return v;
+}
+size_t SANormalMode::NIrreds() const { return parts_.size(); }
+
 } }

@@ -9,6 +9,7 @@
 #include <iostream>
 
 #include <tchem/tchem.hpp>
+#include <tchem/chem/normal_mode.hpp>
 
 namespace {
 int failures = 0;
@@ -205,6 +206,26 @@ int main(int argc, char ** argv) {
         std::cout << "host tensors over " << tchem::b200::host_devices() << " device(s)\n";
         report("compute_IC_J over all devices vs one device", maxabs(Ja - Jb) + maxabs(qa - qb), 0.0);
         tchem::b200::set_host_devices(-1);
+    }
+    {   // normal modes (reference test/normal_mode/main.cpp:49-72): Cartesian and internal-coordinate (GF) analyses of the
+        // same force field give the same frequencies; here on the aniline fixture with a synthetic positive-definite H_q
+        const int64_t n = (int64_t)set.size(), natoms = r_cpu.size(0) / 3;
+        at::Tensor A = at::randn({n, n}, r_cpu.options());
+        at::Tensor Hq = at::matmul(A, A.transpose(0, 1)) / (double)n + at::eye(n, r_cpu.options());
+        std::vector<double> masses(natoms);
+        for (int64_t i = 0; i < natoms; i++) masses[i] = i % 3 == 0 ? 12.0 : (i % 3 == 1 ? 1.00782503223 : 14.0030740048);
+        at::Tensor qv, Jv;
+        std::tie(qv, Jv) = set.compute_IC_J(r);
+        at::Tensor Hr = set.Hessian_int2cart(r, at::zeros({n}, r.options()), Hq.cuda());
+        tchem::chem::CartNormalMode cartvib(masses, Hr);
+        report("observables before kernel() throw not_ready", throws<CL::utility::not_ready>([&] { cartvib.frequency(); }) ? 0 : 1, 0);
+        cartvib.kernel();
+        tchem::chem::IntNormalMode intvib(masses, Jv, Hq.cuda());
+        intvib.kernel();
+        report("normal modes: Cartesian vs internal frequencies", (cartvib.frequency() - intvib.frequency()).norm().item<double>(), 1e-9);
+        report("normal modes: Linv . intmode^T = 1", maxabs(at::matmul(intvib.Linv(), intvib.intmode().transpose(0, 1)) - at::eye(n, r.options())), 1e-9);
+        at::Tensor mw = intvib.cartmode() * at::tensor(masses, r_cpu.options()).repeat_interleave(3).cuda().unsqueeze(0);
+        report("normal modes: Cartesian modes normalised under the mass metric", maxabs(at::matmul(mw, intvib.cartmode().transpose(0, 1)) - at::eye(n, r.options())), 1e-8);
     }
     std::cout << (failures ? "FAILED " : "passed ") << "(" << failures << " failures)\n";
     return failures ? 1 : 0;

@@ -13,6 +13,11 @@
 
 namespace CL { namespace utility {
 
+// thrown by the observables of an analysis whose kernel() has not run (reference source/chem/normal_mode.cpp:79-88)
+class not_ready : public std::runtime_error {
+    public:
+    explicit not_ready(const std::string & what) : std::runtime_error("CL::utility::not_ready: " + what) {}
+};
 class file_error : public std::runtime_error {
 public:
     explicit file_error(const std::string & file) : std::runtime_error("CL::utility::file_error: " + file) {}

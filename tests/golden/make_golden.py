@@ -228,8 +228,23 @@ def round2_goldens():
          K_idx=kidx, K_val=kval, K_shape=np.array(K.shape))
 
 
+def normal_mode_fixture():
+    """`python make_golden.py vib`: the INPUT files of the reference's test/normal_mode (definition, geometry, masses, the
+    Columbus internal-coordinate Hessian as read by test/normal_mode/main.cpp:22-36) - no outputs: the reference's chem module
+    cannot be built here (no Fortran compiler for My_dsygv), see oracle/normal_mode_oracle.py."""
+    d = REF + "/normal_mode/input/"
+    geom = [l.split() for l in open(d + "geom") if l.strip()]
+    r = np.array([[float(x) for x in g[2:5]] for g in geom]).ravel()
+    masses = np.array([float(g[5]) for g in geom])
+    h = np.array(open(d + "hessian").read().split(), dtype=float).reshape(48, 48)
+    save("ref_normal_mode_vib", definition=np.array(open(d + "IntCoordDef").read()), r=r, masses=masses, hessian_raw=h,
+         sections=np.array([27, 21]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+    if len(sys.argv) > 1 and sys.argv[1] == "vib":
+        normal_mode_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "round2":
         round2_goldens()
     elif len(sys.argv) > 1 and sys.argv[1] == "poly":
         polynomial_goldens()

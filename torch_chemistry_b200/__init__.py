@@ -8,6 +8,7 @@ from ._capi import lib as _lib, LIB_PATH, FileError  # noqa: F401  (import fails
 from .intcoord import IntCoordSet  # noqa: F401
 from .sap import SAPSet  # noqa: F401
 from .polynomial import Polynomial, PolynomialSet  # noqa: F401
+from .normal_mode import CartNormalMode, IntNormalMode, SANormalMode  # noqa: F401
 from . import workloads, sharding  # noqa: F401
 
 
