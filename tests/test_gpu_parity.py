@@ -557,6 +557,32 @@ def test_transforms_on_32_reference_geometries_C4(T):
     assert torch.equal(Q1, Qb[7])
 
 
+def test_transform_edge_batches(T):
+    """batches of 1, 2, 149 (one more than the SMs) and 301 geometries through all five transforms: every geometry of a
+    batch must be BIT-identical to the same geometry evaluated alone (fixed summation orders, no atomics; the persistent
+    grids, the double-buffered prefetches and the slice workspace must not leak state between geometries)"""
+    w = T.workloads.get("C4")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    n, cd = s.intdim, s.cartdim
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    r = dev(w.geometries(301, seed=77))
+    gq = torch.randn(301, n, dtype=torch.float64, device="cuda", generator=gen)
+    Hq = torch.randn(301, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    gr = s.gradient_int2cart(r, gq)
+    Hr = s.Hessian_int2cart(r, gq, Hq)
+    full = [s.gradient_cart2int(r, gr), s.gradient_cart2int_matrix(r), Hr, s.Hessian_cart2int(r, gr, Hr)]
+    for B in (1, 2, 149):
+        part = [s.gradient_cart2int(r[:B], gr[:B]), s.gradient_cart2int_matrix(r[:B]), s.Hessian_int2cart(r[:B], gq[:B], Hq[:B]),
+                s.Hessian_cart2int(r[:B], gr[:B], Hr[:B])]
+        for name, a, b in zip(("gradient_cart2int", "gradient_cart2int_matrix", "Hessian_int2cart", "Hessian_cart2int"), part, full):
+            assert torch.equal(a, b[:B]), "%s: batch of %d differs from the first %d of a batch of 301" % (name, B, B)
+    # the last geometry alone (a different position in the persistent schedule)
+    assert torch.equal(s.Hessian_cart2int(r[300], gr[300], Hr[300]), full[3][300])
+    assert torch.equal(s.gradient_cart2int(r[300], gr[300]), full[0][300])
+    # empty batch
+    assert s.Hessian_int2cart(r[:0], gq[:0], Hq[:0]).shape == (0, cd, cd)
+
+
 def test_transform_round_trip_C4(T):
     """test/intcoord/main.cpp:120-149 at BASELINE config 4 (30 atoms, 84 = 3N-6 coordinates):
     int -> cart -> int -> cart reproduces gradient and Hessian; batch larger than the grid."""
@@ -817,7 +843,8 @@ def test_warp_group_kernel_variants(T, env):
 
 
 @pytest.mark.parametrize("env", [{"TCHEM_DENSE_DMMA": "1", "TCHEM_EXPECT_KERNEL": "dense_kernel"},
-                                 {"TCHEM_FACTOR_WARPS": "2", "TCHEM_EXPECT_KERNEL": "factor_kernel"},
+                                 {"TCHEM_FACTOR_WARPS": "2", "TCHEM_FACTOR_ALIAS": "0", "TCHEM_EXPECT_KERNEL": "factor_kernel"},
+                                 {"TCHEM_SPARSE_TABS": "0", "TCHEM_EXPECT_KERNEL": "hess_kernel"},
                                  {"TCHEM_DENSE_DMMA": "1", "TCHEM_DENSE_WORKSPACE": "1", "TCHEM_EXPECT_KERNEL": "dense_kernel"}])
 def test_transform_kernel_variants(T, env):
     """The transforms are served by the sparse-J kernels (ic_sparse.cu) whenever the molecule fits them; the all-DMMA

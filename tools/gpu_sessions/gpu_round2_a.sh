@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session A of round 2: new sparse-J kernels vs the oracle, then the whole suite, smoke and the bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > gpurun_out/a_gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q -k "transform or hessian or cart2int or dense or alternating or round_trip" > gpurun_out/a_t1.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q -x -k "transform or hessian or cart2int or dense or alternating or round_trip or 32_reference" > gpurun_out/b_t1.log 2>&1
 echo "rc $?" >> gpurun_out/b_t1.log

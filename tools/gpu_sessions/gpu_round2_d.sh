@@ -1,7 +1,7 @@
 #!/bin/bash
 # multi-GPU session: (N = 2: whole GPU suite incl. the 2-GPU gather test and the multi-device C++ call,) bench under
 # torchrun, kernel-vs-gather measurement (N = 8: also on 4 of the GPUs). usage: bash tools/gpu_round2_d.sh N
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/d_topo_$N.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # profile session of round 2 (one GPU): launch list of the default bench, one ncu --set full capture per serving kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python tools/profile_all.py > gpurun_out/e_profile_all.log 2>&1 || exit 1
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/e_launch_list.csv \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # validation session (one GPU): whole suite, smoke, default bench (all extras), reference arm, launch lists
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/f_full.log 2>&1
 echo "rc $?" >> gpurun_out/f_full.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for h in 0 1 2; do
   TCHEM_JIT_CACHE=0 TCHEM_JIT_L2HINT=$h timeout 300 python bench.py --workload C2 --extras none --no-e2e --no-cpu-baseline --steps 20 > gpurun_out/g_bench_h$h.json 2> gpurun_out/g_bench_h$h.err

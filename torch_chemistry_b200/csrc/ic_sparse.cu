@@ -1370,7 +1370,8 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     if (op != 1) {
         HessPlan pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, (st.prog.blob_bytes - st.prog.hess_tab_offset + 7) / 8);
         st.prog.tab_in_smem = 1;
-        if ((size_t)pl.total * sizeof(double) + 1024 > (size_t)t->max_smem_optin) {
+        static const int tabs_env = [] { const char * e = getenv("TCHEM_SPARSE_TABS"); return e ? atoi(e) : 1; }();   // 0: tables stay in global memory
+        if (!tabs_env || (size_t)pl.total * sizeof(double) + 1024 > (size_t)t->max_smem_optin) {
             pl = hess_plan(op, n, cd, st.prog.ldh, st.prog.nnz_pad, st.prog.nslots, 0);
             st.prog.tab_in_smem = 0;
         }
