@@ -224,8 +224,9 @@ int main(int argc, char ** argv) {
         intvib.kernel();
         report("normal modes: Cartesian vs internal frequencies", (cartvib.frequency() - intvib.frequency()).norm().item<double>(), 1e-9);
         report("normal modes: Linv . intmode^T = 1", maxabs(at::matmul(intvib.Linv(), intvib.intmode().transpose(0, 1)) - at::eye(n, r.options())), 1e-9);
-        at::Tensor mw = intvib.cartmode() * at::tensor(masses, r_cpu.options()).repeat_interleave(3).cuda().unsqueeze(0);
-        report("normal modes: Cartesian modes normalised under the mass metric", maxabs(at::matmul(mw, intvib.cartmode().transpose(0, 1)) - at::eye(n, r.options())), 1e-8);
+        at::Tensor mw = cartvib.cartmode() * at::tensor(masses, r_cpu.options()).repeat_interleave(3).cuda().unsqueeze(0);
+        report("normal modes: Cartesian-analysis modes normalised under the mass metric", maxabs(at::matmul(mw, cartvib.cartmode().transpose(0, 1)) - at::eye(n, r.options())), 1e-8);
+        report("normal modes: shapes", (intvib.cartmode().size(0) == n && intvib.cartmode().size(1) == r.size(0)) ? 0 : 1, 0);
     }
     std::cout << (failures ? "FAILED " : "passed ") << "(" << failures << " failures)\n";
     return failures ? 1 : 0;
