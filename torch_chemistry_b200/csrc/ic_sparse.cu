@@ -64,7 +64,7 @@ struct SparseProgram {                // device pointers into one blob (starts a
     const uint32_t * pair_ent;        // [maxc][npairs_pad] (Jv position in row i << 16) | Jv position in row j of a common atom
     const uint32_t * gk_blk;          // [ngblk] (atom A << 16) | atom B: 3 x 3 block of the g.K accumulator that receives slots
     const uint32_t * gk_ptr;          // [ngblk + 1]
-    const uint32_t * gk_src;          // [ngsrc] (slot index << 1) | transposed
+    const uint32_t * gk_src;          // [ngsrc] (slot index << 2) | (negated << 1) | transposed
     int32_t nterms, njrow, nktasks, nnz, nnz_pad, npairs_pad, maxc, ngblk, ngsrc, nslots;
     int32_t natoms;
     int32_t intdim, cartdim, ldh;     // ldh: leading dimension of the intdim x intdim DMMA operands (4 or 12 mod 16)
@@ -807,9 +807,10 @@ __device__ __forceinline__ void gather_slots(const SparseProgram & sp, const dou
         for (uint32_t p = sp.gk_ptr[blk]; p < p1; p++) {
             const uint32_t src = sp.gk_src[p];
             const bool tr = src & 1u;
-            const double * q = slots + (src >> 1) + (tr ? k : 3 * k);
+            const double * q = slots + (src >> 2) + (tr ? k : 3 * k);
             const int st = tr ? 3 : 1;
-            s0 += q[0]; s1 += q[st]; s2 += q[2 * st];
+            const double sg = (src & 2u) ? -1.0 : 1.0;             // negated: block (0, 0) of a term from translational invariance
+            s0 = fma(sg, q[0], s0); s1 = fma(sg, q[st], s1); s2 = fma(sg, q[2 * st], s2);
         }
         double * h = H + (3 * (ab >> 16) + k) * ld + 3 * (ab & 0xffffu);
         h[0] += s0; h[1] += s1; h[2] += s2;
@@ -1085,7 +1086,11 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             for (int a = 0; a < 5; a++) st.pos[a] = (int16_t)(a < d.natoms ? atom_pos[i][d.atoms[a]] : zero_pos);
             st.kslot = nslots;
             nslots += 9 * (d.natoms * (d.natoms + 1) / 2);
-            for (int dir = 0; dir < 3 * d.natoms; dir++) ktasks.push_back(((uint32_t)terms.size() << 8) | (uint32_t)dir);
+            // Translational invariance: the second-derivative blocks of a row of atoms sum to zero, K(i, 0) = - sum_{j >= 1} K(i, j).
+            // The direction passes of atom 0 only produce block (0, 0), so they are not run at all for the 2 - 4 atom types
+            // (torsion 9 passes instead of 12, bend 6 of 9, stretch 3 of 6): the gather below builds (0, 0) from the others.
+            for (int dir = (d.natoms >= 2 && d.natoms <= 4) ? 3 : 0; dir < 3 * d.natoms; dir++)
+                ktasks.push_back(((uint32_t)terms.size() << 8) | (uint32_t)dir);
             terms.push_back(st);
         }
         row_ptr.push_back((int32_t)terms.size());
@@ -1212,8 +1217,13 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             for (int j = i; j < N; j++) {
                 const uint32_t base = (uint32_t)(st.kslot + 9 * (i * N - (i * (i - 1)) / 2 + (j - i)));
                 const int A = st.pd.atoms[i], Bt = st.pd.atoms[j];
-                gk[{A, Bt}].push_back(base << 1);
-                if (i != j) gk[{Bt, A}].push_back((base << 1) | 1u);
+                if (i == 0 && j == 0 && N >= 2 && N <= 4) {
+                    // block (0, 0) = - sum_{j >= 1} K(0, j): negated sources, no slot of its own is ever written
+                    for (int jj = 1; jj < N; jj++) gk[{A, A}].push_back(((uint32_t)(st.kslot + 9 * jj) << 2) | 2u);
+                    continue;
+                }
+                gk[{A, Bt}].push_back(base << 2);
+                if (i != j) gk[{Bt, A}].push_back((base << 2) | 1u);
             }
     }
     std::vector<uint32_t> gk_blk, gk_ptr(1, 0), gk_src;
