@@ -60,6 +60,8 @@ struct SparseProgram {                // device pointers into one blob (starts a
     const uint16_t * nz_col;          // [nnz] column of every Jv position
     const uint16_t * col_ptr;         // [natoms + 1] compressed COLUMN BLOCKS: the three columns of an atom share their row list
     const uint32_t * col_ent;         // [nnz / 3] (row << 16) | Jv position of the x component (y, z follow)
+    const uint16_t * aw_ptr;          // [hess warps + 1] the atoms (column blocks) each warp of the block kernel owns in the products with J
+    const uint16_t * aw_atom;         // [natoms] longest-processing-time assignment by the length of the row lists
     const uint32_t * pair_dest;       // [npairs_pad] packed index (i (i + 1) / 2 + j) of a structurally nonzero A[i][j], j <= i
     const uint32_t * pair_ent;        // [maxc][npairs_pad] (Jv position in row i << 16) | Jv position in row j of a common atom
     const uint32_t * gk_blk;          // [ngblk] (atom A << 16) | atom B: 3 x 3 block of the g.K accumulator that receives slots
@@ -687,35 +689,46 @@ __device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t
 //
 // OUT[3 A + c][l] = sum over the rows k of atom A of  J[k][3 A + c] * IN[k][l]     (OUT: cartdim x width): OUT = J^T IN
 // lanes along l (contiguous in IN)
-__device__ __forceinline__ void spmm_JT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
-                                        double * OUT, int ldout) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t in0 = smem_addr(IN) + 8u * (uint32_t)lane;
-    for (int A = warp; A < sp.natoms; A += nwarps) {
-        double acc[3][kMaxSlots];
+template <int NS>
+__device__ __forceinline__ void spmm_JT_slots(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
+                                              double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t in_m[NS];                 // (lanes past the end read a clamped address; their sums are never stored)
+#pragma unroll
+    for (int m = 0; m < NS; m++) in_m[m] = smem_addr(IN) + 8u * (uint32_t)(lane + 32 * m < width ? lane + 32 * m : lane);
+    const uint32_t jv0 = smem_addr(Jv), rowb = 8u * (uint32_t)ldin;
+    for (int ai = sp.aw_ptr[warp]; ai < sp.aw_ptr[warp + 1]; ai++) {
+        const int A = sp.aw_atom[ai];
+        double acc[3][NS];
 #pragma unroll
         for (int c = 0; c < 3; c++)
 #pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) acc[c][m] = 0.0;
+            for (int m = 0; m < NS; m++) acc[c][m] = 0.0;
+        int e = sp.col_ptr[A];
         const int e1 = sp.col_ptr[A + 1];
-        for (int e = sp.col_ptr[A]; e < e1; e++) {
-            const uint32_t ent = sp.col_ent[e];
-            const double * jv = Jv + (ent & 0xffffu);
-            const double v0 = jv[0], v1 = jv[1], v2 = jv[2];
-            const uint32_t row = in0 + 8u * (uint32_t)((ent >> 16) * ldin);
+        // the entry word and the three J values of the NEXT entry are fetched while this one's FMAs run (the chain
+        // entry -> position -> values is two load latencies; col_ent is padded and position 0 is always valid)
+        uint32_t ent = sp.col_ent[e];
+        uint32_t jp = jv0 + 8u * (ent & 0xffffu);
+        double v0 = lds64(jp), v1 = lds64(jp + 8), v2 = lds64(jp + 16);
+        for (; e < e1; e++) {
+            const uint32_t row = (ent >> 16) * rowb;
+            double x[NS];
 #pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                if (32 * m < width) {
-                    // (lanes past the end read a clamped address; their sums are never stored)
-                    const double x = lds64(lane + 32 * m < width ? row + 256u * m : row);
-                    acc[0][m] = fma(v0, x, acc[0][m]);
-                    acc[1][m] = fma(v1, x, acc[1][m]);
-                    acc[2][m] = fma(v2, x, acc[2][m]);
-                }
+            for (int m = 0; m < NS; m++) x[m] = lds64(in_m[m] + row);
+            ent = sp.col_ent[e + 1];
+            jp = jv0 + 8u * (ent & 0xffffu);
+            const double n0 = lds64(jp), n1 = lds64(jp + 8), n2 = lds64(jp + 16);
+#pragma unroll
+            for (int m = 0; m < NS; m++) {
+                acc[0][m] = fma(v0, x[m], acc[0][m]);
+                acc[1][m] = fma(v1, x[m], acc[1][m]);
+                acc[2][m] = fma(v2, x[m], acc[2][m]);
             }
+            v0 = n0; v1 = n1; v2 = n2;
         }
 #pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
+        for (int m = 0; m < NS; m++) {
             const int l = lane + 32 * m;
             if (l < width) {
 #pragma unroll
@@ -724,44 +737,70 @@ __device__ __forceinline__ void spmm_JT(const SparseProgram & sp, const double *
         }
     }
 }
+__device__ __forceinline__ void spmm_JT(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int width,
+                                        double * OUT, int ldout) {
+    switch ((width + 31) >> 5) {       // the slot count as a compile-time constant: no predicates in the entry loop
+    case 1:  spmm_JT_slots<1>(sp, Jv, IN, ldin, width, OUT, ldout); break;
+    case 2:  spmm_JT_slots<2>(sp, Jv, IN, ldin, width, OUT, ldout); break;
+    case 3:  spmm_JT_slots<3>(sp, Jv, IN, ldin, width, OUT, ldout); break;
+    default: spmm_JT_slots<4>(sp, Jv, IN, ldin, width, OUT, ldout); break;
+    }
+}
 // OUT[a][3 B + c] = sum over the rows l of atom B of  IN[a][l] * J[l][3 B + c]     (OUT: height x cartdim): OUT = IN J
 // lanes along a (IN's leading dimension is odd: conflict-free)
-__device__ __forceinline__ void spmm_J(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
-                                       double * OUT, int ldout) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    uint32_t in_m[kMaxSlots];
+template <int NS>
+__device__ __forceinline__ void spmm_J_slots(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
+                                             double * OUT, int ldout) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t in_m[NS];
 #pragma unroll
-    for (int m = 0; m < kMaxSlots; m++) in_m[m] = smem_addr(IN) + 8u * (uint32_t)(min(lane + 32 * m, height - 1) * ldin);
-    for (int Bc = warp; Bc < sp.natoms; Bc += nwarps) {
-        double acc[3][kMaxSlots];
+    for (int m = 0; m < NS; m++) in_m[m] = smem_addr(IN) + 8u * (uint32_t)(min(lane + 32 * m, height - 1) * ldin);
+    const uint32_t jv0 = smem_addr(Jv);
+    for (int ai = sp.aw_ptr[warp]; ai < sp.aw_ptr[warp + 1]; ai++) {
+        const int Bc = sp.aw_atom[ai];
+        double acc[3][NS];
 #pragma unroll
         for (int c = 0; c < 3; c++)
 #pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) acc[c][m] = 0.0;
+            for (int m = 0; m < NS; m++) acc[c][m] = 0.0;
+        int e = sp.col_ptr[Bc];
         const int e1 = sp.col_ptr[Bc + 1];
-        for (int e = sp.col_ptr[Bc]; e < e1; e++) {
-            const uint32_t ent = sp.col_ent[e];
-            const double * jv = Jv + (ent & 0xffffu);
-            const double v0 = jv[0], v1 = jv[1], v2 = jv[2];
+        uint32_t ent = sp.col_ent[e];                                       // next entry's words and values in flight: see spmm_JT
+        uint32_t jp = jv0 + 8u * (ent & 0xffffu);
+        double v0 = lds64(jp), v1 = lds64(jp + 8), v2 = lds64(jp + 16);
+        for (; e < e1; e++) {
             const uint32_t off = 8u * (ent >> 16);
+            double x[NS];
 #pragma unroll
-            for (int m = 0; m < kMaxSlots; m++) {
-                if (32 * m < height) {
-                    const double x = lds64(in_m[m] + off);
-                    acc[0][m] = fma(v0, x, acc[0][m]);
-                    acc[1][m] = fma(v1, x, acc[1][m]);
-                    acc[2][m] = fma(v2, x, acc[2][m]);
-                }
+            for (int m = 0; m < NS; m++) x[m] = lds64(in_m[m] + off);
+            ent = sp.col_ent[e + 1];
+            jp = jv0 + 8u * (ent & 0xffffu);
+            const double n0 = lds64(jp), n1 = lds64(jp + 8), n2 = lds64(jp + 16);
+#pragma unroll
+            for (int m = 0; m < NS; m++) {
+                acc[0][m] = fma(v0, x[m], acc[0][m]);
+                acc[1][m] = fma(v1, x[m], acc[1][m]);
+                acc[2][m] = fma(v2, x[m], acc[2][m]);
             }
+            v0 = n0; v1 = n1; v2 = n2;
         }
 #pragma unroll
-        for (int m = 0; m < kMaxSlots; m++) {
+        for (int m = 0; m < NS; m++) {
             const int a = lane + 32 * m;
             if (a < height) {
                 double * o = OUT + a * ldout + 3 * Bc;
                 o[0] = acc[0][m]; o[1] = acc[1][m]; o[2] = acc[2][m];
             }
         }
+    }
+}
+__device__ __forceinline__ void spmm_J(const SparseProgram & sp, const double * Jv, const double * IN, int ldin, int height,
+                                       double * OUT, int ldout) {
+    switch ((height + 31) >> 5) {
+    case 1:  spmm_J_slots<1>(sp, Jv, IN, ldin, height, OUT, ldout); break;
+    case 2:  spmm_J_slots<2>(sp, Jv, IN, ldin, height, OUT, ldout); break;
+    case 3:  spmm_J_slots<3>(sp, Jv, IN, ldin, height, OUT, ldout); break;
+    default: spmm_J_slots<4>(sp, Jv, IN, ldin, height, OUT, ldout); break;
     }
 }
 
@@ -803,14 +842,26 @@ __device__ __forceinline__ void gather_slots(const SparseProgram & sp, const dou
         const int blk = e / 3, k = e - 3 * blk;
         const uint32_t ab = sp.gk_blk[blk];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        const uint32_t p1 = sp.gk_ptr[blk + 1];
-        for (uint32_t p = sp.gk_ptr[blk]; p < p1; p++) {
-            const uint32_t src = sp.gk_src[p];
-            const bool tr = src & 1u;
-            const double * q = slots + (src >> 2) + (tr ? k : 3 * k);
-            const int st = tr ? 3 : 1;
-            const double sg = (src & 2u) ? -1.0 : 1.0;             // negated: block (0, 0) of a term from translational invariance
-            s0 = fma(sg, q[0], s0); s1 = fma(sg, q[st], s1); s2 = fma(sg, q[2 * st], s2);
+        const uint32_t p0 = sp.gk_ptr[blk], p1 = sp.gk_ptr[blk + 1];
+        // four sources per trip: their table words, then their slots, are loaded together, so a block with many sources
+        // (the diagonal block of a ring atom) pays one load latency per four instead of per source; the additions stay
+        // in table order
+        for (uint32_t p = p0; p < p1; p += 4) {
+            uint32_t src[4];
+            double v[4][3], sg[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) src[u] = sp.gk_src[min(p + u, p1 - 1)];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool tr = src[u] & 1u;
+                const double * q = slots + (src[u] >> 2) + (tr ? k : 3 * k);
+                const int st = tr ? 3 : 1;
+                v[u][0] = q[0]; v[u][1] = q[st]; v[u][2] = q[2 * st];
+                // negated: block (0, 0) of a term from translational invariance; past the end: no contribution
+                sg[u] = (p + u < p1) ? ((src[u] & 2u) ? -1.0 : 1.0) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { s0 = fma(sg[u], v[u][0], s0); s1 = fma(sg[u], v[u][1], s1); s2 = fma(sg[u], v[u][2], s2); }
         }
         double * h = H + (3 * (ab >> 16) + k) * ld + 3 * (ab & 0xffffu);
         h[0] += s0; h[1] += s1; h[2] += s2;
@@ -867,6 +918,7 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
 #define TC_REBASE(field, type) sp.field = reinterpret_cast<const type *>(tb + (reinterpret_cast<const char *>(sp_global.field) - base))
         TC_REBASE(terms, SpTerm); TC_REBASE(row_ptr, int32_t); TC_REBASE(jrow_order, int32_t); TC_REBASE(ktasks, uint32_t);
         TC_REBASE(nz_ptr, uint16_t); TC_REBASE(nz_col, uint16_t); TC_REBASE(col_ptr, uint16_t); TC_REBASE(col_ent, uint32_t);
+        TC_REBASE(aw_ptr, uint16_t); TC_REBASE(aw_atom, uint16_t);
         TC_REBASE(gk_blk, uint32_t); TC_REBASE(gk_ptr, uint32_t); TC_REBASE(gk_src, uint32_t);
         TC_REBASE(sched_ptr, uint16_t); TC_REBASE(sched_step, uint16_t);
 #undef TC_REBASE
@@ -1185,6 +1237,26 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         }
     }
     col_ptr[natoms] = (uint16_t)col_ent.size();
+    // atoms -> warps of the block kernel: a ring atom's row list is three times a hydrogen's, so round robin leaves
+    // some warps with twice the work of others
+    std::vector<uint16_t> aw_ptr(hess_warps + 1, 0), aw_atom;
+    {
+        std::vector<int> order(natoms);
+        for (int a = 0; a < natoms; a++) order[a] = a;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col_ptr[a + 1] - col_ptr[a] > col_ptr[b + 1] - col_ptr[b]; });
+        std::vector<std::vector<uint16_t>> per_warp(hess_warps);
+        std::vector<int> load(hess_warps, 0);
+        for (int a : order) {
+            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            per_warp[w].push_back((uint16_t)a);
+            load[w] += 2 + col_ptr[a + 1] - col_ptr[a];           // (2: the fixed cost of a column block)
+        }
+        for (int w = 0; w < hess_warps; w++) {
+            aw_ptr[w] = (uint16_t)aw_atom.size();
+            for (uint16_t a : per_warp[w]) aw_atom.push_back(a);
+        }
+        aw_ptr[hess_warps] = (uint16_t)aw_atom.size();
+    }
     // J J^T: pairs of rows that share atoms
     std::vector<uint32_t> pair_dest;
     std::vector<std::vector<uint32_t>> pair_lists;
@@ -1227,10 +1299,16 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             }
     }
     std::vector<uint32_t> gk_blk, gk_ptr(1, 0), gk_src;
-    for (const auto & kv : gk) {
-        gk_blk.push_back(((uint32_t)kv.first.first << 16) | (uint32_t)kv.first.second);
-        for (uint32_t s : kv.second) gk_src.push_back(s);
-        gk_ptr.push_back((uint32_t)gk_src.size());
+    {
+        // heaviest blocks first: the gather's first round of threads takes them, the light ones fill the later rounds
+        std::vector<const std::pair<const std::pair<int, int>, std::vector<uint32_t>> *> order;
+        for (const auto & kv : gk) order.push_back(&kv);
+        std::stable_sort(order.begin(), order.end(), [](auto a, auto b) { return a->second.size() > b->second.size(); });
+        for (auto kv : order) {
+            gk_blk.push_back(((uint32_t)kv->first.first << 16) | (uint32_t)kv->first.second);
+            for (uint32_t s : kv->second) gk_src.push_back(s);
+            gk_ptr.push_back((uint32_t)gk_src.size());
+        }
     }
     // blob
     auto a16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -1244,6 +1322,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
                  o_nzptr = place(nz_ptr.size() * 2), o_nzcol = place(nz_col.size() * 2 + 2);
     const size_t hess_begin = off;
     const size_t o_ktasks = place(step_tasks.size() * 4), o_schedptr = place(sched_ptr.size() * 2), o_schedstep = place(sched_step.size() * 2 + 2), o_colptr = place(col_ptr.size() * 2), o_colent = place(col_ent.size() * 4 + 4),
+                 o_awptr = place(aw_ptr.size() * 2), o_awatom = place(aw_atom.size() * 2 + 2),
                  o_gkblk = place(gk_blk.size() * 4 + 4), o_gkptr = place(gk_ptr.size() * 4), o_gksrc = place(gk_src.size() * 4 + 4);
     const size_t total = off + 16;
     std::vector<unsigned char> blob(total, 0);
@@ -1257,6 +1336,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     std::memcpy(blob.data() + o_nzcol, nz_col.data(), nz_col.size() * 2);
     std::memcpy(blob.data() + o_colptr, col_ptr.data(), col_ptr.size() * 2);
     std::memcpy(blob.data() + o_colent, col_ent.data(), col_ent.size() * 4);
+    std::memcpy(blob.data() + o_awptr, aw_ptr.data(), aw_ptr.size() * 2);
+    std::memcpy(blob.data() + o_awatom, aw_atom.data(), aw_atom.size() * 2);
     std::memcpy(blob.data() + o_gkblk, gk_blk.data(), gk_blk.size() * 4);
     std::memcpy(blob.data() + o_gkptr, gk_ptr.data(), gk_ptr.size() * 4);
     std::memcpy(blob.data() + o_gksrc, gk_src.data(), gk_src.size() * 4);
@@ -1282,6 +1363,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     p.nz_col = reinterpret_cast<const uint16_t *>(d + o_nzcol);
     p.col_ptr = reinterpret_cast<const uint16_t *>(d + o_colptr);
     p.col_ent = reinterpret_cast<const uint32_t *>(d + o_colent);
+    p.aw_ptr = reinterpret_cast<const uint16_t *>(d + o_awptr);
+    p.aw_atom = reinterpret_cast<const uint16_t *>(d + o_awatom);
     p.pair_dest = reinterpret_cast<const uint32_t *>(d + o_pdest);
     p.pair_ent = reinterpret_cast<const uint32_t *>(d + o_pent);
     p.gk_blk = reinterpret_cast<const uint32_t *>(d + o_gkblk);
