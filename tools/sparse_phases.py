@@ -26,14 +26,19 @@ names = {0: "factor: J rows + zero A", 1: "factor: J J^T pairs + border row", 2:
          20: "hess c2i: expand inverse + wait H_r", 21: "hess c2i: tasks", 22: "hess c2i: gather", 23: "hess c2i: M^T = J^T inv",
          24: "hess c2i: T2 = H_c M^T (DMMA)", 25: "hess c2i: H_q = M T2 (DMMA)", 26: "hess c2i: store"}
 buf = (ctypes.c_ulonglong * 32)()
+sbuf = (ctypes.c_ulonglong * 96)()
 def run(label, fn, per):
-    fn(); lib.tchem_debug_sparse_phases(buf, 1)          # warm, reset
-    fn(); lib.tchem_debug_sparse_phases(buf, 1)
+    fn(); lib.tchem_debug_sparse_phases(buf, 1); lib.tchem_debug_sparse_steps(sbuf, 1)         # warm, reset
+    fn(); lib.tchem_debug_sparse_phases(buf, 1); lib.tchem_debug_sparse_steps(sbuf, 1)
     tot = sum(buf[i] for i in range(32))
     print("%s: %d geometries through the probed thread, %.0f cycles per geometry" % (label, per, tot / per))
     for i in range(32):
         if buf[i]:
             print("   %-44s %8.0f cycles  %5.1f %%" % (names.get(i, str(i)), buf[i] / per, 100.0 * buf[i] / tot))
+    if any(sbuf):
+        print("   task phase, cycles per warp step (step index: static schedule order of the table): "
+              + " ".join("%d:%.0f" % (i, sbuf[i] / per) for i in range(64) if sbuf[i]))
+        print("   task phase, cycles per warp (whole list): " + " ".join("%.0f" % (sbuf[64 + i] / per) for i in range(16) if sbuf[64 + i]))
 per_block = (B + 147) // 148
 fw = int(os.environ.get("TCHEM_FACTOR_WARPS", "6"))
 per_warp = (B + 148 * fw - 1) // (148 * fw)

@@ -40,13 +40,15 @@
 
 namespace tchem_b200 {
 
-struct SpTerm {                       // 64 bytes
-    PrimDesc pd;                      // pd.out = internal coordinate (row) of the term
-    double coef;
+struct SpTerm {                       // 72 bytes = 18 words: the lanes of a warp step read the same field of CONSECUTIVE terms, and a
+    PrimDesc pd;                      // 16-word stride would put all 32 of them on two banks (measured: a third of the block kernel's
+    double coef;                      // shared-memory wavefronts were bank conflicts); pd.out = internal coordinate (row) of the term
     int16_t pos[5];                   // Jv position of the 3 entries of atom slot a (row-compressed J)
     int16_t pad_;
     int32_t kslot;                    // first slot of the term's block-upper second-derivative storage
+    int32_t pad2_[2];
 };
+static_assert(sizeof(SpTerm) == 72, "SpTerm layout");
 
 struct SparseProgram {                // device pointers into one blob (starts at `terms`)
     const SpTerm *   terms;           // row order
@@ -87,6 +89,7 @@ constexpr int kHessThreads = 384;     // 12 warps: the (term, direction) tasks +
 // (tchem_debug_sparse_phases; tools/sparse_phases.py). Off in the product.
 #ifdef TCHEM_SPARSE_PHASES
 __device__ unsigned long long g_sparse_phase[32];
+__device__ unsigned long long g_sparse_step[96];       // [0, 64): cycles of each warp step of the task phase; [64, 80): cycles of each warp's whole list
 __device__ __forceinline__ long long sphase_clock(const double * probe) {
     const double x = *reinterpret_cast<const volatile double *>(probe);      // the read waits for the barrier's release
     long long t;
@@ -812,7 +815,20 @@ template <bool HAS5>
 __device__ __forceinline__ void run_tasks(const SparseProgram & sp, const double * rg, const double * weight, double sign, double * slots,
                                           const double * rg_next, double * Jv_next) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef TCHEM_SPARSE_PHASES
+    const long long steps_t0 = clock64();
+    long long step_t0 = steps_t0;
+    int step_prev = -1;
+#endif
     for (int s = sp.sched_ptr[warp]; s < sp.sched_ptr[warp + 1]; s++) {
+#ifdef TCHEM_SPARSE_PHASES
+        __syncwarp();
+        if (blockIdx.x == 0 && lane == 0) {
+            const long long t = clock64();
+            if (step_prev >= 0 && step_prev < 64) g_sparse_step[step_prev] += (unsigned long long)(t - step_t0);
+            step_t0 = t; step_prev = sp.sched_step[s];
+        }
+#endif
         const uint32_t task = sp.ktasks[32 * sp.sched_step[s] + lane];
         if (task == 0xffffffffu) continue;
         if (!(task & 0x80000000u)) {
@@ -833,6 +849,14 @@ __device__ __forceinline__ void run_tasks(const SparseProgram & sp, const double
             }
         }
     }
+#ifdef TCHEM_SPARSE_PHASES
+    __syncwarp();
+    if (blockIdx.x == 0 && lane == 0) {
+        const long long t = clock64();
+        if (step_prev >= 0 && step_prev < 64) g_sparse_step[step_prev] += (unsigned long long)(t - step_t0);
+        if (warp < 16) g_sparse_step[64 + warp] += (unsigned long long)(t - steps_t0);
+    }
+#endif
 }
 
 // H[3 A + k][3 B + l] += sum of the block's slots, in table order (no atomics: bit-reproducible); one thread per
@@ -1097,6 +1121,20 @@ int type_cost(int type, int natoms) {          // relative cost of one evaluatio
     return natoms == 2 ? 2 : 0;
 }
 
+// Cost of one warp step of the block kernel's task phase, in units of ~100 cycles as measured on C4 with three warps per
+// scheduler (tools/sparse_phases.py prints the cycles of every step): a Dual pass of a primitive's J, and the plain J
+// of the terms of a row (the J-row steps also zero their row and add into it: a fixed part per step).
+int kdir_step_cost(int type, int natoms) {
+    if (natoms == 5) return 100;
+    if (natoms == 4) return 30;
+    if (natoms == 3) return 21;
+    return natoms == 2 ? 12 : 1;
+}
+int jrow_step_cost(int type, int natoms, int nterms) {
+    const int per_term = natoms == 5 ? 60 : natoms == 4 ? 23 : natoms == 3 ? 10 : 8;
+    return 12 + per_term * nterms;
+}
+
 int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     std::lock_guard<std::mutex> lock(sparse_mutex());
     auto it = sparse_tables().find(t);
@@ -1108,6 +1146,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     std::vector<uint16_t> nz_ptr(1, 0), nz_col;
     std::vector<std::vector<int>> row_atoms(n);
     std::vector<std::map<int, int>> atom_pos(n);              // atom -> first Jv position in that row
+    int nnz_true = 0;
     for (int i = 0; i < n; i++) {
         std::set<int> atoms;
         for (int k : rows[i]) for (int a = 0; a < t->terms[k].natoms; a++) atoms.insert(t->terms[k].atoms[a]);
@@ -1116,6 +1155,10 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             row_atoms[i].push_back(a);
             for (int c = 0; c < 3; c++) nz_col.push_back((uint16_t)(3 * a + c));
         }
+        nnz_true += (int)(nz_col.size() - nz_ptr.back());
+        // rows of even length get one padding position (value always zero, column = the row's last): the lanes of a warp take
+        // consecutive rows of one type, and an odd distance between their positions keeps their 8-byte accesses off each other's banks
+        if (!atoms.empty() && ((nz_col.size() - nz_ptr.back()) & 1) == 0) nz_col.push_back(nz_col.back());
         nz_ptr.push_back((uint16_t)nz_col.size());
     }
     const int nnz = (int)nz_col.size();
@@ -1137,7 +1180,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             st.coef = d.coeff;
             for (int a = 0; a < 5; a++) st.pos[a] = (int16_t)(a < d.natoms ? atom_pos[i][d.atoms[a]] : zero_pos);
             st.kslot = nslots;
-            nslots += 9 * (d.natoms * (d.natoms + 1) / 2);
+            // odd distance between the slot blocks of consecutive terms: the lanes' 8-byte stores spread over all banks
+            nslots += (9 * (d.natoms * (d.natoms + 1) / 2)) | 1;
             // Translational invariance: the second-derivative blocks of a row of atoms sum to zero, K(i, 0) = - sum_{j >= 1} K(i, j).
             // The direction passes of atom 0 only produce block (0, 0), so they are not run at all for the 2 - 4 atom types
             // (torsion 9 passes instead of 12, bend 6 of 9, stretch 3 of 6): the gather below builds (0, 0) from the others.
@@ -1190,7 +1234,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         for (uint32_t task : ktasks) {                          // already sorted by cost, type, direction
             const PrimDesc & pd = terms[task >> 8].pd;
             if (pd.type != gtype && !grp.empty()) { flush_group(grp, gcost); grp.clear(); }
-            gtype = pd.type; gcost = 2 * type_cost(pd.type, pd.natoms);
+            gtype = pd.type; gcost = kdir_step_cost(pd.type, pd.natoms);
             grp.push_back(task);
         }
         if (!grp.empty()) flush_group(grp, gcost);
@@ -1199,7 +1243,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         for (int32_t row : jrow_order) {
             if (row < 0) continue;
             const auto & d = t->terms[rows[row][0]];
-            const int cost = type_cost(d.type, d.natoms) * (int)rows[row].size();
+            const int cost = jrow_step_cost(d.type, d.natoms, (int)rows[row].size());
             if ((cost != prev_cost || (int)d.type != prev_type) && !grp.empty()) { flush_group(grp, std::max(prev_cost, 1)); grp.clear(); }
             prev_cost = cost; prev_type = d.type;
             grp.push_back(0x80000000u | (uint32_t)row);
@@ -1214,10 +1258,18 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return step_cost[a] > step_cost[b]; });
         std::vector<std::vector<uint16_t>> per_warp(hess_warps);
         std::vector<long> load(hess_warps, 0);
+        // two levels: warps w, w + 4, w + 8 share a scheduler (and its FP64 pipe), and a step lasts longer the more its
+        // scheduler has to do - so the heaviest remaining step goes to the least loaded SCHEDULER, there to its least loaded warp
+        // (warps as independent machines left one scheduler with 15 % more work than the others, and the barrier waits for it)
+        long smsp_load[4] = {0, 0, 0, 0};
         for (int k : order) {
-            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            int q = 0;
+            for (int c = 1; c < 4; c++) if (smsp_load[c] < smsp_load[q]) q = c;
+            int w = q;
+            for (int c = q + 4; c < hess_warps; c += 4) if (load[c] < load[w]) w = c;
             per_warp[w].push_back((uint16_t)k);
             load[w] += step_cost[k];
+            smsp_load[q] += step_cost[k];
         }
         for (int w = 0; w < hess_warps; w++) {
             sched_ptr[w] = (uint16_t)sched_step.size();
@@ -1387,7 +1439,7 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
         p.npairs_lo = p.jv_alias ? lo : npairs_pad;
     }
     p.tab_in_smem = 0;
-    st.density = (double)nnz / ((double)n * cd);
+    st.density = (double)nnz_true / ((double)n * cd);
     sparse_tables()[t] = st;
     out = st;
     return TCHEM_OK;
@@ -1408,6 +1460,12 @@ extern "C" __attribute__((visibility("default"))) int tchem_debug_sparse_phases(
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out32, g_sparse_phase, sizeof(g_sparse_phase)) != cudaSuccess) return 1;
     if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_sparse_phase, z, sizeof(z)); }
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) int tchem_debug_sparse_steps(unsigned long long * out96, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out96, g_sparse_step, sizeof(g_sparse_step)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[96] = {0}; cudaMemcpyToSymbol(g_sparse_step, z, sizeof(z)); }
     return 0;
 }
 #endif
