@@ -21,6 +21,7 @@ Hq = torch.randn(B, n, n, dtype=torch.float64, device="cuda", generator=g); Hq =
 Hr = torch.randn(B, cd, cd, dtype=torch.float64, device="cuda", generator=g); Hr = Hr + Hr.transpose(1, 2)
 names = {0: "factor: J rows + zero A", 1: "factor: J J^T pairs + border row", 2: "factor: potrf", 3: "factor: back substitution",
          4: "factor: trtri", 5: "factor: lauum", 6: "factor: write inverse",
+         7: "   (of potrf: panels)", 8: "   (of potrf: trailing DMMA updates)",
          10: "hess i2c: wait H_q", 11: "hess i2c: U = J^T H_q", 12: "hess i2c: X = U J", 13: "hess i2c: tasks (g.K + next J rows)",
          14: "hess i2c: gather", 15: "hess i2c: store",
          20: "hess c2i: expand inverse + wait H_r", 21: "hess c2i: tasks", 22: "hess c2i: gather", 23: "hess c2i: M^T = J^T inv",
@@ -30,7 +31,7 @@ sbuf = (ctypes.c_ulonglong * 96)()
 def run(label, fn, per):
     fn(); lib.tchem_debug_sparse_phases(buf, 1); lib.tchem_debug_sparse_steps(sbuf, 1)         # warm, reset
     fn(); lib.tchem_debug_sparse_phases(buf, 1); lib.tchem_debug_sparse_steps(sbuf, 1)
-    tot = sum(buf[i] for i in range(32))
+    tot = sum(buf[i] for i in range(32) if i not in (7, 8))
     print("%s: %d geometries through the probed thread, %.0f cycles per geometry" % (label, per, tot / per))
     for i in range(32):
         if buf[i]:

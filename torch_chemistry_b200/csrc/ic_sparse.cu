@@ -231,6 +231,9 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
     const int gid = lane >> 2, tig = lane & 3;
     bool ok = true;
     for (int j0 = 0; j0 < n; j0 += kNB) {
+#ifdef TCHEM_SPARSE_PHASES
+        const long long sub_t0 = clock64();
+#endif
         const int bs = min(kNB, n - j0);
         const int nrows = last - j0 + 1;
         bool pok;
@@ -240,6 +243,10 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
         else                  pok = warp_potrf_panel<4>(A, n, last, j0, bs, rdiag, lane);
         ok = ok && pok;
         __syncwarp();
+#ifdef TCHEM_SPARSE_PHASES
+        long long sub_t1 = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sub_t1 = clock64(); g_sparse_phase[7] += (unsigned long long)(sub_t1 - sub_t0); }
+#endif
         const int t0 = j0 + bs;
         if (t0 < n) {                                   // (bs == 8 here: only the last panel can be narrower)
             for (int I = t0; I <= last; I += 8) {
@@ -273,6 +280,9 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
             }
             __syncwarp();
         }
+#ifdef TCHEM_SPARSE_PHASES
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_sparse_phase[8] += (unsigned long long)(clock64() - sub_t1);
+#endif
     }
     return ok;
 }
