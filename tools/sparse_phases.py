@@ -25,7 +25,7 @@ names = {0: "factor: J rows + zero A", 1: "factor: J J^T pairs + border row", 2:
          10: "hess i2c: wait H_q", 11: "hess i2c: U = J^T H_q", 12: "hess i2c: X = U J", 13: "hess i2c: tasks (g.K + next J rows)",
          14: "hess i2c: gather", 15: "hess i2c: store",
          20: "hess c2i: expand inverse + wait H_r", 21: "hess c2i: tasks", 22: "hess c2i: gather", 23: "hess c2i: M^T = J^T inv",
-         24: "hess c2i: T2 = H_c M^T (DMMA)", 25: "hess c2i: H_q = M T2 (DMMA)", 26: "hess c2i: store"}
+         24: "hess c2i: T2 = H_c M^T (DMMA)", 25: "hess c2i: H_q = M T2 (DMMA)", 26: "hess c2i: store", 27: "hess c2i: issue of the next prefetches"}
 buf = (ctypes.c_ulonglong * 32)()
 sbuf = (ctypes.c_ulonglong * 96)()
 def run(label, fn, per):

@@ -18,14 +18,16 @@
 //    (right-looking Cholesky, panels of 8 columns held in registers, pivots exchanged by shuffles), with the
 //    right-hand side J g_r riding along as a bordered row (= the forward substitution), then back substitution.
 //    For the matrix / Hessian entry points the same warp continues with the reference's potri (explicit inverse of
-//    the factor, row-oriented; then W^T W), still in place, and parks the packed inverse and g_q in a workspace.
+//    the factor, row-oriented; then W^T W), still in place, and writes the inverse - expanded to the full symmetric
+//    matrix - and g_q to a workspace.
 //    The serial pivot chain of one geometry overlaps with the other warps' geometries instead of idling a block.
-//  * hess_kernel - one block per geometry: compressed-column products U = J^T H_q, X = U J (int -> cart) or
-//    V = J H_c, S = V J^T and the DMMA products (J J^T)^-1 S (J J^T)^-1 (cart -> int); the second-derivative term
+//  * hess_kernel - one block per geometry: compressed-column products U = J^T H_q, X = U J (int -> cart), or
+//    M^T = J^T (J J^T)^-1 by the same sparse product followed by the two dense DMMA products T2 = H_c M^T,
+//    H_q = M T2 (cart -> int; the reference's order of operations - see the kernel). The second-derivative term
 //    sum_k g_k K[k] is evaluated as (term, direction) Dual passes that park their 3 x 3 blocks in slots, and a fixed-
-//    order gather adds the slots into the accumulator: no atomics, bit-reproducible. The next geometry's operand
-//    matrix is in flight (cp.async) while the current one is being worked on, and its J rows are evaluated by the
-//    threads left over by the (term, direction) tasks.
+//    order gather adds the slots into the accumulator: no atomics, bit-reproducible. The next geometry's matrices
+//    are in flight (TMA bulk copies completing on an mbarrier; cp.async where alignment forbids) while the current
+//    one is being worked on, and its J rows are evaluated by the warps left over by the (term, direction) tasks.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -196,19 +198,35 @@ __device__ __forceinline__ bool warp_potrf_panel(double * A, int n, int last, in
 #pragma unroll
         for (int c = 0; c < kNB; c++) a[m][c] = c <= cmax ? Ai[c] : 0.0;
     }
+    // The 8 x 8 diagonal block is ALSO held, whole, by every lane (broadcast loads) and factored redundantly alongside:
+    // pivots and multipliers then come from the lane's own registers, and the chain per column is rsqrt -> scale -> fma
+    // (about 115 cycles) instead of shuffle -> rsqrt -> scale -> shuffle -> fma (about 175). Same operations in the same
+    // order as the lanes that own those rows perform on a[0][.], so both copies hold the same bits.
+    double dd[kNB][kNB];
+#pragma unroll
+    for (int r = 0; r < kNB; r++) {
+        const int i = min(j0 + r, last);
+        const double * Ad = A + tri(i) + j0;
+#pragma unroll
+        for (int c = 0; c < kNB; c++) dd[r][c] = (c <= r && r < bs) ? Ad[c] : 0.0;
+    }
 #pragma unroll
     for (int c = 0; c < kNB; c++) {
         if (c < bs) {
-            const double d = __shfl_sync(kFull, a[0][c], c);
+            const double d = dd[c][c];
             ok = ok && d > 0.0;
             double rs = rsqrt(d);
             rs = fma(0.5 * rs, fma(-d * rs, rs, 1.0), rs);              // one Newton step: correctly rounded in all but rare cases
             if (lane == 0) rdiag[j0 + c] = rs;
 #pragma unroll
+            for (int r = c; r < kNB; r++) dd[r][c] *= rs;
+#pragma unroll
             for (int m = 0; m < NS; m++) a[m][c] *= rs;                 // the pivot's own lane: d / sqrt(d) = sqrt(d)
 #pragma unroll
             for (int c2 = c + 1; c2 < kNB; c2++) {
-                const double t = __shfl_sync(kFull, a[0][c], c2);       // L[j0 + c2][j0 + c]  (columns >= bs: zeros, harmless)
+                const double t = dd[c2][c];                             // L[j0 + c2][j0 + c]  (columns >= bs: zeros, harmless)
+#pragma unroll
+                for (int r = c2; r < kNB; r++) dd[r][c2] = fma(-dd[r][c], t, dd[r][c2]);
 #pragma unroll
                 for (int m = 0; m < NS; m++) a[m][c2] = fma(-a[m][c], t, a[m][c2]);
             }
@@ -492,7 +510,8 @@ __host__ __device__ inline int factor_smem_doubles(int n, int cd, int nnz_pad, i
 constexpr int kMaxHiPairs = 8;        // pairs per lane that can wait in registers while Jv still occupies their destination
 
 // OPF 0: g_q = (J J^T)^-1 (J g_r)                     -> gq_out[B][n]
-// OPF 1: the same (g_r may be null) plus the packed inverse -> ainv_out[B][n (n + 1) / 2]
+// OPF 1: the same (g_r may be null) plus the inverse as a full symmetric matrix -> ainv_out[B][even_up(n n)] (what the block
+// kernel's single bulk copy per geometry wants; expanding the packed form there cost 7 600 cycles of 8-byte cp.async issue)
 // The block's warps work on different geometries and never meet after the definition tables (the leading
 // `factor_tab_bytes` of the blob: pair lists, terms, compressed-row structure) have been copied to shared memory:
 // every table read is a shared-memory read (from global memory each of them is an L2 round trip on the critical path
@@ -591,7 +610,7 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
             // the reference's at::cholesky throws (IntCoordSet.cpp:182): flag the table, NaN for this geometry
             if (lane == 0) atomicExch(status, 1);
             if (gq_out) for (int i = lane; i < n; i += kLanes) gq_out[b * n + i] = nan64();
-            if (OPF == 1) for (int p = lane; p < ntri; p += kLanes) ainv_out[b * ntri + p] = nan64();
+            if (OPF == 1) for (int p = lane; p < n * n; p += kLanes) ainv_out[b * even_up(n * n) + p] = nan64();
             __syncwarp();
             continue;
         }
@@ -610,8 +629,27 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
             SPHASE(4);
             warp_lauum_packed(A, n, lane);
             SPHASE(5);
-            double * dst = ainv_out + b * ntri;
-            for (int p = lane; p < ntri; p += kLanes) dst[p] = A[p];
+            // full symmetric matrix, four rows per trip (their loads are independent: one latency per trip, not per element)
+            double * dst = ainv_out + b * even_up(n * n);
+            int jc[kMaxSlots], tj[kMaxSlots];
+#pragma unroll
+            for (int m = 0; m < kMaxSlots; m++) { jc[m] = min(lane + 32 * m, n - 1); tj[m] = tri(jc[m]); }
+            for (int i0 = 0; i0 < n; i0 += 4) {
+                double v[4][kMaxSlots];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = min(i0 + u, n - 1), ti = tri(i);
+#pragma unroll
+                    for (int m = 0; m < kMaxSlots; m++)
+                        if (32 * m < n) v[u][m] = A[jc[m] <= i ? ti + jc[m] : tj[m] + i];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+#pragma unroll
+                    for (int m = 0; m < kMaxSlots; m++)
+                        if (i0 + u < n && lane + 32 * m < n) __stcg(dst + (i0 + u) * n + lane + 32 * m, v[u][m]);
+                }
+            }
         }
         __syncwarp();
         SPHASE(6);
@@ -916,16 +954,24 @@ __device__ __forceinline__ void bulk_store_read_done() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_all_done() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// packed inverse of one geometry (workspace) -> full symmetric Ai[n][ldh], element-wise cp.async (no commit): the
-// expansion travels in the background like the operand matrix
-__device__ __forceinline__ void expand_inverse_async(const double * __restrict__ pk, double * Ai, int n, int ldh) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < n; i += nwarps)
-        for (int j = lane; j <= i; j += kLanes) {
-            const double * src = pk + tri(i) + j;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(Ai + i * ldh + j)), "l"(src) : "memory");
-            if (j != i) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(Ai + j * ldh + i)), "l"(src) : "memory");
-        }
+// global -> shared through the TMA unit (1-D bulk copy) with completion on an mbarrier: one instruction per matrix (or per
+// row when the shared-memory rows are padded) instead of thousands of per-thread cp.async - the issue of those was a phase
+// of its own. Protocol per geometry: thread 0 arms the barrier with the byte count, the copies complete_tx on it, every
+// thread waits for the phase (parity flips per use).
+__device__ __forceinline__ void mbar_init(uint64_t * mb, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * mb, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(mb)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(double * dst, const double * src, uint32_t bytes, uint64_t * mb) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(mb)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * mb, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n}\n" ::"r"(smem_addr(mb)), "r"(parity) : "memory");
 }
 
 // OP 0: gradient_cart2int_matrix   ainv (workspace)                                  out = M[n][cd]
@@ -939,8 +985,9 @@ __global__ void __launch_bounds__(kHessThreads, 1)
 hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const double * __restrict__ in1,
             const double * __restrict__ in2, const double * __restrict__ ainv, const int64_t B, double * __restrict__ out) {
     extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) uint64_t big_mbar;          // completion of the bulk copies of a geometry's matrices
+    if (threadIdx.x == 0) { mbar_init(&big_mbar, 1); fence_async_proxy(); }
     const int n = sp_global.intdim, cd = sp_global.cartdim, ldh = sp_global.ldh;
-    const int ntri = (n * (n + 1)) >> 1;
     const int tab_doubles = TABS ? (sp_global.blob_bytes - sp_global.hess_tab_offset + 7) / 8 : 0;
     const HessPlan pl = hess_plan(OP, n, cd, ldh, sp_global.nnz_pad, sp_global.nslots, tab_doubles);
     SparseProgram sp = sp_global;
@@ -973,13 +1020,51 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(vd + i)), "l"(vs + i) : "memory");
     };
     const int big_count = OP == 2 ? n * n : cd * cd;                       // H_q / H_r of one geometry
+    // The matrices of a geometry come through the TMA unit whenever shape and alignment allow 16-byte granules (else per-thread
+    // cp.async, same group discipline): H_q as one bulk copy, the inverse (full symmetric, from the factor kernel's workspace) as
+    // one, H_r row by row into its padded DMMA layout (one instruction each from cd different threads).
+    const int astride = even_up(n * n);
+    const bool bulk_inv = OP != 2;
+    const bool bulk_hq = OP == 2 && ((n * n) & 1) == 0 && (reinterpret_cast<uintptr_t>(in2) & 15) == 0;
+    const bool bulk_hr = OP == 3 && (cd & 1) == 0 && (reinterpret_cast<uintptr_t>(in2) & 15) == 0;
+    const bool bulk_any = bulk_inv || bulk_hq;
+    uint32_t big_parity = 0;
     auto fetch_big = [&](int64_t bb) {
-        if (OP == 2) block_copy_async(in2 + bb * (int64_t)big_count, BIG, big_count);
-        if (OP == 3) {
-            block_rows_async(in2 + bb * (int64_t)big_count, BIG, cd, cd, ldj);       // DMMA operand: padded rows
-            expand_inverse_async(ainv + bb * (int64_t)ntri, THIRD, n, ldh);
+        if (OP == 2) {
+            if (bulk_hq) {
+                if (threadIdx.x == 0) {
+                    fence_async_proxy();
+                    mbar_expect_tx(&big_mbar, (uint32_t)big_count * 8u);
+                    bulk_load(BIG, in2 + bb * (int64_t)big_count, (uint32_t)big_count * 8u, &big_mbar);
+                }
+            } else block_copy_async(in2 + bb * (int64_t)big_count, BIG, big_count);
         }
-        if (OP == 0) expand_inverse_async(ainv + bb * (int64_t)ntri, BIG, n, ldh);
+        if (OP == 3) {
+            double * Ai = THIRD;
+            if (threadIdx.x == 0) {
+                fence_async_proxy();
+                mbar_expect_tx(&big_mbar, (uint32_t)astride * 8u + (bulk_hr ? (uint32_t)big_count * 8u : 0u));
+                bulk_load(Ai, ainv + bb * (int64_t)astride, (uint32_t)astride * 8u, &big_mbar);
+            }
+            if (bulk_hr) {                                                            // DMMA operand: padded rows
+                // (the bulk-copy instruction takes warp-uniform operands, so a warp issues its lanes' copies one after the
+                // other: the rows are dealt to the first lanes of ALL warps, not to the first cd threads)
+                const int nwarps = blockDim.x >> 5, per_warp = (cd + nwarps - 1) / nwarps;
+                const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) * per_warp + lane;
+                if (lane < per_warp && row < cd) {
+                    fence_async_proxy();
+                    bulk_load(BIG + row * ldj, in2 + bb * (int64_t)big_count + row * cd, (uint32_t)cd * 8u, &big_mbar);
+                }
+            } else block_rows_async(in2 + bb * (int64_t)big_count, BIG, cd, cd, ldj);
+        }
+        if (OP == 0 && threadIdx.x == 0) {
+            fence_async_proxy();
+            mbar_expect_tx(&big_mbar, (uint32_t)astride * 8u);
+            bulk_load(BIG, ainv + bb * (int64_t)astride, (uint32_t)astride * 8u, &big_mbar);
+        }
+    };
+    auto wait_big = [&]() {
+        if (bulk_any) { mbar_wait(&big_mbar, big_parity); big_parity ^= 1u; }
     };
 
     // prologue: the first geometry's small inputs and J rows; then its successor's small inputs and its own matrices fly
@@ -1006,13 +1091,14 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
         if (OP == 2) {
             double * Hq = BIG, * U = MID, * X = THIRD;
             cp_async_wait<1>();                                            // H_q of b (the small inputs of bn, fetched last, may still fly)
+            wait_big();
             __syncthreads();                                               // + J rows of b (prologue or previous task phase)
             SPHASE(10);
             spmm_JT(sp, Jv, Hq, n, n, U, ldo);                             // U = J^T H_q        (cd x n)
             if (threadIdx.x == 0) bulk_store_read_done();                  // the previous geometry's X has left shared memory
             __syncthreads();
             SPHASE(11);
-            if (has_next) block_copy_async(in2 + bn * (int64_t)big_count, BIG, big_count);   // H_q is dead: the next one travels during the rest
+            if (has_next) fetch_big(bn);                                   // H_q is dead: the next one travels during the rest
             cp_async_commit();
             spmm_J(sp, Jv, U, ldo, cd, X, cd);                             // X = U J            (cd x cd)
             cp_async_wait<1>();                                            // the small inputs of bn (the next H_q may still fly)
@@ -1039,8 +1125,9 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
         if (OP == 0) {
             double * Ai = BIG, * M = MID;
             cp_async_wait<0>();
+            wait_big();
             __syncthreads();
-            spmm_JT(sp, Jv, Ai, ldh, n, M, n);          // (J^T inv)[c][i] = M[i][c]: stored transposed below
+            spmm_JT(sp, Jv, Ai, n, n, M, n);            // (J^T inv)[c][i] = M[i][c]: stored transposed below
             __syncthreads();
             if (has_next) fetch_big(bn);
             cp_async_commit();
@@ -1064,13 +1151,14 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             SPHASE(20);
             run_tasks<HAS5>(sp, rg, gvec, -1.0, SL, has_next ? rg_of(cur ^ 1) : nullptr, jv_of(cur ^ 1));
             cp_async_wait<0>();                                            // H_r and the inverse of b
+            wait_big();
             __syncthreads();
             SPHASE(21);
             gather_slots(sp, SL, Hc, ldj);                                 // H_c = H_r - sum_k g_q[k] K[k]
             __syncthreads();
             SPHASE(22);
             double * MT = MID;
-            spmm_JT(sp, Jv, Ai, ldh, n, MT, ldh);                          // M^T = J^T inv       (cd x n; inv is symmetric)
+            spmm_JT(sp, Jv, Ai, n, n, MT, ldh);                            // M^T = J^T inv       (cd x n; inv is symmetric, contiguous rows)
             __syncthreads();
             SPHASE(23);
             double * T2 = THIRD;
@@ -1096,6 +1184,7 @@ hess_kernel(const SparseProgram sp_global, const double * __restrict__ r, const 
             cp_async_commit();
             if (has_next) fetch_big(bn);
             cp_async_commit();
+            SPHASE(27);
             cur ^= 1;
         }
     }
@@ -1512,7 +1601,6 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     // stay bit-reproducible; TCHEM_SPARSE_MAX_DENSITY sends denser tables to the DMMA kernels)
     static const double max_density = [] { const char * e = getenv("TCHEM_SPARSE_MAX_DENSITY"); return e ? atof(e) : 1.01; }();
     if (st.density > max_density || st.prog.nnz_pad > 65000 || st.prog.nslots > (1 << 30)) return -1;
-    const int ntri = n * (n + 1) / 2;
     // ---- kernel 1 (cart -> int): factor / solve / inverse, one warp per geometry ---------------------------------
     static const int alias_env = [] { const char * e = getenv("TCHEM_FACTOR_ALIAS"); return e ? atoi(e) : 1; }();
     if (!alias_env) { st.prog.jv_alias = 0; st.prog.npairs_lo = st.prog.npairs_pad; }
@@ -1560,15 +1648,16 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     };
     if (op == 1) return launch_factor(0, r, in1, B, out, nullptr);
     if (op == 2) return launch_hess(2, r, in1, in2, nullptr, B, out);
-    // matrix / Hessian cart -> int: the packed inverses (and g_q) of a slice of the batch go through a stream-ordered workspace
+    // matrix / Hessian cart -> int: the inverses (and g_q) of a slice of the batch go through a stream-ordered workspace
     const int64_t slice = std::min<int64_t>(B, 16384);
     double * ws = nullptr;
-    const size_t ws_doubles = (size_t)slice * (ntri + n);
+    const size_t astride = (size_t)even_up(n * n);              // full symmetric inverse per geometry (+ g_q)
+    const size_t ws_doubles = (size_t)slice * (astride + n);
     if (cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_doubles * sizeof(double), stream) != cudaSuccess) {
         cudaGetLastError();
         return set_error(TCHEM_ENOMEM, "tchem::IC::IntCoordSet: cannot allocate the workspace of the cart2int transforms");
     }
-    double * ws_ainv = ws, * ws_gq = ws + (size_t)slice * ntri;
+    double * ws_ainv = ws, * ws_gq = ws + (size_t)slice * astride;
     rc = TCHEM_OK;
     for (int64_t b0 = 0; b0 < B && rc == TCHEM_OK; b0 += slice) {
         const int64_t nb = std::min<int64_t>(slice, B - b0);
