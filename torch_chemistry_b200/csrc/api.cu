@@ -34,6 +34,19 @@ int ensure_max_dynamic_smem(const void * fn, int device, int max_smem_optin) {
     done.insert({fn, device});
     return TCHEM_OK;
 }
+void keep_async_pool(int device) {
+    static std::mutex m;
+    static std::set<int> done;
+    std::lock_guard<std::mutex> lock(m);
+    if (done.count(device)) return;
+    done.insert(device);
+    const char * e = getenv("TCHEM_KEEP_WORKSPACE");
+    if (e && atoi(e) == 0) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) { cudaGetLastError(); return; }
+    uint64_t threshold = UINT64_MAX;
+    if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold) != cudaSuccess) cudaGetLastError();
+}
 namespace {
 std::mutex g_log_mutex;
 std::map<std::string, int64_t> & kernel_log() { static std::map<std::string, int64_t> m; return m; }

@@ -15,6 +15,11 @@ void count_launch(const char * kernel = nullptr, int n = 1);   // counts a launc
 // (function, device). The attribute belongs to the FUNCTION, which every table shares: setting it to
 // one table's need would lower it under another table's cached launch shape.
 int ensure_max_dynamic_smem(const void * fn, int device, int max_smem_optin);
+// The slice workspaces of the transforms come from the device's default stream-ordered pool (cudaMallocAsync). Its release
+// threshold is 0 by default: every synchronisation hands the memory back to the driver and the next call maps it again
+// (milliseconds for a 0.9 GB slice - seen as occasional 30 % slower steps). Raised once per device so that the pool keeps what the
+// largest call needed; TCHEM_KEEP_WORKSPACE=0 leaves the pool alone.
+void keep_async_pool(int device);
 
 #define TC_CUDA(expr)                                                                        \
     do {                                                                                     \

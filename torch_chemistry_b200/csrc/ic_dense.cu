@@ -749,6 +749,7 @@ int launch_dense(int op, const char * who, const tchem_ic_table * t, const doubl
         TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDenseThreads, 0));
         grid = std::min<int64_t>(B, (int64_t)t->sm_count * std::max(per_sm, 1));
         const size_t bytes = (size_t)grid * pl.total * sizeof(double);
+        keep_async_pool(t->device);
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&workspace), bytes, stream);
         if (e != cudaSuccess) { cudaGetLastError(); return set_error(TCHEM_ECUDA, name + ": cannot allocate the workspace for a molecule of this size"); }
     } else {

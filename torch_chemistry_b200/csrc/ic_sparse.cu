@@ -267,31 +267,41 @@ __device__ __forceinline__ bool warp_potrf_packed(double * A, int n, bool border
 #endif
         const int t0 = j0 + bs;
         if (t0 < n) {                                   // (bs == 8 here: only the last panel can be narrower)
-            for (int I = t0; I <= last; I += 8) {
-                const int i = I + gid, ic = min(i, last);
-                const double * Li = A + tri(ic) + j0 + tig;
-                const double a0 = Li[0], a1 = Li[4];                   // A fragments of the two k-steps: L[i][j0 + tig (+ 4)]
-                double * Ci = A + tri(ic) + 2 * tig;
-                const int jmax = i <= last ? min(i, n - 1) : -1;
-                const int jend = min(I + 8, n);
+            // two row tiles (I, I + 8) x two column tiles per pass: the B fragments are loaded once for both row tiles (-6 % on the
+            // phase; applying the updates one pass later, after the next pass's DMMAs, was measured SLOWER: on the schedulers that
+            // host two of the six warps the phase is bound by the DMMA pipe itself, 16 cycles per instruction, not by the chain)
+            for (int I = t0; I <= last; I += 16) {
+                const int ia = I + gid, ib = I + 8 + gid, ica = min(ia, last), icb = min(ib, last);
+                const double * La = A + tri(ica) + j0 + tig, * Lb = A + tri(icb) + j0 + tig;
+                const double a0 = La[0], a1 = La[4], f0 = Lb[0], f1 = Lb[4];       // A fragments: L[i][j0 + tig (+ 4)]
+                double * Ca = A + tri(ica) + 2 * tig, * Cb = A + tri(icb) + 2 * tig;
+                const int jmax_a = ia <= last ? min(ia, n - 1) : -1, jmax_b = ib <= last ? min(ib, n - 1) : -1;
+                const int jend = min(I + 16, n);
                 // B fragments: L[J + gid][j0 + tig (+ 4)]; the row pointer advances by tri(j + 8) - tri(j) = 8 j + 36
                 int jb = t0 + gid;
                 const double * Lj = A + tri(min(jb, n - 1)) + j0 + tig;
-                // two column tiles per pass: four independent DMMAs in flight
                 for (int J = t0; J < jend; J += 16) {
                     const double b00 = Lj[0], b01 = Lj[4];
                     const double * Lj2 = Lj + (jb + 8 < n ? 8 * jb + 36 : 0);
                     const double b10 = Lj2[0], b11 = Lj2[4];
-                    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
                     dmma(c0, c1, a0, b00);
                     dmma(e0, e1, a0, b10);
+                    dmma(g0, g1, f0, b00);
+                    dmma(h0, h1, f0, b10);
                     dmma(c0, c1, a1, b01);
                     dmma(e0, e1, a1, b11);
+                    dmma(g0, g1, f1, b01);
+                    dmma(h0, h1, f1, b11);
                     const int j = J + 2 * tig;
-                    if (j <= jmax) Ci[J] -= c0;
-                    if (j + 1 <= jmax) Ci[J + 1] -= c1;
-                    if (j + 8 <= jmax) Ci[J + 8] -= e0;            // (the second tile may lie right of the diagonal: nothing stored)
-                    if (j + 9 <= jmax) Ci[J + 9] -= e1;
+                    if (j <= jmax_a) Ca[J] -= c0;                  // (tiles right of a row's diagonal: nothing stored)
+                    if (j + 1 <= jmax_a) Ca[J + 1] -= c1;
+                    if (j + 8 <= jmax_a) Ca[J + 8] -= e0;
+                    if (j + 9 <= jmax_a) Ca[J + 9] -= e1;
+                    if (j <= jmax_b) Cb[J] -= g0;
+                    if (j + 1 <= jmax_b) Cb[J + 1] -= g1;
+                    if (j + 8 <= jmax_b) Cb[J + 8] -= h0;
+                    if (j + 9 <= jmax_b) Cb[J + 9] -= h1;
                     Lj = Lj2 + (jb + 16 < n ? 8 * (jb + 8) + 36 : 0);
                     jb += 16;
                 }
@@ -519,7 +529,8 @@ constexpr int kMaxHiPairs = 8;        // pairs per lane that can wait in registe
 template <int OPF, bool HAS5>
 __global__ void __launch_bounds__(192)
 factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, const double * __restrict__ gr, const int64_t B,
-              double * __restrict__ gq_out, double * __restrict__ ainv_out, int * __restrict__ status) {
+              double * __restrict__ gq_out, double * __restrict__ ainv_out, int * __restrict__ status,
+              unsigned long long * __restrict__ next_geometry) {
     extern __shared__ __align__(16) double sm_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int n = sp_global.intdim, cd = sp_global.cartdim;
@@ -546,7 +557,13 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
     double * Jv = sp.jv_alias ? A + (atot - sp.nnz_pad) : gs + ((cd + 1) & ~1);
     const int lo_end = sp.jv_alias ? atot - sp.nnz_pad : atot;             // A[0 .. lo_end) does not overlap Jv
     SPHASE_BEGIN(Ds);
-    for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    // Geometries are handed out one at a time (a global counter, zeroed before the launch; every warp starts on its own index
+    // and asks for the next one while it works on the current): six warps on four schedulers means two schedulers host two
+    // warps, whose DMMA and FP64 issue they share - with a fixed stride the two lone warps would idle a quarter of the time.
+    int64_t b = (int64_t)blockIdx.x * nwarps + warp;
+    while (b < B) {
+        unsigned long long taken = 0;
+        if (lane == 0) taken = atomicAdd(next_geometry, 1ull);
         // the geometry (and the gradient) are read once, coalesced: every later use is a shared-memory read
         for (int i = lane; i < cd; i += kLanes) { rg[i] = r[b * cd + i]; if (gr != nullptr) gs[i] = gr[b * cd + i]; }
         for (int p = sp.nnz + lane; p < sp.nnz_pad; p += kLanes) Jv[p] = 0.0;      // the zero entries the padded pair lists point to
@@ -612,6 +629,7 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
             if (gq_out) for (int i = lane; i < n; i += kLanes) gq_out[b * n + i] = nan64();
             if (OPF == 1) for (int p = lane; p < n * n; p += kLanes) ainv_out[b * even_up(n * n) + p] = nan64();
             __syncwarp();
+            b = (int64_t)gridDim.x * nwarps + (int64_t)__shfl_sync(kFull, taken, 0);
             continue;
         }
         if (gq_out) {
@@ -653,6 +671,7 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
         }
         __syncwarp();
         SPHASE(6);
+        b = (int64_t)gridDim.x * nwarps + (int64_t)__shfl_sync(kFull, taken, 0);
     }
 }
 
@@ -1500,8 +1519,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     if (e != cudaSuccess) { cudaFree(dev); return set_error(TCHEM_ECUDA, cudaGetErrorString(e)); }
     SparseTable st;
     st.blob = dev;
-    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.status), sizeof(int)));
-    TC_CUDA(cudaMemset(st.status, 0, sizeof(int)));
+    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.status), 4 * sizeof(int)));       // [0] factorisation flag, [2..3] the factor kernel's geometry counter
+    TC_CUDA(cudaMemset(st.status, 0, 4 * sizeof(int)));
     unsigned char * d = static_cast<unsigned char *>(dev);
     SparseProgram & p = st.prog;
     p.terms = reinterpret_cast<const SpTerm *>(d + o_terms);
@@ -1631,7 +1650,9 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
         const void * fn = opf == 0 ? factor_fn<0>(t->has5) : factor_fn<1>(t->has5);
         { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
         const int64_t grid = std::min<int64_t>((nb + fwarps - 1) / fwarps, (int64_t)t->sm_count);
-        void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&gr, (void *)&nb, (void *)&gq, (void *)&ainv, (void *)&st.status};
+        unsigned long long * counter = reinterpret_cast<unsigned long long *>(st.status + 2);      // (8-byte aligned: status is 16 bytes)
+        TC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&gr, (void *)&nb, (void *)&gq, (void *)&ainv, (void *)&st.status, (void *)&counter};
         TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32 * fwarps), args, fsmem, stream));
         count_launch(opf == 0 ? "factor_kernel<solve>" : "factor_kernel<inverse>");
         return TCHEM_OK;
@@ -1653,6 +1674,7 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     double * ws = nullptr;
     const size_t astride = (size_t)even_up(n * n);              // full symmetric inverse per geometry (+ g_q)
     const size_t ws_doubles = (size_t)slice * (astride + n);
+    keep_async_pool(t->device);
     if (cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_doubles * sizeof(double), stream) != cudaSuccess) {
         cudaGetLastError();
         return set_error(TCHEM_ENOMEM, "tchem::IC::IntCoordSet: cannot allocate the workspace of the cart2int transforms");

@@ -92,6 +92,7 @@ extern "C" int tchem_ic_sap_eval_cart(const tchem_ic_table * ic, const tchem_sap
     int64_t slice = (int64_t)std::max<size_t>(1, budget / (per_geom * sizeof(double)));
     slice = std::min<int64_t>(slice, B);
     double * ws = nullptr;
+    keep_async_pool(ic->device);
     if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)slice * per_geom * sizeof(double), stream) != cudaSuccess) {
         cudaGetLastError();
         return set_error(TCHEM_ENOMEM, "tchem_ic_sap_eval_cart: cannot allocate the workspace");
