@@ -219,12 +219,7 @@ __device__ __forceinline__ Pair operator+(Pair x, Pair y) { return mkp(x.a + y.a
 __device__ __forceinline__ Pair operator-(Pair x, Pair y) { return mkp(x.a - y.a, x.b - y.b); }
 __device__ __forceinline__ Pair operator-(Pair x) { return mkp(-x.a, -x.b); }
 __device__ __forceinline__ Pair operator*(Pair x, Pair y) { return mkp(x.a * y.a, x.b * y.b); }
-__device__ __forceinline__ Pair operator+(double c, Pair x) { return mkp(c + x.a, c + x.b); }
 __device__ __forceinline__ Pair operator-(double c, Pair x) { return mkp(c - x.a, c - x.b); }
-__device__ __forceinline__ Pair operator*(double c, Pair x) { return mkp(c * x.a, c * x.b); }
-__device__ __forceinline__ Pair operator*(Pair x, double c) { return mkp(c * x.a, c * x.b); }
-__device__ __forceinline__ Pair sqrt_(Pair x) { return mkp(sqrt(x.a), sqrt(x.b)); }
-__device__ __forceinline__ Pair rcp_(Pair x) { return mkp(1.0 / x.a, 1.0 / x.b); }
 __device__ __forceinline__ Pair rsqrt_(Pair x) { return mkp(rsqrt(x.a), rsqrt(x.b)); }
 
 template <int DUMMY>
