@@ -583,6 +583,31 @@ def test_transform_edge_batches(T):
     assert s.Hessian_int2cart(r[:0], gq[:0], Hq[:0]).shape == (0, cd, cd)
 
 
+def test_cart2int_on_two_streams_of_one_table(T):
+    """The factor kernel hands its geometries out through a counter: the counter belongs to the launch, so two streams working
+    on the SAME IntCoordSet at once must each get exactly their own geometries (bit-identical to the serial calls)."""
+    w = T.workloads.get("C4")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    s.check_factorisation = False                       # (the check synchronises: the two launches must overlap)
+    n, cd = s.intdim, s.cartdim
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    ra, rb = dev(w.geometries(6000, seed=1)), dev(w.geometries(6000, seed=2))
+    ga = torch.randn(6000, cd, dtype=torch.float64, device="cuda", generator=gen)
+    gb = torch.randn(6000, cd, dtype=torch.float64, device="cuda", generator=gen)
+    ref_a, ref_b = s.gradient_cart2int(ra, ga), s.gradient_cart2int(rb, gb)
+    ref_m = s.gradient_cart2int_matrix(rb[:3000])
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(sa):
+            out_a = s.gradient_cart2int(ra, ga)
+        with torch.cuda.stream(sb):
+            out_b = s.gradient_cart2int(rb, gb)
+            out_m = s.gradient_cart2int_matrix(rb[:3000])
+        torch.cuda.synchronize()
+        assert torch.equal(out_a, ref_a) and torch.equal(out_b, ref_b) and torch.equal(out_m, ref_m)
+
+
 def test_transform_round_trip_C4(T):
     """test/intcoord/main.cpp:120-149 at BASELINE config 4 (30 atoms, 84 = 3N-6 coordinates):
     int -> cart -> int -> cart reproduces gradient and Hessian; batch larger than the grid."""

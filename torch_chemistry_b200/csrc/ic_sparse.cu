@@ -557,7 +557,7 @@ factor_kernel(const SparseProgram sp_global, const double * __restrict__ r, cons
     double * Jv = sp.jv_alias ? A + (atot - sp.nnz_pad) : gs + ((cd + 1) & ~1);
     const int lo_end = sp.jv_alias ? atot - sp.nnz_pad : atot;             // A[0 .. lo_end) does not overlap Jv
     SPHASE_BEGIN(Ds);
-    // Geometries are handed out one at a time (a global counter, zeroed before the launch; every warp starts on its own index
+    // Geometries are handed out one at a time (a global counter owned by the launch, zeroed before it; every warp starts on its own index
     // and asks for the next one while it works on the current): six warps on four schedulers means two schedulers host two
     // warps, whose DMMA and FP64 issue they share - with a fixed stride the two lone warps would idle a quarter of the time.
     int64_t b = (int64_t)blockIdx.x * nwarps + warp;
@@ -1519,8 +1519,8 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
     if (e != cudaSuccess) { cudaFree(dev); return set_error(TCHEM_ECUDA, cudaGetErrorString(e)); }
     SparseTable st;
     st.blob = dev;
-    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.status), 4 * sizeof(int)));       // [0] factorisation flag, [2..3] the factor kernel's geometry counter
-    TC_CUDA(cudaMemset(st.status, 0, 4 * sizeof(int)));
+    TC_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.status), sizeof(int)));
+    TC_CUDA(cudaMemset(st.status, 0, sizeof(int)));
     unsigned char * d = static_cast<unsigned char *>(dev);
     SparseProgram & p = st.prog;
     p.terms = reinterpret_cast<const SpTerm *>(d + o_terms);
@@ -1650,10 +1650,16 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
         const void * fn = opf == 0 ? factor_fn<0>(t->has5) : factor_fn<1>(t->has5);
         { const int rc_ = ensure_max_dynamic_smem(fn, t->device, t->max_smem_optin); if (rc_ != TCHEM_OK) return rc_; }
         const int64_t grid = std::min<int64_t>((nb + fwarps - 1) / fwarps, (int64_t)t->sm_count);
-        unsigned long long * counter = reinterpret_cast<unsigned long long *>(st.status + 2);      // (8-byte aligned: status is 16 bytes)
-        TC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        // the geometry counter belongs to THIS launch (stream-ordered allocation from the retained pool: microseconds), so that
+        // launches on the same table from different streams cannot take each other's geometries
+        unsigned long long * counter = nullptr;
+        keep_async_pool(t->device);
+        TC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&counter), sizeof(unsigned long long), stream));
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
         void * args[] = {(void *)&st.prog, (void *)&rr, (void *)&gr, (void *)&nb, (void *)&gq, (void *)&ainv, (void *)&st.status, (void *)&counter};
-        TC_CUDA(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32 * fwarps), args, fsmem, stream));
+        if (e == cudaSuccess) e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(32 * fwarps), args, fsmem, stream);
+        cudaFreeAsync(counter, stream);
+        if (e != cudaSuccess) return set_error(TCHEM_ECUDA, std::string("factor_kernel launch: ") + cudaGetErrorString(e));
         count_launch(opf == 0 ? "factor_kernel<solve>" : "factor_kernel<inverse>");
         return TCHEM_OK;
     };
