@@ -213,6 +213,10 @@ TCHEM_API int64_t tchem_sap_jit_source(const int32_t * term_ptr, const int32_t *
 TCHEM_API int64_t tchem_ic_sap_jit_cart_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim,
                                                const int32_t * term_ptr, const int32_t * coords, int n_sap,
                                                const int32_t * dims, int n_irreducibles, char * buf, int64_t capacity);
+/* the same pair kernel with whole-tile TMA bulk stores (tchem_jit_chain_cart_bulk); 0 when the pair is not eligible (odd row lengths) */
+TCHEM_API int64_t tchem_ic_sap_jit_cart_bulk_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim,
+                                                    const int32_t * term_ptr, const int32_t * coords, int n_sap,
+                                                    const int32_t * dims, int n_irreducibles, char * buf, int64_t capacity);
 TCHEM_API int tchem_ic_jit_compile_check(const char * source, char * log, int64_t capacity);
 /* 1 when a q + J call on B geometries is served by the specialised kernel, 0 = interpreter */
 TCHEM_API int tchem_ic_uses_specialised(const tchem_ic_table * t, int64_t B);

@@ -366,9 +366,10 @@ def test_chained_cartesian_derivatives(T):
         return out
 
     r = w.geometries(20011, seed=31)                       # ragged tile, above the specialised kernel's threshold
-    before = T.kernel_log().get("tchem_jit_chain_cart", 0)
+    served = lambda: T.kernel_log().get("tchem_jit_chain_cart", 0) + T.kernel_log().get("tchem_jit_chain_cart_bulk", 0)
+    before = served()
     y, g = sap.chained_cart(ic, dev(r))
-    assert T.kernel_log().get("tchem_jit_chain_cart", 0) == before + 1
+    assert served() == before + 1
     idx = np.arange(0, 20011, 997)
     yo, go = reference(r[idx], False)
     assert_parity(host(y)[idx], yo, "C5 chained Cartesian: values (specialised)")
@@ -395,6 +396,22 @@ def test_chained_cartesian_derivatives(T):
     q, J = oic2.qJ(r2[::1000])
     assert_parity(host(g3)[::1000], np.einsum("btk,bkc->btc", osap2.jacobian(q), J), "C2 chained Cartesian: dy/dr")
     assert_parity(host(y3)[::1000], osap2.value(q), "C2 chained Cartesian: values")
+
+
+def test_chained_cartesian_kernel_variants(T):
+    """The pair kernel with the Cartesian Jacobian exists with whole-tile TMA bulk stores (default when the row lengths are even)
+    and with warp copy-out (TCHEM_JIT_BULK=0): same literal expressions per element, so the results must be the same bytes."""
+    import subprocess, sys
+    out = {}
+    for bulk in ("1", "0"):
+        e = dict(os.environ)
+        e["TCHEM_JIT_BULK"] = bulk
+        p = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_cart_variant_check.py")],
+                           env=e, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        out[bulk] = p.stdout.strip().split()
+    assert out["1"][0] == "tchem_jit_chain_cart_bulk" and out["0"][0] == "tchem_jit_chain_cart", out
+    assert out["1"][1] == out["0"][1], out
 
 
 def test_chained_specialised_multichunk_C2(T):

@@ -275,3 +275,15 @@ def test_chained_cartesian_jacobian_source_compiles_for_sm100a():
         if rc != 0 and "not available" in log.value.decode():
             pytest.skip("NVRTC not available")
         assert rc == 0, log.value.decode()[-2000:]
+        # the same pair with whole-tile TMA bulk stores (needs an even number of monomials)
+        n = lib.tchem_ic_sap_jit_cart_bulk_source(terms, nt.value, nic.value, cd, tp, cs, ns.value, d, len(dims), None, 0)
+        if ns.value % 2:
+            assert n == 0
+            continue
+        assert n > 0
+        buf = C.create_string_buffer(n)
+        lib.tchem_ic_sap_jit_cart_bulk_source(terms, nt.value, nic.value, cd, tp, cs, ns.value, d, len(dims), buf, n)
+        src = buf.value.decode()
+        assert "tchem_jit_chain_cart_bulk" in src and "cp.async.bulk.global.shared::cta" in src and "#define SDO %d" % cd in src
+        rc = lib.tchem_ic_jit_compile_check(src.encode(), log, 1 << 16)
+        assert rc == 0, log.value.decode()[-2000:]

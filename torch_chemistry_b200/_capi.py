@@ -83,6 +83,7 @@ _sig("tchem_ic_sap_eval", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp, _vp)
 _sig("tchem_ic_sap_eval_host", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp)
 _sig("tchem_ic_sap_eval_cart", _int, _vp, _vp, _dp, _i64, _dp, _dp, _dp, _vp)
 _sig("tchem_ic_sap_jit_cart_source", _i64, C.POINTER(InvDisp), _int, _int, _int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _int, C.POINTER(C.c_int32), _int, C.c_char_p, _i64)
+_sig("tchem_ic_sap_jit_cart_bulk_source", _i64, C.POINTER(InvDisp), _int, _int, _int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _int, C.POINTER(C.c_int32), _int, C.c_char_p, _i64)
 
 # every symbol include/tchem_b200.h declares (checked by tests/test_capi.py)
 DECLARED = ["tchem_last_error", "tchem_device_count", "tchem_launch_count", "tchem_kernel_log", "tchem_jit_stats", "tchem_ic_parse_file",
@@ -91,7 +92,7 @@ DECLARED = ["tchem_last_error", "tchem_device_count", "tchem_launch_count", "tch
             "tchem_sap_table_create", "tchem_sap_table_destroy", "tchem_sap_table_nterms", "tchem_sap_table_sumdim",
             "tchem_ic_eval", "tchem_ic_eval_host", "tchem_ic_eval_timed", "tchem_ic_grad_int2cart",
             "tchem_ic_grad_cart2int", "tchem_ic_grad_cart2int_matrix", "tchem_ic_hess_int2cart",
-            "tchem_ic_hess_cart2int", "tchem_ic_factor_status", "tchem_ic_program_export", "tchem_ic_jit_source", "tchem_ic_jit_source_bulk", "tchem_ic_jit_source_group", "tchem_sap_jit_hess_source", "tchem_sap_jit_source", "tchem_ic_jit_compile_check", "tchem_ic_uses_specialised", "tchem_ic_sap_uses_specialised", "tchem_sap_eval", "tchem_sap_jacobian2nd", "tchem_ic_sap_eval", "tchem_ic_sap_eval_host", "tchem_ic_sap_eval_cart", "tchem_ic_sap_jit_cart_source"]
+            "tchem_ic_hess_cart2int", "tchem_ic_factor_status", "tchem_ic_program_export", "tchem_ic_jit_source", "tchem_ic_jit_source_bulk", "tchem_ic_jit_source_group", "tchem_sap_jit_hess_source", "tchem_sap_jit_source", "tchem_ic_jit_compile_check", "tchem_ic_uses_specialised", "tchem_ic_sap_uses_specialised", "tchem_sap_eval", "tchem_sap_jacobian2nd", "tchem_ic_sap_eval", "tchem_ic_sap_eval_host", "tchem_ic_sap_eval_cart", "tchem_ic_sap_jit_cart_source", "tchem_ic_sap_jit_cart_bulk_source"]
 
 
 class FileError(OSError):

@@ -349,16 +349,17 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     std::vector<std::vector<std::pair<double, int>>> rows;
     if (!plain && !collect(terms, n_ic, prims, rows)) return std::string();
     const int nt = (int)saps.size(), sd = n_ic;
-    if (cart && (plain || bulk)) return std::string();
+    if (cart && plain) return std::string();
     const int sdo = cart ? cartdim : sd;              // row length of the Jacobian that leaves the kernel
     const int per_term = 1 + sdo;
     if (per_term > dcap) return std::string();
     const int tper = chain_terms_per_chunk(nt, per_term, dcap);
-    if (bulk && !chain_bulk_eligible(nt, sd, dcap)) return std::string();
+    // (cart + bulk: the box holds [32][NT] values and [32][NT * CD] Cartesian rows per warp; dcap only sizes the q staging)
+    if (bulk && !(cart ? nt % 2 == 0 && (nt * sdo) % 2 == 0 : chain_bulk_eligible(nt, sd, dcap))) return std::string();
     std::ostringstream o;
     o << "#define NT " << nt << "\n#define SD " << sd << "\n#define SDO " << sdo << "\n";
     if (bulk)
-        emit_prologue(o, "tchem_jit_chain_bulk", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
+        emit_prologue(o, cart ? "tchem_jit_chain_cart_bulk" : "tchem_jit_chain_bulk", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
                       cartdim, sd, warps, blocks, prims, plain ? sd : 0, 32 * nt * per_term);
     else
     emit_prologue(o, cart ? "tchem_jit_chain_cart" : "tchem_jit_chain", "double * __restrict__ q, double * __restrict__ y, double * __restrict__ J",
@@ -399,29 +400,47 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
     auto power = [](int col, int p) { return "x" + std::to_string(col) + "p" + std::to_string(p); };
     if (bulk) {
         // boxes: [32][NT] values, then [32][NT * SD] Jacobian rows; a lane owns row `lane` of both
-        std::vector<std::string> yv(nt), jv((size_t)nt * sd, "0.0");
+        std::vector<std::string> yv(nt), jv((size_t)nt * sdo, "0.0");
+        std::ostringstream gdefs;                          // cart: the nonzero d SAP / d q_k as named values
         for (int t = 0; t < nt; t++) {
             std::string v;
             for (auto & u : saps[t]) v = v.empty() ? power(u.first, u.second) : v + " * " + power(u.first, u.second);
             yv[t] = v.empty() ? "1.0" : v;
+            std::vector<std::string> g(sd, "0.0");
             for (size_t ui = 0; ui < saps[t].size(); ui++) {
                 const auto & u = saps[t][ui];
                 std::string e = hexd((double)u.second);
                 if (u.second > 1) e += " * " + power(u.first, u.second - 1);
                 for (size_t wi = 0; wi < saps[t].size(); wi++)
                     if (wi != ui) e += " * " + power(saps[t][wi].first, saps[t][wi].second);
-                jv[(size_t)t * sd + u.first] = e;
+                g[u.first] = e;
+            }
+            if (!cart) {
+                for (int k = 0; k < sd; k++) jv[(size_t)t * sd + k] = g[k];
+                continue;
+            }
+            // d/dr_c = sum_k (d/dq_k) J[k][c] over the rows k where both factors are structurally nonzero
+            for (int k = 0; k < sd; k++)
+                if (g[k] != "0.0") gdefs << "            const double g" << t << "_" << k << " = " << g[k] << ";\n";
+            for (int c = 0; c < sdo; c++) {
+                std::string e;
+                for (int k = 0; k < sd; k++) {
+                    if (g[k] == "0.0" || !jnz[k][c]) continue;
+                    const std::string gk = "g" + std::to_string(t) + "_" + std::to_string(k), jk = "J" + std::to_string(k) + "_" + std::to_string(c);
+                    e = e.empty() ? gk + " * " + jk : "fma(" + gk + ", " + jk + ", " + e + ")";
+                }
+                if (!e.empty()) jv[(size_t)t * sdo + c] = e;
             }
         }
-        o << "        {\n"
+        o << "        {\n" << gdefs.str()
           << "            const int row = warp * LANES + lane;                   // this geometry's row in the block's boxes\n"
-          << "            double * Yb = Box + row * NT, * Jb = Box + nwarps * LANES * NT + row * (NT * SD);\n"
+          << "            double * Yb = Box + row * NT, * Jb = Box + nwarps * LANES * NT + row * (NT * SDO);\n"
           << "            // the previous block tile's stores have read the boxes\n"
           << "            if (threadIdx.x == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
           << "            __syncthreads();\n";
         for (int t = 0; t < nt; t += 2)
             o << "            *reinterpret_cast<double2 *>(Yb + " << t << ") = make_double2(" << yv[t] << ", " << yv[t + 1] << ");\n";
-        for (int e = 0; e < nt * sd; e += 2)
+        for (int e = 0; e < nt * sdo; e += 2)
             if (jv[e] != "0.0" || jv[e + 1] != "0.0")
                 o << "            *reinterpret_cast<double2 *>(Jb + " << e << ") = make_double2(" << jv[e] << ", " << jv[e + 1] << ");\n";
         o << "            asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
@@ -431,7 +450,7 @@ std::string jit_chain_source(const std::vector<tchem_invdisp_t> & terms, int n_i
           << "                const int nblk = (int)min((int64_t)nwarps * LANES, B - g0);\n"
           << "                const uint32_t box_sh = (uint32_t)__cvta_generic_to_shared(Box);\n"
           << "                if (y) asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(y + g0 * NT), \"r\"(box_sh), \"r\"(nblk * (NT * 8)) : \"memory\");\n"
-          << "                if (J) asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(J + g0 * (NT * SD)), \"r\"(box_sh + nwarps * LANES * NT * 8), \"r\"(nblk * (NT * SD * 8)) : \"memory\");\n"
+          << "                if (J) asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(J + g0 * (NT * SDO)), \"r\"(box_sh + nwarps * LANES * NT * 8), \"r\"(nblk * (NT * SDO * 8)) : \"memory\");\n"
           << "                asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n"
           << "            }\n        }\n    }\n"
           << "    if (threadIdx.x == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n}\n";
@@ -1111,7 +1130,12 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
     // single-chunk sets: whole-tile TMA bulk stores (16-byte aligned results, even row lengths)
     int variant = want_bulk && chain_bulk_eligible(nt, st->sumdim, dcap)
                   && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 1 : 0;
-    if (cart) variant = 2;                         // variant 2: Cartesian Jacobian (warp copy-out)
+    // Cartesian Jacobian: variant 3 (whole-tile TMA bulk stores: [32][NT] values + [32][NT * cartdim] rows per warp must leave
+    // room for at least two boxes per SM) or variant 2 (warp copy-out)
+    const size_t cart_box = chain_warp_doubles(in_dim, st->sumdim, 32 * nt * per_term) * sizeof(double);
+    if (cart) variant = want_bulk && nt % 2 == 0 && (nt * t->cartdim) % 2 == 0 && 2 * cart_box + 2048 <= (size_t)st->max_smem_optin
+                        && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(J)) & 15) == 0 ? 3 : 2;
+    static const char * const names[4] = {"tchem_jit_chain", "tchem_jit_chain_bulk", "tchem_jit_chain_cart", "tchem_jit_chain_cart_bulk"};
     JitKernel * k = nullptr;
     for (; variant >= 0; variant--) {
         std::lock_guard<std::mutex> lock(jit_mutex());
@@ -1121,15 +1145,20 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
             // 2 warps x 4 blocks 86.5 %, 4 x 2 89.0 %, 8 x 1 83 % (too few independent blocks per SM)
             jk.warps = env_int("TCHEM_JIT_WARPS", 4);
             jk.blocks = env_int("TCHEM_JIT_BLOCKS", 2);
+            if (variant == 3) {
+                // one warp per block, as many independent blocks as fit: a block's store overlaps the other blocks' arithmetic
+                jk.warps = env_int("TCHEM_JIT_CART_WARPS", 1);
+                jk.blocks = std::max(1, std::min(env_int("TCHEM_JIT_CART_BLOCKS", 8), (int)((size_t)st->max_smem_optin / (jk.warps * cart_box + 1024))));
+            }
             const int tper = chain_terms_per_chunk(nt, per_term, dcap);
             static const std::vector<tchem_invdisp_t> no_terms;
-            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks, variant == 1, variant == 2);
-            const size_t smem = variant == 1 ? (size_t)jk.warps * chain_warp_doubles(in_dim, st->sumdim, 32 * nt * per_term) * sizeof(double)
-                                             : (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
-            jit_finish(jk, src, variant == 1 ? "tchem_jit_chain_bulk" : variant == 2 ? "tchem_jit_chain_cart" : "tchem_jit_chain", smem, st->max_smem_optin, debug);
+            const std::string src = jit_chain_source(t ? t->terms : no_terms, st->sumdim, in_dim, st->h_terms, dcap, jk.warps, jk.blocks, variant == 1 || variant == 3, variant >= 2);
+            const size_t smem = (variant == 1 || variant == 3) ? (size_t)jk.warps * chain_warp_doubles(in_dim, st->sumdim, 32 * nt * per_term) * sizeof(double)
+                                                               : (size_t)jk.warps * (in_dim + std::max(tper * per_term, st->sumdim)) * 33 * sizeof(double);
+            jit_finish(jk, src, names[variant], smem, st->max_smem_optin, debug);
         }
         if (!jk.failed) { k = &jk; break; }
-        if (cart) break;                           // no other specialised flavour computes the Cartesian product
+        if (cart && variant == 2) break;           // no other specialised flavour computes the Cartesian product
     }
     if (!k) return jit_strict() ? set_error(TCHEM_ECUDA, "tchem: the specialised chained kernel could not be built (TCHEM_JIT_STRICT=1)") : -1;
     const int64_t ntiles = (B + 31) / 32;
@@ -1137,7 +1166,7 @@ int launch_jit_chain(const tchem_sap_table * st, const tchem_ic_table * t, const
     long long Bll = B;
     void * args[] = {(void *)&r, (void *)&Bll, (void *)&q, (void *)&y, (void *)&J};
     TC_CUDA(cudaLaunchKernel((const void *)k->fn, dim3((unsigned)grid), dim3(k->warps * 32), args, k->smem, stream));
-    count_launch(variant == 1 ? "tchem_jit_chain_bulk" : variant == 2 ? "tchem_jit_chain_cart" : "tchem_jit_chain");
+    count_launch(names[variant]);
     return TCHEM_OK;
 }
 
@@ -1362,6 +1391,28 @@ int64_t tchem_ic_sap_jit_cart_source(const tchem_invdisp_t * terms, int n_terms,
     const int dcap = n_sap * per_term <= 128 ? n_sap * per_term : std::max(per_term, 120);
     std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
     const std::string s = jit_chain_source(v, n_ic, cartdim, saps, dcap, 4, 2, false, true);
+    if (buf && capacity > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + (s.empty() ? 0 : 1);
+}
+
+int64_t tchem_ic_sap_jit_cart_bulk_source(const tchem_invdisp_t * terms, int n_terms, int n_ic, int cartdim, const int32_t * term_ptr,
+                                          const int32_t * coords, int n_sap, const int32_t * dims, int n_irreducibles, char * buf, int64_t capacity) {
+    if (!terms || !term_ptr || !dims || n_terms <= 0 || n_sap <= 0 || n_irreducibles <= 0) return 0;
+    std::vector<int> offset(n_irreducibles + 1, 0);
+    for (int i = 0; i < n_irreducibles; i++) offset[i + 1] = offset[i] + dims[i];
+    if (offset[n_irreducibles] != n_ic) return 0;
+    std::vector<std::vector<std::pair<int, int>>> saps(n_sap);
+    for (int t = 0; t < n_sap; t++) {
+        std::map<int, int> powers;
+        for (int c = term_ptr[t]; c < term_ptr[t + 1]; c++) powers[offset[coords[2 * c]] + coords[2 * c + 1]]++;
+        for (auto & kv : powers) saps[t].push_back({kv.first, kv.second});
+    }
+    std::vector<tchem_invdisp_t> v(terms, terms + n_terms);
+    const std::string s = jit_chain_source(v, n_ic, cartdim, saps, std::max(n_ic, 1 + cartdim), 1, 3, true, true);
     if (buf && capacity > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
         std::memcpy(buf, s.data(), n);
