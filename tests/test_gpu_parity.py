@@ -600,6 +600,27 @@ def test_transform_edge_batches(T):
     assert s.Hessian_int2cart(r[:0], gq[:0], Hq[:0]).shape == (0, cd, cd)
 
 
+def test_transforms_repeatable_bit_for_bit(T):
+    """Five runs of every transform on the same 3 000 geometries (20 rounds of the persistent grids, mbarrier phases flipping,
+    geometries handed out dynamically) must give the same bytes: fixed summation orders, no atomics on data, and any race on
+    the double-buffered shared-memory regions would show up here as a difference."""
+    w = T.workloads.get("C4")
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=w.natoms)
+    n, cd = s.intdim, s.cartdim
+    gen = torch.Generator(device="cuda").manual_seed(23)
+    r = dev(w.geometries(3000, seed=9))
+    gq = torch.randn(3000, n, dtype=torch.float64, device="cuda", generator=gen)
+    Hq = torch.randn(3000, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    gr = s.gradient_int2cart(r, gq)
+    Hr = s.Hessian_int2cart(r, gq, Hq)
+    first = [s.gradient_cart2int(r, gr), s.gradient_cart2int_matrix(r), Hr, s.Hessian_cart2int(r, gr, Hr)]
+    assert all(bool(torch.isfinite(x).all()) for x in first)
+    for _ in range(4):
+        again = [s.gradient_cart2int(r, gr), s.gradient_cart2int_matrix(r), s.Hessian_int2cart(r, gq, Hq), s.Hessian_cart2int(r, gr, Hr)]
+        for name, a, b in zip(("gradient_cart2int", "gradient_cart2int_matrix", "Hessian_int2cart", "Hessian_cart2int"), again, first):
+            assert torch.equal(a, b), name + ": two runs on the same inputs differ"
+
+
 def test_cart2int_on_two_streams_of_one_table(T):
     """The factor kernel hands its geometries out through a counter: the counter belongs to the launch, so two streams working
     on the SAME IntCoordSet at once must each get exactly their own geometries (bit-identical to the serial calls)."""
