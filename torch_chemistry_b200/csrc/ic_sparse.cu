@@ -739,10 +739,13 @@ __device__ __forceinline__ void block_store_rows(const double * s, double * __re
             __stcs(reinterpret_cast<double2 *>(g + i), *reinterpret_cast<const double2 *>(s + i));
         return;
     }
+    // padded rows of even length: 16 bytes per lane (two thirds of the store instructions of the 8-byte loop for 84 columns)
+    const bool vec = ((cols | ld) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
     for (int r = warp; r < rows; r += nwarps) {
         const double * src = s + r * ld;
         double * dst = g + (int64_t)r * cols;
-        for (int c = lane; c < cols; c += kLanes) __stcs(dst + c, src[c]);
+        if (vec) for (int c = 2 * lane; c < cols; c += 2 * kLanes) __stcs(reinterpret_cast<double2 *>(dst + c), *reinterpret_cast<const double2 *>(src + c));
+        else     for (int c = lane; c < cols; c += kLanes) __stcs(dst + c, src[c]);
     }
 }
 
