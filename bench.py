@@ -13,6 +13,7 @@ remaining BASELINE config, measured the same way in the same run:
     C4Hc Hessian cart->int, 10^5           C5   r->q->SAPSet value+Jacobian, 1.25*10^7 per GPU (10^8 over 8)
     C5K  SAPSet second-order Jacobian, 1.25*10^7
     C5r  r->q->SAPSet value + CARTESIAN Jacobian (dSAP/dq) J, 1.25*10^7
+    C5r2 the same plus the Cartesian second derivatives J^T (d2SAP/dq2) J + sum_k (dSAP/dq_k) K[k], 2*10^5 (composed path)
 With N > 1 every rank owns its own shard of every workload (weak scaling, no collective in the data path) and
 the extras default to C5 (BASELINE config 5) and C4H. One JSON line is printed by rank 0; DESIGN.md section 5.
 """
@@ -45,14 +46,15 @@ WORKLOADS = {
     "C4Hc": ("Hessian_cart2int", lambda cd, n, ns: 8 * (cd + cd + cd * cd + n * n)),
     "C5": ("q->SAPSet value+Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * n)),
     "C5r": ("q->SAPSet value+Cartesian Jacobian", lambda cd, n, ns: 8 * (cd + ns + ns * cd)),
+    "C5r2": ("q->SAPSet value+Cartesian Jacobian+Cartesian second derivatives", lambda cd, n, ns: 8 * (cd + ns + ns * cd + ns * cd * cd)),
     "C5x": ("SAPSet value+Jacobian on given coordinates", lambda cd, n, ns: 8 * (n + ns + ns * n)),
     "C5K": ("SAPSet Jacobian2nd on given coordinates", lambda cd, n, ns: 8 * (n + ns * n * n)),
 }
-WL_KEY = {"C3K": "C3", "C5x": "C5", "C5K": "C5", "C5r": "C5", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}
+WL_KEY = {"C3K": "C3", "C5x": "C5", "C5K": "C5", "C5r": "C5", "C5r2": "C5", "C4J": "C4", "C4g": "C4", "C4gc": "C4", "C4H": "C4", "C4Hc": "C4"}
 DEFAULT_BATCH = {"C1": 10 ** 4, "C2": 10 ** 6, "C3": 10 ** 5, "C3K": 10 ** 5, "C4J": 10 ** 5, "C4g": 10 ** 5, "C4gc": 10 ** 5,
-                 "C4H": 10 ** 5, "C4Hc": 10 ** 5, "C5": 12500000, "C5x": 12500000, "C5K": 12500000, "C5r": 12500000}
+                 "C4H": 10 ** 5, "C4Hc": 10 ** 5, "C5": 12500000, "C5x": 12500000, "C5K": 12500000, "C5r": 12500000, "C5r2": 200000}
 K_CHUNK = 8192          # q+J+K: 1.55 MB of K per 20-atom geometry -> the batch is walked in chunks
-EXTRAS_1GPU = ["C1", "C3", "C3K", "C4g", "C4gc", "C4H", "C4Hc", "C5", "C5K", "C5r"]
+EXTRAS_1GPU = ["C1", "C3", "C3K", "C4g", "C4gc", "C4H", "C4Hc", "C5", "C5K", "C5r", "C5r2"]
 EXTRAS_NGPU = ["C5", "C4H"]
 # Dense-equivalent flops per geometry of the contraction-bound transforms: what the reference's algorithm costs
 # with dense operands, counted once, LAPACK conventions (potrf n^3/3 + potri 2n^3/3 = n^3).
@@ -226,6 +228,12 @@ def _cpu_worker(job):
         s.Hessian_int2cart(r, np.ones((r.shape[0], s.intdim)), np.tile(np.eye(s.intdim), (r.shape[0], 1, 1)))
     elif what == "Hessian_cart2int":
         s.Hessian_cart2int(r, np.ones((r.shape[0], r.shape[1])), np.tile(np.eye(r.shape[1]), (r.shape[0], 1, 1)))
+    elif "second derivatives" in what:
+        q, J, K = s.qJK(r)                     # the same composition, second order
+        sap.value(q)
+        g = sap.jacobian(q)
+        np.einsum("btk,bkc->btc", g, J)
+        np.einsum("bka,btkl,blc->btac", J, sap.jacobian2nd(q), J) + np.einsum("btk,bkac->btac", g, K)
     elif "Cartesian" in what:
         q, J = s.qJ(r)                         # what callers of the reference do by hand (test/normal_mode/main.cpp:56-61)
         sap.value(q)
@@ -284,7 +292,7 @@ def per_core_sample(key, headline):
     # headline: roughly 10-20 s of CPU work per process at the reference's measured per-geometry cost;
     # extras: a few seconds each, so that the default run stays within minutes
     full = {"C1": 20000, "C2": 4000, "C3": 1500, "C3K": 24, "C4J": 1000, "C4g": 1000, "C4gc": 1000, "C4H": 16, "C4Hc": 16,
-            "C5": 20000, "C5x": 20000, "C5K": 20000, "C5r": 20000}[key]
+            "C5": 20000, "C5x": 20000, "C5K": 20000, "C5r": 20000, "C5r2": 2000}[key]
     return full if headline else max(4, full // 4)
 
 
@@ -431,6 +439,8 @@ class Bench:
                                                                       C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
         elif key == "C5r":
             step = lambda: sap.chained_cart(ic, r_dev)
+        elif key == "C5r2":
+            step = lambda: sap.chained_cart(ic, r_dev, second_order=True)
         elif key == "C5x":
             x_dev = ic(r_dev).contiguous()                      # the coordinates a caller would bring
             souts = sap.eval_cat(x_dev)
@@ -475,7 +485,7 @@ class Bench:
 
         # ---- e2e: host buffers through the public API, copies inside the timed region --------------
         e2e = None
-        if not args.no_e2e and key not in ("C5x", "C5K", "C5r"):
+        if not args.no_e2e and key not in ("C5x", "C5K", "C5r", "C5r2"):
             pin = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
             Be = B
             if sap is not None:
