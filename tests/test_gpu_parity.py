@@ -396,6 +396,26 @@ def test_chained_cartesian_derivatives(T):
     q, J = oic2.qJ(r2[::1000])
     assert_parity(host(g3)[::1000], np.einsum("btk,bkc->btc", osap2.jacobian(q), J), "C2 chained Cartesian: dy/dr")
     assert_parity(host(y3)[::1000], osap2.value(q), "C2 chained Cartesian: values")
+    # second order for C2H4 (J and K of a geometry staged in shared memory: chain_cart_second_block_kernel) ...
+    before = T.kernel_log().get("chain_cart_second_block_kernel", 0)
+    y4, g4, h4 = sap2.chained_cart(ic2, dev(r2[:41]), second_order=True)
+    assert T.kernel_log().get("chain_cart_second_block_kernel", 0) == before + 1
+    q, J, K = oic2.qJK(r2[:41])
+    gq, Hq = osap2.jacobian(q), osap2.jacobian2nd(q)
+    assert_parity(host(h4), np.einsum("bka,btkl,blc->btac", J, Hq, J) + np.einsum("btk,bkac->btac", gq, K), "C2 chained Cartesian: d2y/dr2")
+    # ... and for the 20-atom chain, whose K (1.5 MB per geometry) does not fit: the element-per-thread kernel
+    w3 = T.workloads.get("C3")
+    ic3, oic3 = T.IntCoordSet.from_text("default", w3.ic_text, n_atoms=w3.natoms), O.IntCoordSet("default", w3.ic_text)
+    text3 = "1,1\n1,2    1,1\n1,54    1,30\n1,7    1,7    1,20\n"
+    sap3, osap3 = T.SAPSet.from_text(text3, 0, [ic3.intdim]), O.SAPSet(text3, 0, [ic3.intdim])
+    r3 = w3.geometries(3, seed=8)
+    before = T.kernel_log().get("chain_cart_second_kernel", 0)
+    y5, g5, h5 = sap3.chained_cart(ic3, dev(r3), second_order=True)
+    assert T.kernel_log().get("chain_cart_second_kernel", 0) == before + 1
+    q, J, K = oic3.qJK(r3)
+    gq, Hq = osap3.jacobian(q), osap3.jacobian2nd(q)
+    assert_parity(host(g5), np.einsum("btk,bkc->btc", gq, J), "C3 chained Cartesian: dy/dr (composed)")
+    assert_parity(host(h5), np.einsum("bka,btkl,blc->btac", J, Hq, J) + np.einsum("btk,bkac->btac", gq, K), "C3 chained Cartesian: d2y/dr2")
 
 
 def test_chained_cartesian_kernel_variants(T):

@@ -60,6 +60,55 @@ chain_cart_second_kernel(const double * __restrict__ g, const double * __restric
     }
 }
 
+// The same contraction with the geometry's J and K staged in shared memory: one block per geometry at a time, its warps
+// take the monomials in turn - V = H_t J first (lanes over the n x cd elements), then the cartdim^2 outputs of the term
+// (lanes over (a, c): consecutive lanes write consecutive doubles, K[k][a][c] and the output are read / written contiguously).
+// Per element the same fma order as the kernel above (bit-identical), which serves the molecules whose K does not fit.
+// The element-per-thread version re-read H, J and K from global memory for every output: 95 % of the composed path's time.
+constexpr int kCart2Warps = 4;
+__host__ __device__ inline size_t cart2_smem_doubles(int n, int cd, int nt) {
+    return (size_t)n * cd + (size_t)n * cd * cd + (size_t)nt * ((size_t)n + (size_t)n * n) + (size_t)kCart2Warps * (size_t)n * cd;
+}
+__global__ void __launch_bounds__(32 * kCart2Warps)
+chain_cart_second_block_kernel(const double * __restrict__ g, const double * __restrict__ H, const double * __restrict__ J,
+                               const double * __restrict__ K, int64_t B, int nt, int n, int cd, double * __restrict__ out) {
+    extern __shared__ __align__(16) double sm2[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncd = n * cd, nk = n * cd * cd, ncc = cd * cd, nn = n * n;
+    // one coalesced load phase per geometry (J, K and every monomial's gradient and Hessian): loads from global memory inside
+    // the per-term loops cost one L2 latency per loop trip; several resident blocks per SM overlap this phase with the others' arithmetic
+    double * Js = sm2, * Ks = Js + ncd, * Gs = Ks + nk, * Hs = Gs + (size_t)nt * n, * Vs = Hs + (size_t)nt * nn + (size_t)warp * ncd;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();                                           // the previous geometry's operands are no longer read
+        for (int i = threadIdx.x; i < ncd; i += blockDim.x) Js[i] = J[b * ncd + i];
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) Ks[i] = K[b * (int64_t)nk + i];
+        for (int i = threadIdx.x; i < nt * n; i += blockDim.x) Gs[i] = g[b * nt * n + i];
+        for (int i = threadIdx.x; i < nt * nn; i += blockDim.x) Hs[i] = H[b * (int64_t)nt * nn + i];
+        __syncthreads();
+        for (int t = warp; t < nt; t += kCart2Warps) {
+            const double * gs = Gs + t * n, * Hp = Hs + t * nn;
+            for (int e = lane; e < ncd; e += 32) {
+                const int k = e / cd, c = e - k * cd;
+                double u = 0.0;                                    // (H J)[k][c]
+                for (int l = 0; l < n; l++) u = fma(Hp[k * n + l], Js[l * cd + c], u);
+                Vs[e] = u;
+            }
+            __syncwarp();
+            double * op = out + (b * nt + t) * (int64_t)ncc;
+            for (int e = lane; e < ncc; e += 32) {
+                const int a = e / cd, c = e - a * cd;
+                double s = 0.0;
+                for (int k = 0; k < n; k++) {
+                    s = fma(Js[k * cd + a], Vs[k * cd + c], s);
+                    s = fma(gs[k], Ks[(k * cd + a) * cd + c], s);
+                }
+                __stcs(op + e, s);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 } // namespace
 } // namespace tchem_b200
 
@@ -115,10 +164,24 @@ extern "C" int tchem_ic_sap_eval_cart(const tchem_ic_table * ic, const tchem_sap
         if (rc == TCHEM_OK && second) {
             rc = tchem_sap_jacobian2nd(sap, q_ws, nb, H_ws, stream_);
             if (rc == TCHEM_OK) {
-                const int64_t total = nb * nt * cd * cd;
-                const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ic->sm_count * 8);
-                chain_cart_second_kernel<<<grid, 256, 0, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd, d2ydr2 + b0 * (int64_t)nt * cd * cd);
-                count_launch("chain_cart_second_kernel");
+                const size_t smem2 = cart2_smem_doubles(n, cd, nt) * sizeof(double);
+                if (smem2 + 1024 <= (size_t)ic->max_smem_optin) {
+                    const void * fn = reinterpret_cast<const void *>(&chain_cart_second_block_kernel);
+                    rc = ensure_max_dynamic_smem(fn, ic->device, ic->max_smem_optin);
+                    if (rc == TCHEM_OK) {
+                        // small molecules: several blocks per SM (their shared memory allows it), one geometry per block at a time
+                        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)ic->max_smem_optin / (smem2 + 1024)));
+                        const unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)ic->sm_count * per_sm);
+                        chain_cart_second_block_kernel<<<grid, 32 * kCart2Warps, smem2, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd,
+                                                                                              d2ydr2 + b0 * (int64_t)nt * cd * cd);
+                        count_launch("chain_cart_second_block_kernel");
+                    }
+                } else {
+                    const int64_t total = nb * nt * cd * cd;
+                    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ic->sm_count * 8);
+                    chain_cart_second_kernel<<<grid, 256, 0, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd, d2ydr2 + b0 * (int64_t)nt * cd * cd);
+                    count_launch("chain_cart_second_kernel");
+                }
             }
         }
         if (rc == TCHEM_OK && cudaGetLastError() != cudaSuccess) rc = set_error(TCHEM_ECUDA, "tchem_ic_sap_eval_cart: kernel launch failed");
