@@ -403,6 +403,19 @@ def test_chained_cartesian_derivatives(T):
     q, J, K = oic2.qJK(r2[:41])
     gq, Hq = osap2.jacobian(q), osap2.jacobian2nd(q)
     assert_parity(host(h4), np.einsum("bka,btkl,blc->btac", J, Hq, J) + np.einsum("btk,bkac->btac", gq, K), "C2 chained Cartesian: d2y/dr2")
+    # four atoms (6 coordinates): the size-specialised contraction, as for the three atoms of C5 above
+    w4 = T.workloads.chain(4, "chain4")
+    ic4, oic4 = T.IntCoordSet.from_text("default", w4.ic_text, n_atoms=4), O.IntCoordSet("default", w4.ic_text)
+    text4 = "1,1\n1,6    1,1\n1,4    1,5    1,6\n1,2    1,2\n1,3    1,6    1,6\n"
+    sap4, osap4 = T.SAPSet.from_text(text4, 0, [6]), O.SAPSet(text4, 0, [6])
+    r4 = w4.geometries(53, seed=12)
+    before = T.kernel_log().get("chain_cart_second_small_kernel", 0)
+    y6, g6, h6 = sap4.chained_cart(ic4, dev(r4), second_order=True)
+    assert T.kernel_log().get("chain_cart_second_small_kernel", 0) == before + 1
+    q, J, K = oic4.qJK(r4)
+    gq, Hq = osap4.jacobian(q), osap4.jacobian2nd(q)
+    assert_parity(host(g6), np.einsum("btk,bkc->btc", gq, J), "4-atom chain chained Cartesian: dy/dr (composed)")
+    assert_parity(host(h6), np.einsum("bka,btkl,blc->btac", J, Hq, J) + np.einsum("btk,bkac->btac", gq, K), "4-atom chain chained Cartesian: d2y/dr2")
     # ... and for the 20-atom chain, whose K (1.5 MB per geometry) does not fit: the element-per-thread kernel
     w3 = T.workloads.get("C3")
     ic3, oic3 = T.IntCoordSet.from_text("default", w3.ic_text, n_atoms=w3.natoms), O.IntCoordSet("default", w3.ic_text)

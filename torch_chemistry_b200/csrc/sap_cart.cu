@@ -109,6 +109,65 @@ chain_cart_second_block_kernel(const double * __restrict__ g, const double * __r
     }
 }
 
+// The same kernel for small molecules with the sizes as template parameters (N internal coordinates, IT = ceil(cartdim^2 / 32)
+// outputs per lane): the lane's (a, c) pairs, J[k][a] and K[k][a][c] do not depend on the monomial and live in registers across the
+// whole term loop, the k loops are unrolled. The generic version spends 66 instructions per output on 6 useful FMAs (index
+// division, runtime loop bounds, three shared-memory loads per FMA pair) and is issue bound.
+template <int N, int IT>
+__global__ void __launch_bounds__(32 * kCart2Warps)
+chain_cart_second_small_kernel(const double * __restrict__ g, const double * __restrict__ H, const double * __restrict__ J,
+                               const double * __restrict__ K, int64_t B, int nt, int cd, double * __restrict__ out) {
+    extern __shared__ __align__(16) double sm2[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncd = N * cd, nk = N * cd * cd, ncc = cd * cd;
+    double * Js = sm2, * Ks = Js + ncd, * Gs = Ks + nk, * Hs = Gs + (size_t)nt * N, * Vs = Hs + (size_t)nt * N * N + (size_t)warp * ncd;
+    int ea[IT], ec[IT];
+#pragma unroll
+    for (int i = 0; i < IT; i++) {
+        const int e = min(lane + 32 * i, ncc - 1);
+        ea[i] = e / cd; ec[i] = e - ea[i] * cd;
+    }
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncd; i += blockDim.x) Js[i] = J[b * ncd + i];
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) Ks[i] = K[b * (int64_t)nk + i];
+        for (int i = threadIdx.x; i < nt * N; i += blockDim.x) Gs[i] = g[b * nt * N + i];
+        for (int i = threadIdx.x; i < nt * N * N; i += blockDim.x) Hs[i] = H[b * (int64_t)nt * N * N + i];
+        __syncthreads();
+        double Jr[IT][N], Kr[IT][N];
+#pragma unroll
+        for (int i = 0; i < IT; i++)
+#pragma unroll
+            for (int k = 0; k < N; k++) { Jr[i][k] = Js[k * cd + ea[i]]; Kr[i][k] = Ks[(k * cd + ea[i]) * cd + ec[i]]; }
+        for (int t = warp; t < nt; t += kCart2Warps) {
+            const double * gs = Gs + t * N, * Hp = Hs + t * N * N;
+            for (int e = lane; e < ncd; e += 32) {
+                const int k = e / cd, c = e - k * cd;
+                double u = 0.0;                                    // (H J)[k][c]
+#pragma unroll
+                for (int l = 0; l < N; l++) u = fma(Hp[k * N + l], Js[l * cd + c], u);
+                Vs[e] = u;
+            }
+            double gr[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) gr[k] = gs[k];
+            __syncwarp();
+            double * op = out + (b * nt + t) * (int64_t)ncc;
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    s = fma(Jr[i][k], Vs[k * cd + ec[i]], s);
+                    s = fma(gr[k], Kr[i][k], s);
+                }
+                if (lane + 32 * i < ncc) __stcs(op + lane + 32 * i, s);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 } // namespace
 } // namespace tchem_b200
 
@@ -172,9 +231,21 @@ extern "C" int tchem_ic_sap_eval_cart(const tchem_ic_table * ic, const tchem_sap
                         // small molecules: several blocks per SM (their shared memory allows it), one geometry per block at a time
                         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)ic->max_smem_optin / (smem2 + 1024)));
                         const unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)ic->sm_count * per_sm);
-                        chain_cart_second_block_kernel<<<grid, 32 * kCart2Warps, smem2, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd,
-                                                                                              d2ydr2 + b0 * (int64_t)nt * cd * cd);
-                        count_launch("chain_cart_second_block_kernel");
+                        double * o2 = d2ydr2 + b0 * (int64_t)nt * cd * cd;
+                        if (n == 3 && cd * cd <= 96) {             // three atoms (H2O: the BASELINE SAPSet workload)
+                            rc = ensure_max_dynamic_smem(reinterpret_cast<const void *>(&chain_cart_second_small_kernel<3, 3>), ic->device, ic->max_smem_optin);
+                            if (rc != TCHEM_OK) break;
+                            chain_cart_second_small_kernel<3, 3><<<grid, 32 * kCart2Warps, smem2, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, cd, o2);
+                            count_launch("chain_cart_second_small_kernel");
+                        } else if (n == 6 && cd * cd <= 160) {     // four atoms
+                            rc = ensure_max_dynamic_smem(reinterpret_cast<const void *>(&chain_cart_second_small_kernel<6, 5>), ic->device, ic->max_smem_optin);
+                            if (rc != TCHEM_OK) break;
+                            chain_cart_second_small_kernel<6, 5><<<grid, 32 * kCart2Warps, smem2, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, cd, o2);
+                            count_launch("chain_cart_second_small_kernel");
+                        } else {
+                            chain_cart_second_block_kernel<<<grid, 32 * kCart2Warps, smem2, stream>>>(g_ws, H_ws, J_ws, K_ws, nb, nt, n, cd, o2);
+                            count_launch("chain_cart_second_block_kernel");
+                        }
                     }
                 } else {
                     const int64_t total = nb * nt * cd * cd;
