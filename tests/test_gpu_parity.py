@@ -751,6 +751,42 @@ def test_dense_transforms_43_atoms_odd_cartdim(T):
     assert_parity(host(s.gradient_cart2int_matrix(dev(r))), orc.gradient_cart2int_matrix(r), "chain43 cart2int matrix vs oracle", tol=1e-11)
 
 
+def test_sparse_transforms_odd_dimensions_chain13(T):
+    """13 atoms: 33 internal and 39 Cartesian coordinates, both odd - the block kernel's matrices cannot travel as 16-byte
+    bulk copies (H_q and H_r fall back to per-thread cp.async; the inverse still comes as one bulk copy from a workspace
+    slice padded to an even length) and the packed / padded layouts hit their odd branches. A batch larger than the grid,
+    physical inputs (cart -> int applied to int -> cart results), against the oracle; bit-identical to single geometries."""
+    rng = np.random.default_rng(17)
+    natoms = 13
+    w = T.workloads.chain(natoms, "chain13", seed=21)
+    s = T.IntCoordSet.from_text("default", w.ic_text, n_atoms=natoms)
+    orc = O.IntCoordSet("default", w.ic_text)
+    assert s.intdim == 33 and s.cartdim == 39
+    B = 301
+    r = w.geometries(B, seed=6)
+    gq = rng.standard_normal((B, s.intdim))
+    Hq = rng.standard_normal((B, s.intdim, s.intdim))
+    Hq = Hq + Hq.transpose(0, 2, 1)
+    before = T.kernel_log().get("hess_kernel<3:Hessian_cart2int>", 0)
+    gr = s.gradient_int2cart(dev(r), dev(gq))
+    Hr = s.Hessian_int2cart(dev(r), dev(gq), dev(Hq))
+    gq2 = s.gradient_cart2int(dev(r), gr)
+    M = s.gradient_cart2int_matrix(dev(r))
+    Hq2 = s.Hessian_cart2int(dev(r), gr, Hr)
+    assert T.kernel_log().get("hess_kernel<3:Hessian_cart2int>", 0) == before + 1
+    idx = np.array([0, 1, 147, 148, 149, 300])
+    assert_parity(host(Hr)[idx], orc.Hessian_int2cart(r[idx], gq[idx], Hq[idx]), "chain13 Hessian_int2cart vs oracle")
+    assert_parity(host(gq2)[idx], orc.gradient_cart2int(r[idx], host(gr)[idx]), "chain13 gradient_cart2int vs oracle", tol=1e-11)
+    assert_parity(host(M)[idx], orc.gradient_cart2int_matrix(r[idx]), "chain13 cart2int matrix vs oracle", tol=1e-11)
+    assert_parity(host(Hq2)[idx], orc.Hessian_cart2int(r[idx], host(gr)[idx], host(Hr)[idx]), "chain13 Hessian_cart2int vs oracle", tol=1e-11)
+    # the round trip closes (gradient and Hessian in internal coordinates are recovered)
+    assert float((gq2 - dev(gq)).abs().max()) < 1e-9 and float((Hq2 - dev(Hq)).abs().max()) < 1e-8
+    for i in (0, 300):
+        ri = dev(r[i])
+        assert torch.equal(s.Hessian_cart2int(ri, gr[i], Hr[i]), Hq2[i])
+        assert torch.equal(s.Hessian_int2cart(ri, dev(gq[i]), dev(Hq[i])), Hr[i])
+
+
 def test_alternating_tables_of_different_size(T):
     """The dynamic shared-memory limit is an attribute of the kernel FUNCTION, which all tables share: a small
     table's first use must not lower it under a larger table's cached launch shape (every kernel family)."""
