@@ -776,9 +776,9 @@ def test_sparse_transforms_odd_dimensions_chain13(T):
     assert T.kernel_log().get("hess_kernel<3:Hessian_cart2int>", 0) == before + 1
     idx = np.array([0, 1, 147, 148, 149, 300])
     assert_parity(host(Hr)[idx], orc.Hessian_int2cart(r[idx], gq[idx], Hq[idx]), "chain13 Hessian_int2cart vs oracle")
-    assert_parity(host(gq2)[idx], orc.gradient_cart2int(r[idx], host(gr)[idx]), "chain13 gradient_cart2int vs oracle", tol=1e-11)
-    assert_parity(host(M)[idx], orc.gradient_cart2int_matrix(r[idx]), "chain13 cart2int matrix vs oracle", tol=1e-11)
-    assert_parity(host(Hq2)[idx], orc.Hessian_cart2int(r[idx], host(gr)[idx], host(Hr)[idx]), "chain13 Hessian_cart2int vs oracle", tol=1e-11)
+    assert_parity(host(gq2)[idx], orc.gradient_cart2int(r[idx], host(gr)[idx]), "chain13 gradient_cart2int vs oracle")
+    assert_parity(host(M)[idx], orc.gradient_cart2int_matrix(r[idx]), "chain13 cart2int matrix vs oracle")
+    assert_parity(host(Hq2)[idx], orc.Hessian_cart2int(r[idx], host(gr)[idx], host(Hr)[idx]), "chain13 Hessian_cart2int vs oracle")
     # the round trip closes (gradient and Hessian in internal coordinates are recovered)
     assert float((gq2 - dev(gq)).abs().max()) < 1e-9 and float((Hq2 - dev(Hq)).abs().max()) < 1e-8
     for i in (0, 300):
