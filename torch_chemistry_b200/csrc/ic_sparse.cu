@@ -132,12 +132,22 @@ struct JvSink {                        // Jv[pos[atom slot] + component] += coef
 struct SlotSink {                      // S[9 kblock(i, j) + 3 k + l] = w * d2 q / d r_(i,k) d r_(j,l),  i <= j
     double * S;
     double w;
+    bool ends_free;                    // plain torsion: only the passes of atoms 1 and 2 run (see get_sparse), so block (j, 3) comes
+                                       // from the pass of atom j as the transpose of what this pass emits for atom 3
     __device__ __forceinline__ void value(double) const {}
     __device__ __forceinline__ void jac_block(const int *, int, const V3<double> &) const {}
     __device__ __forceinline__ void jac_entry(const int *, int, double) const {}
     template <int N> __device__ __forceinline__ void hess_block(const int *, int dir, int i, const V3<Dual> & J) const {
         const int j = dir / 3, l = dir - 3 * j;
-        if (i > j) return;
+        if (i > j) {
+            if (N == 4 && ends_free && i == 3) {
+                double * p = S + 9 * kblock(j, i, N) + 3 * l;
+                p[0] = w * J.x.d;
+                p[1] = w * J.y.d;
+                p[2] = w * J.z.d;
+            }
+            return;
+        }
         double * p = S + 9 * kblock(i, j, N) + l;
         p[0] = w * J.x.d;
         p[3] = w * J.y.d;
@@ -907,6 +917,7 @@ __device__ __forceinline__ void run_tasks(const SparseProgram & sp, const double
             SlotSink sink;
             sink.S = slots + term.kslot;
             sink.w = sign * weight[term.pd.out] * term.coef;
+            sink.ends_free = term.pd.type == TCHEM_TORSION;
             eval_primitive<MODE_KDIR, HAS5>(term.pd, GeomLoader{rg}, sink, dir, dir + 1);
         } else if (rg_next != nullptr) {
             const int row = (int)(task & 0x7fffffffu);
@@ -1306,7 +1317,11 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             // Translational invariance: the second-derivative blocks of a row of atoms sum to zero, K(i, 0) = - sum_{j >= 1} K(i, j).
             // The direction passes of atom 0 only produce block (0, 0), so they are not run at all for the 2 - 4 atom types
             // (torsion 9 passes instead of 12, bend 6 of 9, stretch 3 of 6): the gather below builds (0, 0) from the others.
-            for (int dir = (d.natoms >= 2 && d.natoms <= 4) ? 3 : 0; dir < 3 * d.natoms; dir++)
+            // Plain torsion: the gradient block of an end atom does not depend on the other end (J_0 is a function of atoms 0, 1, 2
+            // only), so K(0, 3) = 0 exactly and K(3, 3) = - K(3, 1) - K(3, 2): the passes of atom 3 are not needed either - 6 of 12.
+            // (Not the sine / cosine variants: their J_0 carries a factor cos / sin of the angle, which depends on atom 3.)
+            const bool tors0 = d.type == TCHEM_TORSION && d.natoms == 4;
+            for (int dir = (d.natoms >= 2 && d.natoms <= 4) ? 3 : 0; dir < (tors0 ? 9 : 3 * d.natoms); dir++)
                 ktasks.push_back(((uint32_t)terms.size() << 8) | (uint32_t)dir);
             terms.push_back(st);
         }
@@ -1462,9 +1477,17 @@ int get_sparse(const tchem_ic_table * t, SparseTable & out) {
             for (int j = i; j < N; j++) {
                 const uint32_t base = (uint32_t)(st.kslot + 9 * (i * N - (i * (i - 1)) / 2 + (j - i)));
                 const int A = st.pd.atoms[i], Bt = st.pd.atoms[j];
+                const bool tors0 = st.pd.type == TCHEM_TORSION && N == 4;
                 if (i == 0 && j == 0 && N >= 2 && N <= 4) {
                     // block (0, 0) = - sum_{j >= 1} K(0, j): negated sources, no slot of its own is ever written
-                    for (int jj = 1; jj < N; jj++) gk[{A, A}].push_back(((uint32_t)(st.kslot + 9 * jj) << 2) | 2u);
+                    for (int jj = 1; jj < (tors0 ? 3 : N); jj++) gk[{A, A}].push_back(((uint32_t)(st.kslot + 9 * jj) << 2) | 2u);
+                    continue;
+                }
+                if (tors0 && i == 0 && j == 3) continue;                       // K(0, 3) = 0
+                if (tors0 && i == 3 && j == 3) {
+                    // K(3, 3) = - K(3, 1) - K(3, 2) = - K(1, 3)^T - K(2, 3)^T: negated and transposed sources
+                    for (int ii = 1; ii < 3; ii++)
+                        gk[{A, A}].push_back(((uint32_t)(st.kslot + 9 * (ii * N - (ii * (ii - 1)) / 2 + (3 - ii))) << 2) | 3u);
                     continue;
                 }
                 gk[{A, Bt}].push_back(base << 2);
