@@ -15,12 +15,13 @@
 // Two kernels:
 //  * factor_kernel - ONE WARP PER GEOMETRY, six resident per SM, no block barrier anywhere. J J^T is assembled
 //    from the compressed rows into ROW-MAJOR PACKED lower storage (28 KB for 84 coordinates), factored in place
-//    (right-looking Cholesky, panels of 8 columns held in registers, pivots exchanged by shuffles), with the
+//    (right-looking Cholesky, panels of 8 columns held in registers, the diagonal block replicated in every lane), with the
 //    right-hand side J g_r riding along as a bordered row (= the forward substitution), then back substitution.
 //    For the matrix / Hessian entry points the same warp continues with the reference's potri (explicit inverse of
 //    the factor, row-oriented; then W^T W), still in place, and writes the inverse - expanded to the full symmetric
 //    matrix - and g_q to a workspace.
-//    The serial pivot chain of one geometry overlaps with the other warps' geometries instead of idling a block.
+//    The serial pivot chain of one geometry overlaps with the other warps' geometries instead of idling a block;
+//    geometries are handed out through a per-launch counter (the warps do not run at the same speed).
 //  * hess_kernel - one block per geometry: compressed-column products U = J^T H_q, X = U J (int -> cart), or
 //    M^T = J^T (J J^T)^-1 by the same sparse product followed by the two dense DMMA products T2 = H_c M^T,
 //    H_q = M T2 (cart -> int; the reference's order of operations - see the kernel). The second-derivative term
