@@ -1703,7 +1703,11 @@ int launch_sparse(int op, const tchem_ic_table * t, const double * r, const doub
     if (op == 1) return launch_factor(0, r, in1, B, out, nullptr);
     if (op == 2) return launch_hess(2, r, in1, in2, nullptr, B, out);
     // matrix / Hessian cart -> int: the inverses (and g_q) of a slice of the batch go through a stream-ordered workspace
-    const int64_t slice = std::min<int64_t>(B, 16384);
+    // slices of at most 32 768 geometries, equal in size (100 000 -> 4 x 25 000: no short last slice whose factor kernel would run two
+    // nearly empty rounds; every slice boundary costs the factor kernel about one geometry time of tail)
+    static const int64_t max_slice = [] { const char * e = getenv("TCHEM_CART2INT_SLICE"); return (int64_t)std::max(1, e ? atoi(e) : 32768); }();
+    const int64_t nslices = (B + max_slice - 1) / max_slice;
+    const int64_t slice = (B + nslices - 1) / nslices;
     double * ws = nullptr;
     const size_t astride = (size_t)even_up(n * n);              // full symmetric inverse per geometry (+ g_q)
     const size_t ws_doubles = (size_t)slice * (astride + n);
